@@ -1,0 +1,93 @@
+/*
+ * fq_device.h — the operations the host engine (fq_engine.cpp) needs from the GPU.
+ *
+ * The product implementation is FqCudaDevice (fq_cuda.cu): hand-written sm_100a kernels on one CUDA stream.
+ * tests/sim/ holds a sequential stand-in with the same interface so that the host logic (chunking, bridging,
+ * event ordering, report) can be exercised on a machine without a GPU; it is never linked into libfastq_gpu.
+ */
+#ifndef FQ_DEVICE_H
+#define FQ_DEVICE_H
+#include <stddef.h>
+#include <stdint.h>
+#include "fq_types.h"
+
+/* where to find the bytes of a name given the index of its record inside a file: one entry per segment */
+typedef struct {
+  unsigned long long g0;     /* index of the segment's first record */
+  const FqName* names;       /* descriptors of the segment's records */
+  const uint8_t* data;       /* chunk the descriptors point into */
+} FqDirEntry;
+
+typedef struct {
+  const uint8_t* data;       /* chunk bytes (allocation padded by ≥ 64 bytes) */
+  const uint32_t* line_end;  /* exclusive end offset of every gz-line of the chunk */
+  const FqLine* lines;       /* explicit lines, 4 per record (serially split records); NULL → derive from line_end */
+  uint32_t q, j0;            /* the segment's first line starts at byte q and ends at line_end[j0] */
+  uint32_t nrec;
+  uint64_t g0;               /* index of the first record inside its file */
+  uint64_t step_base;        /* steps preceding this file's loop (mate loop) */
+  FqRecCtx cx;
+  FqStats* stats;            /* counters to update (num_rds, n_names, mem_sum) */
+  FqStats* stats_range;      /* min/max read length and quality to update: the mate loop's are never reported (fastq_info.c:316-320 snapshots file 1's before it) */
+  unsigned long long* hist;  /* read-length histogram, FQ_MAX_READ_LENGTH bins */
+  unsigned long long* key;   /* global minimum event key */
+  FqName* names;             /* out: nrec descriptors (NULL when the loop has no name step) */
+} FqRecordsArgs;
+
+typedef struct {
+  const FqName* names; const uint8_t* data; uint32_t nrec; uint64_t g0; uint64_t step_base;
+  FqSlot* slots; uint64_t mask;            /* capacity-1 (power of two) */
+  const FqDirEntry* dir1; uint32_t ndir1;  /* file-1 directory: resolves a stored idx1 to name bytes */
+  unsigned long long* key;
+  unsigned long long* counters;            /* [0] hash collisions seen, [1] slots claimed by the mate loop, [2] table full */
+} FqTableArgs;
+
+typedef struct {
+  const FqName* a; const uint8_t* da; uint32_t stride_a;
+  const FqName* b; const uint8_t* db; uint32_t stride_b;
+  uint32_t npairs; uint64_t p0;            /* step of the first pair */
+  uint32_t rank;                           /* FQ_RI_UNPAIRED or FQ_RS_MISMATCH */
+  unsigned long long* key;
+} FqPairArgs;
+
+class FqDevice {
+ public:
+  virtual ~FqDevice() {}
+  virtual const char* name() const = 0;
+  /* memory: device allocations are zero-padded by the callee's caller; all copies are ordered on one stream */
+  virtual void* alloc(size_t n) = 0;
+  virtual void release(void* p) = 0;
+  virtual void upload(void* dst, const void* src, size_t n) = 0;
+  virtual void download(void* dst, const void* src, size_t n) = 0; /* synchronises */
+  virtual void copy(void* dst, const void* src, size_t n) = 0;
+  virtual void fill(void* dst, int byte, size_t n) = 0;
+  virtual void sync() = 0;
+  /* K1: exclusive end offsets of all lines of data[0,n) in order; a last line without LF counts when virtual_end.
+   * out[0] = number of lines, out[1] = 1 if more than cap were found (only the first cap are stored). */
+  virtual void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) = 0;
+  /* first line i in [j0, j0+nlines) whose raw length reaches the gzgets limit of its phase ((i-j0)&3); *out = min(*out, i) */
+  /* When tail_from_n != 0 the unterminated bytes after the last counted line (up to n) are judged as line j0+nlines. */
+  virtual void find_overlong(const uint32_t* line_end, uint32_t q, uint32_t j0, uint32_t nlines, uint32_t n, int tail_from_n, uint32_t* out) = 0;
+  /* gzgets emulation for one record starting at byte q: lines[4], out3 = {next byte, lines obtained (0..4), LFs consumed}.
+   * A line cut short by the end of the data only counts when is_eof. */
+  virtual void split_serial(const uint8_t* data, uint32_t n, uint32_t q, int is_eof, FqLine* lines4, uint32_t* out3) = 0;
+  /* format / colour-space sniff on (hdr1, seq) of a file's first record: out2 = {FQ_SNIFF_*, is_color} */
+  virtual void sniff(const uint8_t* data, FqLine hdr1, FqLine seq, int32_t* out2) = 0;
+  /* K2: reader flags + validation + statistics + event key + name descriptors */
+  virtual void records(const FqRecordsArgs& a) = 0;
+  /* K3: index insert (file 1) / K4: mate claim (file 2) / pair compare (interleaved, sorted) */
+  virtual void index_insert(const FqTableArgs& a) = 0;
+  virtual void mate_claim(const FqTableArgs& a) = 0;
+  virtual void pair_compare(const FqPairArgs& a) = 0;
+  /* details of one record for the error message */
+  virtual void explain(const uint8_t* data, const FqLine* lines4_host, const FqRecCtx& cx, FqRecOut* out_dev) = 0;
+  /* device-side stopwatch on the stream (CUDA events) */
+  virtual void timer_start() = 0;
+  virtual double timer_stop_ms() = 0;
+  /* how many kernels were launched so far (bench.py's gpu_launches) */
+  virtual unsigned long long launches() const = 0;
+};
+
+FqDevice* fq_make_cuda_device(int ordinal); /* fq_cuda.cu; throws std::runtime_error when no CUDA device */
+
+#endif

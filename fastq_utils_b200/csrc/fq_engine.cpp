@@ -1,0 +1,750 @@
+/*
+ * fq_engine.cpp — host orchestration of the fastq_info hot path on one GPU (see fq_engine.h).
+ *
+ * Reference control flow being replaced: src/fastq_info.c:57-176 (three loops), :273-362 (dispatch, index loop
+ * call, mate loop) and src/fastq.c:396-439 (index loop).  The reference walks records one by one and stops at the
+ * first failing check; here every record of a chunk is checked at once and each failure becomes an *event key*
+ * (step << 6 | rank) ordered exactly like the reference's sequential execution; the smallest key wins.
+ */
+#include "fq_engine.h"
+#include <algorithm>
+#include <cstring>
+
+static const uint32_t kPad = 64;                 /* readable bytes after every chunk */
+static const size_t kMaxChunk = 1ull << 31;      /* bytes per chunk: offsets are 32-bit */
+static const uint32_t kNone32 = 0xFFFFFFFFu;
+
+static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+static int fmt_of_sniff(int s) { return s == FQ_SNIFF_DEFAULT ? FQ_FMT_DEFAULT : s == FQ_SNIFF_CASAVA ? FQ_FMT_CASAVA : FQ_FMT_INT; }
+
+FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) {
+  key_ = (unsigned long long*)dev_->alloc(sizeof(unsigned long long));
+  counters_ = (unsigned long long*)dev_->alloc(4 * sizeof(unsigned long long));
+  scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
+  recout_ = (FqRecOut*)dev_->alloc(sizeof(FqRecOut));
+  for (int f = 0; f < 2; f++) {
+    f_[f].stats = (FqStats*)dev_->alloc(sizeof(FqStats));
+    f_[f].hist = (unsigned long long*)dev_->alloc((size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
+  }
+  if (cfg_.index_capacity_hint && (cfg_.mode == FQG_MODE_INDEX || cfg_.mode == FQG_MODE_INDEX_PAIR)) {
+    table_cap_ = pow2_at_least(std::max<uint64_t>(1u << 16, cfg_.index_capacity_hint * 2));
+    slots_ = (FqSlot*)dev_->alloc(table_cap_ * sizeof(FqSlot));
+  }
+  reset();
+}
+
+void FqEngine::free_file(FqFile& F) {
+  for (auto& s : F.segs) { if (s.names) dev_->release(s.names); if (s.lines_dev) dev_->release(s.lines_dev); }
+  for (auto& b : F.bufs) { if (b.owned && b.data) dev_->release(b.data); if (b.line_end) dev_->release(b.line_end); }
+  if (F.pend) dev_->release(F.pend);
+  if (F.dir_dev) dev_->release(F.dir_dev);
+  FqStats* st = F.stats; unsigned long long* h = F.hist;
+  F = FqFile();
+  F.stats = st; F.hist = h;
+}
+
+FqEngine::~FqEngine() {
+  dev_->sync();
+  for (int f = 0; f < 2; f++) { free_file(f_[f]); dev_->release(f_[f].stats); dev_->release(f_[f].hist); }
+  if (slots_) dev_->release(slots_);
+  dev_->release(key_); dev_->release(counters_); dev_->release(scratch_); dev_->release(recout_);
+}
+
+/* forget input and results; the index keeps its allocation */
+void FqEngine::reset() {
+  dev_->sync();
+  for (int f = 0; f < 2; f++) free_file(f_[f]);
+  seed_ = 0; finished_ = false;
+  /* results */
+  dev_->fill(key_, 0xFF, sizeof(unsigned long long));
+  dev_->fill(counters_, 0, 4 * sizeof(unsigned long long));
+  for (int f = 0; f < 2; f++) {
+    FqStats init; memset(&init, 0, sizeof init);
+    init.min_rl = 0xFFFFFFFFu; init.min_q = 255u;
+    dev_->upload(f_[f].stats, &init, sizeof init);
+    dev_->fill(f_[f].hist, 0, (size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
+  }
+  dev_->sync(); /* `init` is a stack object */
+  if (slots_) dev_->fill(slots_, 0xFF, table_cap_ * sizeof(FqSlot));
+  table_names_ = 0;
+}
+
+int FqEngine::loop_of(int file) const {
+  switch (cfg_.mode) {
+    case FQG_MODE_SINGLE: return FQ_LOOP_SINGLE;
+    case FQG_MODE_INDEX: return FQ_LOOP_INDEX;
+    case FQG_MODE_INDEX_PAIR: return file == 0 ? FQ_LOOP_INDEX : FQ_LOOP_MATE;
+    case FQG_MODE_INTERLEAVED: return FQ_LOOP_INTERLEAVED;
+    default: return file == 0 ? FQ_LOOP_SORTED1 : FQ_LOOP_SORTED2;
+  }
+}
+static uint64_t eff_records(const FqFile& F) { return std::min<uint64_t>(F.nrec, F.limit); }
+uint64_t FqEngine::step_base(int file) const { return loop_of(file) == FQ_LOOP_MATE ? eff_records(f_[0]) + 1 : 0; }
+
+FqRecCtx FqEngine::make_ctx(int file) const {
+  FqRecCtx cx; memset(&cx, 0, sizeof cx);
+  cx.loop = loop_of(file);
+  cx.fmt_key = fmt_of_sniff(f_[file].sniff_fmt);
+  cx.pe_key = (cfg_.mode == FQG_MODE_INDEX) ? 0 : 1; /* fastq_info.c:63,112-113,158,290,327 */
+  if (cx.loop == FQ_LOOP_MATE) { /* fastq_info.c:345: file-2 records are validated against file 1's state */
+    cx.fmt_val = fmt_of_sniff(f_[0].sniff_fmt); cx.pe_val = 1; cx.space = f_[0].sniff_color;
+  } else { cx.fmt_val = cx.fmt_key; cx.pe_val = cx.pe_key; cx.space = f_[file].sniff_color; }
+  cx.weight = cx.loop == FQ_LOOP_INDEX ? 2 : 1; /* fastq.c:241 + :344 */
+  cx.seed = seed_;
+  return cx;
+}
+
+/* ------------------------------------------------------------------------------------------------ feeding */
+void FqEngine::feed_host(int file, const void* bytes, size_t n, bool last) {
+  const uint8_t* p = (const uint8_t*)bytes;
+  if (n == 0) { add_buffer(file, nullptr, 0, last, false); return; }
+  while (n) {
+    size_t k = std::min(n, kMaxChunk);
+    uint8_t* d = (uint8_t*)dev_->alloc(k + kPad);
+    dev_->upload(d, p, k);
+    dev_->fill(d + k, 0, kPad);
+    add_buffer(file, d, (uint32_t)k, last && k == n, true);
+    p += k; n -= k;
+  }
+}
+void FqEngine::feed_device(int file, const void* dptr, size_t n, bool last) {
+  uint8_t* p = (uint8_t*)dptr;
+  if (n == 0) { add_buffer(file, nullptr, 0, last, false); return; }
+  while (n) {
+    size_t k = std::min(n, kMaxChunk);
+    add_buffer(file, p, (uint32_t)k, last && k == n, false);
+    p += k; n -= k;
+  }
+}
+
+uint32_t FqEngine::line_end_at(const FqBuffer& b, uint32_t idx) {
+  uint32_t v; dev_->download(&v, b.line_end + idx, sizeof v); return v;
+}
+
+void FqEngine::append_pending(int file, const uint8_t* src, size_t n, uint32_t lfs) {
+  FqFile& F = f_[file];
+  if (F.pend_n + n + kPad > F.pend_cap) {
+    size_t cap = std::max<size_t>((F.pend_n + n + kPad) * 2, 1 << 16);
+    uint8_t* np = (uint8_t*)dev_->alloc(cap);
+    if (F.pend_n) dev_->copy(np, F.pend, F.pend_n);
+    if (F.pend) { dev_->sync(); dev_->release(F.pend); }
+    F.pend = np; F.pend_cap = cap;
+  }
+  dev_->copy(F.pend + F.pend_n, src, n);
+  F.pend_n += n; F.pend_lfs += lfs;
+}
+
+/* The file ended while bytes were still waiting for the rest of their record: what is left may still split into
+ * a complete record (over-long lines), so it goes through the normal path as the file's final chunk. */
+void FqEngine::flush_pending_as_last(int file) {
+  FqFile& F = f_[file];
+  if (F.pend_n == 0) { end_file(file, nullptr, 0); return; }
+  size_t bn = F.pend_n;
+  uint8_t* bd = (uint8_t*)dev_->alloc(bn + kPad);
+  dev_->copy(bd, F.pend, bn);
+  dev_->fill(bd + bn, 0, kPad);
+  F.pend_n = 0; F.pend_lfs = 0;
+  add_buffer(file, bd, (uint32_t)bn, true, true);
+}
+
+void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned) {
+  FqFile& F = f_[file];
+  if (F.ended) throw std::runtime_error("fqg_feed after the end of the file");
+  if (cfg_.mode == FQG_MODE_INDEX_PAIR && file == 1 && !f_[0].ended) throw std::runtime_error("INDEX_PAIR: file 1 fed before file 0 ended");
+  if (file >= nfiles()) throw std::runtime_error("file index out of range for this mode");
+  F.fed = true;
+  if (n == 0) {
+    if (owned && data) dev_->release(data);
+    if (last) flush_pending_as_last(file);
+    return;
+  }
+  int b = (int)F.bufs.size();
+  F.bufs.push_back(FqBuffer());
+  {
+    FqBuffer& B = F.bufs[b];
+    B.data = data; B.n = n; B.owned = owned;
+    /* K1: line index.  Capacity is a guess (one line per 32 bytes); on overflow rescan with the exact count. */
+    uint32_t cap = n / 32 + 4096;
+    for (;;) {
+      B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
+      dev_->scan_lines(data, n, last ? 1 : 0, B.line_end, cap, scratch_);
+      uint32_t out2[2]; dev_->download(out2, scratch_, sizeof out2);
+      B.nlines = out2[0];
+      if (!out2[1]) break;
+      dev_->release(B.line_end); cap = B.nlines;
+    }
+  }
+  uint32_t pos = 0, j = 0;
+  /* bridge: finish the record that straddles the previous chunk boundary in a small chunk of its own */
+  while (F.pend_n > 0 && !F.ended) {
+    const FqBuffer B = F.bufs[b];
+    uint32_t need = 4 - std::min<uint32_t>(F.pend_lfs, 3);
+    uint32_t avail = B.nlines - j;
+    if (avail >= need) {
+      uint32_t cut = line_end_at(B, j + need - 1);
+      size_t bn = F.pend_n + (cut - pos);
+      uint8_t* bd = (uint8_t*)dev_->alloc(bn + kPad);
+      dev_->copy(bd, F.pend, F.pend_n);
+      dev_->copy(bd + F.pend_n, B.data + pos, cut - pos);
+      dev_->fill(bd + bn, 0, kPad);
+      F.pend_n = 0; F.pend_lfs = 0;
+      bool blast = last && cut == B.n;
+      pos = cut; j += need;
+      add_buffer(file, bd, (uint32_t)bn, blast, true); /* may leave a new remainder in F.pend (over-long lines) */
+    } else {
+      append_pending(file, B.data + pos, B.n - pos, avail);
+      pos = B.n; j = B.nlines;
+      if (last) flush_pending_as_last(file);
+      return;
+    }
+  }
+  if (F.ended) return;
+  segmentize(file, b, pos, j, last);
+}
+
+void FqEngine::segmentize(int file, int b, uint32_t pos, uint32_t j, bool last) {
+  FqFile& F = f_[file];
+  for (;;) {
+    const FqBuffer B = F.bufs[b];
+    uint32_t avail = B.nlines - j, nrec = avail / 4;
+    uint32_t a = kNone32;
+    if (avail > 0 || (!last && pos < B.n)) {
+      dev_->fill(scratch_, 0xFF, sizeof(uint32_t));
+      dev_->find_overlong(B.line_end, pos, j, avail, B.n, last ? 0 : 1, scratch_);
+      dev_->download(&a, scratch_, sizeof a);
+    }
+    uint32_t nfast = a == kNone32 ? nrec : std::min(nrec, (a - j) / 4);
+    if (nfast) {
+      FqSegment s; s.buf = b; s.q = pos; s.j0 = j; s.nrec = nfast;
+      add_segment(file, s);
+      j += 4 * nfast;
+      pos = line_end_at(B, j - 1);
+    }
+    if (a == kNone32) break;
+    /* the record starting at pos holds a line that gzgets would split: emulate the four reads serially */
+    FqLine* ld = (FqLine*)dev_->alloc(4 * sizeof(FqLine));
+    dev_->split_serial(B.data, B.n, pos, last ? 1 : 0, ld, scratch_);
+    uint32_t out3[3]; dev_->download(out3, scratch_, sizeof out3);
+    if (out3[1] != 4) { dev_->release(ld); break; }
+    FqSegment s; s.buf = b; s.q = pos; s.j0 = j; s.nrec = 1; s.explicit_lines = true; s.lines_dev = ld;
+    dev_->download(s.lines_host, ld, 4 * sizeof(FqLine));
+    add_segment(file, s);
+    pos = out3[0]; j += out3[2];
+  }
+  const FqBuffer B = F.bufs[b];
+  if (last) end_file(file, B.data + pos, B.n - pos);
+  else if (pos < B.n) append_pending(file, B.data + pos, B.n - pos, B.nlines - j);
+}
+
+/* The file ended; [tail, tail+n) holds fewer than four gz-lines.  Split them the way gzgets would. */
+void FqEngine::end_file(int file, const uint8_t* dev_tail, size_t n) {
+  FqFile& F = f_[file];
+  F.tail.assign(n, 0);
+  if (n) dev_->download(F.tail.data(), dev_tail, n);
+  F.tail_lines.clear();
+  size_t p = 0; int i = 0;
+  while (p < n) {
+    size_t maxb = ((i & 1) == 0 ? FQ_MAX_LABEL_LENGTH : FQ_MAX_READ_LENGTH) - 1, k = 0;
+    while (k < maxb && p + k < n) { k++; if (F.tail[p + k - 1] == '\n') break; }
+    FqTailLine tl; tl.off = (uint32_t)p; tl.len = (uint32_t)k;
+    F.tail_lines.push_back(tl);
+    p += k; i++;
+  }
+  F.ended = true;
+}
+
+void FqEngine::sync_dir(int file) {
+  FqFile& F = f_[file];
+  if (F.dir_synced == F.dir_host.size()) return;
+  if (F.dir_host.size() > F.dir_cap) {
+    size_t cap = std::max<size_t>(F.dir_host.size() * 2, 64);
+    FqDirEntry* nd = (FqDirEntry*)dev_->alloc(cap * sizeof(FqDirEntry));
+    if (F.dir_dev) { dev_->sync(); dev_->release(F.dir_dev); }
+    F.dir_dev = nd; F.dir_cap = cap; F.dir_synced = 0;
+  }
+  dev_->upload(F.dir_dev + F.dir_synced, F.dir_host.data() + F.dir_synced, (F.dir_host.size() - F.dir_synced) * sizeof(FqDirEntry));
+  dev_->sync(); /* dir_host may reallocate later */
+  F.dir_synced = F.dir_host.size();
+}
+
+void FqEngine::add_segment(int file, FqSegment s) {
+  FqFile& F = f_[file];
+  s.g0 = F.nrec; F.nrec += s.nrec;
+  if (loop_of(file) != FQ_LOOP_SINGLE) s.names = (FqName*)dev_->alloc((size_t)s.nrec * sizeof(FqName));
+  F.segs.push_back(s);
+  FqDirEntry de; de.g0 = s.g0; de.names = s.names; de.data = F.bufs[s.buf].data;
+  F.dir_host.push_back(de);
+  launch_segment(file, F.segs.size() - 1);
+}
+
+void FqEngine::record_lines(int file, uint64_t g, FqLine out[4], const uint8_t** data) {
+  FqFile& F = f_[file];
+  size_t lo = 0, hi = F.segs.size();
+  while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (F.segs[mid].g0 <= g) lo = mid; else hi = mid; }
+  const FqSegment& s = F.segs[lo];
+  const FqBuffer& B = F.bufs[s.buf];
+  if (data) *data = B.data;
+  if (s.explicit_lines) { memcpy(out, s.lines_host, 4 * sizeof(FqLine)); return; }
+  uint32_t k = (uint32_t)(g - s.g0), j = s.j0 + 4 * k;
+  uint32_t e[5];
+  if (j == 0 || k == 0) { e[0] = s.q; dev_->download(e + 1, B.line_end + j, 4 * sizeof(uint32_t)); }
+  else dev_->download(e, B.line_end + j - 1, 5 * sizeof(uint32_t));
+  for (int i = 0; i < 4; i++) { out[i].off = e[i]; out[i].len = e[i + 1] - e[i]; }
+}
+
+void FqEngine::sniff_if_needed(int file, const FqSegment& s) {
+  FqFile& F = f_[file];
+  if (F.sniff_fmt >= 0 || s.g0 != 0) return;
+  FqLine L[4]; const uint8_t* data;
+  record_lines(file, 0, L, &data);
+  dev_->sniff(data, L[0], L[1], (int32_t*)scratch_);
+  int32_t out2[2]; dev_->download(out2, scratch_, sizeof out2);
+  F.sniff_fmt = out2[0]; F.sniff_color = out2[1];
+}
+
+void FqEngine::ensure_table(uint64_t names_total) {
+  if (slots_ && names_total * 2 <= table_cap_) return;
+  uint64_t cap = pow2_at_least(std::max<uint64_t>(1u << 16, names_total * 4));
+  if (slots_) { dev_->sync(); dev_->release(slots_); }
+  slots_ = (FqSlot*)dev_->alloc(cap * sizeof(FqSlot));
+  table_cap_ = cap;
+  dev_->fill(slots_, 0xFF, cap * sizeof(FqSlot));
+  /* re-insert what the smaller table held */
+  uint64_t done = table_names_; table_names_ = 0;
+  FqFile& F = f_[0];
+  for (size_t si = 0; si < F.segs.size() && table_names_ < done; si++) {
+    uint64_t lim = eff_records(F);
+    if (F.segs[si].g0 >= lim) break;
+    launch_names(0, si, (uint32_t)std::min<uint64_t>(F.segs[si].nrec, lim - F.segs[si].g0));
+  }
+}
+
+void FqEngine::launch_names(int file, size_t si, uint32_t nrec) {
+  FqFile& F = f_[file];
+  const FqSegment& s = F.segs[si];
+  int loop = loop_of(file);
+  if (loop != FQ_LOOP_INDEX && loop != FQ_LOOP_MATE) return;
+  FqTableArgs t; memset(&t, 0, sizeof t);
+  t.names = s.names; t.data = F.bufs[s.buf].data; t.nrec = nrec; t.g0 = s.g0; t.step_base = step_base(file);
+  t.key = key_; t.counters = counters_;
+  sync_dir(0);
+  t.dir1 = f_[0].dir_dev; t.ndir1 = (uint32_t)f_[0].dir_host.size();
+  if (loop == FQ_LOOP_INDEX) {
+    ensure_table(table_names_ + nrec);
+    t.slots = slots_; t.mask = table_cap_ - 1;
+    dev_->index_insert(t);
+    table_names_ += nrec;
+  } else {
+    ensure_table(table_names_);
+    t.slots = slots_; t.mask = table_cap_ - 1;
+    dev_->mate_claim(t);
+  }
+}
+
+void FqEngine::launch_segment(int file, size_t si) {
+  FqFile& F = f_[file];
+  const FqSegment& s = F.segs[si];
+  uint64_t lim = F.limit;
+  if (s.g0 >= lim) return;
+  if (loop_of(file) == FQ_LOOP_MATE && eff_records(f_[0]) == 0) return; /* "No reads found": file 2 is never opened */
+  uint32_t nrec = (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0);
+  sniff_if_needed(file, s);
+  const FqBuffer& B = F.bufs[s.buf];
+  FqRecordsArgs a; memset(&a, 0, sizeof a);
+  a.data = B.data; a.line_end = B.line_end; a.lines = s.explicit_lines ? s.lines_dev : nullptr;
+  a.q = s.q; a.j0 = s.j0; a.nrec = nrec; a.g0 = s.g0; a.step_base = step_base(file);
+  a.cx = make_ctx(file);
+  int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
+  a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats;
+  a.key = key_; a.names = s.names;
+  dev_->records(a);
+  launch_names(file, si, nrec);
+}
+
+/* interleaved mates and sorted pairs: compare the two names of every pair (fastq_info.c:86-91, :133-138) */
+void FqEngine::launch_pairs() {
+  if (cfg_.mode == FQG_MODE_INTERLEAVED) {
+    FqFile& F = f_[0];
+    uint64_t N = eff_records(F);
+    for (size_t si = 0; si < F.segs.size(); si++) {
+      const FqSegment& s = F.segs[si];
+      if (s.g0 >= N) break;
+      uint64_t end = std::min<uint64_t>(s.g0 + s.nrec, N);
+      uint64_t e0 = s.g0 + (s.g0 & 1);
+      const uint8_t* d = F.bufs[s.buf].data;
+      if (e0 + 1 < end) {
+        FqPairArgs p; memset(&p, 0, sizeof p);
+        p.a = s.names + (e0 - s.g0); p.b = p.a + 1; p.da = p.db = d; p.stride_a = p.stride_b = 2;
+        p.npairs = (uint32_t)((end - e0) / 2); p.p0 = e0 / 2; p.rank = FQ_RI_UNPAIRED; p.key = key_;
+        dev_->pair_compare(p);
+      }
+      /* a pair split across two segments */
+      if (((s.g0 + s.nrec) & 1) && s.g0 + s.nrec < N && si + 1 < F.segs.size()) {
+        const FqSegment& t = F.segs[si + 1];
+        FqPairArgs p; memset(&p, 0, sizeof p);
+        p.a = s.names + (s.nrec - 1); p.da = d; p.b = t.names; p.db = F.bufs[t.buf].data; p.stride_a = p.stride_b = 1;
+        p.npairs = 1; p.p0 = (s.g0 + s.nrec - 1) / 2; p.rank = FQ_RI_UNPAIRED; p.key = key_;
+        dev_->pair_compare(p);
+      }
+    }
+  } else if (cfg_.mode == FQG_MODE_SORTED_PAIR) {
+    uint64_t N = std::min(eff_records(f_[0]), eff_records(f_[1]));
+    size_t i = 0, k = 0;
+    while (i < f_[0].segs.size() && k < f_[1].segs.size()) {
+      const FqSegment& s = f_[0].segs[i]; const FqSegment& t = f_[1].segs[k];
+      uint64_t lo = std::max(s.g0, t.g0), hi = std::min<uint64_t>(std::min(s.g0 + s.nrec, t.g0 + t.nrec), N);
+      if (lo < hi) {
+        FqPairArgs p; memset(&p, 0, sizeof p);
+        p.a = s.names + (lo - s.g0); p.da = f_[0].bufs[s.buf].data; p.b = t.names + (lo - t.g0); p.db = f_[1].bufs[t.buf].data;
+        p.stride_a = p.stride_b = 1; p.npairs = (uint32_t)(hi - lo); p.p0 = lo; p.rank = FQ_RS_MISMATCH; p.key = key_;
+        dev_->pair_compare(p);
+      }
+      if (s.g0 + s.nrec <= t.g0 + t.nrec) i++; else k++;
+    }
+  }
+}
+
+/* run every kernel again over the resident chunks (after a limit or the hash seed changed) */
+void FqEngine::reprocess() {
+  dev_->sync();
+  dev_->fill(key_, 0xFF, sizeof(unsigned long long));
+  dev_->fill(counters_, 0, 4 * sizeof(unsigned long long));
+  for (int f = 0; f < 2; f++) {
+    FqStats init; memset(&init, 0, sizeof init);
+    init.min_rl = 0xFFFFFFFFu; init.min_q = 255u;
+    dev_->upload(f_[f].stats, &init, sizeof init);
+    dev_->sync();
+    dev_->fill(f_[f].hist, 0, (size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
+  }
+  if (slots_) dev_->fill(slots_, 0xFF, table_cap_ * sizeof(FqSlot));
+  table_names_ = 0;
+  for (int f = 0; f < nfiles(); f++)
+    for (size_t si = 0; si < f_[f].segs.size(); si++) launch_segment(f, si);
+}
+
+/* first byte of the gz-line with this index inside the file; -1 when the file has no such line */
+int FqEngine::first_byte_of_line(int file, uint64_t gl) {
+  FqFile& F = f_[file];
+  uint64_t r = gl / 4;
+  if (r < F.nrec) {
+    FqLine L[4]; const uint8_t* data;
+    record_lines(file, r, L, &data);
+    if (L[gl & 3].len == 0) return -1;
+    uint8_t c; dev_->download(&c, data + L[gl & 3].off, 1);
+    return c;
+  }
+  uint64_t ti = gl - 4 * F.nrec;
+  if (ti < F.tail_lines.size() && F.tail_lines[ti].len) return F.tail[F.tail_lines[ti].off];
+  return -1;
+}
+
+/* ------------------------------------------------------------------------------------------------ finish */
+namespace {
+struct HostEvent { uint64_t key; int code; int file; uint64_t line; uint64_t a; };
+enum { PEEK_NONE = 0, PEEK_TRUNC = 1, PEEK_RECORD = 2 };
+}
+
+void FqEngine::finish(fqg_report* rep) {
+  memset(rep, 0, sizeof *rep);
+  rep->mode = cfg_.mode;
+  for (int f = 0; f < nfiles(); f++)
+    if (!f_[f].ended) {
+      if (f == 1 && cfg_.mode == FQG_MODE_INDEX_PAIR && f_[0].ended) continue; /* caller stopped after file 1: allowed when file 1 failed */
+      throw std::runtime_error("fqg_finish before the end of every file");
+    }
+  auto peek_record = [&](int file, uint64_t first_line) -> int { /* what fastq_read_entry would do from this line on */
+    int b0 = first_byte_of_line(file, first_line);
+    if (b0 <= 0) return PEEK_NONE;
+    for (int i = 1; i < 4; i++) if (first_byte_of_line(file, first_line + i) <= 0) return PEEK_TRUNC;
+    return PEEK_RECORD;
+  };
+  auto tail_first = [&](int file) -> int { /* -1 nothing left, else first byte of what is left */
+    FqFile& F = f_[file];
+    if (F.limit < F.nrec) return -1;
+    return F.tail_lines.empty() ? -1 : (int)F.tail[0];
+  };
+
+  HostEvent ev; uint64_t dev_key = FQ_KEY_NONE; unsigned long long ctr[4] = {0, 0, 0, 0};
+  bool sorted_end_f1 = false; uint64_t sorted_end_step = 0; bool have_end = false;
+  bool sorted_validated[2] = {false, false};
+  for (int attempt = 0;; attempt++) {
+    if (attempt > 16) throw std::runtime_error("finish: too many reprocessing rounds");
+    launch_pairs();
+    dev_->download(&dev_key, key_, sizeof dev_key);
+    dev_->download(ctr, counters_, sizeof ctr);
+    if (ctr[2]) throw std::runtime_error("index table overflow");
+    if (ctr[0]) { seed_++; reprocess(); continue; } /* two different names shared a 64-bit hash: new seed */
+    /* events only the host can see: what is left at the end of each file */
+    ev.key = FQ_KEY_NONE; ev.code = 0; ev.file = 0; ev.line = 0; ev.a = 0;
+    auto offer = [&](uint64_t key, int code, int file, uint64_t line, uint64_t a) {
+      if (key < ev.key) { ev.key = key; ev.code = code; ev.file = file; ev.line = line; ev.a = a; }
+    };
+    uint64_t N0 = eff_records(f_[0]), N1 = eff_records(f_[1]);
+    int t0 = tail_first(0), t1 = nfiles() > 1 && f_[1].ended ? tail_first(1) : -1;
+    have_end = false;
+    switch (cfg_.mode) {
+      case FQG_MODE_SINGLE: case FQG_MODE_INDEX:
+        if (t0 > 0) offer(FQ_KEY(N0, FQ_R_TRUNC), FQ_E_TRUNC, 0, 4 * N0, 0);
+        break;
+      case FQG_MODE_INDEX_PAIR:
+        if (t0 > 0) offer(FQ_KEY(N0, FQ_R_TRUNC), FQ_E_TRUNC, 0, 4 * N0, 0);
+        if (N0 > 0 && f_[1].ended) {
+          uint64_t S1 = N0 + 1;
+          if (t1 > 0) offer(FQ_KEY(S1 + N1, FQ_R_TRUNC), FQ_E_TRUNC, 1, 4 * N1, 0);
+          FqStats st; dev_->download(&st, f_[0].stats, sizeof st);
+          uint64_t left = st.n_names - ctr[1];
+          if (left > 0) offer(FQ_KEY(S1 + N1 + 1, 0), FQ_E_LEFTOVER, 0, 0, left);
+        }
+        break;
+      case FQG_MODE_INTERLEAVED:
+        if (f_[0].limit >= f_[0].nrec) {
+          if ((N0 & 1) == 0) { if (t0 > 0) offer(FQ_KEY(N0 / 2, FQ_RI_TRUNC1), FQ_E_TRUNC, 0, 4 * N0, 0); }
+          else if (t0 > 0) offer(FQ_KEY(N0 / 2, FQ_RI_TRUNC2), FQ_E_TRUNC, 0, 4 * N0, 0);
+          else offer(FQ_KEY(N0 / 2, FQ_RI_NOM2), FQ_E_TRUNC_PE, 0, 4 * N0, 0);
+        }
+        break;
+      default: { /* sorted pair: the loop ends at the first file that runs out (fastq_info.c:121-141) */
+        uint64_t k1 = t0 > 0 ? FQ_KEY_NONE : FQ_KEY(N0, FQ_RS_STOP1), k2 = t1 > 0 ? FQ_KEY_NONE : FQ_KEY(N1, FQ_RS_STOP2);
+        if (t0 > 0) offer(FQ_KEY(N0, FQ_RS_TRUNC1), FQ_E_TRUNC, 0, 4 * N0, 0);
+        if (t1 > 0) offer(FQ_KEY(N1, FQ_RS_TRUNC2), FQ_E_TRUNC, 1, 4 * N1, 0);
+        uint64_t first_err = std::min(ev.key, dev_key);
+        uint64_t kend = std::min(k1, k2);
+        if (kend < first_err) { have_end = true; sorted_end_f1 = k1 < k2; sorted_end_step = sorted_end_f1 ? N0 : N1; }
+        break;
+      }
+    }
+    /* a record whose first line starts with NUL ends its file early (fastq.c:248): restrict and run again */
+    uint64_t first = std::min(ev.key, dev_key);
+    if (dev_key != FQ_KEY_NONE && dev_key == first && !(have_end)) {
+      uint64_t step = FQ_KEY_STEP(dev_key); uint32_t rank = FQ_KEY_RANK(dev_key);
+      bool restricted = false;
+      switch (cfg_.mode) {
+        case FQG_MODE_SINGLE: case FQG_MODE_INDEX:
+          if (rank == FQ_R_STOP) { f_[0].limit = step; restricted = true; }
+          break;
+        case FQG_MODE_INDEX_PAIR:
+          if (rank == FQ_R_STOP) {
+            if (step < N0 + 1) f_[0].limit = step; else f_[1].limit = step - (N0 + 1);
+            restricted = true;
+          }
+          break;
+        case FQG_MODE_INTERLEAVED:
+          if (rank == FQ_RI_STOP1) { f_[0].limit = 2 * step; restricted = true; }
+          break;
+        default:
+          if (rank == FQ_RS_STOP1) { f_[0].limit = step; f_[1].limit = std::min<uint64_t>(f_[1].limit, step); restricted = true; }
+          else if (rank == FQ_RS_STOP2) { f_[1].limit = step; f_[0].limit = std::min<uint64_t>(f_[0].limit, step + 1); restricted = true; }
+          break;
+      }
+      if (restricted) { reprocess(); continue; }
+    }
+    break;
+  }
+
+  uint64_t first = std::min(ev.key, dev_key);
+  uint64_t N0 = eff_records(f_[0]), N1 = eff_records(f_[1]);
+  /* sorted pair: the two reads after the loop (fastq_info.c:142-149) */
+  if (cfg_.mode == FQG_MODE_SORTED_PAIR && have_end) {
+    uint64_t k = sorted_end_step;
+    /* a file that stopped on a NUL-led line has consumed only that line */
+    bool f1_nul = sorted_end_f1 && first_byte_of_line(0, 4 * k) == 0;
+    bool f2_nul = !sorted_end_f1 && first_byte_of_line(1, 4 * k) == 0;
+    uint64_t next1 = sorted_end_f1 ? (f1_nul ? 4 * k + 1 : 4 * k + 4) : 4 * (k + 1);
+    uint64_t next2 = sorted_end_f1 ? 4 * k : (f2_nul ? 4 * k + 1 : 4 * k + 4);
+    uint64_t read1 = sorted_end_f1 ? k : k + 1; /* records file 1 has read */
+    first = FQ_KEY_NONE; ev.key = FQ_KEY_NONE; dev_key = FQ_KEY_NONE;
+    int p1 = peek_record(0, next1);
+    if (p1 == PEEK_TRUNC) { ev.key = 0; ev.code = FQ_E_TRUNC; ev.file = 0; ev.line = 4 * read1; }
+    else if (p1 == PEEK_RECORD) { ev.key = 0; ev.code = FQ_E_EOF2; ev.file = 0; }
+    else {
+      int p2 = peek_record(1, next2);
+      if (p2 == PEEK_TRUNC) { ev.key = 0; ev.code = FQ_E_TRUNC; ev.file = 1; ev.line = 4 * k; }
+      else if (p2 == PEEK_RECORD) { ev.key = 0; ev.code = FQ_E_EOF1; ev.file = 1; }
+    }
+    first = ev.key;
+    if (first == FQ_KEY_NONE) { /* success: statistics cover exactly the records the loop validated */
+      uint64_t l0 = read1, l1 = k;
+      if (l0 < N0 || l1 < N1) { f_[0].limit = l0; f_[1].limit = l1; reprocess(); launch_pairs(); dev_->sync(); }
+    }
+    rep->reads_before_error[0] = k; rep->reads_before_error[1] = k;
+    sorted_validated[0] = read1 >= 1; sorted_validated[1] = k >= 1;
+    N0 = eff_records(f_[0]); N1 = eff_records(f_[1]);
+  }
+
+  rep->file[0].n_records = N0; rep->file[1].n_records = N1;
+  for (int f = 0; f < 2; f++) { rep->file[f].sniff_format = -1; rep->file[f].color_space = -1; }
+  if (first == FQ_KEY_NONE) {
+    rep->error.code = FQG_OK;
+    if (cfg_.mode != FQG_MODE_SORTED_PAIR) { rep->reads_before_error[0] = N0; rep->reads_before_error[1] = N1; }
+    if (cfg_.mode == FQG_MODE_INTERLEAVED) rep->reads_before_error[0] = N0 / 2;
+  } else if (first == ev.key) {
+    fill_error(rep, FQ_KEY_NONE, ev.code, ev.file, ev.line, ev.a);
+    if (cfg_.mode != FQG_MODE_SORTED_PAIR || !have_end) {
+      uint64_t step = FQ_KEY_STEP(ev.key);
+      if (cfg_.mode == FQG_MODE_INDEX_PAIR) {
+        if (step <= N0) { rep->reads_before_error[0] = step; rep->reads_before_error[1] = 0; }
+        else { rep->reads_before_error[0] = N0; rep->reads_before_error[1] = std::min<uint64_t>(step - (N0 + 1), N1); }
+      } else { rep->reads_before_error[0] = step; rep->reads_before_error[1] = step; }
+    }
+  } else {
+    fill_error(rep, dev_key, 0, 0, 0, 0);
+  }
+  fill_stats(rep);
+  /* which sniff lines the reference had printed by the time it stopped */
+  {
+    uint64_t k = first;
+    auto sniffed = [&](int f, uint64_t sniff_key) {
+      if (f_[f].sniff_fmt < 0 || eff_records(f_[f]) == 0) return;
+      if (k > sniff_key) { rep->file[f].sniff_format = f_[f].sniff_fmt; rep->file[f].color_space = f_[f].sniff_color; }
+    };
+    if (cfg_.mode == FQG_MODE_SORTED_PAIR && have_end) { /* the loop itself completed: a file was sniffed iff one of its records was validated */
+      for (int f = 0; f < 2; f++)
+        if (sorted_validated[f] && f_[f].sniff_fmt >= 0) { rep->file[f].sniff_format = f_[f].sniff_fmt; rep->file[f].color_space = f_[f].sniff_color; }
+      k = 0;
+    }
+    switch (cfg_.mode) {
+      case FQG_MODE_SINGLE: sniffed(0, FQ_KEY(0, FQ_R_V0 + FQ_V_PLUS)); break;
+      case FQG_MODE_INDEX: sniffed(0, FQ_KEY(0, FQ_R_WRONGHDR)); break;
+      case FQG_MODE_INDEX_PAIR: sniffed(0, FQ_KEY(0, FQ_R_WRONGHDR)); sniffed(1, FQ_KEY(N0 + 1, FQ_R_WRONGHDR)); break;
+      case FQG_MODE_INTERLEAVED: sniffed(0, FQ_KEY(0, FQ_RI_WRONGHDR1)); break;
+      default: sniffed(0, FQ_KEY(0, FQ_RS_V1 + FQ_V_PLUS)); sniffed(1, FQ_KEY(0, FQ_RS_V2 + FQ_V_PLUS)); break;
+    }
+  }
+  finished_ = true;
+}
+
+static void copy_cstr(char* dst, uint32_t* len_out, const std::vector<uint8_t>& src) {
+  size_t n = 0;
+  while (n < src.size() && n < 1023 && src[n] != 0) n++;
+  memcpy(dst, src.data(), n); dst[n] = 0; *len_out = (uint32_t)n;
+}
+
+/* Build the error part of the report.  key != NONE: an event found on the device (needs the record's details). */
+void FqEngine::fill_error(fqg_report* rep, uint64_t key, int host_code, int host_file, uint64_t host_line, uint64_t host_a) {
+  fqg_error& e = rep->error;
+  if (key == FQ_KEY_NONE) {
+    e.code = host_code; e.file = host_file; e.msg_file = host_file; e.line = host_line; e.a = host_a;
+    e.record = host_file == 0 ? eff_records(f_[0]) : eff_records(f_[1]);
+    return;
+  }
+  uint64_t step = FQ_KEY_STEP(key); uint32_t rank = FQ_KEY_RANK(key);
+  uint64_t N0 = eff_records(f_[0]);
+  int file = 0; uint64_t g = 0, L = 0; int code = 0; int vrank = -1; int msg_file = 0;
+  switch (cfg_.mode) {
+    case FQG_MODE_SINGLE: case FQG_MODE_INDEX: case FQG_MODE_INDEX_PAIR: {
+      bool mate = cfg_.mode == FQG_MODE_INDEX_PAIR && step >= N0 + 1;
+      file = mate ? 1 : 0; g = mate ? step - (N0 + 1) : step; msg_file = file;
+      L = 4 * (g + 1);
+      if (rank == FQ_R_TRUNC) { code = FQ_E_TRUNC; L = 4 * g; }
+      else if (rank == FQ_R_WRONGHDR) code = FQ_E_WRONGHDR;
+      else if (rank == FQ_R_NAME) code = mate ? FQ_E_UNPAIRED : FQ_E_DUP;
+      else { vrank = (int)rank - FQ_R_V0; if (mate) { msg_file = 0; L = 4 * N0; } }
+      rep->reads_before_error[0] = mate ? N0 : g; rep->reads_before_error[1] = mate ? g : 0;
+      break;
+    }
+    case FQG_MODE_INTERLEAVED: {
+      uint64_t p = step; L = 8 * (p + 1); g = 2 * p;
+      if (rank == FQ_RI_TRUNC1) { code = FQ_E_TRUNC; L = 8 * p; }
+      else if (rank == FQ_RI_NOM2) { code = FQ_E_TRUNC_PE; L = 8 * p + 4; g = 2 * p + 1; }
+      else if (rank == FQ_RI_TRUNC2) { code = FQ_E_TRUNC; L = 8 * p + 4; g = 2 * p + 1; }
+      else if (rank == FQ_RI_WRONGHDR1) code = FQ_E_WRONGHDR;
+      else if (rank == FQ_RI_WRONGHDR2) { code = FQ_E_WRONGHDR; g = 2 * p + 1; }
+      else if (rank == FQ_RI_UNPAIRED) code = FQ_E_UNPAIRED;
+      else if (rank >= FQ_RI_V2) { vrank = (int)rank - FQ_RI_V2; g = 2 * p + 1; }
+      else vrank = (int)rank - FQ_RI_V1;
+      rep->reads_before_error[0] = p;
+      break;
+    }
+    default: {
+      uint64_t k = step; g = k; L = 4 * (k + 1);
+      if (rank == FQ_RS_TRUNC1) { code = FQ_E_TRUNC; L = 4 * k; }
+      else if (rank == FQ_RS_TRUNC2) { code = FQ_E_TRUNC; L = 4 * k; file = 1; }
+      else if (rank == FQ_RS_MISMATCH) { code = FQ_E_MISMATCH; e.a = k + 2; }
+      else if (rank >= FQ_RS_V2) { vrank = (int)rank - FQ_RS_V2; file = 1; }
+      else vrank = (int)rank - FQ_RS_V1;
+      msg_file = file;
+      rep->reads_before_error[0] = k; rep->reads_before_error[1] = k;
+      break;
+    }
+  }
+  e.file = file; e.msg_file = msg_file; e.record = g;
+  /* details from the record itself */
+  FqLine Ls[4]; const uint8_t* data;
+  record_lines(file, g, Ls, &data);
+  FqRecCtx cx = make_ctx(file);
+  dev_->explain(data, Ls, cx, recout_);
+  FqRecOut o; dev_->download(&o, recout_, sizeof o);
+  if (vrank >= 0) {
+    code = (int)o.code;
+    if (code == FQ_E_BADCHAR) { L += 1; e.chr = (int32_t)o.bad; }
+    else if (code == FQ_E_UT) L -= 2;
+    else if (code == FQ_E_SHORT) { L += 1; e.a = o.slen; }
+    else if (code == FQ_E_PLUS) L += 2;
+    else if (code == FQ_E_LEN || code == FQ_E_LEN_CS) { e.a = o.slen; e.b = o.qlen; }
+  }
+  e.code = code; e.line = L;
+  std::vector<uint8_t> tmp;
+  auto fetch = [&](uint32_t off, uint32_t len, char* dst, uint32_t* lo) {
+    tmp.assign(std::min<uint32_t>(len, 1023), 0);
+    if (!tmp.empty()) dev_->download(tmp.data(), data + off, tmp.size());
+    copy_cstr(dst, lo, tmp);
+  };
+  fetch(Ls[0].off, Ls[0].len, e.hdr1, &e.hdr1_len);
+  fetch(Ls[2].off, Ls[2].len, e.hdr2, &e.hdr2_len);
+  fetch(o.name_off, o.name_len, e.name, &e.name_len);
+}
+
+void FqEngine::fill_stats(fqg_report* rep) {
+  FqStats st[2];
+  for (int f = 0; f < 2; f++) dev_->download(&st[f], f_[f].stats, sizeof(FqStats));
+  unsigned long long ctr[4]; dev_->download(ctr, counters_, sizeof ctr);
+  for (int f = 0; f < 2; f++) {
+    fqg_file_report& r = rep->file[f];
+    r.num_rds = st[f].num_rds;
+    r.min_rl = std::min<uint64_t>(FQ_MAX_READ_LENGTH, st[f].min_rl);
+    r.max_rl = st[f].max_rl;
+    /* (unsigned int)(char)c, fastq.c:374: bytes >= 0x80 become 0xFFFFFFxx */
+    uint64_t mn = st[f].min_q >= 0x80 ? (0xFFFFFF00ull | st[f].min_q) : st[f].min_q;
+    uint64_t mx = st[f].max_q >= 0x80 ? (0xFFFFFF00ull | st[f].max_q) : st[f].max_q;
+    r.min_qual = std::min<uint64_t>(FQ_MAX_PHRED, mn);
+    r.max_qual = mx;
+  }
+  rep->n_index_entries = st[0].n_names;
+  rep->n_index_left = st[0].n_names - ctr[1];
+  rep->index_mem = 8 + st[0].mem_sum + st[0].n_names * (16 + 1 + 24); /* fastq.c:609, fastq_info.c:293 */
+  /* median_rl, fastq_info.c:39-55: file 1's histogram (the mate loop also counts into it) */
+  const FqStats& s = st[0];
+  bool fd2_null = cfg_.mode != FQG_MODE_INDEX_PAIR || !f_[1].fed || eff_records(f_[0]) == 0;
+  uint64_t med = 1;
+  if (s.num_rds == 1 && fd2_null) med = std::min<uint64_t>(FQ_MAX_READ_LENGTH, s.min_rl);
+  else if (s.num_rds <= 1) med = FQ_MAX_READ_LENGTH;
+  else {
+    uint32_t lo = s.min_rl, hi = s.max_rl;
+    if (cfg_.mode == FQG_MODE_INDEX_PAIR && st[1].max_rl > 0) { lo = std::min(lo, st[1].min_rl); hi = std::max(hi, st[1].max_rl); }
+    std::vector<unsigned long long> h(hi - lo + 1);
+    dev_->download(h.data(), f_[0].hist + lo, h.size() * sizeof(unsigned long long));
+    unsigned long long c = 0; med = FQ_MAX_READ_LENGTH;
+    for (uint32_t l = lo; l <= hi; l++) { c += h[l - lo]; if (c > s.num_rds / 2) { med = l; break; } }
+  }
+  rep->median_rl = med;
+}
+
+void FqEngine::index_records(const void* host_bytes, size_t n, uint64_t* starts, size_t cap, uint64_t* n_records) {
+  if (n > kMaxChunk) throw std::runtime_error("fqg_index_records: at most 2 GiB per call");
+  uint8_t* d = (uint8_t*)dev_->alloc(n + kPad);
+  dev_->upload(d, host_bytes, n); dev_->fill(d + n, 0, kPad);
+  uint32_t lcap = (uint32_t)(n / 32 + 4096); uint32_t* le; uint32_t out2[2];
+  for (;;) {
+    le = (uint32_t*)dev_->alloc((size_t)lcap * 4 + kPad);
+    dev_->scan_lines(d, (uint32_t)n, 1, le, lcap, scratch_);
+    dev_->download(out2, scratch_, sizeof out2);
+    if (!out2[1]) break;
+    dev_->release(le); lcap = out2[0];
+  }
+  uint64_t nrec = out2[0] / 4;
+  *n_records = nrec;
+  std::vector<uint32_t> h(out2[0]);
+  if (out2[0]) dev_->download(h.data(), le, (size_t)out2[0] * 4);
+  for (uint64_t i = 0; i < nrec && i < cap; i++) starts[i] = i == 0 ? 0 : h[4 * i - 1];
+  dev_->release(le); dev_->release(d);
+}

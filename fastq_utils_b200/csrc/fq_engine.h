@@ -1,0 +1,99 @@
+/*
+ * fq_engine.h — host side of libfastq_gpu: turns a stream of byte chunks per file into kernel launches and the
+ * kernels' results into the report of include/fastq_gpu.h.  No FASTQ byte is interpreted on the host except the
+ * (< 1 record) tail left at the end of a file, which is what the reference's reader sees when it hits EOF.
+ */
+#ifndef FQ_ENGINE_H
+#define FQ_ENGINE_H
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/fastq_gpu.h"
+#include "fq_device.h"
+
+struct FqBuffer {
+  uint8_t* data = nullptr;   /* device */
+  uint32_t n = 0;
+  bool owned = false;
+  uint32_t* line_end = nullptr;
+  uint32_t nlines = 0;       /* lines with an end inside the buffer (a final LF-less line counts when the file ended here) */
+};
+
+struct FqSegment {
+  int buf = -1;
+  uint32_t q = 0, j0 = 0, nrec = 0;
+  bool explicit_lines = false;
+  FqLine lines_host[4];
+  FqLine* lines_dev = nullptr;
+  uint64_t g0 = 0;
+  FqName* names = nullptr;   /* device, nrec entries (NULL for the single loop) */
+};
+
+struct FqTailLine { uint32_t off, len; };
+
+struct FqFile {
+  std::vector<FqBuffer> bufs;
+  std::vector<FqSegment> segs;
+  uint64_t nrec = 0;
+  /* bytes after the last complete record of the buffers seen so far (device) */
+  uint8_t* pend = nullptr; size_t pend_n = 0, pend_cap = 0; uint32_t pend_lfs = 0;
+  bool fed = false, ended = false;
+  /* what is left when the file ended: < 4 gz-lines, interpreted on the host like the reference's reader at EOF */
+  std::vector<uint8_t> tail;
+  std::vector<FqTailLine> tail_lines;
+  int sniff_fmt = -1, sniff_color = -1;
+  FqStats* stats = nullptr; unsigned long long* hist = nullptr; /* device */
+  FqDirEntry* dir_dev = nullptr; size_t dir_cap = 0; std::vector<FqDirEntry> dir_host; size_t dir_synced = 0;
+  uint64_t limit = ~0ull;   /* records at or beyond this index are never read (early clean end of file) */
+};
+
+class FqEngine {
+ public:
+  FqEngine(const fqg_config& cfg, FqDevice* dev);
+  ~FqEngine();
+  void feed_host(int file, const void* bytes, size_t n, bool last);
+  void feed_device(int file, const void* dptr, size_t n, bool last);
+  void finish(fqg_report* rep);
+  void reset();
+  void index_records(const void* host_bytes, size_t n, uint64_t* starts, size_t cap, uint64_t* n_records);
+  FqDevice* device() { return dev_; }
+  std::string last_error;
+
+ private:
+  fqg_config cfg_;
+  FqDevice* dev_;
+  FqFile f_[2];
+  unsigned long long* key_ = nullptr;       /* device: global minimum event key */
+  unsigned long long* counters_ = nullptr;  /* device: [0] collisions, [1] claimed, [2] table full */
+  uint32_t* scratch_ = nullptr;             /* device: small result words */
+  FqRecOut* recout_ = nullptr;              /* device: explain result */
+  FqSlot* slots_ = nullptr; uint64_t table_cap_ = 0; uint64_t table_names_ = 0;
+  uint32_t seed_ = 0;
+  bool finished_ = false;
+
+  int nfiles() const { return cfg_.mode == FQG_MODE_INDEX_PAIR || cfg_.mode == FQG_MODE_SORTED_PAIR ? 2 : 1; }
+  int loop_of(int file) const;
+  uint64_t step_base(int file) const;
+  FqRecCtx make_ctx(int file) const;
+  void add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned);
+  void segmentize(int file, int b, uint32_t pos, uint32_t j, bool last);
+  void flush_pending_as_last(int file);
+  void end_file(int file, const uint8_t* dev_tail, size_t n);
+  void append_pending(int file, const uint8_t* dev_src, size_t n, uint32_t lfs);
+  void add_segment(int file, FqSegment s);
+  void launch_segment(int file, size_t si);
+  void launch_names(int file, size_t si, uint32_t nrec);
+  void ensure_table(uint64_t names_total);
+  void sync_dir(int file);
+  void sniff_if_needed(int file, const FqSegment& s);
+  uint32_t line_end_at(const FqBuffer& b, uint32_t idx);
+  void record_lines(int file, uint64_t g, FqLine out[4], const uint8_t** data);
+  int first_byte_of_line(int file, uint64_t global_line);
+  void launch_pairs();
+  void reprocess();
+  void fill_error(fqg_report* rep, uint64_t key, int host_code, int host_file, uint64_t host_line, uint64_t host_a);
+  void fill_stats(fqg_report* rep);
+  void free_file(FqFile& f);
+};
+
+#endif

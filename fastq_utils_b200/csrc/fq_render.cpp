@@ -1,0 +1,335 @@
+/*
+ * fq_render.cpp — turns a finished report into the text and exit status the reference's fastq_info produces
+ * (stdout / stderr split, message wording, blank lines: src/fastq_info.c:190-396, src/fastq.h:69-82), and
+ * fqg_fastq_info_mem(): main() on inflated streams — option parsing, mode dispatch, feeding, rendering.
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "fq_engine.h"
+
+namespace {
+
+struct Text {
+  std::string out, err;
+  int rc = 0;
+  void o(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vput(out, fmt, ap); va_end(ap); }
+  void e(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vput(err, fmt, ap); va_end(ap); }
+  static void vput(std::string& s, const char* fmt, va_list ap) {
+    va_list ap2; va_copy(ap2, ap);
+    int k = vsnprintf(nullptr, 0, fmt, ap2); va_end(ap2);
+    std::vector<char> buf((size_t)k + 1);
+    vsnprintf(buf.data(), buf.size(), fmt, ap);
+    s.append(buf.data(), (size_t)k);
+  }
+};
+/* PRINT_ERROR, src/fastq.h:69 */
+#define ERR_BEGIN(t) (t).err += "\nERROR: "
+#define ERR_END(t) (t).err += "\n"
+
+const char* qual_range2enc(unsigned int lo, unsigned int hi) { /* fastq_qualRange2enc, src/fastq.c:274-297 */
+  static const char* names[] = {"33", "64", "solexa", "33 *", "sanger"};
+  int enc;
+  if (lo >= 33 && lo < 59 && hi >= 90) enc = 4;
+  else if (lo >= 33 && hi <= 73) enc = 0;
+  else if (lo < 59) enc = 0;
+  else if (lo >= 64 && hi > 74) enc = 1;
+  else if (lo >= 59 && hi > 74) enc = 2;
+  else enc = 3;
+  if (hi > FQ_MAX_PHRED) return nullptr;
+  if (enc != 4 && hi > lo + 60) return nullptr;
+  return names[enc];
+}
+
+void sniff_lines(Text& t, const fqg_file_report& f) { /* src/fastq.c:459-485 */
+  if (f.sniff_format == FQ_SNIFF_CASAVA) t.e("CASAVA=1.8\n");
+  else if (f.sniff_format == FQ_SNIFF_INT) t.e("Read name provided as an integer\n");
+  else if (f.sniff_format == FQ_SNIFF_NOSUFFIX) t.e("Read name provided with no suffix\n");
+  if (f.color_space == 1) t.e("Color space\n");
+}
+/* PRINT_READS_PROCESSED after each of `iters` loop iterations; the counter advances by `per_iter` */
+void progress(Text& t, uint64_t iters, uint64_t per_iter) {
+  uint64_t every = 100000 / per_iter;
+  for (uint64_t c = every; c <= iters; c += every) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", (unsigned long)(c * per_iter));
+}
+
+void error_text(Text& t, const fqg_error& e, const char* n1, const char* n2) {
+  const char* F = e.msg_file == 0 ? n1 : n2;
+  unsigned long L = (unsigned long)e.line;
+  ERR_BEGIN(t);
+  switch (e.code) {
+    case FQG_E_TRUNC: t.e("Error in file %s: line %lu: file truncated", F, L); break;
+    case FQG_E_TRUNC_PE: t.e("Error in file %s: line %lu: file truncated?", F, L); break;
+    case FQG_E_WRONGHDR: t.e("Error in file %s: line %lu: wrong header ", F, L); t.err.append(e.hdr1, e.hdr1_len); break;
+    case FQG_E_AT: t.e("Error in file %s: line %lu: sequence identifier should start with an @ - ", F, L); t.err.append(e.hdr1, e.hdr1_len); break;
+    case FQG_E_IDLEN: t.e("Error in file %s: line %lu: sequence identifier should be longer than 1", F, L); break;
+    case FQG_E_BADCHAR:
+      t.e("Error in file %s: line %lu: invalid character '", F, L);
+      t.err.push_back((char)e.chr);
+      t.e("' (hex. code:'%x'), expected ACGTUacgtu0123nN.", (int)(signed char)e.chr);
+      break;
+    case FQG_E_UT: t.e("Error in file %s: line %lu: read contains both U and T bases", F, L); break;
+    case FQG_E_SHORT: t.e("Error in file %s: line %lu: read length too small - %lu", F, L, (unsigned long)e.a); break;
+    case FQG_E_PLUS: t.e("Error in file %s: line %lu:  header2 wrong. The line should contain only '+' followed by a newline or read name (header1).", F, L); break;
+    case FQG_E_HDR2:
+      t.e("Error in file %s: line %lu:  header2 differs from header1\nheader 1 \"", F, L);
+      t.err.append(e.hdr1, e.hdr1_len); t.err += "\"\nheader 2 \""; t.err.append(e.hdr2, e.hdr2_len); t.err += "\"";
+      break;
+    case FQG_E_LEN: t.e("Error in file %s: line %lu: sequence and quality don't have the same length %lu!=%lu", F, L, (unsigned long)e.a, (unsigned long)e.b); break;
+    case FQG_E_LEN_CS: t.e("Error in file %s: line %lu: sequence and quality length don't match %lu!=%lu", F, L, (unsigned long)e.a, (unsigned long)e.b); break;
+    case FQG_E_DUP: t.e("Error in file %s: line %lu: duplicated sequence ", F, L); t.err.append(e.name, e.name_len); break;
+    case FQG_E_UNPAIRED: t.e("Error in file %s: line %lu: unpaired read - ", F, L); t.err.append(e.name, e.name_len); break;
+    case FQG_E_LEFTOVER: t.e("Error in file %s: found %llu unpaired reads", n1, (unsigned long long)e.a); break;
+    case FQG_E_MISMATCH: t.e("Readnames do not match across files (read #%ld)", (long)e.a); break;
+    case FQG_E_EOF1: t.e("Premature end of file1"); break;
+    case FQG_E_EOF2: t.e("Premature end of file2"); break;
+    default: t.e("internal: unknown error code %d", e.code);
+  }
+  ERR_END(t);
+  t.rc = e.code == FQG_E_TRUNC ? 1 : 3;
+}
+
+/* Everything after the banner, for a run whose files could be opened.  Returns false when the text is complete
+ * (an error was printed). */
+void render_run(Text& t, const fqg_report& r, const fqg_render_opts& o, bool f2_unopenable = false) {
+  const char* n1 = o.name1 ? o.name1 : "";
+  const char* n2 = o.name2 ? o.name2 : "";
+  const fqg_error& e = r.error;
+  bool failed = e.code != FQG_OK;
+  unsigned long num_reads1 = 0;
+  bool mate_pass = false;
+  switch (r.mode) {
+    case FQG_MODE_INTERLEAVED:
+      sniff_lines(t, r.file[0]);
+      progress(t, r.reads_before_error[0], 2);
+      if (failed) { error_text(t, e, n1, n2); return; }
+      t.o("\n");
+      num_reads1 = (unsigned long)r.file[0].num_rds;
+      break;
+    case FQG_MODE_SORTED_PAIR:
+      sniff_lines(t, r.file[0]); sniff_lines(t, r.file[1]);
+      progress(t, r.reads_before_error[0], 2);
+      if (failed) { error_text(t, e, n1, n2); return; }
+      t.o("\n");
+      num_reads1 = (unsigned long)r.file[0].num_rds;
+      break;
+    case FQG_MODE_SINGLE:
+      sniff_lines(t, r.file[0]);
+      progress(t, r.reads_before_error[0], 1);
+      if (failed) { error_text(t, e, n1, n2); return; }
+      t.o("\n");
+      num_reads1 = (unsigned long)r.file[0].num_rds;
+      break;
+    default: { /* index loop, then the mate loop */
+      t.e("DEFAULT_HASHSIZE=%lu\n", 39000001UL);
+      t.e("Scanning and indexing all reads from %s\n", n1);
+      sniff_lines(t, r.file[0]);
+      progress(t, r.reads_before_error[0], 1);
+      bool in_index_loop = failed && e.file == 0 && e.code != FQG_E_LEFTOVER;
+      if (in_index_loop) { error_text(t, e, n1, n2); return; }
+      t.e("Scanning complete.\n");
+      num_reads1 = (unsigned long)r.n_index_entries;
+      t.e("\n");
+      t.e("Reads processed: %llu\n", (unsigned long long)r.n_index_entries);
+      t.e("Memory used in indexing: ~%ld MB\n", (long)(r.index_mem / 1024 / 1024));
+      mate_pass = r.mode == FQG_MODE_INDEX_PAIR;
+    }
+  }
+  if (num_reads1 == 0) { /* src/fastq_info.c:304-314 */
+    if (o.empty_ok) {
+      t.o("Number of reads: %lu\n", 0L);
+      t.o("Quality encoding range: %lu %lu\n", 0L, 0L);
+      t.o("Quality encoding: %s\n", "");
+      t.o("Read length: %lu %lu %u\n", 0L, 0L, 0);
+      t.rc = 0; return;
+    }
+    ERR_BEGIN(t); t.e("No reads found in %s.", n1); ERR_END(t);
+    t.rc = 3; return;
+  }
+  if (mate_pass) {
+    t.e("File %s processed\n", n1);
+    t.e("Next file %s\n", n2);
+    if (o.name2 == nullptr) { t.rc = FQG_ERR_USAGE; return; }
+    if (f2_unopenable) { ERR_BEGIN(t); t.e("Unable to open %s", n2); ERR_END(t); t.rc = 1; return; } /* src/fastq.c:651-655 */
+    sniff_lines(t, r.file[1]);
+    progress(t, r.reads_before_error[1], 1);
+    if (failed && e.code != FQG_E_LEFTOVER) { error_text(t, e, n1, n2); return; }
+    t.o("\n");
+    if (failed) { error_text(t, e, n1, n2); return; }
+  }
+  const fqg_file_report& f = r.file[0];
+  t.e("------------------------------------\n");
+  t.e("Number of reads: %lu\n", num_reads1);
+  const char* enc = qual_range2enc((unsigned int)f.min_qual, (unsigned int)f.max_qual);
+  if (!enc && !o.no_enc_ok) {
+    ERR_BEGIN(t);
+    if (f.max_qual > FQ_MAX_PHRED) t.e("Unable to determine quality encoding - unknown range [%lu,>%u]", (unsigned long)f.min_qual, FQ_MAX_PHRED);
+    else t.e("Unable to determine quality encoding - unknown range [%lu,%lu]", (unsigned long)f.min_qual, (unsigned long)f.max_qual);
+    ERR_END(t);
+    t.rc = 3; return;
+  }
+  t.e("Quality encoding range: %lu %lu\n", (unsigned long)f.min_qual, (unsigned long)f.max_qual);
+  if (!enc) t.e("Quality encoding: NA\n"); else t.e("Quality encoding: %s\n", enc);
+  t.e("Read length: %lu %lu %u\n", (unsigned long)(f.min_rl - 1), (unsigned long)(f.max_rl - 1), (unsigned int)(r.median_rl - 1));
+  t.e("OK\n");
+  t.rc = 0;
+}
+
+void usage(Text& t, bool verbose) { /* src/fastq_info.c:178-188 */
+  t.o("Usage: fastq_info [-r -e -s -q -h] fastq1 [fastq2 file|pe]\n");
+  if (verbose) {
+    t.o(" -h  : print this help message\n");
+    t.o(" -s  : the reads in the two fastq files have the same ordering\n");
+    t.o(" -e  : do not fail with empty files\n");
+    t.o(" -q  : do not fail if quality encoding cannot be determined\n");
+    t.o(" -r  : skip check for duplicated readnames\n");
+  }
+}
+
+void to_transcript(const Text& t, fqg_transcript* tr) {
+  tr->rc = t.rc;
+  tr->out = (char*)malloc(t.out.size() + 1); memcpy(tr->out, t.out.data(), t.out.size()); tr->out[t.out.size()] = 0; tr->out_len = t.out.size();
+  tr->err = (char*)malloc(t.err.size() + 1); memcpy(tr->err, t.err.data(), t.err.size()); tr->err[t.err.size()] = 0; tr->err_len = t.err.size();
+}
+
+void feed_all(FqEngine& eng, int file, const void* p, size_t n, size_t chunk) {
+  if (chunk == 0 || n <= chunk) { eng.feed_host(file, p, n, true); return; }
+  const uint8_t* b = (const uint8_t*)p;
+  for (size_t off = 0; off < n; off += chunk) {
+    size_t k = n - off < chunk ? n - off : chunk;
+    eng.feed_host(file, b + off, k, off + k == n);
+  }
+}
+
+}  // namespace
+
+extern "C" int fqg_render(const fqg_report* rep, const fqg_render_opts* opts, fqg_transcript* tr) {
+  if (!rep || !opts || !tr) return FQG_ERR_USAGE;
+  Text t;
+  t.e("fastq_utils %s\n", "0.25.3");
+  switch (rep->mode) {
+    case FQG_MODE_INTERLEAVED: t.e("Paired-end interleaved\n"); break;
+    case FQG_MODE_SORTED_PAIR: t.e("-s option used: assuming that reads have the same ordering in both files\n"); break;
+    case FQG_MODE_SINGLE: t.e("Skipping check for duplicated read names\n"); break;
+    default: break;
+  }
+  render_run(t, *rep, *opts);
+  if (t.rc < 0) return t.rc;
+  to_transcript(t, tr);
+  return 0;
+}
+
+extern "C" void fqg_transcript_free(fqg_transcript* t) {
+  if (!t) return;
+  free(t->out); free(t->err); t->out = t->err = nullptr;
+}
+
+FqDevice* fq_default_device(int ordinal); /* fq_abi.cpp (CUDA) or the test stand-in */
+
+extern "C" int fqg_fastq_info_mem(int argc, const char** argv_in, const void* f1, size_t n1, const void* f2, size_t n2,
+                                  int device, size_t chunk_bytes, fqg_transcript* tr) {
+  Text t;
+  const size_t UNOPENABLE = (size_t)-1;
+  bool is_paired = false, is_interleaved = false, is_sorted = false, empty_ok = false, no_enc_ok = false, skip_names = false;
+  int nopt = 0;
+  t.e("fastq_utils %s\n", "0.25.3");
+  /* getopt("esfrhq") as GNU libc runs it: option words are permuted to the front, in order; "--" ends them */
+  std::vector<const char*> argv; argv.push_back(argc > 0 ? argv_in[0] : "fastq_info");
+  {
+    bool stop = false;
+    for (int i = 1; i < argc; i++) {
+      const char* w = argv_in[i];
+      if (!stop && !strcmp(w, "--")) { argv.push_back(w); stop = true; continue; }
+      if (!stop && w[0] == '-' && w[1] != '\0') argv.push_back(w);
+    }
+    size_t nflag_words = argv.size();
+    stop = false;
+    for (int i = 1; i < argc; i++) {
+      const char* w = argv_in[i];
+      if (!stop && !strcmp(w, "--")) { stop = true; continue; }
+      if (stop || !(w[0] == '-' && w[1] != '\0')) argv.push_back(w);
+    }
+    for (size_t i = 1; i < nflag_words; i++) {
+      const char* w = argv[i];
+      if (!strcmp(w, "--")) break;
+      for (const char* c = w + 1; *c; c++) {
+        switch (*c) {
+          case 'q': no_enc_ok = true; ++nopt; break;
+          case 'e': empty_ok = true; ++nopt; break;
+          case 's': is_sorted = true; ++nopt; break;
+          case 'r': skip_names = true; ++nopt; break;
+          case 'h': usage(t, true); t.rc = 0; to_transcript(t, tr); return 0;
+          case 'f':
+            t.e("Fixing (-f) enabled: Replacing . by N (creating .fix.gz files)\n");
+            ERR_BEGIN(t); t.e("-f option is no longer valid."); ERR_END(t);
+            t.rc = 1; to_transcript(t, tr); return 0;
+          default:
+            ++nopt;
+            ERR_BEGIN(t); t.e("Option -%c invalid", *c); ERR_END(t);
+            t.rc = 1; to_transcript(t, tr); return 0;
+        }
+      }
+    }
+  }
+  if (argc - nopt < 2 || argc - nopt > 3) {
+    ERR_BEGIN(t); t.e("Invalid number of arguments"); ERR_END(t);
+    usage(t, false);
+    t.rc = 1; to_transcript(t, tr); return 0;
+  }
+  const char* a1 = argv[1 + nopt];
+  const char* a2 = (argc - nopt == 3) ? argv[2 + nopt] : nullptr;
+  if (a2) { is_paired = true; is_interleaved = strncmp(a2, "pe", 2) == 0; }
+
+  auto unopenable = [&](const char* name) { ERR_BEGIN(t); t.e("Unable to open %s", name); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; };
+  fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device;
+  bool second_file = false, f2_unopenable = false;
+  if (is_interleaved) {
+    cfg.mode = FQG_MODE_INTERLEAVED; t.e("Paired-end interleaved\n");
+    if (n1 == UNOPENABLE) return unopenable(a1);
+  } else if (is_paired && is_sorted && skip_names) {
+    cfg.mode = FQG_MODE_SORTED_PAIR; second_file = true;
+    t.e("-s option used: assuming that reads have the same ordering in both files\n");
+    if (n1 == UNOPENABLE) return unopenable(a1);
+    if (n2 == UNOPENABLE) return unopenable(a2);
+  } else if (!is_paired && skip_names) {
+    cfg.mode = FQG_MODE_SINGLE; t.e("Skipping check for duplicated read names\n");
+    if (n1 == UNOPENABLE) return unopenable(a1);
+  } else {
+    second_file = is_paired && !is_sorted;
+    cfg.mode = second_file ? FQG_MODE_INDEX_PAIR : FQG_MODE_INDEX;
+    if (n1 == UNOPENABLE) return unopenable(a1);
+  }
+  fqg_report rep;
+  try {
+    FqDevice* dev = fq_default_device(device);
+    {
+      FqEngine eng(cfg, dev);
+      feed_all(eng, 0, f1, n1, chunk_bytes);
+      if (second_file) {
+        bool open2 = true;
+        if (cfg.mode == FQG_MODE_INDEX_PAIR) {
+          /* the reference opens file 2 only after file 1 was indexed without error and holds reads */
+          fqg_report r1; eng.finish(&r1);
+          bool stop_after_1 = (r1.error.code != FQG_OK && r1.error.file == 0) || r1.n_index_entries == 0;
+          if (stop_after_1) open2 = false;
+          else if (n2 == UNOPENABLE) { open2 = false; f2_unopenable = true; }
+        }
+        if (open2) feed_all(eng, 1, f2, n2, chunk_bytes);
+      }
+      eng.finish(&rep);
+    }
+    delete dev;
+  } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
+  } catch (const std::exception& ex) {
+    fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
+    return strstr(ex.what(), "CUDA") ? (strstr(ex.what(), "no CUDA") ? FQG_ERR_NO_DEVICE : FQG_ERR_CUDA) : FQG_ERR_INTERNAL;
+  }
+  fqg_render_opts o; o.empty_ok = empty_ok; o.no_enc_ok = no_enc_ok; o.name1 = a1; o.name2 = a2;
+  render_run(t, rep, o, f2_unopenable);
+  if (t.rc < 0) return t.rc;
+  to_transcript(t, tr);
+  return 0;
+}

@@ -1,0 +1,129 @@
+/*
+ * fastq_gpu.h — C ABI of libfastq_gpu: the fastq_info hot path (record split, validation, read-name
+ * uniqueness, mate matching) of nunofonseca/fastq_utils 0.25.3 on one B200.
+ *
+ * The reference has no FFI; its boundary for this path is the C API of src/fastq.h:133-158 + src/hash.h:64-78
+ * as driven by the four loops of src/fastq_info.c.  A record-at-a-time call cannot be accelerated, so the
+ * library replaces the LOOP level and leaves argv parsing, zlib and exit() to the caller:
+ *
+ *   fqg_create / fqg_feed / fqg_finish   replace   fastq_new + the loop + the statistics it leaves behind
+ *        FQG_MODE_SINGLE       validate_single_fastq_file           src/fastq_info.c:155-176   (-r file)
+ *        FQG_MODE_INDEX        fastq_index_readnames                src/fastq.c:396-439        (file)
+ *        FQG_MODE_INDEX_PAIR   ... followed by main()'s mate loop   src/fastq_info.c:322-362   (file1 file2)
+ *        FQG_MODE_INTERLEAVED  validate_interleaved                 src/fastq_info.c:57-106    (file pe)
+ *        FQG_MODE_SORTED_PAIR  validate_paired_sorted_fastq_file    src/fastq_info.c:108-152   (-r -s file1 file2)
+ *   fqg_render                  replaces   the fprintf/PRINT_ERROR/exit sequence of src/fastq_info.c:190-396
+ *   fqg_fastq_info_mem          = main() on already-inflated streams (what the CLI and the parity tests call)
+ *   fqg_index_records           exposes the record index for reader-style tools (src/fastq_num_reads.c, fastq_truncate.c)
+ *
+ * Nothing here prints or exits.  All functions return 0 on success or a negative FQG_ERR_* (the caller maps
+ * these to the reference's SYS_INT_ERROR_EXIT_STATUS = 2, src/fastq.h:79).  A context is used by one host
+ * thread.  There is no CPU fallback: without a CUDA device fqg_create fails with FQG_ERR_NO_DEVICE.
+ */
+#ifndef FASTQ_GPU_H
+#define FASTQ_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQG_VERSION "0.25.3-b200.1"
+
+enum { FQG_MODE_SINGLE = 0, FQG_MODE_INDEX = 1, FQG_MODE_INDEX_PAIR = 2, FQG_MODE_INTERLEAVED = 3, FQG_MODE_SORTED_PAIR = 4 };
+enum { FQG_ERR_NO_DEVICE = -1, FQG_ERR_CUDA = -2, FQG_ERR_OOM = -3, FQG_ERR_USAGE = -4, FQG_ERR_INTERNAL = -5 };
+
+typedef struct fqg_ctx fqg_ctx;
+
+typedef struct {
+  int32_t mode;                  /* FQG_MODE_* */
+  int32_t device;                /* CUDA ordinal */
+  uint64_t index_capacity_hint;  /* expected number of read names (0 = grow on demand) */
+  uint32_t reserved[4];
+} fqg_config;
+
+/* statistics of one FASTQ_FILE as the reference holds them at the end of its loops (src/fastq.h:110-131) */
+typedef struct {
+  uint64_t n_records;   /* records read by fastq_read_entry                                   */
+  uint64_t num_rds;     /* the reference's counter (index loop counts twice, fastq.c:241,344) */
+  uint64_t min_rl, max_rl;       /* terminators included; 2500000 / 0 when nothing was read   */
+  uint64_t min_qual, max_qual;   /* sign-extension quirk applied (fastq.c:374)                */
+  int32_t sniff_format;          /* -1 not sniffed, 0 default, 1 casava 1.8, 2 integer, 3 no suffix */
+  int32_t color_space;           /* -1 not sniffed, 0 / 1                                     */
+} fqg_file_report;
+
+/* codes: SURVEY.md appendix B */
+enum {
+  FQG_OK = 0, FQG_E_TRUNC, FQG_E_TRUNC_PE, FQG_E_WRONGHDR, FQG_E_AT, FQG_E_IDLEN, FQG_E_BADCHAR, FQG_E_UT, FQG_E_SHORT,
+  FQG_E_PLUS, FQG_E_HDR2, FQG_E_LEN, FQG_E_LEN_CS, FQG_E_DUP, FQG_E_UNPAIRED, FQG_E_LEFTOVER, FQG_E_MISMATCH,
+  FQG_E_EOF1, FQG_E_EOF2, FQG_E_EMPTY, FQG_E_ENC
+};
+
+typedef struct {
+  int32_t code;          /* FQG_E_*; FQG_OK when every record passed                              */
+  int32_t file;          /* file whose loop raised it (0/1)                                       */
+  int32_t msg_file;      /* file NAME the reference prints (mate loop validates against file 1)   */
+  int32_t chr;           /* FQG_E_BADCHAR: the byte                                               */
+  uint64_t record;       /* index of the record inside `file`                                     */
+  uint64_t line;         /* the line number the reference prints                                  */
+  uint64_t a, b;         /* slen / qlen, read number, count of unpaired reads                      */
+  uint32_t hdr1_len, hdr2_len, name_len;
+  char hdr1[1024];       /* raw lines as C strings, for the messages that quote them              */
+  char hdr2[1024];
+  char name[1024];
+} fqg_error;
+
+typedef struct {
+  int32_t mode;
+  int32_t reserved;
+  fqg_file_report file[2];
+  uint64_t n_index_entries;      /* index->n_entries after the index loop                         */
+  uint64_t n_index_left;         /* ... after the mate loop                                       */
+  uint64_t index_mem;            /* bytes, as accumulated by fastq.c:609 (+8, fastq_info.c:293)   */
+  uint64_t median_rl;            /* median_rl(), fastq_info.c:39-55 (terminator included)         */
+  uint64_t reads_before_error[2];/* records fully processed per file before the first error (progress lines) */
+  fqg_error error;
+} fqg_report;
+
+int fqg_create(const fqg_config* cfg, fqg_ctx** out);
+void fqg_destroy(fqg_ctx* ctx);
+/* Hand `n` decompressed bytes of file `file` (0 or 1) to the device.  `last` marks the end of that file.
+ * INDEX_PAIR: file 1 may only be fed after file 0 was fed with last=1 (the reference's order). */
+int fqg_feed(fqg_ctx* ctx, int file, const void* host_bytes, size_t n, int last);
+/* Same, for bytes already in device memory; the buffer is borrowed until fqg_reset / fqg_destroy and must be
+ * followed by at least 64 readable bytes. */
+int fqg_feed_device(fqg_ctx* ctx, int file, const void* device_bytes, size_t n, int last);
+int fqg_finish(fqg_ctx* ctx, fqg_report* out);
+/* forget all input and results, keep the device workspace (bench loops) */
+int fqg_reset(fqg_ctx* ctx);
+const char* fqg_last_error(const fqg_ctx* ctx);
+/* kernels launched by this context so far */
+uint64_t fqg_launch_count(const fqg_ctx* ctx);
+/* device time (ms, CUDA events on the context's stream) spent between the first feed and the end of finish */
+double fqg_device_ms(const fqg_ctx* ctx);
+
+/* Record index of a device- or host-resident stream: writes up to cap byte offsets of record starts, returns
+ * the number of complete records in *n_records (fastq_num_reads / fastq_truncate style consumers). */
+int fqg_index_records(fqg_ctx* ctx, const void* host_bytes, size_t n, uint64_t* starts, size_t cap, uint64_t* n_records);
+
+/* ---- text: the reference's stdout / stderr for a finished run ---- */
+typedef struct {
+  int32_t empty_ok;      /* -e */
+  int32_t no_enc_ok;     /* -q */
+  const char* name1;     /* file operands as given on the command line */
+  const char* name2;
+} fqg_render_opts;
+typedef struct { int32_t rc; char* out; size_t out_len; char* err; size_t err_len; } fqg_transcript;
+int fqg_render(const fqg_report* rep, const fqg_render_opts* opts, fqg_transcript* t);
+void fqg_transcript_free(fqg_transcript* t);
+
+/* fastq_info's main() on inflated streams: argv as the reference receives it; n = (size_t)-1 means "could not
+ * be opened" (src/fastq.c:651-655).  chunk_bytes > 0 feeds the streams in pieces of that size. */
+int fqg_fastq_info_mem(int argc, const char** argv, const void* f1, size_t n1, const void* f2, size_t n2,
+                       int device, size_t chunk_bytes, fqg_transcript* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

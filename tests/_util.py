@@ -107,3 +107,61 @@ def ref_run(argv, cwd=GOLDEN):
     """Run the unmodified reference binary (oracle/_ref) → (rc, stdout, stderr)."""
     p = subprocess.run([REF_BIN] + list(argv), cwd=cwd, capture_output=True)
     return p.returncode, p.stdout.decode("latin-1"), p.stderr.decode("latin-1")
+
+
+# ---------------------------------------------------------------------------------------------- libfastq_gpu
+class _Transcript(ctypes.Structure):
+    _fields_ = [("rc", ctypes.c_int), ("out", ctypes.c_void_p), ("out_len", ctypes.c_size_t),
+                ("err", ctypes.c_void_p), ("err_len", ctypes.c_size_t)]
+
+
+_fqg = {}
+
+
+def fqg_lib(kind="gpu"):
+    """kind='gpu': the product, fastq_utils_b200/libfastq_gpu.so (needs a CUDA device to create a context).
+    kind='sim': tests/sim/libfastq_sim.so — same host code over a sequential stand-in device (host-logic tests only)."""
+    if kind not in _fqg:
+        if kind == "sim":
+            d = os.path.join(ROOT, "tests", "sim")
+            subprocess.check_call(["make", "-C", d], stdout=subprocess.DEVNULL)
+            so = os.path.join(d, "libfastq_sim.so")
+        else:
+            so = os.path.join(ROOT, "fastq_utils_b200", "libfastq_gpu.so")
+        lib = ctypes.CDLL(so)
+        lib.fqg_fastq_info_mem.restype = ctypes.c_int
+        lib.fqg_fastq_info_mem.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, ctypes.c_size_t,
+                                           ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_size_t,
+                                           ctypes.POINTER(_Transcript)]
+        lib.fqg_transcript_free.argtypes = [ctypes.POINTER(_Transcript)]
+        _fqg[kind] = lib
+    return _fqg[kind]
+
+
+def fqg_run(argv, data1=None, data2=None, chunk=0, kind="gpu"):
+    """fastq_info through the C ABI on in-memory streams → (rc, stdout, stderr) as latin-1 text."""
+    lib = fqg_lib(kind)
+    full = [b"fastq_info"] + [a.encode("latin-1") for a in argv]
+    arr = (ctypes.c_char_p * (len(full) + 1))(*full, None)
+    tr = _Transcript()
+    unopenable = ctypes.c_size_t(-1).value
+    st = lib.fqg_fastq_info_mem(len(full), arr, data1, len(data1) if data1 is not None else unopenable,
+                                data2, len(data2) if data2 is not None else unopenable, 0, chunk, ctypes.byref(tr))
+    if st != 0:
+        raise RuntimeError(f"fqg_fastq_info_mem failed with status {st}")
+    out = ctypes.string_at(tr.out, tr.out_len).decode("latin-1")
+    err = ctypes.string_at(tr.err, tr.err_len).decode("latin-1")
+    rc = tr.rc
+    lib.fqg_transcript_free(ctypes.byref(tr))
+    return rc, out, err
+
+
+def fqg_run_files(argv, cwd=GOLDEN, chunk=0, kind="gpu"):
+    pos = positional_files(argv)
+    datas = []
+    for p in pos[:2]:
+        path = os.path.join(cwd, p)
+        datas.append(read_stream(path) if os.path.isfile(path) else None)
+    while len(datas) < 2:
+        datas.append(None)
+    return fqg_run(argv, datas[0], datas[1], chunk=chunk, kind=kind)

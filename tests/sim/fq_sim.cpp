@@ -1,0 +1,176 @@
+/*
+ * tests/sim/fq_sim.cpp — TEST INFRASTRUCTURE ONLY.  A sequential stand-in for FqCudaDevice so that the host
+ * engine (chunking, bridging, event ordering, report, rendering) and the shared per-record semantics
+ * (fq_record.h) can be exercised without a GPU.  Built into tests/sim/libfastq_sim.so by tests/sim/Makefile;
+ * never linked into libfastq_gpu.so and never used by bench.py or the -m gpu tests.
+ */
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include "../../fastq_utils_b200/csrc/fq_device.h"
+#include "../../fastq_utils_b200/csrc/fq_record.h"
+
+namespace {
+
+class FqSimDevice : public FqDevice {
+ public:
+  const char* name() const override { return "sim"; }
+  void* alloc(size_t n) override { void* p = calloc(1, n + 64); if (!p) throw std::bad_alloc(); return p; }
+  void release(void* p) override { free(p); }
+  void upload(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
+  void download(void* d, const void* s, size_t n) override { memcpy(d, s, n); }
+  void copy(void* d, const void* s, size_t n) override { memmove(d, s, n); }
+  void fill(void* d, int b, size_t n) override { memset(d, b, n); }
+  void sync() override {}
+  void timer_start() override {}
+  double timer_stop_ms() override { return 0.0; }
+  unsigned long long launches() const override { return n_launch_; }
+
+  void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) override {
+    n_launch_++;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; i++)
+      if (data[i] == '\n') { if (k < cap) line_end[k] = i + 1; k++; }
+    if (virtual_end && n > 0 && data[n - 1] != '\n') { if (k < cap) line_end[k] = n; k++; }
+    out2[0] = k; out2[1] = k > cap;
+  }
+  void find_overlong(const uint32_t* line_end, uint32_t q, uint32_t j0, uint32_t nlines, uint32_t n, int tail_from_n, uint32_t* out) override {
+    n_launch_++;
+    for (uint32_t i = 0; i <= nlines; i++) {
+      uint32_t start = i == 0 ? q : line_end[j0 + i - 1];
+      uint32_t end;
+      if (i < nlines) end = line_end[j0 + i];
+      else { if (!tail_from_n) break; end = n; }
+      uint32_t lim = (i & 1) == 0 ? FQ_MAX_LABEL_LENGTH : FQ_MAX_READ_LENGTH;
+      if (end - start >= lim) { if (j0 + i < *out) *out = j0 + i; break; }
+    }
+  }
+  void split_serial(const uint8_t* data, uint32_t n, uint32_t q, int is_eof, FqLine* lines4, uint32_t* out3) override {
+    n_launch_++;
+    uint32_t p = q, got = 0, lfs = 0;
+    for (int i = 0; i < 4; i++) {
+      uint32_t maxb = ((i & 1) == 0 ? FQ_MAX_LABEL_LENGTH : FQ_MAX_READ_LENGTH) - 1, k = 0;
+      bool lf = false;
+      while (k < maxb && p + k < n) { k++; if (data[p + k - 1] == '\n') { lf = true; break; } }
+      bool complete = lf || k == maxb || (is_eof && k > 0);
+      if (!complete) break;
+      lines4[i].off = p; lines4[i].len = k; p += k; got++; lfs += lf;
+    }
+    for (uint32_t i = got; i < 4; i++) { lines4[i].off = p; lines4[i].len = 0; }
+    out3[0] = p; out3[1] = got; out3[2] = lfs;
+  }
+  void sniff(const uint8_t* data, FqLine hdr1, FqLine seq, int32_t* out2) override {
+    n_launch_++;
+    uint32_t cl0 = fq_cstrlen(data, hdr1.off, hdr1.len), cl1 = fq_cstrlen(data, seq.off, seq.len);
+    out2[0] = fq_sniff_format(data + hdr1.off + 1, cl0 >= 1 ? cl0 - 1 : 0);
+    out2[1] = fq_sniff_colorspace(data + seq.off, cl1);
+  }
+  static void lines_of(const FqRecordsArgs& a, uint32_t k, FqLine L[4]) {
+    if (a.lines) { memcpy(L, a.lines + 4 * k, 4 * sizeof(FqLine)); return; }
+    uint32_t j = a.j0 + 4 * k;
+    uint32_t s = k == 0 ? a.q : a.line_end[j - 1];
+    for (int i = 0; i < 4; i++) { uint32_t e = a.line_end[j + i]; L[i].off = s; L[i].len = e - s; s = e; }
+  }
+  void records(const FqRecordsArgs& a) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < a.nrec; k++) {
+      FqLine L[4]; lines_of(a, k, L);
+      FqRecOut o; fq_check_record(a.data, L, a.cx, &o);
+      uint64_t g = a.g0 + k;
+      uint64_t key = fq_record_key(a.cx.loop, g, a.step_base, o);
+      if (key < *a.key) *a.key = key;
+      bool named = fq_record_has_name(a.cx.loop, o);
+      if (a.names) {
+        a.names[k].off = o.name_off; a.names[k].len = o.name_len;
+        a.names[k].hash = named ? fq_hash_name(a.data + o.name_off, o.name_len, a.cx.seed) : FQ_HASH_SKIP;
+      }
+      if (a.cx.loop == FQ_LOOP_INDEX && named) { a.stats->n_names++; a.stats->mem_sum += o.mem_len; }
+      /* statistics are only ever reported when every record was clean, so only clean records are counted */
+      if (o.flags || o.vrank != FQ_V_OK) continue;
+      uint32_t w = a.cx.weight;
+      a.stats->num_rds += w;
+      if (o.read_len < a.stats_range->min_rl) a.stats_range->min_rl = o.read_len;
+      if (o.read_len > a.stats_range->max_rl) a.stats_range->max_rl = o.read_len;
+      a.hist[o.read_len] += w;
+      if (o.qmin <= o.qmax) {
+        if (o.qmin < a.stats_range->min_q) a.stats_range->min_q = o.qmin;
+        if (o.qmax > a.stats_range->max_q) a.stats_range->max_q = o.qmax;
+      }
+    }
+  }
+  static const uint8_t* name_of(const FqDirEntry* dir, uint32_t nd, uint64_t g, uint32_t* len) {
+    uint32_t lo = 0, hi = nd;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (dir[mid].g0 <= g) lo = mid; else hi = mid; }
+    const FqName& nm = dir[lo].names[g - dir[lo].g0];
+    *len = nm.len;
+    return dir[lo].data + nm.off;
+  }
+  void index_insert(const FqTableArgs& a) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < a.nrec; k++) {
+      const FqName& nm = a.names[k];
+      if (nm.hash == FQ_HASH_SKIP) continue;
+      uint64_t g = a.g0 + k, i = nm.hash & a.mask, probes = 0;
+      for (;; i = (i + 1) & a.mask) {
+        if (++probes > a.mask) { a.counters[2] = 1; break; }
+        FqSlot& s = a.slots[i];
+        if (s.hash == FQ_HASH_EMPTY) { s.hash = nm.hash; s.idx1 = g; break; }
+        if (s.hash != nm.hash) continue;
+        uint64_t old = s.idx1; if (g < old) s.idx1 = g;
+        uint32_t ol; const uint8_t* on = name_of(a.dir1, a.ndir1, old, &ol);
+        if (ol == nm.len && fq_bytes_equal(on, a.data + nm.off, nm.len)) {
+          uint64_t later = old > g ? old : g;
+          uint64_t key = FQ_KEY(a.step_base + later, FQ_R_NAME);
+          if (key < *a.key) *a.key = key;
+        } else a.counters[0]++;
+        break;
+      }
+    }
+  }
+  void mate_claim(const FqTableArgs& a) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < a.nrec; k++) {
+      const FqName& nm = a.names[k];
+      if (nm.hash == FQ_HASH_SKIP) continue;
+      uint64_t g = a.g0 + k, i = nm.hash & a.mask, probes = 0;
+      for (;; i = (i + 1) & a.mask) {
+        uint64_t unpaired = FQ_KEY_NONE;
+        if (++probes > a.mask + 1) { unpaired = g; }
+        else {
+          FqSlot& s = a.slots[i];
+          if (s.hash == FQ_HASH_EMPTY) unpaired = g;
+          else if (s.hash != nm.hash) continue;
+          else {
+            uint32_t ol; const uint8_t* on = name_of(a.dir1, a.ndir1, s.idx1, &ol);
+            if (!(ol == nm.len && fq_bytes_equal(on, a.data + nm.off, nm.len))) { a.counters[0]++; break; }
+            uint64_t old = s.claim2; if (g < old) s.claim2 = g;
+            if (old == FQ_IDX_NONE) a.counters[1]++;
+            else unpaired = old > g ? old : g;
+          }
+        }
+        if (unpaired != FQ_KEY_NONE) { uint64_t key = FQ_KEY(a.step_base + unpaired, FQ_R_NAME); if (key < *a.key) *a.key = key; }
+        break;
+      }
+    }
+  }
+  void pair_compare(const FqPairArgs& a) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < a.npairs; k++) {
+      const FqName& x = a.a[(size_t)k * a.stride_a]; const FqName& y = a.b[(size_t)k * a.stride_b];
+      if (x.hash == FQ_HASH_SKIP || y.hash == FQ_HASH_SKIP) continue;
+      bool same = x.hash == y.hash && x.len == y.len && fq_bytes_equal(a.da + x.off, a.db + y.off, x.len);
+      if (!same) { uint64_t key = FQ_KEY(a.p0 + k, a.rank); if (key < *a.key) *a.key = key; }
+    }
+  }
+  void explain(const uint8_t* data, const FqLine* lines4, const FqRecCtx& cx, FqRecOut* out) override {
+    n_launch_++;
+    fq_check_record(data, lines4, cx, out);
+  }
+
+ private:
+  unsigned long long n_launch_ = 0;
+};
+
+}  // namespace
+
+FqDevice* fq_default_device(int) { return new FqSimDevice(); }
