@@ -1,0 +1,200 @@
+"""ctypes binding of include/fastq_gpu.h.  Mirrors the reference's fastq_info entry points (src/fastq_info.c:190-396):
+`fastq_info(argv, ...)` is main() on inflated streams, `FastqInfo` is the create / feed / finish loop-level API."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfastq_gpu.so")
+
+MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED, MODE_SORTED_PAIR = range(5)
+KERNEL_CLASSES = ["scan", "records", "index", "mate", "pair", "other"]
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("device", ctypes.c_int32), ("index_capacity_hint", ctypes.c_uint64),
+                ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 3)]
+
+
+class FileReport(ctypes.Structure):
+    _fields_ = [("n_records", ctypes.c_uint64), ("num_rds", ctypes.c_uint64), ("min_rl", ctypes.c_uint64),
+                ("max_rl", ctypes.c_uint64), ("min_qual", ctypes.c_uint64), ("max_qual", ctypes.c_uint64),
+                ("sniff_format", ctypes.c_int32), ("color_space", ctypes.c_int32)]
+
+
+class Error(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_int32), ("file", ctypes.c_int32), ("msg_file", ctypes.c_int32), ("chr", ctypes.c_int32),
+                ("record", ctypes.c_uint64), ("line", ctypes.c_uint64), ("a", ctypes.c_uint64), ("b", ctypes.c_uint64),
+                ("hdr1_len", ctypes.c_uint32), ("hdr2_len", ctypes.c_uint32), ("name_len", ctypes.c_uint32),
+                ("hdr1", ctypes.c_char * 1024), ("hdr2", ctypes.c_char * 1024), ("name", ctypes.c_char * 1024)]
+
+
+class Report(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("reserved", ctypes.c_int32), ("file", FileReport * 2),
+                ("n_index_entries", ctypes.c_uint64), ("n_index_left", ctypes.c_uint64), ("index_mem", ctypes.c_uint64),
+                ("median_rl", ctypes.c_uint64), ("reads_before_error", ctypes.c_uint64 * 2), ("error", Error)]
+
+
+class RenderOpts(ctypes.Structure):
+    _fields_ = [("empty_ok", ctypes.c_int32), ("no_enc_ok", ctypes.c_int32), ("name1", ctypes.c_char_p), ("name2", ctypes.c_char_p)]
+
+
+class Transcript(ctypes.Structure):
+    _fields_ = [("rc", ctypes.c_int32), ("out", ctypes.c_void_p), ("out_len", ctypes.c_size_t),
+                ("err", ctypes.c_void_p), ("err_len", ctypes.c_size_t)]
+
+
+class KernelStat(ctypes.Structure):
+    _fields_ = [("ms", ctypes.c_double), ("launches", ctypes.c_uint64), ("bytes", ctypes.c_uint64), ("items", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libfastq_gpu.so (built in-tree by __graft_entry__.build() / csrc/Makefile).  Fails loudly when missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise RuntimeError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+        L = ctypes.CDLL(_SO)
+        vp, u64, sz, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int
+        L.fqg_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(vp)]
+        L.fqg_destroy.argtypes = [vp]
+        L.fqg_destroy.restype = None
+        L.fqg_feed.argtypes = [vp, ci, vp, sz, ci]
+        L.fqg_feed_device.argtypes = [vp, ci, vp, sz, ci]
+        L.fqg_finish.argtypes = [vp, ctypes.POINTER(Report)]
+        L.fqg_reset.argtypes = [vp]
+        L.fqg_last_error.argtypes = [vp]
+        L.fqg_last_error.restype = ctypes.c_char_p
+        L.fqg_launch_count.argtypes = [vp]
+        L.fqg_launch_count.restype = u64
+        L.fqg_device_ms.argtypes = [vp]
+        L.fqg_device_ms.restype = ctypes.c_double
+        L.fqg_index_records.argtypes = [vp, vp, sz, ctypes.POINTER(u64), sz, ctypes.POINTER(u64)]
+        L.fqg_render.argtypes = [ctypes.POINTER(Report), ctypes.POINTER(RenderOpts), ctypes.POINTER(Transcript)]
+        L.fqg_transcript_free.argtypes = [ctypes.POINTER(Transcript)]
+        L.fqg_transcript_free.restype = None
+        L.fqg_fastq_info_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, vp, sz, ci, sz, ctypes.POINTER(Transcript)]
+        L.fqg_kernel_stats.argtypes = [vp, ci, ctypes.POINTER(KernelStat)]
+        L.fqg_kernel_stats_reset.argtypes = [vp]
+        L.fqg_synth_illumina.argtypes = [vp, u64, u64, u64, ci, u64, vp]
+        L.fqg_synth_longreads.argtypes = [vp, vp, u64, u64, u64, vp]
+        _lib = L
+    return _lib
+
+
+def _check(ctx, st, what):
+    if st != 0:
+        msg = lib().fqg_last_error(ctx).decode("latin-1") if ctx else ""
+        raise RuntimeError(f"{what} failed with status {st}: {msg}")
+
+
+def _take(tr):
+    out = ctypes.string_at(tr.out, tr.out_len).decode("latin-1")
+    err = ctypes.string_at(tr.err, tr.err_len).decode("latin-1")
+    rc = tr.rc
+    lib().fqg_transcript_free(ctypes.byref(tr))
+    return rc, out, err
+
+
+def fastq_info(argv, data1=None, data2=None, chunk=0, device=0):
+    """`fastq_info argv...` on in-memory inflated streams → (exit status, stdout, stderr).  None = file could not be opened."""
+    full = [b"fastq_info"] + [a.encode("latin-1") if isinstance(a, str) else a for a in argv]
+    arr = (ctypes.c_char_p * (len(full) + 1))(*full, None)
+    tr = Transcript()
+    un = ctypes.c_size_t(-1).value
+    st = lib().fqg_fastq_info_mem(len(full), arr, data1, len(data1) if data1 is not None else un,
+                                  data2, len(data2) if data2 is not None else un, device, chunk, ctypes.byref(tr))
+    if st != 0:
+        raise RuntimeError(f"fqg_fastq_info_mem failed with status {st}")
+    return _take(tr)
+
+
+class FastqInfo:
+    """One validation run: feed the inflated bytes of the file(s), then finish() for the report."""
+
+    def __init__(self, mode, device=0, index_capacity_hint=0, flags=0):
+        cfg = Config(mode=mode, device=device, index_capacity_hint=index_capacity_hint, flags=flags)
+        self._ctx = ctypes.c_void_p()
+        st = lib().fqg_create(ctypes.byref(cfg), ctypes.byref(self._ctx))
+        if st != 0:
+            raise RuntimeError(f"fqg_create failed with status {st} (-1 = no CUDA device; there is no CPU fallback)")
+        self.mode = mode
+
+    def close(self):
+        if self._ctx:
+            lib().fqg_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def feed(self, file, data, last=True):
+        """Host bytes (bytes / bytearray / anything exposing a pointer via torch/numpy `data_ptr`-like int tuple (ptr, n))."""
+        if isinstance(data, tuple):
+            ptr, n = data
+        else:
+            n = len(data)
+            ptr = ctypes.cast(ctypes.c_char_p(bytes(data)) if not isinstance(data, bytes) else ctypes.c_char_p(data), ctypes.c_void_p)
+        _check(self._ctx, lib().fqg_feed(self._ctx, file, ptr, n, 1 if last else 0), "fqg_feed")
+
+    def feed_device(self, file, ptr, n, last=True):
+        _check(self._ctx, lib().fqg_feed_device(self._ctx, file, ctypes.c_void_p(ptr), n, 1 if last else 0), "fqg_feed_device")
+
+    def finish(self):
+        rep = Report()
+        _check(self._ctx, lib().fqg_finish(self._ctx, ctypes.byref(rep)), "fqg_finish")
+        return rep
+
+    def reset(self):
+        _check(self._ctx, lib().fqg_reset(self._ctx), "fqg_reset")
+
+    def render(self, rep, name1, name2=None, empty_ok=False, no_enc_ok=False):
+        o = RenderOpts(empty_ok=int(empty_ok), no_enc_ok=int(no_enc_ok), name1=name1.encode("latin-1"),
+                       name2=name2.encode("latin-1") if name2 is not None else None)
+        tr = Transcript()
+        _check(self._ctx, lib().fqg_render(ctypes.byref(rep), ctypes.byref(o), ctypes.byref(tr)), "fqg_render")
+        return _take(tr)
+
+    def launch_count(self):
+        return int(lib().fqg_launch_count(self._ctx))
+
+    def device_ms(self):
+        return float(lib().fqg_device_ms(self._ctx))
+
+    def kernel_stats(self, reset=False):
+        out = {}
+        for i, name in enumerate(KERNEL_CLASSES):
+            ks = KernelStat()
+            _check(self._ctx, lib().fqg_kernel_stats(self._ctx, i, ctypes.byref(ks)), "fqg_kernel_stats")
+            out[name] = {"ms": ks.ms, "launches": int(ks.launches), "bytes": int(ks.bytes), "items": int(ks.items)}
+        if reset:
+            lib().fqg_kernel_stats_reset(self._ctx)
+        return out
+
+    def index_records(self, data, cap=0):
+        n = ctypes.c_uint64()
+        starts = (ctypes.c_uint64 * max(cap, 1))()
+        _check(self._ctx, lib().fqg_index_records(self._ctx, data, len(data), starts, cap, ctypes.byref(n)), "fqg_index_records")
+        return int(n.value), list(starts[:min(cap, n.value)])
+
+
+def illumina_record_bytes():
+    return int(lib().fqg_synth_illumina_record_bytes())
+
+
+def synth_illumina(tensor, first_record, n_records, seed=42, mate=1, perm_window=0, stream=0):
+    """Fill a CUDA uint8 tensor (≥ n_records*359 bytes) with synthetic Illumina records first_record..+n_records."""
+    st = lib().fqg_synth_illumina(ctypes.c_void_p(tensor.data_ptr()), first_record, n_records, seed, mate, perm_window, ctypes.c_void_p(stream))
+    if st != 0:
+        raise RuntimeError(f"fqg_synth_illumina failed with status {st}")
+
+
+def synth_longreads(tensor, offsets, first_record, n_records, seed=7, stream=0):
+    st = lib().fqg_synth_longreads(ctypes.c_void_p(tensor.data_ptr()), ctypes.c_void_p(offsets.data_ptr()), first_record, n_records, seed, ctypes.c_void_p(stream))
+    if st != 0:
+        raise RuntimeError(f"fqg_synth_longreads failed with status {st}")

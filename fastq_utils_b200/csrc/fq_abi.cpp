@@ -78,3 +78,12 @@ extern "C" int fqg_index_records(fqg_ctx* c, const void* host_bytes, size_t n, u
   if (!c || (!host_bytes && n) || !n_records) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->eng->index_records(host_bytes, n, starts, cap, n_records))
 }
+
+extern "C" int fqg_kernel_stats(fqg_ctx* c, int which, fqg_kernel_stat* out) {
+  if (!c || !out) return FQG_ERR_USAGE;
+  FQG_GUARD(c, { if (!c->dev->kernel_stat(which, &out->ms, &out->launches, &out->bytes, &out->items)) throw std::runtime_error("fqg_kernel_stats: unknown kernel class"); })
+}
+extern "C" int fqg_kernel_stats_reset(fqg_ctx* c) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->dev->kernel_stats_reset())
+}

@@ -1,0 +1,546 @@
+/*
+ * fq_cuda.cu — the sm_100a kernels of libfastq_gpu and the FqDevice that launches them on one CUDA stream.
+ *
+ *   K1  fq_scan_kernel          line index: coalesced 128-bit loads, SWAR newline masks, warp-shuffle prefix sums and a
+ *                               single-pass decoupled look-back across tiles (replaces the 4×gzgets splitter, src/fastq.c:245-261)
+ *   K1b fq_overlong_kernel      first line that gzgets would split (src/fastq.h:30-37 limits)
+ *   K2  fq_records_kernel       reader flags, validation, statistics, event key, name hash (src/fastq.c:300-392, :442-516, :97-110)
+ *   K3  fq_index_insert_kernel  open-addressing name index: 64-bit hash, atomicCAS claim, atomicMin of the record index,
+ *                               exact byte compare on equal hashes (replaces src/hash.c + src/fastq.c:529-611)
+ *   K4  fq_mate_claim_kernel    lookup-then-delete of the mate loop as a claim with atomicMin (src/fastq_info.c:333-350)
+ *       fq_pair_compare_kernel  interleaved / sorted pair name equality (src/fastq_info.c:86-91, :133-138)
+ *   single-thread helpers: gzgets emulation for over-long lines, first-record sniffers, error details.
+ *
+ * HBM-bound byte/integer work: no tensor cores.  Event ordering (first error wins) is a 64-bit atomicMin.
+ */
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/fastq_gpu.h"
+#include "fq_device.h"
+#include "fq_record.h"
+
+#define FQ_CUDA_CHECK(call)                                                                            \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      std::string m_ = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+      if (e_ == cudaErrorMemoryAllocation) m_ += " (out of memory)";                                   \
+      throw std::runtime_error(m_);                                                                    \
+    }                                                                                                  \
+  } while (0)
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int kSMs = 148;
+
+/* ------------------------------------------------------------------------------------------------ K1: line index */
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_WARP_BYTES = 2048;                 /* 4 rows of 32 lanes × 16 B */
+constexpr int SCAN_TILE = SCAN_WARPS * SCAN_WARP_BYTES; /* 16 KiB per CTA */
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_VALUE = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+/* 16 bytes → 16-bit mask, bit b set iff byte b is LF.  Two words are merged before one multiply gathers their flag
+ * bits: flags of word A sit at bits 0,8,16,24 and of word B at 4,12,20,28; × (1+2^7+2^14+2^21) lines them up in bits 21..28. */
+__device__ __forceinline__ uint32_t lf_mask16(uint4 v) {
+  uint32_t z0 = fq_zero_bytes(v.x ^ 0x0A0A0A0Au), z1 = fq_zero_bytes(v.y ^ 0x0A0A0A0Au);
+  uint32_t z2 = fq_zero_bytes(v.z ^ 0x0A0A0A0Au), z3 = fq_zero_bytes(v.w ^ 0x0A0A0A0Au);
+  uint32_t lo = (((z0 >> 7) | (z1 >> 3)) * 0x00204081u) >> 21;
+  uint32_t hi = (((z2 >> 7) | (z3 >> 3)) * 0x00204081u) >> 21;
+  return (lo & 0xFFu) | ((hi & 0xFFu) << 8);
+}
+__device__ __forceinline__ unsigned long long ld_volatile64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+fq_scan_kernel(const uint8_t* __restrict__ data, uint32_t n, int virtual_end, uint32_t* __restrict__ line_end, uint32_t cap,
+               unsigned long long* tile_state, uint32_t* ticket, uint32_t ntiles, uint32_t* out2) {
+  __shared__ uint32_t s_tile, s_warp_tot[SCAN_WARPS], s_warp_base[SCAN_WARPS], s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u); /* tiles are claimed in order: look-back never waits on an unscheduled CTA */
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t wbase = tile * (uint32_t)SCAN_TILE + warp * SCAN_WARP_BYTES + lane * 16;
+  uint32_t m[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint32_t off = wbase + i * 512;
+    m[i] = 0;
+    if (off < n) { /* the allocation is readable 64 bytes past n */
+      m[i] = lf_mask16(ld_stream16(data + off));
+      if (n - off < 16) m[i] &= (1u << (n - off)) - 1u;
+    }
+  }
+  /* inclusive prefix over the warp's four rows, two 16-bit counters per register */
+  uint32_t c01 = __popc(m[0]) | (__popc(m[1]) << 16), c23 = __popc(m[2]) | (__popc(m[3]) << 16);
+  uint32_t p01 = c01, p23 = c23;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t a = __shfl_up_sync(FULL, p01, d), b = __shfl_up_sync(FULL, p23, d);
+    if (lane >= d) { p01 += a; p23 += b; }
+  }
+  uint32_t t01 = __shfl_sync(FULL, p01, 31), t23 = __shfl_sync(FULL, p23, 31);
+  uint32_t rowbase[4] = {0, t01 & 0xFFFFu, (t01 & 0xFFFFu) + (t01 >> 16), (t01 & 0xFFFFu) + (t01 >> 16) + (t23 & 0xFFFFu)};
+  uint32_t wtot = rowbase[3] + (t23 >> 16);
+  if (lane == 0) s_warp_tot[warp] = wtot;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = lane < SCAN_WARPS ? s_warp_tot[lane] : 0, incl = v;
+#pragma unroll
+    for (int d = 1; d < SCAN_WARPS; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += a; }
+    if (lane < SCAN_WARPS) s_warp_base[lane] = incl - v;
+    uint32_t total = __shfl_sync(FULL, incl, SCAN_WARPS - 1);
+    /* decoupled look-back: publish this tile's count, then add up the predecessors' */
+    unsigned long long acc = 0;
+    if (tile > 0) {
+      if (lane == 0) st_volatile64(tile_state + tile, ST_AGG | total);
+      int look = (int)tile - 1;
+      for (;;) {
+        int idx = look - lane;
+        unsigned long long v64 = idx >= 0 ? ld_volatile64(tile_state + idx) : ST_INCL;
+        while (__any_sync(FULL, (v64 >> 62) == 0)) { if ((v64 >> 62) == 0) v64 = ld_volatile64(tile_state + idx); }
+        uint32_t incl_mask = __ballot_sync(FULL, (v64 >> 62) == 2);
+        int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+        unsigned long long part = lane <= first ? (v64 & ST_VALUE) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+        acc += part;
+        if (incl_mask) break;
+        look -= 32;
+      }
+    }
+    if (lane == 0) {
+      st_volatile64(tile_state + tile, ST_INCL | (acc + total));
+      s_base = (uint32_t)acc;
+      if (tile == ntiles - 1) {
+        uint32_t cnt = (uint32_t)acc + total;
+        if (virtual_end && n > 0 && data[n - 1] != '\n') { if (cnt < cap) line_end[cnt] = n; cnt++; }
+        out2[0] = cnt; out2[1] = cnt > cap ? 1u : 0u;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t base = s_base + s_warp_base[warp];
+  const uint32_t incl[4] = {p01 & 0xFFFFu, p01 >> 16, p23 & 0xFFFFu, p23 >> 16};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint32_t mm = m[i];
+    if (mm) {
+      uint32_t rank = base + rowbase[i] + incl[i] - __popc(mm);
+      uint32_t off = wbase + i * 512;
+      while (mm) {
+        uint32_t b = __ffs(mm) - 1; mm &= mm - 1;
+        if (rank < cap) line_end[rank] = off + b + 1;
+        rank++;
+      }
+    }
+  }
+}
+
+__global__ void fq_overlong_kernel(const uint32_t* __restrict__ line_end, uint32_t q, uint32_t j0, uint32_t nlines, uint32_t n,
+                                   int tail_from_n, uint32_t* out) {
+  uint32_t total = nlines + (tail_from_n ? 1u : 0u);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t start = i == 0 ? q : line_end[j0 + i - 1];
+    uint32_t end = i < nlines ? line_end[j0 + i] : n;
+    uint32_t lim = (i & 1u) == 0 ? FQ_MAX_LABEL_LENGTH : FQ_MAX_READ_LENGTH;
+    if (end - start >= lim) atomicMin(out, j0 + i);
+  }
+}
+
+/* gzgets emulation (zlib: at most max-1 bytes, stops after LF) for the four lines of one record */
+__global__ void fq_split_serial_kernel(const uint8_t* data, uint32_t n, uint32_t q, int is_eof, FqLine* lines4, uint32_t* out3) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint32_t p = q, got = 0, lfs = 0;
+  for (int i = 0; i < 4; i++) {
+    uint32_t maxb = ((i & 1) == 0 ? FQ_MAX_LABEL_LENGTH : FQ_MAX_READ_LENGTH) - 1, k = 0;
+    bool lf = false;
+    while (k < maxb && p + k < n) { k++; if (data[p + k - 1] == '\n') { lf = true; break; } }
+    bool complete = lf || k == maxb || (is_eof && k > 0);
+    if (!complete) break;
+    lines4[i].off = p; lines4[i].len = k; p += k; got++; lfs += lf ? 1 : 0;
+  }
+  for (uint32_t i = got; i < 4; i++) { lines4[i].off = p; lines4[i].len = 0; }
+  out3[0] = p; out3[1] = got; out3[2] = lfs;
+}
+
+__global__ void fq_sniff_kernel(const uint8_t* data, FqLine hdr1, FqLine seq, int32_t* out2) {
+  if (threadIdx.x || blockIdx.x) return;
+  uint32_t cl0 = fq_cstrlen(data, hdr1.off, hdr1.len), cl1 = fq_cstrlen(data, seq.off, seq.len);
+  out2[0] = fq_sniff_format(data + hdr1.off + 1, cl0 >= 1 ? cl0 - 1 : 0);
+  out2[1] = fq_sniff_colorspace(data + seq.off, cl1);
+}
+
+__global__ void fq_explain_kernel(const uint8_t* data, FqLine l0, FqLine l1, FqLine l2, FqLine l3, FqRecCtx cx, FqRecOut* out) {
+  if (threadIdx.x || blockIdx.x) return;
+  FqLine L[4] = {l0, l1, l2, l3};
+  FqRecOut o;
+  fq_check_record(data, L, cx, &o);
+  *out = o;
+}
+
+/* ------------------------------------------------------------------------------------------------ K2: records */
+constexpr int REC_THREADS = 128;
+
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { unsigned long long o = __shfl_xor_sync(FULL, v, d); v = o < v ? o : v; }
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+/* add `count` to hist[len] for every lane with count > 0, one atomic per distinct length in the warp */
+__device__ __forceinline__ void hist_flush(unsigned long long* hist, uint32_t len, uint32_t count) {
+  unsigned active = __ballot_sync(FULL, count > 0);
+  if (!active) return;
+  if (count > 0) {
+    unsigned peers = __match_any_sync(active, len);
+    unsigned long long sum = 0;
+    for (unsigned p = peers; p; p &= p - 1) sum += __shfl_sync(peers, count, __ffs(p) - 1);
+    if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(hist + len, sum);
+  }
+}
+
+struct RecParams {
+  const uint8_t* data; const uint32_t* line_end; const FqLine* lines;
+  uint32_t q, j0, nrec; unsigned long long g0, step_base;
+  FqRecCtx cx;
+  FqStats* stats; FqStats* stats_range; unsigned long long* hist; unsigned long long* key; FqName* names;
+};
+
+__global__ void __launch_bounds__(REC_THREADS)
+fq_records_kernel(const RecParams P) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long my_key = FQ_KEY_NONE, my_rds = 0, my_names = 0, my_mem = 0;
+  uint32_t mn_rl = 0xFFFFFFFFu, mx_rl = 0, mn_q = 255, mx_q = 0;
+  uint32_t run_len = 0, run_cnt = 0; /* run-length cache for the histogram: reads of one length are the common case */
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < P.nrec; base += stride) {
+    uint32_t k = base + threadIdx.x;
+    bool valid = k < P.nrec;
+    uint32_t flush_len = 0, flush_cnt = 0;
+    if (valid) {
+      FqLine L[4];
+      if (P.lines) { for (int i = 0; i < 4; i++) L[i] = P.lines[4 * (size_t)k + i]; }
+      else {
+        uint32_t j = P.j0 + 4 * k;
+        uint32_t s = k == 0 ? P.q : P.line_end[j - 1];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { uint32_t e = P.line_end[j + i]; L[i].off = s; L[i].len = e - s; s = e; }
+      }
+      FqRecOut o;
+      fq_check_record(P.data, L, P.cx, &o);
+      unsigned long long g = P.g0 + k;
+      unsigned long long key = fq_record_key(P.cx.loop, g, P.step_base, o);
+      if (key < my_key) my_key = key;
+      bool named = fq_record_has_name(P.cx.loop, o);
+      if (P.names) {
+        FqName nm; nm.off = o.name_off; nm.len = o.name_len;
+        nm.hash = named ? fq_hash_name(P.data + o.name_off, o.name_len, P.cx.seed) : FQ_HASH_SKIP;
+        P.names[k] = nm;
+      }
+      if (P.cx.loop == FQ_LOOP_INDEX && named) { my_names++; my_mem += o.mem_len; }
+      if (!o.flags && o.vrank == FQ_V_OK) { /* statistics are only reported when every record is clean */
+        my_rds += P.cx.weight;
+        mn_rl = min(mn_rl, o.read_len); mx_rl = max(mx_rl, o.read_len);
+        if (o.qmin <= o.qmax) { mn_q = min(mn_q, o.qmin); mx_q = max(mx_q, o.qmax); }
+        if (run_cnt && o.read_len != run_len) { flush_len = run_len; flush_cnt = run_cnt; run_cnt = 0; }
+        run_len = o.read_len; run_cnt += P.cx.weight;
+      }
+    }
+    hist_flush(P.hist, flush_len, flush_cnt);
+  }
+  hist_flush(P.hist, run_len, run_cnt);
+  /* one set of atomics per warp */
+  my_key = warp_min64(my_key);
+  my_rds = warp_sum64(my_rds); my_names = warp_sum64(my_names); my_mem = warp_sum64(my_mem);
+  mn_rl = __reduce_min_sync(FULL, mn_rl); mx_rl = __reduce_max_sync(FULL, mx_rl);
+  mn_q = __reduce_min_sync(FULL, mn_q); mx_q = __reduce_max_sync(FULL, mx_q);
+  if (lane == 0) {
+    if (my_key != FQ_KEY_NONE) atomicMin(P.key, my_key);
+    if (my_rds) atomicAdd(&P.stats->num_rds, my_rds);
+    if (my_names) { atomicAdd(&P.stats->n_names, my_names); atomicAdd(&P.stats->mem_sum, my_mem); }
+    if (mx_rl) { atomicMin(&P.stats_range->min_rl, mn_rl); atomicMax(&P.stats_range->max_rl, mx_rl); }
+    if (mn_q <= mx_q) { atomicMin(&P.stats_range->min_q, mn_q); atomicMax(&P.stats_range->max_q, mx_q); }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ K3 / K4: the index */
+__device__ __forceinline__ const uint8_t* dir_name(const FqDirEntry* dir, uint32_t nd, unsigned long long g, uint32_t* len) {
+  uint32_t lo = 0, hi = nd;
+  while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (dir[mid].g0 <= g) lo = mid; else hi = mid; }
+  const FqName nm = dir[lo].names[g - dir[lo].g0];
+  *len = nm.len;
+  return dir[lo].data + nm.off;
+}
+
+struct TableParams {
+  const FqName* names; const uint8_t* data; uint32_t nrec; unsigned long long g0, step_base;
+  FqSlot* slots; unsigned long long mask; const FqDirEntry* dir1; uint32_t ndir1;
+  unsigned long long* key; unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(256)
+fq_index_insert_kernel(const TableParams P) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.nrec; k += gridDim.x * blockDim.x) {
+    const FqName nm = P.names[k];
+    if (nm.hash == FQ_HASH_SKIP) continue;
+    const unsigned long long g = P.g0 + k;
+    unsigned long long i = nm.hash & P.mask, probes = 0;
+    for (;; i = (i + 1) & P.mask) {
+      if (++probes > P.mask) { atomicExch(P.counters + 2, 1ull); break; }
+      FqSlot* s = P.slots + i;
+      unsigned long long cur = ld_volatile64(&s->hash);
+      if (cur == FQ_HASH_EMPTY) cur = atomicCAS(&s->hash, FQ_HASH_EMPTY, nm.hash);
+      if (cur != FQ_HASH_EMPTY && cur != nm.hash) continue;
+      /* slot carries this hash: keep the smallest record index; whoever sees an earlier arrival compares the names */
+      unsigned long long old = atomicMin(&s->idx1, g);
+      if (old != FQ_IDX_NONE) {
+        uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, old, &ol);
+        if (ol == nm.len && fq_bytes_equal(on, P.data + nm.off, nm.len)) {
+          unsigned long long later = old > g ? old : g; /* min over all arrivals of max(old, g) = 2nd smallest of the group */
+          atomicMin(P.key, FQ_KEY(P.step_base + later, FQ_R_NAME));
+        } else atomicAdd(P.counters + 0, 1ull);
+      }
+      break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fq_mate_claim_kernel(const TableParams P) {
+  unsigned long long claimed = 0;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < P.nrec; base += gridDim.x * blockDim.x) {
+    uint32_t k = base + threadIdx.x;
+    if (k >= P.nrec) continue;
+    const FqName nm = P.names[k];
+    if (nm.hash == FQ_HASH_SKIP) continue;
+    const unsigned long long g = P.g0 + k;
+    unsigned long long i = nm.hash & P.mask, probes = 0, unpaired = FQ_IDX_NONE;
+    for (;; i = (i + 1) & P.mask) {
+      if (++probes > P.mask + 1) { unpaired = g; break; }
+      const FqSlot* s = P.slots + i;
+      unsigned long long cur = s->hash;
+      if (cur == FQ_HASH_EMPTY) { unpaired = g; break; }
+      if (cur != nm.hash) continue;
+      uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, s->idx1, &ol);
+      if (!(ol == nm.len && fq_bytes_equal(on, P.data + nm.off, nm.len))) { atomicAdd(P.counters + 0, 1ull); break; }
+      unsigned long long old = atomicMin(&P.slots[i].claim2, g);
+      if (old == FQ_IDX_NONE) claimed++;           /* first claim = the reference's delete */
+      else unpaired = old > g ? old : g;           /* the entry was already deleted when the later one arrives */
+      break;
+    }
+    if (unpaired != FQ_IDX_NONE) atomicMin(P.key, FQ_KEY(P.step_base + unpaired, FQ_R_NAME));
+  }
+  __syncwarp();
+  claimed = warp_sum64(claimed);
+  if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(P.counters + 1, claimed);
+}
+
+struct PairParams {
+  const FqName* a; const uint8_t* da; uint32_t stride_a; const FqName* b; const uint8_t* db; uint32_t stride_b;
+  uint32_t npairs; unsigned long long p0; uint32_t rank; unsigned long long* key;
+};
+__global__ void __launch_bounds__(256)
+fq_pair_compare_kernel(const PairParams P) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.npairs; k += gridDim.x * blockDim.x) {
+    const FqName x = P.a[(size_t)k * P.stride_a], y = P.b[(size_t)k * P.stride_b];
+    if (x.hash == FQ_HASH_SKIP || y.hash == FQ_HASH_SKIP) continue;
+    bool same = x.hash == y.hash && x.len == y.len && fq_bytes_equal(P.da + x.off, P.db + y.off, x.len);
+    if (!same) atomicMin(P.key, FQ_KEY(P.p0 + k, P.rank));
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ the device */
+class FqCudaDevice : public FqDevice {
+ public:
+  explicit FqCudaDevice(int ordinal) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) throw std::runtime_error("no CUDA device available: libfastq_gpu has no CPU fallback");
+    if (ordinal < 0 || ordinal >= count) throw std::runtime_error("fqg_create: CUDA ordinal out of range");
+    dev_ = ordinal;
+    FQ_CUDA_CHECK(cudaSetDevice(dev_));
+    cudaDeviceProp prop; FQ_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev_));
+    sms_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : kSMs;
+    FQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    FQ_CUDA_CHECK(cudaEventCreate(&ev0_)); FQ_CUDA_CHECK(cudaEventCreate(&ev1_));
+    cudaMemPool_t pool; FQ_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev_));
+    unsigned long long thr = ~0ull; /* keep freed blocks in the pool: allocations repeat every chunk */
+    FQ_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    max_tiles_ = (uint32_t)((1ull << 31) / SCAN_TILE) + 2;
+    FQ_CUDA_CHECK(cudaMalloc(&tile_state_, (size_t)max_tiles_ * sizeof(unsigned long long) + 64));
+    ticket_ = (uint32_t*)(tile_state_ + max_tiles_);
+  }
+  ~FqCudaDevice() override {
+    cudaSetDevice(dev_);
+    cudaStreamSynchronize(st_);
+    for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : free_ev_) cudaEventDestroy(e);
+    cudaFree(tile_state_);
+    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_);
+    cudaStreamDestroy(st_);
+  }
+  const char* name() const override { return "cuda"; }
+  void* alloc(size_t n) override {
+    void* p = nullptr;
+    FQ_CUDA_CHECK(cudaSetDevice(dev_));
+    FQ_CUDA_CHECK(cudaMallocAsync(&p, n ? n : 1, st_));
+    return p;
+  }
+  void release(void* p) override { if (p) cudaFreeAsync(p, st_); }
+  void upload(void* d, const void* s, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st_)); }
+  void download(void* d, const void* s, size_t n) override {
+    if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st_));
+    FQ_CUDA_CHECK(cudaStreamSynchronize(st_));
+  }
+  void copy(void* d, const void* s, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st_)); }
+  void fill(void* d, int b, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemsetAsync(d, b, n, st_)); }
+  void sync() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); }
+  void timer_start() override { FQ_CUDA_CHECK(cudaEventRecord(ev0_, st_)); }
+  double timer_stop_ms() override {
+    FQ_CUDA_CHECK(cudaEventRecord(ev1_, st_)); FQ_CUDA_CHECK(cudaEventSynchronize(ev1_));
+    float ms = 0; FQ_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    return ms;
+  }
+  unsigned long long launches() const override { return n_launch_; }
+  bool kernel_stat(int which, double* ms, uint64_t* launches, uint64_t* bytes, uint64_t* items) override {
+    if (which < 0 || which >= FQG_K_COUNT) return false;
+    collect();
+    *ms = kst_[which].ms; *launches = kst_[which].launches; *bytes = kst_[which].bytes; *items = kst_[which].items;
+    return true;
+  }
+  void kernel_stats_reset() override { collect(); for (auto& k : kst_) k = KStat(); }
+
+  void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) override {
+    uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (ntiles == 0) { FQ_CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(uint32_t), st_)); return; }
+    if (ntiles > max_tiles_) throw std::runtime_error("scan_lines: chunk larger than 2 GiB");
+    FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));
+    FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
+    tic(FQG_K_SCAN, n, ntiles);
+    fq_scan_kernel<<<ntiles, SCAN_THREADS, 0, st_>>>(data, n, virtual_end, line_end, cap, tile_state_, ticket_, ntiles, out2);
+    toc();
+    launched();
+  }
+  void find_overlong(const uint32_t* line_end, uint32_t q, uint32_t j0, uint32_t nlines, uint32_t n, int tail_from_n, uint32_t* out) override {
+    uint32_t total = nlines + (tail_from_n ? 1u : 0u);
+    if (!total) return;
+    int grid = (int)std::min<uint32_t>((total + 255) / 256, (uint32_t)sms_ * 8);
+    fq_overlong_kernel<<<grid, 256, 0, st_>>>(line_end, q, j0, nlines, n, tail_from_n, out);
+    launched();
+  }
+  void split_serial(const uint8_t* data, uint32_t n, uint32_t q, int is_eof, FqLine* lines4, uint32_t* out3) override {
+    fq_split_serial_kernel<<<1, 32, 0, st_>>>(data, n, q, is_eof, lines4, out3);
+    launched();
+  }
+  void sniff(const uint8_t* data, FqLine hdr1, FqLine seq, int32_t* out2) override {
+    fq_sniff_kernel<<<1, 32, 0, st_>>>(data, hdr1, seq, out2);
+    launched();
+  }
+  void records(const FqRecordsArgs& a) override {
+    if (!a.nrec) return;
+    RecParams P;
+    P.data = a.data; P.line_end = a.line_end; P.lines = a.lines; P.q = a.q; P.j0 = a.j0; P.nrec = a.nrec; P.g0 = a.g0;
+    P.step_base = a.step_base; P.cx = a.cx; P.stats = a.stats; P.stats_range = a.stats_range; P.hist = a.hist; P.key = a.key; P.names = a.names;
+    int grid = (int)std::min<uint32_t>((a.nrec + REC_THREADS - 1) / REC_THREADS, (uint32_t)sms_ * 16);
+    tic(FQG_K_RECORDS, a.span_bytes, a.nrec);
+    fq_records_kernel<<<grid, REC_THREADS, 0, st_>>>(P);
+    toc();
+    launched();
+  }
+  static TableParams table_params(const FqTableArgs& a) {
+    TableParams P;
+    P.names = a.names; P.data = a.data; P.nrec = a.nrec; P.g0 = a.g0; P.step_base = a.step_base; P.slots = a.slots; P.mask = a.mask;
+    P.dir1 = a.dir1; P.ndir1 = a.ndir1; P.key = a.key; P.counters = a.counters;
+    return P;
+  }
+  void index_insert(const FqTableArgs& a) override {
+    if (!a.nrec) return;
+    int grid = (int)std::min<uint32_t>((a.nrec + 255) / 256, (uint32_t)sms_ * 8);
+    tic(FQG_K_INDEX, 0, a.nrec);
+    fq_index_insert_kernel<<<grid, 256, 0, st_>>>(table_params(a));
+    toc();
+    launched();
+  }
+  void mate_claim(const FqTableArgs& a) override {
+    if (!a.nrec) return;
+    int grid = (int)std::min<uint32_t>((a.nrec + 255) / 256, (uint32_t)sms_ * 8);
+    tic(FQG_K_MATE, 0, a.nrec);
+    fq_mate_claim_kernel<<<grid, 256, 0, st_>>>(table_params(a));
+    toc();
+    launched();
+  }
+  void pair_compare(const FqPairArgs& a) override {
+    if (!a.npairs) return;
+    PairParams P;
+    P.a = a.a; P.da = a.da; P.stride_a = a.stride_a; P.b = a.b; P.db = a.db; P.stride_b = a.stride_b;
+    P.npairs = a.npairs; P.p0 = a.p0; P.rank = a.rank; P.key = a.key;
+    int grid = (int)std::min<uint32_t>((a.npairs + 255) / 256, (uint32_t)sms_ * 8);
+    tic(FQG_K_PAIR, 0, a.npairs);
+    fq_pair_compare_kernel<<<grid, 256, 0, st_>>>(P);
+    toc();
+    launched();
+  }
+  void explain(const uint8_t* data, const FqLine* L, const FqRecCtx& cx, FqRecOut* out_dev) override {
+    fq_explain_kernel<<<1, 32, 0, st_>>>(data, L[0], L[1], L[2], L[3], cx, out_dev);
+    launched();
+  }
+
+ private:
+  void launched() { n_launch_++; FQ_CUDA_CHECK(cudaGetLastError()); }
+  /* CUDA-event stopwatch around one launch; elapsed times are read back lazily (collect) */
+  struct KStat { double ms = 0; uint64_t launches = 0, bytes = 0, items = 0; };
+  struct Pending { int cls; cudaEvent_t a, b; };
+  void tic(int cls, uint64_t bytes, uint64_t items) {
+    Pending p; p.cls = cls;
+    if (free_ev_.size() >= 2) { p.a = free_ev_.back(); free_ev_.pop_back(); p.b = free_ev_.back(); free_ev_.pop_back(); }
+    else { FQ_CUDA_CHECK(cudaEventCreate(&p.a)); FQ_CUDA_CHECK(cudaEventCreate(&p.b)); }
+    kst_[cls].launches++; kst_[cls].bytes += bytes; kst_[cls].items += items;
+    FQ_CUDA_CHECK(cudaEventRecord(p.a, st_));
+    pending_.push_back(p);
+  }
+  void toc() { FQ_CUDA_CHECK(cudaEventRecord(pending_.back().b, st_)); }
+  void collect() {
+    if (pending_.empty()) return;
+    FQ_CUDA_CHECK(cudaStreamSynchronize(st_));
+    for (auto& p : pending_) {
+      float ms = 0; FQ_CUDA_CHECK(cudaEventElapsedTime(&ms, p.a, p.b));
+      kst_[p.cls].ms += ms;
+      free_ev_.push_back(p.a); free_ev_.push_back(p.b);
+    }
+    pending_.clear();
+  }
+  KStat kst_[FQG_K_COUNT];
+  std::vector<Pending> pending_;
+  std::vector<cudaEvent_t> free_ev_;
+  int dev_ = 0, sms_ = kSMs;
+  cudaStream_t st_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;
+  unsigned long long n_launch_ = 0;
+};
+
+}  // namespace
+
+FqDevice* fq_make_cuda_device(int ordinal) { return new FqCudaDevice(ordinal); }
+FqDevice* fq_default_device(int ordinal) { return fq_make_cuda_device(ordinal); }

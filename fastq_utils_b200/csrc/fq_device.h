@@ -24,6 +24,7 @@ typedef struct {
   const FqLine* lines;       /* explicit lines, 4 per record (serially split records); NULL → derive from line_end */
   uint32_t q, j0;            /* the segment's first line starts at byte q and ends at line_end[j0] */
   uint32_t nrec;
+  uint64_t span_bytes;       /* FASTQ bytes the records cover (kernel statistics only) */
   uint64_t g0;               /* index of the first record inside its file */
   uint64_t step_base;        /* steps preceding this file's loop (mate loop) */
   FqRecCtx cx;
@@ -84,6 +85,9 @@ class FqDevice {
   /* device-side stopwatch on the stream (CUDA events) */
   virtual void timer_start() = 0;
   virtual double timer_stop_ms() = 0;
+  /* per-kernel-class device time: which = FQG_K_*; returns false for an unknown class */
+  virtual bool kernel_stat(int which, double* ms, uint64_t* launches, uint64_t* bytes, uint64_t* items) = 0;
+  virtual void kernel_stats_reset() = 0;
   /* how many kernels were launched so far (bench.py's gpu_launches) */
   virtual unsigned long long launches() const = 0;
 };

@@ -85,7 +85,7 @@ FqRecCtx FqEngine::make_ctx(int file) const {
   FqRecCtx cx; memset(&cx, 0, sizeof cx);
   cx.loop = loop_of(file);
   cx.fmt_key = fmt_of_sniff(f_[file].sniff_fmt);
-  cx.pe_key = (cfg_.mode == FQG_MODE_INDEX) ? 0 : 1; /* fastq_info.c:63,112-113,158,290,327 */
+  cx.pe_key = (cfg_.mode == FQG_MODE_INDEX && !(cfg_.flags & FQG_FLAG_PAIRED_NAMES)) ? 0 : 1; /* fastq_info.c:63,112-113,158,290,327 */
   if (cx.loop == FQ_LOOP_MATE) { /* fastq_info.c:345: file-2 records are validated against file 1's state */
     cx.fmt_val = fmt_of_sniff(f_[0].sniff_fmt); cx.pe_val = 1; cx.space = f_[0].sniff_color;
   } else { cx.fmt_val = cx.fmt_key; cx.pe_val = cx.pe_key; cx.space = f_[file].sniff_color; }
@@ -216,9 +216,10 @@ void FqEngine::segmentize(int file, int b, uint32_t pos, uint32_t j, bool last) 
     uint32_t nfast = a == kNone32 ? nrec : std::min(nrec, (a - j) / 4);
     if (nfast) {
       FqSegment s; s.buf = b; s.q = pos; s.j0 = j; s.nrec = nfast;
-      add_segment(file, s);
       j += 4 * nfast;
       pos = line_end_at(B, j - 1);
+      s.span = pos - s.q;
+      add_segment(file, s);
     }
     if (a == kNone32) break;
     /* the record starting at pos holds a line that gzgets would split: emulate the four reads serially */
@@ -228,6 +229,7 @@ void FqEngine::segmentize(int file, int b, uint32_t pos, uint32_t j, bool last) 
     if (out3[1] != 4) { dev_->release(ld); break; }
     FqSegment s; s.buf = b; s.q = pos; s.j0 = j; s.nrec = 1; s.explicit_lines = true; s.lines_dev = ld;
     dev_->download(s.lines_host, ld, 4 * sizeof(FqLine));
+    s.span = out3[0] - pos;
     add_segment(file, s);
     pos = out3[0]; j += out3[2];
   }
@@ -352,7 +354,7 @@ void FqEngine::launch_segment(int file, size_t si) {
   const FqBuffer& B = F.bufs[s.buf];
   FqRecordsArgs a; memset(&a, 0, sizeof a);
   a.data = B.data; a.line_end = B.line_end; a.lines = s.explicit_lines ? s.lines_dev : nullptr;
-  a.q = s.q; a.j0 = s.j0; a.nrec = nrec; a.g0 = s.g0; a.step_base = step_base(file);
+  a.q = s.q; a.j0 = s.j0; a.nrec = nrec; a.span_bytes = s.span; a.g0 = s.g0; a.step_base = step_base(file);
   a.cx = make_ctx(file);
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
   a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats;

@@ -22,6 +22,7 @@ struct FqBuffer {
 struct FqSegment {
   int buf = -1;
   uint32_t q = 0, j0 = 0, nrec = 0;
+  uint64_t span = 0;
   bool explicit_lines = false;
   FqLine lines_host[4];
   FqLine* lines_dev = nullptr;

@@ -300,6 +300,7 @@ extern "C" int fqg_fastq_info_mem(int argc, const char** argv_in, const void* f1
   } else {
     second_file = is_paired && !is_sorted;
     cfg.mode = second_file ? FQG_MODE_INDEX_PAIR : FQG_MODE_INDEX;
+    if (is_paired) cfg.flags |= FQG_FLAG_PAIRED_NAMES;
     if (n1 == UNOPENABLE) return unopenable(a1);
   }
   fqg_report rep;

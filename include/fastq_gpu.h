@@ -40,8 +40,12 @@ typedef struct {
   int32_t mode;                  /* FQG_MODE_* */
   int32_t device;                /* CUDA ordinal */
   uint64_t index_capacity_hint;  /* expected number of read names (0 = grow on demand) */
-  uint32_t reserved[4];
+  uint32_t flags;                /* FQG_FLAG_* */
+  uint32_t reserved[3];
 } fqg_config;
+/* FQG_MODE_INDEX only: a second file operand exists but is never read (`-s f1 f2` without -r): the reference still
+ * strips the mate digit from default-format names (is_pe, src/fastq_info.c:290) */
+#define FQG_FLAG_PAIRED_NAMES 1u
 
 /* statistics of one FASTQ_FILE as the reference holds them at the end of its loops (src/fastq.h:110-131) */
 typedef struct {
@@ -122,6 +126,21 @@ void fqg_transcript_free(fqg_transcript* t);
  * be opened" (src/fastq.c:651-655).  chunk_bytes > 0 feeds the streams in pieces of that size. */
 int fqg_fastq_info_mem(int argc, const char** argv, const void* f1, size_t n1, const void* f2, size_t n2,
                        int device, size_t chunk_bytes, fqg_transcript* t);
+
+/* ---- per-kernel device timing (CUDA events around every launch on the context's stream) ---- */
+enum { FQG_K_SCAN = 0, FQG_K_RECORDS = 1, FQG_K_INDEX = 2, FQG_K_MATE = 3, FQG_K_PAIR = 4, FQG_K_OTHER = 5, FQG_K_COUNT = 6 };
+typedef struct { double ms; uint64_t launches; uint64_t bytes; uint64_t items; } fqg_kernel_stat;
+/* accumulated since fqg_create / the last fqg_kernel_stats_reset; `bytes` = FASTQ bytes the launches covered */
+int fqg_kernel_stats(fqg_ctx* ctx, int which, fqg_kernel_stat* out);
+int fqg_kernel_stats_reset(fqg_ctx* ctx);
+
+/* ---- synthetic inputs generated on the device (bench.py, large parity tests); see fq_synth.cu ---- */
+int fqg_synth_illumina_record_bytes(void);
+int fqg_synth_long_header_bytes(void);
+int fqg_synth_illumina(void* device_out, uint64_t first_record, uint64_t n_records, uint64_t seed, int mate,
+                       uint64_t perm_window, void* cuda_stream);
+int fqg_synth_longreads(void* device_out, const uint64_t* device_offsets, uint64_t first_record, uint64_t n_records,
+                        uint64_t seed, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,8 @@ class FqSimDevice : public FqDevice {
   void timer_start() override {}
   double timer_stop_ms() override { return 0.0; }
   unsigned long long launches() const override { return n_launch_; }
+  bool kernel_stat(int, double* ms, uint64_t* l, uint64_t* b, uint64_t* i) override { *ms = 0; *l = *b = *i = 0; return true; }
+  void kernel_stats_reset() override {}
 
   void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) override {
     n_launch_++;

@@ -1,0 +1,179 @@
+"""Parity of the CUDA path (through the C ABI of libfastq_gpu.so) with the reference: golden transcripts of the
+unmodified reference binary, differential fuzz against the CPU oracle, the CLI, and synthetic Illumina / long-read
+streams generated on the device (checked against the oracle at sizes it finishes in seconds, and through
+size-independent properties at larger sizes)."""
+import os
+import random
+import subprocess
+
+import pytest
+
+from _util import GOLDEN, ROOT, fqg_run, fqg_run_files, golden_transcripts, oracle_run
+from test_oracle_fuzz import NAMES, make_file, mutate, render
+
+pytestmark = pytest.mark.gpu
+CASES = golden_transcripts()
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_gpu_matches_reference_transcript(idx):
+    c = CASES[idx]
+    got = fqg_run_files(c["argv"], chunk=0, kind="gpu")
+    assert got == (c["rc"], c["stdout"], c["stderr"]), c["argv"]
+
+
+@pytest.mark.parametrize("idx", range(0, len(CASES), 3))
+def test_gpu_matches_reference_transcript_chunked(idx):
+    c = CASES[idx]
+    chunk = [64, 1000, 4096][idx % 3]
+    got = fqg_run_files(c["argv"], chunk=chunk, kind="gpu")
+    assert got == (c["rc"], c["stdout"], c["stderr"]), (c["argv"], chunk)
+
+
+@pytest.mark.parametrize("seed", range(300))
+def test_gpu_fuzz_against_oracle(seed):
+    rng = random.Random(20_000 + seed)
+    style = rng.randrange(len(NAMES))
+    n = rng.choice([0, 1, 2, 3, 5, 8, 13, 40, 300])
+    mode = rng.choice(["single", "single_r", "pe", "pair", "pair_rs", "pair_s", "pair_r"])
+    r1 = make_file(rng, n, style, 1)
+    two = mode.startswith("pair")
+    r2 = make_file(rng, n, style, 2) if two else None
+    if mode == "pe":
+        inter = []
+        for a, b in zip(r1, make_file(rng, n, style, 2)):
+            inter += [a, b]
+        r1 = inter
+    if two and rng.random() < 0.5:
+        rng.shuffle(r2)
+    for _ in range(rng.choice([0, 0, 1, 1, 2])):
+        mutate(rng, r1 if (not two or rng.random() < 0.5) else r2)
+    nl = "crlf" if rng.random() < 0.08 else "lf"
+    d1 = render(rng, r1, nl)
+    d2 = render(rng, r2, nl) if two else None
+    argv = {"single": [], "single_r": ["-r"], "pe": [], "pair": [], "pair_rs": ["-r", "-s"], "pair_s": ["-s"], "pair_r": ["-r"]}[mode]
+    if rng.random() < 0.2: argv = ["-q"] + argv
+    if rng.random() < 0.2: argv = ["-e"] + argv
+    argv = argv + ["a.fq"] + (["b.fq"] if two else []) + (["pe"] if mode == "pe" else [])
+    chunk = rng.choice([0, 0, 1, 5, 33, 200, 5000])
+    assert fqg_run(argv, d1, d2, chunk=chunk, kind="gpu") == oracle_run(argv, d1, d2), (argv, chunk, d1, d2)
+
+
+CLI = os.path.join(ROOT, "fastq_utils_b200", "fastq_info_gpu")
+
+
+@pytest.mark.parametrize("idx", [i for i, c in enumerate(CASES) if any(k in " ".join(c["argv"]) for k in ("c18_10000", "test_e1.", "test_e9", "test_21", "solid", "test_empty"))][:40])
+def test_cli_matches_reference_transcript(idx):
+    c = CASES[idx]
+    p = subprocess.run([CLI] + c["argv"], cwd=GOLDEN, capture_output=True)
+    assert (p.returncode, p.stdout.decode("latin-1"), p.stderr.decode("latin-1")) == (c["rc"], c["stdout"], c["stderr"]), c["argv"]
+
+
+# ------------------------------------------------------------------------------------------- synthetic streams
+def _illumina(n, mate=1, perm=0, first=0, seed=42):
+    import torch
+    import fastq_utils_b200 as fq
+    rb = fq.illumina_record_bytes()
+    t = torch.zeros(n * rb + 64, dtype=torch.uint8, device="cuda")
+    fq.synth_illumina(t, first, n, seed=seed, mate=mate, perm_window=perm, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return t, n * rb
+
+
+def test_synth_illumina_single_matches_oracle():
+    t, nb = _illumina(60_000)
+    data = bytes(t[:nb].cpu().numpy())
+    for argv in (["a.fq"], ["-r", "a.fq"], ["a.fq", "pe"]):
+        assert fqg_run(argv, data, None, chunk=0, kind="gpu") == oracle_run(argv, data, None), argv
+    assert fqg_run(["a.fq"], data, None, chunk=1 << 20, kind="gpu") == oracle_run(["a.fq"], data, None)
+
+
+def test_synth_illumina_pair_matches_oracle():
+    t1, nb = _illumina(40_960, mate=1)
+    t2, _ = _illumina(40_960, mate=2, perm=1024)
+    d1, d2 = bytes(t1[:nb].cpu().numpy()), bytes(t2[:nb].cpu().numpy())
+    for argv in (["a.fq", "b.fq"], ["-r", "-s", "a.fq", "b.fq"], ["-s", "a.fq", "b.fq"]):
+        got = fqg_run(argv, d1, d2, chunk=0, kind="gpu")
+        assert got == oracle_run(argv, d1, d2), argv
+    assert fqg_run(["a.fq", "b.fq"], d1, d2, chunk=0, kind="gpu")[0] == 0
+    assert "Readnames do not match" in fqg_run(["-r", "-s", "a.fq", "b.fq"], d1, d2, chunk=0, kind="gpu")[2]
+
+
+def test_synth_negative_twins_match_oracle():
+    import fastq_utils_b200 as fq
+    rb = fq.illumina_record_bytes()
+    t, nb = _illumina(30_000)
+    base = bytearray(t[:nb].cpu().numpy().tobytes())
+    # duplicate of record 100 injected at 20000; an invalid base at record 25000 (later: the duplicate wins)
+    dup = bytearray(base); dup[20_000 * rb:20_001 * rb] = base[100 * rb:101 * rb]; dup[25_000 * rb + 70] = ord("X")
+    # invalid base earlier than the duplicate: it wins
+    bad = bytearray(dup); bad[5_000 * rb + 60] = ord("*")
+    # quality one byte short / a '+' line replaced / truncated last record
+    short = bytearray(base); del short[7_000 * rb + rb - 2]
+    plus = bytearray(base); plus[9_000 * rb + 55 + 151] = ord("-")
+    trunc = base[:len(base) - 100]
+    for data in (dup, bad, short, plus, trunc):
+        for argv in (["a.fq"], ["-r", "a.fq"]):
+            assert fqg_run(argv, bytes(data), None, chunk=0, kind="gpu") == oracle_run(argv, bytes(data), None), argv
+    # mates: one removed from file 2 / one extra name in file 1
+    t2, _ = _illumina(30_000, mate=2, perm=1024)
+    m2 = bytearray(t2[:nb].cpu().numpy().tobytes())
+    removed = m2[:123 * rb] + m2[124 * rb:]
+    for f1, f2 in ((bytes(base), bytes(removed)), (bytes(base), bytes(m2[:20_000 * rb])), (bytes(base[:29_000 * rb]), bytes(m2))):
+        assert fqg_run(["a.fq", "b.fq"], f1, f2, chunk=0, kind="gpu") == oracle_run(["a.fq", "b.fq"], f1, f2)
+
+
+def test_large_device_resident_properties():
+    """4 M records (1.4 GB) fed straight from device memory in one call: counts, ranges and verdict are known by construction."""
+    import torch
+    import fastq_utils_b200 as fq
+    n = 4_000_000
+    t, nb = _illumina(n)
+    h = fq.FastqInfo(fq.MODE_INDEX, index_capacity_hint=n)
+    h.feed_device(0, t.data_ptr(), nb, last=True)
+    rep = h.finish()
+    assert rep.error.code == 0
+    assert rep.n_index_entries == n and rep.file[0].n_records == n and rep.file[0].num_rds == 2 * n
+    assert (rep.file[0].min_rl, rep.file[0].max_rl, rep.median_rl) == (151, 151, 151)
+    assert (rep.file[0].min_qual, rep.file[0].max_qual) == (35, 73)
+    rc, out, err = h.render(rep, "x.fq")
+    assert rc == 0 and err.endswith("Number of reads: 4000000\nQuality encoding range: 35 73\nQuality encoding: 33\nRead length: 150 150 150\nOK\n")
+    # same bytes through -r: identical statistics, no index
+    h2 = fq.FastqInfo(fq.MODE_SINGLE)
+    h2.feed_device(0, t.data_ptr(), nb, last=True)
+    r2 = h2.finish()
+    assert r2.error.code == 0 and r2.file[0].num_rds == n and r2.median_rl == 151
+    # idempotence: reset and run again on the same context
+    h.reset()
+    h.feed_device(0, t.data_ptr(), nb, last=True)
+    rep3 = h.finish()
+    assert rep3.error.code == 0 and rep3.n_index_entries == n
+    # a duplicate far apart is found at the later record
+    rb = fq.illumina_record_bytes()
+    t[3_999_000 * rb:3_999_001 * rb] = t[17 * rb:18 * rb].clone()
+    h.reset()
+    h.feed_device(0, t.data_ptr(), nb, last=True)
+    rep4 = h.finish()
+    assert rep4.error.code == 13 and rep4.error.record == 3_999_000 and rep4.error.line == 4 * 3_999_001
+    h.close(); h2.close()
+    del t
+    torch.cuda.empty_cache()
+
+
+def test_longreads_match_oracle():
+    import torch
+    import fastq_utils_b200 as fq
+    g = torch.Generator().manual_seed(7)
+    lens = torch.exp(torch.randn(300, generator=g) + 9.0).clamp(1000, 100000).to(torch.int64)
+    hdr = fq.lib().fqg_synth_long_header_bytes()
+    rec = hdr + 2 * lens + 4
+    off = torch.zeros(301, dtype=torch.int64)
+    off[1:] = torch.cumsum(rec, 0)
+    nb = int(off[-1])
+    t = torch.zeros(nb + 64, dtype=torch.uint8, device="cuda")
+    fq.synth_longreads(t, off.cuda(), 0, 300, seed=7, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    data = bytes(t[:nb].cpu().numpy())
+    for argv in (["-r", "a.fq"], ["a.fq"]):
+        assert fqg_run(argv, data, None, chunk=0, kind="gpu") == oracle_run(argv, data, None), argv
+    assert fqg_run(["-r", "a.fq"], data, None, chunk=1 << 20, kind="gpu") == oracle_run(["-r", "a.fq"], data, None)
