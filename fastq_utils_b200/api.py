@@ -137,6 +137,7 @@ class FastqInfo:
         """Host bytes (bytes / bytearray / anything exposing a pointer via torch/numpy `data_ptr`-like int tuple (ptr, n))."""
         if isinstance(data, tuple):
             ptr, n = data
+            ptr = ctypes.c_void_p(ptr)
         else:
             n = len(data)
             ptr = ctypes.cast(ctypes.c_char_p(bytes(data)) if not isinstance(data, bytes) else ctypes.c_char_p(data), ctypes.c_void_p)
