@@ -164,8 +164,12 @@ def main():
     if world > 1:
         from fastq_utils_b200 import dist as fqdist
         runner = fqdist.ShardedFastqInfo(fq.MODE_INDEX, local, n_hint=n)
-        step = lambda: runner.run_device(data.data_ptr(), nb)  # noqa: E731
         ctx = runner.ctx
+
+        def step():
+            res = runner.run_device(data.data_ptr(), nb, name="synthetic.fastq")
+            assert res["event_key"] == (1 << 64) - 1 and res["n_index_entries"] == n * world, (res["event_key"], res["n_index_entries"])
+            return res
     else:
         ctx = fq.FastqInfo(fq.MODE_INDEX, device=local, index_capacity_hint=n)
 
@@ -201,6 +205,10 @@ def main():
     sampler.join(timeout=2)
     launches = ctx.launch_count() - l0
     ks = ctx.kernel_stats()
+    if world > 1:  # the index shard lives in its own context
+        launches += runner.shard.launch_count()
+        ks["index"] = runner.shard.kernel_stats()["index"]
+        dev_ms = 0.0
     # the step is host-driven (several synchronising read-backs); device-event time and wall time are both reported, the larger one counts
     per_step = max(dev_ms / 1e3, wall) / a.steps
     if world > 1:
@@ -226,6 +234,9 @@ def main():
            "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": config, "reads_per_s": n * world / per_step, "device_ms_per_step": dev_ms / a.steps, "wall_ms_per_step": wall / a.steps * 1e3,
            "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary()}
+    if world > 1:
+        out["config"]["parallelism"] = f"byte-range shards x{world}, names routed by hash (all-to-all over NCCL), stats all-reduced"
+        out["e2e"] = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "measured at N=1 only"}
 
     if rank == 0 and world == 1:
         # ---------------- e2e: the same job through fqg_feed from pinned host memory (H2D inside the timed region)

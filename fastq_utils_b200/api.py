@@ -5,9 +5,13 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libfastq_gpu.so")
+# Test hook (tests/test_dist_gloo.py only): the same host code linked against the sequential stand-in device of tests/sim,
+# so that the multi-rank orchestration can run under gloo on a machine without GPUs.  Never set outside the test-suite.
+_SO = os.environ.get("FQG_SIM_LIBRARY_FOR_TESTS", _SO)
 
 MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED, MODE_SORTED_PAIR = range(5)
 KERNEL_CLASSES = ["scan", "records", "index", "mate", "pair", "other"]
+FLAG_PAIRED_NAMES, FLAG_EXTERNAL_INDEX = 1, 2
 
 
 class Config(ctypes.Structure):
@@ -23,7 +27,7 @@ class FileReport(ctypes.Structure):
 
 class Error(ctypes.Structure):
     _fields_ = [("code", ctypes.c_int32), ("file", ctypes.c_int32), ("msg_file", ctypes.c_int32), ("chr", ctypes.c_int32),
-                ("record", ctypes.c_uint64), ("line", ctypes.c_uint64), ("a", ctypes.c_uint64), ("b", ctypes.c_uint64),
+                ("record", ctypes.c_uint64), ("line", ctypes.c_uint64), ("a", ctypes.c_uint64), ("b", ctypes.c_uint64), ("event_key", ctypes.c_uint64),
                 ("hdr1_len", ctypes.c_uint32), ("hdr2_len", ctypes.c_uint32), ("name_len", ctypes.c_uint32),
                 ("hdr1", ctypes.c_char * 1024), ("hdr2", ctypes.c_char * 1024), ("name", ctypes.c_char * 1024)]
 
@@ -78,8 +82,16 @@ def lib():
         L.fqg_fastq_info_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, vp, sz, ci, sz, ctypes.POINTER(Transcript)]
         L.fqg_kernel_stats.argtypes = [vp, ci, ctypes.POINTER(KernelStat)]
         L.fqg_kernel_stats_reset.argtypes = [vp]
-        L.fqg_synth_illumina.argtypes = [vp, u64, u64, u64, ci, u64, vp]
-        L.fqg_synth_longreads.argtypes = [vp, vp, u64, u64, u64, vp]
+        L.fqg_prescan_device.argtypes = [vp, ci, vp, sz, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64)]
+        L.fqg_set_stream_start.argtypes = [vp, ci, ctypes.c_uint32, u64]
+        L.fqg_names_count.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+        L.fqg_names_pack.argtypes = [vp, ci, ctypes.c_uint32, vp, vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+        L.fqg_shard_insert.argtypes = [vp, vp, u64, vp, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+        L.fqg_shard_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(u64)]
+        L.fqg_hist_range.argtypes = [vp, ci, u64, u64, ctypes.POINTER(u64)]
+        if hasattr(L, "fqg_synth_illumina"):  # absent from the test stand-in
+            L.fqg_synth_illumina.argtypes = [vp, u64, u64, u64, ci, u64, vp]
+            L.fqg_synth_longreads.argtypes = [vp, vp, u64, u64, u64, vp]
         _lib = L
     return _lib
 
@@ -176,6 +188,40 @@ class FastqInfo:
         if reset:
             lib().fqg_kernel_stats_reset(self._ctx)
         return out
+
+    # ---- multi-GPU building blocks (see dist.py) ----
+    def prescan_device(self, file, ptr, n, at_eof):
+        nl, lf, first = ctypes.c_uint64(), ctypes.c_int32(), (ctypes.c_uint64 * 4)()
+        _check(self._ctx, lib().fqg_prescan_device(self._ctx, file, ctypes.c_void_p(ptr), n, int(at_eof), ctypes.byref(nl), ctypes.byref(lf), first), "fqg_prescan_device")
+        return int(nl.value), bool(lf.value), [int(x) for x in first]
+
+    def set_stream_start(self, file, skip_lines, first_record):
+        _check(self._ctx, lib().fqg_set_stream_start(self._ctx, file, skip_lines, first_record), "fqg_set_stream_start")
+
+    def names_count(self, file, world):
+        c, b = (ctypes.c_uint64 * world)(), (ctypes.c_uint64 * world)()
+        _check(self._ctx, lib().fqg_names_count(self._ctx, file, world, c, b), "fqg_names_count")
+        return list(c), list(b)
+
+    def names_pack(self, file, world, meta_ptr, blob_ptr, meta_base, blob_base):
+        mb, bb = (ctypes.c_uint64 * world)(*meta_base), (ctypes.c_uint64 * world)(*blob_base)
+        _check(self._ctx, lib().fqg_names_pack(self._ctx, file, world, ctypes.c_void_p(meta_ptr), ctypes.c_void_p(blob_ptr), mb, bb), "fqg_names_pack")
+
+    def shard_insert(self, meta_ptr, n, blob_ptr, meta_start, blob_start):
+        ns = len(blob_start)
+        ms, bs = (ctypes.c_uint64 * (ns + 1))(*meta_start), (ctypes.c_uint64 * ns)(*blob_start)
+        _check(self._ctx, lib().fqg_shard_insert(self._ctx, ctypes.c_void_p(meta_ptr), n, ctypes.c_void_p(blob_ptr), ns, ms, bs), "fqg_shard_insert")
+
+    def shard_result(self):
+        key, rec, ln, col = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_uint64()
+        name = ctypes.create_string_buffer(1024)
+        _check(self._ctx, lib().fqg_shard_result(self._ctx, ctypes.byref(key), ctypes.byref(rec), name, ctypes.byref(ln), ctypes.byref(col)), "fqg_shard_result")
+        return int(key.value), int(rec.value), name.raw[:ln.value], int(col.value)
+
+    def hist_range(self, file, lo, hi):
+        out = (ctypes.c_uint64 * (hi - lo + 1))()
+        _check(self._ctx, lib().fqg_hist_range(self._ctx, file, lo, hi, out), "fqg_hist_range")
+        return list(out)
 
     def index_records(self, data, cap=0):
         n = ctypes.c_uint64()

@@ -87,3 +87,32 @@ extern "C" int fqg_kernel_stats_reset(fqg_ctx* c) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->dev->kernel_stats_reset())
 }
+
+extern "C" int fqg_prescan_device(fqg_ctx* c, int file, const void* dptr, size_t n, int at_eof, uint64_t* n_lines, int32_t* ends_lf, uint64_t first_ends[4]) {
+  if (!c || file < 0 || file > 1 || !dptr || !n || !n_lines || !ends_lf || !first_ends) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->prescan_device(file, dptr, n, at_eof != 0, n_lines, ends_lf, first_ends))
+}
+extern "C" int fqg_set_stream_start(fqg_ctx* c, int file, uint32_t skip_lines, uint64_t first_record) {
+  if (!c || file < 0 || file > 1) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->set_stream_start(file, skip_lines, first_record))
+}
+extern "C" int fqg_names_count(fqg_ctx* c, int file, uint32_t world, uint64_t* counts, uint64_t* bytes) {
+  if (!c || file < 0 || file > 1 || !counts || !bytes) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->names_count(file, world, counts, bytes))
+}
+extern "C" int fqg_names_pack(fqg_ctx* c, int file, uint32_t world, void* meta, void* blob, const uint64_t* meta_base, const uint64_t* blob_base) {
+  if (!c || file < 0 || file > 1 || !meta_base || !blob_base) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->names_pack(file, world, meta, blob, meta_base, blob_base))
+}
+extern "C" int fqg_shard_insert(fqg_ctx* c, const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start) {
+  if (!c || !meta_start || !blob_start) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_insert(meta, n, blob, n_src, meta_start, blob_start))
+}
+extern "C" int fqg_shard_result(fqg_ctx* c, uint64_t* key, uint64_t* record, char name[1024], uint32_t* name_len, uint64_t* collisions) {
+  if (!c || !key || !record || !name || !name_len || !collisions) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_result(key, record, name, name_len, collisions))
+}
+extern "C" int fqg_hist_range(fqg_ctx* c, int file, uint64_t lo, uint64_t hi, uint64_t* out) {
+  if (!c || file < 0 || file > 1 || !out) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->hist_range(file, lo, hi, out))
+}

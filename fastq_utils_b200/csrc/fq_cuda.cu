@@ -370,6 +370,90 @@ fq_pair_compare_kernel(const PairParams P) {
   }
 }
 
+/* ------------------------------------------------------------------------------------------------ multi-GPU: names to owners */
+__global__ void __launch_bounds__(256)
+fq_names_count_kernel(const FqName* __restrict__ names, uint32_t nrec, uint32_t world, unsigned long long* out) {
+  __shared__ unsigned long long sc[2 * FQ_SHARD_MAX_SRC];
+  if (threadIdx.x < 2 * world) sc[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nrec; k += gridDim.x * blockDim.x) {
+    unsigned long long h = names[k].hash;
+    if (h == FQ_HASH_SKIP) continue;
+    uint32_t o = fq_owner_of(h, world);
+    atomicAdd(&sc[2 * o], 1ull); atomicAdd(&sc[2 * o + 1], (unsigned long long)names[k].len);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * world && sc[threadIdx.x]) atomicAdd(out + threadIdx.x, sc[threadIdx.x]);
+}
+
+/* block-aggregated reservation: shared-memory atomics hand out positions inside the block's share, one global atomic per owner
+ * and block reserves the share */
+__global__ void __launch_bounds__(256)
+fq_names_pack_kernel(const FqName* __restrict__ names, const uint8_t* __restrict__ data, uint32_t nrec, unsigned long long g0, uint32_t world,
+                     FqPackedName* meta, uint8_t* blob, const unsigned long long* __restrict__ base, unsigned long long* cursor) {
+  __shared__ unsigned long long s_cnt[2 * FQ_SHARD_MAX_SRC], s_base[2 * FQ_SHARD_MAX_SRC];
+  for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < nrec; b0 += gridDim.x * blockDim.x) {
+    if (threadIdx.x < 2 * world) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t k = b0 + threadIdx.x;
+    FqName nm; nm.hash = FQ_HASH_SKIP; nm.off = 0; nm.len = 0;
+    if (k < nrec) nm = names[k];
+    bool valid = nm.hash != FQ_HASH_SKIP;
+    uint32_t o = 0; unsigned long long my_m = 0, my_b = 0;
+    if (valid) { o = fq_owner_of(nm.hash, world); my_m = atomicAdd(&s_cnt[2 * o], 1ull); my_b = atomicAdd(&s_cnt[2 * o + 1], (unsigned long long)nm.len); }
+    __syncthreads();
+    if (threadIdx.x < 2 * world) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(cursor + threadIdx.x, s_cnt[threadIdx.x]) : 0ull;
+    __syncthreads();
+    if (valid) {
+      unsigned long long bo = s_base[2 * o + 1] + my_b;
+      FqPackedName pn; pn.hash = nm.hash; pn.record = g0 + k; pn.off = (uint32_t)bo; pn.len = nm.len;
+      meta[base[2 * o] + s_base[2 * o] + my_m] = pn;
+      uint8_t* dst = blob + base[2 * o + 1] + bo; const uint8_t* src = data + nm.off;
+      for (uint32_t i = 0; i < nm.len; i++) dst[i] = src[i];
+    }
+    __syncthreads();
+  }
+}
+
+struct ShardParams { FqShardArgs a; };
+__device__ __forceinline__ const uint8_t* shard_name(const FqShardArgs& a, unsigned long long pos, uint32_t* len) {
+  uint32_t src = 0;
+  while (src + 1 < a.n_src && pos >= a.meta_start[src + 1]) src++;
+  const FqPackedName pn = a.meta[pos];
+  *len = pn.len;
+  return a.blob + a.blob_start[src] + pn.off;
+}
+__global__ void __launch_bounds__(256)
+fq_shard_insert_kernel(const ShardParams P) {
+  const FqShardArgs& a = P.a;
+  const unsigned long long posmask = (1ull << FQ_SHARD_POS_BITS) - 1;
+  for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; m < a.n; m += (unsigned long long)gridDim.x * blockDim.x) {
+    const FqPackedName pn = a.meta[m];
+    const unsigned long long mine = (pn.record << FQ_SHARD_POS_BITS) | m; /* orders by record index first */
+    unsigned long long i = pn.hash & a.mask, probes = 0;
+    for (;; i = (i + 1) & a.mask) {
+      if (++probes > a.mask) { atomicExch(a.counters + 2, 1ull); break; }
+      FqSlot* s = a.slots + i;
+      unsigned long long cur = ld_volatile64(&s->hash);
+      if (cur == FQ_HASH_EMPTY) cur = atomicCAS(&s->hash, FQ_HASH_EMPTY, pn.hash);
+      if (cur != FQ_HASH_EMPTY && cur != pn.hash) continue;
+      unsigned long long old = atomicMin(&s->idx1, mine);
+      if (old != FQ_IDX_NONE) {
+        uint32_t ol, ml; const uint8_t* on = shard_name(a, old & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
+        if (ol == ml && fq_bytes_equal(on, mn, ml)) {
+          unsigned long long og = old >> FQ_SHARD_POS_BITS, later = og > pn.record ? og : pn.record;
+          atomicMin(a.dup_key, FQ_KEY(later, FQ_R_NAME));
+        } else atomicAdd(a.counters + 0, 1ull);
+      }
+      break;
+    }
+  }
+}
+__global__ void fq_shard_find_kernel(const FqPackedName* __restrict__ meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) {
+  for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (unsigned long long)gridDim.x * blockDim.x)
+    if (meta[m].record == record) atomicMin(out_pos, m);
+}
+
 /* ------------------------------------------------------------------------------------------------ the device */
 class FqCudaDevice : public FqDevice {
  public:
@@ -499,6 +583,35 @@ class FqCudaDevice : public FqDevice {
     tic(FQG_K_PAIR, 0, a.npairs);
     fq_pair_compare_kernel<<<grid, 256, 0, st_>>>(P);
     toc();
+    launched();
+  }
+  void names_count(const FqName* names, uint32_t nrec, uint32_t world, unsigned long long* out) override {
+    if (!nrec) return;
+    int grid = (int)std::min<uint32_t>((nrec + 255) / 256, (uint32_t)sms_ * 8);
+    tic(FQG_K_OTHER, 0, nrec);
+    fq_names_count_kernel<<<grid, 256, 0, st_>>>(names, nrec, world, out);
+    toc(); launched();
+  }
+  void names_pack(const FqName* names, const uint8_t* data, uint32_t nrec, uint64_t g0, uint32_t world, FqPackedName* meta, uint8_t* blob,
+                  const unsigned long long* base, unsigned long long* cursor) override {
+    if (!nrec) return;
+    int grid = (int)std::min<uint32_t>((nrec + 255) / 256, (uint32_t)sms_ * 8);
+    tic(FQG_K_OTHER, 0, nrec);
+    fq_names_pack_kernel<<<grid, 256, 0, st_>>>(names, data, nrec, g0, world, meta, blob, base, cursor);
+    toc(); launched();
+  }
+  void shard_insert(const FqShardArgs& a) override {
+    if (!a.n) return;
+    ShardParams P; P.a = a;
+    int grid = (int)std::min<unsigned long long>((a.n + 255) / 256, (unsigned long long)sms_ * 8);
+    tic(FQG_K_INDEX, 0, a.n);
+    fq_shard_insert_kernel<<<grid, 256, 0, st_>>>(P);
+    toc(); launched();
+  }
+  void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {
+    if (!n) return;
+    int grid = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)sms_ * 8);
+    fq_shard_find_kernel<<<grid, 256, 0, st_>>>(meta, n, record, out_pos);
     launched();
   }
   void explain(const uint8_t* data, const FqLine* L, const FqRecCtx& cx, FqRecOut* out_dev) override {

@@ -51,6 +51,19 @@ typedef struct {
   unsigned long long* key;
 } FqPairArgs;
 
+/* a name on its way to the owner of its hash (multi-GPU sharded index); same layout as fqg_packed_name */
+typedef struct { unsigned long long hash; unsigned long long record; uint32_t off; uint32_t len; } FqPackedName;
+#define FQ_SHARD_POS_BITS 28
+#define FQ_SHARD_MAX_SRC 64
+typedef struct {
+  const FqPackedName* meta; unsigned long long n; const uint8_t* blob;
+  uint32_t n_src; unsigned long long meta_start[FQ_SHARD_MAX_SRC + 1]; unsigned long long blob_start[FQ_SHARD_MAX_SRC];
+  FqSlot* slots; unsigned long long mask;
+  unsigned long long* dup_key;   /* min event key of a duplicate */
+  unsigned long long* counters;  /* [0] collisions, [2] table full */
+} FqShardArgs;
+FQ_HD uint32_t fq_owner_of(uint64_t hash, uint32_t world) { return (uint32_t)((hash >> 40) % world); }
+
 class FqDevice {
  public:
   virtual ~FqDevice() {}
@@ -80,6 +93,12 @@ class FqDevice {
   virtual void index_insert(const FqTableArgs& a) = 0;
   virtual void mate_claim(const FqTableArgs& a) = 0;
   virtual void pair_compare(const FqPairArgs& a) = 0;
+  /* multi-GPU: per-owner counts (out[2*o] names, out[2*o+1] bytes), packing, owner-side insert, lookup of a record's tuple */
+  virtual void names_count(const FqName* names, uint32_t nrec, uint32_t world, unsigned long long* out) = 0;
+  virtual void names_pack(const FqName* names, const uint8_t* data, uint32_t nrec, uint64_t g0, uint32_t world, FqPackedName* meta,
+                          uint8_t* blob, const unsigned long long* base, unsigned long long* cursor) = 0;
+  virtual void shard_insert(const FqShardArgs& a) = 0;
+  virtual void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) = 0;
   /* details of one record for the error message */
   virtual void explain(const uint8_t* data, const FqLine* lines4_host, const FqRecCtx& cx, FqRecOut* out_dev) = 0;
   /* device-side stopwatch on the stream (CUDA events) */

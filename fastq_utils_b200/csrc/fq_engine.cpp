@@ -38,6 +38,7 @@ void FqEngine::free_file(FqFile& F) {
   for (auto& b : F.bufs) { if (b.owned && b.data) dev_->release(b.data); if (b.line_end) dev_->release(b.line_end); }
   if (F.pend) dev_->release(F.pend);
   if (F.dir_dev) dev_->release(F.dir_dev);
+  for (auto& ps : F.prescans) dev_->release(ps.line_end);
   FqStats* st = F.stats; unsigned long long* h = F.hist;
   F = FqFile();
   F.stats = st; F.hist = h;
@@ -147,6 +148,19 @@ void FqEngine::flush_pending_as_last(int file) {
   add_buffer(file, bd, (uint32_t)bn, true, true);
 }
 
+/* K1: line index.  Capacity is a guess (one line per 32 bytes); on overflow rescan with the exact count. */
+void FqEngine::scan_buffer(FqBuffer& B, bool last) {
+  uint32_t cap = B.n / 32 + 4096;
+  for (;;) {
+    B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
+    dev_->scan_lines(B.data, B.n, last ? 1 : 0, B.line_end, cap, scratch_);
+    uint32_t out2[2]; dev_->download(out2, scratch_, sizeof out2);
+    B.nlines = out2[0];
+    if (!out2[1]) break;
+    dev_->release(B.line_end); cap = B.nlines;
+  }
+}
+
 void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned) {
   FqFile& F = f_[file];
   if (F.ended) throw std::runtime_error("fqg_feed after the end of the file");
@@ -163,18 +177,21 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
   {
     FqBuffer& B = F.bufs[b];
     B.data = data; B.n = n; B.owned = owned;
-    /* K1: line index.  Capacity is a guess (one line per 32 bytes); on overflow rescan with the exact count. */
-    uint32_t cap = n / 32 + 4096;
-    for (;;) {
-      B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
-      dev_->scan_lines(data, n, last ? 1 : 0, B.line_end, cap, scratch_);
-      uint32_t out2[2]; dev_->download(out2, scratch_, sizeof out2);
-      B.nlines = out2[0];
-      if (!out2[1]) break;
-      dev_->release(B.line_end); cap = B.nlines;
+    bool cached = false;
+    for (size_t i = 0; i < F.prescans.size(); i++) {
+      FqFile::Prescan& ps = F.prescans[i];
+      if (ps.data == data && ps.n == n && ps.last == last) { B.line_end = ps.line_end; B.nlines = ps.nlines; F.prescans.erase(F.prescans.begin() + i); cached = true; break; }
     }
+    if (!cached) scan_buffer(B, last);
   }
   uint32_t pos = 0, j = 0;
+  if (!F.started) { /* multi-GPU: the first lines of a range belong to the previous range's last record */
+    F.started = true;
+    if (F.start_skip) {
+      if (F.bufs[b].nlines < F.start_skip) throw std::runtime_error("fqg_set_stream_start: the first buffer holds fewer lines than skip_lines");
+      j = F.start_skip; pos = line_end_at(F.bufs[b], j - 1);
+    }
+  }
   /* bridge: finish the record that straddles the previous chunk boundary in a small chunk of its own */
   while (F.pend_n > 0 && !F.ended) {
     const FqBuffer B = F.bufs[b];
@@ -326,6 +343,7 @@ void FqEngine::launch_names(int file, size_t si, uint32_t nrec) {
   const FqSegment& s = F.segs[si];
   int loop = loop_of(file);
   if (loop != FQ_LOOP_INDEX && loop != FQ_LOOP_MATE) return;
+  if (cfg_.flags & FQG_FLAG_EXTERNAL_INDEX) return; /* the names go to the owners of their hashes instead (fqg_names_pack) */
   FqTableArgs t; memset(&t, 0, sizeof t);
   t.names = s.names; t.data = F.bufs[s.buf].data; t.nrec = nrec; t.g0 = s.g0; t.step_base = step_base(file);
   t.key = key_; t.counters = counters_;
@@ -354,7 +372,7 @@ void FqEngine::launch_segment(int file, size_t si) {
   const FqBuffer& B = F.bufs[s.buf];
   FqRecordsArgs a; memset(&a, 0, sizeof a);
   a.data = B.data; a.line_end = B.line_end; a.lines = s.explicit_lines ? s.lines_dev : nullptr;
-  a.q = s.q; a.j0 = s.j0; a.nrec = nrec; a.span_bytes = s.span; a.g0 = s.g0; a.step_base = step_base(file);
+  a.q = s.q; a.j0 = s.j0; a.nrec = nrec; a.span_bytes = s.span; a.g0 = s.g0 + F.g_base; a.step_base = step_base(file);
   a.cx = make_ctx(file);
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
   a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats;
@@ -486,7 +504,7 @@ void FqEngine::finish(fqg_report* rep) {
     have_end = false;
     switch (cfg_.mode) {
       case FQG_MODE_SINGLE: case FQG_MODE_INDEX:
-        if (t0 > 0) offer(FQ_KEY(N0, FQ_R_TRUNC), FQ_E_TRUNC, 0, 4 * N0, 0);
+        if (t0 > 0) offer(FQ_KEY(f_[0].g_base + N0, FQ_R_TRUNC), FQ_E_TRUNC, 0, 4 * (f_[0].g_base + N0), 0);
         break;
       case FQG_MODE_INDEX_PAIR:
         if (t0 > 0) offer(FQ_KEY(N0, FQ_R_TRUNC), FQ_E_TRUNC, 0, 4 * N0, 0);
@@ -522,7 +540,7 @@ void FqEngine::finish(fqg_report* rep) {
       bool restricted = false;
       switch (cfg_.mode) {
         case FQG_MODE_SINGLE: case FQG_MODE_INDEX:
-          if (rank == FQ_R_STOP) { f_[0].limit = step; restricted = true; }
+          if (rank == FQ_R_STOP) { f_[0].limit = step - f_[0].g_base; restricted = true; }
           break;
         case FQG_MODE_INDEX_PAIR:
           if (rank == FQ_R_STOP) {
@@ -591,6 +609,7 @@ void FqEngine::finish(fqg_report* rep) {
   } else {
     fill_error(rep, dev_key, 0, 0, 0, 0);
   }
+  rep->error.event_key = first;
   fill_stats(rep);
   /* which sniff lines the reference had printed by the time it stopped */
   {
@@ -636,7 +655,7 @@ void FqEngine::fill_error(fqg_report* rep, uint64_t key, int host_code, int host
     case FQG_MODE_SINGLE: case FQG_MODE_INDEX: case FQG_MODE_INDEX_PAIR: {
       bool mate = cfg_.mode == FQG_MODE_INDEX_PAIR && step >= N0 + 1;
       file = mate ? 1 : 0; g = mate ? step - (N0 + 1) : step; msg_file = file;
-      L = 4 * (g + 1);
+      L = 4 * (g + 1); /* g is global here; made local below for the lookup */
       if (rank == FQ_R_TRUNC) { code = FQ_E_TRUNC; L = 4 * g; }
       else if (rank == FQ_R_WRONGHDR) code = FQ_E_WRONGHDR;
       else if (rank == FQ_R_NAME) code = mate ? FQ_E_UNPAIRED : FQ_E_DUP;
@@ -672,7 +691,7 @@ void FqEngine::fill_error(fqg_report* rep, uint64_t key, int host_code, int host
   e.file = file; e.msg_file = msg_file; e.record = g;
   /* details from the record itself */
   FqLine Ls[4]; const uint8_t* data;
-  record_lines(file, g, Ls, &data);
+  record_lines(file, g - f_[file].g_base, Ls, &data);
   FqRecCtx cx = make_ctx(file);
   dev_->explain(data, Ls, cx, recout_);
   FqRecOut o; dev_->download(&o, recout_, sizeof o);
@@ -749,4 +768,114 @@ void FqEngine::index_records(const void* host_bytes, size_t n, uint64_t* starts,
   if (out2[0]) dev_->download(h.data(), le, (size_t)out2[0] * 4);
   for (uint64_t i = 0; i < nrec && i < cap; i++) starts[i] = i == 0 ? 0 : h[4 * i - 1];
   dev_->release(le); dev_->release(d);
+}
+
+/* ------------------------------------------------------------------------------------------------ multi-GPU building blocks */
+void FqEngine::prescan_device(int file, const void* dptr, size_t n, bool at_eof, uint64_t* n_lines, int32_t* ends_lf, uint64_t first_ends[4]) {
+  FqFile& F = f_[file];
+  const uint8_t* p = (const uint8_t*)dptr;
+  uint64_t total = 0, off = 0; int got = 0;
+  for (int i = 0; i < 4; i++) first_ends[i] = ~0ull;
+  while (n) {
+    size_t k = std::min(n, kMaxChunk);
+    FqBuffer B; B.data = (uint8_t*)p; B.n = (uint32_t)k;
+    bool last = at_eof && k == n;
+    scan_buffer(B, last);
+    if (got < 4 && B.nlines) {
+      uint32_t e[4]; uint32_t take = std::min<uint32_t>(4 - got, B.nlines);
+      dev_->download(e, B.line_end, take * sizeof(uint32_t));
+      for (uint32_t i = 0; i < take; i++) first_ends[got++] = off + e[i];
+    }
+    FqFile::Prescan ps; ps.data = p; ps.n = (uint32_t)k; ps.last = last; ps.line_end = B.line_end; ps.nlines = B.nlines;
+    F.prescans.push_back(ps);
+    total += B.nlines; p += k; n -= k; off += k;
+    if (n == 0) { uint8_t c = 0; dev_->download(&c, p - 1, 1); *ends_lf = c == '\n'; }
+  }
+  *n_lines = total;
+}
+
+void FqEngine::set_stream_start(int file, uint32_t skip_lines, uint64_t first_record) {
+  FqFile& F = f_[file];
+  if (F.started) throw std::runtime_error("fqg_set_stream_start after the first feed");
+  if (first_record && !(cfg_.mode == FQG_MODE_SINGLE || (cfg_.mode == FQG_MODE_INDEX && (cfg_.flags & FQG_FLAG_EXTERNAL_INDEX))))
+    throw std::runtime_error("fqg_set_stream_start: a record offset needs FQG_MODE_SINGLE or FQG_MODE_INDEX with FQG_FLAG_EXTERNAL_INDEX");
+  F.start_skip = skip_lines; F.g_base = first_record;
+}
+
+void FqEngine::names_count(int file, uint32_t world, uint64_t* counts, uint64_t* bytes) {
+  if (world == 0 || world > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_names_count: world out of range");
+  FqFile& F = f_[file];
+  unsigned long long* d = (unsigned long long*)dev_->alloc(2 * world * sizeof(unsigned long long));
+  dev_->fill(d, 0, 2 * world * sizeof(unsigned long long));
+  uint64_t lim = eff_records(F);
+  for (auto& s : F.segs) {
+    if (s.g0 >= lim || !s.names) continue;
+    dev_->names_count(s.names, (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0), world, d);
+  }
+  std::vector<unsigned long long> h(2 * world);
+  dev_->download(h.data(), d, h.size() * sizeof(unsigned long long));
+  for (uint32_t o = 0; o < world; o++) { counts[o] = h[2 * o]; bytes[o] = h[2 * o + 1]; }
+  dev_->release(d);
+}
+
+void FqEngine::names_pack(int file, uint32_t world, void* meta, void* blob, const uint64_t* meta_base, const uint64_t* blob_base) {
+  if (world == 0 || world > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_names_pack: world out of range");
+  FqFile& F = f_[file];
+  std::vector<unsigned long long> h(2 * world);
+  for (uint32_t o = 0; o < world; o++) { h[2 * o] = meta_base[o]; h[2 * o + 1] = blob_base[o]; }
+  unsigned long long* base = (unsigned long long*)dev_->alloc(4 * world * sizeof(unsigned long long));
+  unsigned long long* cursor = base + 2 * world;
+  dev_->upload(base, h.data(), 2 * world * sizeof(unsigned long long));
+  dev_->fill(cursor, 0, 2 * world * sizeof(unsigned long long));
+  uint64_t lim = eff_records(F);
+  for (auto& s : F.segs) {
+    if (s.g0 >= lim || !s.names) continue;
+    dev_->names_pack(s.names, F.bufs[s.buf].data, (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0), s.g0 + F.g_base, world,
+                     (FqPackedName*)meta, (uint8_t*)blob, base, cursor);
+  }
+  dev_->sync(); /* h is a local */
+  dev_->release(base);
+}
+
+void FqEngine::shard_insert(const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start) {
+  if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_insert: n_src out of range");
+  if (n >= (1ull << FQ_SHARD_POS_BITS)) throw std::runtime_error("fqg_shard_insert: more than 2^28 names for one owner");
+  dev_->fill(counters_ + 3, 0xFF, sizeof(unsigned long long));
+  shard_meta_ = (const FqPackedName*)meta; shard_n_ = n; shard_blob_ = (const uint8_t*)blob; shard_nsrc_ = n_src;
+  for (uint32_t i = 0; i <= n_src; i++) shard_meta_start_[i] = meta_start[i];
+  for (uint32_t i = 0; i < n_src; i++) shard_blob_start_[i] = blob_start[i];
+  if (!n) return;
+  table_names_ = 0;
+  ensure_table(n);
+  FqShardArgs a; memset(&a, 0, sizeof a);
+  a.meta = shard_meta_; a.n = n; a.blob = shard_blob_; a.n_src = n_src;
+  memcpy(a.meta_start, shard_meta_start_, sizeof(unsigned long long) * (n_src + 1));
+  memcpy(a.blob_start, shard_blob_start_, sizeof(unsigned long long) * n_src);
+  a.slots = slots_; a.mask = table_cap_ - 1; a.dup_key = counters_ + 3; a.counters = counters_;
+  dev_->shard_insert(a);
+  table_names_ = n;
+}
+
+void FqEngine::shard_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* collisions) {
+  unsigned long long ctr[4]; dev_->download(ctr, counters_, sizeof ctr);
+  if (ctr[2]) throw std::runtime_error("index table overflow");
+  *collisions = ctr[0]; *key = ctr[3]; *record = 0; *name_len = 0; name[0] = 0;
+  if (ctr[3] == FQ_KEY_NONE || !shard_n_) return;
+  *record = FQ_KEY_STEP(ctr[3]);
+  unsigned long long* d = (unsigned long long*)dev_->alloc(sizeof(unsigned long long));
+  dev_->fill(d, 0xFF, sizeof(unsigned long long));
+  dev_->shard_find(shard_meta_, shard_n_, *record, d);
+  unsigned long long pos; dev_->download(&pos, d, sizeof pos);
+  dev_->release(d);
+  if (pos == ~0ull) return;
+  FqPackedName pn; dev_->download(&pn, shard_meta_ + pos, sizeof pn);
+  uint32_t src = 0; while (src + 1 < shard_nsrc_ && pos >= shard_meta_start_[src + 1]) src++;
+  uint32_t len = std::min<uint32_t>(pn.len, 1023);
+  if (len) dev_->download(name, shard_blob_ + shard_blob_start_[src] + pn.off, len);
+  name[len] = 0; *name_len = len;
+}
+
+void FqEngine::hist_range(int file, uint64_t lo, uint64_t hi, uint64_t* out) {
+  if (hi < lo || hi >= FQ_MAX_READ_LENGTH) throw std::runtime_error("fqg_hist_range: bad range");
+  dev_->download(out, f_[file].hist + lo, (hi - lo + 1) * sizeof(unsigned long long));
 }

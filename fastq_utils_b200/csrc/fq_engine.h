@@ -46,6 +46,12 @@ struct FqFile {
   FqStats* stats = nullptr; unsigned long long* hist = nullptr; /* device */
   FqDirEntry* dir_dev = nullptr; size_t dir_cap = 0; std::vector<FqDirEntry> dir_host; size_t dir_synced = 0;
   uint64_t limit = ~0ull;   /* records at or beyond this index are never read (early clean end of file) */
+  /* multi-GPU: this context holds a range of the file */
+  uint64_t g_base = 0;      /* index (inside the whole file) of the first record of this stream */
+  uint32_t start_skip = 0;  /* lines of the first buffer that belong to the previous range */
+  bool started = false;
+  struct Prescan { const uint8_t* data; uint32_t n; bool last; uint32_t* line_end; uint32_t nlines; };
+  std::vector<Prescan> prescans;
 };
 
 class FqEngine {
@@ -57,6 +63,13 @@ class FqEngine {
   void finish(fqg_report* rep);
   void reset();
   void index_records(const void* host_bytes, size_t n, uint64_t* starts, size_t cap, uint64_t* n_records);
+  void prescan_device(int file, const void* dptr, size_t n, bool at_eof, uint64_t* n_lines, int32_t* ends_lf, uint64_t first_ends[4]);
+  void set_stream_start(int file, uint32_t skip_lines, uint64_t first_record);
+  void names_count(int file, uint32_t world, uint64_t* counts, uint64_t* bytes);
+  void names_pack(int file, uint32_t world, void* meta, void* blob, const uint64_t* meta_base, const uint64_t* blob_base);
+  void shard_insert(const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start);
+  void shard_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* collisions);
+  void hist_range(int file, uint64_t lo, uint64_t hi, uint64_t* out);
   FqDevice* device() { return dev_; }
   std::string last_error;
 
@@ -70,6 +83,9 @@ class FqEngine {
   FqRecOut* recout_ = nullptr;              /* device: explain result */
   FqSlot* slots_ = nullptr; uint64_t table_cap_ = 0; uint64_t table_names_ = 0;
   uint32_t seed_ = 0;
+  const FqPackedName* shard_meta_ = nullptr; uint64_t shard_n_ = 0; const uint8_t* shard_blob_ = nullptr;
+  uint32_t shard_nsrc_ = 0; uint64_t shard_meta_start_[FQ_SHARD_MAX_SRC + 1], shard_blob_start_[FQ_SHARD_MAX_SRC];
+  void scan_buffer(FqBuffer& B, bool last);
   bool finished_ = false;
 
   int nfiles() const { return cfg_.mode == FQG_MODE_INDEX_PAIR || cfg_.mode == FQG_MODE_SORTED_PAIR ? 2 : 1; }

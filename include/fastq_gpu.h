@@ -46,6 +46,8 @@ typedef struct {
 /* FQG_MODE_INDEX only: a second file operand exists but is never read (`-s f1 f2` without -r): the reference still
  * strips the mate digit from default-format names (is_pe, src/fastq_info.c:290) */
 #define FQG_FLAG_PAIRED_NAMES 1u
+/* the read-name index lives elsewhere (sharded over GPUs): names are exported with fqg_names_* instead of inserted */
+#define FQG_FLAG_EXTERNAL_INDEX 2u
 
 /* statistics of one FASTQ_FILE as the reference holds them at the end of its loops (src/fastq.h:110-131) */
 typedef struct {
@@ -72,6 +74,7 @@ typedef struct {
   uint64_t record;       /* index of the record inside `file`                                     */
   uint64_t line;         /* the line number the reference prints                                  */
   uint64_t a, b;         /* slen / qlen, read number, count of unpaired reads                      */
+  uint64_t event_key;    /* position of the event in the reference's sequential order (smaller = earlier); ~0 when none */
   uint32_t hdr1_len, hdr2_len, name_len;
   char hdr1[1024];       /* raw lines as C strings, for the messages that quote them              */
   char hdr2[1024];
@@ -126,6 +129,29 @@ void fqg_transcript_free(fqg_transcript* t);
  * be opened" (src/fastq.c:651-655).  chunk_bytes > 0 feeds the streams in pieces of that size. */
 int fqg_fastq_info_mem(int argc, const char** argv, const void* f1, size_t n1, const void* f2, size_t n2,
                        int device, size_t chunk_bytes, fqg_transcript* t);
+
+/* ---- multi-GPU building blocks (fastq_utils_b200/dist.py drives them with torch.distributed) ----
+ * A rank holds a contiguous byte range of a file.  fqg_prescan_device builds the line index of the range (kept for the
+ * following fqg_feed_device of the same pointer) and reports what the ranks exchange to fix each range's line phase. */
+int fqg_prescan_device(fqg_ctx* ctx, int file, const void* device_bytes, size_t n, int at_eof,
+                       uint64_t* n_lines, int32_t* ends_with_lf, uint64_t first_line_ends[4]);
+/* the first record of this context's stream starts after `skip_lines` lines of the first fed buffer and is record
+ * number `first_record` of the whole file (event keys, line numbers and name indices become global) */
+int fqg_set_stream_start(fqg_ctx* ctx, int file, uint32_t skip_lines, uint64_t first_record);
+/* names of all records fed so far, routed by hash to `world` owners: sizes, then the packed tuples
+ * (24-byte fqg_packed_name grouped by owner + the name bytes grouped by owner) into caller-provided device memory */
+typedef struct { uint64_t hash; uint64_t record; uint32_t off; uint32_t len; } fqg_packed_name;
+int fqg_names_count(fqg_ctx* ctx, int file, uint32_t world, uint64_t* counts, uint64_t* bytes);
+int fqg_names_pack(fqg_ctx* ctx, int file, uint32_t world, void* device_meta, void* device_blob,
+                   const uint64_t* meta_base, const uint64_t* blob_base);
+/* owner side: insert received tuples (n_src groups, group s = metas [meta_start[s], meta_start[s+1]) whose `off` is
+ * relative to blob_start[s]) into this context's index shard; the buffers must stay valid until fqg_shard_result */
+int fqg_shard_insert(fqg_ctx* ctx, const void* device_meta, uint64_t n, const void* device_blob, uint32_t n_src,
+                     const uint64_t* meta_start, const uint64_t* blob_start);
+/* earliest duplicate this shard saw: event key (~0 = none), the later record's index and the name */
+int fqg_shard_result(fqg_ctx* ctx, uint64_t* event_key, uint64_t* record, char name[1024], uint32_t* name_len, uint64_t* hash_collisions);
+/* bins [lo, hi] of a file's read-length histogram (terminator included, like the reference's rdlen_ctr) */
+int fqg_hist_range(fqg_ctx* ctx, int file, uint64_t lo, uint64_t hi, uint64_t* out);
 
 /* ---- per-kernel device timing (CUDA events around every launch on the context's stream) ---- */
 enum { FQG_K_SCAN = 0, FQG_K_RECORDS = 1, FQG_K_INDEX = 2, FQG_K_MATE = 3, FQG_K_PAIR = 4, FQG_K_OTHER = 5, FQG_K_COUNT = 6 };

@@ -1,0 +1,49 @@
+"""Worker for tests/test_dist_gloo.py: run by torch.distributed.run with N ranks on CPU (gloo).  Uses the sequential
+stand-in device (tests/sim) behind the same C ABI and the same fastq_utils_b200.dist orchestration as the GPU path."""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ["FQG_SIM_LIBRARY_FOR_TESTS"] = os.path.join(ROOT, "tests", "sim", "libfastq_sim.so")
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import fastq_utils_b200 as fq  # noqa: E402
+from fastq_utils_b200 import dist as fqdist  # noqa: E402
+
+
+def main():
+    cases = json.load(open(sys.argv[1]))
+    dist.init_process_group("gloo")
+    r, W = dist.get_rank(), dist.get_world_size()
+    out = []
+    for c in cases:
+        data = bytes.fromhex(c["hex"])
+        cuts = [int(len(data) * x) for x in c["cuts"]][:W - 1]
+        cuts = [0] + sorted(cuts) + [len(data)]
+        while len(cuts) < W + 1:
+            cuts.insert(-1, cuts[-1])
+        lo, hi = cuts[r], cuts[r + 1]
+        mine = bytearray(data[lo:hi]) + bytearray(64)
+        buf = (ctypes.c_uint8 * len(mine)).from_buffer(mine)
+        mode = fq.MODE_SINGLE if c["mode"] == "single" else fq.MODE_INDEX
+        try:
+            run = fqdist.ShardedFastqInfo(mode, device=0, tensor_device=torch.device("cpu"))
+            res = run.run_device(ctypes.addressof(buf), hi - lo, name="a.fq")
+            tr = res.get("transcript")
+        except (NotImplementedError, RuntimeError) as ex:
+            tr = ["EXC", type(ex).__name__, str(ex)]
+        if r == 0:
+            out.append(list(tr))
+        dist.barrier()
+    if r == 0:
+        json.dump(out, open(sys.argv[2], "w"))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,7 @@
  * (fq_record.h) can be exercised without a GPU.  Built into tests/sim/libfastq_sim.so by tests/sim/Makefile;
  * never linked into libfastq_gpu.so and never used by bench.py or the -m gpu tests.
  */
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -163,6 +164,58 @@ class FqSimDevice : public FqDevice {
       bool same = x.hash == y.hash && x.len == y.len && fq_bytes_equal(a.da + x.off, a.db + y.off, x.len);
       if (!same) { uint64_t key = FQ_KEY(a.p0 + k, a.rank); if (key < *a.key) *a.key = key; }
     }
+  }
+  void names_count(const FqName* names, uint32_t nrec, uint32_t world, unsigned long long* out) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < nrec; k++) {
+      if (names[k].hash == FQ_HASH_SKIP) continue;
+      uint32_t o = fq_owner_of(names[k].hash, world);
+      out[2 * o]++; out[2 * o + 1] += names[k].len;
+    }
+  }
+  void names_pack(const FqName* names, const uint8_t* data, uint32_t nrec, uint64_t g0, uint32_t world, FqPackedName* meta, uint8_t* blob,
+                  const unsigned long long* base, unsigned long long* cursor) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < nrec; k++) {
+      const FqName& nm = names[k];
+      if (nm.hash == FQ_HASH_SKIP) continue;
+      uint32_t o = fq_owner_of(nm.hash, world);
+      unsigned long long mi = cursor[2 * o]++, bo = cursor[2 * o + 1]; cursor[2 * o + 1] += nm.len;
+      FqPackedName& pn = meta[base[2 * o] + mi];
+      pn.hash = nm.hash; pn.record = g0 + k; pn.off = (uint32_t)bo; pn.len = nm.len;
+      memcpy(blob + base[2 * o + 1] + bo, data + nm.off, nm.len);
+    }
+  }
+  static const uint8_t* shard_name(const FqShardArgs& a, unsigned long long pos, uint32_t* len) {
+    uint32_t src = 0; while (src + 1 < a.n_src && pos >= a.meta_start[src + 1]) src++;
+    *len = a.meta[pos].len;
+    return a.blob + a.blob_start[src] + a.meta[pos].off;
+  }
+  void shard_insert(const FqShardArgs& a) override {
+    n_launch_++;
+    const unsigned long long posmask = (1ull << FQ_SHARD_POS_BITS) - 1;
+    for (unsigned long long m = 0; m < a.n; m++) {
+      const FqPackedName& pn = a.meta[m];
+      unsigned long long i = pn.hash & a.mask, probes = 0, mine = (pn.record << FQ_SHARD_POS_BITS) | m;
+      for (;; i = (i + 1) & a.mask) {
+        if (++probes > a.mask) { a.counters[2] = 1; break; }
+        FqSlot& s = a.slots[i];
+        if (s.hash == FQ_HASH_EMPTY) { s.hash = pn.hash; s.idx1 = mine; break; }
+        if (s.hash != pn.hash) continue;
+        unsigned long long old = s.idx1; if (mine < old) s.idx1 = mine;
+        uint32_t ol, ml; const uint8_t* on = shard_name(a, old & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
+        if (ol == ml && fq_bytes_equal(on, mn, ml)) {
+          unsigned long long later = std::max(old >> FQ_SHARD_POS_BITS, (unsigned long long)pn.record);
+          unsigned long long key = FQ_KEY(later, FQ_R_NAME);
+          if (key < *a.dup_key) *a.dup_key = key;
+        } else a.counters[0]++;
+        break;
+      }
+    }
+  }
+  void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {
+    n_launch_++;
+    for (unsigned long long m = 0; m < n; m++) if (meta[m].record == record && m < *out_pos) *out_pos = m;
   }
   void explain(const uint8_t* data, const FqLine* lines4, const FqRecCtx& cx, FqRecOut* out) override {
     n_launch_++;

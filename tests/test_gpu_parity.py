@@ -177,3 +177,23 @@ def test_longreads_match_oracle():
     for argv in (["-r", "a.fq"], ["a.fq"]):
         assert fqg_run(argv, data, None, chunk=0, kind="gpu") == oracle_run(argv, data, None), argv
     assert fqg_run(["-r", "a.fq"], data, None, chunk=1 << 20, kind="gpu") == oracle_run(["-r", "a.fq"], data, None)
+
+
+def test_sharded_path_world1_matches_oracle():
+    """The multi-GPU orchestration with a single rank: prescan, stream start, name packing, shard insert, merged render."""
+    import torch
+    import fastq_utils_b200 as fq
+    from fastq_utils_b200 import dist as fqdist
+    rb = fq.illumina_record_bytes()
+    t, nb = _illumina(50_000)
+    for mode, argv in ((fq.MODE_INDEX, ["a.fq"]), (fq.MODE_SINGLE, ["-r", "a.fq"])):
+        run = fqdist.ShardedFastqInfo(mode, device=0, n_hint=50_000)
+        res = run.run_device(t.data_ptr(), nb, name="a.fq")
+        data = bytes(t[:nb].cpu().numpy())
+        assert res["transcript"] == oracle_run(argv, data, None)
+    t[40_000 * rb:40_001 * rb] = t[5 * rb:6 * rb].clone()
+    t[45_000 * rb + 70] = ord("X")
+    torch.cuda.synchronize()
+    data = bytes(t[:nb].cpu().numpy())
+    run = fqdist.ShardedFastqInfo(fq.MODE_INDEX, device=0)
+    assert run.run_device(t.data_ptr(), nb, name="a.fq")["transcript"] == oracle_run(["a.fq"], data, None)
