@@ -37,8 +37,8 @@ def test_every_declared_symbol_is_exported(built):
 
 
 def test_no_torch_types_in_signatures():
-    text = open(HDR).read()
-    assert "torch" not in text and "at::" not in text and "std::" not in text
+    text = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)  # declarations only
+    assert "torch" not in text and "at::" not in text and "std::" not in text and "Tensor" not in text
 
 
 def test_create_fails_loudly_without_device(built):
