@@ -10,8 +10,8 @@ _SO = os.path.join(_HERE, "libfastq_gpu.so")
 _SO = os.environ.get("FQG_SIM_LIBRARY_FOR_TESTS", _SO)
 
 MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED, MODE_SORTED_PAIR = range(5)
-KERNEL_CLASSES = ["scan", "records", "index", "mate", "pair", "other"]
-FLAG_PAIRED_NAMES, FLAG_EXTERNAL_INDEX = 1, 2
+KERNEL_CLASSES = ["scan", "records", "index", "mate", "pair", "other", "tile"]
+FLAG_PAIRED_NAMES, FLAG_EXTERNAL_INDEX, FLAG_TWO_PASS = 1, 2, 4
 
 
 class Config(ctypes.Structure):

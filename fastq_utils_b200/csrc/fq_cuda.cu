@@ -284,6 +284,239 @@ fq_records_kernel(const RecParams P) {
   }
 }
 
+/* ------------------------------------------------------------------------------------------------ K1+K2 fused: one pass over HBM
+ * A persistent CTA claims 32 KiB tiles in order.  The tile plus a 4 KiB look-ahead margin (and the 16 bytes before it) is
+ * brought into shared memory by ONE bulk async copy (cp.async.bulk → UBLKCP, completion on an mbarrier).  From shared memory:
+ * LF masks → block prefix → decoupled look-back gives the tile's global line number → the line ends go out to the line index,
+ * and every record that STARTS in the tile is validated in place (one thread per record, fq_check_record on the shared window).
+ * Records whose four lines do not fit the window are counted in out[3]; the host then falls back to the two-pass path. */
+constexpr int TILE_BYTES = 32768, TILE_MARGIN = 4096, TILE_LEFT = 16;
+constexpr int TILE_WIN = TILE_LEFT + TILE_BYTES + TILE_MARGIN;
+constexpr int TILE_THREADS = 128;
+constexpr int TILE_LMAX = 2048;
+constexpr int TILE_CHUNKS_PER_THREAD = (TILE_BYTES + TILE_MARGIN) / 16 / TILE_THREADS; /* 18 */
+constexpr int TILE_SMEM = TILE_WIN + 48 + TILE_LMAX * 2;
+static_assert((TILE_BYTES + TILE_MARGIN) / 16 % TILE_THREADS == 0, "chunks must divide evenly");
+
+struct TileParams {
+  const uint8_t* data; uint32_t n; int virtual_end; uint32_t* line_end; uint32_t cap;
+  unsigned long long* tile_state; uint32_t* ticket; uint32_t ntiles;
+  uint32_t* out; /* [0] lines, [1] cap overflow, [2] first over-long header line, [3] records that did not fit, [4] internal error */
+  uint32_t j0, max_rec; unsigned long long g0, step_base; FqRecCtx cx;
+  FqStats* stats; FqStats* stats_range; unsigned long long* hist; unsigned long long* key; FqName* names; uint32_t names_cap;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+__global__ void __launch_bounds__(TILE_THREADS)
+fq_tile_kernel(const TileParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* win = smem;
+  uint16_t* lend = (uint16_t*)(smem + TILE_WIN + 48);
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tile, s_warp_all[TILE_THREADS / 32], s_warp_T[TILE_THREADS / 32], s_base, s_nl, s_cntT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar = smem_u32(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t parity = 0;
+  unsigned long long my_key = FQ_KEY_NONE, my_rds = 0, my_names = 0, my_mem = 0;
+  uint32_t mn_rl = 0xFFFFFFFFu, mx_rl = 0, mn_q = 255, mx_q = 0, run_len = 0, run_cnt = 0;
+
+  for (;;) {
+    __syncthreads(); /* everyone is done with the previous window */
+    if (tid == 0) {
+      uint32_t t = atomicAdd(P.ticket, 1u);
+      s_tile = t;
+      if (t < P.ntiles) {
+        unsigned long long t0 = (unsigned long long)t * TILE_BYTES;
+        unsigned long long src = t ? t0 - TILE_LEFT : 0;
+        uint32_t dst_off = t ? 0 : TILE_LEFT;
+        unsigned long long want = (unsigned long long)TILE_WIN - dst_off, have = ((unsigned long long)P.n - src + 15) & ~15ull;
+        uint32_t bytes = (uint32_t)(want < have ? want : have);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(win + dst_off)), "l"(P.data + src), "r"(bytes), "r"(bar) : "memory");
+      }
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= P.ntiles) break;
+    const unsigned long long t0 = (unsigned long long)tile * TILE_BYTES;
+    /* window offset w ↔ global offset t0 - 16 + w; real data below nloc */
+    const uint32_t nloc = (uint32_t)min((unsigned long long)TILE_WIN, (unsigned long long)TILE_LEFT + (P.n - t0));
+    {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) { if (tid == 0) atomicExch(P.out + 4, 1u); break; } }
+      parity ^= 1;
+    }
+    if (tile == 0 && tid == 0) win[TILE_LEFT - 1] = '\n';
+    /* LF masks of this thread's 18 consecutive 16-byte chunks (window offsets 16 + 288*tid ...) */
+    uint32_t mk[TILE_CHUNKS_PER_THREAD / 2];
+    uint32_t c_all = 0, c_T = 0;
+    const uint32_t w0 = TILE_LEFT + tid * (TILE_CHUNKS_PER_THREAD * 16);
+#pragma unroll
+    for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i++) {
+      uint32_t w = w0 + i * 16, m = 0;
+      if (w < nloc) {
+        m = lf_mask16(*(const uint4*)(win + w));
+        if (nloc - w < 16) m &= (1u << (nloc - w)) - 1u;
+      }
+      if (i & 1) mk[i >> 1] |= m << 16; else mk[i >> 1] = m;
+      uint32_t c = __popc(m);
+      c_all += c;
+      if (w < TILE_LEFT + TILE_BYTES) c_T += c;
+    }
+    /* block-wide exclusive prefix of c_all, total of c_T */
+    uint32_t incl = c_all, sumT = c_T;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += a; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sumT += __shfl_xor_sync(FULL, sumT, d);
+    if (lane == 31) s_warp_all[warp] = incl;
+    if (lane == 0) s_warp_T[warp] = sumT;
+    __syncthreads();
+    uint32_t rank = incl - c_all;
+    for (int wgt = 0; wgt < warp; wgt++) rank += s_warp_all[wgt];
+    if (warp == 0) {
+      uint32_t nl = 0, cntT = 0;
+      for (int wgt = 0; wgt < TILE_THREADS / 32; wgt++) { nl += s_warp_all[wgt]; cntT += s_warp_T[wgt]; }
+      unsigned long long acc = 0;
+      if (tile > 0) {
+        if (lane == 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
+        int look = (int)tile - 1;
+        uint32_t spins = 0;
+        for (;;) {
+          int idx = look - lane;
+          unsigned long long v64 = idx >= 0 ? ld_volatile64(P.tile_state + idx) : ST_INCL;
+          while (__any_sync(FULL, (v64 >> 62) == 0)) {
+            if ((v64 >> 62) == 0) v64 = ld_volatile64(P.tile_state + idx);
+            if (++spins > (1u << 26)) { if (lane == 0) atomicExch(P.out + 4, 2u); v64 = ST_INCL; }
+          }
+          uint32_t incl_mask = __ballot_sync(FULL, (v64 >> 62) == 2);
+          int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+          unsigned long long part = lane <= first ? (v64 & ST_VALUE) : 0ull;
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+          acc += part;
+          if (incl_mask) break;
+          look -= 32;
+        }
+      }
+      if (lane == 0) {
+        st_volatile64(P.tile_state + tile, ST_INCL | (acc + cntT));
+        s_base = (uint32_t)acc; s_nl = nl; s_cntT = cntT;
+        if (tile == P.ntiles - 1) {
+          uint32_t cnt = (uint32_t)acc + cntT;
+          if (P.virtual_end && P.n > 0 && win[nloc - 1] != '\n') { if (cnt < P.cap) P.line_end[cnt] = P.n; cnt++; }
+          P.out[0] = cnt; P.out[1] = cnt > P.cap ? 1u : 0u;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t base_line = s_base, nl_win = s_nl, cntT = s_cntT;
+    /* line ends: window-relative list in shared memory, global offsets into the line index */
+    {
+      const uint32_t gofs = (uint32_t)(t0 - TILE_LEFT);
+#pragma unroll
+      for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i++) {
+        uint32_t m = (i & 1) ? (mk[i >> 1] >> 16) : (mk[i >> 1] & 0xFFFFu);
+        uint32_t w = w0 + i * 16;
+        while (m) {
+          uint32_t b = __ffs(m) - 1; m &= m - 1;
+          uint32_t e = w + b + 1;
+          if (rank < TILE_LMAX) lend[rank] = (uint16_t)e;
+          if (rank < cntT) { uint32_t gi = base_line + rank; if (gi < P.cap) P.line_end[gi] = gofs + e; }
+          rank++;
+        }
+      }
+    }
+    __syncthreads();
+    /* records that start in this tile */
+    {
+      const bool starts_here = win[TILE_LEFT - 1] == '\n';
+      uint32_t lo = starts_here ? 0u : 1u;
+      if (P.j0 > base_line + lo) lo = P.j0 - base_line;
+      const uint32_t k0 = lo + ((4u - ((base_line + lo - P.j0) & 3u)) & 3u);
+      const uint32_t nl_list = nl_win < (uint32_t)TILE_LMAX ? nl_win : (uint32_t)TILE_LMAX;
+      const bool at_data_end = nloc < (uint32_t)TILE_WIN || t0 + TILE_BYTES + TILE_MARGIN >= P.n;
+      const uint32_t nrec_tile = k0 <= cntT ? (cntT - k0) / 4 + 1 : 0;
+      for (uint32_t rb = 0; rb < nrec_tile; rb += TILE_THREADS) { /* trip count is uniform over the block */
+        uint32_t r = rb + tid;
+        uint32_t flush_len = 0, flush_cnt = 0;
+        if (r < nrec_tile) {
+          uint32_t k = k0 + 4 * r;
+          uint32_t start = k == 0 ? (uint32_t)TILE_LEFT : (uint32_t)lend[k - 1 < (uint32_t)TILE_LMAX ? k - 1 : 0];
+          bool in_list = k == 0 || k - 1 < nl_list;
+          if (in_list && start < TILE_LEFT + TILE_BYTES) {
+            uint32_t g_local = (base_line + k - P.j0) >> 2;
+            if (g_local < P.max_rec) {
+              if (k + 3 >= nl_list) { /* the record's last line end is not in the window */
+                bool virtual_last = at_data_end && P.virtual_end && k + 3 == nl_list && win[nloc - 1] != '\n' && nl_win <= (uint32_t)TILE_LMAX;
+                if (virtual_last) {
+                  /* file ends without LF: the fourth line ends at the end of the data */
+                } else if (!at_data_end || nl_win > (uint32_t)TILE_LMAX) atomicAdd(P.out + 3, 1u);
+                if (!virtual_last) goto next_record;
+              }
+              {
+                FqLine L[4];
+                uint32_t s = start;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                  uint32_t e = (k + i < nl_list) ? (uint32_t)lend[k + i] : nloc;
+                  L[i].off = s; L[i].len = e - s; s = e;
+                }
+                if (L[0].len >= FQ_MAX_LABEL_LENGTH) atomicMin(P.out + 2, base_line + k);
+                if (L[2].len >= FQ_MAX_LABEL_LENGTH) atomicMin(P.out + 2, base_line + k + 2);
+                FqRecOut o;
+                fq_check_record(win, L, P.cx, &o);
+                unsigned long long g = P.g0 + g_local;
+                unsigned long long key = fq_record_key(P.cx.loop, g, P.step_base, o);
+                if (key < my_key) my_key = key;
+                bool named = fq_record_has_name(P.cx.loop, o);
+                if (P.names && g_local < P.names_cap) {
+                  FqName nm; nm.off = o.name_off + (uint32_t)(t0 - TILE_LEFT); nm.len = o.name_len;
+                  nm.hash = named ? fq_hash_name(win + o.name_off, o.name_len, P.cx.seed) : FQ_HASH_SKIP;
+                  P.names[g_local] = nm;
+                }
+                if (P.cx.loop == FQ_LOOP_INDEX && named) { my_names++; my_mem += o.mem_len; }
+                if (!o.flags && o.vrank == FQ_V_OK) {
+                  my_rds += P.cx.weight;
+                  mn_rl = min(mn_rl, o.read_len); mx_rl = max(mx_rl, o.read_len);
+                  if (o.qmin <= o.qmax) { mn_q = min(mn_q, o.qmin); mx_q = max(mx_q, o.qmax); }
+                  if (run_cnt && o.read_len != run_len) { flush_len = run_len; flush_cnt = run_cnt; run_cnt = 0; }
+                  run_len = o.read_len; run_cnt += P.cx.weight;
+                }
+              }
+            }
+          }
+        }
+      next_record:
+        hist_flush(P.hist, flush_len, flush_cnt);
+      }
+    }
+  }
+  hist_flush(P.hist, run_len, run_cnt);
+  my_key = warp_min64(my_key);
+  my_rds = warp_sum64(my_rds); my_names = warp_sum64(my_names); my_mem = warp_sum64(my_mem);
+  mn_rl = __reduce_min_sync(FULL, mn_rl); mx_rl = __reduce_max_sync(FULL, mx_rl);
+  mn_q = __reduce_min_sync(FULL, mn_q); mx_q = __reduce_max_sync(FULL, mx_q);
+  if (lane == 0) {
+    if (my_key != FQ_KEY_NONE) atomicMin(P.key, my_key);
+    if (my_rds) atomicAdd(&P.stats->num_rds, my_rds);
+    if (my_names) { atomicAdd(&P.stats->n_names, my_names); atomicAdd(&P.stats->mem_sum, my_mem); }
+    if (mx_rl) { atomicMin(&P.stats_range->min_rl, mn_rl); atomicMax(&P.stats_range->max_rl, mx_rl); }
+    if (mn_q <= mx_q) { atomicMin(&P.stats_range->min_q, mn_q); atomicMax(&P.stats_range->max_q, mx_q); }
+  }
+}
+
 /* ------------------------------------------------------------------------------------------------ K3 / K4: the index */
 __device__ __forceinline__ const uint8_t* dir_name(const FqDirEntry* dir, uint32_t nd, unsigned long long g, uint32_t* len) {
   uint32_t lo = 0, hi = nd;
@@ -552,6 +785,30 @@ class FqCudaDevice : public FqDevice {
     toc();
     launched();
   }
+  bool tile_pass(const FqTileArgs& a) override {
+    if (!a.n) return false;
+    uint32_t ntiles = (a.n + TILE_BYTES - 1) / TILE_BYTES;
+    if (ntiles > max_tiles_) return false;
+    if (tile_blocks_ == 0) {
+      FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+      int per_sm = 0;
+      FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fq_tile_kernel, TILE_THREADS, TILE_SMEM));
+      if (per_sm < 1) return false;
+      tile_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
+    }
+    TileParams P;
+    P.data = a.data; P.n = a.n; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
+    P.tile_state = tile_state_; P.ticket = ticket_; P.ntiles = ntiles; P.out = a.out5;
+    P.j0 = a.j0; P.max_rec = a.max_rec; P.g0 = a.g0; P.step_base = a.step_base; P.cx = a.cx;
+    P.stats = a.stats; P.stats_range = a.stats_range; P.hist = a.hist; P.key = a.key; P.names = a.names; P.names_cap = a.names_cap;
+    FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));
+    FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
+    int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)tile_blocks_);
+    tic(FQG_K_TILE, a.n, ntiles);
+    fq_tile_kernel<<<grid, TILE_THREADS, TILE_SMEM, st_>>>(P);
+    toc(); launched();
+    return true;
+  }
   static TableParams table_params(const FqTableArgs& a) {
     TableParams P;
     P.names = a.names; P.data = a.data; P.nrec = a.nrec; P.g0 = a.g0; P.step_base = a.step_base; P.slots = a.slots; P.mask = a.mask;
@@ -646,7 +903,7 @@ class FqCudaDevice : public FqDevice {
   KStat kst_[FQG_K_COUNT];
   std::vector<Pending> pending_;
   std::vector<cudaEvent_t> free_ev_;
-  int dev_ = 0, sms_ = kSMs;
+  int dev_ = 0, sms_ = kSMs, tile_blocks_ = 0;
   cudaStream_t st_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;

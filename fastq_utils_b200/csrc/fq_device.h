@@ -64,6 +64,14 @@ typedef struct {
 } FqShardArgs;
 FQ_HD uint32_t fq_owner_of(uint64_t hash, uint32_t world) { return (uint32_t)((hash >> 40) % world); }
 
+/* fused scan + validate pass over one chunk (FqCudaDevice only): the records of the segment that starts at line j0 */
+typedef struct {
+  const uint8_t* data; uint32_t n; int virtual_end; uint32_t* line_end; uint32_t cap;
+  uint32_t* out5;            /* device: lines, cap overflow, first over-long header line (init ~0), records that did not fit, internal error */
+  uint32_t j0; uint32_t max_rec; uint64_t g0; uint64_t step_base; FqRecCtx cx;
+  FqStats* stats; FqStats* stats_range; unsigned long long* hist; unsigned long long* key; FqName* names; uint32_t names_cap;
+} FqTileArgs;
+
 class FqDevice {
  public:
   virtual ~FqDevice() {}
@@ -89,6 +97,8 @@ class FqDevice {
   virtual void sniff(const uint8_t* data, FqLine hdr1, FqLine seq, int32_t* out2) = 0;
   /* K2: reader flags + validation + statistics + event key + name descriptors */
   virtual void records(const FqRecordsArgs& a) = 0;
+  /* K1+K2 in one pass over HBM; false when the device has no such kernel (the engine then uses K1 and K2) */
+  virtual bool tile_pass(const FqTileArgs& a) = 0;
   /* K3: index insert (file 1) / K4: mate claim (file 2) / pair compare (interleaved, sorted) */
   virtual void index_insert(const FqTableArgs& a) = 0;
   virtual void mate_claim(const FqTableArgs& a) = 0;

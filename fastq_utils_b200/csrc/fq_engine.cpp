@@ -8,6 +8,7 @@
  */
 #include "fq_engine.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 static const uint32_t kPad = 64;                 /* readable bytes after every chunk */
@@ -22,6 +23,7 @@ FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) 
   counters_ = (unsigned long long*)dev_->alloc(4 * sizeof(unsigned long long));
   scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
   recout_ = (FqRecOut*)dev_->alloc(sizeof(FqRecOut));
+  tile_out_ = (uint32_t*)dev_->alloc(8 * sizeof(uint32_t));
   for (int f = 0; f < 2; f++) {
     f_[f].stats = (FqStats*)dev_->alloc(sizeof(FqStats));
     f_[f].hist = (unsigned long long*)dev_->alloc((size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
@@ -48,14 +50,15 @@ FqEngine::~FqEngine() {
   dev_->sync();
   for (int f = 0; f < 2; f++) { free_file(f_[f]); dev_->release(f_[f].stats); dev_->release(f_[f].hist); }
   if (slots_) dev_->release(slots_);
-  dev_->release(key_); dev_->release(counters_); dev_->release(scratch_); dev_->release(recout_);
+  dev_->release(key_); dev_->release(counters_); dev_->release(scratch_); dev_->release(recout_); dev_->release(tile_out_);
 }
 
 /* forget input and results; the index keeps its allocation */
 void FqEngine::reset() {
   dev_->sync();
   for (int f = 0; f < 2; f++) free_file(f_[f]);
-  seed_ = 0; finished_ = false;
+  seed_ = 0; finished_ = false; fused_ok_ = !(cfg_.flags & FQG_FLAG_TWO_PASS);
+  { const char* e = getenv("FQG_FUSED_MIN_BYTES"); fused_min_ = e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 20); } /* test hook */
   /* results */
   dev_->fill(key_, 0xFF, sizeof(unsigned long long));
   dev_->fill(counters_, 0, 4 * sizeof(unsigned long long));
@@ -161,7 +164,78 @@ void FqEngine::scan_buffer(FqBuffer& B, bool last) {
   }
 }
 
-void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned) {
+/* Sniff the first record of a file from a short prefix so that the fused pass knows the read-name format and colour space
+ * before it runs.  False when the prefix does not hold the two lines (the two-pass path sniffs later). */
+bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip) {
+  FqFile& F = f_[file];
+  if (F.sniff_fmt >= 0) return true;
+  uint32_t pn = std::min<uint32_t>(n, 1u << 16), cap = 4096;
+  uint32_t* le = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
+  dev_->scan_lines(data, pn, 0, le, cap, scratch_);
+  uint32_t out2[2]; dev_->download(out2, scratch_, sizeof out2);
+  bool ok = false;
+  if (out2[0] >= skip + 2 && skip + 2 <= cap) {
+    uint32_t e[3] = {0, 0, 0};
+    if (skip) dev_->download(e, le + skip - 1, 3 * sizeof(uint32_t)); else dev_->download(e + 1, le, 2 * sizeof(uint32_t));
+    FqLine h, q; h.off = e[0]; h.len = e[1] - e[0]; q.off = e[1]; q.len = e[2] - e[1];
+    if (h.len < FQ_MAX_LABEL_LENGTH && q.len < 2048) { /* short reads only: long records do not fit the fused pass's window */
+      dev_->sniff(data, h, q, (int32_t*)scratch_);
+      int32_t o2[2]; dev_->download(o2, scratch_, sizeof o2);
+      F.sniff_fmt = o2[0]; F.sniff_color = o2[1];
+      ok = true;
+    }
+  }
+  dev_->release(le);
+  return ok;
+}
+
+/* K1+K2 fused over buffer b.  Returns false (nothing launched, or results discarded) when the two-pass path must be used. */
+bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap) {
+  FqFile& F = f_[file];
+  FqBuffer& B = F.bufs[b];
+  int loop = loop_of(file);
+  if (loop == FQ_LOOP_MATE && eff_records(f_[0]) == 0) return false;
+  if (F.limit != ~0ull) return false;
+  if (F.sniff_fmt < 0) {
+    if (F.nrec != 0 || F.pend_n != 0) return false;
+    if (!presniff(file, B.data, B.n, j0)) return false;
+  }
+  uint32_t cap = B.n / 32 + 4096;
+  B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
+  uint32_t ncap = cap / 4 + 1;
+  FqName* names = loop != FQ_LOOP_SINGLE ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
+  uint32_t init[5] = {0, 0, kNone32, 0, 0};
+  dev_->upload(tile_out_, init, sizeof init);
+  FqTileArgs a; memset(&a, 0, sizeof a);
+  a.data = B.data; a.n = B.n; a.virtual_end = last ? 1 : 0; a.line_end = B.line_end; a.cap = cap; a.out5 = tile_out_;
+  a.j0 = j0; a.max_rec = kNone32; a.g0 = g0_local + F.g_base; a.step_base = step_base(file); a.cx = make_ctx(file);
+  int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
+  a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; a.key = key_; a.names = names; a.names_cap = ncap;
+  bool launched = dev_->tile_pass(a);
+  uint32_t out5[5] = {0, 0, kNone32, 0, 0};
+  if (launched) dev_->download(out5, tile_out_, sizeof out5); else dev_->sync();
+  if (launched && !out5[1] && out5[2] == kNone32 && !out5[3] && !out5[4]) {
+    B.nlines = out5[0];
+    *names_out = names; *names_cap = ncap;
+    return true;
+  }
+  /* not usable: a line gzgets would split, a record longer than the window, more lines than guessed, or no such kernel */
+  if (names) dev_->release(names);
+  bool keep_index = launched && !out5[1] && !out5[4];
+  if (keep_index) B.nlines = out5[0]; else { dev_->release(B.line_end); B.line_end = nullptr; }
+  if (launched) fused_fallback();
+  else fused_ok_ = false;
+  return false;
+}
+
+/* the fused pass touched the global statistics / event key with results we cannot use: redo everything seen so far two-pass */
+void FqEngine::fused_fallback() {
+  fused_ok_ = false;
+  for (int f = 0; f < 2; f++) for (auto& s : f_[f].segs) s.fused = false;
+  reprocess();
+}
+
+void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned, bool allow_fused) {
   FqFile& F = f_[file];
   if (F.ended) throw std::runtime_error("fqg_feed after the end of the file");
   if (cfg_.mode == FQG_MODE_INDEX_PAIR && file == 1 && !f_[0].ended) throw std::runtime_error("INDEX_PAIR: file 1 fed before file 0 ended");
@@ -174,6 +248,7 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
   }
   int b = (int)F.bufs.size();
   F.bufs.push_back(FqBuffer());
+  bool fused = false; uint32_t fused_j0 = 0, fused_ncap = 0; uint64_t fused_g0 = 0; FqName* fused_names = nullptr;
   {
     FqBuffer& B = F.bufs[b];
     B.data = data; B.n = n; B.owned = owned;
@@ -182,7 +257,12 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
       FqFile::Prescan& ps = F.prescans[i];
       if (ps.data == data && ps.n == n && ps.last == last) { B.line_end = ps.line_end; B.nlines = ps.nlines; F.prescans.erase(F.prescans.begin() + i); cached = true; break; }
     }
-    if (!cached) scan_buffer(B, last);
+    if (!cached && allow_fused && fused_ok_ && n >= fused_min_) {
+      fused_j0 = F.pend_n > 0 ? 4 - std::min<uint32_t>(F.pend_lfs, 3) : (F.started ? 0 : F.start_skip);
+      fused_g0 = F.nrec + (F.pend_n > 0 ? 1 : 0);
+      fused = try_fused_pass(file, b, last, fused_j0, fused_g0, &fused_names, &fused_ncap);
+    }
+    if (!fused && !cached && !F.bufs[b].line_end) scan_buffer(F.bufs[b], last);
   }
   uint32_t pos = 0, j = 0;
   if (!F.started) { /* multi-GPU: the first lines of a range belong to the previous range's last record */
@@ -207,7 +287,7 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
       F.pend_n = 0; F.pend_lfs = 0;
       bool blast = last && cut == B.n;
       pos = cut; j += need;
-      add_buffer(file, bd, (uint32_t)bn, blast, true); /* may leave a new remainder in F.pend (over-long lines) */
+      add_buffer(file, bd, (uint32_t)bn, blast, true, false); /* may leave a new remainder in F.pend (over-long lines) */
     } else {
       append_pending(file, B.data + pos, B.n - pos, avail);
       pos = B.n; j = B.nlines;
@@ -216,6 +296,30 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
     }
   }
   if (F.ended) return;
+  if (fused) {
+    /* the fused pass assumed: records start at line fused_j0 and the first one is record fused_g0 of the file */
+    const FqBuffer B = F.bufs[b];
+    if (j == fused_j0 && F.nrec == fused_g0 && F.pend_n == 0) {
+      uint32_t nrec = (B.nlines - j) / 4;
+      if (nrec > fused_ncap) nrec = fused_ncap; /* cannot happen: ncap = cap/4+1 and lines <= cap */
+      if (nrec) {
+        FqSegment s; s.buf = b; s.q = pos; s.j0 = j; s.nrec = nrec; s.fused = true;
+        j += 4 * nrec;
+        uint32_t end = line_end_at(B, j - 1);
+        s.span = end - pos; pos = end;
+        s.g0 = F.nrec; F.nrec += nrec; s.names = fused_names;
+        F.segs.push_back(s);
+        FqDirEntry de; de.g0 = s.g0; de.names = s.names; de.data = B.data;
+        F.dir_host.push_back(de);
+        launch_names(file, F.segs.size() - 1, nrec);
+      } else if (fused_names) dev_->release(fused_names);
+      segmentize(file, b, pos, j, last); /* what is left: fewer than four lines (over-long check, pending bytes / end of file) */
+      return;
+    }
+    /* the bridge did not behave as assumed (over-long lines around the chunk boundary): discard the fused results */
+    if (fused_names) dev_->release(fused_names);
+    fused_fallback();
+  }
   segmentize(file, b, pos, j, last);
 }
 
@@ -368,6 +472,7 @@ void FqEngine::launch_segment(int file, size_t si) {
   if (s.g0 >= lim) return;
   if (loop_of(file) == FQ_LOOP_MATE && eff_records(f_[0]) == 0) return; /* "No reads found": file 2 is never opened */
   uint32_t nrec = (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0);
+  if (s.fused) { launch_names(file, si, nrec); return; } /* only reached when a table rebuild replays the name step */
   sniff_if_needed(file, s);
   const FqBuffer& B = F.bufs[s.buf];
   FqRecordsArgs a; memset(&a, 0, sizeof a);
@@ -427,6 +532,7 @@ void FqEngine::launch_pairs() {
 /* run every kernel again over the resident chunks (after a limit or the hash seed changed) */
 void FqEngine::reprocess() {
   dev_->sync();
+  for (int f = 0; f < 2; f++) for (auto& s : f_[f].segs) s.fused = false; /* limits / seeds changed: the two-pass kernels redo every segment */
   dev_->fill(key_, 0xFF, sizeof(unsigned long long));
   dev_->fill(counters_, 0, 4 * sizeof(unsigned long long));
   for (int f = 0; f < 2; f++) {

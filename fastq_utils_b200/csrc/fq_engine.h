@@ -24,6 +24,7 @@ struct FqSegment {
   uint32_t q = 0, j0 = 0, nrec = 0;
   uint64_t span = 0;
   bool explicit_lines = false;
+  bool fused = false;        /* validated by the fused pass already: only the name step remains */
   FqLine lines_host[4];
   FqLine* lines_dev = nullptr;
   uint64_t g0 = 0;
@@ -87,12 +88,18 @@ class FqEngine {
   uint32_t shard_nsrc_ = 0; uint64_t shard_meta_start_[FQ_SHARD_MAX_SRC + 1], shard_blob_start_[FQ_SHARD_MAX_SRC];
   void scan_buffer(FqBuffer& B, bool last);
   bool finished_ = false;
+  bool fused_ok_ = true;     /* cleared for the rest of the job once a chunk needed the two-pass path */
+  uint32_t* tile_out_ = nullptr;
+  uint32_t fused_min_ = 1u << 20; /* chunks smaller than this always take the two-pass path */
 
   int nfiles() const { return cfg_.mode == FQG_MODE_INDEX_PAIR || cfg_.mode == FQG_MODE_SORTED_PAIR ? 2 : 1; }
   int loop_of(int file) const;
   uint64_t step_base(int file) const;
   FqRecCtx make_ctx(int file) const;
-  void add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned);
+  void add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned, bool allow_fused = true);
+  bool try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap);
+  bool presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip);
+  void fused_fallback();
   void segmentize(int file, int b, uint32_t pos, uint32_t j, bool last);
   void flush_pending_as_last(int file);
   void end_file(int file, const uint8_t* dev_tail, size_t n);

@@ -48,6 +48,8 @@ typedef struct {
 #define FQG_FLAG_PAIRED_NAMES 1u
 /* the read-name index lives elsewhere (sharded over GPUs): names are exported with fqg_names_* instead of inserted */
 #define FQG_FLAG_EXTERNAL_INDEX 2u
+/* never use the fused single-pass kernel (A/B measurements; results are identical) */
+#define FQG_FLAG_TWO_PASS 4u
 
 /* statistics of one FASTQ_FILE as the reference holds them at the end of its loops (src/fastq.h:110-131) */
 typedef struct {
@@ -154,7 +156,7 @@ int fqg_shard_result(fqg_ctx* ctx, uint64_t* event_key, uint64_t* record, char n
 int fqg_hist_range(fqg_ctx* ctx, int file, uint64_t lo, uint64_t hi, uint64_t* out);
 
 /* ---- per-kernel device timing (CUDA events around every launch on the context's stream) ---- */
-enum { FQG_K_SCAN = 0, FQG_K_RECORDS = 1, FQG_K_INDEX = 2, FQG_K_MATE = 3, FQG_K_PAIR = 4, FQG_K_OTHER = 5, FQG_K_COUNT = 6 };
+enum { FQG_K_SCAN = 0, FQG_K_RECORDS = 1, FQG_K_INDEX = 2, FQG_K_MATE = 3, FQG_K_PAIR = 4, FQG_K_OTHER = 5, FQG_K_TILE = 6 /* fused scan+records */, FQG_K_COUNT = 7 };
 typedef struct { double ms; uint64_t launches; uint64_t bytes; uint64_t items; } fqg_kernel_stat;
 /* accumulated since fqg_create / the last fqg_kernel_stats_reset; `bytes` = FASTQ bytes the launches covered */
 int fqg_kernel_stats(fqg_ctx* ctx, int which, fqg_kernel_stat* out);

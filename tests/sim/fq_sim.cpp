@@ -101,6 +101,7 @@ class FqSimDevice : public FqDevice {
       }
     }
   }
+  bool tile_pass(const FqTileArgs&) override { return false; }
   static const uint8_t* name_of(const FqDirEntry* dir, uint32_t nd, uint64_t g, uint32_t* len) {
     uint32_t lo = 0, hi = nd;
     while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (dir[mid].g0 <= g) lo = mid; else hi = mid; }

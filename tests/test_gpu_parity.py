@@ -197,3 +197,39 @@ def test_sharded_path_world1_matches_oracle():
     data = bytes(t[:nb].cpu().numpy())
     run = fqdist.ShardedFastqInfo(fq.MODE_INDEX, device=0)
     assert run.run_device(t.data_ptr(), nb, name="a.fq")["transcript"] == oracle_run(["a.fq"], data, None)
+
+
+# ------------------------------------------------------------------------------------------- the fused single-pass kernel on small inputs
+@pytest.mark.parametrize("idx", range(0, len(CASES), 2))
+def test_gpu_fused_pass_on_corpus(idx, monkeypatch):
+    """FQG_FUSED_MIN_BYTES=1 sends even tiny chunks through the fused scan+validate kernel (with its fallbacks)."""
+    monkeypatch.setenv("FQG_FUSED_MIN_BYTES", "1")
+    c = CASES[idx]
+    chunk = [0, 0, 4096, 100][idx % 4]
+    got = fqg_run_files(c["argv"], chunk=chunk, kind="gpu")
+    assert got == (c["rc"], c["stdout"], c["stderr"]), (c["argv"], chunk)
+
+
+@pytest.mark.parametrize("seed", range(200))
+def test_gpu_fused_pass_fuzz(seed, monkeypatch):
+    monkeypatch.setenv("FQG_FUSED_MIN_BYTES", "1")
+    rng = random.Random(30_000 + seed)
+    style = rng.randrange(len(NAMES))
+    n = rng.choice([1, 2, 5, 13, 40, 300, 1500])
+    mode = rng.choice(["single", "single_r", "pe", "pair", "pair_rs"])
+    r1 = make_file(rng, n, style, 1, seqlen=(1, 300))
+    two = mode.startswith("pair")
+    r2 = make_file(rng, n, style, 2, seqlen=(1, 300)) if two else None
+    if mode == "pe":
+        inter = []
+        for a, b in zip(r1, make_file(rng, n, style, 2)):
+            inter += [a, b]
+        r1 = inter
+    for _ in range(rng.choice([0, 0, 1, 2])):
+        mutate(rng, r1 if (not two or rng.random() < 0.5) else r2)
+    d1 = render(rng, r1, "lf")
+    d2 = render(rng, r2, "lf") if two else None
+    argv = {"single": [], "single_r": ["-r"], "pe": [], "pair": [], "pair_rs": ["-r", "-s"]}[mode]
+    argv = argv + ["a.fq"] + (["b.fq"] if two else []) + (["pe"] if mode == "pe" else [])
+    chunk = rng.choice([0, 0, 20000, 70000])
+    assert fqg_run(argv, d1, d2, chunk=chunk, kind="gpu") == oracle_run(argv, d1, d2), (argv, chunk)
