@@ -191,7 +191,7 @@ __global__ void fq_explain_kernel(const uint8_t* data, FqLine l0, FqLine l1, FqL
   if (threadIdx.x || blockIdx.x) return;
   FqLine L[4] = {l0, l1, l2, l3};
   FqRecOut o;
-  fq_check_record(data, L, cx, &o);
+  fq_check_record_careful(data, L, cx, &o);
   *out = o;
 }
 
@@ -248,14 +248,15 @@ fq_records_kernel(const RecParams P) {
         for (int i = 0; i < 4; i++) { uint32_t e = P.line_end[j + i]; L[i].off = s; L[i].len = e - s; s = e; }
       }
       FqRecOut o;
-      fq_check_record(P.data, L, P.cx, &o);
+      uint64_t hsh;
+      fq_check_record(P.data, L, P.cx, &o, &hsh);
       unsigned long long g = P.g0 + k;
       unsigned long long key = fq_record_key(P.cx.loop, g, P.step_base, o);
       if (key < my_key) my_key = key;
       bool named = fq_record_has_name(P.cx.loop, o);
       if (P.names) {
         FqName nm; nm.off = o.name_off; nm.len = o.name_len;
-        nm.hash = named ? fq_hash_name(P.data + o.name_off, o.name_len, P.cx.seed) : FQ_HASH_SKIP;
+        nm.hash = named ? hsh : FQ_HASH_SKIP;
         P.names[k] = nm;
       }
       if (P.cx.loop == FQ_LOOP_INDEX && named) { my_names++; my_mem += o.mem_len; }
@@ -476,14 +477,15 @@ fq_tile_kernel(const TileParams P) {
                 if (L[0].len >= FQ_MAX_LABEL_LENGTH) atomicMin(P.out + 2, base_line + k);
                 if (L[2].len >= FQ_MAX_LABEL_LENGTH) atomicMin(P.out + 2, base_line + k + 2);
                 FqRecOut o;
-                fq_check_record(win, L, P.cx, &o);
+                uint64_t hsh;
+                fq_check_record(win, L, P.cx, &o, &hsh);
                 unsigned long long g = P.g0 + g_local;
                 unsigned long long key = fq_record_key(P.cx.loop, g, P.step_base, o);
                 if (key < my_key) my_key = key;
                 bool named = fq_record_has_name(P.cx.loop, o);
                 if (P.names && g_local < P.names_cap) {
                   FqName nm; nm.off = o.name_off + (uint32_t)(t0 - TILE_LEFT); nm.len = o.name_len;
-                  nm.hash = named ? fq_hash_name(win + o.name_off, o.name_len, P.cx.seed) : FQ_HASH_SKIP;
+                  nm.hash = named ? hsh : FQ_HASH_SKIP;
                   P.names[g_local] = nm;
                 }
                 if (P.cx.loop == FQ_LOOP_INDEX && named) { my_names++; my_mem += o.mem_len; }

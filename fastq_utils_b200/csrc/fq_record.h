@@ -268,7 +268,7 @@ FQ_HD int fq_sniff_colorspace(const uint8_t* sq, uint32_t s) {
 FQ_HD uint8_t fq_first_byte(const uint8_t* d, const FqLine& l) { return l.len ? d[l.off] : 0; }
 
 /* Reader step flags + validator verdict + statistics for one record whose four raw lines are L[0..3]. */
-FQ_HD void fq_check_record(const uint8_t* d, const FqLine* L, const FqRecCtx& cx, FqRecOut* o) {
+FQ_HD void fq_check_record_careful(const uint8_t* d, const FqLine* L, const FqRecCtx& cx, FqRecOut* o) {
   o->flags = 0; o->vrank = FQ_V_OK; o->code = 0; o->read_len = 0; o->slen = 0; o->qlen = 0;
   o->qmin = 255; o->qmax = 0; o->bad = 0; o->name_off = L[0].off + 1; o->name_len = 0; o->mem_len = 0;
   /* fastq_read_entry, src/fastq.c:245-261 */
@@ -304,6 +304,186 @@ FQ_HD void fq_check_record(const uint8_t* d, const FqLine* L, const FqRecCtx& cx
   if (cx.space == FQ_SPACE_COLOR) {
     if (!(qs.qlen == sq.slen - 1 || qs.qlen == sq.slen)) { o->vrank = FQ_V_LEN; o->code = FQ_E_LEN_CS; }
   } else if (qs.qlen != sq.slen) { o->vrank = FQ_V_LEN; o->code = FQ_E_LEN; }
+}
+
+/* does a record of this loop reach the name step (index insert / mate claim / pair compare)? */
+FQ_HD bool fq_record_has_name(int loop, const FqRecOut& o) {
+  if (o.flags & (FQ_RF_STOP | FQ_RF_TRUNC | FQ_RF_NOTAT)) return false;
+  return loop != FQ_LOOP_SINGLE;
+}
+
+
+/* ---------------------------------------------------------------- the common case, 16 bytes at a time
+ * A record made of: "@name...\n", bases from ACGTN/acgtn + LF or CRLF, "+\n" or "+\r\n", qualities above 0x0D + LF or
+ * CRLF, with matching lengths, is clean; for it the functions below produce exactly what fq_check_record_careful
+ * produces (tests/sim/test_record_paths.cpp compares the two on random records).  Anything else — every error, NUL
+ * bytes, other alphabets, a header-2 that repeats the name — returns false and the careful path decides. */
+typedef struct { uint32_t x, y, z, w; } FqU4;
+FQ_HD FqU4 fq_ld128(const uint8_t* d, uint32_t a16) {
+  FqU4 r;
+#if defined(__CUDA_ARCH__)
+  uint4 v = *(const uint4*)(d + a16);
+  r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+#else
+  const uint8_t* p = d + a16;
+  uint32_t t[4];
+  for (int i = 0; i < 4; i++) t[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+  r.x = t[0]; r.y = t[1]; r.z = t[2]; r.w = t[3];
+#endif
+  return r;
+}
+/* bits of the 16-byte chunk at `a` whose byte addresses lie in [s, e)   (a < e, a + 16 > s) */
+FQ_HD uint32_t fq_range16(uint32_t a, uint32_t s, uint32_t e) {
+  uint32_t lo = s > a ? s - a : 0u, hi = e - a < 16u ? e - a : 16u;
+  return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+}
+/* four words holding a flag in bit 0 of every byte → 16 flags in byte order */
+FQ_HD uint32_t fq_gather16(uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3) {
+  uint32_t lo = (((l0 & 0x01010101u) | ((l1 & 0x01010101u) << 4)) * 0x00204081u) >> 21;
+  uint32_t hi = (((l2 & 0x01010101u) | ((l3 & 0x01010101u) << 4)) * 0x00204081u) >> 21;
+  return (lo & 0xFFu) | ((hi & 0xFFu) << 8);
+}
+/* 4 flag bits → 0xFF in each flagged byte */
+FQ_HD uint32_t fq_bytes_of4(uint32_t bits4) { return (((bits4 & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu; }
+/* ACGTN / acgtn predicate in bit 0 of every byte (other bits undefined) */
+FQ_HD uint32_t fq_base_pred(uint32_t w) {
+  uint32_t b0 = w, b1 = w >> 1, b2 = w >> 2, b3 = w >> 3, b4 = w >> 4, b6 = w >> 6, b7 = w >> 7;
+  uint32_t g00 = b0 & (~b2 | b1), g01 = b2 & b1 & ~b0, g10 = b2 & ~b1 & ~b0;
+  return ((~b4 & ~b3 & g00) | (~b4 & b3 & g01) | (b4 & ~b3 & g10)) & b6 & ~b7;
+}
+/* every byte of [s, e) is one of ACGTN/acgtn  (e > s) */
+FQ_HD bool fq_seq_fast(const uint8_t* d, uint32_t s, uint32_t e) {
+  uint32_t a = s & ~15u, alast = (e - 1) & ~15u;
+  FqU4 v = fq_ld128(d, a);
+  if (~fq_gather16(fq_base_pred(v.x), fq_base_pred(v.y), fq_base_pred(v.z), fq_base_pred(v.w)) & fq_range16(a, s, e)) return false;
+  if (a == alast) return true;
+  uint32_t all = 0x01010101u;
+  for (a += 16; a < alast; a += 16) {
+    v = fq_ld128(d, a);
+    all &= fq_base_pred(v.x) & fq_base_pred(v.y) & fq_base_pred(v.z) & fq_base_pred(v.w);
+  }
+  if ((all & 0x01010101u) != 0x01010101u) return false;
+  v = fq_ld128(d, alast);
+  return !(~fq_gather16(fq_base_pred(v.x), fq_base_pred(v.y), fq_base_pred(v.z), fq_base_pred(v.w)) & fq_range16(alast, s, e));
+}
+FQ_HD uint32_t fq_odd_bytes(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(w, 0u, 0x4341u);
+#else
+  return (w >> 8) & 0x00FF00FFu;
+#endif
+}
+/* unsigned min / max over the bytes of [s, e), kept as two 16-bit lanes until the end  (e > s) */
+FQ_HD void fq_qual_fast(const uint8_t* d, uint32_t s, uint32_t e, uint32_t* qmin, uint32_t* qmax) {
+  uint32_t mn = 0x00FF00FFu, mx = 0u;
+  uint32_t a = s & ~15u, alast = (e - 1) & ~15u;
+#define FQ_QW(w_) do { uint32_t ev_ = (w_) & 0x00FF00FFu, od_ = fq_odd_bytes(w_); \
+    mn = fq_min2x16(mn, fq_min2x16(ev_, od_)); mx = fq_max2x16(mx, fq_max2x16(ev_, od_)); } while (0)
+#define FQ_QWM(w_, bm_) do { uint32_t lo_ = (w_) | ~(bm_), hi_ = (w_) & (bm_); \
+    mn = fq_min2x16(mn, fq_min2x16(lo_ & 0x00FF00FFu, fq_odd_bytes(lo_))); mx = fq_max2x16(mx, fq_max2x16(hi_ & 0x00FF00FFu, fq_odd_bytes(hi_))); } while (0)
+  {
+    FqU4 v = fq_ld128(d, a); uint32_t rm = fq_range16(a, s, e);
+    FQ_QWM(v.x, fq_bytes_of4(rm)); FQ_QWM(v.y, fq_bytes_of4(rm >> 4)); FQ_QWM(v.z, fq_bytes_of4(rm >> 8)); FQ_QWM(v.w, fq_bytes_of4(rm >> 12));
+  }
+  if (a != alast) {
+    for (a += 16; a < alast; a += 16) { FqU4 v = fq_ld128(d, a); FQ_QW(v.x); FQ_QW(v.y); FQ_QW(v.z); FQ_QW(v.w); }
+    FqU4 v = fq_ld128(d, alast); uint32_t rm = fq_range16(alast, s, e);
+    FQ_QWM(v.x, fq_bytes_of4(rm)); FQ_QWM(v.y, fq_bytes_of4(rm >> 4)); FQ_QWM(v.z, fq_bytes_of4(rm >> 8)); FQ_QWM(v.w, fq_bytes_of4(rm >> 12));
+  }
+#undef FQ_QW
+#undef FQ_QWM
+  *qmin = (mn & 0xFFFFu) < (mn >> 16) ? (mn & 0xFFFFu) : (mn >> 16);
+  *qmax = (mx & 0xFFFFu) > (mx >> 16) ? (mx & 0xFFFFu) : (mx >> 16);
+}
+/* little-endian 32-bit word at any byte offset, from two aligned words */
+FQ_HD uint32_t fq_ldu32(const uint8_t* d, uint32_t off) {
+  uint32_t a = off & ~3u, sh = (off & 3u) * 8u;
+  uint32_t lo = fq_ld32(d, a), hi = fq_ld32(d, a + 4);
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+FQ_HD uint32_t fq_low_bytes(uint32_t w, uint32_t nbytes) { return nbytes >= 4 ? w : (w & ((1u << (8u * nbytes)) - 1u)); }
+/* same value as fq_hash_name, four bytes at a time */
+FQ_HD uint64_t fq_hash_name_words(const uint8_t* d, uint32_t off, uint32_t len, uint32_t seed) {
+  uint64_t h = 0x243F6A8885A308D3ull ^ ((uint64_t)seed * 0xFF51AFD7ED558CCDull);
+  uint32_t i = 0;
+  for (; i + 4 <= len; i += 4) h = fq_hash_mix(h, fq_ldu32(d, off + i));
+  if (i < len) h = fq_hash_mix(h, fq_low_bytes(fq_ldu32(d, off + i), len - i));
+  return fq_hash_fin(h, len);
+}
+
+/* Clean record of the common shape → fills *o like the careful path would (and *hash with the name hash) and returns
+ * true.  Returns false without touching *o otherwise. */
+FQ_HD bool fq_check_record_fast(const uint8_t* d, const FqLine* L, const FqRecCtx& cx, FqRecOut* o, uint64_t* hash) {
+  const uint32_t h0 = L[0].off, hl = L[0].len, s0 = L[1].off, sl = L[1].len, p0 = L[2].off, pl = L[2].len, q0 = L[3].off, ql = L[3].len;
+  if (hl < 3 || sl < 2 || ql < 2) return false;
+  /* header 2: "+\n" or "+\r\n" */
+  if (!(d[p0] == '+' && ((pl == 2 && d[p0 + 1] == '\n') || (pl == 3 && d[p0 + 1] == '\r' && d[p0 + 2] == '\n')))) return false;
+  /* header 1: '@', a second byte that is a name byte, LF-terminated, no NUL */
+  if (d[h0] != '@' || d[h0 + hl - 1] != '\n') return false;
+  { uint8_t c1 = d[h0 + 1]; if (c1 == 0 || c1 == '\n' || c1 == '\r') return false; }
+  const uint32_t ns = h0 + 1, s = hl - 1; /* rn = line + 1, strlen(rn) = s when there is no NUL */
+  uint32_t nlen; uint64_t mem_len;
+  if (cx.fmt_key == FQ_FMT_CASAVA) { /* first space (or the end), then drop a trailing "/x" */
+    uint32_t len = s;
+    for (uint32_t i = 0; i < s; i += 4) {
+      uint32_t w = fq_ldu32(d, ns + i);
+      uint32_t z = (fq_zero_bytes(w) | fq_zero_bytes(w ^ 0x20202020u));
+      if (s - i < 4) z &= (1u << (8u * (s - i))) - 1u;
+      if (z) {
+        uint32_t k = 0; while (!((z >> (8 * k + 7)) & 1u)) k++;
+        if (((w >> (8 * k)) & 0xFFu) == 0) return false; /* NUL */
+        len = i + k; break;
+      }
+    }
+    /* bytes after the space may still hide a NUL: the careful path's strlen would stop there */
+    for (uint32_t i = (len & ~3u); i < s; i += 4) {
+      uint32_t z = fq_zero_bytes(fq_ldu32(d, ns + i));
+      if (s - i < 4) z &= (1u << (8u * (s - i))) - 1u;
+      if (z) return false;
+    }
+    if (len >= 2 && d[ns + len - 2] == '/') len -= 2;
+    nlen = len; mem_len = len;
+  } else {
+    for (uint32_t i = 0; i < s; i += 4) {
+      uint32_t z = fq_zero_bytes(fq_ldu32(d, ns + i));
+      if (s - i < 4) z &= (1u << (8u * (s - i))) - 1u;
+      if (z) return false;
+    }
+    if (cx.fmt_key == FQ_FMT_INT) { nlen = s - 1; mem_len = s; }
+    else { uint32_t len = s - (cx.pe_key ? 1u : 0u); mem_len = len; nlen = len >= 1 ? len - 1 : s; }
+  }
+  /* sequence */
+  if (d[s0 + sl - 1] != '\n') return false;
+  uint32_t se = s0 + sl - 1;
+  if (se > s0 && d[se - 1] == '\r') se--;
+  if (se == s0) return false;
+  if (!fq_seq_fast(d, s0, se)) return false;
+  /* quality */
+  if (d[q0 + ql - 1] != '\n') return false;
+  uint32_t qe = q0 + ql - 1;
+  if (qe > q0 && d[qe - 1] == '\r') qe--;
+  if (qe == q0) return false;
+  uint32_t slen = se - s0, qlen = qe - q0;
+  if (cx.space == FQ_SPACE_COLOR) { if (!(qlen == slen - 1 || qlen == slen)) return false; }
+  else if (qlen != slen) return false;
+  uint32_t qmin, qmax;
+  fq_qual_fast(d, q0, qe, &qmin, &qmax);
+  if (qmin <= 0x0Du) return false;
+  o->flags = 0; o->vrank = FQ_V_OK; o->code = 0; o->read_len = sl; o->slen = slen; o->qlen = qlen;
+  o->qmin = qmin; o->qmax = qmax; o->bad = 0; o->name_off = ns; o->name_len = nlen; o->mem_len = mem_len;
+  *hash = cx.loop != FQ_LOOP_SINGLE ? fq_hash_name_words(d, ns, nlen, cx.seed) : FQ_HASH_SKIP;
+  return true;
+}
+
+/* Reader step flags + validator verdict + statistics + (when the record reaches the name step) the name hash. */
+FQ_HD void fq_check_record(const uint8_t* d, const FqLine* L, const FqRecCtx& cx, FqRecOut* o, uint64_t* hash) {
+  if (fq_check_record_fast(d, L, cx, o, hash)) return;
+  fq_check_record_careful(d, L, cx, o);
+  *hash = fq_record_has_name(cx.loop, *o) ? fq_hash_name(d + o->name_off, o->name_len, cx.seed) : FQ_HASH_SKIP;
 }
 
 /* event key of one record's own failure (reader flags + validator), FQ_KEY_NONE when it is clean.  g = index of
@@ -348,10 +528,4 @@ FQ_HD uint64_t fq_record_key(int loop, uint64_t g, uint64_t step_base, const FqR
       return FQ_KEY_NONE;
   }
 }
-/* does a record of this loop reach the name step (index insert / mate claim / pair compare)? */
-FQ_HD bool fq_record_has_name(int loop, const FqRecOut& o) {
-  if (o.flags & (FQ_RF_STOP | FQ_RF_TRUNC | FQ_RF_NOTAT)) return false;
-  return loop != FQ_LOOP_SINGLE;
-}
-
 #endif

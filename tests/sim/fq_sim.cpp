@@ -78,14 +78,14 @@ class FqSimDevice : public FqDevice {
     n_launch_++;
     for (uint32_t k = 0; k < a.nrec; k++) {
       FqLine L[4]; lines_of(a, k, L);
-      FqRecOut o; fq_check_record(a.data, L, a.cx, &o);
+      FqRecOut o; uint64_t hsh; fq_check_record(a.data, L, a.cx, &o, &hsh);
       uint64_t g = a.g0 + k;
       uint64_t key = fq_record_key(a.cx.loop, g, a.step_base, o);
       if (key < *a.key) *a.key = key;
       bool named = fq_record_has_name(a.cx.loop, o);
       if (a.names) {
         a.names[k].off = o.name_off; a.names[k].len = o.name_len;
-        a.names[k].hash = named ? fq_hash_name(a.data + o.name_off, o.name_len, a.cx.seed) : FQ_HASH_SKIP;
+        a.names[k].hash = named ? hsh : FQ_HASH_SKIP;
       }
       if (a.cx.loop == FQ_LOOP_INDEX && named) { a.stats->n_names++; a.stats->mem_sum += o.mem_len; }
       /* statistics are only ever reported when every record was clean, so only clean records are counted */
@@ -220,7 +220,7 @@ class FqSimDevice : public FqDevice {
   }
   void explain(const uint8_t* data, const FqLine* lines4, const FqRecCtx& cx, FqRecOut* out) override {
     n_launch_++;
-    fq_check_record(data, lines4, cx, out);
+    fq_check_record_careful(data, lines4, cx, out);
   }
 
  private:

@@ -49,3 +49,14 @@ def test_sim_fuzz_against_oracle(seed):
     argv = argv + ["a.fq"] + (["b.fq"] if two else []) + (["pe"] if mode == "pe" else [])
     chunk = rng.choice([0, 0, 1, 5, 33, 200])
     assert fqg_run(argv, d1, d2, chunk=chunk, kind="sim") == oracle_run(argv, d1, d2), (argv, chunk, d1, d2)
+
+
+def test_fast_record_path_equals_careful_path(tmp_path):
+    """fq_record.h: the 16-byte-at-a-time path for clean records vs the byte-wise path (random records, all alignments)."""
+    import os
+    import subprocess
+    from _util import ROOT
+    exe = tmp_path / "test_record_paths"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "sim", "test_record_paths.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
