@@ -293,9 +293,9 @@ fq_records_kernel(const RecParams P) {
  * Records whose four lines do not fit the window are counted in out[3]; the host then falls back to the two-pass path. */
 constexpr int TILE_BYTES = 32768, TILE_MARGIN = 4096, TILE_LEFT = 16;
 constexpr int TILE_WIN = TILE_LEFT + TILE_BYTES + TILE_MARGIN;
-constexpr int TILE_THREADS = 128;
+constexpr int TILE_THREADS = 192;
 constexpr int TILE_LMAX = 2048;
-constexpr int TILE_CHUNKS_PER_THREAD = (TILE_BYTES + TILE_MARGIN) / 16 / TILE_THREADS; /* 18 */
+constexpr int TILE_CHUNKS_PER_THREAD = (TILE_BYTES + TILE_MARGIN) / 16 / TILE_THREADS; /* 12 */
 constexpr int TILE_SMEM = TILE_WIN + 48 + TILE_LMAX * 2;
 static_assert((TILE_BYTES + TILE_MARGIN) / 16 % TILE_THREADS == 0, "chunks must divide evenly");
 
@@ -363,17 +363,39 @@ fq_tile_kernel(const TileParams P) {
     uint32_t mk[TILE_CHUNKS_PER_THREAD / 2];
     uint32_t c_all = 0, c_T = 0;
     const uint32_t w0 = TILE_LEFT + tid * (TILE_CHUNKS_PER_THREAD * 16);
+    if (nloc == (uint32_t)TILE_WIN) { /* every tile but the last few: no bounds to check */
 #pragma unroll
-    for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i++) {
-      uint32_t w = w0 + i * 16, m = 0;
-      if (w < nloc) {
-        m = lf_mask16(*(const uint4*)(win + w));
-        if (nloc - w < 16) m &= (1u << (nloc - w)) - 1u;
+      for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i += 2) {
+        uint32_t m0 = lf_mask16(*(const uint4*)(win + w0 + i * 16)), m1 = lf_mask16(*(const uint4*)(win + w0 + i * 16 + 16));
+        mk[i >> 1] = m0 | (m1 << 16);
       }
-      if (i & 1) mk[i >> 1] |= m << 16; else mk[i >> 1] = m;
-      uint32_t c = __popc(m);
-      c_all += c;
-      if (w < TILE_LEFT + TILE_BYTES) c_T += c;
+      /* a thread's 12 chunks lie on one side of the tile / margin border except for one thread */
+      const uint32_t border = TILE_LEFT + TILE_BYTES;
+      if (w0 + TILE_CHUNKS_PER_THREAD * 16 <= border) {
+#pragma unroll
+        for (int j = 0; j < TILE_CHUNKS_PER_THREAD / 2; j++) c_all += __popc(mk[j]);
+        c_T = c_all;
+      } else {
+#pragma unroll
+        for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i++) {
+          uint32_t c = __popc((i & 1) ? (mk[i >> 1] >> 16) : (mk[i >> 1] & 0xFFFFu));
+          c_all += c;
+          if (w0 + i * 16 < border) c_T += c;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i++) {
+        uint32_t w = w0 + i * 16, m = 0;
+        if (w < nloc) {
+          m = lf_mask16(*(const uint4*)(win + w));
+          if (nloc - w < 16) m &= (1u << (nloc - w)) - 1u;
+        }
+        if (i & 1) mk[i >> 1] |= m << 16; else mk[i >> 1] = m;
+        uint32_t c = __popc(m);
+        c_all += c;
+        if (w < TILE_LEFT + TILE_BYTES) c_T += c;
+      }
     }
     /* block-wide exclusive prefix of c_all, total of c_T */
     uint32_t incl = c_all, sumT = c_T;
@@ -427,9 +449,9 @@ fq_tile_kernel(const TileParams P) {
     {
       const uint32_t gofs = (uint32_t)(t0 - TILE_LEFT);
 #pragma unroll
-      for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i++) {
-        uint32_t m = (i & 1) ? (mk[i >> 1] >> 16) : (mk[i >> 1] & 0xFFFFu);
-        uint32_t w = w0 + i * 16;
+      for (int j = 0; j < TILE_CHUNKS_PER_THREAD / 2; j++) {
+        uint32_t m = mk[j];
+        const uint32_t w = w0 + j * 32; /* bit b of the pair of chunks ↔ window offset w + b */
         while (m) {
           uint32_t b = __ffs(m) - 1; m &= m - 1;
           uint32_t e = w + b + 1;

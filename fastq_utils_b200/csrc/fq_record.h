@@ -337,17 +337,18 @@ FQ_HD uint32_t fq_range16(uint32_t a, uint32_t s, uint32_t e) {
   uint32_t lo = s > a ? s - a : 0u, hi = e - a < 16u ? e - a : 16u;
   return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
 }
-/* four words holding a flag in bit 0 of every byte → 16 flags in byte order */
+/* four words holding a flag in bit 7 of every byte → 16 flags in byte order */
 FQ_HD uint32_t fq_gather16(uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3) {
-  uint32_t lo = (((l0 & 0x01010101u) | ((l1 & 0x01010101u) << 4)) * 0x00204081u) >> 21;
-  uint32_t hi = (((l2 & 0x01010101u) | ((l3 & 0x01010101u) << 4)) * 0x00204081u) >> 21;
+  uint32_t lo = ((((l0 & 0x80808080u) >> 7) | ((l1 & 0x80808080u) >> 3)) * 0x00204081u) >> 21;
+  uint32_t hi = ((((l2 & 0x80808080u) >> 7) | ((l3 & 0x80808080u) >> 3)) * 0x00204081u) >> 21;
   return (lo & 0xFFu) | ((hi & 0xFFu) << 8);
 }
 /* 4 flag bits → 0xFF in each flagged byte */
 FQ_HD uint32_t fq_bytes_of4(uint32_t bits4) { return (((bits4 & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu; }
-/* ACGTN / acgtn predicate in bit 0 of every byte (other bits undefined) */
+/* ACGTN / acgtn predicate in bit 7 of every byte (other bits undefined).  The bits of a byte are lined up at bit 7 with
+ * multiplications by powers of two: on sm_100a these become IMAD.SHL on the FMA pipe, leaving the ALU pipe the seven LOP3s. */
 FQ_HD uint32_t fq_base_pred(uint32_t w) {
-  uint32_t b0 = w, b1 = w >> 1, b2 = w >> 2, b3 = w >> 3, b4 = w >> 4, b6 = w >> 6, b7 = w >> 7;
+  uint32_t b0 = w * 128u, b1 = w * 64u, b2 = w * 32u, b3 = w * 16u, b4 = w * 8u, b6 = w * 2u, b7 = w;
   uint32_t g00 = b0 & (~b2 | b1), g01 = b2 & b1 & ~b0, g10 = b2 & ~b1 & ~b0;
   return ((~b4 & ~b3 & g00) | (~b4 & b3 & g01) | (b4 & ~b3 & g10)) & b6 & ~b7;
 }
@@ -357,12 +358,12 @@ FQ_HD bool fq_seq_fast(const uint8_t* d, uint32_t s, uint32_t e) {
   FqU4 v = fq_ld128(d, a);
   if (~fq_gather16(fq_base_pred(v.x), fq_base_pred(v.y), fq_base_pred(v.z), fq_base_pred(v.w)) & fq_range16(a, s, e)) return false;
   if (a == alast) return true;
-  uint32_t all = 0x01010101u;
+  uint32_t all = 0x80808080u;
   for (a += 16; a < alast; a += 16) {
     v = fq_ld128(d, a);
     all &= fq_base_pred(v.x) & fq_base_pred(v.y) & fq_base_pred(v.z) & fq_base_pred(v.w);
   }
-  if ((all & 0x01010101u) != 0x01010101u) return false;
+  if ((all & 0x80808080u) != 0x80808080u) return false;
   v = fq_ld128(d, alast);
   return !(~fq_gather16(fq_base_pred(v.x), fq_base_pred(v.y), fq_base_pred(v.z), fq_base_pred(v.w)) & fq_range16(alast, s, e));
 }
