@@ -286,22 +286,18 @@ fq_records_kernel(const RecParams P) {
 }
 
 /* ------------------------------------------------------------------------------------------------ K1+K2 fused: one pass over HBM
- * Every WARP of a persistent grid claims 8 KiB tiles in order and works alone (no block barriers).  The tile, a 1.5 KiB
- * look-ahead margin and the 16 bytes before it are brought into the warp's slice of shared memory by ONE bulk async copy
- * (cp.async.bulk → UBLKCP, completion on the warp's mbarrier).  From shared memory: LF masks → warp prefix → decoupled
- * look-back gives the tile's global line number → the line ends go out to the line index, and every record that STARTS in
- * the tile is validated in place (one lane per record, fq_check_record on the shared window).  Records whose four lines do
- * not fit the window are counted in out[3]; the host then falls back to the two-pass path. */
-constexpr int TILE_BYTES = 8192, TILE_MARGIN = 1536, TILE_LEFT = 16;
+ * A persistent CTA claims 32 KiB tiles in order.  The tile plus a 4 KiB look-ahead margin (and the 16 bytes before it) is
+ * brought into shared memory by ONE bulk async copy (cp.async.bulk → UBLKCP, completion on an mbarrier).  From shared memory:
+ * LF masks → block prefix → decoupled look-back gives the tile's global line number → the line ends go out to the line index,
+ * and every record that STARTS in the tile is validated in place (one thread per record, fq_check_record on the shared window).
+ * Records whose four lines do not fit the window are counted in out[3]; the host then falls back to the two-pass path. */
+constexpr int TILE_BYTES = 32768, TILE_MARGIN = 4096, TILE_LEFT = 16;
 constexpr int TILE_WIN = TILE_LEFT + TILE_BYTES + TILE_MARGIN;
-constexpr int TILE_WARPS = 4, TILE_THREADS = TILE_WARPS * 32;
-constexpr int TILE_LMAX = 512;
-constexpr int TILE_CHUNKS_PER_LANE = (TILE_BYTES + TILE_MARGIN) / 16 / 32; /* 19 */
-constexpr int TILE_MASK_REGS = (TILE_CHUNKS_PER_LANE + 1) / 2;
-constexpr int TILE_WARP_SMEM = TILE_WIN + 48 + TILE_LMAX * 2 + 16;
-constexpr int TILE_SMEM = TILE_WARPS * TILE_WARP_SMEM;
-static_assert((TILE_BYTES + TILE_MARGIN) / 16 % 32 == 0, "chunks must divide evenly over the lanes");
-static_assert(TILE_WARP_SMEM % 16 == 0, "warp slices must stay 16-byte aligned");
+constexpr int TILE_THREADS = 192;
+constexpr int TILE_LMAX = 2048;
+constexpr int TILE_CHUNKS_PER_THREAD = (TILE_BYTES + TILE_MARGIN) / 16 / TILE_THREADS; /* 12 */
+constexpr int TILE_SMEM = TILE_WIN + 48 + TILE_LMAX * 2;
+static_assert((TILE_BYTES + TILE_MARGIN) / 16 % TILE_THREADS == 0, "chunks must divide evenly");
 
 struct TileParams {
   const uint8_t* data; uint32_t n; int virtual_end; uint32_t* line_end; uint32_t cap;
@@ -321,28 +317,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __global__ void __launch_bounds__(TILE_THREADS)
 fq_tile_kernel(const TileParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint8_t* win = smem + warp * TILE_WARP_SMEM;
-  uint16_t* lend = (uint16_t*)(win + TILE_WIN + 48);
-  const uint32_t bar = smem_u32(win + TILE_WIN + 48 + TILE_LMAX * 2);
-  if (lane == 0) {
+  uint8_t* win = smem;
+  uint16_t* lend = (uint16_t*)(smem + TILE_WIN + 48);
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tile, s_warp_all[TILE_THREADS / 32], s_warp_T[TILE_THREADS / 32], s_base, s_nl, s_cntT;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar = smem_u32(&s_bar);
+  if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
   uint32_t parity = 0;
   unsigned long long my_key = FQ_KEY_NONE, my_rds = 0, my_names = 0, my_mem = 0;
   uint32_t mn_rl = 0xFFFFFFFFu, mx_rl = 0, mn_q = 255, mx_q = 0, run_len = 0, run_cnt = 0;
 
   for (;;) {
-    __syncwarp(); /* every lane is done with the previous window */
-    uint32_t tile = 0;
-    if (lane == 0) {
-      tile = atomicAdd(P.ticket, 1u); /* tiles are claimed in order: the look-back only waits on warps that already run */
-      if (tile < P.ntiles) {
-        unsigned long long t0 = (unsigned long long)tile * TILE_BYTES;
-        unsigned long long src = tile ? t0 - TILE_LEFT : 0;
-        uint32_t dst_off = tile ? 0 : TILE_LEFT;
+    __syncthreads(); /* everyone is done with the previous window */
+    if (tid == 0) {
+      uint32_t t = atomicAdd(P.ticket, 1u);
+      s_tile = t;
+      if (t < P.ntiles) {
+        unsigned long long t0 = (unsigned long long)t * TILE_BYTES;
+        unsigned long long src = t ? t0 - TILE_LEFT : 0;
+        uint32_t dst_off = t ? 0 : TILE_LEFT;
         unsigned long long want = (unsigned long long)TILE_WIN - dst_off, have = ((unsigned long long)P.n - src + 15) & ~15ull;
         uint32_t bytes = (uint32_t)(want < have ? want : have);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -350,35 +347,37 @@ fq_tile_kernel(const TileParams P) {
                      ::"r"(smem_u32(win + dst_off)), "l"(P.data + src), "r"(bytes), "r"(bar) : "memory");
       }
     }
-    tile = __shfl_sync(FULL, tile, 0);
+    __syncthreads();
+    const uint32_t tile = s_tile;
     if (tile >= P.ntiles) break;
     const unsigned long long t0 = (unsigned long long)tile * TILE_BYTES;
     /* window offset w ↔ global offset t0 - 16 + w; real data below nloc */
     const uint32_t nloc = (uint32_t)min((unsigned long long)TILE_WIN, (unsigned long long)TILE_LEFT + (P.n - t0));
     {
       uint32_t spins = 0;
-      while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) { if (lane == 0) atomicExch(P.out + 4, 1u); break; } }
+      while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) { if (tid == 0) atomicExch(P.out + 4, 1u); break; } }
       parity ^= 1;
     }
-    if (tile == 0 && lane == 0) win[TILE_LEFT - 1] = '\n';
-    /* LF masks of this lane's 19 consecutive 16-byte chunks (304 bytes: conflict-free 128-bit shared loads) */
-    uint32_t mk[TILE_MASK_REGS];
+    if (tile == 0 && tid == 0) win[TILE_LEFT - 1] = '\n';
+    /* LF masks of this thread's 18 consecutive 16-byte chunks (window offsets 16 + 288*tid ...) */
+    uint32_t mk[TILE_CHUNKS_PER_THREAD / 2];
     uint32_t c_all = 0, c_T = 0;
-    const uint32_t w0 = TILE_LEFT + lane * (TILE_CHUNKS_PER_LANE * 16);
-    const uint32_t border = TILE_LEFT + TILE_BYTES;
-    if (nloc == (uint32_t)TILE_WIN) { /* every tile but the last: no bounds to check */
+    const uint32_t w0 = TILE_LEFT + tid * (TILE_CHUNKS_PER_THREAD * 16);
+    if (nloc == (uint32_t)TILE_WIN) { /* every tile but the last few: no bounds to check */
 #pragma unroll
-      for (int i = 0; i < TILE_CHUNKS_PER_LANE; i++) {
-        uint32_t m = lf_mask16(*(const uint4*)(win + w0 + i * 16));
-        if (i & 1) mk[i >> 1] |= m << 16; else mk[i >> 1] = m;
+      for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i += 2) {
+        uint32_t m0 = lf_mask16(*(const uint4*)(win + w0 + i * 16)), m1 = lf_mask16(*(const uint4*)(win + w0 + i * 16 + 16));
+        mk[i >> 1] = m0 | (m1 << 16);
       }
-      if (w0 + TILE_CHUNKS_PER_LANE * 16 <= border) {
+      /* a thread's 12 chunks lie on one side of the tile / margin border except for one thread */
+      const uint32_t border = TILE_LEFT + TILE_BYTES;
+      if (w0 + TILE_CHUNKS_PER_THREAD * 16 <= border) {
 #pragma unroll
-        for (int j = 0; j < TILE_MASK_REGS; j++) c_all += __popc(mk[j]);
+        for (int j = 0; j < TILE_CHUNKS_PER_THREAD / 2; j++) c_all += __popc(mk[j]);
         c_T = c_all;
       } else {
 #pragma unroll
-        for (int i = 0; i < TILE_CHUNKS_PER_LANE; i++) {
+        for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i++) {
           uint32_t c = __popc((i & 1) ? (mk[i >> 1] >> 16) : (mk[i >> 1] & 0xFFFFu));
           c_all += c;
           if (w0 + i * 16 < border) c_T += c;
@@ -386,7 +385,7 @@ fq_tile_kernel(const TileParams P) {
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < TILE_CHUNKS_PER_LANE; i++) {
+      for (int i = 0; i < TILE_CHUNKS_PER_THREAD; i++) {
         uint32_t w = w0 + i * 16, m = 0;
         if (w < nloc) {
           m = lf_mask16(*(const uint4*)(win + w));
@@ -395,54 +394,62 @@ fq_tile_kernel(const TileParams P) {
         if (i & 1) mk[i >> 1] |= m << 16; else mk[i >> 1] = m;
         uint32_t c = __popc(m);
         c_all += c;
-        if (w < border) c_T += c;
+        if (w < TILE_LEFT + TILE_BYTES) c_T += c;
       }
     }
-    /* warp-wide exclusive prefix of c_all, total of c_T */
-    uint32_t incl = c_all, cntT = c_T;
+    /* block-wide exclusive prefix of c_all, total of c_T */
+    uint32_t incl = c_all, sumT = c_T;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += a; }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cntT += __shfl_xor_sync(FULL, cntT, d);
+    for (int d = 16; d > 0; d >>= 1) sumT += __shfl_xor_sync(FULL, sumT, d);
+    if (lane == 31) s_warp_all[warp] = incl;
+    if (lane == 0) s_warp_T[warp] = sumT;
+    __syncthreads();
     uint32_t rank = incl - c_all;
-    const uint32_t nl_win = __shfl_sync(FULL, incl, 31);
-    /* decoupled look-back: publish this tile's count, then add up the predecessors' */
-    unsigned long long acc = 0;
-    if (tile > 0) {
-      if (lane == 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
-      long long look = (long long)tile - 1;
-      uint32_t spins = 0;
-      for (;;) {
-        long long idx = look - lane;
-        unsigned long long v64 = idx >= 0 ? ld_volatile64(P.tile_state + idx) : ST_INCL;
-        while (__any_sync(FULL, (v64 >> 62) == 0)) {
-          if ((v64 >> 62) == 0) v64 = ld_volatile64(P.tile_state + idx);
-          if (++spins > (1u << 26)) { if (lane == 0) atomicExch(P.out + 4, 2u); v64 = ST_INCL; }
-        }
-        uint32_t incl_mask = __ballot_sync(FULL, (v64 >> 62) == 2);
-        int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
-        unsigned long long part = lane <= first ? (v64 & ST_VALUE) : 0ull;
+    for (int wgt = 0; wgt < warp; wgt++) rank += s_warp_all[wgt];
+    if (warp == 0) {
+      uint32_t nl = 0, cntT = 0;
+      for (int wgt = 0; wgt < TILE_THREADS / 32; wgt++) { nl += s_warp_all[wgt]; cntT += s_warp_T[wgt]; }
+      unsigned long long acc = 0;
+      if (tile > 0) {
+        if (lane == 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
+        int look = (int)tile - 1;
+        uint32_t spins = 0;
+        for (;;) {
+          int idx = look - lane;
+          unsigned long long v64 = idx >= 0 ? ld_volatile64(P.tile_state + idx) : ST_INCL;
+          while (__any_sync(FULL, (v64 >> 62) == 0)) {
+            if ((v64 >> 62) == 0) v64 = ld_volatile64(P.tile_state + idx);
+            if (++spins > (1u << 26)) { if (lane == 0) atomicExch(P.out + 4, 2u); v64 = ST_INCL; }
+          }
+          uint32_t incl_mask = __ballot_sync(FULL, (v64 >> 62) == 2);
+          int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+          unsigned long long part = lane <= first ? (v64 & ST_VALUE) : 0ull;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
-        acc += part;
-        if (incl_mask) break;
-        look -= 32;
+          for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
+          acc += part;
+          if (incl_mask) break;
+          look -= 32;
+        }
+      }
+      if (lane == 0) {
+        st_volatile64(P.tile_state + tile, ST_INCL | (acc + cntT));
+        s_base = (uint32_t)acc; s_nl = nl; s_cntT = cntT;
+        if (tile == P.ntiles - 1) {
+          uint32_t cnt = (uint32_t)acc + cntT;
+          if (P.virtual_end && P.n > 0 && win[nloc - 1] != '\n') { if (cnt < P.cap) P.line_end[cnt] = P.n; cnt++; }
+          P.out[0] = cnt; P.out[1] = cnt > P.cap ? 1u : 0u;
+        }
       }
     }
-    if (lane == 0) {
-      st_volatile64(P.tile_state + tile, ST_INCL | (acc + cntT));
-      if (tile == P.ntiles - 1) {
-        uint32_t cnt = (uint32_t)acc + cntT;
-        if (P.virtual_end && P.n > 0 && win[nloc - 1] != '\n') { if (cnt < P.cap) P.line_end[cnt] = P.n; cnt++; }
-        P.out[0] = cnt; P.out[1] = cnt > P.cap ? 1u : 0u;
-      }
-    }
-    const uint32_t base_line = (uint32_t)acc;
+    __syncthreads();
+    const uint32_t base_line = s_base, nl_win = s_nl, cntT = s_cntT;
     /* line ends: window-relative list in shared memory, global offsets into the line index */
     {
       const uint32_t gofs = (uint32_t)(t0 - TILE_LEFT);
 #pragma unroll
-      for (int j = 0; j < TILE_MASK_REGS; j++) {
+      for (int j = 0; j < TILE_CHUNKS_PER_THREAD / 2; j++) {
         uint32_t m = mk[j];
         const uint32_t w = w0 + j * 32; /* bit b of the pair of chunks ↔ window offset w + b */
         while (m) {
@@ -454,7 +461,7 @@ fq_tile_kernel(const TileParams P) {
         }
       }
     }
-    __syncwarp();
+    __syncthreads();
     /* records that start in this tile */
     {
       const bool starts_here = win[TILE_LEFT - 1] == '\n';
@@ -464,22 +471,22 @@ fq_tile_kernel(const TileParams P) {
       const uint32_t nl_list = nl_win < (uint32_t)TILE_LMAX ? nl_win : (uint32_t)TILE_LMAX;
       const bool at_data_end = nloc < (uint32_t)TILE_WIN || t0 + TILE_BYTES + TILE_MARGIN >= P.n;
       const uint32_t nrec_tile = k0 <= cntT ? (cntT - k0) / 4 + 1 : 0;
-      for (uint32_t rb = 0; rb < nrec_tile; rb += 32) { /* trip count is uniform over the warp */
-        uint32_t r = rb + lane;
+      for (uint32_t rb = 0; rb < nrec_tile; rb += TILE_THREADS) { /* trip count is uniform over the block */
+        uint32_t r = rb + tid;
         uint32_t flush_len = 0, flush_cnt = 0;
         if (r < nrec_tile) {
           uint32_t k = k0 + 4 * r;
           uint32_t start = k == 0 ? (uint32_t)TILE_LEFT : (uint32_t)lend[k - 1 < (uint32_t)TILE_LMAX ? k - 1 : 0];
           bool in_list = k == 0 || k - 1 < nl_list;
-          if (in_list && start < border) {
+          if (in_list && start < TILE_LEFT + TILE_BYTES) {
             uint32_t g_local = (base_line + k - P.j0) >> 2;
             if (g_local < P.max_rec) {
               if (k + 3 >= nl_list) { /* the record's last line end is not in the window */
                 bool virtual_last = at_data_end && P.virtual_end && k + 3 == nl_list && win[nloc - 1] != '\n' && nl_win <= (uint32_t)TILE_LMAX;
-                if (!virtual_last) {
-                  if (!at_data_end || nl_win > (uint32_t)TILE_LMAX) atomicAdd(P.out + 3, 1u);
-                  goto next_record;
-                }
+                if (virtual_last) {
+                  /* file ends without LF: the fourth line ends at the end of the data */
+                } else if (!at_data_end || nl_win > (uint32_t)TILE_LMAX) atomicAdd(P.out + 3, 1u);
+                if (!virtual_last) goto next_record;
               }
               {
                 FqLine L[4];
@@ -721,7 +728,7 @@ class FqCudaDevice : public FqDevice {
     cudaMemPool_t pool; FQ_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev_));
     unsigned long long thr = ~0ull; /* keep freed blocks in the pool: allocations repeat every chunk */
     FQ_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    max_tiles_ = (uint32_t)((1ull << 31) / TILE_BYTES) + 2;
+    max_tiles_ = (uint32_t)((1ull << 31) / SCAN_TILE) + 2;
     FQ_CUDA_CHECK(cudaMalloc(&tile_state_, (size_t)max_tiles_ * sizeof(unsigned long long) + 64));
     ticket_ = (uint32_t*)(tile_state_ + max_tiles_);
   }
@@ -811,7 +818,7 @@ class FqCudaDevice : public FqDevice {
       int per_sm = 0;
       FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fq_tile_kernel, TILE_THREADS, TILE_SMEM));
       if (per_sm < 1) return false;
-      tile_blocks_ = per_sm * sms_; /* every warp resident: the look-back may wait on any earlier tile */
+      tile_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
     }
     TileParams P;
     P.data = a.data; P.n = a.n; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
@@ -820,7 +827,7 @@ class FqCudaDevice : public FqDevice {
     P.stats = a.stats; P.stats_range = a.stats_range; P.hist = a.hist; P.key = a.key; P.names = a.names; P.names_cap = a.names_cap;
     FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));
     FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
-    int grid = (int)std::min<uint32_t>((ntiles + TILE_WARPS - 1) / TILE_WARPS, (uint32_t)tile_blocks_);
+    int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)tile_blocks_);
     tic(FQG_K_TILE, a.n, ntiles);
     fq_tile_kernel<<<grid, TILE_THREADS, TILE_SMEM, st_>>>(P);
     toc(); launched();

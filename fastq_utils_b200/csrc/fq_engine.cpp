@@ -178,7 +178,7 @@ bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip
     uint32_t e[3] = {0, 0, 0};
     if (skip) dev_->download(e, le + skip - 1, 3 * sizeof(uint32_t)); else dev_->download(e + 1, le, 2 * sizeof(uint32_t));
     FqLine h, q; h.off = e[0]; h.len = e[1] - e[0]; q.off = e[1]; q.len = e[2] - e[1];
-    if (h.len < 400 && q.len < 500) { /* short reads only: long records do not fit the fused pass's window */
+    if (h.len < FQ_MAX_LABEL_LENGTH && q.len < 2048) { /* short reads only: long records do not fit the fused pass's window */
       dev_->sniff(data, h, q, (int32_t*)scratch_);
       int32_t o2[2]; dev_->download(o2, scratch_, sizeof o2);
       F.sniff_fmt = o2[0]; F.sniff_color = o2[1];
