@@ -302,7 +302,8 @@ static_assert((TILE_BYTES + TILE_MARGIN) / 16 % TILE_THREADS == 0, "chunks must 
 struct TileParams {
   const uint8_t* data; uint32_t n; int virtual_end; uint32_t* line_end; uint32_t cap;
   unsigned long long* tile_state; uint32_t* ticket; uint32_t ntiles;
-  uint32_t* out; /* [0] lines, [1] cap overflow, [2] first over-long header line, [3] records that did not fit, [4] internal error */
+  uint32_t* out; /* [0] lines, [1] cap overflow, [2] first over-long header line, [3] records that did not fit, [4] internal error,
+                    [5] first line whose end was stored by the tail tiles (line ends below 8 are stored too) */
   uint32_t j0, max_rec; unsigned long long g0, step_base; FqRecCtx cx;
   FqStats* stats; FqStats* stats_range; unsigned long long* hist; unsigned long long* key; FqName* names; uint32_t names_cap;
 };
@@ -436,6 +437,7 @@ fq_tile_kernel(const TileParams P) {
       if (lane == 0) {
         st_volatile64(P.tile_state + tile, ST_INCL | (acc + cntT));
         s_base = (uint32_t)acc; s_nl = nl; s_cntT = cntT;
+        if (tile + 2 == P.ntiles || (P.ntiles == 1 && tile == 0)) P.out[5] = (uint32_t)acc;
         if (tile == P.ntiles - 1) {
           uint32_t cnt = (uint32_t)acc + cntT;
           if (P.virtual_end && P.n > 0 && win[nloc - 1] != '\n') { if (cnt < P.cap) P.line_end[cnt] = P.n; cnt++; }
@@ -448,6 +450,9 @@ fq_tile_kernel(const TileParams P) {
     /* line ends: window-relative list in shared memory, global offsets into the line index */
     {
       const uint32_t gofs = (uint32_t)(t0 - TILE_LEFT);
+      /* the host only ever needs the first and the last few line ends of a chunk it validated in this pass: the full line
+       * index (4 bytes per line) is not written; the two-pass path rebuilds it on demand */
+      const bool keep_all = tile + 2 >= P.ntiles;
 #pragma unroll
       for (int j = 0; j < TILE_CHUNKS_PER_THREAD / 2; j++) {
         uint32_t m = mk[j];
@@ -456,7 +461,7 @@ fq_tile_kernel(const TileParams P) {
           uint32_t b = __ffs(m) - 1; m &= m - 1;
           uint32_t e = w + b + 1;
           if (rank < TILE_LMAX) lend[rank] = (uint16_t)e;
-          if (rank < cntT) { uint32_t gi = base_line + rank; if (gi < P.cap) P.line_end[gi] = gofs + e; }
+          if (rank < cntT) { uint32_t gi = base_line + rank; if ((keep_all || gi < 8u) && gi < P.cap) P.line_end[gi] = gofs + e; }
           rank++;
         }
       }
@@ -724,6 +729,8 @@ class FqCudaDevice : public FqDevice {
     cudaDeviceProp prop; FQ_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev_));
     sms_ = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : kSMs;
     FQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    FQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st2_, cudaStreamNonBlocking));
+    FQ_CUDA_CHECK(cudaEventCreateWithFlags(&evx_, cudaEventDisableTiming));
     FQ_CUDA_CHECK(cudaEventCreate(&ev0_)); FQ_CUDA_CHECK(cudaEventCreate(&ev1_));
     cudaMemPool_t pool; FQ_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev_));
     unsigned long long thr = ~0ull; /* keep freed blocks in the pool: allocations repeat every chunk */
@@ -734,12 +741,12 @@ class FqCudaDevice : public FqDevice {
   }
   ~FqCudaDevice() override {
     cudaSetDevice(dev_);
-    cudaStreamSynchronize(st_);
+    cudaStreamSynchronize(st_); cudaStreamSynchronize(st2_);
     for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : free_ev_) cudaEventDestroy(e);
     cudaFree(tile_state_);
-    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_);
-    cudaStreamDestroy(st_);
+    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_);
+    cudaStreamDestroy(st_); cudaStreamDestroy(st2_);
   }
   const char* name() const override { return "cuda"; }
   void* alloc(size_t n) override {
@@ -756,7 +763,7 @@ class FqCudaDevice : public FqDevice {
   }
   void copy(void* d, const void* s, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st_)); }
   void fill(void* d, int b, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemsetAsync(d, b, n, st_)); }
-  void sync() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); }
+  void sync() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); }
   void timer_start() override { FQ_CUDA_CHECK(cudaEventRecord(ev0_, st_)); }
   double timer_stop_ms() override {
     FQ_CUDA_CHECK(cudaEventRecord(ev1_, st_)); FQ_CUDA_CHECK(cudaEventSynchronize(ev1_));
@@ -842,17 +849,19 @@ class FqCudaDevice : public FqDevice {
   void index_insert(const FqTableArgs& a) override {
     if (!a.nrec) return;
     int grid = (int)std::min<uint32_t>((a.nrec + 255) / 256, (uint32_t)sms_ * 8);
-    tic(FQG_K_INDEX, 0, a.nrec);
-    fq_index_insert_kernel<<<grid, 256, 0, st_>>>(table_params(a));
-    toc();
+    after_main();
+    tic(FQG_K_INDEX, 0, a.nrec, st2_);
+    fq_index_insert_kernel<<<grid, 256, 0, st2_>>>(table_params(a));
+    toc(st2_);
     launched();
   }
   void mate_claim(const FqTableArgs& a) override {
     if (!a.nrec) return;
     int grid = (int)std::min<uint32_t>((a.nrec + 255) / 256, (uint32_t)sms_ * 8);
-    tic(FQG_K_MATE, 0, a.nrec);
-    fq_mate_claim_kernel<<<grid, 256, 0, st_>>>(table_params(a));
-    toc();
+    after_main();
+    tic(FQG_K_MATE, 0, a.nrec, st2_);
+    fq_mate_claim_kernel<<<grid, 256, 0, st2_>>>(table_params(a));
+    toc(st2_);
     launched();
   }
   void pair_compare(const FqPairArgs& a) override {
@@ -885,9 +894,10 @@ class FqCudaDevice : public FqDevice {
     if (!a.n) return;
     ShardParams P; P.a = a;
     int grid = (int)std::min<unsigned long long>((a.n + 255) / 256, (unsigned long long)sms_ * 8);
-    tic(FQG_K_INDEX, 0, a.n);
-    fq_shard_insert_kernel<<<grid, 256, 0, st_>>>(P);
-    toc(); launched();
+    after_main();
+    tic(FQG_K_INDEX, 0, a.n, st2_);
+    fq_shard_insert_kernel<<<grid, 256, 0, st2_>>>(P);
+    toc(st2_); launched();
   }
   void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {
     if (!n) return;
@@ -905,18 +915,25 @@ class FqCudaDevice : public FqDevice {
   /* CUDA-event stopwatch around one launch; elapsed times are read back lazily (collect) */
   struct KStat { double ms = 0; uint64_t launches = 0, bytes = 0, items = 0; };
   struct Pending { int cls; cudaEvent_t a, b; };
-  void tic(int cls, uint64_t bytes, uint64_t items) {
+  /* The index kernels (random-access, latency-bound) run on a second stream so that they overlap the next chunk's
+   * streaming pass; they start after everything queued on the main stream so far (names, table fills, directories). */
+  void after_main() {
+    FQ_CUDA_CHECK(cudaEventRecord(evx_, st_));
+    FQ_CUDA_CHECK(cudaStreamWaitEvent(st2_, evx_, 0));
+  }
+  void tic(int cls, uint64_t bytes, uint64_t items, cudaStream_t st = nullptr) {
+    if (!st) st = st_;
     Pending p; p.cls = cls;
     if (free_ev_.size() >= 2) { p.a = free_ev_.back(); free_ev_.pop_back(); p.b = free_ev_.back(); free_ev_.pop_back(); }
     else { FQ_CUDA_CHECK(cudaEventCreate(&p.a)); FQ_CUDA_CHECK(cudaEventCreate(&p.b)); }
     kst_[cls].launches++; kst_[cls].bytes += bytes; kst_[cls].items += items;
-    FQ_CUDA_CHECK(cudaEventRecord(p.a, st_));
+    FQ_CUDA_CHECK(cudaEventRecord(p.a, st));
     pending_.push_back(p);
   }
-  void toc() { FQ_CUDA_CHECK(cudaEventRecord(pending_.back().b, st_)); }
+  void toc(cudaStream_t st = nullptr) { FQ_CUDA_CHECK(cudaEventRecord(pending_.back().b, st ? st : st_)); }
   void collect() {
     if (pending_.empty()) return;
-    FQ_CUDA_CHECK(cudaStreamSynchronize(st_));
+    FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
     for (auto& p : pending_) {
       float ms = 0; FQ_CUDA_CHECK(cudaEventElapsedTime(&ms, p.a, p.b));
       kst_[p.cls].ms += ms;
@@ -928,7 +945,8 @@ class FqCudaDevice : public FqDevice {
   std::vector<Pending> pending_;
   std::vector<cudaEvent_t> free_ev_;
   int dev_ = 0, sms_ = kSMs, tile_blocks_ = 0;
-  cudaStream_t st_ = nullptr;
+  cudaStream_t st_ = nullptr, st2_ = nullptr;
+  cudaEvent_t evx_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;
   unsigned long long n_launch_ = 0;

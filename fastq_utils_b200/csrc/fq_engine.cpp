@@ -121,7 +121,16 @@ void FqEngine::feed_device(int file, const void* dptr, size_t n, bool last) {
   }
 }
 
-uint32_t FqEngine::line_end_at(const FqBuffer& b, uint32_t idx) {
+/* the fused pass stores only the line ends the host normally needs; anything else rebuilds the index with K1 */
+void FqEngine::ensure_full_index(FqBuffer& b) {
+  if (!b.index_partial) return;
+  uint32_t cap = b.n / 32 + 4096; /* the capacity the fused pass allocated and did not overflow */
+  dev_->scan_lines(b.data, b.n, b.index_virtual_end ? 1 : 0, b.line_end, cap, scratch_);
+  dev_->sync();
+  b.index_partial = false;
+}
+uint32_t FqEngine::line_end_at(FqBuffer& b, uint32_t idx) {
+  if (b.index_partial && idx >= 8 && idx < b.index_from) ensure_full_index(b);
   uint32_t v; dev_->download(&v, b.line_end + idx, sizeof v); return v;
 }
 
@@ -204,7 +213,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
   uint32_t ncap = cap / 4 + 1;
   FqName* names = loop != FQ_LOOP_SINGLE ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
-  uint32_t init[5] = {0, 0, kNone32, 0, 0};
+  uint32_t init[6] = {0, 0, kNone32, 0, 0, 0};
   dev_->upload(tile_out_, init, sizeof init);
   FqTileArgs a; memset(&a, 0, sizeof a);
   a.data = B.data; a.n = B.n; a.virtual_end = last ? 1 : 0; a.line_end = B.line_end; a.cap = cap; a.out5 = tile_out_;
@@ -212,17 +221,18 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
   a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; a.key = key_; a.names = names; a.names_cap = ncap;
   bool launched = dev_->tile_pass(a);
-  uint32_t out5[5] = {0, 0, kNone32, 0, 0};
+  uint32_t out5[6] = {0, 0, kNone32, 0, 0, 0};
   if (launched) dev_->download(out5, tile_out_, sizeof out5); else dev_->sync();
   if (launched && !out5[1] && out5[2] == kNone32 && !out5[3] && !out5[4]) {
-    B.nlines = out5[0];
+    B.nlines = out5[0]; B.index_partial = true; B.index_from = out5[5]; B.index_virtual_end = last;
     *names_out = names; *names_cap = ncap;
     return true;
   }
   /* not usable: a line gzgets would split, a record longer than the window, more lines than guessed, or no such kernel */
   if (names) dev_->release(names);
   bool keep_index = launched && !out5[1] && !out5[4];
-  if (keep_index) B.nlines = out5[0]; else { dev_->release(B.line_end); B.line_end = nullptr; }
+  if (keep_index) { B.nlines = out5[0]; B.index_partial = true; B.index_from = out5[5]; B.index_virtual_end = last; }
+  else { dev_->release(B.line_end); B.line_end = nullptr; }
   if (launched) fused_fallback();
   else fused_ok_ = false;
   return false;
@@ -278,7 +288,7 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
     uint32_t need = 4 - std::min<uint32_t>(F.pend_lfs, 3);
     uint32_t avail = B.nlines - j;
     if (avail >= need) {
-      uint32_t cut = line_end_at(B, j + need - 1);
+      uint32_t cut = line_end_at(F.bufs[b], j + need - 1);
       size_t bn = F.pend_n + (cut - pos);
       uint8_t* bd = (uint8_t*)dev_->alloc(bn + kPad);
       dev_->copy(bd, F.pend, F.pend_n);
@@ -305,7 +315,7 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
       if (nrec) {
         FqSegment s; s.buf = b; s.q = pos; s.j0 = j; s.nrec = nrec; s.fused = true;
         j += 4 * nrec;
-        uint32_t end = line_end_at(B, j - 1);
+        uint32_t end = line_end_at(F.bufs[b], j - 1);
         s.span = end - pos; pos = end;
         s.g0 = F.nrec; F.nrec += nrec; s.names = fused_names;
         F.segs.push_back(s);
@@ -329,6 +339,7 @@ void FqEngine::segmentize(int file, int b, uint32_t pos, uint32_t j, bool last) 
     const FqBuffer B = F.bufs[b];
     uint32_t avail = B.nlines - j, nrec = avail / 4;
     uint32_t a = kNone32;
+    if (B.index_partial && !(j >= 1 && j - 1 >= B.index_from) && !(B.nlines <= 8)) { ensure_full_index(F.bufs[b]); }
     if (avail > 0 || (!last && pos < B.n)) {
       dev_->fill(scratch_, 0xFF, sizeof(uint32_t));
       dev_->find_overlong(B.line_end, pos, j, avail, B.n, last ? 0 : 1, scratch_);
@@ -338,7 +349,7 @@ void FqEngine::segmentize(int file, int b, uint32_t pos, uint32_t j, bool last) 
     if (nfast) {
       FqSegment s; s.buf = b; s.q = pos; s.j0 = j; s.nrec = nfast;
       j += 4 * nfast;
-      pos = line_end_at(B, j - 1);
+      pos = line_end_at(F.bufs[b], j - 1);
       s.span = pos - s.q;
       add_segment(file, s);
     }
@@ -405,6 +416,7 @@ void FqEngine::record_lines(int file, uint64_t g, FqLine out[4], const uint8_t**
   size_t lo = 0, hi = F.segs.size();
   while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (F.segs[mid].g0 <= g) lo = mid; else hi = mid; }
   const FqSegment& s = F.segs[lo];
+  ensure_full_index(F.bufs[s.buf]);
   const FqBuffer& B = F.bufs[s.buf];
   if (data) *data = B.data;
   if (s.explicit_lines) { memcpy(out, s.lines_host, 4 * sizeof(FqLine)); return; }
@@ -473,6 +485,7 @@ void FqEngine::launch_segment(int file, size_t si) {
   if (loop_of(file) == FQ_LOOP_MATE && eff_records(f_[0]) == 0) return; /* "No reads found": file 2 is never opened */
   uint32_t nrec = (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0);
   if (s.fused) { launch_names(file, si, nrec); return; } /* only reached when a table rebuild replays the name step */
+  ensure_full_index(F.bufs[s.buf]);
   sniff_if_needed(file, s);
   const FqBuffer& B = F.bufs[s.buf];
   FqRecordsArgs a; memset(&a, 0, sizeof a);
@@ -596,6 +609,7 @@ void FqEngine::finish(fqg_report* rep) {
   for (int attempt = 0;; attempt++) {
     if (attempt > 16) throw std::runtime_error("finish: too many reprocessing rounds");
     launch_pairs();
+    dev_->sync(); /* the index kernels run on their own stream */
     dev_->download(&dev_key, key_, sizeof dev_key);
     dev_->download(ctr, counters_, sizeof ctr);
     if (ctr[2]) throw std::runtime_error("index table overflow");
@@ -822,6 +836,7 @@ void FqEngine::fill_error(fqg_report* rep, uint64_t key, int host_code, int host
 }
 
 void FqEngine::fill_stats(fqg_report* rep) {
+  dev_->sync();
   FqStats st[2];
   for (int f = 0; f < 2; f++) dev_->download(&st[f], f_[f].stats, sizeof(FqStats));
   unsigned long long ctr[4]; dev_->download(ctr, counters_, sizeof ctr);
@@ -963,6 +978,7 @@ void FqEngine::shard_insert(const void* meta, uint64_t n, const void* blob, uint
 }
 
 void FqEngine::shard_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* collisions) {
+  dev_->sync();
   unsigned long long ctr[4]; dev_->download(ctr, counters_, sizeof ctr);
   if (ctr[2]) throw std::runtime_error("index table overflow");
   *collisions = ctr[0]; *key = ctr[3]; *record = 0; *name_len = 0; name[0] = 0;

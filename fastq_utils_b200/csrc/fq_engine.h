@@ -17,6 +17,9 @@ struct FqBuffer {
   bool owned = false;
   uint32_t* line_end = nullptr;
   uint32_t nlines = 0;       /* lines with an end inside the buffer (a final LF-less line counts when the file ended here) */
+  bool index_partial = false; /* fused pass: only line ends [0,8) and [index_from, nlines) are stored */
+  uint32_t index_from = 0;
+  bool index_virtual_end = false;
 };
 
 struct FqSegment {
@@ -110,7 +113,8 @@ class FqEngine {
   void ensure_table(uint64_t names_total);
   void sync_dir(int file);
   void sniff_if_needed(int file, const FqSegment& s);
-  uint32_t line_end_at(const FqBuffer& b, uint32_t idx);
+  uint32_t line_end_at(FqBuffer& b, uint32_t idx);
+  void ensure_full_index(FqBuffer& b);
   void record_lines(int file, uint64_t g, FqLine out[4], const uint8_t** data);
   int first_byte_of_line(int file, uint64_t global_line);
   void launch_pairs();
