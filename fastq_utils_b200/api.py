@@ -89,6 +89,11 @@ def lib():
         L.fqg_shard_insert.argtypes = [vp, vp, u64, vp, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
         L.fqg_shard_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(u64)]
         L.fqg_hist_range.argtypes = [vp, ci, u64, u64, ctypes.POINTER(u64)]
+        L.fqg_shard_claim.argtypes = [vp, vp, u64, vp, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64), u64]
+        L.fqg_shard_claim_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(u64), ctypes.POINTER(u64)]
+        L.fqg_sniff_device.argtypes = [vp, ci, vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+        L.fqg_set_sniff.argtypes = [vp, ci, ctypes.c_int32, ctypes.c_int32]
+        L.fqg_set_file_total.argtypes = [vp, ci, u64]
         if hasattr(L, "fqg_synth_illumina"):  # absent from the test stand-in
             L.fqg_synth_illumina.argtypes = [vp, u64, u64, u64, ci, u64, vp]
             L.fqg_synth_longreads.argtypes = [vp, vp, u64, u64, u64, vp]
@@ -217,6 +222,28 @@ class FastqInfo:
         name = ctypes.create_string_buffer(1024)
         _check(self._ctx, lib().fqg_shard_result(self._ctx, ctypes.byref(key), ctypes.byref(rec), name, ctypes.byref(ln), ctypes.byref(col)), "fqg_shard_result")
         return int(key.value), int(rec.value), name.raw[:ln.value], int(col.value)
+
+    def shard_claim(self, meta_ptr, n, blob_ptr, meta_start, blob_start, step_base):
+        ns = len(blob_start)
+        ms, bs = (ctypes.c_uint64 * (ns + 1))(*meta_start), (ctypes.c_uint64 * ns)(*blob_start)
+        _check(self._ctx, lib().fqg_shard_claim(self._ctx, ctypes.c_void_p(meta_ptr), n, ctypes.c_void_p(blob_ptr), ns, ms, bs, step_base), "fqg_shard_claim")
+
+    def shard_claim_result(self):
+        key, rec, ln, cl, col = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_uint64(), ctypes.c_uint64()
+        name = ctypes.create_string_buffer(1024)
+        _check(self._ctx, lib().fqg_shard_claim_result(self._ctx, ctypes.byref(key), ctypes.byref(rec), name, ctypes.byref(ln), ctypes.byref(cl), ctypes.byref(col)), "fqg_shard_claim_result")
+        return int(key.value), int(rec.value), name.raw[:ln.value], int(cl.value), int(col.value)
+
+    def sniff_device(self, file, ptr, n, skip):
+        f, c = ctypes.c_int32(), ctypes.c_int32()
+        _check(self._ctx, lib().fqg_sniff_device(self._ctx, file, ctypes.c_void_p(ptr), n, skip, ctypes.byref(f), ctypes.byref(c)), "fqg_sniff_device")
+        return int(f.value), int(c.value)
+
+    def set_sniff(self, file, fmt, color):
+        _check(self._ctx, lib().fqg_set_sniff(self._ctx, file, fmt, color), "fqg_set_sniff")
+
+    def set_file_total(self, file, total):
+        _check(self._ctx, lib().fqg_set_file_total(self._ctx, file, total), "fqg_set_file_total")
 
     def hist_range(self, file, lo, hi):
         out = (ctypes.c_uint64 * (hi - lo + 1))()

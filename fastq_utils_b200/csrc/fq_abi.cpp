@@ -116,3 +116,24 @@ extern "C" int fqg_hist_range(fqg_ctx* c, int file, uint64_t lo, uint64_t hi, ui
   if (!c || file < 0 || file > 1 || !out) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->eng->hist_range(file, lo, hi, out))
 }
+
+extern "C" int fqg_shard_claim(fqg_ctx* c, const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start, uint64_t step_base) {
+  if (!c || !meta_start || !blob_start) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_claim(meta, n, blob, n_src, meta_start, blob_start, step_base))
+}
+extern "C" int fqg_shard_claim_result(fqg_ctx* c, uint64_t* key, uint64_t* record, char name[1024], uint32_t* name_len, uint64_t* claimed, uint64_t* collisions) {
+  if (!c || !key || !record || !name || !name_len || !claimed || !collisions) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_claim_result(key, record, name, name_len, claimed, collisions))
+}
+extern "C" int fqg_sniff_device(fqg_ctx* c, int file, const void* dptr, size_t n, uint32_t skip, int32_t* fmt, int32_t* color) {
+  if (!c || file < 0 || file > 1 || !dptr || !n || !fmt || !color) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->sniff_device(file, dptr, n, skip, fmt, color))
+}
+extern "C" int fqg_set_sniff(fqg_ctx* c, int file, int32_t fmt, int32_t color) {
+  if (!c || file < 0 || file > 1) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->set_sniff(file, fmt, color))
+}
+extern "C" int fqg_set_file_total(fqg_ctx* c, int file, uint64_t total) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->set_file_total(file, total))
+}

@@ -59,6 +59,12 @@ __device__ __forceinline__ uint32_t lf_mask16(uint4 v) {
   uint32_t hi = (((z2 >> 7) | (z3 >> 3)) * 0x00204081u) >> 21;
   return (lo & 0xFFu) | ((hi & 0xFFu) << 8);
 }
+/* interleaved flag layout of fq_count_kernel: byte k of word i sits at bit 8k+i; keep the bytes below `valid` (1..15) */
+__device__ __forceinline__ uint32_t lf_mask_bits_below(uint32_t valid) {
+  uint32_t m = 0;
+  for (uint32_t b = 0; b < valid; b++) m |= 1u << (8u * (b & 3u) + (b >> 2));
+  return m;
+}
 __device__ __forceinline__ unsigned long long ld_volatile64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -151,6 +157,23 @@ fq_scan_kernel(const uint8_t* __restrict__ data, uint32_t n, int virtual_end, ui
       }
     }
   }
+}
+
+/* LF count only (multi-GPU prescan: the line phase of a byte range must be known before it can be validated) */
+__global__ void __launch_bounds__(256)
+fq_count_kernel(const uint8_t* __restrict__ data, uint32_t n, unsigned long long* out) {
+  unsigned long long c = 0;
+  const uint32_t nchunks = (n + 15) / 16;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nchunks; i += gridDim.x * blockDim.x) {
+    uint4 v = ld_stream16(data + (size_t)i * 16);
+    uint32_t z = (fq_zero_bytes(v.x ^ 0x0A0A0A0Au) >> 7) | (fq_zero_bytes(v.y ^ 0x0A0A0A0Au) >> 6) |
+                 (fq_zero_bytes(v.z ^ 0x0A0A0A0Au) >> 5) | (fq_zero_bytes(v.w ^ 0x0A0A0A0Au) >> 4);
+    if (n - i * 16 < 16) z &= lf_mask_bits_below(n - i * 16);
+    c += __popc(z);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(FULL, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 __global__ void fq_overlong_kernel(const uint32_t* __restrict__ line_end, uint32_t q, uint32_t j0, uint32_t nlines, uint32_t n,
@@ -642,7 +665,7 @@ fq_names_count_kernel(const FqName* __restrict__ names, uint32_t nrec, uint32_t 
     unsigned long long h = names[k].hash;
     if (h == FQ_HASH_SKIP) continue;
     uint32_t o = fq_owner_of(h, world);
-    atomicAdd(&sc[2 * o], 1ull); atomicAdd(&sc[2 * o + 1], (unsigned long long)names[k].len);
+    atomicAdd(&sc[2 * o], 1ull); atomicAdd(&sc[2 * o + 1], (unsigned long long)((names[k].len + 3u) & ~3u));
   }
   __syncthreads();
   if (threadIdx.x < 2 * world && sc[threadIdx.x]) atomicAdd(out + threadIdx.x, sc[threadIdx.x]);
@@ -662,16 +685,16 @@ fq_names_pack_kernel(const FqName* __restrict__ names, const uint8_t* __restrict
     if (k < nrec) nm = names[k];
     bool valid = nm.hash != FQ_HASH_SKIP;
     uint32_t o = 0; unsigned long long my_m = 0, my_b = 0;
-    if (valid) { o = fq_owner_of(nm.hash, world); my_m = atomicAdd(&s_cnt[2 * o], 1ull); my_b = atomicAdd(&s_cnt[2 * o + 1], (unsigned long long)nm.len); }
+    if (valid) { o = fq_owner_of(nm.hash, world); my_m = atomicAdd(&s_cnt[2 * o], 1ull); my_b = atomicAdd(&s_cnt[2 * o + 1], (unsigned long long)((nm.len + 3u) & ~3u)); }
     __syncthreads();
     if (threadIdx.x < 2 * world) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(cursor + threadIdx.x, s_cnt[threadIdx.x]) : 0ull;
     __syncthreads();
     if (valid) {
-      unsigned long long bo = s_base[2 * o + 1] + my_b;
+      unsigned long long bo = s_base[2 * o + 1] + my_b; /* multiple of 4: names are padded to whole words in the blob */
       FqPackedName pn; pn.hash = nm.hash; pn.record = g0 + k; pn.off = (uint32_t)bo; pn.len = nm.len;
       meta[base[2 * o] + s_base[2 * o] + my_m] = pn;
-      uint8_t* dst = blob + base[2 * o + 1] + bo; const uint8_t* src = data + nm.off;
-      for (uint32_t i = 0; i < nm.len; i++) dst[i] = src[i];
+      uint32_t* dst = (uint32_t*)(blob + base[2 * o + 1] + bo);
+      for (uint32_t i = 0; i < nm.len; i += 4) dst[i >> 2] = fq_low_bytes(fq_ldu32(data, nm.off + i), nm.len - i);
     }
     __syncthreads();
   }
@@ -710,6 +733,37 @@ fq_shard_insert_kernel(const ShardParams P) {
       break;
     }
   }
+}
+struct ClaimParams { FqShardArgs a; FqShardArgs ins; unsigned long long sb; };
+__global__ void __launch_bounds__(256)
+fq_shard_claim_kernel(const ClaimParams P) {
+  const FqShardArgs& a = P.a;
+  const unsigned long long posmask = (1ull << FQ_SHARD_POS_BITS) - 1;
+  unsigned long long claimed = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long b0 = (unsigned long long)blockIdx.x * blockDim.x; b0 < a.n; b0 += stride) {
+    unsigned long long m = b0 + threadIdx.x;
+    if (m >= a.n) continue;
+    const FqPackedName pn = a.meta[m];
+    unsigned long long i = pn.hash & a.mask, probes = 0, unpaired = FQ_IDX_NONE;
+    for (;; i = (i + 1) & a.mask) {
+      if (++probes > a.mask + 1) { unpaired = pn.record; break; }
+      const FqSlot* s = a.slots + i;
+      unsigned long long cur = s->hash;
+      if (cur == FQ_HASH_EMPTY) { unpaired = pn.record; break; }
+      if (cur != pn.hash) continue;
+      uint32_t ol, ml; const uint8_t* on = shard_name(P.ins, s->idx1 & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
+      if (!(ol == ml && fq_bytes_equal(on, mn, ml))) { atomicAdd(a.counters + 0, 1ull); break; }
+      unsigned long long old = atomicMin(&a.slots[i].claim2, pn.record);
+      if (old == FQ_IDX_NONE) claimed++;
+      else unpaired = old > pn.record ? old : pn.record;
+      break;
+    }
+    if (unpaired != FQ_IDX_NONE) atomicMin(a.dup_key, FQ_KEY(P.sb + unpaired, FQ_R_NAME));
+  }
+  __syncwarp();
+  claimed = warp_sum64(claimed);
+  if ((threadIdx.x & 31) == 0 && claimed) atomicAdd(a.counters + 1, claimed);
 }
 __global__ void fq_shard_find_kernel(const FqPackedName* __restrict__ meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) {
   for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (unsigned long long)gridDim.x * blockDim.x)
@@ -789,6 +843,12 @@ class FqCudaDevice : public FqDevice {
     fq_scan_kernel<<<ntiles, SCAN_THREADS, 0, st_>>>(data, n, virtual_end, line_end, cap, tile_state_, ticket_, ntiles, out2);
     toc();
     launched();
+  }
+  void count_lines(const uint8_t* data, uint32_t n, unsigned long long* out) override {
+    if (!n) return;
+    tic(FQG_K_SCAN, n, 1);
+    fq_count_kernel<<<sms_ * 8, 256, 0, st_>>>(data, n, out);
+    toc(); launched();
   }
   void find_overlong(const uint32_t* line_end, uint32_t q, uint32_t j0, uint32_t nlines, uint32_t n, int tail_from_n, uint32_t* out) override {
     uint32_t total = nlines + (tail_from_n ? 1u : 0u);
@@ -897,6 +957,15 @@ class FqCudaDevice : public FqDevice {
     after_main();
     tic(FQG_K_INDEX, 0, a.n, st2_);
     fq_shard_insert_kernel<<<grid, 256, 0, st2_>>>(P);
+    toc(st2_); launched();
+  }
+  void shard_claim(const FqShardArgs& a, const FqShardArgs& ins, unsigned long long sb) override {
+    if (!a.n) return;
+    ClaimParams P; P.a = a; P.ins = ins; P.sb = sb;
+    int grid = (int)std::min<unsigned long long>((a.n + 255) / 256, (unsigned long long)sms_ * 8);
+    after_main();
+    tic(FQG_K_MATE, 0, a.n, st2_);
+    fq_shard_claim_kernel<<<grid, 256, 0, st2_>>>(P);
     toc(st2_); launched();
   }
   void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {

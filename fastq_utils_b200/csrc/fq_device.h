@@ -87,6 +87,8 @@ class FqDevice {
   /* K1: exclusive end offsets of all lines of data[0,n) in order; a last line without LF counts when virtual_end.
    * out[0] = number of lines, out[1] = 1 if more than cap were found (only the first cap are stored). */
   virtual void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) = 0;
+  /* number of LF bytes in data[0,n): *out += count (64-bit) */
+  virtual void count_lines(const uint8_t* data, uint32_t n, unsigned long long* out) = 0;
   /* first line i in [j0, j0+nlines) whose raw length reaches the gzgets limit of its phase ((i-j0)&3); *out = min(*out, i) */
   /* When tail_from_n != 0 the unterminated bytes after the last counted line (up to n) are judged as line j0+nlines. */
   virtual void find_overlong(const uint32_t* line_end, uint32_t q, uint32_t j0, uint32_t nlines, uint32_t n, int tail_from_n, uint32_t* out) = 0;
@@ -108,6 +110,9 @@ class FqDevice {
   virtual void names_pack(const FqName* names, const uint8_t* data, uint32_t nrec, uint64_t g0, uint32_t world, FqPackedName* meta,
                           uint8_t* blob, const unsigned long long* base, unsigned long long* cursor) = 0;
   virtual void shard_insert(const FqShardArgs& a) = 0;
+  /* owner side of the mate loop: tuples of file 2 claim the slots filled from `inserted` (file 1's tuples); unpaired events
+   * go to a.dup_key as FQ_KEY(step_base + record, FQ_R_NAME), first claims are counted in a.counters[1] */
+  virtual void shard_claim(const FqShardArgs& a, const FqShardArgs& inserted, unsigned long long step_base) = 0;
   virtual void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) = 0;
   /* details of one record for the error message */
   virtual void explain(const uint8_t* data, const FqLine* lines4_host, const FqRecCtx& cx, FqRecOut* out_dev) = 0;

@@ -57,7 +57,7 @@ FqEngine::~FqEngine() {
 void FqEngine::reset() {
   dev_->sync();
   for (int f = 0; f < 2; f++) free_file(f_[f]);
-  seed_ = 0; finished_ = false; fused_ok_ = !(cfg_.flags & FQG_FLAG_TWO_PASS);
+  seed_ = 0; finished_ = false; total0_set_ = false; total0_ = 0; fused_ok_ = !(cfg_.flags & FQG_FLAG_TWO_PASS);
   { const char* e = getenv("FQG_FUSED_MIN_BYTES"); fused_min_ = e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 20); } /* test hook */
   /* results */
   dev_->fill(key_, 0xFF, sizeof(unsigned long long));
@@ -83,7 +83,9 @@ int FqEngine::loop_of(int file) const {
   }
 }
 static uint64_t eff_records(const FqFile& F) { return std::min<uint64_t>(F.nrec, F.limit); }
-uint64_t FqEngine::step_base(int file) const { return loop_of(file) == FQ_LOOP_MATE ? eff_records(f_[0]) + 1 : 0; }
+/* records the index loop read from file 1 (over all ranks in a sharded run) */
+uint64_t FqEngine::total0() const { return total0_set_ ? total0_ : eff_records(f_[0]); }
+uint64_t FqEngine::step_base(int file) const { return loop_of(file) == FQ_LOOP_MATE ? total0() + 1 : 0; }
 
 FqRecCtx FqEngine::make_ctx(int file) const {
   FqRecCtx cx; memset(&cx, 0, sizeof cx);
@@ -175,7 +177,7 @@ void FqEngine::scan_buffer(FqBuffer& B, bool last) {
 
 /* Sniff the first record of a file from a short prefix so that the fused pass knows the read-name format and colour space
  * before it runs.  False when the prefix does not hold the two lines (the two-pass path sniffs later). */
-bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip) {
+bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip, bool short_only) {
   FqFile& F = f_[file];
   if (F.sniff_fmt >= 0) return true;
   uint32_t pn = std::min<uint32_t>(n, 1u << 16), cap = 4096;
@@ -187,7 +189,7 @@ bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip
     uint32_t e[3] = {0, 0, 0};
     if (skip) dev_->download(e, le + skip - 1, 3 * sizeof(uint32_t)); else dev_->download(e + 1, le, 2 * sizeof(uint32_t));
     FqLine h, q; h.off = e[0]; h.len = e[1] - e[0]; q.off = e[1]; q.len = e[2] - e[1];
-    if (h.len < FQ_MAX_LABEL_LENGTH && q.len < 2048) { /* short reads only: long records do not fit the fused pass's window */
+    if (!short_only || (h.len < FQ_MAX_LABEL_LENGTH && q.len < 2048)) { /* fused pass: short reads only, long records do not fit its window */
       dev_->sniff(data, h, q, (int32_t*)scratch_);
       int32_t o2[2]; dev_->download(o2, scratch_, sizeof o2);
       F.sniff_fmt = o2[0]; F.sniff_color = o2[1];
@@ -203,7 +205,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   FqFile& F = f_[file];
   FqBuffer& B = F.bufs[b];
   int loop = loop_of(file);
-  if (loop == FQ_LOOP_MATE && eff_records(f_[0]) == 0) return false;
+  if (loop == FQ_LOOP_MATE && total0() == 0) return false;
   if (F.limit != ~0ull) return false;
   if (F.sniff_fmt < 0) {
     if (F.nrec != 0 || F.pend_n != 0) return false;
@@ -482,7 +484,7 @@ void FqEngine::launch_segment(int file, size_t si) {
   const FqSegment& s = F.segs[si];
   uint64_t lim = F.limit;
   if (s.g0 >= lim) return;
-  if (loop_of(file) == FQ_LOOP_MATE && eff_records(f_[0]) == 0) return; /* "No reads found": file 2 is never opened */
+  if (loop_of(file) == FQ_LOOP_MATE && total0() == 0) return; /* "No reads found": file 2 is never opened */
   uint32_t nrec = (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0);
   if (s.fused) { launch_names(file, si, nrec); return; } /* only reached when a table rebuild replays the name step */
   ensure_full_index(F.bufs[s.buf]);
@@ -627,13 +629,15 @@ void FqEngine::finish(fqg_report* rep) {
         if (t0 > 0) offer(FQ_KEY(f_[0].g_base + N0, FQ_R_TRUNC), FQ_E_TRUNC, 0, 4 * (f_[0].g_base + N0), 0);
         break;
       case FQG_MODE_INDEX_PAIR:
-        if (t0 > 0) offer(FQ_KEY(N0, FQ_R_TRUNC), FQ_E_TRUNC, 0, 4 * N0, 0);
-        if (N0 > 0 && f_[1].ended) {
-          uint64_t S1 = N0 + 1;
-          if (t1 > 0) offer(FQ_KEY(S1 + N1, FQ_R_TRUNC), FQ_E_TRUNC, 1, 4 * N1, 0);
-          FqStats st; dev_->download(&st, f_[0].stats, sizeof st);
-          uint64_t left = st.n_names - ctr[1];
-          if (left > 0) offer(FQ_KEY(S1 + N1 + 1, 0), FQ_E_LEFTOVER, 0, 0, left);
+        if (t0 > 0) offer(FQ_KEY(f_[0].g_base + N0, FQ_R_TRUNC), FQ_E_TRUNC, 0, 4 * (f_[0].g_base + N0), 0);
+        if (total0() > 0 && f_[1].ended) {
+          uint64_t S1 = total0() + 1;
+          if (t1 > 0) offer(FQ_KEY(S1 + f_[1].g_base + N1, FQ_R_TRUNC), FQ_E_TRUNC, 1, 4 * (f_[1].g_base + N1), 0);
+          if (!(cfg_.flags & FQG_FLAG_EXTERNAL_INDEX)) { /* sharded runs count the leftovers at the owners */
+            FqStats st; dev_->download(&st, f_[0].stats, sizeof st);
+            uint64_t left = st.n_names - ctr[1];
+            if (left > 0) offer(FQ_KEY(S1 + N1 + 1, 0), FQ_E_LEFTOVER, 0, 0, left);
+          }
         }
         break;
       case FQG_MODE_INTERLEAVED:
@@ -664,7 +668,7 @@ void FqEngine::finish(fqg_report* rep) {
           break;
         case FQG_MODE_INDEX_PAIR:
           if (rank == FQ_R_STOP) {
-            if (step < N0 + 1) f_[0].limit = step; else f_[1].limit = step - (N0 + 1);
+            if (step < total0() + 1) f_[0].limit = step - f_[0].g_base; else f_[1].limit = step - (total0() + 1) - f_[1].g_base;
             restricted = true;
           }
           break;
@@ -746,7 +750,7 @@ void FqEngine::finish(fqg_report* rep) {
     switch (cfg_.mode) {
       case FQG_MODE_SINGLE: sniffed(0, FQ_KEY(0, FQ_R_V0 + FQ_V_PLUS)); break;
       case FQG_MODE_INDEX: sniffed(0, FQ_KEY(0, FQ_R_WRONGHDR)); break;
-      case FQG_MODE_INDEX_PAIR: sniffed(0, FQ_KEY(0, FQ_R_WRONGHDR)); sniffed(1, FQ_KEY(N0 + 1, FQ_R_WRONGHDR)); break;
+      case FQG_MODE_INDEX_PAIR: sniffed(0, FQ_KEY(0, FQ_R_WRONGHDR)); sniffed(1, FQ_KEY(total0() + 1, FQ_R_WRONGHDR)); break;
       case FQG_MODE_INTERLEAVED: sniffed(0, FQ_KEY(0, FQ_RI_WRONGHDR1)); break;
       default: sniffed(0, FQ_KEY(0, FQ_RS_V1 + FQ_V_PLUS)); sniffed(1, FQ_KEY(0, FQ_RS_V2 + FQ_V_PLUS)); break;
     }
@@ -769,7 +773,7 @@ void FqEngine::fill_error(fqg_report* rep, uint64_t key, int host_code, int host
     return;
   }
   uint64_t step = FQ_KEY_STEP(key); uint32_t rank = FQ_KEY_RANK(key);
-  uint64_t N0 = eff_records(f_[0]);
+  uint64_t N0 = cfg_.mode == FQG_MODE_INDEX_PAIR ? total0() : eff_records(f_[0]);
   int file = 0; uint64_t g = 0, L = 0; int code = 0; int vrank = -1; int msg_file = 0;
   switch (cfg_.mode) {
     case FQG_MODE_SINGLE: case FQG_MODE_INDEX: case FQG_MODE_INDEX_PAIR: {
@@ -895,31 +899,58 @@ void FqEngine::index_records(const void* host_bytes, size_t n, uint64_t* starts,
 void FqEngine::prescan_device(int file, const void* dptr, size_t n, bool at_eof, uint64_t* n_lines, int32_t* ends_lf, uint64_t first_ends[4]) {
   FqFile& F = f_[file];
   const uint8_t* p = (const uint8_t*)dptr;
-  uint64_t total = 0, off = 0; int got = 0;
   for (int i = 0; i < 4; i++) first_ends[i] = ~0ull;
-  while (n) {
-    size_t k = std::min(n, kMaxChunk);
-    FqBuffer B; B.data = (uint8_t*)p; B.n = (uint32_t)k;
-    bool last = at_eof && k == n;
-    scan_buffer(B, last);
-    if (got < 4 && B.nlines) {
-      uint32_t e[4]; uint32_t take = std::min<uint32_t>(4 - got, B.nlines);
-      dev_->download(e, B.line_end, take * sizeof(uint32_t));
-      for (uint32_t i = 0; i < take; i++) first_ends[got++] = off + e[i];
+  uint8_t lastc = 0; dev_->download(&lastc, p + n - 1, 1);
+  *ends_lf = lastc == '\n';
+  if (fused_ok_ && n >= fused_min_) {
+    /* the fused pass will build what it needs later: here only the LF count and the first line ends are wanted */
+    {
+      FqBuffer B; B.data = (uint8_t*)p; B.n = (uint32_t)std::min<size_t>(n, 1u << 20);
+      scan_buffer(B, at_eof && B.n == n);
+      uint32_t e[4]; uint32_t take = std::min<uint32_t>(4, B.nlines);
+      if (take) dev_->download(e, B.line_end, take * sizeof(uint32_t));
+      for (uint32_t i = 0; i < take; i++) first_ends[i] = e[i];
+      dev_->release(B.line_end);
+      if (take < 4 && B.n < n) goto full_scan; /* very long first lines: take the exact path */
     }
-    FqFile::Prescan ps; ps.data = p; ps.n = (uint32_t)k; ps.last = last; ps.line_end = B.line_end; ps.nlines = B.nlines;
-    F.prescans.push_back(ps);
-    total += B.nlines; p += k; n -= k; off += k;
-    if (n == 0) { uint8_t c = 0; dev_->download(&c, p - 1, 1); *ends_lf = c == '\n'; }
+    {
+      unsigned long long* d = (unsigned long long*)dev_->alloc(sizeof(unsigned long long));
+      dev_->fill(d, 0, sizeof(unsigned long long));
+      size_t left = n; const uint8_t* q = p;
+      while (left) { size_t k = std::min(left, kMaxChunk); dev_->count_lines(q, (uint32_t)k, d); q += k; left -= k; }
+      unsigned long long total = 0; dev_->download(&total, d, sizeof total);
+      dev_->release(d);
+      *n_lines = total + ((at_eof && lastc != '\n') ? 1 : 0);
+      return;
+    }
   }
-  *n_lines = total;
+full_scan:
+  {
+    uint64_t total = 0, off = 0; int got = 0;
+    for (int i = 0; i < 4; i++) first_ends[i] = ~0ull;
+    while (n) {
+      size_t k = std::min(n, kMaxChunk);
+      FqBuffer B; B.data = (uint8_t*)p; B.n = (uint32_t)k;
+      bool last = at_eof && k == n;
+      scan_buffer(B, last);
+      if (got < 4 && B.nlines) {
+        uint32_t e[4]; uint32_t take = std::min<uint32_t>(4 - got, B.nlines);
+        dev_->download(e, B.line_end, take * sizeof(uint32_t));
+        for (uint32_t i = 0; i < take; i++) first_ends[got++] = off + e[i];
+      }
+      FqFile::Prescan ps; ps.data = p; ps.n = (uint32_t)k; ps.last = last; ps.line_end = B.line_end; ps.nlines = B.nlines;
+      F.prescans.push_back(ps);
+      total += B.nlines; p += k; n -= k; off += k;
+    }
+    *n_lines = total;
+  }
 }
 
 void FqEngine::set_stream_start(int file, uint32_t skip_lines, uint64_t first_record) {
   FqFile& F = f_[file];
   if (F.started) throw std::runtime_error("fqg_set_stream_start after the first feed");
-  if (first_record && !(cfg_.mode == FQG_MODE_SINGLE || (cfg_.mode == FQG_MODE_INDEX && (cfg_.flags & FQG_FLAG_EXTERNAL_INDEX))))
-    throw std::runtime_error("fqg_set_stream_start: a record offset needs FQG_MODE_SINGLE or FQG_MODE_INDEX with FQG_FLAG_EXTERNAL_INDEX");
+  if (first_record && !(cfg_.mode == FQG_MODE_SINGLE || ((cfg_.mode == FQG_MODE_INDEX || cfg_.mode == FQG_MODE_INDEX_PAIR) && (cfg_.flags & FQG_FLAG_EXTERNAL_INDEX))))
+    throw std::runtime_error("fqg_set_stream_start: a record offset needs FQG_MODE_SINGLE, or an index mode with FQG_FLAG_EXTERNAL_INDEX");
   F.start_skip = skip_lines; F.g_base = first_record;
 }
 
@@ -1000,4 +1031,61 @@ void FqEngine::shard_result(uint64_t* key, uint64_t* record, char* name, uint32_
 void FqEngine::hist_range(int file, uint64_t lo, uint64_t hi, uint64_t* out) {
   if (hi < lo || hi >= FQ_MAX_READ_LENGTH) throw std::runtime_error("fqg_hist_range: bad range");
   dev_->download(out, f_[file].hist + lo, (hi - lo + 1) * sizeof(unsigned long long));
+}
+
+void FqEngine::set_file_total(int file, uint64_t total) {
+  if (file != 0) throw std::runtime_error("fqg_set_file_total: only file 0 has a total that other loops depend on");
+  total0_set_ = true; total0_ = total;
+}
+void FqEngine::set_sniff(int file, int fmt, int color) { f_[file].sniff_fmt = fmt; f_[file].sniff_color = color; }
+void FqEngine::sniff_device(int file, const void* dptr, size_t n, uint32_t skip, int32_t* fmt, int32_t* color) {
+  FqFile& F = f_[file];
+  int sf = F.sniff_fmt, sc = F.sniff_color;
+  F.sniff_fmt = -1; F.sniff_color = -1;
+  presniff(file, (const uint8_t*)dptr, (uint32_t)std::min<size_t>(n, kMaxChunk), skip, false);
+  *fmt = F.sniff_fmt; *color = F.sniff_color;
+  F.sniff_fmt = sf; F.sniff_color = sc;
+}
+
+void FqEngine::shard_claim(const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start, uint64_t sb) {
+  if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_claim: n_src out of range");
+  dev_->sync();
+  dev_->fill(counters_ + 3, 0xFF, sizeof(unsigned long long));
+  dev_->fill(counters_ + 1, 0, sizeof(unsigned long long));
+  claim_meta_ = (const FqPackedName*)meta; claim_n_ = n; claim_blob_ = (const uint8_t*)blob; claim_nsrc_ = n_src;
+  for (uint32_t i = 0; i <= n_src; i++) claim_meta_start_[i] = meta_start[i];
+  for (uint32_t i = 0; i < n_src; i++) claim_blob_start_[i] = blob_start[i];
+  if (!n) return;
+  ensure_table(table_names_);
+  FqShardArgs a; memset(&a, 0, sizeof a);
+  a.meta = claim_meta_; a.n = n; a.blob = claim_blob_; a.n_src = n_src;
+  memcpy(a.meta_start, claim_meta_start_, sizeof(unsigned long long) * (n_src + 1));
+  memcpy(a.blob_start, claim_blob_start_, sizeof(unsigned long long) * n_src);
+  a.slots = slots_; a.mask = table_cap_ - 1; a.dup_key = counters_ + 3; a.counters = counters_;
+  /* the names the slots point at: the tuples inserted before */
+  FqShardArgs ins; memset(&ins, 0, sizeof ins);
+  ins.meta = shard_meta_; ins.n = shard_n_; ins.blob = shard_blob_; ins.n_src = shard_nsrc_;
+  memcpy(ins.meta_start, shard_meta_start_, sizeof(unsigned long long) * (shard_nsrc_ + 1));
+  memcpy(ins.blob_start, shard_blob_start_, sizeof(unsigned long long) * shard_nsrc_);
+  claim_sb_ = sb;
+  dev_->shard_claim(a, ins, sb);
+}
+
+void FqEngine::shard_claim_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* claimed, uint64_t* collisions) {
+  dev_->sync();
+  unsigned long long ctr[4]; dev_->download(ctr, counters_, sizeof ctr);
+  *collisions = ctr[0]; *claimed = ctr[1]; *key = ctr[3]; *record = 0; *name_len = 0; name[0] = 0;
+  if (ctr[3] == FQ_KEY_NONE || !claim_n_) return;
+  *record = FQ_KEY_STEP(ctr[3]) - claim_sb_; /* index of the unpaired record inside file 2 */
+  unsigned long long* d = (unsigned long long*)dev_->alloc(sizeof(unsigned long long));
+  dev_->fill(d, 0xFF, sizeof(unsigned long long));
+  dev_->shard_find(claim_meta_, claim_n_, *record, d);
+  unsigned long long pos; dev_->download(&pos, d, sizeof pos);
+  dev_->release(d);
+  if (pos == ~0ull) return;
+  FqPackedName pn; dev_->download(&pn, claim_meta_ + pos, sizeof pn);
+  uint32_t src = 0; while (src + 1 < claim_nsrc_ && pos >= claim_meta_start_[src + 1]) src++;
+  uint32_t len = std::min<uint32_t>(pn.len, 1023);
+  if (len) dev_->download(name, claim_blob_ + claim_blob_start_[src] + pn.off, len);
+  name[len] = 0; *name_len = len;
 }

@@ -74,6 +74,11 @@ class FqEngine {
   void shard_insert(const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start);
   void shard_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* collisions);
   void hist_range(int file, uint64_t lo, uint64_t hi, uint64_t* out);
+  void set_file_total(int file, uint64_t total);
+  void set_sniff(int file, int fmt, int color);
+  void sniff_device(int file, const void* dptr, size_t n, uint32_t skip, int32_t* fmt, int32_t* color);
+  void shard_claim(const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start, uint64_t step_base);
+  void shard_claim_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* claimed, uint64_t* collisions);
   FqDevice* device() { return dev_; }
   std::string last_error;
 
@@ -91,6 +96,10 @@ class FqEngine {
   uint32_t shard_nsrc_ = 0; uint64_t shard_meta_start_[FQ_SHARD_MAX_SRC + 1], shard_blob_start_[FQ_SHARD_MAX_SRC];
   void scan_buffer(FqBuffer& B, bool last);
   bool finished_ = false;
+  bool total0_set_ = false; uint64_t total0_ = 0; /* multi-GPU: records of file 1 over all ranks */
+  uint64_t total0() const;
+  const FqPackedName* claim_meta_ = nullptr; uint64_t claim_n_ = 0; const uint8_t* claim_blob_ = nullptr;
+  uint64_t claim_sb_ = 0; uint32_t claim_nsrc_ = 0; uint64_t claim_meta_start_[FQ_SHARD_MAX_SRC + 1], claim_blob_start_[FQ_SHARD_MAX_SRC];
   bool fused_ok_ = true;     /* cleared for the rest of the job once a chunk needed the two-pass path */
   uint32_t* tile_out_ = nullptr;
   uint32_t fused_min_ = 1u << 20; /* chunks smaller than this always take the two-pass path */
@@ -101,7 +110,7 @@ class FqEngine {
   FqRecCtx make_ctx(int file) const;
   void add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned, bool allow_fused = true);
   bool try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap);
-  bool presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip);
+  bool presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip, bool short_only = true);
   void fused_fallback();
   void segmentize(int file, int b, uint32_t pos, uint32_t j, bool last);
   void flush_pending_as_last(int file);

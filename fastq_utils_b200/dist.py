@@ -1,19 +1,21 @@
 """Multi-GPU fastq_info: one process per GPU, torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests) for
 the plumbing, libfastq_gpu for every byte of work.
 
-Each rank holds a contiguous byte range of the (single) input file.
+Each rank holds a contiguous byte range of every input file.
 
-  1. every rank builds the line index of its range (`fqg_prescan_device`); an all-gather of (line feeds, ends-with-LF,
+  1. every rank counts the line feeds of its range (`fqg_prescan_device`); an all-gather of (line feeds, ends-with-LF,
      first line ends) fixes each range's line phase; the bytes before a range's first record start are sent to the
-     previous rank, which appends them to its stream (the library's chunk-bridging joins them with its tail);
+     previous rank, which appends them to its stream (the library's chunk-bridging joins them with its tail).  The rank
+     that holds a file's first record sniffs the read-name format / colour space and everyone adopts it;
   2. validation runs locally with global record indices (`fqg_set_stream_start`);
-  3. default mode: read names are routed by hash to their owner rank with two all-to-alls (24-byte tuples + name bytes);
-     the owner inserts them into its shard of the index with exact byte compares (`fqg_shard_insert`);
-  4. the earliest event (smallest key in the reference's sequential order) wins; statistics are all-reduced and the
-     merged report is rendered with `fqg_render`, so the text and exit status equal the reference's.
+  3. index modes: read names are routed by hash to their owner rank with two all-to-alls (24-byte tuples + name bytes);
+     the owner inserts file 1's names into its shard of the index (`fqg_shard_insert`, duplicates) and lets file 2's
+     names claim them (`fqg_shard_claim`, unpaired reads), always confirming equal hashes on the bytes;
+  4. the earliest event (smallest key in the reference's sequential order) wins; statistics are reduced and the merged
+     report is rendered with `fqg_render`, so the text and exit status equal the reference's.
 
-Supported modes: MODE_SINGLE (-r) and MODE_INDEX (default, one file).  A clean early end of file caused by a NUL-led
-header line (src/fastq.c:248) is reported as unsupported in the sharded path (the single-GPU path handles it).
+Supported: MODE_SINGLE (-r), MODE_INDEX (default, one file), MODE_INDEX_PAIR (default, two files).  A clean early end of
+file caused by a NUL-led header line (src/fastq.c:248) is reported as unsupported here (the single-GPU path handles it).
 """
 import ctypes
 
@@ -24,25 +26,21 @@ from . import api
 
 KEY_NONE = (1 << 64) - 1
 R_STOP, R_NAME = 0, 3
-E_DUP = 13
+E_DUP, E_UNPAIRED, E_LEFTOVER = 13, 14, 15
 MAX_READ_LENGTH = 2_500_000
-
-
-def _key(step, rank):
-    return (step << 6) | rank
 
 
 class ShardedFastqInfo:
     def __init__(self, mode, device=0, n_hint=0, tensor_device=None):
-        if mode not in (api.MODE_SINGLE, api.MODE_INDEX):
-            raise NotImplementedError("sharded runs support MODE_SINGLE and MODE_INDEX")
+        if mode not in (api.MODE_SINGLE, api.MODE_INDEX, api.MODE_INDEX_PAIR):
+            raise NotImplementedError("sharded runs support MODE_SINGLE, MODE_INDEX and MODE_INDEX_PAIR")
         self.mode = mode
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.tdev = tensor_device if tensor_device is not None else torch.device("cuda", device)
-        flags = api.FLAG_EXTERNAL_INDEX if mode == api.MODE_INDEX else 0
-        self.ctx = api.FastqInfo(mode, device=device, flags=flags)
-        self.shard = api.FastqInfo(api.MODE_INDEX, device=device, index_capacity_hint=n_hint) if mode == api.MODE_INDEX else None
+        indexed = mode != api.MODE_SINGLE
+        self.ctx = api.FastqInfo(mode, device=device, flags=api.FLAG_EXTERNAL_INDEX if indexed else 0)
+        self.shard = api.FastqInfo(api.MODE_INDEX, device=device, index_capacity_hint=n_hint) if indexed else None
         self._keep = []
 
     # ------------------------------------------------------------------ helpers
@@ -53,6 +51,10 @@ class ShardedFastqInfo:
         dist.all_gather_object(out, obj)
         return out
 
+    def _sync(self):
+        if self.tdev.type == "cuda":
+            torch.cuda.synchronize()
+
     def _a2a(self, send, in_splits, out_splits):
         recv = torch.empty(sum(out_splits) + 64, dtype=torch.uint8, device=self.tdev)
         if self.world == 1:
@@ -61,23 +63,18 @@ class ShardedFastqInfo:
             dist.all_to_all_single(recv[:sum(out_splits)], send[:sum(in_splits)], output_split_sizes=out_splits, input_split_sizes=in_splits)
         return recv
 
-    # ------------------------------------------------------------------ one job
-    def run_device(self, ptr, nbytes, name="-", empty_ok=False, no_enc_ok=False):
-        """ptr/nbytes: this rank's byte range in device memory (64 readable bytes must follow).  Returns a dict with the
-        merged report fields and, on rank 0, the rendered (rc, stdout, stderr)."""
-        W, r = self.world, self.rank
-        self.ctx.reset()
-        if self.shard:
-            self.shard.reset()
-        self._keep = []
+    def _feed_file(self, f, ptr, nbytes):
+        """Steps 1-2 for one file: line phase, head exchange, sniff, feed.  Returns (records expected on this rank or None
+        when the file was gathered on rank 0, records of the file over all ranks)."""
+        W, r, ctx = self.world, self.rank, self.ctx
         last_rank = r == W - 1
-        # -- 1. line phase
         if nbytes > 0:
-            nlines, ends_lf, first = self.ctx.prescan_device(0, ptr, nbytes, at_eof=last_rank)
+            nlines, ends_lf, first = ctx.prescan_device(f, ptr, nbytes, at_eof=last_rank)
         else:
             nlines, ends_lf, first = 0, True, [KEY_NONE] * 4
-        lfs = nlines - (1 if (last_rank and nbytes > 0 and not ends_lf) else 0)
-        info = self._gather((lfs, ends_lf, first, nbytes))
+        virt = 1 if (last_rank and nbytes > 0 and not ends_lf) else 0
+        lfs = nlines - virt
+        info = self._gather((lfs, ends_lf, first, nbytes, virt))
         G = [0] * (W + 1)
         for i in range(W):
             G[i + 1] = G[i] + info[i][0]
@@ -85,17 +82,15 @@ class ShardedFastqInfo:
         degenerate = False
         for i in range(W):
             prev_lf = True if i == 0 else info[i - 1][1]
-            if i == 0 or (prev_lf and G[i] % 4 == 0):
-                skip[i] = 0
-            else:
-                skip[i] = (4 - G[i] % 4) % 4 or 4
+            skip[i] = 0 if (i == 0 or (prev_lf and G[i] % 4 == 0)) else ((4 - G[i] % 4) % 4 or 4)
             if i > 0 and (info[i][0] < skip[i] or info[i][3] == 0):
                 degenerate = True  # a range without a record start of its own (tiny inputs)
                 break
             firstrec[i] = (G[i] + skip[i]) // 4
             cut[i] = info[i][2][skip[i] - 1] if skip[i] > 0 else 0
-        head = None
-        if degenerate:
+        total_lines = G[W] + info[W - 1][4]
+        total_records = total_lines // 4
+        if degenerate or info[0][3] == 0:
             # tiny input: everything goes to rank 0, the other ranks hold an empty stream (the collectives below still run)
             sizes = [info[i][3] for i in range(W)]
             if r == 0:
@@ -108,137 +103,182 @@ class ShardedFastqInfo:
                         dist.recv(whole[off:off + sizes[s]], s)
                     off += sizes[s]
                 self._keep.append(whole)
-                self.ctx.set_stream_start(0, 0, 0)
+                ctx.set_stream_start(f, 0, 0)
                 if off:
-                    self.ctx.feed_device(0, whole.data_ptr(), off, last=True)
+                    ctx.feed_device(f, whole.data_ptr(), off, last=True)
                 else:
-                    self.ctx.feed(0, b"", last=True)
+                    ctx.feed(f, b"", last=True)
             else:
                 if nbytes:
                     dist.send(_as_tensor(ptr, nbytes, self.tdev), 0)
-                self.ctx.set_stream_start(0, 0, G[W] // 4)
-                self.ctx.feed(0, b"", last=True)
-            lfs_local = None
+                ctx.set_stream_start(f, 0, total_records)
+                ctx.feed(f, b"", last=True)
+            return None, total_records
+        # the read-name format and colour space come from the file's first record, which rank 0 holds
+        sn = ctx.sniff_device(f, ptr, nbytes, 0) if r == 0 else None
+        sn = self._gather(sn)[0]
+        if sn[0] >= 0:
+            ctx.set_sniff(f, sn[0], sn[1])
+        # head of range r+1 travels to rank r
+        head, reqs = None, []
+        if W > 1:
+            if r > 0 and cut[r] > 0:
+                view = _as_tensor(ptr, cut[r], self.tdev)
+                reqs.append(dist.isend(view, r - 1))
+                self._keep.append(view)
+            if r < W - 1 and cut[r + 1] > 0:
+                head = torch.zeros(cut[r + 1] + 64, dtype=torch.uint8, device=self.tdev)
+                reqs.append(dist.irecv(head[:cut[r + 1]], r + 1))
+            for q in reqs:
+                q.wait()
+        ctx.set_stream_start(f, skip[r], firstrec[r])
+        if last_rank:
+            ctx.feed_device(f, ptr, nbytes, last=True)
         else:
-            # -- head of range r+1 travels to rank r
-            reqs = []
-            if W > 1:
-                if r > 0 and cut[r] > 0:
-                    view = _as_tensor(ptr, cut[r], self.tdev)
-                    reqs.append(dist.isend(view, r - 1))
-                    self._keep.append(view)
-                if r < W - 1 and cut[r + 1] > 0:
-                    head = torch.zeros(cut[r + 1] + 64, dtype=torch.uint8, device=self.tdev)
-                    reqs.append(dist.irecv(head[:cut[r + 1]], r + 1))
-                for q in reqs:
-                    q.wait()
-            # -- 2. local validation with global indices
-            self.ctx.set_stream_start(0, skip[r], firstrec[r])
-            if last_rank:
-                self.ctx.feed_device(0, ptr, nbytes, last=True) if nbytes else self.ctx.feed(0, b"", last=True)
+            ctx.feed_device(f, ptr, nbytes, last=False)
+            if head is not None:
+                ctx.feed_device(f, head.data_ptr(), cut[r + 1], last=True)
+                self._keep.append(head)
             else:
-                if nbytes:
-                    self.ctx.feed_device(0, ptr, nbytes, last=False)
-                if head is not None:
-                    self.ctx.feed_device(0, head.data_ptr(), cut[r + 1], last=True)
-                    self._keep.append(head)
-                else:
-                    self.ctx.feed(0, b"", last=True)
-            lfs_local = lfs
-        rep = self.ctx.finish()
+                ctx.feed(f, b"", last=True)
+        expected = (lfs + virt - skip[r] + (skip[r + 1] if r < W - 1 else 0)) // 4
+        return expected, total_records
+
+    def _route_names(self, f):
+        """Step 3, sender side: pack the names of file f by owner and exchange them.  Returns what the owner needs."""
+        W, r = self.world, self.rank
+        counts, nb = self.ctx.names_count(f, W)
+        theirs = self._gather((counts, nb))
+        in_meta, in_blob = [c * 24 for c in counts], list(nb)
+        out_cnt = [theirs[s][0][r] for s in range(W)]
+        out_meta, out_blob = [c * 24 for c in out_cnt], [theirs[s][1][r] for s in range(W)]
+        meta_base, blob_base = [0] * W, [0] * W
+        for o in range(1, W):
+            meta_base[o] = meta_base[o - 1] + counts[o - 1]
+            blob_base[o] = blob_base[o - 1] + nb[o - 1]
+        send_meta = torch.empty(sum(in_meta) + 64, dtype=torch.uint8, device=self.tdev)
+        send_blob = torch.empty(sum(in_blob) + 64, dtype=torch.uint8, device=self.tdev)
+        self.ctx.names_pack(f, W, send_meta.data_ptr(), send_blob.data_ptr(), meta_base, blob_base)
+        self._sync()
+        recv_meta = self._a2a(send_meta, in_meta, out_meta)
+        recv_blob = self._a2a(send_blob, in_blob, out_blob)
+        self._sync()
+        ms, bs, acc = [0], [], 0
+        for s in range(W):
+            ms.append(ms[-1] + out_cnt[s])
+            bs.append(acc)
+            acc += out_blob[s]
+        self._keep += [recv_meta, recv_blob]
+        return recv_meta, recv_blob, ms, bs
+
+    # ------------------------------------------------------------------ one job
+    def run_device(self, ptr, nbytes, name="-", ptr2=None, nbytes2=0, name2=None, empty_ok=False, no_enc_ok=False):
+        """ptr/nbytes (and ptr2/nbytes2 for MODE_INDEX_PAIR): this rank's byte range of each file in device memory (16-byte
+        aligned, 64 readable bytes after it).  Returns the merged report and, on rank 0, the rendered (rc, stdout, stderr)."""
+        W, r, ctx = self.world, self.rank, self.ctx
+        ctx.reset()
+        if self.shard:
+            self.shard.reset()
+        self._keep = []
+        pair = self.mode == api.MODE_INDEX_PAIR
+        exp0, T0 = self._feed_file(0, ptr, nbytes)
+        exp1, T1 = None, 0
+        if pair:
+            ctx.set_file_total(0, T0)
+            if T0 > 0:
+                exp1, T1 = self._feed_file(1, ptr2, nbytes2)
+        rep = ctx.finish()
         local_key = rep.error.event_key if rep.error.code != 0 else KEY_NONE
-        expected = 0 if lfs_local is None else (lfs + (1 if (last_rank and nbytes > 0 and not ends_lf) else 0) - skip[r] + (skip[r + 1] if r < W - 1 else 0)) // 4
-        if rep.file[0].n_records < expected and rep.error.code == 0:
-            raise NotImplementedError("NUL-led header line (early clean EOF) in a sharded run")
-        if rep.error.code != 0 and (local_key & 63) == R_STOP:
+        stopped = (exp0 is not None and rep.file[0].n_records < exp0) or (exp1 is not None and rep.file[1].n_records < exp1)
+        if rep.error.code == 0 and stopped:
             raise NotImplementedError("NUL-led header line (early clean EOF) in a sharded run")
         # -- 3. names to their owners
-        dup = (KEY_NONE, 0, b"")
+        dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0
         if self.shard is not None:
-            counts, nbytes_names = self.ctx.names_count(0, W)
-            theirs = self._gather((counts, nbytes_names))
-            in_meta = [c * 24 for c in counts]
-            in_blob = list(nbytes_names)
-            out_cnt = [theirs[s][0][r] for s in range(W)]
-            out_meta = [c * 24 for c in out_cnt]
-            out_blob = [theirs[s][1][r] for s in range(W)]
-            meta_base, blob_base = [0] * W, [0] * W
-            for o in range(1, W):
-                meta_base[o] = meta_base[o - 1] + counts[o - 1]
-                blob_base[o] = blob_base[o - 1] + nbytes_names[o - 1]
-            send_meta = torch.empty(sum(in_meta) + 64, dtype=torch.uint8, device=self.tdev)
-            send_blob = torch.empty(sum(in_blob) + 64, dtype=torch.uint8, device=self.tdev)
-            self.ctx.names_pack(0, W, send_meta.data_ptr(), send_blob.data_ptr(), meta_base, blob_base)
-            if self.tdev.type == "cuda":
-                torch.cuda.synchronize()
-            recv_meta = self._a2a(send_meta, in_meta, out_meta)
-            recv_blob = self._a2a(send_blob, in_blob, out_blob)
-            if self.tdev.type == "cuda":
-                torch.cuda.synchronize()
-            ms, bs = [0], []
-            acc = 0
-            for s in range(W):
-                ms.append(ms[-1] + out_cnt[s])
-                bs.append(acc)
-                acc += out_blob[s]
-            self.shard.shard_insert(recv_meta.data_ptr(), ms[-1], recv_blob.data_ptr(), ms, bs)
+            meta, blob, ms, bs = self._route_names(0)
+            self.shard.shard_insert(meta.data_ptr(), ms[-1], blob.data_ptr(), ms, bs)
             dkey, drec, dname, coll = self.shard.shard_result()
+            dup = (dkey, drec, dname)
+            if pair and T0 > 0:
+                meta2, blob2, ms2, bs2 = self._route_names(1)
+                self.shard.shard_claim(meta2.data_ptr(), ms2[-1], blob2.data_ptr(), ms2, bs2, T0 + 1)
+                ukey, urec, uname, claimed, coll2 = self.shard.shard_claim_result()
+                unp = (ukey, urec, uname)
+                coll += coll2
             if sum(self._gather(coll)):
                 raise NotImplementedError("64-bit name hash collision between different names in a sharded run: rerun with another seed")
-            dup = (dkey, drec, dname)
-            self._keep += [send_meta, send_blob, recv_meta, recv_blob]
         # -- 4. merge
-        f0 = rep.file[0]
-        mine = {"key": local_key, "dup": dup, "err": bytes(ctypes.string_at(ctypes.addressof(rep.error), ctypes.sizeof(api.Error))) if local_key != KEY_NONE else None,
-                "nrec": int(f0.n_records), "num_rds": int(f0.num_rds), "min_rl": int(f0.min_rl), "max_rl": int(f0.max_rl),
-                "min_q": int(f0.min_qual), "max_q": int(f0.max_qual), "names": int(rep.n_index_entries), "mem": int(rep.index_mem) - 8,
-                "sniff": (int(f0.sniff_format), int(f0.color_space)), "rbe": int(rep.reads_before_error[0])}
+        f0, f1 = rep.file[0], rep.file[1]
+        mine = {"key": local_key, "dup": dup, "unp": unp, "claimed": claimed,
+                "err": bytes(ctypes.string_at(ctypes.addressof(rep.error), ctypes.sizeof(api.Error))) if local_key != KEY_NONE else None,
+                "nrec": (int(f0.n_records), int(f1.n_records)), "num_rds": int(f0.num_rds), "min_rl": int(f0.min_rl), "max_rl": int(f0.max_rl),
+                "rl1": (int(f1.min_rl), int(f1.max_rl)), "min_q": int(f0.min_qual), "max_q": int(f0.max_qual), "names": int(rep.n_index_entries),
+                "mem": int(rep.index_mem) - 8, "sniff": ((int(f0.sniff_format), int(f0.color_space)), (int(f1.sniff_format), int(f1.color_space)))}
         allr = self._gather(mine)
-        best = min(min(a["key"], a["dup"][0]) for a in allr)
+        N0, N1 = sum(a["nrec"][0] for a in allr), sum(a["nrec"][1] for a in allr)
+        names_total = sum(a["names"] for a in allr)
+        left = names_total - sum(a["claimed"] for a in allr)
+        cands = [(a["key"], "local", a) for a in allr] + [(a["dup"][0], "dup", a) for a in allr] + [(a["unp"][0], "unp", a) for a in allr]
+        if pair and T0 > 0 and left > 0:
+            cands.append((((T0 + 1 + N1 + 1) << 6), "left", None))
+        best, kind, holder = min(cands, key=lambda c: c[0])
         merged = api.Report()
         merged.mode = self.mode
         m0 = merged.file[0]
-        m0.n_records = sum(a["nrec"] for a in allr)
+        m0.n_records, merged.file[1].n_records = N0, N1
         m0.num_rds = sum(a["num_rds"] for a in allr)
         m0.min_rl = min(a["min_rl"] for a in allr)
         m0.max_rl = max(a["max_rl"] for a in allr)
         m0.min_qual = min(a["min_q"] for a in allr)
         m0.max_qual = max(a["max_q"] for a in allr)
-        m0.sniff_format, m0.color_space = next((a["sniff"] for a in allr if a["nrec"] > 0), allr[0]["sniff"])  # the rank holding record 0
-        merged.file[1].sniff_format = merged.file[1].color_space = -1
-        merged.n_index_entries = sum(a["names"] for a in allr)
-        merged.n_index_left = merged.n_index_entries
+        for f in (0, 1):  # sniff lines: decided by the rank that holds the file's first record
+            fmt, col = next((a["sniff"][f] for a in allr if a["nrec"][f] > 0), allr[0]["sniff"][f])
+            merged.file[f].sniff_format, merged.file[f].color_space = fmt, col
+        merged.n_index_entries = names_total
+        merged.n_index_left = left
         merged.index_mem = 8 + sum(a["mem"] for a in allr)
-        merged.reads_before_error[0] = m0.n_records
+        merged.reads_before_error[0], merged.reads_before_error[1] = N0, N1
         if best != KEY_NONE:
-            holder = next(a for a in allr if min(a["key"], a["dup"][0]) == best)
-            if holder["key"] == best:
-                ctypes.memmove(ctypes.addressof(merged.error), holder["err"], ctypes.sizeof(api.Error))
-            else:
-                e = merged.error
+            step = best >> 6
+            e = merged.error
+            if kind == "local":
+                ctypes.memmove(ctypes.addressof(e), holder["err"], ctypes.sizeof(api.Error))
+            elif kind == "dup":
                 e.code, e.file, e.msg_file, e.record = E_DUP, 0, 0, holder["dup"][1]
                 e.line = 4 * (holder["dup"][1] + 1)
-                e.event_key = best
-                nm = holder["dup"][2][:1023]
-                e.name = nm
-                e.name_len = len(nm)
-            merged.reads_before_error[0] = best >> 6
-        # median over the merged histogram (src/fastq_info.c:39-55)
+                e.name = holder["dup"][2][:1023]
+                e.name_len = len(holder["dup"][2][:1023])
+            elif kind == "unp":
+                e.code, e.file, e.msg_file, e.record = E_UNPAIRED, 1, 1, holder["unp"][1]
+                e.line = 4 * (holder["unp"][1] + 1)
+                e.name = holder["unp"][2][:1023]
+                e.name_len = len(holder["unp"][2][:1023])
+            else:
+                e.code, e.file, e.msg_file, e.a = E_LEFTOVER, 0, 0, left
+            e.event_key = best
+            if pair and step >= T0 + 1:
+                merged.reads_before_error[0], merged.reads_before_error[1] = T0, min(step - (T0 + 1), N1)
+            else:
+                merged.reads_before_error[0], merged.reads_before_error[1] = step, 0
+        # median over the merged histogram (src/fastq_info.c:39-55); the mate loop counts into file 1's histogram too
         lo, hi = int(m0.min_rl), int(m0.max_rl)
+        for a in allr:
+            if a["rl1"][1] > 0:
+                lo, hi = min(lo, a["rl1"][0]), max(hi, a["rl1"][1])
         med = MAX_READ_LENGTH
-        if m0.num_rds == 1:
-            med = lo
-        elif m0.num_rds > 1 and hi >= lo and hi < MAX_READ_LENGTH:
+        if m0.num_rds == 1 and not (pair and T0 > 0):
+            med = int(m0.min_rl)
+        elif m0.num_rds > 1 and lo <= hi < MAX_READ_LENGTH:
             h = torch.tensor(self.ctx.hist_range(0, lo, hi), dtype=torch.int64, device=self.tdev)
             if W > 1:
                 dist.all_reduce(h)
             c = torch.cumsum(h, 0)
-            idx = int(torch.nonzero(c > m0.num_rds // 2)[0]) if bool((c > m0.num_rds // 2).any()) else None
-            med = lo + idx if idx is not None else MAX_READ_LENGTH
+            over = c > m0.num_rds // 2
+            med = lo + int(torch.nonzero(over)[0]) if bool(over.any()) else MAX_READ_LENGTH
         merged.median_rl = med
-        out = {"report": merged, "event_key": best, "n_records": int(m0.n_records), "n_index_entries": int(merged.n_index_entries)}
+        out = {"report": merged, "event_key": best, "n_records": N0, "n_records2": N1, "n_index_entries": names_total, "n_index_left": left}
         if r == 0:
-            out["transcript"] = self.ctx.render(merged, name, None, empty_ok=empty_ok, no_enc_ok=no_enc_ok)
+            out["transcript"] = self.ctx.render(merged, name, name2 if pair else None, empty_ok=empty_ok, no_enc_ok=no_enc_ok)
         return out
 
 

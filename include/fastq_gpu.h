@@ -152,6 +152,19 @@ int fqg_shard_insert(fqg_ctx* ctx, const void* device_meta, uint64_t n, const vo
                      const uint64_t* meta_start, const uint64_t* blob_start);
 /* earliest duplicate this shard saw: event key (~0 = none), the later record's index and the name */
 int fqg_shard_result(fqg_ctx* ctx, uint64_t* event_key, uint64_t* record, char name[1024], uint32_t* name_len, uint64_t* hash_collisions);
+/* mate loop at the owner: tuples of file 2 claim the names inserted by fqg_shard_insert (lookup-then-delete of
+ * src/fastq_info.c:333-350); step_base = records of file 1 + 1.  Result: earliest "unpaired read" event, the record's index
+ * inside file 2, its name, and how many index entries were claimed (the rest are the "found N unpaired reads"). */
+int fqg_shard_claim(fqg_ctx* ctx, const void* device_meta, uint64_t n, const void* device_blob, uint32_t n_src,
+                    const uint64_t* meta_start, const uint64_t* blob_start, uint64_t step_base);
+int fqg_shard_claim_result(fqg_ctx* ctx, uint64_t* event_key, uint64_t* record, char name[1024], uint32_t* name_len,
+                           uint64_t* claimed, uint64_t* hash_collisions);
+/* sharded runs: the read-name format / colour space of a file come from ITS first record (src/fastq.c:459-485), which only
+ * one rank holds: that rank sniffs (fqg_sniff_device), everyone sets the result before feeding */
+int fqg_sniff_device(fqg_ctx* ctx, int file, const void* device_bytes, size_t n, uint32_t skip_lines, int32_t* sniff_format, int32_t* color_space);
+int fqg_set_sniff(fqg_ctx* ctx, int file, int32_t sniff_format, int32_t color_space);
+/* records of file 0 over all ranks: the mate loop's steps and line numbers continue after them */
+int fqg_set_file_total(fqg_ctx* ctx, int file, uint64_t total_records);
 /* bins [lo, hi] of a file's read-length histogram (terminator included, like the reference's rdlen_ctr) */
 int fqg_hist_range(fqg_ctx* ctx, int file, uint64_t lo, uint64_t hi, uint64_t* out);
 

@@ -47,6 +47,35 @@ def main():
                 want = oracle_run(argv, bytes(w[:nb].cpu().numpy()), None)
                 results.append({"variant": variant, "argv": argv, "ok": tuple(res["transcript"]) == want, "got": res["transcript"][2][-200:], "want": want[2][-200:]})
             dist.barrier()
+    # default two-file mode: index loop over file 1, mate loop over file 2 (mates permuted inside windows of 1024)
+    n2 = 81_920
+    f1 = torch.zeros(n2 * rb + 64, dtype=torch.uint8, device="cuda")
+    f2 = torch.zeros(n2 * rb + 64, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    fq.synth_illumina(f1, 0, n2, seed=43, mate=1, stream=st)
+    fq.synth_illumina(f2, 0, n2, seed=43, mate=2, perm_window=1024, stream=st)
+    torch.cuda.synchronize()
+    for variant in ("clean", "missing_mate", "extra_in_1"):
+        a, b = f1[:n2 * rb].clone(), f2[:n2 * rb].clone()
+        if variant == "missing_mate":
+            b = torch.cat([b[:777 * rb], b[778 * rb:]])
+        if variant == "extra_in_1":
+            b = b[:(n2 - 2048) * rb]
+        parts = []
+        for t in (a, b):
+            nb = t.numel()
+            cuts = [0] + [int(nb * (i + 1) / W) + 53 * (i + 1) for i in range(W - 1)] + [nb]
+            mine = torch.zeros(cuts[r + 1] - cuts[r] + 64, dtype=torch.uint8, device="cuda")
+            mine[:cuts[r + 1] - cuts[r]] = t[cuts[r]:cuts[r + 1]]
+            parts.append((mine, cuts[r + 1] - cuts[r]))
+        torch.cuda.synchronize()
+        run = fqdist.ShardedFastqInfo(fq.MODE_INDEX_PAIR, device=local, n_hint=n2 // W)
+        res = run.run_device(parts[0][0].data_ptr(), parts[0][1], name="a.fq", ptr2=parts[1][0].data_ptr(), nbytes2=parts[1][1], name2="b.fq")
+        if r == 0:
+            from _util import oracle_run
+            want = oracle_run(["a.fq", "b.fq"], bytes(a.cpu().numpy()), bytes(b.cpu().numpy()))
+            results.append({"variant": "pair_" + variant, "argv": ["a.fq", "b.fq"], "ok": tuple(res["transcript"]) == want, "got": res["transcript"][2][-200:], "want": want[2][-200:]})
+        dist.barrier()
     if r == 0:
         json.dump(results, open(sys.argv[1], "w"))
     dist.destroy_process_group()

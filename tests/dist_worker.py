@@ -30,10 +30,19 @@ def main():
         lo, hi = cuts[r], cuts[r + 1]
         mine = bytearray(data[lo:hi]) + bytearray(64)
         buf = (ctypes.c_uint8 * len(mine)).from_buffer(mine)
-        mode = fq.MODE_SINGLE if c["mode"] == "single" else fq.MODE_INDEX
+        mode = {"single": fq.MODE_SINGLE, "index": fq.MODE_INDEX, "pair": fq.MODE_INDEX_PAIR}[c["mode"]]
+        kw = {}
+        if mode == fq.MODE_INDEX_PAIR:
+            data2 = bytes.fromhex(c["hex2"])
+            cuts2 = [0] + sorted(int(len(data2) * x) for x in c["cuts2"])[:W - 1] + [len(data2)]
+            while len(cuts2) < W + 1:
+                cuts2.insert(-1, cuts2[-1])
+            mine2 = bytearray(data2[cuts2[r]:cuts2[r + 1]]) + bytearray(64)
+            buf2 = (ctypes.c_uint8 * len(mine2)).from_buffer(mine2)
+            kw = {"ptr2": ctypes.addressof(buf2), "nbytes2": cuts2[r + 1] - cuts2[r], "name2": "b.fq"}
         try:
             run = fqdist.ShardedFastqInfo(mode, device=0, tensor_device=torch.device("cpu"))
-            res = run.run_device(ctypes.addressof(buf), hi - lo, name="a.fq")
+            res = run.run_device(ctypes.addressof(buf), hi - lo, name="a.fq", **kw)
             tr = res.get("transcript")
         except (NotImplementedError, RuntimeError) as ex:
             tr = ["EXC", type(ex).__name__, str(ex)]

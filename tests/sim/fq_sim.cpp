@@ -37,6 +37,10 @@ class FqSimDevice : public FqDevice {
     if (virtual_end && n > 0 && data[n - 1] != '\n') { if (k < cap) line_end[k] = n; k++; }
     out2[0] = k; out2[1] = k > cap;
   }
+  void count_lines(const uint8_t* data, uint32_t n, unsigned long long* out) override {
+    n_launch_++;
+    for (uint32_t i = 0; i < n; i++) *out += data[i] == '\n';
+  }
   void find_overlong(const uint32_t* line_end, uint32_t q, uint32_t j0, uint32_t nlines, uint32_t n, int tail_from_n, uint32_t* out) override {
     n_launch_++;
     for (uint32_t i = 0; i <= nlines; i++) {
@@ -171,7 +175,7 @@ class FqSimDevice : public FqDevice {
     for (uint32_t k = 0; k < nrec; k++) {
       if (names[k].hash == FQ_HASH_SKIP) continue;
       uint32_t o = fq_owner_of(names[k].hash, world);
-      out[2 * o]++; out[2 * o + 1] += names[k].len;
+      out[2 * o]++; out[2 * o + 1] += (names[k].len + 3u) & ~3u;
     }
   }
   void names_pack(const FqName* names, const uint8_t* data, uint32_t nrec, uint64_t g0, uint32_t world, FqPackedName* meta, uint8_t* blob,
@@ -181,7 +185,7 @@ class FqSimDevice : public FqDevice {
       const FqName& nm = names[k];
       if (nm.hash == FQ_HASH_SKIP) continue;
       uint32_t o = fq_owner_of(nm.hash, world);
-      unsigned long long mi = cursor[2 * o]++, bo = cursor[2 * o + 1]; cursor[2 * o + 1] += nm.len;
+      unsigned long long mi = cursor[2 * o]++, bo = cursor[2 * o + 1]; cursor[2 * o + 1] += (nm.len + 3u) & ~3u;
       FqPackedName& pn = meta[base[2 * o] + mi];
       pn.hash = nm.hash; pn.record = g0 + k; pn.off = (uint32_t)bo; pn.len = nm.len;
       memcpy(blob + base[2 * o + 1] + bo, data + nm.off, nm.len);
@@ -212,6 +216,27 @@ class FqSimDevice : public FqDevice {
         } else a.counters[0]++;
         break;
       }
+    }
+  }
+  void shard_claim(const FqShardArgs& a, const FqShardArgs& ins, unsigned long long sb) override {
+    n_launch_++;
+    const unsigned long long posmask = (1ull << FQ_SHARD_POS_BITS) - 1;
+    for (unsigned long long m = 0; m < a.n; m++) {
+      const FqPackedName& pn = a.meta[m];
+      unsigned long long i = pn.hash & a.mask, probes = 0, unpaired = FQ_IDX_NONE;
+      for (;; i = (i + 1) & a.mask) {
+        if (++probes > a.mask + 1) { unpaired = pn.record; break; }
+        FqSlot& s = a.slots[i];
+        if (s.hash == FQ_HASH_EMPTY) { unpaired = pn.record; break; }
+        if (s.hash != pn.hash) continue;
+        uint32_t ol, ml; const uint8_t* on = shard_name(ins, s.idx1 & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
+        if (!(ol == ml && fq_bytes_equal(on, mn, ml))) { a.counters[0]++; break; }
+        unsigned long long old = s.claim2; if (pn.record < old) s.claim2 = pn.record;
+        if (old == FQ_IDX_NONE) a.counters[1]++;
+        else unpaired = old > pn.record ? old : pn.record;
+        break;
+      }
+      if (unpaired != FQ_IDX_NONE) { unsigned long long key = FQ_KEY(sb + unpaired, FQ_R_NAME); if (key < *a.dup_key) *a.dup_key = key; }
     }
   }
   void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {

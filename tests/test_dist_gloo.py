@@ -28,6 +28,25 @@ def _cases():
     for cuts in ([0.1, 0.5], [0.5, 0.97], [0.045, 0.046]):
         cases.append({"file": "synthetic_dup", "mode": "index", "hex": data.hex(), "cuts": cuts})
         cases.append({"file": "synthetic_dup", "mode": "single", "hex": data.hex(), "cuts": cuts})
+    # pairs: default two-file mode (index loop + mate loop)
+    def pair_case(f1, f2, c1, c2):
+        d1, d2 = read_stream(os.path.join(GOLDEN, "inputs", f1)), read_stream(os.path.join(GOLDEN, "inputs", f2))
+        return {"file": f1 + "+" + f2, "mode": "pair", "hex": d1.hex(), "hex2": d2.hex(), "cuts": c1, "cuts2": c2}
+    for f1, f2 in [("c18_10000_1.fastq.gz", "c18_10000_2.fastq.gz"), ("a_1.fastq.gz", "a_2.fastq.gz"), ("test_21_1.fastq.gz", "test_21_2.fastq.gz"),
+                   ("edge_pair_1.fastq", "edge_pair_2_perm.fastq"), ("edge_pair_1.fastq", "edge_pair_2_rep.fastq"), ("edge_pair_1.fastq", "edge_pair_2_short.fastq"),
+                   ("edge_pair_1.fastq", "edge_pair_2_bad.fastq"), ("edge_pair_1.fastq", "edge_pair_2_trunc.fastq"), ("casava.1.8_1.fastq.gz", "casava.1.8_2.fastq.gz"),
+                   ("test_solid_1.fastq.gz", "test_solid_2.fastq.gz"), ("test_e19_1.fastq.gz", "test_empty.fastq.gz"), ("test_empty.fastq.gz", "test_1.fastq.gz")]:
+        cases.append(pair_case(f1, f2, sorted([rng.random(), rng.random()]), sorted([rng.random(), rng.random()])))
+    mates = [r.replace(" 1:N", " 2:N") for r in recs]
+    mates[17] = recs[17].replace(" 1:N", " 2:N")
+    rng.shuffle(mates)
+    cases.append({"file": "synthetic_pair_dup", "mode": "pair", "hex": data.hex(), "hex2": "".join(mates).encode().hex(), "cuts": [0.3, 0.6], "cuts2": [0.2, 0.7]})
+    clean = [f"@M0:1:FC:1:11:{i}:{i * 7} 1:N:0:AC\n{'ACGTN' * (3 + i % 5)}\n+\n{'F' * (5 * (3 + i % 5))}\n" for i in range(400)]
+    m2 = [x.replace(" 1:N", " 2:N") for x in clean]
+    rng.shuffle(m2)
+    cases.append({"file": "synthetic_pair_ok", "mode": "pair", "hex": "".join(clean).encode().hex(), "hex2": "".join(m2).encode().hex(), "cuts": [0.3, 0.6], "cuts2": [0.2, 0.7]})
+    cases.append({"file": "synthetic_pair_missing", "mode": "pair", "hex": "".join(clean).encode().hex(), "hex2": "".join(m2[:-3]).encode().hex(), "cuts": [0.3, 0.6], "cuts2": [0.2, 0.7]})
+    cases.append({"file": "synthetic_pair_extra", "mode": "pair", "hex": "".join(clean[:-5]).encode().hex(), "hex2": "".join(m2).encode().hex(), "cuts": [0.5, 0.6], "cuts2": [0.1, 0.7]})
     return cases
 
 
@@ -44,6 +63,6 @@ def test_sharded_transcripts_match_oracle(tmp_path, world):
     got = json.load(open(cout))
     assert len(got) == len(cases)
     for c, g in zip(cases, got):
-        argv = (["-r"] if c["mode"] == "single" else []) + ["a.fq"]
-        want = oracle_run(argv, bytes.fromhex(c["hex"]), None)
+        argv = (["-r"] if c["mode"] == "single" else []) + ["a.fq"] + (["b.fq"] if c["mode"] == "pair" else [])
+        want = oracle_run(argv, bytes.fromhex(c["hex"]), bytes.fromhex(c["hex2"]) if c["mode"] == "pair" else None)
         assert tuple(g) == want, (c["file"], c["mode"], c["cuts"], g)
