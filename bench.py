@@ -220,14 +220,14 @@ def main():
 
     # dominant kernel and its roofline
     peak, peak_kind = measured_peak()
-    dom = max(["scan", "records", "tile"], key=lambda k: ks[k]["ms"])
+    dom = max(["scan", "records", "tile", "lanes"], key=lambda k: ks[k]["ms"])
     kd = ks[dom]
     ach = kd["bytes"] / (kd["ms"] / 1e3) / 1e9 if kd["ms"] > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": {"scan": "fq_scan_kernel", "records": "fq_records_kernel", "tile": "fq_tile_kernel"}[dom], "achieved": ach, "peak": peak, "peak_kind": peak_kind,
+    roof = {"bound": "hbm", "kernel": {"scan": "fq_scan_kernel", "records": "fq_records_kernel", "tile": "fq_tile_kernel", "lanes": "fq_lanes_kernel"}[dom], "achieved": ach, "peak": peak, "peak_kind": peak_kind,
             "unit": "GB/s", "frac": ach / peak, "traffic": None, "launches": kd["launches"], "avg_launch_ms": kd["ms"] / max(1, kd["launches"]),
             "algorithmic_bytes_per_launch": kd["bytes"] / max(1, kd["launches"]),
             "all_kernels_ms_per_step": {k: v["ms"] / a.steps for k, v in ks.items()},
-            "parse_validate_GBps": nb * a.steps / ((ks["scan"]["ms"] + ks["records"]["ms"] + ks["tile"]["ms"]) / 1e3) / 1e9 if ks["scan"]["ms"] + ks["records"]["ms"] + ks["tile"]["ms"] > 0 else None,
+            "parse_validate_GBps": nb * a.steps / (sum(ks[k]["ms"] for k in ("scan", "records", "tile", "lanes")) / 1e3) / 1e9 if sum(ks[k]["ms"] for k in ("scan", "records", "tile", "lanes")) > 0 else None,
             "index_Mops_per_s": ks["index"]["items"] / (ks["index"]["ms"] / 1e3) / 1e6 if ks["index"]["ms"] > 0 else None}
 
     out = {"metric": "fastq_info_validated_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

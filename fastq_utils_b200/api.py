@@ -10,7 +10,7 @@ _SO = os.path.join(_HERE, "libfastq_gpu.so")
 _SO = os.environ.get("FQG_SIM_LIBRARY_FOR_TESTS", _SO)
 
 MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED, MODE_SORTED_PAIR = range(5)
-KERNEL_CLASSES = ["scan", "records", "index", "mate", "pair", "other", "tile"]
+KERNEL_CLASSES = ["scan", "records", "index", "mate", "pair", "other", "tile", "lanes"]
 FLAG_PAIRED_NAMES, FLAG_EXTERNAL_INDEX, FLAG_TWO_PASS = 1, 2, 4
 
 
@@ -73,6 +73,7 @@ def lib():
         L.fqg_last_error.restype = ctypes.c_char_p
         L.fqg_launch_count.argtypes = [vp]
         L.fqg_launch_count.restype = u64
+        L.fqg_path_counts.argtypes = [vp, ctypes.POINTER(u64 * 4)]
         L.fqg_device_ms.argtypes = [vp]
         L.fqg_device_ms.restype = ctypes.c_double
         L.fqg_index_records.argtypes = [vp, vp, sz, ctypes.POINTER(u64), sz, ctypes.POINTER(u64)]
@@ -180,6 +181,12 @@ class FastqInfo:
 
     def launch_count(self):
         return int(lib().fqg_launch_count(self._ctx))
+
+    def path_counts(self):
+        """chunks by validating path: {lanes, lanes_handed_on, tile, two_pass_fallbacks}"""
+        out = (ctypes.c_uint64 * 4)()
+        _check(self._ctx, lib().fqg_path_counts(self._ctx, ctypes.byref(out)), "fqg_path_counts")
+        return dict(zip(("lanes", "lanes_handed_on", "tile", "two_pass_fallbacks"), (int(x) for x in out)))
 
     def device_ms(self):
         return float(lib().fqg_device_ms(self._ctx))

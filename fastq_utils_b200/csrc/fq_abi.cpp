@@ -83,6 +83,10 @@ extern "C" int fqg_kernel_stats(fqg_ctx* c, int which, fqg_kernel_stat* out) {
   if (!c || !out) return FQG_ERR_USAGE;
   FQG_GUARD(c, { if (!c->dev->kernel_stat(which, &out->ms, &out->launches, &out->bytes, &out->items)) throw std::runtime_error("fqg_kernel_stats: unknown kernel class"); })
 }
+extern "C" int fqg_path_counts(fqg_ctx* c, uint64_t out[4]) {
+  if (!c || !out) return FQG_ERR_USAGE;
+  FQG_GUARD(c, { for (int i = 0; i < 4; i++) out[i] = c->eng->path_counts[i]; })
+}
 extern "C" int fqg_kernel_stats_reset(fqg_ctx* c) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->dev->kernel_stats_reset())

@@ -569,6 +569,8 @@ fq_tile_kernel(const TileParams P) {
   }
 }
 
+#include "fq_lanes.cuh"
+
 /* ------------------------------------------------------------------------------------------------ K3 / K4: the index */
 __device__ __forceinline__ const uint8_t* dir_name(const FqDirEntry* dir, uint32_t nd, unsigned long long g, uint32_t* len) {
   uint32_t lo = 0, hi = nd;
@@ -877,7 +879,7 @@ class FqCudaDevice : public FqDevice {
     launched();
   }
   bool tile_pass(const FqTileArgs& a) override {
-    if (!a.n) return false;
+    if (!a.n || ((uintptr_t)a.data & 15u)) return false; /* its bulk copies need a 16-byte aligned chunk */
     uint32_t ntiles = (a.n + TILE_BYTES - 1) / TILE_BYTES;
     if (ntiles > max_tiles_) return false;
     if (tile_blocks_ == 0) {
@@ -899,6 +901,45 @@ class FqCudaDevice : public FqDevice {
     fq_tile_kernel<<<grid, TILE_THREADS, TILE_SMEM, st_>>>(P);
     toc(); launched();
     return true;
+  }
+  bool lanes_pass(const FqTileArgs& a) override {
+    if (!a.n) return false;
+    const uint32_t lead = (uint32_t)((uintptr_t)a.data & 15u); /* bulk copies need a 16-byte aligned source: start a little early */
+    uint32_t ntiles = (uint32_t)(((uint64_t)a.n + lead + LN_TILE - 1) / LN_TILE);
+    if (ntiles > max_tiles_) return false;
+    if (lanes_blocks_ == 0) {
+      FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+      int per_sm = 0;
+      FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fq_lanes_kernel, LN_THREADS, LN_SMEM));
+      if (per_sm < 1) return false;
+      lanes_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
+    }
+    LanesParams P;
+    P.data = a.data - lead; P.lead = lead; P.n = a.n + lead; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
+    P.tile_state = tile_state_; P.ticket = ticket_; P.ntiles = ntiles; P.out = a.out5;
+    P.j0 = a.j0; P.cx = a.cx; P.names = a.names; P.names_cap = a.names_cap;
+    FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));
+    FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
+    int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)lanes_blocks_);
+    tic(FQG_K_LANES, a.n, ntiles);
+    fq_lanes_kernel<<<grid, LN_THREADS, LN_SMEM, st_>>>(P);
+    toc(); launched();
+    lanes_records(a, false);
+    return true;
+  }
+  void lanes_records(const FqTileArgs& a, bool undo) {
+    LanesRecParams R;
+    R.line_end = a.line_end; R.out = a.out5; R.j0 = a.j0; R.names = a.names; R.cx = a.cx; R.stats = a.stats; R.hist = a.hist; R.undo = undo ? 1 : 0;
+    uint32_t max_rec = a.cap / 4 + 1;
+    int grid = (int)std::min<uint32_t>((max_rec + 255) / 256, (uint32_t)sms_ * 8);
+    tic(FQG_K_RECORDS, 0, max_rec);
+    fq_lanes_records_kernel<<<grid, 256, 0, st_>>>(R);
+    toc(); launched();
+  }
+  void lanes_commit(const FqTileArgs& a, bool undo) override {
+    if (undo) { lanes_records(a, true); return; }
+    fq_lanes_commit_kernel<<<1, 32, 0, st_>>>(a.out5, a.stats_range);
+    launched();
   }
   static TableParams table_params(const FqTableArgs& a) {
     TableParams P;
@@ -1013,7 +1054,7 @@ class FqCudaDevice : public FqDevice {
   KStat kst_[FQG_K_COUNT];
   std::vector<Pending> pending_;
   std::vector<cudaEvent_t> free_ev_;
-  int dev_ = 0, sms_ = kSMs, tile_blocks_ = 0;
+  int dev_ = 0, sms_ = kSMs, tile_blocks_ = 0, lanes_blocks_ = 0;
   cudaStream_t st_ = nullptr, st2_ = nullptr;
   cudaEvent_t evx_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

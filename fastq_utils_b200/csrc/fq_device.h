@@ -72,6 +72,7 @@ typedef struct {
   FqStats* stats; FqStats* stats_range; unsigned long long* hist; unsigned long long* key; FqName* names; uint32_t names_cap;
 } FqTileArgs;
 
+#define FQ_LANES_OUT_WORDS 12
 class FqDevice {
  public:
   virtual ~FqDevice() {}
@@ -101,6 +102,13 @@ class FqDevice {
   virtual void records(const FqRecordsArgs& a) = 0;
   /* K1+K2 in one pass over HBM; false when the device has no such kernel (the engine then uses K1 and K2) */
   virtual bool tile_pass(const FqTileArgs& a) = 0;
+  /* K5: the clean-data pass (FqCudaDevice only; false = no such kernel).  Proves the chunk clean and stages line index, name
+   * descriptors and statistics; a.out5 holds FQ_LANES_OUT_WORDS words: [0] lines, [1] cap overflow, [2] first over-long header
+   * line, [3] anomaly bits of the pass, [4] internal error, [5] index of a final line without LF, [6..9] staged min/max of
+   * quality and read length, [10] a record broke a length rule.  The counters / histogram are committed by the pass itself
+   * when [1..4] are clear; lanes_commit(undo=false) folds the staged min/max in, lanes_commit(undo=true) takes the counters back. */
+  virtual bool lanes_pass(const FqTileArgs& a) { (void)a; return false; }
+  virtual void lanes_commit(const FqTileArgs& a, bool undo) { (void)a; (void)undo; }
   /* K3: index insert (file 1) / K4: mate claim (file 2) / pair compare (interleaved, sorted) */
   virtual void index_insert(const FqTableArgs& a) = 0;
   virtual void mate_claim(const FqTableArgs& a) = 0;

@@ -23,7 +23,7 @@ FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) 
   counters_ = (unsigned long long*)dev_->alloc(4 * sizeof(unsigned long long));
   scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
   recout_ = (FqRecOut*)dev_->alloc(sizeof(FqRecOut));
-  tile_out_ = (uint32_t*)dev_->alloc(8 * sizeof(uint32_t));
+  tile_out_ = (uint32_t*)dev_->alloc(16 * sizeof(uint32_t));
   for (int f = 0; f < 2; f++) {
     f_[f].stats = (FqStats*)dev_->alloc(sizeof(FqStats));
     f_[f].hist = (unsigned long long*)dev_->alloc((size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
@@ -57,8 +57,10 @@ FqEngine::~FqEngine() {
 void FqEngine::reset() {
   dev_->sync();
   for (int f = 0; f < 2; f++) free_file(f_[f]);
+  for (auto& c : path_counts) c = 0;
   seed_ = 0; finished_ = false; total0_set_ = false; total0_ = 0; fused_ok_ = !(cfg_.flags & FQG_FLAG_TWO_PASS);
   { const char* e = getenv("FQG_FUSED_MIN_BYTES"); fused_min_ = e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 20); } /* test hook */
+  { const char* e = getenv("FQG_NO_LANES"); lanes_ok_ = !(e && *e && *e != '0'); }                                  /* test hook */
   /* results */
   dev_->fill(key_, 0xFF, sizeof(unsigned long long));
   dev_->fill(counters_, 0, 4 * sizeof(unsigned long long));
@@ -118,7 +120,12 @@ void FqEngine::feed_device(int file, const void* dptr, size_t n, bool last) {
   if (n == 0) { add_buffer(file, nullptr, 0, last, false); return; }
   while (n) {
     size_t k = std::min(n, kMaxChunk);
-    add_buffer(file, p, (uint32_t)k, last && k == n, false);
+    if ((uintptr_t)p & 15u) { /* the kernels read 16 bytes at a time: an unaligned piece is copied once into an aligned chunk */
+      uint8_t* d = (uint8_t*)dev_->alloc(k + kPad);
+      dev_->copy(d, p, k);
+      dev_->fill(d + k, 0, kPad);
+      add_buffer(file, d, (uint32_t)k, last && k == n, true);
+    } else add_buffer(file, p, (uint32_t)k, last && k == n, false);
     p += k; n -= k;
   }
 }
@@ -209,25 +216,46 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   if (F.limit != ~0ull) return false;
   if (F.sniff_fmt < 0) {
     if (F.nrec != 0 || F.pend_n != 0) return false;
-    if (!presniff(file, B.data, B.n, j0)) return false;
+    if (!presniff(file, B.data, B.n, j0, !lanes_ok_)) return false; /* the clean-data pass has no record-length limit */
   }
   uint32_t cap = B.n / 32 + 4096;
   B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
   uint32_t ncap = cap / 4 + 1;
   FqName* names = loop != FQ_LOOP_SINGLE ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
-  uint32_t init[6] = {0, 0, kNone32, 0, 0, 0};
-  dev_->upload(tile_out_, init, sizeof init);
   FqTileArgs a; memset(&a, 0, sizeof a);
   a.data = B.data; a.n = B.n; a.virtual_end = last ? 1 : 0; a.line_end = B.line_end; a.cap = cap; a.out5 = tile_out_;
   a.j0 = j0; a.max_rec = kNone32; a.g0 = g0_local + F.g_base; a.step_base = step_base(file); a.cx = make_ctx(file);
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
   a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; a.key = key_; a.names = names; a.names_cap = ncap;
+  /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
+   * below decide (they own the reference's first-error semantics). */
+  if (lanes_ok_ && a.cx.space != FQ_SPACE_COLOR) {
+    uint32_t linit[FQ_LANES_OUT_WORDS] = {0, 0, kNone32, 0, 0, kNone32, kNone32, 0, kNone32, 0, 0, 0};
+    dev_->upload(tile_out_, linit, sizeof linit);
+    if (dev_->lanes_pass(a)) {
+      uint32_t o[FQ_LANES_OUT_WORDS];
+      dev_->download(o, tile_out_, sizeof o);
+      bool pass_ok = !o[1] && o[2] == kNone32 && !o[3] && !o[4];
+      if (pass_ok && !o[10]) {
+        dev_->lanes_commit(a, false);
+        path_counts[0]++;
+        B.nlines = o[0]; B.index_partial = false; B.index_virtual_end = last;
+        *names_out = names; *names_cap = ncap;
+        return true;
+      }
+      path_counts[1]++;
+      if (pass_ok) dev_->lanes_commit(a, true); /* counters went in before a record broke a length rule: take them back */
+    } else dev_->sync();
+  }
+  uint32_t init[6] = {0, 0, kNone32, 0, 0, 0};
+  dev_->upload(tile_out_, init, sizeof init);
   bool launched = dev_->tile_pass(a);
   uint32_t out5[6] = {0, 0, kNone32, 0, 0, 0};
   if (launched) dev_->download(out5, tile_out_, sizeof out5); else dev_->sync();
   if (launched && !out5[1] && out5[2] == kNone32 && !out5[3] && !out5[4]) {
     B.nlines = out5[0]; B.index_partial = true; B.index_from = out5[5]; B.index_virtual_end = last;
     *names_out = names; *names_cap = ncap;
+    path_counts[2]++;
     return true;
   }
   /* not usable: a line gzgets would split, a record longer than the window, more lines than guessed, or no such kernel */
@@ -243,6 +271,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
 /* the fused pass touched the global statistics / event key with results we cannot use: redo everything seen so far two-pass */
 void FqEngine::fused_fallback() {
   fused_ok_ = false;
+  path_counts[3]++;
   for (int f = 0; f < 2; f++) for (auto& s : f_[f].segs) s.fused = false;
   reprocess();
 }

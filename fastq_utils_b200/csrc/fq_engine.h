@@ -81,6 +81,7 @@ class FqEngine {
   void shard_claim_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* claimed, uint64_t* collisions);
   FqDevice* device() { return dev_; }
   std::string last_error;
+  uint64_t path_counts[4] = {0, 0, 0, 0}; /* lanes accepted, lanes handed on, fused per-record accepted, two-pass fallbacks */
 
  private:
   fqg_config cfg_;
@@ -102,6 +103,7 @@ class FqEngine {
   uint64_t claim_sb_ = 0; uint32_t claim_nsrc_ = 0; uint64_t claim_meta_start_[FQ_SHARD_MAX_SRC + 1], claim_blob_start_[FQ_SHARD_MAX_SRC];
   bool fused_ok_ = true;     /* cleared for the rest of the job once a chunk needed the two-pass path */
   uint32_t* tile_out_ = nullptr;
+  bool lanes_ok_ = true;     /* FQG_NO_LANES=1 (test hook) skips the clean-data pass */
   uint32_t fused_min_ = 1u << 20; /* chunks smaller than this always take the two-pass path */
 
   int nfiles() const { return cfg_.mode == FQG_MODE_INDEX_PAIR || cfg_.mode == FQG_MODE_SORTED_PAIR ? 2 : 1; }

@@ -416,19 +416,15 @@ FQ_HD uint64_t fq_hash_name_words(const uint8_t* d, uint32_t off, uint32_t len, 
   return fq_hash_fin(h, len);
 }
 
-/* Clean record of the common shape → fills *o like the careful path would (and *hash with the name hash) and returns
- * true.  Returns false without touching *o otherwise. */
-FQ_HD bool fq_check_record_fast(const uint8_t* d, const FqLine* L, const FqRecCtx& cx, FqRecOut* o, uint64_t* hash) {
-  const uint32_t h0 = L[0].off, hl = L[0].len, s0 = L[1].off, sl = L[1].len, p0 = L[2].off, pl = L[2].len, q0 = L[3].off, ql = L[3].len;
-  if (hl < 3 || sl < 2 || ql < 2) return false;
-  /* header 2: "+\n" or "+\r\n" */
-  if (!(d[p0] == '+' && ((pl == 2 && d[p0 + 1] == '\n') || (pl == 3 && d[p0 + 1] == '\r' && d[p0 + 2] == '\n')))) return false;
-  /* header 1: '@', a second byte that is a name byte, LF-terminated, no NUL */
+/* Header line [h0, h0+hl) of the common shape — '@', a name byte, no NUL, LF at the end — → length of the normalised
+ * name (which starts at h0+1) and the `len` fastq_get_readname reports.  False: let the careful path decide. */
+FQ_HD bool fq_header_fast(const uint8_t* d, uint32_t h0, uint32_t hl, int fmt, int is_pe, uint32_t* name_len, uint64_t* mem_len_out) {
+  if (hl < 3) return false;
   if (d[h0] != '@' || d[h0 + hl - 1] != '\n') return false;
   { uint8_t c1 = d[h0 + 1]; if (c1 == 0 || c1 == '\n' || c1 == '\r') return false; }
   const uint32_t ns = h0 + 1, s = hl - 1; /* rn = line + 1, strlen(rn) = s when there is no NUL */
   uint32_t nlen; uint64_t mem_len;
-  if (cx.fmt_key == FQ_FMT_CASAVA) { /* first space (or the end), then drop a trailing "/x" */
+  if (fmt == FQ_FMT_CASAVA) { /* first space (or the end), then drop a trailing "/x" */
     uint32_t len = s;
     for (uint32_t i = 0; i < s; i += 4) {
       uint32_t w = fq_ldu32(d, ns + i);
@@ -454,9 +450,23 @@ FQ_HD bool fq_check_record_fast(const uint8_t* d, const FqLine* L, const FqRecCt
       if (s - i < 4) z &= (1u << (8u * (s - i))) - 1u;
       if (z) return false;
     }
-    if (cx.fmt_key == FQ_FMT_INT) { nlen = s - 1; mem_len = s; }
-    else { uint32_t len = s - (cx.pe_key ? 1u : 0u); mem_len = len; nlen = len >= 1 ? len - 1 : s; }
+    if (fmt == FQ_FMT_INT) { nlen = s - 1; mem_len = s; }
+    else { uint32_t len = s - (is_pe ? 1u : 0u); mem_len = len; nlen = len >= 1 ? len - 1 : s; }
   }
+  *name_len = nlen; *mem_len_out = mem_len;
+  return true;
+}
+
+/* Clean record of the common shape → fills *o like the careful path would (and *hash with the name hash) and returns
+ * true.  Returns false without touching *o otherwise. */
+FQ_HD bool fq_check_record_fast(const uint8_t* d, const FqLine* L, const FqRecCtx& cx, FqRecOut* o, uint64_t* hash) {
+  const uint32_t h0 = L[0].off, hl = L[0].len, s0 = L[1].off, sl = L[1].len, p0 = L[2].off, pl = L[2].len, q0 = L[3].off, ql = L[3].len;
+  if (hl < 3 || sl < 2 || ql < 2) return false;
+  /* header 2: "+\n" or "+\r\n" */
+  if (!(d[p0] == '+' && ((pl == 2 && d[p0 + 1] == '\n') || (pl == 3 && d[p0 + 1] == '\r' && d[p0 + 2] == '\n')))) return false;
+  const uint32_t ns = h0 + 1;
+  uint32_t nlen; uint64_t mem_len;
+  if (!fq_header_fast(d, h0, hl, cx.fmt_key, cx.pe_key, &nlen, &mem_len)) return false;
   /* sequence */
   if (d[s0 + sl - 1] != '\n') return false;
   uint32_t se = s0 + sl - 1;

@@ -101,7 +101,8 @@ void fqg_destroy(fqg_ctx* ctx);
  * INDEX_PAIR: file 1 may only be fed after file 0 was fed with last=1 (the reference's order). */
 int fqg_feed(fqg_ctx* ctx, int file, const void* host_bytes, size_t n, int last);
 /* Same, for bytes already in device memory; the buffer is borrowed until fqg_reset / fqg_destroy and must be
- * followed by at least 64 readable bytes. */
+ * followed by at least 64 readable bytes.  A pointer that is not 16-byte aligned is accepted but costs one device copy
+ * of the piece (the kernels read 16 bytes at a time). */
 int fqg_feed_device(fqg_ctx* ctx, int file, const void* device_bytes, size_t n, int last);
 int fqg_finish(fqg_ctx* ctx, fqg_report* out);
 /* forget all input and results, keep the device workspace (bench loops) */
@@ -169,11 +170,17 @@ int fqg_set_file_total(fqg_ctx* ctx, int file, uint64_t total_records);
 int fqg_hist_range(fqg_ctx* ctx, int file, uint64_t lo, uint64_t hi, uint64_t* out);
 
 /* ---- per-kernel device timing (CUDA events around every launch on the context's stream) ---- */
-enum { FQG_K_SCAN = 0, FQG_K_RECORDS = 1, FQG_K_INDEX = 2, FQG_K_MATE = 3, FQG_K_PAIR = 4, FQG_K_OTHER = 5, FQG_K_TILE = 6 /* fused scan+records */, FQG_K_COUNT = 7 };
+enum { FQG_K_SCAN = 0, FQG_K_RECORDS = 1, FQG_K_INDEX = 2, FQG_K_MATE = 3, FQG_K_PAIR = 4, FQG_K_OTHER = 5, FQG_K_TILE = 6 /* fused scan+records, one thread per record */,
+       FQG_K_LANES = 7 /* clean-data pass, chunk-parallel */, FQG_K_COUNT = 8 };
 typedef struct { double ms; uint64_t launches; uint64_t bytes; uint64_t items; } fqg_kernel_stat;
 /* accumulated since fqg_create / the last fqg_kernel_stats_reset; `bytes` = FASTQ bytes the launches covered */
 int fqg_kernel_stats(fqg_ctx* ctx, int which, fqg_kernel_stat* out);
 int fqg_kernel_stats_reset(fqg_ctx* ctx);
+
+/* which path validated the chunks fed so far (since fqg_create / fqg_reset): out[0] chunks accepted by the clean-data pass,
+ * out[1] chunks it handed on (an anomaly: the per-record kernels decided), out[2] chunks validated by the fused per-record
+ * kernel, out[3] times the job fell back to the two-pass kernels */
+int fqg_path_counts(fqg_ctx* ctx, uint64_t out[4]);
 
 /* ---- synthetic inputs generated on the device (bench.py, large parity tests); see fq_synth.cu ---- */
 int fqg_synth_illumina_record_bytes(void);

@@ -233,3 +233,131 @@ def test_gpu_fused_pass_fuzz(seed, monkeypatch):
     argv = argv + ["a.fq"] + (["b.fq"] if two else []) + (["pe"] if mode == "pe" else [])
     chunk = rng.choice([0, 0, 20000, 70000])
     assert fqg_run(argv, d1, d2, chunk=chunk, kind="gpu") == oracle_run(argv, d1, d2), (argv, chunk)
+
+
+# ------------------------------------------------------------------------------------------- the clean-data pass (fq_lanes_kernel)
+@pytest.mark.parametrize("seed", range(0, 200, 4))
+def test_gpu_per_record_fused_kernel_without_lanes(seed, monkeypatch):
+    """FQG_NO_LANES=1 keeps the per-record fused kernel (the clean-data pass's fallback) covered on its own."""
+    monkeypatch.setenv("FQG_NO_LANES", "1")
+    test_gpu_fused_pass_fuzz(seed, monkeypatch)
+
+
+def _run_ctx(mode, pieces, hint=0):
+    """Feed device-resident pieces [(ptr, n)] of one file through a fresh context → (report, render transcript, path counts)."""
+    import fastq_utils_b200 as fq
+    h = fq.FastqInfo(mode, index_capacity_hint=hint)
+    for i, (ptr, n) in enumerate(pieces):
+        h.feed_device(0, ptr, n, last=i == len(pieces) - 1)
+    rep = h.finish()
+    tr = h.render(rep, "a.fq")
+    pc = h.path_counts()
+    h.close()
+    return rep, tr, pc
+
+
+@pytest.mark.parametrize("cuts", [(), (1 << 20,), (3_000_017, 9_000_001), (5 * 359 * 1000,), (359 * 4096 + 47, 359 * 8192 + 48, 359 * 20000 + 200)])
+def test_lanes_pass_clean_illumina(cuts):
+    """Clean synthetic reads in one or several device-resident pieces cut at arbitrary bytes: the clean-data pass must accept
+    every piece, and the transcript must be the oracle's."""
+    import fastq_utils_b200 as fq
+    n = 60_000
+    t, nb = _illumina(n)
+    data = bytes(t[:nb].cpu().numpy())
+    edges = [0] + [c for c in cuts if c < nb] + [nb]
+    pieces = [(t.data_ptr() + a, b - a) for a, b in zip(edges[:-1], edges[1:])]
+    for mode, argv in ((fq.MODE_INDEX, ["a.fq"]), (fq.MODE_SINGLE, ["-r", "a.fq"])):
+        rep, tr, pc = _run_ctx(mode, pieces, hint=n)
+        assert tr == oracle_run(argv, data, None), (argv, cuts)
+        assert pc["lanes"] == len(pieces) and pc["lanes_handed_on"] == 0 and pc["two_pass_fallbacks"] == 0, pc
+
+
+def test_lanes_pass_longreads():
+    """Records far longer than a tile: no record-length limit in the clean-data pass."""
+    import torch
+    import fastq_utils_b200 as fq
+    g = torch.Generator().manual_seed(11)
+    lens = torch.exp(torch.randn(400, generator=g) + 9.0).clamp(1000, 100000).to(torch.int64)
+    hdr = fq.lib().fqg_synth_long_header_bytes()
+    off = torch.zeros(401, dtype=torch.int64)
+    off[1:] = torch.cumsum(hdr + 2 * lens + 4, 0)
+    nb = int(off[-1])
+    t = torch.zeros(nb + 64, dtype=torch.uint8, device="cuda")
+    fq.synth_longreads(t, off.cuda(), 0, 400, seed=11, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    data = bytes(t[:nb].cpu().numpy())
+    for mode, argv in ((fq.MODE_SINGLE, ["-r", "a.fq"]), (fq.MODE_INDEX, ["a.fq"])):
+        rep, tr, pc = _run_ctx(mode, [(t.data_ptr(), nb)], hint=400)
+        assert tr == oracle_run(argv, data, None), argv
+        assert pc["lanes"] == 1 and pc["lanes_handed_on"] == 0, pc
+    cut = nb // 3 + 5
+    rep, tr, pc = _run_ctx(fq.MODE_SINGLE, [(t.data_ptr(), cut), (t.data_ptr() + cut, nb - cut)])
+    assert tr == oracle_run(["-r", "a.fq"], data, None) and pc["lanes"] == 2, pc
+
+
+def test_lanes_pass_hands_anomalies_on():
+    """Every kind of deviation from the clean shape makes the pass hand the chunk to the per-record kernels; the verdict and
+    the statistics stay the oracle's (some of these inputs are still valid FASTQ)."""
+    import torch
+    import fastq_utils_b200 as fq
+    rb = fq.illumina_record_bytes()
+    n = 20_000
+    t, nb = _illumina(n)
+    base = bytearray(t[:nb].cpu().numpy().tobytes())
+    hl = base.index(b"\n") + 1  # header length of record 0 (all synthetic headers of this range have it)
+    variants = {}
+    v = bytearray(base); v[7000 * rb + hl + 20] = ord("X"); variants["bad base"] = v
+    v = bytearray(base); v[7000 * rb + hl + 20] = ord("a"); variants["lower case (valid)"] = v
+    v = bytearray(base); v[7000 * rb + hl + 20] = ord("."); variants["dot (valid, careful alphabet)"] = v
+    v = bytearray(base); v[7000 * rb + hl + 151 + 2 + 30] = 0x0C; variants["control byte quality (valid)"] = v
+    v = bytearray(base); v[7000 * rb + hl + 151 + 2 + 30] = 0xC8; variants["high quality byte"] = v
+    v = bytearray(base); v[7000 * rb + hl + 151] = ord("-"); variants["plus line"] = v
+    v = bytearray(base); v[7000 * rb] = ord(">"); variants["header marker"] = v
+    v = bytearray(base); v[7000 * rb + 5] = 0; variants["NUL in header"] = v
+    v = bytearray(base); del v[7000 * rb + rb - 2]; variants["short quality"] = v
+    v = bytearray(base); del v[7000 * rb + hl + 10]; variants["short sequence"] = v
+    v = bytearray(base); v[7000 * rb + hl:7000 * rb + hl + 150] = b""; v[7000 * rb + hl + 3:7000 * rb + hl + 3 + 150] = b""; variants["empty read"] = v
+    v = bytearray(base.replace(b"\n", b"\r\n")); variants["crlf"] = v
+    v = bytearray(base[:-1]); variants["no final newline (valid)"] = v
+    v = bytearray(base[:-100]); variants["truncated"] = v
+    v = bytearray(base); v[7000 * rb + 1:7000 * rb + 1] = b"Q" * 1200; variants["over-long header"] = v
+    for name, v in variants.items():
+        d = bytes(v)
+        tt = torch.frombuffer(bytearray(d + b"\0" * 64), dtype=torch.uint8).cuda()
+        for mode, argv in ((fq.MODE_INDEX, ["a.fq"]), (fq.MODE_SINGLE, ["-r", "a.fq"])):
+            rep, tr, pc = _run_ctx(mode, [(tt.data_ptr(), len(d))], hint=n)
+            assert tr == oracle_run(argv, d, None), (name, argv)
+            if name not in ("no final newline (valid)", "lower case (valid)", "high quality byte"):
+                assert pc["lanes_handed_on"] == 1, (name, pc)
+        del tt
+    # accepted although unusual: lower case bases, a final line without LF, bytes above 0x7F as qualities (the host maps them)
+    for name in ("no final newline (valid)", "lower case (valid)", "high quality byte"):
+        d = bytes(variants[name])
+        tt = torch.frombuffer(bytearray(d + b"\0" * 64), dtype=torch.uint8).cuda()
+        rep, tr, pc = _run_ctx(fq.MODE_INDEX, [(tt.data_ptr(), len(d))], hint=n)
+        assert pc["lanes"] == 1 and pc["lanes_handed_on"] == 0, (name, pc)
+
+
+def test_lanes_pass_statistics_roll_back():
+    """A chunk rejected by the record rules (lengths) after the pass itself found nothing must leave no trace in the
+    statistics: same report as with the clean-data pass switched off."""
+    import torch
+    import fastq_utils_b200 as fq
+    rb = fq.illumina_record_bytes()
+    t, nb = _illumina(30_000)
+    base = bytearray(t[:nb].cpu().numpy().tobytes())
+    hl = base.index(b"\n") + 1
+    # record 12000: sequence and quality both one base shorter (valid, changes min length); record 25000: quality one short (error)
+    v = bytearray(base)
+    del v[25_000 * rb + rb - 2]
+    del v[12_000 * rb + hl + 151 + 2 + 5]; del v[12_000 * rb + hl + 5]
+    d = bytes(v)
+    tt = torch.frombuffer(bytearray(d + b"\0" * 64), dtype=torch.uint8).cuda()
+    cut = 20_000 * rb + 11
+    rep, tr, pc = _run_ctx(fq.MODE_SINGLE, [(tt.data_ptr(), cut), (tt.data_ptr() + cut, len(d) - cut)])
+    assert tr == oracle_run(["-r", "a.fq"], d, None)
+    assert pc["lanes"] == 1 and pc["lanes_handed_on"] == 1, pc
+    ok = d[:24_000 * rb - 2]  # everything before the broken record is valid: statistics include the shorter record 12000
+    tt2 = torch.frombuffer(bytearray(ok + b"\0" * 64), dtype=torch.uint8).cuda()
+    rep, tr, pc = _run_ctx(fq.MODE_SINGLE, [(tt2.data_ptr(), len(ok))])
+    assert tr == oracle_run(["-r", "a.fq"], ok, None) and pc["lanes"] == 1 and rep.file[0].min_rl == 150
