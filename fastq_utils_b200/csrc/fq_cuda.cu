@@ -904,8 +904,8 @@ class FqCudaDevice : public FqDevice {
   }
   bool lanes_pass(const FqTileArgs& a) override {
     if (!a.n) return false;
-    const uint32_t lead = (uint32_t)((uintptr_t)a.data & 15u); /* bulk copies need a 16-byte aligned source: start a little early */
-    uint32_t ntiles = (uint32_t)(((uint64_t)a.n + lead + LN_TILE - 1) / LN_TILE);
+    if ((uintptr_t)a.data & 15u) return false; /* bulk copies need a 16-byte aligned source (the engine aligns what it is fed) */
+    uint32_t ntiles = (a.n + LN_TILE - 1) / LN_TILE;
     if (ntiles > max_tiles_) return false;
     if (lanes_blocks_ == 0) {
       FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
@@ -915,7 +915,7 @@ class FqCudaDevice : public FqDevice {
       lanes_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
     }
     LanesParams P;
-    P.data = a.data - lead; P.lead = lead; P.n = a.n + lead; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
+    P.data = a.data; P.n = a.n; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
     P.tile_state = tile_state_; P.ticket = ticket_; P.ntiles = ntiles; P.out = a.out5;
     P.j0 = a.j0; P.cx = a.cx; P.names = a.names; P.names_cap = a.names_cap;
     FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));

@@ -28,28 +28,24 @@
 constexpr int LN_THREADS = 256, LN_WARPS = LN_THREADS / 32;
 constexpr int LN_TILE = 32768, LN_CHUNKS = LN_TILE / 16, LN_CPT = LN_CHUNKS / LN_THREADS; /* 8 chunks per thread */
 constexpr int LN_LEFT = 16, LN_MARGIN = 1024, LN_WIN = LN_LEFT + LN_TILE + LN_MARGIN;
-constexpr int LN_LMAX = 2048;  /* line ends kept per tile */
-constexpr int LN_EMAX = 2048;  /* partial-chunk work items per tile */
+constexpr int LN_LMAX = 2048;                 /* line ends kept per tile */
 constexpr int LN_OFF_MASK = LN_WIN;
-constexpr int LN_OFF_LEND = LN_OFF_MASK + (LN_CHUNKS + 8) * 2;
+constexpr int LN_OFF_LEND = LN_OFF_MASK + LN_CHUNKS * 2;
 constexpr int LN_OFF_PURE = LN_OFF_LEND + LN_LMAX * 2;
-constexpr int LN_OFF_EDGE = LN_OFF_PURE + LN_CHUNKS * 2;
-constexpr int LN_OFF_LUT = LN_OFF_EDGE + LN_EMAX * 4;
+constexpr int LN_OFF_LUT = LN_OFF_PURE + LN_CHUNKS * 2;
 constexpr int LN_SMEM = LN_OFF_LUT + 32 * 16;
 static_assert(LN_CPT == 8, "a thread's masks are one 16-byte load");
-static_assert(LN_WIN % 16 == 0 && LN_OFF_LEND % 16 == 0 && LN_OFF_PURE % 16 == 0 && LN_OFF_EDGE % 16 == 0 && LN_OFF_LUT % 16 == 0, "alignment");
+static_assert(LN_WIN % 16 == 0 && LN_OFF_LEND % 16 == 0 && LN_OFF_PURE % 16 == 0 && LN_OFF_LUT % 16 == 0, "alignment");
 
 /* anomaly bits (out[3]) */
-enum { LN_A_BASE = 1, LN_A_QUAL = 2, LN_A_HEADER = 4, LN_A_PLUS = 8, LN_A_CAPACITY = 16 };
+enum { LN_A_BASE = 1, LN_A_QUAL = 2, LN_A_HEADER = 4, LN_A_PLUS = 8, LN_A_CAPACITY = 16, LN_A_PHASE = 32 };
 /* out words */
 enum { LN_O_LINES = 0, LN_O_CAPOVF = 1, LN_O_OVERLONG = 2, LN_O_ANOMALY = 3, LN_O_INTERNAL = 4, LN_O_VIRTUAL = 5, LN_O_QMIN = 6, LN_O_QMAX = 7,
        LN_O_RLMIN = 8, LN_O_RLMAX = 9, LN_O_RECBAD = 10, LN_O_WORDS = 12 };
 
 struct LanesParams {
-  const uint8_t* data;  /* 16-byte aligned (bulk copies); the chunk's first byte is data[lead] */
-  uint32_t lead;        /* 0..15 bytes in front of the chunk that are not its data */
-  uint32_t n;           /* lead + bytes of the chunk */
-  int virtual_end; uint32_t* line_end; uint32_t cap;
+  const uint8_t* data; /* 16-byte aligned (bulk copies) */
+  uint32_t n; int virtual_end; uint32_t* line_end; uint32_t cap;
   unsigned long long* tile_state; uint32_t* ticket; uint32_t ntiles;
   uint32_t* out;
   uint32_t j0; FqRecCtx cx; FqName* names; uint32_t names_cap;
@@ -79,18 +75,26 @@ __device__ __forceinline__ void ln_minmax_word(uint32_t w, uint32_t& mn, uint32_
   mx = __vmaxu2(mx, __vmaxu2(ev, od));
 }
 
-/* Walk the byte ranges between the LFs of one chunk.  `m` = LF flags, `nvc` = valid bytes of the chunk (16 except at the end of
- * the data), `lo` = first valid byte (0 except at the start of an unaligned chunk), `cls` = line class there (updated).  F(lo, hi, cls) for every non-empty range, G(p) for every LF. */
-template <typename FSeg, typename FLf>
-__device__ __forceinline__ void ln_walk_chunk(uint32_t m, uint32_t lo, uint32_t nvc, uint32_t& cls, FSeg seg, FLf lf) {
-  while (m) {
-    uint32_t p = __ffs(m) - 1; m &= m - 1;
-    if (p > lo) seg(lo, p, cls);
-    lf(p);
-    cls = (cls + 1u) & 3u;
-    lo = p + 1;
-  }
-  if (lo < nvc) seg(lo, nvc, cls);
+/* One round of the block-wide look-back: every thread holds the state of one predecessor tile (tile-1-tid, ...); returns true
+ * when an inclusive count was among them.  *sum accumulates the counts between that tile and ours.  Contains a barrier. */
+__device__ __forceinline__ bool ln_lookback_round(unsigned long long v64, int lane, int warp, uint32_t* s_sum, uint32_t* s_has, uint32_t* sum) {
+  const uint32_t incl_mask = __ballot_sync(FULL, (v64 >> 62) == 2);
+  const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+  uint32_t part = lane <= first ? (uint32_t)(v64 & ST_VALUE) : 0u;
+  part = __reduce_add_sync(FULL, part);
+  if (lane == 0) { s_sum[warp] = part; s_has[warp] = incl_mask ? 1u : 0u; }
+  __syncthreads();
+  bool found = false;
+#pragma unroll
+  for (int w = 0; w < LN_WARPS; w++) if (!found) { *sum += s_sum[w]; found = s_has[w] != 0; }
+  return found;
+}
+__device__ __forceinline__ unsigned long long ln_wait_state(const unsigned long long* p, uint32_t* out) {
+  unsigned long long v64;
+  uint32_t spins = 0;
+  while (((v64 = ld_volatile64(p)) >> 62) == 0)
+    if (++spins > (1u << 24)) { atomicExch(out + LN_O_INTERNAL, 2u); return ST_INCL; }
+  return v64;
 }
 
 __global__ void __launch_bounds__(LN_THREADS, 4)
@@ -99,16 +103,17 @@ fq_lanes_kernel(const LanesParams P) {
   uint8_t* win = smem;
   uint16_t* maskbuf = (uint16_t*)(smem + LN_OFF_MASK);
   uint16_t* lend = (uint16_t*)(smem + LN_OFF_LEND);
-  uint16_t* pure = (uint16_t*)(smem + LN_OFF_PURE);   /* sequence chunks from the front, quality chunks from the back */
-  uint32_t* edge = (uint32_t*)(smem + LN_OFF_EDGE);   /* same, partial chunks: chunk | lo << 11 | (hi-1) << 15 */
+  uint16_t* pure = (uint16_t*)(smem + LN_OFF_PURE);   /* whole chunks, one region of 256 entries per warp: sequence from its front, quality from its back */
   uint4* lut = (uint4*)(smem + LN_OFF_LUT);           /* [lo] bytes >= lo, [16 + h] bytes <= h */
   __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ uint32_t s_tile, s_w1[LN_WARPS], s_w2[LN_WARPS], s_w3[LN_WARPS], s_base;
+  __shared__ uint32_t s_next, s_guess, s_w1[LN_WARPS], s_w3[LN_WARPS], s_w4[LN_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = smem_u32(&s_bar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_next = atomicAdd(P.ticket, 1u);
+    s_guess = 0;
   }
   if (tid < 32) {
     uint32_t w[4];
@@ -130,25 +135,20 @@ fq_lanes_kernel(const LanesParams P) {
   uint32_t anomaly = 0;
 
   for (;;) {
-    __syncthreads(); /* everyone is done with the previous window and lists */
-    if (tid == 0) {
-      uint32_t t = atomicAdd(P.ticket, 1u);
-      s_tile = t;
-      if (t < P.ntiles) {
-        unsigned long long t0 = (unsigned long long)t * LN_TILE;
-        unsigned long long src = t ? t0 - LN_LEFT : 0;
-        uint32_t dst_off = t ? 0 : LN_LEFT;
-        unsigned long long want = (unsigned long long)LN_WIN - dst_off, have = ((unsigned long long)P.n - src + 15) & ~15ull;
-        uint32_t bytes = (uint32_t)(want < have ? want : have);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(win + dst_off)), "l"(P.data + src), "r"(bytes), "r"(bar) : "memory");
-      }
-    }
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    __syncthreads(); /* everyone is done with the previous window and lists; s_next holds the tile claimed for this round */
+    const uint32_t tile = s_next;
     if (tile >= P.ntiles) break;
     const unsigned long long t0 = (unsigned long long)tile * LN_TILE;
+    if (tid == 0) {
+      unsigned long long src = tile ? t0 - LN_LEFT : 0;
+      uint32_t dst_off = tile ? 0 : LN_LEFT;
+      unsigned long long want = (unsigned long long)LN_WIN - dst_off, have = ((unsigned long long)P.n - src + 15) & ~15ull;
+      uint32_t bytes = (uint32_t)(want < have ? want : have);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(win + dst_off)), "l"(P.data + src), "r"(bytes), "r"(bar) : "memory");
+      s_guess = 0;
+    }
     const uint32_t left = (uint32_t)min((unsigned long long)(LN_TILE + LN_MARGIN), (unsigned long long)P.n - t0); /* data bytes from the tile start */
     const uint32_t nv = min(left, (uint32_t)LN_TILE);   /* valid bytes of the tile itself */
     const uint32_t nloc = LN_LEFT + left;               /* window offsets below this hold data */
@@ -158,8 +158,7 @@ fq_lanes_kernel(const LanesParams P) {
       while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) { if (tid == 0) atomicExch(P.out + LN_O_INTERNAL, 1u); break; } }
       parity ^= 1;
     }
-    const uint32_t lead = tile == 0 ? P.lead : 0u; /* bytes of the tile's first 16-byte chunk that precede the data */
-    if (tile == 0 && tid == 0) { win[LN_LEFT - 1] = '\n'; win[LN_LEFT + lead - 1] = '\n'; }
+    if (tile == 0 && tid == 0) win[LN_LEFT - 1] = '\n';
 
     /* ---- A: LF flags; lane ↔ adjacent chunks (conflict-free 128-bit shared loads) */
     {
@@ -169,15 +168,23 @@ fq_lanes_kernel(const LanesParams P) {
         const uint32_t c = cbase + i * 32;
         uint32_t m = ln_lf_mask16(*(const uint4*)(win + LN_LEFT + 16 * c));
         if (!full) { uint32_t valid = nv > 16 * c ? min(16u, nv - 16 * c) : 0u; m &= (1u << valid) - 1u; }
-        if (c == 0) m &= ~((1u << lead) - 1u);
         maskbuf[c] = (uint16_t)m;
       }
     }
     __syncwarp(); /* a thread's 8 consecutive chunks were flagged by its own warp */
     const uint4 mm = *(const uint4*)(maskbuf + LN_CPT * tid);
-    const uint32_t tot = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
+    /* LFs in front of each of the thread's chunks, four 8-bit counters per register */
+    uint32_t cumA, cumB, tot;
+    {
+      const uint32_t n0 = __popc(mm.x & 0xFFFFu), n01 = __popc(mm.x), n2 = __popc(mm.y & 0xFFFFu), n23 = __popc(mm.y);
+      const uint32_t n4 = __popc(mm.z & 0xFFFFu), n45 = __popc(mm.z), n6 = __popc(mm.w & 0xFFFFu), n67 = __popc(mm.w);
+      const uint32_t h = n01 + n23;
+      cumA = (n0 << 8) | (n01 << 16) | ((n01 + n2) << 24);                       /* chunks 0..3: 0, n0, n01, n01+n2 */
+      cumB = h | ((h + n4) << 8) | ((h + n45) << 16) | ((h + n45 + n6) << 24);   /* chunks 4..7 */
+      tot = h + n45 + n67;
+    }
 
-    /* ---- B: prefix of the LF counts inside the tile, look-back across tiles */
+    /* ---- B: prefix of the LF counts inside the tile; this tile's count is published for the tiles behind us */
     uint32_t incl = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += a; }
@@ -186,143 +193,183 @@ fq_lanes_kernel(const LanesParams P) {
     uint32_t excl = incl - tot, cntT = 0;
 #pragma unroll
     for (int w = 0; w < LN_WARPS; w++) { uint32_t x = s_w1[w]; cntT += x; if (w < warp) excl += x; }
-    if (warp == 0) {
-      unsigned long long acc = 0;
-      if (tile > 0) {
-        if (lane == 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
-        int look = (int)tile - 1;
-        uint32_t spins = 0;
-        for (;;) {
-          int idx = look - lane;
-          unsigned long long v64 = idx >= 0 ? ld_volatile64(P.tile_state + idx) : ST_INCL;
-          while (__any_sync(FULL, (v64 >> 62) == 0)) {
-            if ((v64 >> 62) == 0) v64 = ld_volatile64(P.tile_state + idx);
-            if (++spins > (1u << 26)) { if (lane == 0) atomicExch(P.out + LN_O_INTERNAL, 2u); v64 = ST_INCL; }
-          }
-          uint32_t incl_mask = __ballot_sync(FULL, (v64 >> 62) == 2);
-          int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
-          unsigned long long part = lane <= first ? (v64 & ST_VALUE) : 0ull;
-#pragma unroll
-          for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(FULL, part, d);
-          acc += part;
-          if (incl_mask) break;
-          look -= 32;
-        }
-      }
-      if (lane == 0) {
-        st_volatile64(P.tile_state + tile, ST_INCL | (acc + cntT));
-        s_base = (uint32_t)acc;
-        if (tile == P.ntiles - 1) {
-          uint32_t cnt = (uint32_t)acc + cntT;
-          if (P.virtual_end && P.n > P.lead && win[nloc - 1] != '\n') { if (cnt < P.cap) P.line_end[cnt] = P.n - P.lead; P.out[LN_O_VIRTUAL] = cnt; cnt++; }
-          P.out[LN_O_LINES] = cnt; P.out[LN_O_CAPOVF] = cnt > P.cap ? 1u : 0u;
-        }
-      }
-    }
-    __syncthreads();
-    const uint32_t base_line = s_base;
-    const uint32_t cls0 = (base_line + excl - P.j0) & 3u; /* line class at this thread's first byte */
+    if (tid == 0 && tile > 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
+    /* line ends of this thread's LFs: window offsets, in order (needs only the rank inside the tile).  On the way: every
+     * "\n+\n" says that the line ending at its second LF is a plus line, i.e. proposes the line class of the tile's first byte. */
     const uint32_t c0 = LN_CPT * tid;
-    const uint32_t mw[4] = {mm.x, mm.y, mm.z, mm.w};
-
-    /* ---- C1: how many work items of each kind does this thread produce? */
-    uint32_t n_pure = 0, n_edge = 0; /* sequence count in the low half, quality count in the high half */
-    {
-      uint32_t cls = cls0;
-#pragma unroll
-      for (int i = 0; i < LN_CPT; i++) {
-        const uint32_t m = (mw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-        const uint32_t nvc = full ? 16u : (nv > 16 * (c0 + i) ? min(16u, nv - 16 * (c0 + i)) : 0u);
-        const uint32_t lo0 = (i == 0 && tid == 0) ? lead : 0u;
-        if (m == 0 && nvc == 16u && lo0 == 0u) { n_pure += (cls == 1u ? 1u : 0u) + (cls == 3u ? 0x10000u : 0u); }
-        else ln_walk_chunk(m, lo0, nvc, cls,
-                           [&](uint32_t, uint32_t, uint32_t k) { n_edge += (k == 1u ? 1u : 0u) + (k == 3u ? 0x10000u : 0u); },
-                           [&](uint32_t) {});
-      }
-    }
-    uint32_t ip = n_pure, ie = n_edge;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t a = __shfl_up_sync(FULL, ip, d), b = __shfl_up_sync(FULL, ie, d);
-      if (lane >= d) { ip += a; ie += b; }
-    }
-    if (lane == 31) { s_w2[warp] = ip; s_w3[warp] = ie; }
-    __syncthreads();
-    uint32_t xp = ip - n_pure, xe = ie - n_edge, tp = 0, te = 0;
-#pragma unroll
-    for (int w = 0; w < LN_WARPS; w++) { uint32_t a = s_w2[w], b = s_w3[w]; tp += a; te += b; if (w < warp) { xp += a; xe += b; } }
-    const uint32_t n_seq_pure = tp & 0xFFFFu, n_qual_pure = tp >> 16, n_seq_edge = te & 0xFFFFu, n_qual_edge = te >> 16;
-    const bool too_many = n_seq_edge + n_qual_edge > (uint32_t)LN_EMAX || cntT > (uint32_t)LN_LMAX;
+    const bool too_many = cntT > (uint32_t)LN_LMAX;
     if (too_many) anomaly |= LN_A_CAPACITY;
-
-    /* ---- C2: emit line ends and work items */
-    if (!too_many) {
-      uint32_t cls = cls0, rank = excl;
-      uint32_t ps = xp & 0xFFFFu, pq = LN_CHUNKS - 1 - (xp >> 16), es = xe & 0xFFFFu, eq = LN_EMAX - 1 - (xe >> 16);
-#pragma unroll
-      for (int i = 0; i < LN_CPT; i++) {
-        const uint32_t m = (mw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-        const uint32_t c = c0 + i;
-        const uint32_t nvc = full ? 16u : (nv > 16 * c ? min(16u, nv - 16 * c) : 0u);
-        const uint32_t lo0 = (i == 0 && tid == 0) ? lead : 0u;
-        if (m == 0 && nvc == 16u && lo0 == 0u) {
-          if (cls == 1u) pure[ps++] = (uint16_t)c;
-          else if (cls == 3u) pure[pq--] = (uint16_t)c;
-        } else
-          ln_walk_chunk(m, lo0, nvc, cls,
-                        [&](uint32_t lo, uint32_t hi, uint32_t k) {
-                          uint32_t it = c | (lo << 11) | ((hi - 1u) << 15);
-                          if (k == 1u) edge[es++] = it; else if (k == 3u) edge[eq--] = it;
-                        },
-                        [&](uint32_t p) { lend[rank++] = (uint16_t)(LN_LEFT + 16 * c + p + 1); });
-      }
+    else {
+      uint32_t rank = excl, prop = 0;
+      const uint32_t e0 = LN_LEFT + 16 * c0 + 1;
+/* the first two LFs of a 32-byte span without a branch, a loop for the rare rest */
+#define LN_EMIT1(w_, h_) { const uint32_t b = __ffs(w) - 1; const uint32_t e = e0 + 32 * (h_) + b; \
+        if (w) { lend[rank] = (uint16_t)e; if (((w_) >> b) & 4u) { if (win[e] == '+') prop |= 1u << ((1u - rank) & 3u); } rank++; } w &= w - 1; }
+#define LN_EMIT(w_, h_) { uint32_t w = (w_); LN_EMIT1(w_, h_) LN_EMIT1(w_, h_) while (w) LN_EMIT1(w_, h_) }
+      LN_EMIT(mm.x, 0) LN_EMIT(mm.y, 1) LN_EMIT(mm.z, 2) LN_EMIT(mm.w, 3)
+#undef LN_EMIT1
+#undef LN_EMIT
+      prop = __reduce_or_sync(FULL, prop);
+      if (lane == 0 && prop) atomicOr(&s_guess, prop);
     }
     __syncthreads();
 
-    if (!too_many) {
-      /* ---- D: sequence alphabet, quality range; one predicate per warp instruction */
-      for (uint32_t i = tid; i < n_seq_pure; i += LN_THREADS)
-        seq_ok &= ln_pred4(*(const uint4*)(win + LN_LEFT + 16 * (uint32_t)pure[i]));
-      for (uint32_t i = tid; i < n_seq_edge; i += LN_THREADS) {
-        const uint32_t it = edge[i], c = it & 0x7FFu;
-        const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * c);
-        const uint4 a = lut[(it >> 11) & 15u], b = lut[16u + ((it >> 15) & 15u)];
-        /* bytes outside [lo, hi) always pass */
-        seq_ok &= (fq_base_pred(v.x) | ~(a.x & b.x)) & (fq_base_pred(v.y) | ~(a.y & b.y)) & (fq_base_pred(v.z) | ~(a.z & b.z)) & (fq_base_pred(v.w) | ~(a.w & b.w));
+    /* ---- C0: line class of the tile's first byte.  The true value needs the number of lines in front of the tile (the sum of
+     * the counts of all tiles before ours); when the plus lines of the tile agree on it we go on with their answer and check it
+     * against the sum at the end of the tile, when the tiles in front have long published theirs. */
+    uint32_t base_line = 0;
+    bool have_base = false;
+    uint32_t phi;
+    {
+      const uint32_t g = s_guess;
+      if (g == 1u || g == 2u || g == 4u || g == 8u) phi = 31u - __clz(g);
+      else { /* no witness (or witnesses that disagree): wait for the sum now */
+        for (int look = (int)tile - 1;; look -= LN_THREADS) { /* trip count is uniform over the block */
+          const int idx = look - tid;
+          const unsigned long long v64 = idx >= 0 ? ln_wait_state(P.tile_state + idx, P.out) : ST_INCL;
+          if (ln_lookback_round(v64, lane, warp, s_w3, s_w4, &base_line)) break;
+          __syncthreads(); /* s_w3 / s_w4 are rewritten by the next round */
+        }
+        have_base = true;
+        phi = (base_line + 4u - P.j0) & 3u;
       }
-      for (uint32_t i = tid; i < n_qual_pure; i += LN_THREADS) {
-        const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * (uint32_t)pure[LN_CHUNKS - 1 - i]);
+    }
+    /* line numbers relative to the tile: class = number & 3, record of the tile = (number >> 2) - 1 */
+    const uint32_t gbr = 4u + phi;
+    const uint32_t g0t = gbr + excl;                /* line number at this thread's first byte */
+
+    /* ---- C1: whole chunks of sequence / quality lines: classify (all lanes in step), then one list per warp */
+    uint32_t n_seq_w, n_qual_w;
+    {
+      uint32_t is_seq = 0, is_qual = 0; /* bit i: chunk i of this thread is a whole chunk of that class */
+#pragma unroll
+      for (int i = 0; i < LN_CPT; i++) {
+        const uint32_t m = ((i < 2 ? mm.x : i < 4 ? mm.y : i < 6 ? mm.z : mm.w) >> (16 * (i & 1))) & 0xFFFFu;
+        const uint32_t cum = ((i < 4 ? cumA : cumB) >> (8 * (i & 3))) & 0xFFu;
+        const uint32_t cls = (g0t + cum) & 3u;
+        bool whole = m == 0;
+        if (!full) whole = whole && nv >= 16 * (c0 + i) + 16;
+        is_seq |= (whole && cls == 1u) ? 1u << i : 0u;
+        is_qual |= (whole && cls == 3u) ? 1u << i : 0u;
+      }
+      const uint32_t n_pure = __popc(is_seq) | (__popc(is_qual) << 16);
+      uint32_t ip = n_pure;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, ip, d); if (lane >= d) ip += a; }
+      const uint32_t tw = __shfl_sync(FULL, ip, 31), xp = ip - n_pure;
+      n_seq_w = tw & 0xFFFFu; n_qual_w = tw >> 16;
+      uint32_t as = smem_u32(pure) + 2 * (warp * 256 + (xp & 0xFFFFu)), aq = smem_u32(pure) + 2 * (warp * 256 + 255 - (xp >> 16));
+#pragma unroll
+      for (int i = 0; i < LN_CPT; i++) {
+        asm volatile("{ .reg .pred p, q; setp.ne.u32 p, %2, 0; setp.ne.u32 q, %3, 0;\n"
+                     "  @p st.shared.u16 [%0], %4; @p add.u32 %0, %0, 2;\n"
+                     "  @q st.shared.u16 [%1], %4; @q sub.u32 %1, %1, 2; }"
+                     : "+r"(as), "+r"(aq) : "r"(is_seq & (1u << i)), "r"(is_qual & (1u << i)), "h"((uint16_t)(c0 + i)) : "memory");
+      }
+    }
+
+    /* the state of one tile in front of ours, asked for now and looked at after D */
+    unsigned long long pre64 = ST_INCL;
+    if (!have_base && (int)tile - 1 - tid >= 0) pre64 = ld_volatile64(P.tile_state + ((int)tile - 1 - tid));
+    __syncthreads();
+
+    if (!too_many) {
+      /* ---- D: sequence alphabet, quality range; one predicate per warp instruction.
+       * Whole chunks come from the warp's lists.  Partial chunks hang on LFs: the bytes after a header / plus LF and before a
+       * sequence / quality LF; the LFs of one kind are every fourth line end, so item i of a kind is found by arithmetic. */
+      const uint16_t* pw = pure + warp * 256;
+      for (uint32_t i = lane; i < n_seq_w; i += 32)
+        seq_ok &= ln_pred4(*(const uint4*)(win + LN_LEFT + 16 * (uint32_t)pw[i]));
+      for (uint32_t i = lane; i < n_qual_w; i += 32) {
+        const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * (uint32_t)pw[255 - i]);
         ln_minmax_word(v.x, qmn, qmx); ln_minmax_word(v.y, qmn, qmx); ln_minmax_word(v.z, qmn, qmx); ln_minmax_word(v.w, qmn, qmx);
       }
-      for (uint32_t i = tid; i < n_qual_edge; i += LN_THREADS) {
-        const uint32_t it = edge[LN_EMAX - 1 - i], c = it & 0x7FFu, lo = (it >> 11) & 15u;
-        const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * c);
-        const uint4 a = lut[lo], b = lut[16u + ((it >> 15) & 15u)];
-        const uint32_t fill = (uint32_t)win[LN_LEFT + 16 * c + lo] * 0x01010101u; /* a byte of the range stands in for the bytes outside it */
-        uint32_t m;
-        m = a.x & b.x; ln_minmax_word((v.x & m) | (fill & ~m), qmn, qmx);
-        m = a.y & b.y; ln_minmax_word((v.y & m) | (fill & ~m), qmn, qmx);
-        m = a.z & b.z; ln_minmax_word((v.z & m) | (fill & ~m), qmn, qmx);
-        m = a.w & b.w; ln_minmax_word((v.w & m) | (fill & ~m), qmn, qmx);
+      const uint32_t n_items = 2u * ((cntT + 3u) >> 2); /* per kind: two per started group of four lines */
+#pragma unroll
+      for (int kind = 0; kind < 2; kind++) { /* 0: sequence side (classes 0, 1), 1: quality side (classes 2, 3) */
+        const uint32_t ra = ((kind ? 2u : 0u) - gbr) & 3u, rb = ((kind ? 3u : 1u) - gbr) & 3u; /* first line ends of those classes */
+        for (uint32_t i = tid; i < n_items; i += LN_THREADS) {
+          const bool before = i & 1u;                     /* odd items: the bytes before a sequence / quality LF */
+          const uint32_t r = 4u * (i >> 1) + (before ? rb : ra);
+          if (r < cntT) {
+            const uint32_t e = lend[r], q = e - (LN_LEFT + 1), c = q >> 4, p = q & 15u;
+            const uint32_t mc = maskbuf[c];               /* all LFs of this chunk */
+            const uint32_t below = mc & ((1u << p) - 1u), above = mc >> (p + 1);
+            uint32_t nvc = 16u;
+            if (!full) nvc = min(16u, nv - 16 * c);       /* the chunk holds an LF, so it starts inside the data */
+            const uint32_t lo = before ? (below ? 32u - __clz(below) : 0u) : p + 1;
+            const uint32_t hi = before ? p : (above ? p + __ffs(above) : nvc);
+            if (hi > lo) {
+              const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * c);
+              const uint4 a = lut[lo], b = lut[15u + hi];
+              if (kind == 0) /* bytes outside [lo, hi) always pass */
+                seq_ok &= (fq_base_pred(v.x) | ~(a.x & b.x)) & (fq_base_pred(v.y) | ~(a.y & b.y)) & (fq_base_pred(v.z) | ~(a.z & b.z)) & (fq_base_pred(v.w) | ~(a.w & b.w));
+              else {
+                const uint32_t fill = (uint32_t)win[LN_LEFT + 16 * c + lo] * 0x01010101u; /* a byte of the range stands in for the bytes outside it */
+                uint32_t m;
+                m = a.x & b.x; ln_minmax_word((v.x & m) | (fill & ~m), qmn, qmx);
+                m = a.y & b.y; ln_minmax_word((v.y & m) | (fill & ~m), qmn, qmx);
+                m = a.z & b.z; ln_minmax_word((v.z & m) | (fill & ~m), qmn, qmx);
+                m = a.w & b.w; ln_minmax_word((v.w & m) | (fill & ~m), qmn, qmx);
+              }
+            }
+          }
+        }
       }
+      /* the chunk cut by the end of the data, when no LF of its own bounds it */
+      if (!full && (nv & 15u) && (nv >> 4) >= c0 && (nv >> 4) < c0 + LN_CPT && maskbuf[nv >> 4] == 0) {
+        const uint32_t i = (nv >> 4) - c0, c = nv >> 4, hi = nv & 15u;
+        const uint32_t cum = ((i < 4 ? cumA : cumB) >> (8 * (i & 3))) & 0xFFu, cls = (g0t + cum) & 3u;
+        for (uint32_t k = 0; k < hi; k++) {
+          const uint32_t ch = win[LN_LEFT + 16 * c + k];
+          if (cls == 1u) { if (!((fq_base_pred(ch) >> 7) & 1u)) seq_ok = 0; }
+          else if (cls == 3u) { ln_minmax_word(ch * 0x01010101u, qmn, qmx); }
+        }
+      }
+    }
 
-      /* ---- E1: line ends of the tile → global line index */
-      const uint32_t gofs = (uint32_t)(t0 - LN_LEFT) - P.lead; /* window offset → offset inside the chunk */
-      for (uint32_t k = tid; k < cntT; k += LN_THREADS) { uint32_t gi = base_line + k; if (gi < P.cap) P.line_end[gi] = gofs + lend[k]; }
+    /* ---- E0: lines in front of the tile (block-wide look-back, normally one round over states read before D) */
+    if (!have_base) {
+      bool first_round = true;
+      for (int look = (int)tile - 1;; look -= LN_THREADS) {
+        const int idx = look - tid;
+        unsigned long long v64 = ST_INCL;
+        if (idx >= 0) v64 = (first_round && (pre64 >> 62) != 0) ? pre64 : ln_wait_state(P.tile_state + idx, P.out);
+        first_round = false;
+        if (ln_lookback_round(v64, lane, warp, s_w3, s_w4, &base_line)) break;
+        __syncthreads();
+      }
+      if (((base_line + 4u - P.j0) & 3u) != phi) anomaly |= LN_A_PHASE; /* the plus lines of the tile misled us: hand the chunk on */
+    }
+    if (tid == 0) {
+      st_volatile64(P.tile_state + tile, ST_INCL | ((unsigned long long)base_line + cntT));
+      s_next = atomicAdd(P.ticket, 1u);
+      if (tile == P.ntiles - 1) {
+        uint32_t cnt = base_line + cntT;
+        if (P.virtual_end && P.n > 0 && win[nloc - 1] != '\n') { if (cnt < P.cap) P.line_end[cnt] = P.n; P.out[LN_O_VIRTUAL] = cnt; cnt++; }
+        P.out[LN_O_LINES] = cnt; P.out[LN_O_CAPOVF] = cnt > P.cap ? 1u : 0u;
+      }
+    }
+    if (!too_many) {
+      /* line numbers shifted so that the chunk's first record starts at line 4: class = number & 3, record = (number >> 2) - 1 (j0 <= 4) */
+      const uint32_t gb = base_line + 4u - P.j0;
+      const uint32_t gofs = (uint32_t)(t0 - LN_LEFT); /* window offset → offset inside the chunk */
+      /* ---- E1: line ends → global line index */
+      for (uint32_t r = tid; r < cntT; r += LN_THREADS) { const uint32_t gi = base_line + r; if (gi < P.cap) P.line_end[gi] = gofs + lend[r]; }
 
       /* ---- E2: header and plus lines that start in this tile.  Line k of the tile (0..cntT) starts at lend[k-1]. */
       {
         const uint32_t kmin = win[LN_LEFT - 1] == '\n' ? 0u : 1u;
         const uint32_t tile_end = LN_LEFT + nv; /* lines starting at or beyond belong to the next tile (or do not exist) */
-        uint32_t kh0 = kmin + ((0u - (base_line + kmin - P.j0)) & 3u);
-        if (base_line + kh0 < P.j0) kh0 += 4;
-        uint32_t kp0 = kmin + ((2u - (base_line + kmin - P.j0)) & 3u);
-        if (base_line + kp0 < P.j0) kp0 += 4;
+        uint32_t kh0 = kmin + ((0u - (gb + kmin)) & 3u);
+        if (gb + kh0 < 4u) kh0 += 4;
+        uint32_t kp0 = kmin + ((2u - (gb + kmin)) & 3u);
+        if (gb + kp0 < 4u) kp0 += 4;
         const uint32_t nH = kh0 <= cntT ? (cntT - kh0) / 4 + 1 : 0, nP = kp0 <= cntT ? (cntT - kp0) / 4 + 1 : 0;
         for (uint32_t u = tid; u < nH + nP; u += LN_THREADS) {
           const bool is_hdr = u < nH;
           const uint32_t k = is_hdr ? kh0 + 4 * u : kp0 + 4 * (u - nH);
-          const uint32_t s = k == 0 ? (uint32_t)LN_LEFT + lead : (uint32_t)lend[k - 1];
+          const uint32_t s = k == 0 ? (uint32_t)LN_LEFT : (uint32_t)lend[k - 1];
           if (s >= tile_end) continue;
           if (!is_hdr) { /* "+\n" */
             if (s + 1 >= nloc) continue; /* cut by the end of the data: the record is completed (or judged) elsewhere */
@@ -341,12 +388,11 @@ fq_lanes_kernel(const LanesParams P) {
           }
           const uint32_t hl = e - s;
           if (hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, base_line + k); continue; }
-          uint32_t nlen; uint64_t mem_len;
-          if (!fq_header_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, &nlen, &mem_len)) { anomaly |= LN_A_HEADER; continue; }
-          const uint32_t rec = (base_line + k - P.j0) >> 2;
+          uint32_t nlen; uint64_t mem_len, hsh = FQ_HASH_SKIP;
+          if (!fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; continue; }
+          const uint32_t rec = ((gb + k) >> 2) - 1u;
           if (P.names && rec < P.names_cap) {
-            FqName nm; nm.off = gofs + s + 1; nm.len = nlen;
-            nm.hash = fq_hash_name_words(win, s + 1, nlen, P.cx.seed);
+            FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
             P.names[rec] = nm;
           }
         }

@@ -182,12 +182,20 @@ FQ_HD bool fq_compare_headers(const uint8_t* a, uint32_t alen, const uint8_t* b,
 
 /* 64-bit hash of a name, defined on its little-endian 32-bit words (last one zero-padded) and its length, so
  * that any implementation (byte loop here, funnel-shifted words in a kernel) produces the same value.  The
- * value itself is unobservable: equality is always confirmed on the bytes (reference: hashit + strcmp). */
-FQ_HD uint64_t fq_hash_mix(uint64_t h, uint32_t w) {
-  h = (h ^ w) * 0x9E3779B97F4A7C15ull;
-  return h ^ (h >> 29);
+ * value itself is unobservable: equality is always confirmed on the bytes (reference: hashit + strcmp).
+ * Two independent 32-bit multiplicative lanes per word (each step a bijection of its lane, so names that differ in
+ * one word never collide in a lane) keep the per-word cost at five 32-bit instructions; a 64-bit finaliser mixes them. */
+typedef struct { uint32_t a, b; } FqHashState;
+FQ_HD FqHashState fq_hash_init(uint32_t seed) {
+  FqHashState h; h.a = 0x85A308D3u ^ (seed * 0x9E3779B1u); h.b = 0x243F6A88u + seed * 0x85EBCA77u;
+  return h;
 }
-FQ_HD uint64_t fq_hash_fin(uint64_t h, uint32_t len) {
+FQ_HD void fq_hash_word(FqHashState* h, uint32_t w) {
+  h->a = (h->a ^ w) * 0x9E3779B1u;
+  h->b = (((h->b << 13) | (h->b >> 19)) ^ w) * 0xC2B2AE3Du;
+}
+FQ_HD uint64_t fq_hash_fin(FqHashState s, uint32_t len) {
+  uint64_t h = ((uint64_t)s.a << 32) | s.b;
   h = (h ^ len) * 0xD6E8FEB86659FD93ull;
   h ^= h >> 32;
   h *= 0xD6E8FEB86659FD93ull;
@@ -195,16 +203,16 @@ FQ_HD uint64_t fq_hash_fin(uint64_t h, uint32_t len) {
   return h >= FQ_HASH_SKIP ? h - 2 : h;
 }
 FQ_HD uint64_t fq_hash_name(const uint8_t* p, uint32_t len, uint32_t seed) {
-  uint64_t h = 0x243F6A8885A308D3ull ^ ((uint64_t)seed * 0xFF51AFD7ED558CCDull);
+  FqHashState h = fq_hash_init(seed);
   uint32_t i = 0;
   for (; i + 4 <= len; i += 4) {
     uint32_t w = (uint32_t)p[i] | ((uint32_t)p[i + 1] << 8) | ((uint32_t)p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24);
-    h = fq_hash_mix(h, w);
+    fq_hash_word(&h, w);
   }
   if (i < len) {
     uint32_t w = 0;
     for (uint32_t k = 0; i + k < len; k++) w |= (uint32_t)p[i + k] << (8 * k);
-    h = fq_hash_mix(h, w);
+    fq_hash_word(&h, w);
   }
   return fq_hash_fin(h, len);
 }
@@ -409,11 +417,99 @@ FQ_HD uint32_t fq_ldu32(const uint8_t* d, uint32_t off) {
 FQ_HD uint32_t fq_low_bytes(uint32_t w, uint32_t nbytes) { return nbytes >= 4 ? w : (w & ((1u << (8u * nbytes)) - 1u)); }
 /* same value as fq_hash_name, four bytes at a time */
 FQ_HD uint64_t fq_hash_name_words(const uint8_t* d, uint32_t off, uint32_t len, uint32_t seed) {
-  uint64_t h = 0x243F6A8885A308D3ull ^ ((uint64_t)seed * 0xFF51AFD7ED558CCDull);
+  FqHashState h = fq_hash_init(seed);
   uint32_t i = 0;
-  for (; i + 4 <= len; i += 4) h = fq_hash_mix(h, fq_ldu32(d, off + i));
-  if (i < len) h = fq_hash_mix(h, fq_low_bytes(fq_ldu32(d, off + i), len - i));
+  for (; i + 4 <= len; i += 4) fq_hash_word(&h, fq_ldu32(d, off + i));
+  if (i < len) fq_hash_word(&h, fq_low_bytes(fq_ldu32(d, off + i), len - i));
   return fq_hash_fin(h, len);
+}
+
+/* Header line and name hash in ONE walk over the line's words (aligned loads, a carried word and a funnel shift give the
+ * words of the name, which starts one byte into the line).  Same results as fq_header_fast + fq_hash_name_words; false
+ * where fq_header_fast is false. */
+FQ_HD bool fq_header_hash_fast(const uint8_t* d, uint32_t h0, uint32_t hl, int fmt, int is_pe, uint32_t seed, bool want_hash,
+                               uint32_t* name_len, uint64_t* mem_len_out, uint64_t* hash) {
+  if (hl < 3) return false;
+  if (d[h0] != '@' || d[h0 + hl - 1] != '\n') return false;
+  { uint8_t c1 = d[h0 + 1]; if (c1 == 0 || c1 == '\n' || c1 == '\r') return false; }
+  const uint32_t ns = h0 + 1, s = hl - 1;
+  const uint32_t sh = (ns & 3u) * 8u;
+  uint32_t a = ns & ~3u;
+  uint32_t cur = fq_ld32(d, a);
+  FqHashState h = fq_hash_init(seed);
+  /* length of the name when no space cuts it: the line without its LF (INT), and without one more byte (DEFAULT: the mate digit
+   * or the CR of a CRLF line, exactly as the reference drops it) */
+  uint32_t nlen; uint64_t mem_len;
+  bool casava = fmt == FQ_FMT_CASAVA;
+  if (fmt == FQ_FMT_INT) { nlen = s - 1; mem_len = s; }
+  else if (!casava) { uint32_t len = s - (is_pe ? 1u : 0u); mem_len = len; nlen = len >= 1 ? len - 1 : s; }
+  else { nlen = s; mem_len = s; }
+  uint32_t i = 0;
+  bool cut = false; /* casava: the first space was found */
+  for (; i < s; i += 4) {
+    uint32_t next = fq_ld32(d, a + 4); a += 4;
+#if defined(__CUDA_ARCH__)
+    uint32_t w = __funnelshift_r(cur, next, sh);
+#else
+    uint32_t w = sh ? (cur >> sh) | (next << (32u - sh)) : cur;
+#endif
+    cur = next;
+    uint32_t z = fq_zero_bytes(w);
+    if (casava && !cut) z |= fq_zero_bytes(w ^ 0x20202020u);
+    if (s - i < 4) z &= (1u << (8u * (s - i))) - 1u;
+    if (z) {
+      uint32_t k = 0; while (!((z >> (8 * k + 7)) & 1u)) k++;
+      if (((w >> (8 * k)) & 0xFFu) == 0) return false; /* NUL: the careful path's strlen would stop here */
+      /* a space: the name ends here (then a trailing "/x" goes) */
+      uint32_t len = i + k;
+      cut = true;
+      if (len >= 2 && d[ns + len - 2] == '/') { len -= 2; nlen = len; mem_len = len; if (want_hash) h = fq_hash_init(seed); i = 0; break; }
+      nlen = len; mem_len = len;
+      if (want_hash && k) fq_hash_word(&h, w & ((1u << (8u * k)) - 1u));
+      /* the rest of this word and of the line may still hide a NUL */
+      uint32_t z2 = fq_zero_bytes(w) ; if (s - i < 4) z2 &= (1u << (8u * (s - i))) - 1u;
+      if (z2) return false;
+      i += 4;
+      for (; i < s; i += 4) {
+        uint32_t nx = fq_ld32(d, a + 4); a += 4;
+#if defined(__CUDA_ARCH__)
+        uint32_t w2 = __funnelshift_r(cur, nx, sh);
+#else
+        uint32_t w2 = sh ? (cur >> sh) | (nx << (32u - sh)) : cur;
+#endif
+        cur = nx;
+        uint32_t z3 = fq_zero_bytes(w2);
+        if (s - i < 4) z3 &= (1u << (8u * (s - i))) - 1u;
+        if (z3) return false;
+      }
+      *name_len = nlen; *mem_len_out = mem_len;
+      if (want_hash) *hash = fq_hash_fin(h, nlen);
+      return true;
+    }
+    if (want_hash) {
+      if (i + 4 <= nlen) fq_hash_word(&h, w);
+      else if (i < nlen) fq_hash_word(&h, w & ((1u << (8u * (nlen - i))) - 1u));
+    }
+  }
+  if (cut) { /* "/x" in front of the space: hash the shortened name on its own; NULs after the space still matter */
+    for (uint32_t j = (nlen & ~3u); j < s; j += 4) {
+      uint32_t z = fq_zero_bytes(fq_ldu32(d, ns + j));
+      if (s - j < 4) z &= (1u << (8u * (s - j))) - 1u;
+      if (z) return false;
+    }
+    *name_len = nlen; *mem_len_out = mem_len;
+    if (want_hash) *hash = fq_hash_name_words(d, ns, nlen, seed);
+    return true;
+  }
+  if (casava && s >= 2 && d[ns + s - 2] == '/') { /* no space at all: the "/x" rule applies to the end of the line */
+    nlen = s - 2; mem_len = nlen;
+    *name_len = nlen; *mem_len_out = mem_len;
+    if (want_hash) *hash = fq_hash_name_words(d, ns, nlen, seed);
+    return true;
+  }
+  *name_len = nlen; *mem_len_out = mem_len;
+  if (want_hash) *hash = fq_hash_fin(h, nlen);
+  return true;
 }
 
 /* Header line [h0, h0+hl) of the common shape — '@', a name byte, no NUL, LF at the end — → length of the normalised
@@ -465,8 +561,8 @@ FQ_HD bool fq_check_record_fast(const uint8_t* d, const FqLine* L, const FqRecCt
   /* header 2: "+\n" or "+\r\n" */
   if (!(d[p0] == '+' && ((pl == 2 && d[p0 + 1] == '\n') || (pl == 3 && d[p0 + 1] == '\r' && d[p0 + 2] == '\n')))) return false;
   const uint32_t ns = h0 + 1;
-  uint32_t nlen; uint64_t mem_len;
-  if (!fq_header_fast(d, h0, hl, cx.fmt_key, cx.pe_key, &nlen, &mem_len)) return false;
+  uint32_t nlen; uint64_t mem_len, hsh = FQ_HASH_SKIP;
+  if (!fq_header_hash_fast(d, h0, hl, cx.fmt_key, cx.pe_key, cx.seed, cx.loop != FQ_LOOP_SINGLE, &nlen, &mem_len, &hsh)) return false;
   /* sequence */
   if (d[s0 + sl - 1] != '\n') return false;
   uint32_t se = s0 + sl - 1;
@@ -486,7 +582,7 @@ FQ_HD bool fq_check_record_fast(const uint8_t* d, const FqLine* L, const FqRecCt
   if (qmin <= 0x0Du) return false;
   o->flags = 0; o->vrank = FQ_V_OK; o->code = 0; o->read_len = sl; o->slen = slen; o->qlen = qlen;
   o->qmin = qmin; o->qmax = qmax; o->bad = 0; o->name_off = ns; o->name_len = nlen; o->mem_len = mem_len;
-  *hash = cx.loop != FQ_LOOP_SINGLE ? fq_hash_name_words(d, ns, nlen, cx.seed) : FQ_HASH_SKIP;
+  *hash = hsh;
   return true;
 }
 
