@@ -8,6 +8,7 @@
  */
 #include "fq_engine.h"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -236,6 +237,8 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
       uint32_t o[FQ_LANES_OUT_WORDS];
       dev_->download(o, tile_out_, sizeof o);
       bool pass_ok = !o[1] && o[2] == kNone32 && !o[3] && !o[4];
+      if (getenv("FQG_DEBUG")) fprintf(stderr, "[fqg] clean-data pass: n=%u j0=%u lines=%u capovf=%u overlong=%u anomaly=0x%x internal=%u virt=%u q=%u..%u rl=%u..%u recbad=%u\n",
+                                       B.n, j0, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10]);
       if (pass_ok && !o[10]) {
         dev_->lanes_commit(a, false);
         path_counts[0]++;

@@ -29,13 +29,15 @@ constexpr int LN_THREADS = 256, LN_WARPS = LN_THREADS / 32;
 constexpr int LN_TILE = 32768, LN_CHUNKS = LN_TILE / 16, LN_CPT = LN_CHUNKS / LN_THREADS; /* 8 chunks per thread */
 constexpr int LN_LEFT = 16, LN_MARGIN = 1024, LN_WIN = LN_LEFT + LN_TILE + LN_MARGIN;
 constexpr int LN_LMAX = 2048;                 /* line ends kept per tile */
+constexpr int LN_SMAX = 256;                  /* header lines (name descriptors) staged per tile */
 constexpr int LN_OFF_MASK = LN_WIN;
-constexpr int LN_OFF_LEND = LN_OFF_MASK + LN_CHUNKS * 2;
-constexpr int LN_OFF_PURE = LN_OFF_LEND + LN_LMAX * 2;
-constexpr int LN_OFF_LUT = LN_OFF_PURE + LN_CHUNKS * 2;
+constexpr int LN_OFF_PURE = LN_OFF_MASK + LN_CHUNKS * 2;
+constexpr int LN_OFF_LEND = LN_OFF_PURE + LN_CHUNKS * 2;      /* two buffers: the line ends of a tile are written out one round later */
+constexpr int LN_OFF_STAGE = LN_OFF_LEND + 2 * LN_LMAX * 2;
+constexpr int LN_OFF_LUT = LN_OFF_STAGE + LN_SMAX * 16;
 constexpr int LN_SMEM = LN_OFF_LUT + 32 * 16;
 static_assert(LN_CPT == 8, "a thread's masks are one 16-byte load");
-static_assert(LN_WIN % 16 == 0 && LN_OFF_LEND % 16 == 0 && LN_OFF_PURE % 16 == 0 && LN_OFF_LUT % 16 == 0, "alignment");
+static_assert(LN_WIN % 16 == 0 && LN_OFF_LEND % 16 == 0 && LN_OFF_PURE % 16 == 0 && LN_OFF_STAGE % 16 == 0 && LN_OFF_LUT % 16 == 0, "alignment");
 
 /* anomaly bits (out[3]) */
 enum { LN_A_BASE = 1, LN_A_QUAL = 2, LN_A_HEADER = 4, LN_A_PLUS = 8, LN_A_CAPACITY = 16, LN_A_PHASE = 32 };
@@ -75,20 +77,9 @@ __device__ __forceinline__ void ln_minmax_word(uint32_t w, uint32_t& mn, uint32_
   mx = __vmaxu2(mx, __vmaxu2(ev, od));
 }
 
-/* One round of the block-wide look-back: every thread holds the state of one predecessor tile (tile-1-tid, ...); returns true
- * when an inclusive count was among them.  *sum accumulates the counts between that tile and ours.  Contains a barrier. */
-__device__ __forceinline__ bool ln_lookback_round(unsigned long long v64, int lane, int warp, uint32_t* s_sum, uint32_t* s_has, uint32_t* sum) {
-  const uint32_t incl_mask = __ballot_sync(FULL, (v64 >> 62) == 2);
-  const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
-  uint32_t part = lane <= first ? (uint32_t)(v64 & ST_VALUE) : 0u;
-  part = __reduce_add_sync(FULL, part);
-  if (lane == 0) { s_sum[warp] = part; s_has[warp] = incl_mask ? 1u : 0u; }
-  __syncthreads();
-  bool found = false;
-#pragma unroll
-  for (int w = 0; w < LN_WARPS; w++) if (!found) { *sum += s_sum[w]; found = s_has[w] != 0; }
-  return found;
-}
+/* Block-wide look-back: the number of lines in front of `tile` = the counts of the tiles before it, summed back to the nearest
+ * one whose inclusive count is known.  Every thread reads the states of four predecessors per round (1024 per round: hundreds of
+ * tiles are in flight under persistent CTAs, and a round costs an L2 round trip plus a barrier).  Uniform over the block. */
 __device__ __forceinline__ unsigned long long ln_wait_state(const unsigned long long* p, uint32_t* out) {
   unsigned long long v64;
   uint32_t spins = 0;
@@ -96,24 +87,48 @@ __device__ __forceinline__ unsigned long long ln_wait_state(const unsigned long 
     if (++spins > (1u << 24)) { atomicExch(out + LN_O_INTERNAL, 2u); return ST_INCL; }
   return v64;
 }
+__device__ __forceinline__ uint32_t ln_lookback(const unsigned long long* tile_state, uint32_t tile, int tid, int lane, int warp,
+                                                uint32_t* s_sum, uint32_t* s_has, uint32_t* out) {
+  uint32_t base = 0;
+  for (int look = (int)tile - 1;; look -= 4 * LN_THREADS) {
+    uint32_t part = 0; bool has = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { /* nearest first */
+      const int idx = look - 4 * tid - j;
+      const unsigned long long v64 = idx >= 0 ? ln_wait_state(tile_state + idx, out) : ST_INCL;
+      if (!has) { part += (uint32_t)(v64 & ST_VALUE); has = (v64 >> 62) == 2; }
+    }
+    const uint32_t incl_mask = __ballot_sync(FULL, has);
+    const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+    part = __reduce_add_sync(FULL, lane <= first ? part : 0u);
+    if (lane == 0) { s_sum[warp] = part; s_has[warp] = incl_mask ? 1u : 0u; }
+    __syncthreads();
+    bool found = false;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; w++) if (!found) { base += s_sum[w]; found = s_has[w] != 0; }
+    if (found) break;
+    __syncthreads(); /* s_sum / s_has are rewritten by the next round */
+  }
+  return base;
+}
 
 __global__ void __launch_bounds__(LN_THREADS, 4)
 fq_lanes_kernel(const LanesParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* win = smem;
   uint16_t* maskbuf = (uint16_t*)(smem + LN_OFF_MASK);
-  uint16_t* lend = (uint16_t*)(smem + LN_OFF_LEND);
   uint16_t* pure = (uint16_t*)(smem + LN_OFF_PURE);   /* whole chunks, one region of 256 entries per warp: sequence from its front, quality from its back */
+  uint16_t* lend2 = (uint16_t*)(smem + LN_OFF_LEND);  /* line ends (window offsets), [2][LN_LMAX] */
+  FqName* stage = (FqName*)(smem + LN_OFF_STAGE);     /* name descriptors of the tile's header lines, written out one round later */
   uint4* lut = (uint4*)(smem + LN_OFF_LUT);           /* [lo] bytes >= lo, [16 + h] bytes <= h */
   __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ uint32_t s_next, s_guess, s_w1[LN_WARPS], s_w3[LN_WARPS], s_w4[LN_WARPS];
+  __shared__ uint32_t s_next, s_w1[LN_WARPS], s_w3[LN_WARPS], s_w4[LN_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = smem_u32(&s_bar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_next = atomicAdd(P.ticket, 1u);
-    s_guess = 0;
   }
   if (tid < 32) {
     uint32_t w[4];
@@ -129,17 +144,20 @@ fq_lanes_kernel(const LanesParams P) {
     }
     lut[tid] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  uint32_t parity = 0;
+  uint32_t parity = 0, buf = 0;
   uint32_t seq_ok = 0x80808080u;           /* AND of the alphabet predicate over everything this thread checked */
   uint32_t qmn = 0x00FF00FFu, qmx = 0u;    /* quality minimum / maximum, two 16-bit lanes */
   uint32_t anomaly = 0;
+  /* the tile of the previous round: its line ends and names still wait for the number of lines in front of it */
+  bool pend = false, p_have_base = false, p_no_final_lf = false;
+  uint32_t p_tile = 0, p_cnt = 0, p_phi = 0, p_base = 0, p_nstage = 0, p_rl0 = 0;
 
   for (;;) {
     __syncthreads(); /* everyone is done with the previous window and lists; s_next holds the tile claimed for this round */
     const uint32_t tile = s_next;
-    if (tile >= P.ntiles) break;
+    const bool active = tile < P.ntiles;
     const unsigned long long t0 = (unsigned long long)tile * LN_TILE;
-    if (tid == 0) {
+    if (active && tid == 0) {
       unsigned long long src = tile ? t0 - LN_LEFT : 0;
       uint32_t dst_off = tile ? 0 : LN_LEFT;
       unsigned long long want = (unsigned long long)LN_WIN - dst_off, have = ((unsigned long long)P.n - src + 15) & ~15ull;
@@ -147,12 +165,45 @@ fq_lanes_kernel(const LanesParams P) {
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(smem_u32(win + dst_off)), "l"(P.data + src), "r"(bytes), "r"(bar) : "memory");
-      s_guess = 0;
     }
+
+    /* ---- F: while the bulk copy is in flight, finish the previous tile: lines in front of it (its predecessors published their
+     * counts a whole round ago), the check of the line class we assumed, line ends and names → global memory */
+    if (pend) {
+      uint32_t base = p_base;
+      if (!p_have_base) {
+        base = ln_lookback(P.tile_state, p_tile, tid, lane, warp, s_w3, s_w4, P.out);
+        if (((base + 4u - P.j0) & 3u) != p_phi) anomaly |= LN_A_PHASE; /* the plus lines of the tile misled us: hand the chunk on */
+        if (tid == 0) st_volatile64(P.tile_state + p_tile, ST_INCL | ((unsigned long long)base + p_cnt));
+      }
+      if (tid == 0 && p_tile == P.ntiles - 1) {
+        uint32_t cnt = base + p_cnt;
+        if (p_no_final_lf) { if (cnt < P.cap) P.line_end[cnt] = P.n; P.out[LN_O_VIRTUAL] = cnt; cnt++; }
+        P.out[LN_O_LINES] = cnt; P.out[LN_O_CAPOVF] = cnt > P.cap ? 1u : 0u;
+      }
+      const uint16_t* pl = lend2 + (buf ^ 1u) * LN_LMAX;
+      const uint32_t gofs = (uint32_t)((unsigned long long)p_tile * LN_TILE - LN_LEFT); /* window offset → offset inside the chunk */
+      if (p_cnt <= (uint32_t)LN_LMAX)
+        for (uint32_t r = tid; r < p_cnt; r += LN_THREADS) { const uint32_t gi = base + r; if (gi < P.cap) P.line_end[gi] = gofs + pl[r]; }
+      if (P.names) {
+        /* record of a staged name: its number inside the tile plus the records in front of the tile; names of the record cut
+         * by the start of the chunk (lines before j0) get a negative number and are dropped */
+        const uint32_t rec0 = p_rl0 + ((base + 4u - P.j0) >> 2) - 2u;
+        for (uint32_t u = tid; u < p_nstage; u += LN_THREADS) {
+          const FqName nm = stage[u];
+          const uint32_t rec = rec0 + u;
+          if (nm.len != 0xFFFFFFFFu && rec < P.names_cap) P.names[rec] = nm;
+        }
+      }
+      pend = false;
+    }
+    if (!active) break;
+
     const uint32_t left = (uint32_t)min((unsigned long long)(LN_TILE + LN_MARGIN), (unsigned long long)P.n - t0); /* data bytes from the tile start */
     const uint32_t nv = min(left, (uint32_t)LN_TILE);   /* valid bytes of the tile itself */
     const uint32_t nloc = LN_LEFT + left;               /* window offsets below this hold data */
     const bool full = nv == (uint32_t)LN_TILE;
+    uint16_t* lend = lend2 + buf * LN_LMAX;
     {
       uint32_t spins = 0;
       while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) { if (tid == 0) atomicExch(P.out + LN_O_INTERNAL, 1u); break; } }
@@ -184,7 +235,7 @@ fq_lanes_kernel(const LanesParams P) {
       tot = h + n45 + n67;
     }
 
-    /* ---- B: prefix of the LF counts inside the tile; this tile's count is published for the tiles behind us */
+    /* ---- B: prefix of the LF counts inside the tile; the tile's count is published for the tiles behind us; line ends */
     uint32_t incl = tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += a; }
@@ -193,43 +244,45 @@ fq_lanes_kernel(const LanesParams P) {
     uint32_t excl = incl - tot, cntT = 0;
 #pragma unroll
     for (int w = 0; w < LN_WARPS; w++) { uint32_t x = s_w1[w]; cntT += x; if (w < warp) excl += x; }
-    if (tid == 0 && tile > 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
-    /* line ends of this thread's LFs: window offsets, in order (needs only the rank inside the tile).  On the way: every
-     * "\n+\n" says that the line ending at its second LF is a plus line, i.e. proposes the line class of the tile's first byte. */
+    if (tid == 0) {
+      if (tile > 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
+      s_next = atomicAdd(P.ticket, 1u); /* read after the barrier at the top of the next round */
+    }
     const uint32_t c0 = LN_CPT * tid;
     const bool too_many = cntT > (uint32_t)LN_LMAX;
     if (too_many) anomaly |= LN_A_CAPACITY;
-    else {
-      uint32_t rank = excl, prop = 0;
+    else { /* window offsets of this thread's line ends, in order: the first two LFs of a 32-byte span without a branch */
+      uint32_t rank = excl;
       const uint32_t e0 = LN_LEFT + 16 * c0 + 1;
-/* the first two LFs of a 32-byte span without a branch, a loop for the rare rest */
-#define LN_EMIT1(w_, h_) { const uint32_t b = __ffs(w) - 1; const uint32_t e = e0 + 32 * (h_) + b; \
-        if (w) { lend[rank] = (uint16_t)e; if (((w_) >> b) & 4u) { if (win[e] == '+') prop |= 1u << ((1u - rank) & 3u); } rank++; } w &= w - 1; }
-#define LN_EMIT(w_, h_) { uint32_t w = (w_); LN_EMIT1(w_, h_) LN_EMIT1(w_, h_) while (w) LN_EMIT1(w_, h_) }
+#define LN_EMIT1(h_) { const uint32_t b = __ffs(w) - 1; if (w) lend[rank] = (uint16_t)(e0 + 32 * (h_) + b); rank += w ? 1u : 0u; w &= w - 1; }
+#define LN_EMIT(w_, h_) { uint32_t w = (w_); LN_EMIT1(h_) LN_EMIT1(h_) while (w) LN_EMIT1(h_) }
       LN_EMIT(mm.x, 0) LN_EMIT(mm.y, 1) LN_EMIT(mm.z, 2) LN_EMIT(mm.w, 3)
-#undef LN_EMIT1
 #undef LN_EMIT
-      prop = __reduce_or_sync(FULL, prop);
-      if (lane == 0 && prop) atomicOr(&s_guess, prop);
+#undef LN_EMIT1
     }
     __syncthreads();
 
-    /* ---- C0: line class of the tile's first byte.  The true value needs the number of lines in front of the tile (the sum of
-     * the counts of all tiles before ours); when the plus lines of the tile agree on it we go on with their answer and check it
-     * against the sum at the end of the tile, when the tiles in front have long published theirs. */
-    uint32_t base_line = 0;
+    /* ---- C0: line class of the tile's first byte.  The true value needs the number of lines in front of the tile; that sum is
+     * looked up one round later (F), when the tiles in front have long published their counts.  Until then the tile's own lines
+     * answer: a line that is exactly "+\n" is a plus line.  All such lines among the first 32 must agree, or we wait for the sum. */
+    uint32_t phi = 0, base_line = 0;
     bool have_base = false;
-    uint32_t phi;
     {
-      const uint32_t g = s_guess;
-      if (g == 1u || g == 2u || g == 4u || g == 8u) phi = 31u - __clz(g);
-      else { /* no witness (or witnesses that disagree): wait for the sum now */
-        for (int look = (int)tile - 1;; look -= LN_THREADS) { /* trip count is uniform over the block */
-          const int idx = look - tid;
-          const unsigned long long v64 = idx >= 0 ? ln_wait_state(P.tile_state + idx, P.out) : ST_INCL;
-          if (ln_lookback_round(v64, lane, warp, s_w3, s_w4, &base_line)) break;
-          __syncthreads(); /* s_w3 / s_w4 are rewritten by the next round */
-        }
+      const uint32_t k = lane + 1; /* line k of the tile starts at lend[k-1] */
+      bool plus = false;
+      if (!too_many && k < cntT) { const uint32_t s = lend[k - 1], e = lend[k]; plus = e - s == 2u && win[s] == '+'; }
+      const uint32_t pm = __ballot_sync(FULL, plus);
+      /* line k is a plus line ⇒ class of the tile's first line = (2 - k) & 3; bit (k-1) of pm ↔ line k */
+      const uint32_t w0 = pm & 0x11111111u, w1 = pm & 0x22222222u, w2 = pm & 0x44444444u, w3 = pm & 0x88888888u;
+      const uint32_t votes = (w0 ? 1u : 0u) + (w1 ? 1u : 0u) + (w2 ? 1u : 0u) + (w3 ? 1u : 0u);
+      if (tile == 0) { /* nothing in front of the first tile */
+        if (tid == 0) st_volatile64(P.tile_state, ST_INCL | (unsigned long long)cntT);
+        have_base = true;
+        phi = (4u - P.j0) & 3u;
+      } else if (votes == 1u) phi = w0 ? 1u : w1 ? 0u : w2 ? 3u : 2u; /* k = 1, 5, .. → 1;  k = 2, 6, .. → 0;  k = 3, .. → 3;  k = 4, .. → 2 */
+      else { /* no witness (long lines, or plus lines that repeat the name), or witnesses that disagree: wait for the sum now */
+        base_line = ln_lookback(P.tile_state, tile, tid, lane, warp, s_w3, s_w4, P.out);
+        if (tid == 0) st_volatile64(P.tile_state + tile, ST_INCL | ((unsigned long long)base_line + cntT));
         have_base = true;
         phi = (base_line + 4u - P.j0) & 3u;
       }
@@ -267,11 +320,7 @@ fq_lanes_kernel(const LanesParams P) {
                      : "+r"(as), "+r"(aq) : "r"(is_seq & (1u << i)), "r"(is_qual & (1u << i)), "h"((uint16_t)(c0 + i)) : "memory");
       }
     }
-
-    /* the state of one tile in front of ours, asked for now and looked at after D */
-    unsigned long long pre64 = ST_INCL;
-    if (!have_base && (int)tile - 1 - tid >= 0) pre64 = ld_volatile64(P.tile_state + ((int)tile - 1 - tid));
-    __syncthreads();
+    __syncwarp();
 
     if (!too_many) {
       /* ---- D: sequence alphabet, quality range; one predicate per warp instruction.
@@ -326,51 +375,25 @@ fq_lanes_kernel(const LanesParams P) {
           else if (cls == 3u) { ln_minmax_word(ch * 0x01010101u, qmn, qmx); }
         }
       }
-    }
 
-    /* ---- E0: lines in front of the tile (block-wide look-back, normally one round over states read before D) */
-    if (!have_base) {
-      bool first_round = true;
-      for (int look = (int)tile - 1;; look -= LN_THREADS) {
-        const int idx = look - tid;
-        unsigned long long v64 = ST_INCL;
-        if (idx >= 0) v64 = (first_round && (pre64 >> 62) != 0) ? pre64 : ln_wait_state(P.tile_state + idx, P.out);
-        first_round = false;
-        if (ln_lookback_round(v64, lane, warp, s_w3, s_w4, &base_line)) break;
-        __syncthreads();
-      }
-      if (((base_line + 4u - P.j0) & 3u) != phi) anomaly |= LN_A_PHASE; /* the plus lines of the tile misled us: hand the chunk on */
-    }
-    if (tid == 0) {
-      st_volatile64(P.tile_state + tile, ST_INCL | ((unsigned long long)base_line + cntT));
-      s_next = atomicAdd(P.ticket, 1u);
-      if (tile == P.ntiles - 1) {
-        uint32_t cnt = base_line + cntT;
-        if (P.virtual_end && P.n > 0 && win[nloc - 1] != '\n') { if (cnt < P.cap) P.line_end[cnt] = P.n; P.out[LN_O_VIRTUAL] = cnt; cnt++; }
-        P.out[LN_O_LINES] = cnt; P.out[LN_O_CAPOVF] = cnt > P.cap ? 1u : 0u;
-      }
-    }
-    if (!too_many) {
-      /* line numbers shifted so that the chunk's first record starts at line 4: class = number & 3, record = (number >> 2) - 1 (j0 <= 4) */
-      const uint32_t gb = base_line + 4u - P.j0;
-      const uint32_t gofs = (uint32_t)(t0 - LN_LEFT); /* window offset → offset inside the chunk */
-      /* ---- E1: line ends → global line index */
-      for (uint32_t r = tid; r < cntT; r += LN_THREADS) { const uint32_t gi = base_line + r; if (gi < P.cap) P.line_end[gi] = gofs + lend[r]; }
-
-      /* ---- E2: header and plus lines that start in this tile.  Line k of the tile (0..cntT) starts at lend[k-1]. */
+      /* ---- E: header and plus lines that start in this tile.  Line k of the tile (0..cntT) starts at lend[k-1].  Names are staged
+       * in shared memory under their number inside the tile and written out next round (F). */
       {
         const uint32_t kmin = win[LN_LEFT - 1] == '\n' ? 0u : 1u;
         const uint32_t tile_end = LN_LEFT + nv; /* lines starting at or beyond belong to the next tile (or do not exist) */
-        uint32_t kh0 = kmin + ((0u - (gb + kmin)) & 3u);
-        if (gb + kh0 < 4u) kh0 += 4;
-        uint32_t kp0 = kmin + ((2u - (gb + kmin)) & 3u);
-        if (gb + kp0 < 4u) kp0 += 4;
-        const uint32_t nH = kh0 <= cntT ? (cntT - kh0) / 4 + 1 : 0, nP = kp0 <= cntT ? (cntT - kp0) / 4 + 1 : 0;
+        const uint32_t gofs = (uint32_t)(t0 - LN_LEFT);
+        const uint32_t kh0 = kmin + ((0u - (gbr + kmin)) & 3u), kp0 = kmin + ((2u - (gbr + kmin)) & 3u);
+        uint32_t nH = kh0 <= cntT ? (cntT - kh0) / 4 + 1 : 0;
+        const uint32_t nP = kp0 <= cntT ? (cntT - kp0) / 4 + 1 : 0;
+        if (nH > (uint32_t)LN_SMAX) { anomaly |= LN_A_CAPACITY; nH = 0; }
+        p_nstage = nH; p_rl0 = (gbr + kh0) >> 2;
         for (uint32_t u = tid; u < nH + nP; u += LN_THREADS) {
           const bool is_hdr = u < nH;
           const uint32_t k = is_hdr ? kh0 + 4 * u : kp0 + 4 * (u - nH);
           const uint32_t s = k == 0 ? (uint32_t)LN_LEFT : (uint32_t)lend[k - 1];
+          if (is_hdr) stage[u].len = 0xFFFFFFFFu; /* nothing to write out unless the header is judged below */
           if (s >= tile_end) continue;
+          if (tile == 0 && k < P.j0) continue; /* lines of the record cut by the start of the chunk: judged with their record */
           if (!is_hdr) { /* "+\n" */
             if (s + 1 >= nloc) continue; /* cut by the end of the data: the record is completed (or judged) elsewhere */
             if (!(win[s] == '+' && win[s + 1] == '\n')) anomaly |= LN_A_PLUS;
@@ -382,22 +405,22 @@ fq_lanes_kernel(const LanesParams P) {
             uint32_t p = LN_LEFT + nv;
             for (; p < nloc; p++) if (win[p] == '\n') { e = p + 1; break; }
             if (!e) {
-              if (nloc == (uint32_t)LN_WIN) atomicMin(P.out + LN_O_OVERLONG, base_line + k); /* no LF within 1 KiB: a line gzgets would split */
+              if (nloc == (uint32_t)LN_WIN) atomicMin(P.out + LN_O_OVERLONG, tile); /* no LF within 1 KiB: a line gzgets would split */
               continue; /* otherwise cut by the end of the data */
             }
           }
           const uint32_t hl = e - s;
-          if (hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, base_line + k); continue; }
+          if (hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, tile); continue; }
           uint32_t nlen; uint64_t mem_len, hsh = FQ_HASH_SKIP;
           if (!fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; continue; }
-          const uint32_t rec = ((gb + k) >> 2) - 1u;
-          if (P.names && rec < P.names_cap) {
-            FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
-            P.names[rec] = nm;
-          }
+          FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
+          stage[u] = nm;
         }
       }
-    }
+    } else { p_nstage = 0; p_rl0 = 0; }
+    pend = true; p_tile = tile; p_cnt = cntT; p_phi = phi; p_have_base = have_base; p_base = base_line;
+    p_no_final_lf = P.virtual_end && tile == P.ntiles - 1 && P.n > 0 && win[nloc - 1] != '\n';
+    buf ^= 1u;
   }
 
   /* ---- results of this thread → one set of atomics per warp */
