@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -905,12 +906,18 @@ class FqCudaDevice : public FqDevice {
   bool lanes_pass(const FqTileArgs& a) override {
     if (!a.n) return false;
     if ((uintptr_t)a.data & 15u) return false; /* bulk copies need a 16-byte aligned source (the engine aligns what it is fed) */
-    uint32_t ntiles = (a.n + LN_TILE - 1) / LN_TILE;
+    /* short lines (they must end within the 1 KiB margin): one thread per line; anything longer: chunk-parallel */
+    const bool lines_mode = a.hint_line_len > 0 && a.hint_line_len <= 512 && !getenv("FQG_NO_LINES");
+    const uint32_t tile_bytes = lines_mode ? LS_TILE : LN_TILE;
+    uint32_t ntiles = (a.n + tile_bytes - 1) / tile_bytes;
     if (ntiles > max_tiles_) return false;
     if (lanes_blocks_ == 0) {
-      FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
-      int per_sm = 0;
-      FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fq_lanes_kernel, LN_THREADS, LN_SMEM));
+      FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+      FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+      int per_sm = 0, per_sm2 = 0;
+      FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fq_lanes_kernel<false>, LN_THREADS, LN_SMEM));
+      FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, fq_lanes_kernel<true>, LN_THREADS, LN_SMEM));
+      per_sm = std::min(per_sm, per_sm2);
       if (per_sm < 1) return false;
       lanes_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
     }
@@ -922,7 +929,8 @@ class FqCudaDevice : public FqDevice {
     FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
     int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)lanes_blocks_);
     tic(FQG_K_LANES, a.n, ntiles);
-    fq_lanes_kernel<<<grid, LN_THREADS, LN_SMEM, st_>>>(P);
+    if (lines_mode) fq_lanes_kernel<true><<<grid, LN_THREADS, LN_SMEM, st_>>>(P);
+    else fq_lanes_kernel<false><<<grid, LN_THREADS, LN_SMEM, st_>>>(P);
     toc(); launched();
     lanes_records(a, false);
     return true;

@@ -70,6 +70,7 @@ typedef struct {
   uint32_t* out5;            /* device: lines, cap overflow, first over-long header line (init ~0), records that did not fit, internal error */
   uint32_t j0; uint32_t max_rec; uint64_t g0; uint64_t step_base; FqRecCtx cx;
   FqStats* stats; FqStats* stats_range; unsigned long long* hist; unsigned long long* key; FqName* names; uint32_t names_cap;
+  uint32_t hint_line_len;    /* length of the file's first sequence line (0 = unknown): picks the clean-data pass's mode */
 } FqTileArgs;
 
 #define FQ_LANES_OUT_WORDS 12

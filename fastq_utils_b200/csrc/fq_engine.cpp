@@ -201,6 +201,7 @@ bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip
       dev_->sniff(data, h, q, (int32_t*)scratch_);
       int32_t o2[2]; dev_->download(o2, scratch_, sizeof o2);
       F.sniff_fmt = o2[0]; F.sniff_color = o2[1];
+      F.first_seq_len = q.len;
       ok = true;
     }
   }
@@ -228,6 +229,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   a.j0 = j0; a.max_rec = kNone32; a.g0 = g0_local + F.g_base; a.step_base = step_base(file); a.cx = make_ctx(file);
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
   a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; a.key = key_; a.names = names; a.names_cap = ncap;
+  a.hint_line_len = F.first_seq_len;
   /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
    * below decide (they own the reference's first-error semantics). */
   if (lanes_ok_ && a.cx.space != FQ_SPACE_COLOR) {

@@ -47,6 +47,7 @@ struct FqFile {
   std::vector<uint8_t> tail;
   std::vector<FqTailLine> tail_lines;
   int sniff_fmt = -1, sniff_color = -1;
+  uint32_t first_seq_len = 0; /* raw length of the first record's sequence line (0: not seen by this context) */
   FqStats* stats = nullptr; unsigned long long* hist = nullptr; /* device */
   FqDirEntry* dir_dev = nullptr; size_t dir_cap = 0; std::vector<FqDirEntry> dir_host; size_t dir_synced = 0;
   uint64_t limit = ~0ull;   /* records at or beyond this index are never read (early clean end of file) */

@@ -28,6 +28,8 @@
 constexpr int LN_THREADS = 256, LN_WARPS = LN_THREADS / 32;
 constexpr int LN_TILE = 32768, LN_CHUNKS = LN_TILE / 16, LN_CPT = LN_CHUNKS / LN_THREADS; /* 8 chunks per thread */
 constexpr int LN_LEFT = 16, LN_MARGIN = 1024, LN_WIN = LN_LEFT + LN_TILE + LN_MARGIN;
+/* per-line mode: the LF scan covers tile + margin (a line is judged by the tile it starts in, whole), so the tile is a margin shorter */
+constexpr int LS_TILE = LN_TILE - LN_MARGIN, LS_TILE_CHUNKS = LS_TILE / 16;
 constexpr int LN_LMAX = 2048;                 /* line ends kept per tile */
 constexpr int LN_SMAX = 256;                  /* header lines (name descriptors) staged per tile */
 constexpr int LN_OFF_MASK = LN_WIN;
@@ -37,6 +39,7 @@ constexpr int LN_OFF_STAGE = LN_OFF_LEND + 2 * LN_LMAX * 2;
 constexpr int LN_OFF_LUT = LN_OFF_STAGE + LN_SMAX * 16;
 constexpr int LN_SMEM = LN_OFF_LUT + 32 * 16;
 static_assert(LN_CPT == 8, "a thread's masks are one 16-byte load");
+static_assert(LN_SMAX <= LN_THREADS, "one staged name per thread");
 static_assert(LN_WIN % 16 == 0 && LN_OFF_LEND % 16 == 0 && LN_OFF_PURE % 16 == 0 && LN_OFF_STAGE % 16 == 0 && LN_OFF_LUT % 16 == 0, "alignment");
 
 /* anomaly bits (out[3]) */
@@ -77,6 +80,44 @@ __device__ __forceinline__ void ln_minmax_word(uint32_t w, uint32_t& mn, uint32_
   mx = __vmaxu2(mx, __vmaxu2(ev, od));
 }
 
+/* per-line mode: every byte of [s, e) (window offsets, e > s) is ACGTN / acgtn → bit 7 of every byte of the result stays set */
+__device__ __forceinline__ uint32_t ls_seq_line(const uint8_t* win, const uint4* lut, uint32_t s, uint32_t e) {
+  uint32_t a = s & ~15u;
+  const uint32_t alast = (e - 1u) & ~15u;
+  uint4 m = lut[s & 15u];
+  if (a == alast) { const uint4 h = lut[15u + (e - a)]; m.x &= h.x; m.y &= h.y; m.z &= h.z; m.w &= h.w; }
+  uint4 v = *(const uint4*)(win + a);
+  uint32_t ok = (fq_base_pred(v.x) | ~m.x) & (fq_base_pred(v.y) | ~m.y) & (fq_base_pred(v.z) | ~m.z) & (fq_base_pred(v.w) | ~m.w);
+  if (a != alast) {
+    for (a += 16; a < alast; a += 16) ok &= ln_pred4(*(const uint4*)(win + a));
+    m = lut[15u + (e - alast)];
+    v = *(const uint4*)(win + alast);
+    ok &= (fq_base_pred(v.x) | ~m.x) & (fq_base_pred(v.y) | ~m.y) & (fq_base_pred(v.z) | ~m.z) & (fq_base_pred(v.w) | ~m.w);
+  }
+  return ok;
+}
+/* per-line mode: unsigned minimum / maximum over the bytes of [s, e) folded into two 16-bit lanes each */
+__device__ __forceinline__ void ls_qual_line(const uint8_t* win, const uint4* lut, uint32_t s, uint32_t e, uint32_t& mn, uint32_t& mx) {
+  uint32_t a = s & ~15u;
+  const uint32_t alast = (e - 1u) & ~15u;
+  const uint32_t fill = (uint32_t)win[s] * 0x01010101u; /* a byte of the line stands in for the bytes outside it */
+  uint4 m = lut[s & 15u];
+  if (a == alast) { const uint4 h = lut[15u + (e - a)]; m.x &= h.x; m.y &= h.y; m.z &= h.z; m.w &= h.w; }
+  uint4 v = *(const uint4*)(win + a);
+  ln_minmax_word((v.x & m.x) | (fill & ~m.x), mn, mx); ln_minmax_word((v.y & m.y) | (fill & ~m.y), mn, mx);
+  ln_minmax_word((v.z & m.z) | (fill & ~m.z), mn, mx); ln_minmax_word((v.w & m.w) | (fill & ~m.w), mn, mx);
+  if (a != alast) {
+    for (a += 16; a < alast; a += 16) {
+      v = *(const uint4*)(win + a);
+      ln_minmax_word(v.x, mn, mx); ln_minmax_word(v.y, mn, mx); ln_minmax_word(v.z, mn, mx); ln_minmax_word(v.w, mn, mx);
+    }
+    m = lut[15u + (e - alast)];
+    v = *(const uint4*)(win + alast);
+    ln_minmax_word((v.x & m.x) | (fill & ~m.x), mn, mx); ln_minmax_word((v.y & m.y) | (fill & ~m.y), mn, mx);
+    ln_minmax_word((v.z & m.z) | (fill & ~m.z), mn, mx); ln_minmax_word((v.w & m.w) | (fill & ~m.w), mn, mx);
+  }
+}
+
 /* Block-wide look-back: the number of lines in front of `tile` = the counts of the tiles before it, summed back to the nearest
  * one whose inclusive count is known.  Every thread reads the states of four predecessors per round (1024 per round: hundreds of
  * tiles are in flight under persistent CTAs, and a round costs an L2 round trip plus a barrier).  Uniform over the block. */
@@ -112,8 +153,13 @@ __device__ __forceinline__ uint32_t ln_lookback(const unsigned long long* tile_s
   return base;
 }
 
+/* LINES = false: chunk-parallel everywhere (lines of any length).  LINES = true: one thread per line for the bulk scans, warps of
+ * one line class each — a third of the instructions when lines are short (they must end within the margin: < 1 KiB). */
+template <bool LINES>
 __global__ void __launch_bounds__(LN_THREADS, 4)
 fq_lanes_kernel(const LanesParams P) {
+  constexpr int TILE = LINES ? LS_TILE : LN_TILE;          /* bytes a tile owns */
+  constexpr int SCAN = LN_TILE;                            /* bytes whose LFs are flagged: the tile, and in per-line mode the margin too */
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* win = smem;
   uint16_t* maskbuf = (uint16_t*)(smem + LN_OFF_MASK);
@@ -156,22 +202,26 @@ fq_lanes_kernel(const LanesParams P) {
     __syncthreads(); /* everyone is done with the previous window and lists; s_next holds the tile claimed for this round */
     const uint32_t tile = s_next;
     const bool active = tile < P.ntiles;
-    const unsigned long long t0 = (unsigned long long)tile * LN_TILE;
+    const unsigned long long t0 = (unsigned long long)tile * TILE;
     if (active && tid == 0) {
       unsigned long long src = tile ? t0 - LN_LEFT : 0;
       uint32_t dst_off = tile ? 0 : LN_LEFT;
-      unsigned long long want = (unsigned long long)LN_WIN - dst_off, have = ((unsigned long long)P.n - src + 15) & ~15ull;
+      unsigned long long want = (unsigned long long)(LN_LEFT + TILE + LN_MARGIN) - dst_off, have = ((unsigned long long)P.n - src + 15) & ~15ull;
       uint32_t bytes = (uint32_t)(want < have ? want : have);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(smem_u32(win + dst_off)), "l"(P.data + src), "r"(bytes), "r"(bar) : "memory");
     }
 
-    /* ---- F: while the bulk copy is in flight, finish the previous tile: lines in front of it (its predecessors published their
-     * counts a whole round ago), the check of the line class we assumed, line ends and names → global memory */
-    if (pend) {
+    /* ---- F: finish the previous tile: lines in front of it (its predecessors published their counts a round ago, and nothing that
+     * can wait runs before a tile publishes its own), the check of the line class we assumed, line ends and names → global memory */
+    auto finish_previous = [&]() {
       uint32_t base = p_base;
-      if (!p_have_base) {
+      /* the staged name this thread writes out: taken before the barrier below, after which this round may stage its own */
+      FqName my_nm; my_nm.len = 0xFFFFFFFFu; my_nm.off = 0; my_nm.hash = 0;
+      if ((uint32_t)tid < p_nstage) my_nm = stage[tid];
+      if (p_have_base) __syncthreads();
+      else {
         base = ln_lookback(P.tile_state, p_tile, tid, lane, warp, s_w3, s_w4, P.out);
         if (((base + 4u - P.j0) & 3u) != p_phi) anomaly |= LN_A_PHASE; /* the plus lines of the tile misled us: hand the chunk on */
         if (tid == 0) st_volatile64(P.tile_state + p_tile, ST_INCL | ((unsigned long long)base + p_cnt));
@@ -182,27 +232,25 @@ fq_lanes_kernel(const LanesParams P) {
         P.out[LN_O_LINES] = cnt; P.out[LN_O_CAPOVF] = cnt > P.cap ? 1u : 0u;
       }
       const uint16_t* pl = lend2 + (buf ^ 1u) * LN_LMAX;
-      const uint32_t gofs = (uint32_t)((unsigned long long)p_tile * LN_TILE - LN_LEFT); /* window offset → offset inside the chunk */
+      const uint32_t gofs = (uint32_t)((unsigned long long)p_tile * TILE - LN_LEFT); /* window offset → offset inside the chunk */
       if (p_cnt <= (uint32_t)LN_LMAX)
         for (uint32_t r = tid; r < p_cnt; r += LN_THREADS) { const uint32_t gi = base + r; if (gi < P.cap) P.line_end[gi] = gofs + pl[r]; }
       if (P.names) {
         /* record of a staged name: its number inside the tile plus the records in front of the tile; names of the record cut
          * by the start of the chunk (lines before j0) get a negative number and are dropped */
         const uint32_t rec0 = p_rl0 + ((base + 4u - P.j0) >> 2) - 2u;
-        for (uint32_t u = tid; u < p_nstage; u += LN_THREADS) {
-          const FqName nm = stage[u];
-          const uint32_t rec = rec0 + u;
-          if (nm.len != 0xFFFFFFFFu && rec < P.names_cap) P.names[rec] = nm;
-        }
+        const uint32_t rec = rec0 + tid; /* p_nstage <= LN_SMAX <= LN_THREADS: one name per thread */
+        if (my_nm.len != 0xFFFFFFFFu && rec < P.names_cap) P.names[rec] = my_nm;
       }
       pend = false;
-    }
-    if (!active) break;
+    };
+    if (!active) { if (pend) finish_previous(); break; }
 
-    const uint32_t left = (uint32_t)min((unsigned long long)(LN_TILE + LN_MARGIN), (unsigned long long)P.n - t0); /* data bytes from the tile start */
-    const uint32_t nv = min(left, (uint32_t)LN_TILE);   /* valid bytes of the tile itself */
+    const uint32_t left = (uint32_t)min((unsigned long long)(TILE + LN_MARGIN), (unsigned long long)P.n - t0); /* data bytes from the tile start */
+    const uint32_t nv = min(left, (uint32_t)TILE);      /* valid bytes of the tile itself */
+    const uint32_t ns = min(left, (uint32_t)SCAN);      /* valid bytes of the scanned range */
     const uint32_t nloc = LN_LEFT + left;               /* window offsets below this hold data */
-    const bool full = nv == (uint32_t)LN_TILE;
+    const bool full = ns == (uint32_t)SCAN;
     uint16_t* lend = lend2 + buf * LN_LMAX;
     {
       uint32_t spins = 0;
@@ -218,7 +266,7 @@ fq_lanes_kernel(const LanesParams P) {
       for (int i = 0; i < LN_CPT; i++) {
         const uint32_t c = cbase + i * 32;
         uint32_t m = ln_lf_mask16(*(const uint4*)(win + LN_LEFT + 16 * c));
-        if (!full) { uint32_t valid = nv > 16 * c ? min(16u, nv - 16 * c) : 0u; m &= (1u << valid) - 1u; }
+        if (!full) { uint32_t valid = ns > 16 * c ? min(16u, ns - 16 * c) : 0u; m &= (1u << valid) - 1u; }
         maskbuf[c] = (uint16_t)m;
       }
     }
@@ -235,21 +283,25 @@ fq_lanes_kernel(const LanesParams P) {
       tot = h + n45 + n67;
     }
 
-    /* ---- B: prefix of the LF counts inside the tile; the tile's count is published for the tiles behind us; line ends */
-    uint32_t incl = tot;
+    /* ---- B: prefix of the LF counts inside the tile; the tile's count is published for the tiles behind us; line ends.
+     * Low half: LFs of the scanned range (ranks of the line ends); high half: only those of the tile itself (its published count). */
+    const uint32_t c0 = LN_CPT * tid;
+    const uint32_t tot2 = tot | ((!LINES || c0 < (uint32_t)LS_TILE_CHUNKS) ? tot << 16 : 0u);
+    uint32_t incl = tot2;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += a; }
     if (lane == 31) s_w1[warp] = incl;
     __syncthreads();
-    uint32_t excl = incl - tot, cntT = 0;
+    uint32_t excl = incl - tot2, cnt2 = 0;
 #pragma unroll
-    for (int w = 0; w < LN_WARPS; w++) { uint32_t x = s_w1[w]; cntT += x; if (w < warp) excl += x; }
+    for (int w = 0; w < LN_WARPS; w++) { uint32_t x = s_w1[w]; cnt2 += x; if (w < warp) excl += x; }
+    excl &= 0xFFFFu;
+    const uint32_t cntW = cnt2 & 0xFFFFu, cntT = cnt2 >> 16; /* line ends inside the scanned range / inside the tile */
     if (tid == 0) {
       if (tile > 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
       s_next = atomicAdd(P.ticket, 1u); /* read after the barrier at the top of the next round */
     }
-    const uint32_t c0 = LN_CPT * tid;
-    const bool too_many = cntT > (uint32_t)LN_LMAX;
+    const bool too_many = cntW > (uint32_t)LN_LMAX;
     if (too_many) anomaly |= LN_A_CAPACITY;
     else { /* window offsets of this thread's line ends, in order: the first two LFs of a 32-byte span without a branch */
       uint32_t rank = excl;
@@ -261,6 +313,7 @@ fq_lanes_kernel(const LanesParams P) {
 #undef LN_EMIT1
     }
     __syncthreads();
+    if (pend) finish_previous();
 
     /* ---- C0: line class of the tile's first byte.  The true value needs the number of lines in front of the tile; that sum is
      * looked up one round later (F), when the tiles in front have long published their counts.  Until then the tile's own lines
@@ -270,7 +323,7 @@ fq_lanes_kernel(const LanesParams P) {
     {
       const uint32_t k = lane + 1; /* line k of the tile starts at lend[k-1] */
       bool plus = false;
-      if (!too_many && k < cntT) { const uint32_t s = lend[k - 1], e = lend[k]; plus = e - s == 2u && win[s] == '+'; }
+      if (!too_many && k < cntW) { const uint32_t s = lend[k - 1], e = lend[k]; plus = e - s == 2u && win[s] == '+'; }
       const uint32_t pm = __ballot_sync(FULL, plus);
       /* line k is a plus line ⇒ class of the tile's first line = (2 - k) & 3; bit (k-1) of pm ↔ line k */
       const uint32_t w0 = pm & 0x11111111u, w1 = pm & 0x22222222u, w2 = pm & 0x44444444u, w3 = pm & 0x88888888u;
@@ -281,6 +334,7 @@ fq_lanes_kernel(const LanesParams P) {
         phi = (4u - P.j0) & 3u;
       } else if (votes == 1u) phi = w0 ? 1u : w1 ? 0u : w2 ? 3u : 2u; /* k = 1, 5, .. → 1;  k = 2, 6, .. → 0;  k = 3, .. → 3;  k = 4, .. → 2 */
       else { /* no witness (long lines, or plus lines that repeat the name), or witnesses that disagree: wait for the sum now */
+        __syncthreads(); /* the look-back scratch may still be read by the previous tile's look-back */
         base_line = ln_lookback(P.tile_state, tile, tid, lane, warp, s_w3, s_w4, P.out);
         if (tid == 0) st_volatile64(P.tile_state + tile, ST_INCL | ((unsigned long long)base_line + cntT));
         have_base = true;
@@ -291,133 +345,185 @@ fq_lanes_kernel(const LanesParams P) {
     const uint32_t gbr = 4u + phi;
     const uint32_t g0t = gbr + excl;                /* line number at this thread's first byte */
 
-    /* ---- C1: whole chunks of sequence / quality lines: classify (all lanes in step), then one list per warp */
-    uint32_t n_seq_w, n_qual_w;
-    {
-      uint32_t is_seq = 0, is_qual = 0; /* bit i: chunk i of this thread is a whole chunk of that class */
-#pragma unroll
-      for (int i = 0; i < LN_CPT; i++) {
-        const uint32_t m = ((i < 2 ? mm.x : i < 4 ? mm.y : i < 6 ? mm.z : mm.w) >> (16 * (i & 1))) & 0xFFFFu;
-        const uint32_t cum = ((i < 4 ? cumA : cumB) >> (8 * (i & 3))) & 0xFFu;
-        const uint32_t cls = (g0t + cum) & 3u;
-        bool whole = m == 0;
-        if (!full) whole = whole && nv >= 16 * (c0 + i) + 16;
-        is_seq |= (whole && cls == 1u) ? 1u << i : 0u;
-        is_qual |= (whole && cls == 3u) ? 1u << i : 0u;
+    if (LINES) {
+      /* ---- L: one thread per line.  Lines are taken by the tile they start in; line k of the window (0..) starts at lend[k-1]
+       * and ends at lend[k] (tile or margin).  Every fourth line has the same class, so the i-th line of a class is found by
+       * arithmetic; warps take groups of 32 lines of ONE class: sequence lines first, then quality, then header lines. */
+      p_nstage = 0; p_rl0 = 0;
+      if (!too_many) {
+        const uint32_t kmin = win[LN_LEFT - 1] == '\n' ? 0u : 1u;
+        const uint32_t tile_end = LN_LEFT + nv;          /* lines starting at or beyond belong to the next tile (or do not exist) */
+        const uint32_t gofs = (uint32_t)(t0 - LN_LEFT);
+        uint32_t kH = kmin + ((0u - (gbr + kmin)) & 3u), kS = kmin + ((1u - (gbr + kmin)) & 3u), kQ = kmin + ((3u - (gbr + kmin)) & 3u);
+        if (tile == 0) { /* lines of the record cut by the start of the chunk are judged with their record */
+          if (kH < P.j0) kH += 4; if (kS < P.j0) kS += 4; if (kQ < P.j0) kQ += 4;
+        }
+        const uint32_t nS = kS <= cntT ? (cntT - kS) / 4 + 1 : 0, nQ = kQ <= cntT ? (cntT - kQ) / 4 + 1 : 0;
+        uint32_t nH = kH <= cntT ? (cntT - kH) / 4 + 1 : 0;
+        if (nH > (uint32_t)LN_SMAX) { anomaly |= LN_A_CAPACITY; nH = 0; }
+        p_nstage = nH; p_rl0 = (gbr + kH) >> 2;
+        const uint32_t GS = (nS + 31) >> 5, GQ = (nQ + 31) >> 5, GH = (nH + 31) >> 5;
+        for (uint32_t g = warp; g < GS + GQ + GH; g += LN_WARPS) { /* the class is uniform over the warp */
+          const uint32_t cls = g < GS ? 1u : g < GS + GQ ? 3u : 0u;
+          const uint32_t i = 32 * (cls == 1u ? g : cls == 3u ? g - GS : g - GS - GQ) + lane;
+          const uint32_t n = cls == 1u ? nS : cls == 3u ? nQ : nH;
+          const uint32_t k = (cls == 1u ? kS : cls == 3u ? kQ : kH) + 4 * i;
+          if (cls == 0u && i < n) stage[i].len = 0xFFFFFFFFu; /* nothing to write out unless the header is judged below */
+          if (i >= n) continue;
+          const uint32_t s = k == 0 ? (uint32_t)LN_LEFT : (uint32_t)lend[k - 1];
+          if (s >= tile_end) continue;
+          uint32_t e; /* one past the line's last byte; has_lf: that byte is its LF */
+          bool has_lf = true;
+          if (k < cntW) e = lend[k];
+          else if (nloc < (uint32_t)(LN_LEFT + TILE + LN_MARGIN)) { /* the data ends inside the window */
+            if (!P.virtual_end) continue;                             /* more follows: the rest of the line comes with the next chunk */
+            e = nloc; has_lf = false;                                 /* last line of the file, without LF */
+          } else { anomaly |= LN_A_CAPACITY; continue; }              /* longer than the margin: not for this mode */
+          const uint32_t ce = has_lf ? e - 1u : e;                    /* content: [s, ce) */
+          if (cls == 1u) { if (ce > s) seq_ok &= ls_seq_line(win, lut, s, ce); }
+          else if (cls == 3u) {
+            if (!(win[s - 1] == '\n' && win[s - 2] == '+' && win[s - 3] == '\n')) anomaly |= LN_A_PLUS; /* the line in front must be "+\n" */
+            if (ce > s) ls_qual_line(win, lut, s, ce, qmn, qmx);
+          } else {
+            const uint32_t hl = e - s;
+            if (!has_lf) { anomaly |= LN_A_HEADER; continue; }
+            if (hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, tile); continue; }
+            uint32_t nlen; uint64_t mem_len, hsh = FQ_HASH_SKIP;
+            if (!fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; continue; }
+            FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
+            stage[i] = nm;
+          }
+        }
       }
-      const uint32_t n_pure = __popc(is_seq) | (__popc(is_qual) << 16);
-      uint32_t ip = n_pure;
+    } else {
+      /* ---- C1: whole chunks of sequence / quality lines: classify (all lanes in step), then one list per warp */
+      uint32_t n_seq_w, n_qual_w;
+      {
+        uint32_t is_seq = 0, is_qual = 0; /* bit i: chunk i of this thread is a whole chunk of that class */
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, ip, d); if (lane >= d) ip += a; }
-      const uint32_t tw = __shfl_sync(FULL, ip, 31), xp = ip - n_pure;
-      n_seq_w = tw & 0xFFFFu; n_qual_w = tw >> 16;
-      uint32_t as = smem_u32(pure) + 2 * (warp * 256 + (xp & 0xFFFFu)), aq = smem_u32(pure) + 2 * (warp * 256 + 255 - (xp >> 16));
+        for (int i = 0; i < LN_CPT; i++) {
+          const uint32_t m = ((i < 2 ? mm.x : i < 4 ? mm.y : i < 6 ? mm.z : mm.w) >> (16 * (i & 1))) & 0xFFFFu;
+          const uint32_t cum = ((i < 4 ? cumA : cumB) >> (8 * (i & 3))) & 0xFFu;
+          const uint32_t cls = (g0t + cum) & 3u;
+          bool whole = m == 0;
+          if (!full) whole = whole && nv >= 16 * (c0 + i) + 16;
+          is_seq |= (whole && cls == 1u) ? 1u << i : 0u;
+          is_qual |= (whole && cls == 3u) ? 1u << i : 0u;
+        }
+        const uint32_t n_pure = __popc(is_seq) | (__popc(is_qual) << 16);
+        uint32_t ip = n_pure;
 #pragma unroll
-      for (int i = 0; i < LN_CPT; i++) {
-        asm volatile("{ .reg .pred p, q; setp.ne.u32 p, %2, 0; setp.ne.u32 q, %3, 0;\n"
-                     "  @p st.shared.u16 [%0], %4; @p add.u32 %0, %0, 2;\n"
-                     "  @q st.shared.u16 [%1], %4; @q sub.u32 %1, %1, 2; }"
-                     : "+r"(as), "+r"(aq) : "r"(is_seq & (1u << i)), "r"(is_qual & (1u << i)), "h"((uint16_t)(c0 + i)) : "memory");
+        for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, ip, d); if (lane >= d) ip += a; }
+        const uint32_t tw = __shfl_sync(FULL, ip, 31), xp = ip - n_pure;
+        n_seq_w = tw & 0xFFFFu; n_qual_w = tw >> 16;
+        uint32_t as = smem_u32(pure) + 2 * (warp * 256 + (xp & 0xFFFFu)), aq = smem_u32(pure) + 2 * (warp * 256 + 255 - (xp >> 16));
+#pragma unroll
+        for (int i = 0; i < LN_CPT; i++) {
+          asm volatile("{ .reg .pred p, q; setp.ne.u32 p, %2, 0; setp.ne.u32 q, %3, 0;\n"
+                       "  @p st.shared.u16 [%0], %4; @p add.u32 %0, %0, 2;\n"
+                       "  @q st.shared.u16 [%1], %4; @q sub.u32 %1, %1, 2; }"
+                       : "+r"(as), "+r"(aq) : "r"(is_seq & (1u << i)), "r"(is_qual & (1u << i)), "h"((uint16_t)(c0 + i)) : "memory");
+        }
       }
-    }
-    __syncwarp();
+      __syncwarp();
 
-    if (!too_many) {
-      /* ---- D: sequence alphabet, quality range; one predicate per warp instruction.
-       * Whole chunks come from the warp's lists.  Partial chunks hang on LFs: the bytes after a header / plus LF and before a
-       * sequence / quality LF; the LFs of one kind are every fourth line end, so item i of a kind is found by arithmetic. */
-      const uint16_t* pw = pure + warp * 256;
-      for (uint32_t i = lane; i < n_seq_w; i += 32)
-        seq_ok &= ln_pred4(*(const uint4*)(win + LN_LEFT + 16 * (uint32_t)pw[i]));
-      for (uint32_t i = lane; i < n_qual_w; i += 32) {
-        const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * (uint32_t)pw[255 - i]);
-        ln_minmax_word(v.x, qmn, qmx); ln_minmax_word(v.y, qmn, qmx); ln_minmax_word(v.z, qmn, qmx); ln_minmax_word(v.w, qmn, qmx);
-      }
-      const uint32_t n_items = 2u * ((cntT + 3u) >> 2); /* per kind: two per started group of four lines */
+      if (!too_many) {
+        /* ---- D: sequence alphabet, quality range; one predicate per warp instruction.
+         * Whole chunks come from the warp's lists.  Partial chunks hang on LFs: the bytes after a header / plus LF and before a
+         * sequence / quality LF; the LFs of one kind are every fourth line end, so item i of a kind is found by arithmetic. */
+        const uint16_t* pw = pure + warp * 256;
+        for (uint32_t i = lane; i < n_seq_w; i += 32)
+          seq_ok &= ln_pred4(*(const uint4*)(win + LN_LEFT + 16 * (uint32_t)pw[i]));
+        for (uint32_t i = lane; i < n_qual_w; i += 32) {
+          const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * (uint32_t)pw[255 - i]);
+          ln_minmax_word(v.x, qmn, qmx); ln_minmax_word(v.y, qmn, qmx); ln_minmax_word(v.z, qmn, qmx); ln_minmax_word(v.w, qmn, qmx);
+        }
+        const uint32_t n_items = 2u * ((cntT + 3u) >> 2); /* per kind: two per started group of four lines */
 #pragma unroll
-      for (int kind = 0; kind < 2; kind++) { /* 0: sequence side (classes 0, 1), 1: quality side (classes 2, 3) */
-        const uint32_t ra = ((kind ? 2u : 0u) - gbr) & 3u, rb = ((kind ? 3u : 1u) - gbr) & 3u; /* first line ends of those classes */
-        for (uint32_t i = tid; i < n_items; i += LN_THREADS) {
-          const bool before = i & 1u;                     /* odd items: the bytes before a sequence / quality LF */
-          const uint32_t r = 4u * (i >> 1) + (before ? rb : ra);
-          if (r < cntT) {
-            const uint32_t e = lend[r], q = e - (LN_LEFT + 1), c = q >> 4, p = q & 15u;
-            const uint32_t mc = maskbuf[c];               /* all LFs of this chunk */
-            const uint32_t below = mc & ((1u << p) - 1u), above = mc >> (p + 1);
-            uint32_t nvc = 16u;
-            if (!full) nvc = min(16u, nv - 16 * c);       /* the chunk holds an LF, so it starts inside the data */
-            const uint32_t lo = before ? (below ? 32u - __clz(below) : 0u) : p + 1;
-            const uint32_t hi = before ? p : (above ? p + __ffs(above) : nvc);
-            if (hi > lo) {
-              const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * c);
-              const uint4 a = lut[lo], b = lut[15u + hi];
-              if (kind == 0) /* bytes outside [lo, hi) always pass */
-                seq_ok &= (fq_base_pred(v.x) | ~(a.x & b.x)) & (fq_base_pred(v.y) | ~(a.y & b.y)) & (fq_base_pred(v.z) | ~(a.z & b.z)) & (fq_base_pred(v.w) | ~(a.w & b.w));
-              else {
-                const uint32_t fill = (uint32_t)win[LN_LEFT + 16 * c + lo] * 0x01010101u; /* a byte of the range stands in for the bytes outside it */
-                uint32_t m;
-                m = a.x & b.x; ln_minmax_word((v.x & m) | (fill & ~m), qmn, qmx);
-                m = a.y & b.y; ln_minmax_word((v.y & m) | (fill & ~m), qmn, qmx);
-                m = a.z & b.z; ln_minmax_word((v.z & m) | (fill & ~m), qmn, qmx);
-                m = a.w & b.w; ln_minmax_word((v.w & m) | (fill & ~m), qmn, qmx);
+        for (int kind = 0; kind < 2; kind++) { /* 0: sequence side (classes 0, 1), 1: quality side (classes 2, 3) */
+          const uint32_t ra = ((kind ? 2u : 0u) - gbr) & 3u, rb = ((kind ? 3u : 1u) - gbr) & 3u; /* first line ends of those classes */
+          for (uint32_t i = tid; i < n_items; i += LN_THREADS) {
+            const bool before = i & 1u;                     /* odd items: the bytes before a sequence / quality LF */
+            const uint32_t r = 4u * (i >> 1) + (before ? rb : ra);
+            if (r < cntT) {
+              const uint32_t e = lend[r], q = e - (LN_LEFT + 1), c = q >> 4, p = q & 15u;
+              const uint32_t mc = maskbuf[c];               /* all LFs of this chunk */
+              const uint32_t below = mc & ((1u << p) - 1u), above = mc >> (p + 1);
+              uint32_t nvc = 16u;
+              if (!full) nvc = min(16u, nv - 16 * c);       /* the chunk holds an LF, so it starts inside the data */
+              const uint32_t lo = before ? (below ? 32u - __clz(below) : 0u) : p + 1;
+              const uint32_t hi = before ? p : (above ? p + __ffs(above) : nvc);
+              if (hi > lo) {
+                const uint4 v = *(const uint4*)(win + LN_LEFT + 16 * c);
+                const uint4 a = lut[lo], b = lut[15u + hi];
+                if (kind == 0) /* bytes outside [lo, hi) always pass */
+                  seq_ok &= (fq_base_pred(v.x) | ~(a.x & b.x)) & (fq_base_pred(v.y) | ~(a.y & b.y)) & (fq_base_pred(v.z) | ~(a.z & b.z)) & (fq_base_pred(v.w) | ~(a.w & b.w));
+                else {
+                  const uint32_t fill = (uint32_t)win[LN_LEFT + 16 * c + lo] * 0x01010101u; /* a byte of the range stands in for the bytes outside it */
+                  uint32_t m;
+                  m = a.x & b.x; ln_minmax_word((v.x & m) | (fill & ~m), qmn, qmx);
+                  m = a.y & b.y; ln_minmax_word((v.y & m) | (fill & ~m), qmn, qmx);
+                  m = a.z & b.z; ln_minmax_word((v.z & m) | (fill & ~m), qmn, qmx);
+                  m = a.w & b.w; ln_minmax_word((v.w & m) | (fill & ~m), qmn, qmx);
+                }
               }
             }
           }
         }
-      }
-      /* the chunk cut by the end of the data, when no LF of its own bounds it */
-      if (!full && (nv & 15u) && (nv >> 4) >= c0 && (nv >> 4) < c0 + LN_CPT && maskbuf[nv >> 4] == 0) {
-        const uint32_t i = (nv >> 4) - c0, c = nv >> 4, hi = nv & 15u;
-        const uint32_t cum = ((i < 4 ? cumA : cumB) >> (8 * (i & 3))) & 0xFFu, cls = (g0t + cum) & 3u;
-        for (uint32_t k = 0; k < hi; k++) {
-          const uint32_t ch = win[LN_LEFT + 16 * c + k];
-          if (cls == 1u) { if (!((fq_base_pred(ch) >> 7) & 1u)) seq_ok = 0; }
-          else if (cls == 3u) { ln_minmax_word(ch * 0x01010101u, qmn, qmx); }
+        /* the chunk cut by the end of the data, when no LF of its own bounds it */
+        if (!full && (nv & 15u) && (nv >> 4) >= c0 && (nv >> 4) < c0 + LN_CPT && maskbuf[nv >> 4] == 0) {
+          const uint32_t i = (nv >> 4) - c0, c = nv >> 4, hi = nv & 15u;
+          const uint32_t cum = ((i < 4 ? cumA : cumB) >> (8 * (i & 3))) & 0xFFu, cls = (g0t + cum) & 3u;
+          for (uint32_t k = 0; k < hi; k++) {
+            const uint32_t ch = win[LN_LEFT + 16 * c + k];
+            if (cls == 1u) { if (!((fq_base_pred(ch) >> 7) & 1u)) seq_ok = 0; }
+            else if (cls == 3u) { ln_minmax_word(ch * 0x01010101u, qmn, qmx); }
+          }
         }
-      }
 
-      /* ---- E: header and plus lines that start in this tile.  Line k of the tile (0..cntT) starts at lend[k-1].  Names are staged
-       * in shared memory under their number inside the tile and written out next round (F). */
-      {
-        const uint32_t kmin = win[LN_LEFT - 1] == '\n' ? 0u : 1u;
-        const uint32_t tile_end = LN_LEFT + nv; /* lines starting at or beyond belong to the next tile (or do not exist) */
-        const uint32_t gofs = (uint32_t)(t0 - LN_LEFT);
-        const uint32_t kh0 = kmin + ((0u - (gbr + kmin)) & 3u), kp0 = kmin + ((2u - (gbr + kmin)) & 3u);
-        uint32_t nH = kh0 <= cntT ? (cntT - kh0) / 4 + 1 : 0;
-        const uint32_t nP = kp0 <= cntT ? (cntT - kp0) / 4 + 1 : 0;
-        if (nH > (uint32_t)LN_SMAX) { anomaly |= LN_A_CAPACITY; nH = 0; }
-        p_nstage = nH; p_rl0 = (gbr + kh0) >> 2;
-        for (uint32_t u = tid; u < nH + nP; u += LN_THREADS) {
-          const bool is_hdr = u < nH;
-          const uint32_t k = is_hdr ? kh0 + 4 * u : kp0 + 4 * (u - nH);
-          const uint32_t s = k == 0 ? (uint32_t)LN_LEFT : (uint32_t)lend[k - 1];
-          if (is_hdr) stage[u].len = 0xFFFFFFFFu; /* nothing to write out unless the header is judged below */
-          if (s >= tile_end) continue;
-          if (tile == 0 && k < P.j0) continue; /* lines of the record cut by the start of the chunk: judged with their record */
-          if (!is_hdr) { /* "+\n" */
-            if (s + 1 >= nloc) continue; /* cut by the end of the data: the record is completed (or judged) elsewhere */
-            if (!(win[s] == '+' && win[s + 1] == '\n')) anomaly |= LN_A_PLUS;
-            continue;
-          }
-          uint32_t e = 0;
-          if (k < cntT) e = lend[k];
-          else { /* the tile's last line: its LF lies in the margin */
-            uint32_t p = LN_LEFT + nv;
-            for (; p < nloc; p++) if (win[p] == '\n') { e = p + 1; break; }
-            if (!e) {
-              if (nloc == (uint32_t)LN_WIN) atomicMin(P.out + LN_O_OVERLONG, tile); /* no LF within 1 KiB: a line gzgets would split */
-              continue; /* otherwise cut by the end of the data */
+        /* ---- E: header and plus lines that start in this tile.  Line k of the tile (0..cntT) starts at lend[k-1].  Names are staged
+         * in shared memory under their number inside the tile and written out next round (F). */
+        {
+          const uint32_t kmin = win[LN_LEFT - 1] == '\n' ? 0u : 1u;
+          const uint32_t tile_end = LN_LEFT + nv; /* lines starting at or beyond belong to the next tile (or do not exist) */
+          const uint32_t gofs = (uint32_t)(t0 - LN_LEFT);
+          const uint32_t kh0 = kmin + ((0u - (gbr + kmin)) & 3u), kp0 = kmin + ((2u - (gbr + kmin)) & 3u);
+          uint32_t nH = kh0 <= cntT ? (cntT - kh0) / 4 + 1 : 0;
+          const uint32_t nP = kp0 <= cntT ? (cntT - kp0) / 4 + 1 : 0;
+          if (nH > (uint32_t)LN_SMAX) { anomaly |= LN_A_CAPACITY; nH = 0; }
+          p_nstage = nH; p_rl0 = (gbr + kh0) >> 2;
+          for (uint32_t u = tid; u < nH + nP; u += LN_THREADS) {
+            const bool is_hdr = u < nH;
+            const uint32_t k = is_hdr ? kh0 + 4 * u : kp0 + 4 * (u - nH);
+            const uint32_t s = k == 0 ? (uint32_t)LN_LEFT : (uint32_t)lend[k - 1];
+            if (is_hdr) stage[u].len = 0xFFFFFFFFu; /* nothing to write out unless the header is judged below */
+            if (s >= tile_end) continue;
+            if (tile == 0 && k < P.j0) continue; /* lines of the record cut by the start of the chunk: judged with their record */
+            if (!is_hdr) { /* "+\n" */
+              if (s + 1 >= nloc) continue; /* cut by the end of the data: the record is completed (or judged) elsewhere */
+              if (!(win[s] == '+' && win[s + 1] == '\n')) anomaly |= LN_A_PLUS;
+              continue;
             }
+            uint32_t e = 0;
+            if (k < cntT) e = lend[k];
+            else { /* the tile's last line: its LF lies in the margin */
+              uint32_t p = LN_LEFT + nv;
+              for (; p < nloc; p++) if (win[p] == '\n') { e = p + 1; break; }
+              if (!e) {
+                if (nloc == (uint32_t)LN_WIN) atomicMin(P.out + LN_O_OVERLONG, tile); /* no LF within 1 KiB: a line gzgets would split */
+                continue; /* otherwise cut by the end of the data */
+              }
+            }
+            const uint32_t hl = e - s;
+            if (hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, tile); continue; }
+            uint32_t nlen; uint64_t mem_len, hsh = FQ_HASH_SKIP;
+            if (!fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; continue; }
+            FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
+            stage[u] = nm;
           }
-          const uint32_t hl = e - s;
-          if (hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, tile); continue; }
-          uint32_t nlen; uint64_t mem_len, hsh = FQ_HASH_SKIP;
-          if (!fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; continue; }
-          FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
-          stage[u] = nm;
         }
-      }
-    } else { p_nstage = 0; p_rl0 = 0; }
+      } else { p_nstage = 0; p_rl0 = 0; }
+    }
     pend = true; p_tile = tile; p_cnt = cntT; p_phi = phi; p_have_base = have_base; p_base = base_line;
     p_no_final_lf = P.virtual_end && tile == P.ntiles - 1 && P.n > 0 && win[nloc - 1] != '\n';
     buf ^= 1u;

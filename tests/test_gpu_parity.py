@@ -256,8 +256,17 @@ def _run_ctx(mode, pieces, hint=0):
     return rep, tr, pc
 
 
+@pytest.fixture(params=["per-line", "chunk-parallel"])
+def lanes_mode(request, monkeypatch):
+    """The clean-data pass has two modes (one thread per line for short lines, chunk-parallel for any length): FQG_NO_LINES=1
+    forces the second one on short reads too."""
+    if request.param == "chunk-parallel":
+        monkeypatch.setenv("FQG_NO_LINES", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("cuts", [(), (1 << 20,), (3_000_017, 9_000_001), (5 * 359 * 1000,), (359 * 4096 + 47, 359 * 8192 + 48, 359 * 20000 + 200)])
-def test_lanes_pass_clean_illumina(cuts):
+def test_lanes_pass_clean_illumina(cuts, lanes_mode):
     """Clean synthetic reads in one or several device-resident pieces cut at arbitrary bytes: the clean-data pass must accept
     every piece, and the transcript must be the oracle's."""
     import fastq_utils_b200 as fq
@@ -295,7 +304,7 @@ def test_lanes_pass_longreads():
     assert tr == oracle_run(["-r", "a.fq"], data, None) and pc["lanes"] == 2, pc
 
 
-def test_lanes_pass_hands_anomalies_on():
+def test_lanes_pass_hands_anomalies_on(lanes_mode):
     """Every kind of deviation from the clean shape makes the pass hand the chunk to the per-record kernels; the verdict and
     the statistics stay the oracle's (some of these inputs are still valid FASTQ)."""
     import torch
@@ -338,7 +347,7 @@ def test_lanes_pass_hands_anomalies_on():
         assert pc["lanes"] == 1 and pc["lanes_handed_on"] == 0, (name, pc)
 
 
-def test_lanes_pass_statistics_roll_back():
+def test_lanes_pass_statistics_roll_back(lanes_mode):
     """A chunk rejected by the record rules (lengths) after the pass itself found nothing must leave no trace in the
     statistics: same report as with the clean-data pass switched off."""
     import torch
