@@ -73,7 +73,7 @@ typedef struct {
   uint32_t hint_line_len;    /* length of the file's first sequence line (0 = unknown): picks the clean-data pass's mode */
 } FqTileArgs;
 
-#define FQ_LANES_OUT_WORDS 12
+#define FQ_LANES_OUT_WORDS 16
 class FqDevice {
  public:
   virtual ~FqDevice() {}

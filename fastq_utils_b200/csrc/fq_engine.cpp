@@ -233,14 +233,14 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
    * below decide (they own the reference's first-error semantics). */
   if (lanes_ok_ && a.cx.space != FQ_SPACE_COLOR) {
-    uint32_t linit[FQ_LANES_OUT_WORDS] = {0, 0, kNone32, 0, 0, kNone32, kNone32, 0, kNone32, 0, 0, 0};
+    uint32_t linit[FQ_LANES_OUT_WORDS] = {0, 0, kNone32, 0, 0, kNone32, kNone32, 0, kNone32, 0, 0, 0, 0, 0, 0, 0};
     dev_->upload(tile_out_, linit, sizeof linit);
     if (dev_->lanes_pass(a)) {
       uint32_t o[FQ_LANES_OUT_WORDS];
       dev_->download(o, tile_out_, sizeof o);
       bool pass_ok = !o[1] && o[2] == kNone32 && !o[3] && !o[4];
-      if (getenv("FQG_DEBUG")) fprintf(stderr, "[fqg] clean-data pass: n=%u j0=%u lines=%u capovf=%u overlong=%u anomaly=0x%x internal=%u virt=%u q=%u..%u rl=%u..%u recbad=%u\n",
-                                       B.n, j0, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10]);
+      if (getenv("FQG_DEBUG")) fprintf(stderr, "[fqg] clean-data pass: n=%u j0=%u lines=%u capovf=%u overlong=%u anomaly=0x%x internal=%u virt=%u q=%u..%u rl=%u..%u recbad=%u | polls=%u lookback_rounds=%u waited=%u\n",
+                                       B.n, j0, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10], o[11], o[12], o[13]);
       if (pass_ok && !o[10]) {
         dev_->lanes_commit(a, false);
         path_counts[0]++;

@@ -46,7 +46,8 @@ static_assert(LN_WIN % 16 == 0 && LN_OFF_LEND % 16 == 0 && LN_OFF_PURE % 16 == 0
 enum { LN_A_BASE = 1, LN_A_QUAL = 2, LN_A_HEADER = 4, LN_A_PLUS = 8, LN_A_CAPACITY = 16, LN_A_PHASE = 32 };
 /* out words */
 enum { LN_O_LINES = 0, LN_O_CAPOVF = 1, LN_O_OVERLONG = 2, LN_O_ANOMALY = 3, LN_O_INTERNAL = 4, LN_O_VIRTUAL = 5, LN_O_QMIN = 6, LN_O_QMAX = 7,
-       LN_O_RLMIN = 8, LN_O_RLMAX = 9, LN_O_RECBAD = 10, LN_O_WORDS = 12 };
+       LN_O_RLMIN = 8, LN_O_RLMAX = 9, LN_O_RECBAD = 10, LN_O_SPINS = 11 /* diagnostics: polls of unpublished tile states */,
+       LN_O_ROUNDS = 12 /* look-back rounds */, LN_O_WAITED = 13 /* tiles that had to wait for the sum before their scans */, LN_O_WORDS = 16 };
 
 struct LanesParams {
   const uint8_t* data; /* 16-byte aligned (bulk copies) */
@@ -126,29 +127,46 @@ __device__ __forceinline__ unsigned long long ln_wait_state(const unsigned long 
   uint32_t spins = 0;
   while (((v64 = ld_volatile64(p)) >> 62) == 0)
     if (++spins > (1u << 24)) { atomicExch(out + LN_O_INTERNAL, 2u); return ST_INCL; }
+  if (spins) atomicAdd(out + LN_O_SPINS, spins);
   return v64;
 }
-__device__ __forceinline__ uint32_t ln_lookback(const unsigned long long* tile_state, uint32_t tile, int tid, int lane, int warp,
+__device__ __forceinline__ bool ln_lookback_reduce(uint32_t part, bool has, int lane, int warp, uint32_t* s_sum, uint32_t* s_has, uint32_t* base, uint32_t* out) {
+  const uint32_t incl_mask = __ballot_sync(FULL, has);
+  const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+  part = __reduce_add_sync(FULL, lane <= first ? part : 0u);
+  if (lane == 0) { s_sum[warp] = part; s_has[warp] = incl_mask ? 1u : 0u; }
+  if (lane == 0 && warp == 0) atomicAdd(out + LN_O_ROUNDS, 1u);
+  __syncthreads();
+  bool found = false;
+#pragma unroll
+  for (int w = 0; w < LN_WARPS; w++) if (!found) { *base += s_sum[w]; found = s_has[w] != 0; }
+  return found;
+}
+/* `pre` = state of tile (tile - 1 - tid) read earlier (0 when it was not published yet, or not read): the first round looks at
+ * the 256 tiles right in front; only if none of them has its inclusive count do rounds of 1024 (four independent loads per thread)
+ * follow. */
+__device__ __forceinline__ uint32_t ln_lookback(const unsigned long long* tile_state, uint32_t tile, unsigned long long pre, int tid, int lane, int warp,
                                                 uint32_t* s_sum, uint32_t* s_has, uint32_t* out) {
   uint32_t base = 0;
-  for (int look = (int)tile - 1;; look -= 4 * LN_THREADS) {
+  {
+    const int idx = (int)tile - 1 - tid;
+    unsigned long long v64 = ST_INCL;
+    if (idx >= 0) v64 = (pre >> 62) != 0 ? pre : ln_wait_state(tile_state + idx, out);
+    if (ln_lookback_reduce((uint32_t)(v64 & ST_VALUE), (v64 >> 62) == 2, lane, warp, s_sum, s_has, &base, out)) return base;
+    __syncthreads(); /* s_sum / s_has are rewritten by the next round */
+  }
+  for (int look = (int)tile - 1 - LN_THREADS;; look -= 4 * LN_THREADS) {
+    unsigned long long v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const int idx = look - 4 * tid - j; v[j] = idx >= 0 ? ld_volatile64(tile_state + idx) : ST_INCL; }
     uint32_t part = 0; bool has = false;
 #pragma unroll
     for (int j = 0; j < 4; j++) { /* nearest first */
-      const int idx = look - 4 * tid - j;
-      const unsigned long long v64 = idx >= 0 ? ln_wait_state(tile_state + idx, out) : ST_INCL;
-      if (!has) { part += (uint32_t)(v64 & ST_VALUE); has = (v64 >> 62) == 2; }
+      if ((v[j] >> 62) == 0) v[j] = ln_wait_state(tile_state + (look - 4 * tid - j), out);
+      if (!has) { part += (uint32_t)(v[j] & ST_VALUE); has = (v[j] >> 62) == 2; }
     }
-    const uint32_t incl_mask = __ballot_sync(FULL, has);
-    const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
-    part = __reduce_add_sync(FULL, lane <= first ? part : 0u);
-    if (lane == 0) { s_sum[warp] = part; s_has[warp] = incl_mask ? 1u : 0u; }
+    if (ln_lookback_reduce(part, has, lane, warp, s_sum, s_has, &base, out)) break;
     __syncthreads();
-    bool found = false;
-#pragma unroll
-    for (int w = 0; w < LN_WARPS; w++) if (!found) { base += s_sum[w]; found = s_has[w] != 0; }
-    if (found) break;
-    __syncthreads(); /* s_sum / s_has are rewritten by the next round */
   }
   return base;
 }
@@ -213,6 +231,10 @@ fq_lanes_kernel(const LanesParams P) {
                    ::"r"(smem_u32(win + dst_off)), "l"(P.data + src), "r"(bytes), "r"(bar) : "memory");
     }
 
+    /* the state of one tile in front of the previous tile: asked for now, looked at in F */
+    unsigned long long pre64 = 0;
+    if (pend && !p_have_base && (int)p_tile - 1 - tid >= 0) pre64 = ld_volatile64(P.tile_state + ((int)p_tile - 1 - tid));
+
     /* ---- F: finish the previous tile: lines in front of it (its predecessors published their counts a round ago, and nothing that
      * can wait runs before a tile publishes its own), the check of the line class we assumed, line ends and names → global memory */
     auto finish_previous = [&]() {
@@ -222,7 +244,7 @@ fq_lanes_kernel(const LanesParams P) {
       if ((uint32_t)tid < p_nstage) my_nm = stage[tid];
       if (p_have_base) __syncthreads();
       else {
-        base = ln_lookback(P.tile_state, p_tile, tid, lane, warp, s_w3, s_w4, P.out);
+        base = ln_lookback(P.tile_state, p_tile, pre64, tid, lane, warp, s_w3, s_w4, P.out);
         if (((base + 4u - P.j0) & 3u) != p_phi) anomaly |= LN_A_PHASE; /* the plus lines of the tile misled us: hand the chunk on */
         if (tid == 0) st_volatile64(P.tile_state + p_tile, ST_INCL | ((unsigned long long)base + p_cnt));
       }
@@ -335,7 +357,8 @@ fq_lanes_kernel(const LanesParams P) {
       } else if (votes == 1u) phi = w0 ? 1u : w1 ? 0u : w2 ? 3u : 2u; /* k = 1, 5, .. → 1;  k = 2, 6, .. → 0;  k = 3, .. → 3;  k = 4, .. → 2 */
       else { /* no witness (long lines, or plus lines that repeat the name), or witnesses that disagree: wait for the sum now */
         __syncthreads(); /* the look-back scratch may still be read by the previous tile's look-back */
-        base_line = ln_lookback(P.tile_state, tile, tid, lane, warp, s_w3, s_w4, P.out);
+        if (tid == 0) atomicAdd(P.out + LN_O_WAITED, 1u);
+        base_line = ln_lookback(P.tile_state, tile, 0ull, tid, lane, warp, s_w3, s_w4, P.out);
         if (tid == 0) st_volatile64(P.tile_state + tile, ST_INCL | ((unsigned long long)base_line + cntT));
         have_base = true;
         phi = (base_line + 4u - P.j0) & 3u;

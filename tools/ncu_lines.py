@@ -8,6 +8,9 @@ instructions and stall samples per source line (inlined callees are attributed t
 import csv, os, re, subprocess, sys, tempfile, collections
 
 rep, kern = sys.argv[1], sys.argv[2]
+mangled = kern  # substring of the mangled name selecting the function in the cubin ("name@mangled" to give both)
+if "@" in kern:
+    kern, mangled = kern.split("@", 1)
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "fastq_utils_b200", "libfastq_gpu.so")
@@ -22,7 +25,7 @@ for f in os.listdir(tmp):
     for ln in txt.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
         if m:
-            active = kern in m.group(1)
+            active = mangled in m.group(1)
             continue
         if not active:
             continue

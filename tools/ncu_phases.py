@@ -5,7 +5,8 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
-vals = [r for r in rows[2:] if any(kern in x for x in r)][0]
+kname = kern.split("@")[0]
+vals = [r for r in rows[2:] if any(kname in x for x in r)][0]
 want = ["gpu__time_duration.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
