@@ -325,10 +325,14 @@ fq_lanes_kernel(const LanesParams P) {
     }
     const bool too_many = cntW > (uint32_t)LN_LMAX;
     if (too_many) anomaly |= LN_A_CAPACITY;
-    else { /* window offsets of this thread's line ends, in order: the first two LFs of a 32-byte span without a branch */
-      uint32_t rank = excl;
+    else { /* window offsets of this thread's line ends, in order.  The first two LFs of every 32-byte span are stored by predicated
+            * instructions on a running shared-memory address (no branches); a loop only for a third LF in 32 bytes. */
+      uint32_t addr = smem_u32(lend) + 2 * excl;
       const uint32_t e0 = LN_LEFT + 16 * c0 + 1;
-#define LN_EMIT1(h_) { const uint32_t b = __ffs(w) - 1; if (w) lend[rank] = (uint16_t)(e0 + 32 * (h_) + b); rank += w ? 1u : 0u; w &= w - 1; }
+#define LN_EMIT1(h_) asm volatile("{ .reg .pred p; .reg .u32 t, b;\n" \
+                                  "  setp.ne.u32 p, %1, 0; brev.b32 t, %1; bfind.shiftamt.u32 b, t; add.u32 b, b, %2;\n" \
+                                  "  @p st.shared.u16 [%0], b; @p add.u32 %0, %0, 2;\n" \
+                                  "  add.u32 t, %1, -1; and.b32 %1, %1, t; }" : "+r"(addr), "+r"(w) : "r"(e0 + 32 * (h_)) : "memory");
 #define LN_EMIT(w_, h_) { uint32_t w = (w_); LN_EMIT1(h_) LN_EMIT1(h_) while (w) LN_EMIT1(h_) }
       LN_EMIT(mm.x, 0) LN_EMIT(mm.y, 1) LN_EMIT(mm.z, 2) LN_EMIT(mm.w, 3)
 #undef LN_EMIT

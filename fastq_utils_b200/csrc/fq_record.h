@@ -427,6 +427,8 @@ FQ_HD uint64_t fq_hash_name_words(const uint8_t* d, uint32_t off, uint32_t len, 
 /* Header line and name hash in ONE walk over the line's words (aligned loads, a carried word and a funnel shift give the
  * words of the name, which starts one byte into the line).  Same results as fq_header_fast + fq_hash_name_words; false
  * where fq_header_fast is false. */
+/* 0x80 in every byte of x that is <= 0x20 (exact) */
+FQ_HD uint32_t fq_low_bytes_flags(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x5F5F5F5Fu) | x) & 0x80808080u; }
 FQ_HD bool fq_header_hash_fast(const uint8_t* d, uint32_t h0, uint32_t hl, int fmt, int is_pe, uint32_t seed, bool want_hash,
                                uint32_t* name_len, uint64_t* mem_len_out, uint64_t* hash) {
   if (hl < 3) return false;
@@ -454,6 +456,12 @@ FQ_HD bool fq_header_hash_fast(const uint8_t* d, uint32_t h0, uint32_t hl, int f
     uint32_t w = sh ? (cur >> sh) | (next << (32u - sh)) : cur;
 #endif
     cur = next;
+    /* a word without a byte <= 0x20 (NUL, space, terminators, control bytes) needs no closer look: inside the name it is
+     * hashed, beyond it skipped */
+    if (!fq_low_bytes_flags(w) && i + 4 <= s) {
+      if (i + 4 <= nlen) { if (want_hash) fq_hash_word(&h, w); continue; }
+      if (i >= nlen) continue;
+    }
     uint32_t z = fq_zero_bytes(w);
     if (casava && !cut) z |= fq_zero_bytes(w ^ 0x20202020u);
     if (s - i < 4) z &= (1u << (8u * (s - i))) - 1u;
@@ -478,6 +486,7 @@ FQ_HD bool fq_header_hash_fast(const uint8_t* d, uint32_t h0, uint32_t hl, int f
         uint32_t w2 = sh ? (cur >> sh) | (nx << (32u - sh)) : cur;
 #endif
         cur = nx;
+        if (!fq_low_bytes_flags(w2)) continue;
         uint32_t z3 = fq_zero_bytes(w2);
         if (s - i < 4) z3 &= (1u << (8u * (s - i))) - 1u;
         if (z3) return false;

@@ -17,4 +17,9 @@ for _ in range(reps):
     h.feed_device(0, t.data_ptr(), n * rb, last=True)
     rep = h.finish()
     assert rep.error.code == 0, rep.error.code
-print(h.path_counts(), h.kernel_stats())
+ks = h.kernel_stats()
+pc = h.path_counts()
+for k in ("lanes", "tile", "records", "scan", "index"):
+    if ks[k]["launches"]:
+        print(f"{k}: {ks[k]['ms'] / ks[k]['launches']:.4f} ms/launch x{ks[k]['launches']}" + (f"  {ks[k]['bytes'] / ks[k]['ms'] / 1e6:.1f} GB/s" if ks[k]["bytes"] else ""))
+print("paths", pc)
