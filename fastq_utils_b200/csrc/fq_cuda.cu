@@ -919,6 +919,7 @@ class FqCudaDevice : public FqDevice {
       FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, fq_lanes_kernel<true>, LN_THREADS, LN_SMEM));
       per_sm = std::min(per_sm, per_sm2);
       if (per_sm < 1) return false;
+      if (const char* e = getenv("FQG_LANES_CTAS")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; } /* tuning hook: leave room for the index kernel */
       lanes_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
     }
     LanesParams P;
