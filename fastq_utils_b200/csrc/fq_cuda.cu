@@ -587,6 +587,20 @@ struct TableParams {
   unsigned long long* key; unsigned long long* counters;
 };
 
+/* {hash, idx1} of a slot claimed in ONE 128-bit compare-and-swap (ATOMG.CAS.128): an insert into a free slot — the common case
+ * of a table at most half full — is a single atomic on a single DRAM sector.  false: *old_hash / *old_idx hold what was there. */
+__device__ __forceinline__ bool slot_claim128(FqSlot* s, unsigned long long hash, unsigned long long idx, unsigned long long* old_hash, unsigned long long* old_idx) {
+  unsigned long long olo, ohi;
+  asm volatile("{ .reg .b128 e, n, o;\n"
+               "  mov.b128 e, {%3, %4};\n"
+               "  mov.b128 n, {%5, %6};\n"
+               "  atom.global.cas.b128 o, [%2], e, n;\n"
+               "  mov.b128 {%0, %1}, o; }"
+               : "=l"(olo), "=l"(ohi) : "l"(s), "l"(FQ_HASH_EMPTY), "l"(FQ_IDX_NONE), "l"(hash), "l"(idx) : "memory");
+  *old_hash = olo; *old_idx = ohi;
+  return olo == FQ_HASH_EMPTY && ohi == FQ_IDX_NONE;
+}
+
 __global__ void __launch_bounds__(256)
 fq_index_insert_kernel(const TableParams P) {
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.nrec; k += gridDim.x * blockDim.x) {
@@ -597,9 +611,9 @@ fq_index_insert_kernel(const TableParams P) {
     for (;; i = (i + 1) & P.mask) {
       if (++probes > P.mask) { atomicExch(P.counters + 2, 1ull); break; }
       FqSlot* s = P.slots + i;
-      unsigned long long cur = ld_volatile64(&s->hash);
-      if (cur == FQ_HASH_EMPTY) cur = atomicCAS(&s->hash, FQ_HASH_EMPTY, nm.hash);
-      if (cur != FQ_HASH_EMPTY && cur != nm.hash) continue;
+      unsigned long long cur, cur_idx;
+      if (slot_claim128(s, nm.hash, g, &cur, &cur_idx)) break; /* first arrival of this name */
+      if (cur != nm.hash) continue;
       /* slot carries this hash: keep the smallest record index; whoever sees an earlier arrival compares the names */
       unsigned long long old = atomicMin(&s->idx1, g);
       if (old != FQ_IDX_NONE) {
