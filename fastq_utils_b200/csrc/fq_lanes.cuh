@@ -82,21 +82,36 @@ __device__ __forceinline__ void ln_minmax_word(uint32_t w, uint32_t& mn, uint32_
   mx = __vmaxu2(mx, __vmaxu2(ev, od));
 }
 
-/* per-line mode: every byte of [s, e) (window offsets, e > s) is ACGTN / acgtn → bit 7 of every byte of the result stays set */
+/* Alphabet check by reconstruction: bits 1..3 of a byte tell which of A C G T N it could be ((b >> 1) & 7 = 0 1 3 2 7); the byte is
+ * valid iff it EQUALS that letter.  The letter is rebuilt arithmetically in all four byte lanes at once,
+ *     0x41 + 2 c0 + 0x13 c1 - 0x0F c0 c1 + 7 c0 c1 c2      (A C T G . . . N for codes 0..7; codes 4..6 rebuild a letter of another code)
+ * with the right shifts as IMAD.HI and the sums as IMAD: 5 LOP3 on the ALU pipe, 7 on the FMA pipe per word (the bit-sliced
+ * predicate needs 8 + 6).  Result: 0 iff all four bytes are one of ACGTN (upper case). */
+__device__ __forceinline__ uint32_t ln_diff(uint32_t w) {
+  uint32_t t1, t2, t3;
+  asm("mul.hi.u32 %0, %1, 0x80000000;" : "=r"(t1) : "r"(w)); /* w >> 1 on the FMA pipe */
+  asm("mul.hi.u32 %0, %1, 0x40000000;" : "=r"(t2) : "r"(w));
+  asm("mul.hi.u32 %0, %1, 0x20000000;" : "=r"(t3) : "r"(w));
+  const uint32_t c0 = t1 & 0x01010101u, c1 = t2 & 0x01010101u, c01 = t1 & t2 & 0x01010101u, c012 = c01 & t3;
+  uint32_t e = 0x41414141u + 2u * c0; e += 0x13u * c1; e -= 0x0Fu * c01; e += 7u * c012;
+  return w ^ e;
+}
+__device__ __forceinline__ uint32_t ln_diff4(uint4 v) { return ln_diff(v.x) | ln_diff(v.y) | ln_diff(v.z) | ln_diff(v.w); }
+/* per-line mode: every byte of [s, e) (window offsets, e > s) is one of ACGTN → 0 */
 __device__ __forceinline__ uint32_t ls_seq_line(const uint8_t* win, const uint4* lut, uint32_t s, uint32_t e) {
   uint32_t a = s & ~15u;
   const uint32_t alast = (e - 1u) & ~15u;
   uint4 m = lut[s & 15u];
   if (a == alast) { const uint4 h = lut[15u + (e - a)]; m.x &= h.x; m.y &= h.y; m.z &= h.z; m.w &= h.w; }
   uint4 v = *(const uint4*)(win + a);
-  uint32_t ok = (fq_base_pred(v.x) | ~m.x) & (fq_base_pred(v.y) | ~m.y) & (fq_base_pred(v.z) | ~m.z) & (fq_base_pred(v.w) | ~m.w);
+  uint32_t bad = (ln_diff(v.x) & m.x) | (ln_diff(v.y) & m.y) | (ln_diff(v.z) & m.z) | (ln_diff(v.w) & m.w);
   if (a != alast) {
-    for (a += 16; a < alast; a += 16) ok &= ln_pred4(*(const uint4*)(win + a));
+    for (a += 16; a < alast; a += 16) bad |= ln_diff4(*(const uint4*)(win + a));
     m = lut[15u + (e - alast)];
     v = *(const uint4*)(win + alast);
-    ok &= (fq_base_pred(v.x) | ~m.x) & (fq_base_pred(v.y) | ~m.y) & (fq_base_pred(v.z) | ~m.z) & (fq_base_pred(v.w) | ~m.w);
+    bad |= (ln_diff(v.x) & m.x) | (ln_diff(v.y) & m.y) | (ln_diff(v.z) & m.z) | (ln_diff(v.w) & m.w);
   }
-  return ok;
+  return bad;
 }
 /* per-line mode: unsigned minimum / maximum over the bytes of [s, e) folded into two 16-bit lanes each */
 __device__ __forceinline__ void ls_qual_line(const uint8_t* win, const uint4* lut, uint32_t s, uint32_t e, uint32_t& mn, uint32_t& mx) {
@@ -210,7 +225,8 @@ fq_lanes_kernel(const LanesParams P) {
     lut[tid] = make_uint4(w[0], w[1], w[2], w[3]);
   }
   uint32_t parity = 0, buf = 0;
-  uint32_t seq_ok = 0x80808080u;           /* AND of the alphabet predicate over everything this thread checked */
+  uint32_t seq_ok = 0x80808080u;           /* AND of the alphabet predicate over everything this thread checked (chunk-parallel mode) */
+  uint32_t seq_bad = 0;                    /* OR of the alphabet differences (per-line mode) */
   uint32_t qmn = 0x00FF00FFu, qmx = 0u;    /* quality minimum / maximum, two 16-bit lanes */
   uint32_t anomaly = 0;
   /* the tile of the previous round: its line ends and names still wait for the number of lines in front of it */
@@ -448,7 +464,7 @@ fq_lanes_kernel(const LanesParams P) {
             e = nloc; has_lf = false;                                 /* last line of the file, without LF */
           } else { anomaly |= LN_A_CAPACITY; continue; }              /* longer than the margin: not for this mode */
           const uint32_t ce = has_lf ? e - 1u : e;                    /* content: [s, ce) */
-          if (cls == 1u) { if (ce > s) seq_ok &= ls_seq_line(win, lut, s, ce); }
+          if (cls == 1u) { if (ce > s) seq_bad |= ls_seq_line(win, lut, s, ce); }
           else if (cls == 3u) {
             if (!(win[s - 1] == '\n' && win[s - 2] == '+' && win[s - 3] == '\n')) anomaly |= LN_A_PLUS; /* the line in front must be "+\n" */
             if (ce > s) ls_qual_line(win, lut, s, ce, qmn, qmx);
@@ -598,7 +614,7 @@ fq_lanes_kernel(const LanesParams P) {
   }
 
   /* ---- results of this thread → one set of atomics per warp */
-  if ((seq_ok & 0x80808080u) != 0x80808080u) anomaly |= LN_A_BASE;
+  if ((seq_ok & 0x80808080u) != 0x80808080u || seq_bad) anomaly |= LN_A_BASE;
   uint32_t mn = min(qmn & 0xFFFFu, qmn >> 16), mx = max(qmx & 0xFFFFu, qmx >> 16);
   mn = __reduce_min_sync(FULL, mn); mx = __reduce_max_sync(FULL, mx);
   if (mn <= 0x0Du) anomaly |= LN_A_QUAL; /* NUL / LF / CR (or another control byte) inside a quality line: let the careful path look */
