@@ -26,6 +26,9 @@
  */
 
 constexpr int LN_THREADS = 256, LN_WARPS = LN_THREADS / 32;
+#ifndef LN_MAXREG
+#define LN_MAXREG 56 /* 4 CTAs of 256 threads leave 8 K registers per SM: room for a block of the index kernel beside the pass */
+#endif
 constexpr int LN_TILE = 32768, LN_CHUNKS = LN_TILE / 16, LN_CPT = LN_CHUNKS / LN_THREADS; /* 8 chunks per thread */
 constexpr int LN_LEFT = 16, LN_MARGIN = 1024, LN_WIN = LN_LEFT + LN_TILE + LN_MARGIN;
 /* per-line mode: the LF scan covers tile + margin (a line is judged by the tile it starts in, whole), so the tile is a margin shorter */
@@ -190,7 +193,7 @@ __device__ __forceinline__ uint32_t ln_lookback(const unsigned long long* tile_s
 /* LINES = false: chunk-parallel everywhere (lines of any length).  LINES = true: one thread per line for the bulk scans, warps of
  * one line class each — a third of the instructions when lines are short (they must end within the margin: < 1 KiB). */
 template <bool LINES>
-__global__ void __launch_bounds__(LN_THREADS, 4)
+__global__ void __maxnreg__(LN_MAXREG)
 fq_lanes_kernel(const LanesParams P) {
   constexpr int TILE = LINES ? LS_TILE : LN_TILE;          /* bytes a tile owns */
   constexpr int SCAN = LN_TILE;                            /* bytes whose LFs are flagged: the tile, and in per-line mode the margin too */
