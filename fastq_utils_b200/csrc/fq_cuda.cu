@@ -736,9 +736,9 @@ fq_shard_insert_kernel(const ShardParams P) {
     for (;; i = (i + 1) & a.mask) {
       if (++probes > a.mask) { atomicExch(a.counters + 2, 1ull); break; }
       FqSlot* s = a.slots + i;
-      unsigned long long cur = ld_volatile64(&s->hash);
-      if (cur == FQ_HASH_EMPTY) cur = atomicCAS(&s->hash, FQ_HASH_EMPTY, pn.hash);
-      if (cur != FQ_HASH_EMPTY && cur != pn.hash) continue;
+      unsigned long long cur, cur_idx;
+      if (slot_claim128(s, pn.hash, mine, &cur, &cur_idx)) break; /* first arrival of this name: one atomic on one sector */
+      if (cur != pn.hash) continue;
       unsigned long long old = atomicMin(&s->idx1, mine);
       if (old != FQ_IDX_NONE) {
         uint32_t ol, ml; const uint8_t* on = shard_name(a, old & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
