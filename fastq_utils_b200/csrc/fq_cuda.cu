@@ -673,36 +673,66 @@ fq_pair_compare_kernel(const PairParams P) {
 }
 
 /* ------------------------------------------------------------------------------------------------ multi-GPU: names to owners */
+/* Per-owner counts and bytes.  A warp votes owner by owner (ballot + one warp reduction each) instead of 64 shared-memory atomics
+ * on a handful of addresses; lane 0 keeps the warp's totals, one shared atomic per warp and owner at the end. */
 __global__ void __launch_bounds__(256)
 fq_names_count_kernel(const FqName* __restrict__ names, uint32_t nrec, uint32_t world, unsigned long long* out) {
   __shared__ unsigned long long sc[2 * FQ_SHARD_MAX_SRC];
   if (threadIdx.x < 2 * world) sc[threadIdx.x] = 0;
   __syncthreads();
-  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nrec; k += gridDim.x * blockDim.x) {
-    unsigned long long h = names[k].hash;
-    if (h == FQ_HASH_SKIP) continue;
-    uint32_t o = fq_owner_of(h, world);
-    atomicAdd(&sc[2 * o], 1ull); atomicAdd(&sc[2 * o + 1], (unsigned long long)((names[k].len + 3u) & ~3u));
+  const int lane = threadIdx.x & 31;
+  unsigned long long cnt_acc = 0, byte_acc = 0; /* lane w (and w + 32) holds owner w's (w + 32's) totals of this warp */
+  unsigned long long cnt_acc2 = 0, byte_acc2 = 0;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < nrec; base += gridDim.x * blockDim.x) {
+    const uint32_t k = base + threadIdx.x;
+    unsigned long long h = FQ_HASH_SKIP; uint32_t len4 = 0;
+    if (k < nrec) { const FqName nm = names[k]; h = nm.hash; len4 = (nm.len + 3u) & ~3u; }
+    const bool valid = h != FQ_HASH_SKIP;
+    const uint32_t o = valid ? fq_owner_of(h, world) : 0xFFFFFFFFu;
+    for (uint32_t w = 0; w < world; w++) {
+      const uint32_t m = __ballot_sync(FULL, o == w);
+      if (!m) continue;
+      const uint32_t b = __reduce_add_sync(FULL, o == w ? len4 : 0u);
+      if ((uint32_t)lane == (w & 31u)) { if (w < 32) { cnt_acc += __popc(m); byte_acc += b; } else { cnt_acc2 += __popc(m); byte_acc2 += b; } }
+    }
   }
+  if ((uint32_t)lane < world) { if (cnt_acc) { atomicAdd(&sc[2 * lane], cnt_acc); atomicAdd(&sc[2 * lane + 1], byte_acc); } }
+  if ((uint32_t)lane + 32 < world) { if (cnt_acc2) { atomicAdd(&sc[2 * (lane + 32)], cnt_acc2); atomicAdd(&sc[2 * (lane + 32) + 1], byte_acc2); } }
   __syncthreads();
   if (threadIdx.x < 2 * world && sc[threadIdx.x]) atomicAdd(out + threadIdx.x, sc[threadIdx.x]);
 }
 
-/* block-aggregated reservation: shared-memory atomics hand out positions inside the block's share, one global atomic per owner
- * and block reserves the share */
+/* Packing: positions inside an owner's stream come from warp votes (rank among the lanes of the same owner) and one warp prefix of
+ * the padded lengths per owner; the warp reserves its share with one shared atomic per owner, the block its share with one
+ * global atomic per owner. */
 __global__ void __launch_bounds__(256)
 fq_names_pack_kernel(const FqName* __restrict__ names, const uint8_t* __restrict__ data, uint32_t nrec, unsigned long long g0, uint32_t world,
                      FqPackedName* meta, uint8_t* blob, const unsigned long long* __restrict__ base, unsigned long long* cursor) {
   __shared__ unsigned long long s_cnt[2 * FQ_SHARD_MAX_SRC], s_base[2 * FQ_SHARD_MAX_SRC];
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
   for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < nrec; b0 += gridDim.x * blockDim.x) {
     if (threadIdx.x < 2 * world) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     uint32_t k = b0 + threadIdx.x;
     FqName nm; nm.hash = FQ_HASH_SKIP; nm.off = 0; nm.len = 0;
     if (k < nrec) nm = names[k];
-    bool valid = nm.hash != FQ_HASH_SKIP;
-    uint32_t o = 0; unsigned long long my_m = 0, my_b = 0;
-    if (valid) { o = fq_owner_of(nm.hash, world); my_m = atomicAdd(&s_cnt[2 * o], 1ull); my_b = atomicAdd(&s_cnt[2 * o + 1], (unsigned long long)((nm.len + 3u) & ~3u)); }
+    const bool valid = nm.hash != FQ_HASH_SKIP;
+    const uint32_t o = valid ? fq_owner_of(nm.hash, world) : 0xFFFFFFFFu;
+    const uint32_t len4 = (nm.len + 3u) & ~3u;
+    unsigned long long my_m = 0, my_b = 0;
+    for (uint32_t w = 0; w < world; w++) {
+      const uint32_t m = __ballot_sync(FULL, o == w);
+      if (!m) continue;
+      uint32_t incl = o == w ? len4 : 0u; /* prefix of the padded lengths over the lanes of this owner */
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += a; }
+      const uint32_t tot = __shfl_sync(FULL, incl, 31);
+      unsigned long long wm = 0, wb = 0;
+      if (lane == 0) { wm = atomicAdd(&s_cnt[2 * w], (unsigned long long)__popc(m)); wb = atomicAdd(&s_cnt[2 * w + 1], (unsigned long long)tot); }
+      wm = __shfl_sync(FULL, wm, 0); wb = __shfl_sync(FULL, wb, 0);
+      if (o == w) { my_m = wm + __popc(m & lt); my_b = wb + incl - len4; }
+    }
     __syncthreads();
     if (threadIdx.x < 2 * world) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(cursor + threadIdx.x, s_cnt[threadIdx.x]) : 0ull;
     __syncthreads();
