@@ -883,7 +883,7 @@ class FqCudaDevice : public FqDevice {
   void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) override {
     uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (ntiles == 0) { FQ_CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(uint32_t), st_)); return; }
-    if (ntiles > max_tiles_) throw std::runtime_error("scan_lines: chunk larger than 2 GiB");
+    if (ntiles > max_tiles_) throw std::runtime_error("scan_lines: chunk larger than 2 GiB (n=" + std::to_string(n) + ")");
     FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));
     FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
     tic(FQG_K_SCAN, n, ntiles);

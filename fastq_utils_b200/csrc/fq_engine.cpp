@@ -14,6 +14,9 @@
 
 static const uint32_t kPad = 64;                 /* readable bytes after every chunk */
 static const size_t kMaxChunk = 1ull << 31;      /* bytes per chunk: offsets are 32-bit */
+/* test hook: FQG_MAX_CHUNK_BYTES (a multiple of 16) cuts what is fed into smaller chunks, so that chunk boundaries inside records,
+ * bridges and every starting phase are reached with small inputs */
+static size_t feed_chunk() { const char* e = getenv("FQG_MAX_CHUNK_BYTES"); size_t v = e ? strtoull(e, nullptr, 10) & ~(size_t)15 : 0; return v >= 4096 && v < kMaxChunk ? v : kMaxChunk; }
 static const uint32_t kNone32 = 0xFFFFFFFFu;
 
 static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
@@ -107,8 +110,9 @@ FqRecCtx FqEngine::make_ctx(int file) const {
 void FqEngine::feed_host(int file, const void* bytes, size_t n, bool last) {
   const uint8_t* p = (const uint8_t*)bytes;
   if (n == 0) { add_buffer(file, nullptr, 0, last, false); return; }
+  const size_t maxc = feed_chunk();
   while (n) {
-    size_t k = std::min(n, kMaxChunk);
+    size_t k = std::min(n, maxc);
     uint8_t* d = (uint8_t*)dev_->alloc(k + kPad);
     dev_->upload(d, p, k);
     dev_->fill(d + k, 0, kPad);
@@ -119,8 +123,9 @@ void FqEngine::feed_host(int file, const void* bytes, size_t n, bool last) {
 void FqEngine::feed_device(int file, const void* dptr, size_t n, bool last) {
   uint8_t* p = (uint8_t*)dptr;
   if (n == 0) { add_buffer(file, nullptr, 0, last, false); return; }
+  const size_t maxc = feed_chunk();
   while (n) {
-    size_t k = std::min(n, kMaxChunk);
+    size_t k = std::min(n, maxc);
     if ((uintptr_t)p & 15u) { /* the kernels read 16 bytes at a time: an unaligned piece is copied once into an aligned chunk */
       uint8_t* d = (uint8_t*)dev_->alloc(k + kPad);
       dev_->copy(d, p, k);

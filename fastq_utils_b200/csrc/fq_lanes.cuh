@@ -359,9 +359,12 @@ fq_lanes_kernel(const LanesParams P) {
     const uint32_t cntW = cnt2 & 0xFFFFu, cntT = cnt2 >> 16; /* line ends inside the scanned range / inside the tile */
     if (tid == 0) {
       if (tile > 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
-      const uint32_t nxt = atomicAdd(P.ticket, 1u);
-      s_next = nxt; /* read after the barrier at the top of the next round */
-      if (nxt < P.ntiles && !(P.tune & 1u)) { /* pull the next tile into L2 now: its bulk copy, issued when this round is over, then finds it there */
+      /* Per-line mode claims the next tile now (and pulls it into L2).  The chunk-parallel mode claims at the end of the round: many
+       * of its tiles (long lines: no plus line inside) wait for the counts of the tiles in front, and a tile claimed a round before
+       * it is scanned would keep every tile behind it waiting that long. */
+      const uint32_t nxt = LINES ? atomicAdd(P.ticket, 1u) : 0xFFFFFFFFu;
+      if (LINES) s_next = nxt; /* read after the barrier at the top of the next round */
+      if (LINES && nxt < P.ntiles && !(P.tune & 1u)) { /* pull the next tile into L2 now: its bulk copy, issued when this round is over, then finds it there */
         const unsigned long long src = (unsigned long long)nxt * TILE - LN_LEFT;
         const unsigned long long have = ((unsigned long long)P.n - src + 15) & ~15ull;
         const uint32_t bytes = (uint32_t)(have < (unsigned long long)(LN_LEFT + TILE + LN_MARGIN) ? have : (unsigned long long)(LN_LEFT + TILE + LN_MARGIN));
@@ -611,6 +614,7 @@ fq_lanes_kernel(const LanesParams P) {
         }
       } else { p_nstage = 0; p_rl0 = 0; }
     }
+    if (!LINES && tid == 0) s_next = atomicAdd(P.ticket, 1u); /* everyone read s_next before the barriers of this round */
     pend = true; p_tile = tile; p_cnt = cntT; p_phi = phi; p_have_base = have_base; p_base = base_line;
     p_no_final_lf = P.virtual_end && tile == P.ntiles - 1 && P.n > 0 && win[nloc - 1] != '\n';
     buf ^= 1u;

@@ -372,3 +372,39 @@ def test_lanes_pass_statistics_roll_back(lanes_mode):
     tt2 = torch.frombuffer(bytearray(ok + b"\0" * 64), dtype=torch.uint8).cuda()
     rep, tr, pc = _run_ctx(fq.MODE_SINGLE, [(tt2.data_ptr(), len(ok))])
     assert tr == oracle_run(["-r", "a.fq"], ok, None) and pc["lanes"] == 1 and rep.file[0].min_rl == 150
+
+
+@pytest.mark.parametrize("chunk_bytes", [1 << 20, 3 << 20, (5 << 20) + 4096])
+def test_lanes_pass_longreads_many_chunks(chunk_bytes, monkeypatch):
+    """FQG_MAX_CHUNK_BYTES cuts a device-resident stream into small chunks: chunk boundaries fall inside long records, so every
+    starting phase (j0) and the bridge chunks are exercised; the clean-data pass must take every large chunk."""
+    import torch
+    import fastq_utils_b200 as fq
+    monkeypatch.setenv("FQG_MAX_CHUNK_BYTES", str(chunk_bytes))
+    g = torch.Generator().manual_seed(5)
+    nrec = 1500
+    lens = torch.exp(torch.randn(nrec, generator=g) + 8.9).clamp(1000, 100000).to(torch.int64)
+    hdr = fq.lib().fqg_synth_long_header_bytes()
+    off = torch.zeros(nrec + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(hdr + 2 * lens + 4, 0)
+    nb = int(off[-1])
+    t = torch.zeros(nb + 64, dtype=torch.uint8, device="cuda")
+    fq.synth_longreads(t, off.cuda(), 0, nrec, seed=5, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    data = bytes(t[:nb].cpu().numpy())
+    rep, tr, pc = _run_ctx(fq.MODE_SINGLE, [(t.data_ptr(), nb)])
+    assert tr == oracle_run(["-r", "a.fq"], data, None)
+    assert pc["lanes_handed_on"] == 0 and pc["two_pass_fallbacks"] == 0 and pc["lanes"] >= nb // chunk_bytes, pc
+
+
+@pytest.mark.parametrize("chunk_bytes", [1 << 20, (2 << 20) + 16])
+def test_lanes_pass_illumina_many_chunks(chunk_bytes, lanes_mode, monkeypatch):
+    import fastq_utils_b200 as fq
+    monkeypatch.setenv("FQG_MAX_CHUNK_BYTES", str(chunk_bytes))
+    n = 40_000
+    t, nb = _illumina(n)
+    data = bytes(t[:nb].cpu().numpy())
+    for mode, argv in ((fq.MODE_INDEX, ["a.fq"]), (fq.MODE_SINGLE, ["-r", "a.fq"])):
+        rep, tr, pc = _run_ctx(mode, [(t.data_ptr(), nb)], hint=n)
+        assert tr == oracle_run(argv, data, None), argv
+        assert pc["lanes_handed_on"] == 0 and pc["two_pass_fallbacks"] == 0 and pc["lanes"] >= nb // chunk_bytes, pc
