@@ -141,11 +141,20 @@ __device__ __forceinline__ void ls_qual_line(const uint8_t* win, const uint4* lu
 /* Block-wide look-back: the number of lines in front of `tile` = the counts of the tiles before it, summed back to the nearest
  * one whose inclusive count is known.  Every thread reads the states of four predecessors per round (1024 per round: hundreds of
  * tiles are in flight under persistent CTAs, and a round costs an L2 round trip plus a barrier).  Uniform over the block. */
+/* an anomaly was raised somewhere: the chunk goes to the per-record kernels whatever this pass still does, so everybody winds down */
+__device__ __forceinline__ bool ln_chunk_lost(const uint32_t* out) {
+  uint32_t a, o;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(a) : "l"(out + LN_O_ANOMALY));
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(o) : "l"(out + LN_O_OVERLONG));
+  return a != 0 || o != 0xFFFFFFFFu;
+}
 __device__ __forceinline__ unsigned long long ln_wait_state(const unsigned long long* p, uint32_t* out) {
   unsigned long long v64;
   uint32_t spins = 0;
-  while (((v64 = ld_volatile64(p)) >> 62) == 0)
+  while (((v64 = ld_volatile64(p)) >> 62) == 0) {
     if (++spins > (1u << 24)) { atomicExch(out + LN_O_INTERNAL, 2u); return ST_INCL; }
+    if ((spins & 63u) == 0 && ln_chunk_lost(out)) return ST_INCL; /* the tile we wait for may never be scanned: CTAs stop claiming tiles */
+  }
   if (spins) atomicAdd(out + LN_O_SPINS, spins);
   return v64;
 }
@@ -231,7 +240,7 @@ fq_lanes_kernel(const LanesParams P) {
   uint32_t seq_ok = 0x80808080u;           /* AND of the alphabet predicate over everything this thread checked (chunk-parallel mode) */
   uint32_t seq_bad = 0;                    /* OR of the alphabet differences (per-line mode) */
   uint32_t qmn = 0x00FF00FFu, qmx = 0u;    /* quality minimum / maximum, two 16-bit lanes */
-  uint32_t anomaly = 0;
+  uint32_t anomaly = 0, told = 0;
   /* the tile of the previous round: its line ends and names still wait for the number of lines in front of it */
   bool pend = false, p_have_base = false, p_no_final_lf = false;
   uint32_t p_tile = 0, p_cnt = 0, p_phi = 0, p_base = 0, p_nstage = 0, p_rl0 = 0;
@@ -251,6 +260,12 @@ fq_lanes_kernel(const LanesParams P) {
                    ::"r"(smem_u32(win + dst_off)), "l"(P.data + src), "r"(bytes), "r"(bar) : "memory");
     }
 
+    /* has the chunk been lost already (asked for now, looked at when the next tile is claimed: no waiting for the answer) */
+    uint32_t lost_a = 0, lost_o = 0xFFFFFFFFu;
+    if (tid == 0) {
+      asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(lost_a) : "l"(P.out + LN_O_ANOMALY));
+      asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(lost_o) : "l"(P.out + LN_O_OVERLONG));
+    }
     /* the state of one tile in front of the previous tile: asked for now, looked at in F */
     unsigned long long pre64 = 0;
     if (pend && !p_have_base && (int)p_tile - 1 - tid >= 0) pre64 = ld_volatile64(P.tile_state + ((int)p_tile - 1 - tid));
@@ -362,7 +377,7 @@ fq_lanes_kernel(const LanesParams P) {
       /* Per-line mode claims the next tile now (and pulls it into L2).  The chunk-parallel mode claims at the end of the round: many
        * of its tiles (long lines: no plus line inside) wait for the counts of the tiles in front, and a tile claimed a round before
        * it is scanned would keep every tile behind it waiting that long. */
-      const uint32_t nxt = LINES ? atomicAdd(P.ticket, 1u) : 0xFFFFFFFFu;
+      const uint32_t nxt = LINES ? ((lost_a != 0 || lost_o != 0xFFFFFFFFu) ? 0xFFFFFFFFu : atomicAdd(P.ticket, 1u)) : 0xFFFFFFFFu;
       if (LINES) s_next = nxt; /* read after the barrier at the top of the next round */
       if (LINES && nxt < P.ntiles && !(P.tune & 1u)) { /* pull the next tile into L2 now: its bulk copy, issued when this round is over, then finds it there */
         const unsigned long long src = (unsigned long long)nxt * TILE - LN_LEFT;
@@ -614,7 +629,9 @@ fq_lanes_kernel(const LanesParams P) {
         }
       } else { p_nstage = 0; p_rl0 = 0; }
     }
-    if (!LINES && tid == 0) s_next = atomicAdd(P.ticket, 1u); /* everyone read s_next before the barriers of this round */
+    if (!LINES && tid == 0) s_next = (lost_a != 0 || lost_o != 0xFFFFFFFFu) ? 0xFFFFFFFFu : atomicAdd(P.ticket, 1u); /* everyone read s_next before the barriers of this round */
+    if (seq_bad || (seq_ok & 0x80808080u) != 0x80808080u) anomaly |= LN_A_BASE;
+    if (anomaly & ~told) { atomicOr(P.out + LN_O_ANOMALY, anomaly); told |= anomaly; } /* known at once: the other CTAs stop early */
     pend = true; p_tile = tile; p_cnt = cntT; p_phi = phi; p_have_base = have_base; p_base = base_line;
     p_no_final_lf = P.virtual_end && tile == P.ntiles - 1 && P.n > 0 && win[nloc - 1] != '\n';
     buf ^= 1u;

@@ -408,3 +408,24 @@ def test_lanes_pass_illumina_many_chunks(chunk_bytes, lanes_mode, monkeypatch):
         rep, tr, pc = _run_ctx(mode, [(t.data_ptr(), nb)], hint=n)
         assert tr == oracle_run(argv, data, None), argv
         assert pc["lanes_handed_on"] == 0 and pc["two_pass_fallbacks"] == 0 and pc["lanes"] >= nb // chunk_bytes, pc
+
+
+def test_lanes_pass_winds_down_on_hostile_input(lanes_mode):
+    """Inputs on which no tile finds a plus line to vote with (a long run of bytes without LF, old-style '+name' lines): the pass
+    must give up quickly (every tile would otherwise wait for the tiles in front) and the per-record kernels decide."""
+    import time
+    import torch
+    import fastq_utils_b200 as fq
+    rb = fq.illumina_record_bytes()
+    t, nb = _illumina(20_000)
+    base = t[:nb].cpu().numpy().tobytes()
+    zeros = base + b"\0" * (8 << 20)
+    recs = base.split(b"\n")
+    named = b"\n".join((b"+" + recs[i - 2][1:] if i % 4 == 2 else r) for i, r in enumerate(recs))
+    for name, d in (("zero run", zeros), ("+name lines", named)):
+        tt = torch.frombuffer(bytearray(d + b"\0" * 64), dtype=torch.uint8).cuda()
+        t0 = time.perf_counter()
+        rep, tr, pc = _run_ctx(fq.MODE_SINGLE, [(tt.data_ptr(), len(d))])
+        dt = time.perf_counter() - t0
+        assert tr == oracle_run(["-r", "a.fq"], d, None), name
+        assert pc["lanes_handed_on"] == 1 and dt < 5.0, (name, pc, dt)
