@@ -967,7 +967,7 @@ class FqCudaDevice : public FqDevice {
       lanes_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
     }
     LanesParams P;
-    P.data = a.data; P.n = a.n; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
+    P.data = a.data; P.lead = a.lead; P.n = a.n; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
     P.tile_state = tile_state_; P.ticket = ticket_; P.ntiles = ntiles; P.out = a.out5;
     P.j0 = a.j0; P.cx = a.cx; P.names = a.names; P.names_cap = a.names_cap;
     { const char* e = getenv("FQG_LANES_TUNE"); P.tune = e ? (uint32_t)atoi(e) : 0u; }
@@ -983,7 +983,7 @@ class FqCudaDevice : public FqDevice {
   }
   void lanes_records(const FqTileArgs& a, bool undo) {
     LanesRecParams R;
-    R.line_end = a.line_end; R.out = a.out5; R.j0 = a.j0; R.names = a.names; R.cx = a.cx; R.stats = a.stats; R.hist = a.hist; R.undo = undo ? 1 : 0;
+    R.line_end = a.line_end; R.out = a.out5; R.j0 = a.j0; R.lead = a.lead; R.names = a.names; R.cx = a.cx; R.stats = a.stats; R.hist = a.hist; R.undo = undo ? 1 : 0;
     uint32_t max_rec = a.cap / 4 + 1;
     int grid = (int)std::min<uint32_t>((max_rec + 255) / 256, (uint32_t)sms_ * 8);
     tic(FQG_K_RECORDS, 0, max_rec);

@@ -71,6 +71,7 @@ typedef struct {
   uint32_t j0; uint32_t max_rec; uint64_t g0; uint64_t step_base; FqRecCtx cx;
   FqStats* stats; FqStats* stats_range; unsigned long long* hist; unsigned long long* key; FqName* names; uint32_t names_cap;
   uint32_t hint_line_len;    /* length of the file's first sequence line (0 = unknown): picks the clean-data pass's mode */
+  uint32_t lead;             /* clean-data pass only: the first `lead` (< 16) bytes of data[] are not the chunk's (offsets still count from data) */
 } FqTileArgs;
 
 #define FQ_LANES_OUT_WORDS 16

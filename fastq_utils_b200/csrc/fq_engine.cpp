@@ -123,17 +123,35 @@ void FqEngine::feed_host(int file, const void* bytes, size_t n, bool last) {
 void FqEngine::feed_device(int file, const void* dptr, size_t n, bool last) {
   uint8_t* p = (uint8_t*)dptr;
   if (n == 0) { add_buffer(file, nullptr, 0, last, false); return; }
-  const size_t maxc = feed_chunk();
+  const size_t maxc = std::min(feed_chunk(), kMaxChunk - 16);
+  FqFile& F = f_[file];
   while (n) {
     size_t k = std::min(n, maxc);
-    if ((uintptr_t)p & 15u) { /* the kernels read 16 bytes at a time: an unaligned piece is copied once into an aligned chunk */
-      uint8_t* d = (uint8_t*)dev_->alloc(k + kPad);
-      dev_->copy(d, p, k);
-      dev_->fill(d + k, 0, kPad);
-      add_buffer(file, d, (uint32_t)k, last && k == n, true);
-    } else add_buffer(file, p, (uint32_t)k, last && k == n, false);
+    /* the kernels read 16 bytes at a time: a chunk that starts at an unaligned address is handed over from the boundary below
+     * it, with the bytes in between marked as not its own (they are readable: same allocation) */
+    const uint32_t lead = (uint32_t)((uintptr_t)p & 15u);
+    const bool whole_records = F.pend_n == 0; /* nothing carried over: the chunk starts at a record start */
+    add_buffer(file, p - lead, (uint32_t)(k + lead), last && k == n, false, true, lead);
     p += k; n -= k;
+    /* A record cut by the end of the chunk normally travels on as pending bytes and is finished in a bridge chunk.  The bytes are
+     * still here, so the next chunk simply starts at that record instead: no bridge, no second pass over its lines. */
+    if (n && whole_records && !F.ended && F.pend_n > 0 && F.pend_n < k / 2) {
+      p -= F.pend_n; n += F.pend_n;
+      F.pend_n = 0; F.pend_lfs = 0;
+    }
   }
+}
+
+/* a borrowed chunk with bytes in front of its data that the clean-data pass did not take: the other kernels want the data at
+ * offset 0 of an aligned buffer */
+void FqEngine::realign(FqBuffer& B) {
+  if (!B.lead) return;
+  uint32_t k = B.n - B.lead;
+  uint8_t* d = (uint8_t*)dev_->alloc((size_t)k + kPad);
+  dev_->copy(d, B.data + B.lead, k);
+  dev_->fill(d + k, 0, kPad);
+  if (B.owned && B.data) dev_->release(B.data);
+  B.data = d; B.n = k; B.lead = 0; B.owned = true;
 }
 
 /* the fused pass stores only the line ends the host normally needs; anything else rebuilds the index with K1 */
@@ -215,7 +233,7 @@ bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip
 }
 
 /* K1+K2 fused over buffer b.  Returns false (nothing launched, or results discarded) when the two-pass path must be used. */
-bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap) {
+bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap, bool skip_lanes) {
   FqFile& F = f_[file];
   FqBuffer& B = F.bufs[b];
   int loop = loop_of(file);
@@ -235,9 +253,10 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
   a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; a.key = key_; a.names = names; a.names_cap = ncap;
   a.hint_line_len = F.first_seq_len;
+  a.lead = B.lead;
   /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
    * below decide (they own the reference's first-error semantics). */
-  if (lanes_ok_ && a.cx.space != FQ_SPACE_COLOR) {
+  if (lanes_ok_ && !skip_lanes && a.cx.space != FQ_SPACE_COLOR) {
     uint32_t linit[FQ_LANES_OUT_WORDS] = {0, 0, kNone32, 0, 0, kNone32, kNone32, 0, kNone32, 0, 0, 0, 0, 0, 0, 0};
     dev_->upload(tile_out_, linit, sizeof linit);
     if (dev_->lanes_pass(a)) {
@@ -256,6 +275,11 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
       path_counts[1]++;
       if (pass_ok) dev_->lanes_commit(a, true); /* counters went in before a record broke a length rule: take them back */
     } else dev_->sync();
+  }
+  if (B.lead) { /* the per-record kernels want the chunk's data at offset 0: the caller copies it and comes back */
+    if (names) dev_->release(names);
+    dev_->release(B.line_end); B.line_end = nullptr;
+    return false;
   }
   uint32_t init[6] = {0, 0, kNone32, 0, 0, 0};
   dev_->upload(tile_out_, init, sizeof init);
@@ -286,7 +310,7 @@ void FqEngine::fused_fallback() {
   reprocess();
 }
 
-void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned, bool allow_fused) {
+void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned, bool allow_fused, uint32_t lead) {
   FqFile& F = f_[file];
   if (F.ended) throw std::runtime_error("fqg_feed after the end of the file");
   if (cfg_.mode == FQG_MODE_INDEX_PAIR && file == 1 && !f_[0].ended) throw std::runtime_error("INDEX_PAIR: file 1 fed before file 0 ended");
@@ -302,20 +326,26 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
   bool fused = false; uint32_t fused_j0 = 0, fused_ncap = 0; uint64_t fused_g0 = 0; FqName* fused_names = nullptr;
   {
     FqBuffer& B = F.bufs[b];
-    B.data = data; B.n = n; B.owned = owned;
+    B.data = data; B.n = n; B.owned = owned; B.lead = lead;
     bool cached = false;
     for (size_t i = 0; i < F.prescans.size(); i++) {
       FqFile::Prescan& ps = F.prescans[i];
       if (ps.data == data && ps.n == n && ps.last == last) { B.line_end = ps.line_end; B.nlines = ps.nlines; F.prescans.erase(F.prescans.begin() + i); cached = true; break; }
     }
+    if (B.lead && (cached || !allow_fused || !fused_ok_ || n < fused_min_ || F.sniff_fmt < 0 || !F.started || F.pend_n > 0)) realign(B); /* a lead-in only where the clean-data pass may take it */
     if (!cached && allow_fused && fused_ok_ && n >= fused_min_) {
       fused_j0 = F.pend_n > 0 ? 4 - std::min<uint32_t>(F.pend_lfs, 3) : (F.started ? 0 : F.start_skip);
       fused_g0 = F.nrec + (F.pend_n > 0 ? 1 : 0);
       fused = try_fused_pass(file, b, last, fused_j0, fused_g0, &fused_names, &fused_ncap);
+      if (!fused && F.bufs[b].lead) { /* only the clean-data pass takes a chunk with a lead-in: copy it, then the per-record kernels */
+        realign(F.bufs[b]);
+        if (fused_ok_) fused = try_fused_pass(file, b, last, fused_j0, fused_g0, &fused_names, &fused_ncap, true);
+      }
     }
+    if (!fused) realign(F.bufs[b]); /* (no fused pass at all) */
     if (!fused && !cached && !F.bufs[b].line_end) scan_buffer(F.bufs[b], last);
   }
-  uint32_t pos = 0, j = 0;
+  uint32_t pos = F.bufs[b].lead, j = 0;
   if (!F.started) { /* multi-GPU: the first lines of a range belong to the previous range's last record */
     F.started = true;
     if (F.start_skip) {

@@ -14,6 +14,7 @@
 struct FqBuffer {
   uint8_t* data = nullptr;   /* device */
   uint32_t n = 0;
+  uint32_t lead = 0;         /* bytes in front of the chunk's own data (a chunk borrowed at an unaligned address starts at the 16-byte boundary below it) */
   bool owned = false;
   uint32_t* line_end = nullptr;
   uint32_t nlines = 0;       /* lines with an end inside the buffer (a final LF-less line counts when the file ended here) */
@@ -111,8 +112,9 @@ class FqEngine {
   int loop_of(int file) const;
   uint64_t step_base(int file) const;
   FqRecCtx make_ctx(int file) const;
-  void add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned, bool allow_fused = true);
-  bool try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap);
+  void add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned, bool allow_fused = true, uint32_t lead = 0);
+  void realign(FqBuffer& B);
+  bool try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap, bool skip_lanes = false);
   bool presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip, bool short_only = true);
   void fused_fallback();
   void segmentize(int file, int b, uint32_t pos, uint32_t j, bool last);

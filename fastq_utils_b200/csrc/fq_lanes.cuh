@@ -54,6 +54,7 @@ enum { LN_O_LINES = 0, LN_O_CAPOVF = 1, LN_O_OVERLONG = 2, LN_O_ANOMALY = 3, LN_
 
 struct LanesParams {
   const uint8_t* data; /* 16-byte aligned (bulk copies) */
+  uint32_t lead;       /* the first `lead` (< 16) bytes are not the chunk's own: its first line starts at data[lead] */
   uint32_t n; int virtual_end; uint32_t* line_end; uint32_t cap;
   unsigned long long* tile_state; uint32_t* ticket; uint32_t ntiles;
   uint32_t* out;
@@ -319,6 +320,7 @@ fq_lanes_kernel(const LanesParams P) {
       parity ^= 1;
     }
     if (tile == 0 && tid == 0) win[LN_LEFT - 1] = '\n';
+    const uint32_t lead0 = tile == 0 ? P.lead : 0u; /* line 0 of the first tile starts behind the lead-in */
 
     /* ---- A: LF flags; lane ↔ adjacent chunks (conflict-free 128-bit shared loads) */
     {
@@ -328,6 +330,7 @@ fq_lanes_kernel(const LanesParams P) {
         const uint32_t c = cbase + i * 32;
         uint32_t m = ln_lf_mask16(*(const uint4*)(win + LN_LEFT + 16 * c));
         if (!full) { uint32_t valid = ns > 16 * c ? min(16u, ns - 16 * c) : 0u; m &= (1u << valid) - 1u; }
+        if (c == 0) m &= ~((1u << lead0) - 1u);
         maskbuf[c] = (uint16_t)m;
       }
     }
@@ -475,7 +478,7 @@ fq_lanes_kernel(const LanesParams P) {
           const uint32_t k = (cls == 1u ? kS : cls == 3u ? kQ : kH) + 4 * i;
           if (cls == 0u && i < n) stage[i].len = 0xFFFFFFFFu; /* nothing to write out unless the header is judged below */
           if (i >= n) continue;
-          const uint32_t s = k == 0 ? (uint32_t)LN_LEFT : (uint32_t)lend[k - 1];
+          const uint32_t s = k == 0 ? (uint32_t)LN_LEFT + lead0 : (uint32_t)lend[k - 1];
           if (s >= tile_end) continue;
           uint32_t e; /* one past the line's last byte; has_lf: that byte is its LF */
           bool has_lf = true;
@@ -512,6 +515,7 @@ fq_lanes_kernel(const LanesParams P) {
           const uint32_t cls = (g0t + cum) & 3u;
           bool whole = m == 0;
           if (!full) whole = whole && nv >= 16 * (c0 + i) + 16;
+          if (i == 0) whole = whole && !(tid == 0 && lead0);
           is_seq |= (whole && cls == 1u) ? 1u << i : 0u;
           is_qual |= (whole && cls == 3u) ? 1u << i : 0u;
         }
@@ -600,7 +604,7 @@ fq_lanes_kernel(const LanesParams P) {
           for (uint32_t u = tid; u < nH + nP; u += LN_THREADS) {
             const bool is_hdr = u < nH;
             const uint32_t k = is_hdr ? kh0 + 4 * u : kp0 + 4 * (u - nH);
-            const uint32_t s = k == 0 ? (uint32_t)LN_LEFT : (uint32_t)lend[k - 1];
+            const uint32_t s = k == 0 ? (uint32_t)LN_LEFT + lead0 : (uint32_t)lend[k - 1];
             if (is_hdr) stage[u].len = 0xFFFFFFFFu; /* nothing to write out unless the header is judged below */
             if (s >= tile_end) continue;
             if (tile == 0 && k < P.j0) continue; /* lines of the record cut by the start of the chunk: judged with their record */
@@ -654,7 +658,7 @@ fq_lanes_kernel(const LanesParams P) {
  * sequence / quality lengths (:380), fastq_new_entry_stats (:97-110) and the index bookkeeping (n_entries, index_mem).
  * sign = -1 takes the same counts back (a chunk that failed one of these rules is not committed). */
 struct LanesRecParams {
-  const uint32_t* line_end; uint32_t* out; uint32_t j0; const FqName* names; FqRecCtx cx;
+  const uint32_t* line_end; uint32_t* out; uint32_t j0; uint32_t lead; const FqName* names; FqRecCtx cx;
   FqStats* stats; unsigned long long* hist; int undo;
 };
 __device__ __forceinline__ void hist_flush_signed(unsigned long long* hist, uint32_t len, uint32_t count, int undo) {
@@ -682,7 +686,7 @@ fq_lanes_records_kernel(const LanesRecParams P) {
     uint32_t flush_len = 0, flush_cnt = 0;
     if (r < nrec) {
       const uint32_t j = P.j0 + 4 * r;
-      const uint32_t s0 = j ? P.line_end[j - 1] : 0u, e0 = P.line_end[j], e1 = P.line_end[j + 1], e2 = P.line_end[j + 2], e3 = P.line_end[j + 3];
+      const uint32_t s0 = j ? P.line_end[j - 1] : P.lead, e0 = P.line_end[j], e1 = P.line_end[j + 1], e2 = P.line_end[j + 2], e3 = P.line_end[j + 3];
       const uint32_t hl = e0 - s0, sl = e1 - e0, pl = e2 - e1;
       uint32_t ql = e3 - e2;
       if (j + 3 == virt) ql += 1; /* last line of the file without LF: compare contents */
