@@ -844,6 +844,7 @@ class FqCudaDevice : public FqDevice {
     cudaSetDevice(dev_);
     cudaStreamSynchronize(st_); cudaStreamSynchronize(st2_);
     for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto& d : deferred_) cudaEventDestroy(d.ready);
     for (auto e : free_ev_) cudaEventDestroy(e);
     cudaFree(tile_state_);
     cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_);
@@ -864,7 +865,8 @@ class FqCudaDevice : public FqDevice {
   }
   void copy(void* d, const void* s, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st_)); }
   void fill(void* d, int b, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemsetAsync(d, b, n, st_)); }
-  void sync() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); }
+  void sync() override { flush_deferred(); FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); }
+  void sync_main() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); }
   void timer_start() override { FQ_CUDA_CHECK(cudaEventRecord(ev0_, st_)); }
   double timer_stop_ms() override {
     FQ_CUDA_CHECK(cudaEventRecord(ev1_, st_)); FQ_CUDA_CHECK(cudaEventSynchronize(ev1_));
@@ -922,6 +924,7 @@ class FqCudaDevice : public FqDevice {
     fq_records_kernel<<<grid, REC_THREADS, 0, st_>>>(P);
     toc();
     launched();
+    flush_deferred();
   }
   bool tile_pass(const FqTileArgs& a) override {
     if (!a.n || ((uintptr_t)a.data & 15u)) return false; /* its bulk copies need a 16-byte aligned chunk */
@@ -945,6 +948,7 @@ class FqCudaDevice : public FqDevice {
     tic(FQG_K_TILE, a.n, ntiles);
     fq_tile_kernel<<<grid, TILE_THREADS, TILE_SMEM, st_>>>(P);
     toc(); launched();
+    flush_deferred();
     return true;
   }
   bool lanes_pass(const FqTileArgs& a) override {
@@ -979,6 +983,7 @@ class FqCudaDevice : public FqDevice {
     else fq_lanes_kernel<false><<<grid, LN_THREADS, LN_SMEM, st_>>>(P);
     toc(); launched();
     lanes_records(a, false);
+    flush_deferred(); /* the previous chunk's inserts run beside this pass */
     return true;
   }
   void lanes_records(const FqTileArgs& a, bool undo) {
@@ -1001,17 +1006,31 @@ class FqCudaDevice : public FqDevice {
     P.dir1 = a.dir1; P.ndir1 = a.ndir1; P.key = a.key; P.counters = a.counters;
     return P;
   }
+  /* The insert kernel of a chunk is not launched at once: a kernel that starts on an idle GPU takes every register file, and the
+   * clean-data pass of the NEXT chunk (persistent CTAs, 56 registers) could not start beside it.  The launch waits until that pass
+   * has been launched (it leaves room for exactly one insert block per SM) or until somebody needs the results. */
   void index_insert(const FqTableArgs& a) override {
     if (!a.nrec) return;
-    int grid = (int)std::min<uint32_t>((a.nrec + 255) / 256, (uint32_t)sms_ * 8);
-    after_main();
-    tic(FQG_K_INDEX, 0, a.nrec, st2_);
-    fq_index_insert_kernel<<<grid, 256, 0, st2_>>>(table_params(a));
-    toc(st2_);
-    launched();
+    Deferred d; d.tp = table_params(a);
+    if (free_ev_.empty()) { FQ_CUDA_CHECK(cudaEventCreate(&d.ready)); } else { d.ready = free_ev_.back(); free_ev_.pop_back(); }
+    FQ_CUDA_CHECK(cudaEventRecord(d.ready, st_)); /* names, table fills and directories queued so far */
+    deferred_.push_back(d);
+  }
+  void flush_deferred() {
+    for (auto& d : deferred_) {
+      int grid = (int)std::min<uint32_t>((d.tp.nrec + 255) / 256, (uint32_t)sms_ * 8);
+      FQ_CUDA_CHECK(cudaStreamWaitEvent(st2_, d.ready, 0));
+      tic(FQG_K_INDEX, 0, d.tp.nrec, st2_);
+      fq_index_insert_kernel<<<grid, 256, 0, st2_>>>(d.tp);
+      toc(st2_);
+      launched();
+      free_ev_.push_back(d.ready); /* reused only after collect() / a later record: the wait above has been queued already */
+    }
+    deferred_.clear();
   }
   void mate_claim(const FqTableArgs& a) override {
     if (!a.nrec) return;
+    flush_deferred();
     int grid = (int)std::min<uint32_t>((a.nrec + 255) / 256, (uint32_t)sms_ * 8);
     after_main();
     tic(FQG_K_MATE, 0, a.nrec, st2_);
@@ -1096,6 +1115,7 @@ class FqCudaDevice : public FqDevice {
   }
   void toc(cudaStream_t st = nullptr) { FQ_CUDA_CHECK(cudaEventRecord(pending_.back().b, st ? st : st_)); }
   void collect() {
+    flush_deferred();
     if (pending_.empty()) return;
     FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
     for (auto& p : pending_) {
@@ -1105,6 +1125,8 @@ class FqCudaDevice : public FqDevice {
     }
     pending_.clear();
   }
+  struct Deferred { TableParams tp; cudaEvent_t ready; };
+  std::vector<Deferred> deferred_;
   KStat kst_[FQG_K_COUNT];
   std::vector<Pending> pending_;
   std::vector<cudaEvent_t> free_ev_;

@@ -87,6 +87,8 @@ class FqDevice {
   virtual void copy(void* dst, const void* src, size_t n) = 0;
   virtual void fill(void* dst, int byte, size_t n) = 0;
   virtual void sync() = 0;
+  /* wait for the copies and kernels queued on the main stream only (the index kernels on their own stream keep running) */
+  virtual void sync_main() { sync(); }
   /* K1: exclusive end offsets of all lines of data[0,n) in order; a last line without LF counts when virtual_end.
    * out[0] = number of lines, out[1] = 1 if more than cap were found (only the first cap are stored). */
   virtual void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) = 0;

@@ -468,7 +468,7 @@ void FqEngine::sync_dir(int file) {
     F.dir_dev = nd; F.dir_cap = cap; F.dir_synced = 0;
   }
   dev_->upload(F.dir_dev + F.dir_synced, F.dir_host.data() + F.dir_synced, (F.dir_host.size() - F.dir_synced) * sizeof(FqDirEntry));
-  dev_->sync(); /* dir_host may reallocate later */
+  dev_->sync_main(); /* dir_host may reallocate later; the upload is on the main stream, the index kernels need not be waited for */
   F.dir_synced = F.dir_host.size();
 }
 
