@@ -223,8 +223,22 @@ def main():
     dom = max(["scan", "records", "tile", "lanes"], key=lambda k: ks[k]["ms"])
     kd = ks[dom]
     ach = kd["bytes"] / (kd["ms"] / 1e3) / 1e9 if kd["ms"] > 0 else 0.0
+    # DRAM traffic of the dominant kernel per launch, from the committed `ncu --set full` capture of the same kernel on a
+    # 2.118 GB chunk (profiles/r1_lanes_perline_*_ncu_summary.txt), scaled to this run's bytes per launch
+    traffic = None
+    try:
+        import glob
+        import re
+        if dom == "lanes":
+            f = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1_lanes_perline_v*_ncu_summary.txt")))[-1]
+            txt = open(f, errors="ignore").read()
+            rd = float(re.search(r"dram__bytes_read\.sum\s+([\d.]+)\s+Gbyte", txt).group(1))
+            wr = float(re.search(r"dram__bytes_write\.sum\s+([\d.]+)\s+Mbyte", txt).group(1)) / 1e3
+            traffic = (rd + wr) * 1e9 / 2.1181e9 * (kd["bytes"] / max(1, kd["launches"]))
+    except Exception:
+        traffic = None
     roof = {"bound": "hbm", "kernel": {"scan": "fq_scan_kernel", "records": "fq_records_kernel", "tile": "fq_tile_kernel", "lanes": "fq_lanes_kernel"}[dom], "achieved": ach, "peak": peak, "peak_kind": peak_kind,
-            "unit": "GB/s", "frac": ach / peak, "traffic": None, "launches": kd["launches"], "avg_launch_ms": kd["ms"] / max(1, kd["launches"]),
+            "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write of the committed capture, scaled by launch size)", "launches": kd["launches"], "avg_launch_ms": kd["ms"] / max(1, kd["launches"]),
             "algorithmic_bytes_per_launch": kd["bytes"] / max(1, kd["launches"]),
             "all_kernels_ms_per_step": {k: v["ms"] / a.steps for k, v in ks.items()},
             "parse_validate_GBps": nb * a.steps / (sum(ks[k]["ms"] for k in ("scan", "records", "tile", "lanes")) / 1e3) / 1e9 if sum(ks[k]["ms"] for k in ("scan", "records", "tile", "lanes")) > 0 else None,
