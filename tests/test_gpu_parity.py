@@ -429,3 +429,31 @@ def test_lanes_pass_winds_down_on_hostile_input(lanes_mode):
         dt = time.perf_counter() - t0
         assert tr == oracle_run(["-r", "a.fq"], d, None), name
         assert pc["lanes_handed_on"] == 1 and dt < 5.0, (name, pc, dt)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("FQG_FUZZ_SEEDS", "48"))))
+def test_lanes_pass_fuzz_shapes(seed, lanes_mode, monkeypatch):
+    """Clean (and now and then slightly broken) files of many shapes — 1-base to 5000-base reads, every read-name style, ragged
+    lengths, with and without a final newline — through the clean-data pass on small inputs (FQG_FUSED_MIN_BYTES=1), fed from device
+    memory in one to three pieces cut at random bytes, small chunks now and then: transcripts equal the oracle's."""
+    import torch
+    import fastq_utils_b200 as fq
+    monkeypatch.setenv("FQG_FUSED_MIN_BYTES", "1")
+    rng = random.Random(40_000 + seed)
+    if rng.random() < 0.3:
+        monkeypatch.setenv("FQG_MAX_CHUNK_BYTES", str(rng.choice([4096, 65536, 1 << 20])))
+    style = rng.randrange(len(NAMES))
+    lmax = rng.choice([1, 5, 40, 150, 600, 1000, 1500, 5000])
+    lmin = lmax if rng.random() < 0.5 else 1
+    n = rng.choice([1, 3, 40, 400, 3000]) if lmax <= 150 else rng.choice([1, 3, 40, 200])
+    recs = make_file(rng, n, style, 1, seqlen=(lmin, lmax), qual=(rng.choice([14, 33, 35, 64]), rng.choice([74, 104, 126])))
+    if rng.random() < 0.25:
+        mutate(rng, recs)
+    d = render(rng, recs, "lf")
+    mode, argv = rng.choice([(fq.MODE_INDEX, ["a.fq"]), (fq.MODE_SINGLE, ["-r", "a.fq"])])
+    tt = torch.frombuffer(bytearray(d + b"\0" * 64), dtype=torch.uint8).cuda()
+    cuts = sorted(rng.sample(range(1, max(2, len(d))), k=min(rng.choice([0, 0, 1, 2]), max(0, len(d) - 1)))) if len(d) > 2 else []
+    edges = [0] + cuts + [len(d)]
+    pieces = [(tt.data_ptr() + a, b - a) for a, b in zip(edges[:-1], edges[1:]) if b > a] or [(tt.data_ptr(), 0)]
+    rep, tr, pc = _run_ctx(mode, pieces, hint=n)
+    assert tr == oracle_run(argv, d, None), (argv, lmin, lmax, n, cuts, pc)
