@@ -1,5 +1,5 @@
-"""World-1 run of the sharded orchestration (prescan, names to owners, owner-side insert) on 6 M synthetic reads: for ncu launch lists."""
-import os, sys
+"""World-1 run of the sharded orchestration (prescan, names to owners, owner-side insert) on synthetic reads: kernel times per class."""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import fastq_utils_b200 as fq
@@ -8,9 +8,19 @@ from fastq_utils_b200 import dist as fqdist
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5_900_000
 rb = fq.illumina_record_bytes()
 t = torch.zeros(n * rb + 64, dtype=torch.uint8, device="cuda")
-fq.synth_illumina(t, 0, n, seed=42, mate=1, perm_window=0, stream=torch.cuda.current_stream().cuda_stream)
+st = torch.cuda.current_stream().cuda_stream
+for s in range(0, n, 8_000_000):
+    k = min(8_000_000, n - s)
+    fq.synth_illumina(t[s * rb:], s, k, seed=42, mate=1, perm_window=0, stream=st)
 torch.cuda.synchronize()
 run = fqdist.ShardedFastqInfo(fq.MODE_INDEX, device=0, n_hint=n)
-for _ in range(2):
+for i in range(3):
+    if i == 1:
+        run.ctx.kernel_stats(reset=True); run.shard.kernel_stats(reset=True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
     res = run.run_device(t.data_ptr(), n * rb, name="a.fq")
-print(res["transcript"][0], res["transcript"][2][-60:])
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print("step ms", dt * 1e3, res["transcript"][0])
+for nm, c in (("ctx", run.ctx), ("shard", run.shard)):
+    ks = c.kernel_stats()
+    print(nm, {k: round(v["ms"] / 2, 3) for k, v in ks.items() if v["launches"]})
