@@ -573,6 +573,22 @@ fq_tile_kernel(const TileParams P) {
 #include "fq_lanes.cuh"
 
 /* ------------------------------------------------------------------------------------------------ K3 / K4: the index */
+/* exact compare of two names, four bytes at a time whatever their alignment (aligned loads + funnel shifts; reads at most 7 bytes
+ * past a name: chunks, bridges and blobs are padded) */
+__device__ __forceinline__ bool names_equal(const uint8_t* a, const uint8_t* b, uint32_t n) {
+  const uint32_t* wa = (const uint32_t*)((uintptr_t)a & ~(uintptr_t)3);
+  const uint32_t* wb = (const uint32_t*)((uintptr_t)b & ~(uintptr_t)3);
+  const uint32_t sa = ((uint32_t)(uintptr_t)a & 3u) * 8u, sb = ((uint32_t)(uintptr_t)b & 3u) * 8u;
+  uint32_t ca = wa[0], cb = wb[0];
+  for (uint32_t i = 0; i < n; i += 4) {
+    const uint32_t na = wa[(i >> 2) + 1], nb = wb[(i >> 2) + 1];
+    uint32_t diff = __funnelshift_r(ca, na, sa) ^ __funnelshift_r(cb, nb, sb);
+    ca = na; cb = nb;
+    if (n - i < 4) diff &= (1u << (8u * (n - i))) - 1u;
+    if (diff) return false;
+  }
+  return true;
+}
 __device__ __forceinline__ const uint8_t* dir_name(const FqDirEntry* dir, uint32_t nd, unsigned long long g, uint32_t* len) {
   uint32_t lo = 0, hi = nd;
   while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (dir[mid].g0 <= g) lo = mid; else hi = mid; }
@@ -618,7 +634,7 @@ fq_index_insert_kernel(const TableParams P) {
       unsigned long long old = atomicMin(&s->idx1, g);
       if (old != FQ_IDX_NONE) {
         uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, old, &ol);
-        if (ol == nm.len && fq_bytes_equal(on, P.data + nm.off, nm.len)) {
+        if (ol == nm.len && names_equal(on, P.data + nm.off, nm.len)) {
           unsigned long long later = old > g ? old : g; /* min over all arrivals of max(old, g) = 2nd smallest of the group */
           atomicMin(P.key, FQ_KEY(P.step_base + later, FQ_R_NAME));
         } else atomicAdd(P.counters + 0, 1ull);
@@ -645,7 +661,7 @@ fq_mate_claim_kernel(const TableParams P) {
       if (cur == FQ_HASH_EMPTY) { unpaired = g; break; }
       if (cur != nm.hash) continue;
       uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, s->idx1, &ol);
-      if (!(ol == nm.len && fq_bytes_equal(on, P.data + nm.off, nm.len))) { atomicAdd(P.counters + 0, 1ull); break; }
+      if (!(ol == nm.len && names_equal(on, P.data + nm.off, nm.len))) { atomicAdd(P.counters + 0, 1ull); break; }
       unsigned long long old = atomicMin(&P.slots[i].claim2, g);
       if (old == FQ_IDX_NONE) claimed++;           /* first claim = the reference's delete */
       else unpaired = old > g ? old : g;           /* the entry was already deleted when the later one arrives */
@@ -667,7 +683,7 @@ fq_pair_compare_kernel(const PairParams P) {
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.npairs; k += gridDim.x * blockDim.x) {
     const FqName x = P.a[(size_t)k * P.stride_a], y = P.b[(size_t)k * P.stride_b];
     if (x.hash == FQ_HASH_SKIP || y.hash == FQ_HASH_SKIP) continue;
-    bool same = x.hash == y.hash && x.len == y.len && fq_bytes_equal(P.da + x.off, P.db + y.off, x.len);
+    bool same = x.hash == y.hash && x.len == y.len && names_equal(P.da + x.off, P.db + y.off, x.len);
     if (!same) atomicMin(P.key, FQ_KEY(P.p0 + k, P.rank));
   }
 }
@@ -772,7 +788,7 @@ fq_shard_insert_kernel(const ShardParams P) {
       unsigned long long old = atomicMin(&s->idx1, mine);
       if (old != FQ_IDX_NONE) {
         uint32_t ol, ml; const uint8_t* on = shard_name(a, old & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
-        if (ol == ml && fq_bytes_equal(on, mn, ml)) {
+        if (ol == ml && names_equal(on, mn, ml)) {
           unsigned long long og = old >> FQ_SHARD_POS_BITS, later = og > pn.record ? og : pn.record;
           atomicMin(a.dup_key, FQ_KEY(later, FQ_R_NAME));
         } else atomicAdd(a.counters + 0, 1ull);
@@ -800,7 +816,7 @@ fq_shard_claim_kernel(const ClaimParams P) {
       if (cur == FQ_HASH_EMPTY) { unpaired = pn.record; break; }
       if (cur != pn.hash) continue;
       uint32_t ol, ml; const uint8_t* on = shard_name(P.ins, s->idx1 & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
-      if (!(ol == ml && fq_bytes_equal(on, mn, ml))) { atomicAdd(a.counters + 0, 1ull); break; }
+      if (!(ol == ml && names_equal(on, mn, ml))) { atomicAdd(a.counters + 0, 1ull); break; }
       unsigned long long old = atomicMin(&a.slots[i].claim2, pn.record);
       if (old == FQ_IDX_NONE) claimed++;
       else unpaired = old > pn.record ? old : pn.record;
@@ -1009,26 +1025,8 @@ class FqCudaDevice : public FqDevice {
   /* The insert kernel of a chunk is not launched at once: a kernel that starts on an idle GPU takes every register file, and the
    * clean-data pass of the NEXT chunk (persistent CTAs, 56 registers) could not start beside it.  The launch waits until that pass
    * has been launched (it leaves room for exactly one insert block per SM) or until somebody needs the results. */
-  void index_insert(const FqTableArgs& a) override {
-    if (!a.nrec) return;
-    Deferred d; d.tp = table_params(a);
-    if (free_ev_.empty()) { FQ_CUDA_CHECK(cudaEventCreate(&d.ready)); } else { d.ready = free_ev_.back(); free_ev_.pop_back(); }
-    FQ_CUDA_CHECK(cudaEventRecord(d.ready, st_)); /* names, table fills and directories queued so far */
-    deferred_.push_back(d);
-  }
-  void flush_deferred() {
-    for (auto& d : deferred_) {
-      int grid = (int)std::min<uint32_t>((d.tp.nrec + 255) / 256, (uint32_t)sms_ * 8);
-      FQ_CUDA_CHECK(cudaStreamWaitEvent(st2_, d.ready, 0));
-      tic(FQG_K_INDEX, 0, d.tp.nrec, st2_);
-      fq_index_insert_kernel<<<grid, 256, 0, st2_>>>(d.tp);
-      toc(st2_);
-      launched();
-      free_ev_.push_back(d.ready); /* reused only after collect() / a later record: the wait above has been queued already */
-    }
-    deferred_.clear();
-  }
-  void mate_claim(const FqTableArgs& a) override {
+  void index_insert(const FqTableArgs& a) override { defer(a, false); }
+  void mate_claim(const FqTableArgs& a) override { /* not deferred: a claim compares name bytes, one block per SM beside the pass is too slow for it (measured 40 ms against 9) */
     if (!a.nrec) return;
     flush_deferred();
     int grid = (int)std::min<uint32_t>((a.nrec + 255) / 256, (uint32_t)sms_ * 8);
@@ -1037,6 +1035,26 @@ class FqCudaDevice : public FqDevice {
     fq_mate_claim_kernel<<<grid, 256, 0, st2_>>>(table_params(a));
     toc(st2_);
     launched();
+  }
+  void defer(const FqTableArgs& a, bool claim) {
+    if (!a.nrec) return;
+    Deferred d; d.tp = table_params(a); d.claim = claim;
+    if (free_ev_.empty()) { FQ_CUDA_CHECK(cudaEventCreate(&d.ready)); } else { d.ready = free_ev_.back(); free_ev_.pop_back(); }
+    FQ_CUDA_CHECK(cudaEventRecord(d.ready, st_)); /* names, table fills and directories queued so far */
+    deferred_.push_back(d);
+  }
+  void flush_deferred() { /* in order: the claims of the mate loop come after every insert of the index loop */
+    for (auto& d : deferred_) {
+      int grid = (int)std::min<uint32_t>((d.tp.nrec + 255) / 256, (uint32_t)sms_ * 8);
+      FQ_CUDA_CHECK(cudaStreamWaitEvent(st2_, d.ready, 0));
+      tic(d.claim ? FQG_K_MATE : FQG_K_INDEX, 0, d.tp.nrec, st2_);
+      if (d.claim) fq_mate_claim_kernel<<<grid, 256, 0, st2_>>>(d.tp);
+      else fq_index_insert_kernel<<<grid, 256, 0, st2_>>>(d.tp);
+      toc(st2_);
+      launched();
+      free_ev_.push_back(d.ready); /* reused only after a later record: the wait above has been queued already */
+    }
+    deferred_.clear();
   }
   void pair_compare(const FqPairArgs& a) override {
     if (!a.npairs) return;
@@ -1125,7 +1143,7 @@ class FqCudaDevice : public FqDevice {
     }
     pending_.clear();
   }
-  struct Deferred { TableParams tp; cudaEvent_t ready; };
+  struct Deferred { TableParams tp; cudaEvent_t ready; bool claim; };
   std::vector<Deferred> deferred_;
   KStat kst_[FQG_K_COUNT];
   std::vector<Pending> pending_;
