@@ -74,7 +74,7 @@ typedef struct {
   uint32_t lead;             /* clean-data pass only: the first `lead` (< 16) bytes of data[] are not the chunk's (offsets still count from data) */
 } FqTileArgs;
 
-#define FQ_LANES_OUT_WORDS 16
+#define FQ_LANES_OUT_WORDS 24 /* [16..23]: the last 8 line ends of the chunk (fewer when it has fewer lines) */
 class FqDevice {
  public:
   virtual ~FqDevice() {}

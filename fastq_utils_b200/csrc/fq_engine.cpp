@@ -27,7 +27,7 @@ FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) 
   counters_ = (unsigned long long*)dev_->alloc(4 * sizeof(unsigned long long));
   scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
   recout_ = (FqRecOut*)dev_->alloc(sizeof(FqRecOut));
-  tile_out_ = (uint32_t*)dev_->alloc(16 * sizeof(uint32_t));
+  tile_out_ = (uint32_t*)dev_->alloc(32 * sizeof(uint32_t));
   for (int f = 0; f < 2; f++) {
     f_[f].stats = (FqStats*)dev_->alloc(sizeof(FqStats));
     f_[f].hist = (unsigned long long*)dev_->alloc((size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
@@ -163,6 +163,7 @@ void FqEngine::ensure_full_index(FqBuffer& b) {
   b.index_partial = false;
 }
 uint32_t FqEngine::line_end_at(FqBuffer& b, uint32_t idx) {
+  if (idx >= b.tail_from && idx < b.tail_from + b.tail_n) return b.tail_ends[idx - b.tail_from];
   if (b.index_partial && idx >= 8 && idx < b.index_from) ensure_full_index(b);
   uint32_t v; dev_->download(&v, b.line_end + idx, sizeof v); return v;
 }
@@ -257,7 +258,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
    * below decide (they own the reference's first-error semantics). */
   if (lanes_ok_ && !skip_lanes && a.cx.space != FQ_SPACE_COLOR) {
-    uint32_t linit[FQ_LANES_OUT_WORDS] = {0, 0, kNone32, 0, 0, kNone32, kNone32, 0, kNone32, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t linit[FQ_LANES_OUT_WORDS] = {0, 0, kNone32, 0, 0, kNone32, kNone32, 0, kNone32, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     dev_->upload(tile_out_, linit, sizeof linit);
     if (dev_->lanes_pass(a)) {
       uint32_t o[FQ_LANES_OUT_WORDS];
@@ -269,6 +270,8 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
         dev_->lanes_commit(a, false);
         path_counts[0]++;
         B.nlines = o[0]; B.index_partial = false; B.index_virtual_end = last;
+        B.tail_from = o[0] > 8 ? o[0] - 8 : 0; B.tail_n = o[0] - B.tail_from;
+        for (uint32_t i = 0; i < B.tail_n; i++) B.tail_ends[i] = o[16 + i];
         *names_out = names; *names_cap = ncap;
         return true;
       }
@@ -411,7 +414,16 @@ void FqEngine::segmentize(int file, int b, uint32_t pos, uint32_t j, bool last) 
     uint32_t avail = B.nlines - j, nrec = avail / 4;
     uint32_t a = kNone32;
     if (B.index_partial && !(j >= 1 && j - 1 >= B.index_from) && !(B.nlines <= 8)) { ensure_full_index(F.bufs[b]); }
-    if (avail > 0 || (!last && pos < B.n)) {
+    if (avail <= 3 && B.tail_n && (avail == 0 || (j >= B.tail_from && j + avail <= B.tail_from + B.tail_n))) {
+      /* the lines after the last complete record: their ends came back with the pass's result words */
+      uint32_t total = avail + (last ? 0u : 1u), start = pos;
+      for (uint32_t i = 0; i < total; i++) {
+        uint32_t end = i < avail ? B.tail_ends[j + i - B.tail_from] : B.n;
+        uint32_t lim = (i & 1u) == 0 ? FQ_MAX_LABEL_LENGTH : FQ_MAX_READ_LENGTH;
+        if (end - start >= lim) { a = j + i; break; }
+        start = end;
+      }
+    } else if (avail > 0 || (!last && pos < B.n)) {
       dev_->fill(scratch_, 0xFF, sizeof(uint32_t));
       dev_->find_overlong(B.line_end, pos, j, avail, B.n, last ? 0 : 1, scratch_);
       dev_->download(&a, scratch_, sizeof a);

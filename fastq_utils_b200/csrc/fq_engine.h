@@ -21,6 +21,9 @@ struct FqBuffer {
   bool index_partial = false; /* fused pass: only line ends [0,8) and [index_from, nlines) are stored */
   uint32_t index_from = 0;
   bool index_virtual_end = false;
+  /* the last line ends of the chunk, read back together with the pass's result words: the host needs only these (where the last
+   * complete record ends, how long the lines after it are) and would otherwise fetch them one synchronising copy at a time */
+  uint32_t tail_from = 0, tail_n = 0, tail_ends[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct FqSegment {

@@ -677,6 +677,10 @@ fq_lanes_records_kernel(const LanesRecParams P) {
   if (P.out[LN_O_CAPOVF] || P.out[LN_O_OVERLONG] != 0xFFFFFFFFu || P.out[LN_O_ANOMALY] || P.out[LN_O_INTERNAL]) return;
   const uint32_t nlines = P.out[LN_O_LINES], virt = P.out[LN_O_VIRTUAL];
   const uint32_t nrec = nlines > P.j0 ? (nlines - P.j0) / 4 : 0;
+  if (!P.undo && blockIdx.x == 0 && threadIdx.x < 8) { /* the last line ends travel to the host with the result words */
+    const uint32_t from = nlines > 8 ? nlines - 8 : 0;
+    if (from + threadIdx.x < nlines) P.out[16 + threadIdx.x] = P.line_end[from + threadIdx.x];
+  }
   const int lane = threadIdx.x & 31;
   unsigned long long my_rds = 0, my_names = 0, my_mem = 0;
   uint32_t mn_rl = 0xFFFFFFFFu, mx_rl = 0, run_len = 0, run_cnt = 0, bad = 0;
