@@ -756,8 +756,10 @@ fq_names_pack_kernel(const FqName* __restrict__ names, const uint8_t* __restrict
       unsigned long long bo = s_base[2 * o + 1] + my_b; /* multiple of 4: names are padded to whole words in the blob */
       FqPackedName pn; pn.hash = nm.hash; pn.record = g0 + k; pn.off = (uint32_t)bo; pn.len = nm.len;
       meta[base[2 * o] + s_base[2 * o] + my_m] = pn;
-      uint32_t* dst = (uint32_t*)(blob + base[2 * o + 1] + bo);
-      for (uint32_t i = 0; i < nm.len; i += 4) dst[i >> 2] = fq_low_bytes(fq_ldu32(data, nm.off + i), nm.len - i);
+      if (blob) { /* without a blob only the tuples travel: equal hashes are then verified in a second round (rarely needed) */
+        uint32_t* dst = (uint32_t*)(blob + base[2 * o + 1] + bo);
+        for (uint32_t i = 0; i < nm.len; i += 4) dst[i >> 2] = fq_low_bytes(fq_ldu32(data, nm.off + i), nm.len - i);
+      }
     }
     __syncthreads();
   }
@@ -786,7 +788,8 @@ fq_shard_insert_kernel(const ShardParams P) {
       if (slot_claim128(s, pn.hash, mine, &cur, &cur_idx)) break; /* first arrival of this name: one atomic on one sector */
       if (cur != pn.hash) continue;
       unsigned long long old = atomicMin(&s->idx1, mine);
-      if (old != FQ_IDX_NONE) {
+      if (old != FQ_IDX_NONE && !a.blob) atomicAdd(a.counters + 0, 1ull); /* tuples only: an equal hash cannot be judged here */
+      else if (old != FQ_IDX_NONE) {
         uint32_t ol, ml; const uint8_t* on = shard_name(a, old & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
         if (ol == ml && names_equal(on, mn, ml)) {
           unsigned long long og = old >> FQ_SHARD_POS_BITS, later = og > pn.record ? og : pn.record;

@@ -480,7 +480,8 @@ void FqEngine::sync_dir(int file) {
     F.dir_dev = nd; F.dir_cap = cap; F.dir_synced = 0;
   }
   dev_->upload(F.dir_dev + F.dir_synced, F.dir_host.data() + F.dir_synced, (F.dir_host.size() - F.dir_synced) * sizeof(FqDirEntry));
-  dev_->sync_main(); /* dir_host may reallocate later; the upload is on the main stream, the index kernels need not be waited for */
+  /* no wait: a copy from pageable host memory has left the source buffer when cudaMemcpyAsync returns (it is staged), so dir_host
+   * may grow or move afterwards */
   F.dir_synced = F.dir_host.size();
 }
 

@@ -144,10 +144,13 @@ class ShardedFastqInfo:
         expected = (lfs + virt - skip[r] + (skip[r + 1] if r < W - 1 else 0)) // 4
         return expected, total_records
 
-    def _route_names(self, f):
-        """Step 3, sender side: pack the names of file f by owner and exchange them.  Returns what the owner needs."""
+    def _route_names(self, f, with_bytes=True):
+        """Step 3, sender side: pack the names of file f by owner and exchange them.  Returns what the owner needs.
+        with_bytes=False sends the 24-byte tuples only (a quarter of the volume, no byte gathering)."""
         W, r = self.world, self.rank
         counts, nb = self.ctx.names_count(f, W)
+        if not with_bytes:
+            nb = [0] * W
         theirs = self._gather((counts, nb))
         in_meta, in_blob = [c * 24 for c in counts], list(nb)
         out_cnt = [theirs[s][0][r] for s in range(W)]
@@ -158,7 +161,7 @@ class ShardedFastqInfo:
             blob_base[o] = blob_base[o - 1] + nb[o - 1]
         send_meta = torch.empty(sum(in_meta) + 64, dtype=torch.uint8, device=self.tdev)
         send_blob = torch.empty(sum(in_blob) + 64, dtype=torch.uint8, device=self.tdev)
-        self.ctx.names_pack(f, W, send_meta.data_ptr(), send_blob.data_ptr(), meta_base, blob_base)
+        self.ctx.names_pack(f, W, send_meta.data_ptr(), send_blob.data_ptr() if with_bytes else 0, meta_base, blob_base)
         self._sync()
         recv_meta = self._a2a(send_meta, in_meta, out_meta)
         recv_blob = self._a2a(send_blob, in_blob, out_blob)
@@ -195,9 +198,20 @@ class ShardedFastqInfo:
         # -- 3. names to their owners
         dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0
         if self.shard is not None:
-            meta, blob, ms, bs = self._route_names(0)
-            self.shard.shard_insert(meta.data_ptr(), ms[-1], blob.data_ptr(), ms, bs)
-            dkey, drec, dname, coll = self.shard.shard_result()
+            # one file: the tuples travel alone first; only if some owner met an equal hash (a duplicate name or a 64-bit collision) is
+            # the exchange repeated with the name bytes, which the owner then compares.  The mate loop needs the bytes anyway.
+            coll = 1
+            if not pair:
+                meta, blob, ms, bs = self._route_names(0, with_bytes=False)
+                self.shard.shard_insert(meta.data_ptr(), ms[-1], 0, ms, bs)
+                dkey, drec, dname, coll = self.shard.shard_result()
+                coll = sum(self._gather(coll))
+                if coll:
+                    self.shard.reset()
+            if coll:
+                meta, blob, ms, bs = self._route_names(0)
+                self.shard.shard_insert(meta.data_ptr(), ms[-1], blob.data_ptr(), ms, bs)
+                dkey, drec, dname, coll = self.shard.shard_result()
             dup = (dkey, drec, dname)
             if pair and T0 > 0:
                 meta2, blob2, ms2, bs2 = self._route_names(1)

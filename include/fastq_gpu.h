@@ -142,7 +142,10 @@ int fqg_prescan_device(fqg_ctx* ctx, int file, const void* device_bytes, size_t 
  * number `first_record` of the whole file (event keys, line numbers and name indices become global) */
 int fqg_set_stream_start(fqg_ctx* ctx, int file, uint32_t skip_lines, uint64_t first_record);
 /* names of all records fed so far, routed by hash to `world` owners: sizes, then the packed tuples
- * (24-byte fqg_packed_name grouped by owner + the name bytes grouped by owner) into caller-provided device memory */
+ * (24-byte fqg_packed_name grouped by owner + the name bytes grouped by owner) into caller-provided device memory.
+ * device_blob may be NULL: then only the tuples are packed; fqg_shard_insert with a NULL blob counts every equal hash as a
+ * hash collision instead of judging it, and the caller repeats the exchange with the name bytes when any owner reports one
+ * (a duplicate read name or a 64-bit collision: both rare) */
 typedef struct { uint64_t hash; uint64_t record; uint32_t off; uint32_t len; } fqg_packed_name;
 int fqg_names_count(fqg_ctx* ctx, int file, uint32_t world, uint64_t* counts, uint64_t* bytes);
 int fqg_names_pack(fqg_ctx* ctx, int file, uint32_t world, void* device_meta, void* device_blob,

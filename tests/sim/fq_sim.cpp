@@ -188,7 +188,7 @@ class FqSimDevice : public FqDevice {
       unsigned long long mi = cursor[2 * o]++, bo = cursor[2 * o + 1]; cursor[2 * o + 1] += (nm.len + 3u) & ~3u;
       FqPackedName& pn = meta[base[2 * o] + mi];
       pn.hash = nm.hash; pn.record = g0 + k; pn.off = (uint32_t)bo; pn.len = nm.len;
-      memcpy(blob + base[2 * o + 1] + bo, data + nm.off, nm.len);
+      if (blob) memcpy(blob + base[2 * o + 1] + bo, data + nm.off, nm.len);
     }
   }
   static const uint8_t* shard_name(const FqShardArgs& a, unsigned long long pos, uint32_t* len) {
@@ -208,6 +208,7 @@ class FqSimDevice : public FqDevice {
         if (s.hash == FQ_HASH_EMPTY) { s.hash = pn.hash; s.idx1 = mine; break; }
         if (s.hash != pn.hash) continue;
         unsigned long long old = s.idx1; if (mine < old) s.idx1 = mine;
+        if (!a.blob) { a.counters[0]++; break; } /* tuples only: an equal hash cannot be judged here */
         uint32_t ol, ml; const uint8_t* on = shard_name(a, old & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
         if (ol == ml && fq_bytes_equal(on, mn, ml)) {
           unsigned long long later = std::max(old >> FQ_SHARD_POS_BITS, (unsigned long long)pn.record);
