@@ -144,6 +144,68 @@ class ShardedFastqInfo:
         expected = (lfs + virt - skip[r] + (skip[r + 1] if r < W - 1 else 0)) // 4
         return expected, total_records
 
+    def _guess_phase(self, ptr, nbytes):
+        """Line class (0 header, 1 sequence, 2 plus, 3 quality) of the line this range starts in, from the range's own first lines:
+        a complete line that is exactly "+" is a plus line.  Returns (ok, class, ends of the first four lines, ends with LF)."""
+        if nbytes < 4096:
+            return (False, 0, [KEY_NONE] * 4, True)
+        k = min(nbytes, 1 << 18)
+        head = bytes(_as_tensor(ptr, k, self.tdev).cpu().numpy())
+        last = bytes(_as_tensor(ptr + nbytes - 1, 1, self.tdev).cpu().numpy())
+        ends, pos = [], -1
+        while len(ends) < 64:
+            pos = head.find(b"\n", pos + 1)
+            if pos < 0:
+                break
+            ends.append(pos + 1)
+        cls = None
+        for i in range(1, len(ends)):  # line i = head[ends[i-1]:ends[i]-1], complete
+            if ends[i] - ends[i - 1] == 2 and head[ends[i - 1]] == 0x2B:
+                cls = (2 - i) % 4
+                break
+        if cls is None or len(ends) < 5:
+            return (False, 0, [KEY_NONE] * 4, last == b"\n")
+        return (True, cls, ends[:4], last == b"\n")
+
+    def _feed_file_speculative(self, f, ptr, nbytes):
+        """Steps 1-2 without counting the line feeds of the range first: every rank takes the line phase of its range from its own
+        first plus line.  A wrong guess cannot go unnoticed on a valid file (a sequence line lands where a header or a plus line is
+        expected), so any error afterwards simply sends the whole job through the exact path.  False: not applicable here."""
+        W, r, ctx = self.world, self.rank, self.ctx
+        info = self._gather(self._guess_phase(ptr, nbytes) + (nbytes,))
+        if not all(x[0] for x in info) or info[0][1] != 0:
+            return False
+        skip, cut = [0] * W, [0] * W
+        for i in range(1, W):
+            cls0, prev_lf = info[i][1], info[i - 1][3]
+            skip[i] = 0 if (prev_lf and cls0 == 0) else ((4 - cls0) % 4 or 4)
+            cut[i] = info[i][2][skip[i] - 1] if skip[i] > 0 else 0
+        sn = ctx.sniff_device(f, ptr, nbytes, 0) if r == 0 else None
+        sn = self._gather(sn)[0]
+        if sn[0] >= 0:
+            ctx.set_sniff(f, sn[0], sn[1])
+        head, reqs = None, []
+        if r > 0 and cut[r] > 0:
+            view = _as_tensor(ptr, cut[r], self.tdev)
+            reqs.append(dist.isend(view, r - 1))
+            self._keep.append(view)
+        if r < W - 1 and cut[r + 1] > 0:
+            head = torch.zeros(cut[r + 1] + 64, dtype=torch.uint8, device=self.tdev)
+            reqs.append(dist.irecv(head[:cut[r + 1]], r + 1))
+        for q in reqs:
+            q.wait()
+        ctx.set_stream_start(f, skip[r], 0)  # record numbers inside the range: they only matter when something is wrong
+        if r == W - 1:
+            ctx.feed_device(f, ptr, nbytes, last=True)
+        else:
+            ctx.feed_device(f, ptr, nbytes, last=False)
+            if head is not None:
+                ctx.feed_device(f, head.data_ptr(), cut[r + 1], last=True)
+                self._keep.append(head)
+            else:
+                ctx.feed(f, b"", last=True)
+        return True
+
     def _route_names(self, f, with_bytes=True):
         """Step 3, sender side: pack the names of file f by owner and exchange them.  Returns what the owner needs.
         with_bytes=False sends the 24-byte tuples only (a quarter of the volume, no byte gathering)."""
@@ -175,7 +237,7 @@ class ShardedFastqInfo:
         return recv_meta, recv_blob, ms, bs
 
     # ------------------------------------------------------------------ one job
-    def run_device(self, ptr, nbytes, name="-", ptr2=None, nbytes2=0, name2=None, empty_ok=False, no_enc_ok=False):
+    def run_device(self, ptr, nbytes, name="-", ptr2=None, nbytes2=0, name2=None, empty_ok=False, no_enc_ok=False, _exact=False):
         """ptr/nbytes (and ptr2/nbytes2 for MODE_INDEX_PAIR): this rank's byte range of each file in device memory (16-byte
         aligned, 64 readable bytes after it).  Returns the merged report and, on rank 0, the rendered (rc, stdout, stderr)."""
         W, r, ctx = self.world, self.rank, self.ctx
@@ -184,43 +246,57 @@ class ShardedFastqInfo:
             self.shard.reset()
         self._keep = []
         pair = self.mode == api.MODE_INDEX_PAIR
-        exp0, T0 = self._feed_file(0, ptr, nbytes)
-        exp1, T1 = None, 0
-        if pair:
-            ctx.set_file_total(0, T0)
-            if T0 > 0:
-                exp1, T1 = self._feed_file(1, ptr2, nbytes2)
-        rep = ctx.finish()
-        local_key = rep.error.event_key if rep.error.code != 0 else KEY_NONE
-        stopped = (exp0 is not None and rep.file[0].n_records < exp0) or (exp1 is not None and rep.file[1].n_records < exp1)
-        if rep.error.code == 0 and stopped:
-            raise NotImplementedError("NUL-led header line (early clean EOF) in a sharded run")
-        # -- 3. names to their owners
-        dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0
-        if self.shard is not None:
-            # one file: the tuples travel alone first; only if some owner met an equal hash (a duplicate name or a 64-bit collision) is
-            # the exchange repeated with the name bytes, which the owner then compares.  The mate loop needs the bytes anyway.
-            coll = 1
-            if not pair:
+        again = dict(name=name, ptr2=ptr2, nbytes2=nbytes2, name2=name2, empty_ok=empty_ok, no_enc_ok=no_enc_ok, _exact=True)
+        speculative = (not _exact) and W > 1 and not pair and self._feed_file_speculative(0, ptr, nbytes)
+        if speculative:
+            rep = ctx.finish()
+            bad = any(self._gather(rep.error.code != 0))  # every rank takes the same turn: the steps below are collective
+            if not bad and self.shard is not None:
                 meta, blob, ms, bs = self._route_names(0, with_bytes=False)
                 self.shard.shard_insert(meta.data_ptr(), ms[-1], 0, ms, bs)
-                dkey, drec, dname, coll = self.shard.shard_result()
-                coll = sum(self._gather(coll))
+                bad = any(self._gather(self.shard.shard_result()[3] > 0))
+            if bad:
+                return self.run_device(ptr, nbytes, **again)  # an error, a duplicate name or a wrong guess: the exact path decides
+            local_key, T0, T1 = KEY_NONE, 0, 0
+            dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0
+        if not speculative:
+            exp0, T0 = self._feed_file(0, ptr, nbytes)
+            exp1, T1 = None, 0
+            if pair:
+                ctx.set_file_total(0, T0)
+                if T0 > 0:
+                    exp1, T1 = self._feed_file(1, ptr2, nbytes2)
+            rep = ctx.finish()
+            local_key = rep.error.event_key if rep.error.code != 0 else KEY_NONE
+            stopped = (exp0 is not None and rep.file[0].n_records < exp0) or (exp1 is not None and rep.file[1].n_records < exp1)
+            if rep.error.code == 0 and stopped:
+                raise NotImplementedError("NUL-led header line (early clean EOF) in a sharded run")
+            # -- 3. names to their owners
+            dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0
+            if self.shard is not None:
+                # one file: the tuples travel alone first; only if some owner met an equal hash (a duplicate name or a 64-bit collision) is
+                # the exchange repeated with the name bytes, which the owner then compares.  The mate loop needs the bytes anyway.
+                coll = 1
+                if not pair:
+                    meta, blob, ms, bs = self._route_names(0, with_bytes=False)
+                    self.shard.shard_insert(meta.data_ptr(), ms[-1], 0, ms, bs)
+                    dkey, drec, dname, coll = self.shard.shard_result()
+                    coll = sum(self._gather(coll))
+                    if coll:
+                        self.shard.reset()
                 if coll:
-                    self.shard.reset()
-            if coll:
-                meta, blob, ms, bs = self._route_names(0)
-                self.shard.shard_insert(meta.data_ptr(), ms[-1], blob.data_ptr(), ms, bs)
-                dkey, drec, dname, coll = self.shard.shard_result()
-            dup = (dkey, drec, dname)
-            if pair and T0 > 0:
-                meta2, blob2, ms2, bs2 = self._route_names(1)
-                self.shard.shard_claim(meta2.data_ptr(), ms2[-1], blob2.data_ptr(), ms2, bs2, T0 + 1)
-                ukey, urec, uname, claimed, coll2 = self.shard.shard_claim_result()
-                unp = (ukey, urec, uname)
-                coll += coll2
-            if sum(self._gather(coll)):
-                raise NotImplementedError("64-bit name hash collision between different names in a sharded run: rerun with another seed")
+                    meta, blob, ms, bs = self._route_names(0)
+                    self.shard.shard_insert(meta.data_ptr(), ms[-1], blob.data_ptr(), ms, bs)
+                    dkey, drec, dname, coll = self.shard.shard_result()
+                dup = (dkey, drec, dname)
+                if pair and T0 > 0:
+                    meta2, blob2, ms2, bs2 = self._route_names(1)
+                    self.shard.shard_claim(meta2.data_ptr(), ms2[-1], blob2.data_ptr(), ms2, bs2, T0 + 1)
+                    ukey, urec, uname, claimed, coll2 = self.shard.shard_claim_result()
+                    unp = (ukey, urec, uname)
+                    coll += coll2
+                if sum(self._gather(coll)):
+                    raise NotImplementedError("64-bit name hash collision between different names in a sharded run: rerun with another seed")
         # -- 4. merge
         f0, f1 = rep.file[0], rep.file[1]
         mine = {"key": local_key, "dup": dup, "unp": unp, "claimed": claimed,

@@ -28,6 +28,15 @@ def _cases():
     for cuts in ([0.1, 0.5], [0.5, 0.97], [0.045, 0.046]):
         cases.append({"file": "synthetic_dup", "mode": "index", "hex": data.hex(), "cuts": cuts})
         cases.append({"file": "synthetic_dup", "mode": "single", "hex": data.hex(), "cuts": cuts})
+    # large enough for every rank to guess its line phase from its own plus lines (the speculative feed of dist.py): a clean file, a
+    # duplicate (seen only at the owner), an error on one rank only, a file whose ranks all guess wrong-footed ('+name' lines)
+    big = [f"@M0:1:FC:1:11:{i}:{i * 7} 1:N:0:AC\n{'ACGTN' * (3 + i % 5)}\n+\n{'F' * (5 * (3 + i % 5))}\n" for i in range(4000)]
+    dupb = list(big); dupb[3900] = dupb[17]
+    badb = list(big); badb[3000] = badb[3000].replace("ACGTN", "ACXTN", 1)
+    plusb = [r.replace("\n+\n", "\n+" + r.split("\n")[0][1:] + "\n") if i % 7 else r for i, r in enumerate(big)]
+    for nm, rr in (("big_clean", big), ("big_dup", dupb), ("big_bad", badb), ("big_plusnames", plusb)):
+        for mode in ("index", "single"):
+            cases.append({"file": nm, "mode": mode, "hex": "".join(rr).encode().hex(), "cuts": [0.31, 0.64]})
     # pairs: default two-file mode (index loop + mate loop)
     def pair_case(f1, f2, c1, c2):
         d1, d2 = read_stream(os.path.join(GOLDEN, "inputs", f1)), read_stream(os.path.join(GOLDEN, "inputs", f2))
