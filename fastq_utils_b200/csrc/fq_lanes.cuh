@@ -215,7 +215,7 @@ fq_lanes_kernel(const LanesParams P) {
   FqName* stage = (FqName*)(smem + LN_OFF_STAGE);     /* name descriptors of the tile's header lines, written out one round later */
   uint4* lut = (uint4*)(smem + LN_OFF_LUT);           /* [lo] bytes >= lo, [16 + h] bytes <= h */
   __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ uint32_t s_next, s_w1[LN_WARPS], s_w3[LN_WARPS], s_w4[LN_WARPS];
+  __shared__ uint32_t s_next, s_fbase, s_fstate, s_w1[LN_WARPS], s_w3[LN_WARPS], s_w4[LN_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = smem_u32(&s_bar);
   if (tid == 0) {
@@ -375,6 +375,12 @@ fq_lanes_kernel(const LanesParams P) {
     for (int w = 0; w < LN_WARPS; w++) { uint32_t x = s_w1[w]; cnt2 += x; if (w < warp) excl += x; }
     excl &= 0xFFFFu;
     const uint32_t cntW = cnt2 & 0xFFFFu, cntT = cnt2 >> 16; /* line ends inside the scanned range / inside the tile */
+    if (f_lookup && tid == 32) { /* one thread folds the warps' look-back partials; everybody reads the result after the next barrier */
+      uint32_t state = 0, base = 0;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; w++) if (state == 0) { base += s_w3[w]; state = s_w4[w]; }
+      s_fbase = base; s_fstate = state;
+    }
     if (tid == 0) {
       if (tile > 0) st_volatile64(P.tile_state + tile, ST_AGG | cntT);
       /* Per-line mode claims the next tile now (and pulls it into L2).  The chunk-parallel mode claims at the end of the round: many
@@ -408,9 +414,7 @@ fq_lanes_kernel(const LanesParams P) {
     if (pend) { /* F, second half (after this tile's own count went out: nothing that can wait runs before that) */
       uint32_t base = p_base;
       if (f_lookup) {
-        uint32_t state = 0; base = 0;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; w++) if (state == 0) { base += s_w3[w]; state = s_w4[w]; }
+        const uint32_t state = s_fstate; base = s_fbase;
         if (state != 1u) { /* not among the 256 in front, or one of them was late: the look-back with its own barriers */
           __syncthreads();
           base = ln_lookback(P.tile_state, p_tile, 0ull, tid, lane, warp, s_w3, s_w4, P.out);
