@@ -253,6 +253,24 @@ def main():
         out["e2e"] = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "measured at N=1 only"}
 
     if rank == 0 and world == 1:
+        # ---------------- the dominant kernel without the index kernel beside it: the same bytes through the -r loop (no name index)
+        try:
+            solo = fq.FastqInfo(fq.MODE_SINGLE, device=local)
+            for i in range(3):
+                if i == 1:
+                    solo.kernel_stats(reset=True)
+                solo.reset()
+                solo.feed_device(0, data.data_ptr(), nb, last=True)
+                r1 = solo.finish()
+                assert r1.error.code == 0
+            ks1 = solo.kernel_stats()[dom]
+            solo.close()
+            if ks1["ms"] > 0:
+                a1 = ks1["bytes"] / (ks1["ms"] / 1e3) / 1e9
+                out["roofline"]["alone"] = {"achieved": a1, "frac": a1 / peak, "avg_launch_ms": ks1["ms"] / max(1, ks1["launches"]),
+                                            "note": "same kernel, same bytes, -r loop: no index kernel running beside it"}
+        except Exception as ex:
+            out["roofline"]["alone"] = {"error": str(ex)[:200]}
         # ---------------- e2e: the same job through fqg_feed from pinned host memory (H2D inside the timed region)
         if not a.no_e2e:
             try:
