@@ -51,6 +51,8 @@ class KernelStat(ctypes.Structure):
     _fields_ = [("ms", ctypes.c_double), ("launches", ctypes.c_uint64), ("bytes", ctypes.c_uint64), ("items", ctypes.c_uint64)]
 
 
+CHUNK_HOOK = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int)
+
 _lib = None
 
 
@@ -95,6 +97,16 @@ def lib():
         L.fqg_sniff_device.argtypes = [vp, ci, vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
         L.fqg_set_sniff.argtypes = [vp, ci, ctypes.c_int32, ctypes.c_int32]
         L.fqg_set_file_total.argtypes = [vp, ci, u64]
+        L.fqg_set_chunk_hook.argtypes = [vp, CHUNK_HOOK, vp]
+        L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
+        L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64]
+        L.fqg_shard_reserve.argtypes = [vp, u64]
+        L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ci]
+        L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
+        L.fqg_ipc_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.fqg_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.fqg_ipc_close.argtypes = [vp, vp]
+        L.fqg_ipc_free.argtypes = [vp, vp]
         if hasattr(L, "fqg_synth_illumina"):  # absent from the test stand-in
             L.fqg_synth_illumina.argtypes = [vp, u64, u64, u64, ci, u64, vp]
             L.fqg_synth_longreads.argtypes = [vp, vp, u64, u64, u64, vp]
@@ -241,6 +253,48 @@ class FastqInfo:
         _check(self._ctx, lib().fqg_shard_claim_result(self._ctx, ctypes.byref(key), ctypes.byref(rec), name, ctypes.byref(ln), ctypes.byref(cl), ctypes.byref(col)), "fqg_shard_claim_result")
         return int(key.value), int(rec.value), name.raw[:ln.value], int(cl.value), int(col.value)
 
+    # ---- pipelined routing (dist.py `_route_round`) ----
+    def set_chunk_hook(self, fn):
+        """fn(file) is called from inside feed_device right after a chunk's clean-data pass was launched; None removes it."""
+        self._hook = CHUNK_HOOK((lambda user, file: fn(file))) if fn is not None else CHUNK_HOOK()
+        _check(self._ctx, lib().fqg_set_chunk_hook(self._ctx, self._hook, None), "fqg_set_chunk_hook")
+
+    def names_new(self, file):
+        n = ctypes.c_uint64()
+        _check(self._ctx, lib().fqg_names_new(self._ctx, file, ctypes.byref(n)), "fqg_names_new")
+        return int(n.value)
+
+    def names_pack_slots(self, file, region_ptrs, cap):
+        arr = (ctypes.c_void_p * len(region_ptrs))(*region_ptrs)
+        _check(self._ctx, lib().fqg_names_pack_slots(self._ctx, file, len(region_ptrs), arr, cap), "fqg_names_pack_slots")
+
+    def shard_reserve(self, n_names):
+        _check(self._ctx, lib().fqg_shard_reserve(self._ctx, n_names), "fqg_shard_reserve")
+
+    def shard_insert_slots(self, regions_ptr, n_src, cap, beside):
+        _check(self._ctx, lib().fqg_shard_insert_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, cap, 1 if beside else 0), "fqg_shard_insert_slots")
+
+    def shard_slots_result(self):
+        ins, eq, ov = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int32()
+        _check(self._ctx, lib().fqg_shard_slots_result(self._ctx, ctypes.byref(ins), ctypes.byref(eq), ctypes.byref(ov)), "fqg_shard_slots_result")
+        return int(ins.value), int(eq.value), bool(ov.value)
+
+    def ipc_alloc(self, nbytes):
+        p, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        _check(self._ctx, lib().fqg_ipc_alloc(self._ctx, nbytes, ctypes.byref(p), h), "fqg_ipc_alloc")
+        return int(p.value), h.raw
+
+    def ipc_open(self, handle):
+        p = ctypes.c_void_p()
+        _check(self._ctx, lib().fqg_ipc_open(self._ctx, ctypes.create_string_buffer(handle, 64), ctypes.byref(p)), "fqg_ipc_open")
+        return int(p.value)
+
+    def ipc_close(self, ptr):
+        _check(self._ctx, lib().fqg_ipc_close(self._ctx, ctypes.c_void_p(ptr)), "fqg_ipc_close")
+
+    def ipc_free(self, ptr):
+        _check(self._ctx, lib().fqg_ipc_free(self._ctx, ctypes.c_void_p(ptr)), "fqg_ipc_free")
+
     def sniff_device(self, file, ptr, n, skip):
         f, c = ctypes.c_int32(), ctypes.c_int32()
         _check(self._ctx, lib().fqg_sniff_device(self._ctx, file, ctypes.c_void_p(ptr), n, skip, ctypes.byref(f), ctypes.byref(c)), "fqg_sniff_device")
@@ -262,6 +316,13 @@ class FastqInfo:
         starts = (ctypes.c_uint64 * max(cap, 1))()
         _check(self._ctx, lib().fqg_index_records(self._ctx, data, len(data), starts, cap, ctypes.byref(n)), "fqg_index_records")
         return int(n.value), list(starts[:min(cap, n.value)])
+
+
+def feed_chunk_bytes():
+    """Largest piece fqg_feed_device hands to the kernels at once (fq_engine.cpp: kMaxChunk, test hook FQG_MAX_CHUNK_BYTES)."""
+    e = os.environ.get("FQG_MAX_CHUNK_BYTES")
+    v = (int(e) & ~15) if e else 0
+    return v if 4096 <= v < (1 << 31) else (1 << 31) - 16
 
 
 def illumina_record_bytes():

@@ -141,3 +141,45 @@ extern "C" int fqg_set_file_total(fqg_ctx* c, int file, uint64_t total) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->eng->set_file_total(file, total))
 }
+
+/* ---- pipelined routing ---- */
+extern "C" int fqg_set_chunk_hook(fqg_ctx* c, fqg_chunk_hook hook, void* user) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->set_chunk_hook(hook, user))
+}
+extern "C" int fqg_names_new(fqg_ctx* c, int file, uint64_t* n_new) {
+  if (!c || file < 0 || file > 1 || !n_new) return FQG_ERR_USAGE;
+  FQG_GUARD(c, *n_new = c->eng->names_new(file))
+}
+extern "C" int fqg_names_pack_slots(fqg_ctx* c, int file, uint32_t world, void* const* region_ptrs, uint64_t region_cap) {
+  if (!c || file < 0 || file > 1 || !region_ptrs || !region_cap) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->names_pack_slots(file, world, region_ptrs, region_cap))
+}
+extern "C" int fqg_shard_reserve(fqg_ctx* c, uint64_t n_names) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_reserve(n_names))
+}
+extern "C" int fqg_shard_insert_slots(fqg_ctx* c, const void* regions, uint32_t n_src, uint64_t region_cap, int beside) {
+  if (!c || !regions || !region_cap) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_insert_slots(regions, n_src, region_cap, beside != 0))
+}
+extern "C" int fqg_shard_slots_result(fqg_ctx* c, uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow) {
+  if (!c || !inserted || !equal_hashes || !overflow) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_slots_result(inserted, equal_hashes, overflow))
+}
+extern "C" int fqg_ipc_alloc(fqg_ctx* c, size_t bytes, void** dptr, uint8_t handle[64]) {
+  if (!c || !dptr || !handle) return FQG_ERR_USAGE;
+  FQG_GUARD(c, *dptr = c->dev->ipc_alloc(bytes, handle))
+}
+extern "C" int fqg_ipc_open(fqg_ctx* c, const uint8_t handle[64], void** dptr) {
+  if (!c || !dptr || !handle) return FQG_ERR_USAGE;
+  FQG_GUARD(c, *dptr = c->dev->ipc_open(handle))
+}
+extern "C" int fqg_ipc_close(fqg_ctx* c, void* dptr) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->dev->ipc_close(dptr))
+}
+extern "C" int fqg_ipc_free(fqg_ctx* c, void* dptr) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->dev->ipc_free(dptr))
+}

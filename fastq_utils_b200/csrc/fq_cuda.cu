@@ -765,6 +765,78 @@ fq_names_pack_kernel(const FqName* __restrict__ names, const uint8_t* __restrict
   }
 }
 
+/* ------------------------------------------------------------------------------------------------ pipelined routing (tuples only)
+ * The names of a finished chunk travel while the next chunk's clean-data pass runs.  Every owner has a region of fixed capacity
+ * (local send buffer for an all-to-all, or the owner's own memory mapped over NVLink): no counting pass, no size exchange.  The
+ * kernels are capped at 32 registers: one block fits on an SM beside the four resident blocks of the pass. */
+struct SlotPackParams {
+  const FqName* names; uint32_t nrec; unsigned long long g0; uint32_t world; unsigned long long cap; unsigned long long* cursors; FqRegionPtrs R;
+};
+__global__ void __launch_bounds__(256, 8)
+fq_names_pack_slots_kernel(const SlotPackParams P) {
+  __shared__ unsigned long long s_cnt[FQ_SHARD_MAX_SRC], s_base[FQ_SHARD_MAX_SRC];
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < P.nrec; b0 += gridDim.x * blockDim.x) {
+    if (threadIdx.x < P.world) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t k = b0 + threadIdx.x;
+    FqName nm; nm.hash = FQ_HASH_SKIP; nm.off = 0; nm.len = 0;
+    if (k < P.nrec) nm = P.names[k];
+    const bool valid = nm.hash != FQ_HASH_SKIP;
+    const uint32_t o = valid ? fq_owner_of(nm.hash, P.world) : 0xFFFFFFFFu;
+    unsigned long long my = 0;
+    for (uint32_t w = 0; w < P.world; w++) { /* rank among the lanes of the same owner by warp vote, one shared atomic per warp and owner */
+      const uint32_t m = __ballot_sync(FULL, o == w);
+      if (!m) continue;
+      unsigned long long wm = 0;
+      if (lane == 0) wm = atomicAdd(&s_cnt[w], (unsigned long long)__popc(m));
+      wm = __shfl_sync(FULL, wm, 0);
+      if (o == w) my = wm + __popc(m & lt);
+    }
+    __syncthreads();
+    if (threadIdx.x < P.world) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(P.cursors + threadIdx.x, s_cnt[threadIdx.x]) : 0ull;
+    __syncthreads();
+    if (valid) {
+      const unsigned long long pos = s_base[o] + my;
+      if (pos < P.cap) { FqPackedName pn; pn.hash = nm.hash; pn.record = P.g0 + k; pn.off = 0; pn.len = nm.len; P.R.region[o][1 + pos] = pn; }
+    }
+    __syncthreads();
+  }
+}
+struct SlotHeaderParams { const unsigned long long* cursors; uint32_t world; FqRegionPtrs R; };
+__global__ void fq_slots_header_kernel(const SlotHeaderParams P) {
+  if (threadIdx.x < P.world) { FqPackedName h; h.hash = P.cursors[threadIdx.x]; h.record = 0; h.off = 0; h.len = 0; P.R.region[threadIdx.x][0] = h; }
+}
+struct SlotInsertParams { const FqPackedName* regions; uint32_t n_src; unsigned long long cap; FqSlot* slots; unsigned long long mask; unsigned long long* counters; };
+__global__ void __launch_bounds__(256, 8)
+fq_shard_insert_slots_kernel(const SlotInsertParams P) {
+  unsigned long long inserted = 0, equal = 0;
+  const unsigned long long total = (unsigned long long)P.n_src * P.cap, step = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
+    const unsigned long long m = m0 + threadIdx.x;
+    if (m >= total) continue;
+    const unsigned long long src = m / P.cap, idx = m - src * P.cap;
+    const FqPackedName* reg = P.regions + src * (P.cap + 1);
+    const unsigned long long cnt = reg[0].hash;
+    if (cnt > P.cap && idx == 0) atomicExch(P.counters + 2, 1ull); /* the sender had more names for this owner than the region holds */
+    if (idx >= cnt) continue;
+    const FqPackedName pn = reg[1 + idx];
+    unsigned long long i = pn.hash & P.mask, probes = 0;
+    for (;; i = (i + 1) & P.mask) {
+      if (++probes > P.mask) { atomicExch(P.counters + 2, 1ull); break; }
+      unsigned long long cur, cur_idx;
+      if (slot_claim128(P.slots + i, pn.hash, pn.record, &cur, &cur_idx)) { inserted++; break; }
+      if (cur != pn.hash) continue;
+      equal++; /* a duplicate name or a 64-bit collision: tuples alone cannot tell, the exact path decides */
+      break;
+    }
+  }
+  __syncwarp();
+  inserted = warp_sum64(inserted); equal = warp_sum64(equal);
+  if ((threadIdx.x & 31) == 0) { if (inserted) atomicAdd(P.counters + 1, inserted); if (equal) atomicAdd(P.counters + 0, equal); }
+}
+
 struct ShardParams { FqShardArgs a; };
 __device__ __forceinline__ const uint8_t* shard_name(const FqShardArgs& a, unsigned long long pos, uint32_t* len) {
   uint32_t src = 0;
@@ -851,6 +923,7 @@ class FqCudaDevice : public FqDevice {
     FQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     FQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st2_, cudaStreamNonBlocking));
     FQ_CUDA_CHECK(cudaEventCreateWithFlags(&evx_, cudaEventDisableTiming));
+    FQ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_pre_, cudaEventDisableTiming));
     FQ_CUDA_CHECK(cudaEventCreate(&ev0_)); FQ_CUDA_CHECK(cudaEventCreate(&ev1_));
     cudaMemPool_t pool; FQ_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev_));
     unsigned long long thr = ~0ull; /* keep freed blocks in the pool: allocations repeat every chunk */
@@ -866,7 +939,7 @@ class FqCudaDevice : public FqDevice {
     for (auto& d : deferred_) cudaEventDestroy(d.ready);
     for (auto e : free_ev_) cudaEventDestroy(e);
     cudaFree(tile_state_);
-    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_);
+    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_); cudaEventDestroy(ev_pre_);
     cudaStreamDestroy(st_); cudaStreamDestroy(st2_);
   }
   const char* name() const override { return "cuda"; }
@@ -884,6 +957,7 @@ class FqCudaDevice : public FqDevice {
   }
   void copy(void* d, const void* s, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st_)); }
   void fill(void* d, int b, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemsetAsync(d, b, n, st_)); }
+  void fill_index(void* d, int b, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemsetAsync(d, b, n, st2_)); }
   void sync() override { flush_deferred(); FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); }
   void sync_main() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); }
   void timer_start() override { FQ_CUDA_CHECK(cudaEventRecord(ev0_, st_)); }
@@ -994,6 +1068,7 @@ class FqCudaDevice : public FqDevice {
     P.tile_state = tile_state_; P.ticket = ticket_; P.ntiles = ntiles; P.out = a.out5;
     P.j0 = a.j0; P.cx = a.cx; P.names = a.names; P.names_cap = a.names_cap;
     { const char* e = getenv("FQG_LANES_TUNE"); P.tune = e ? (uint32_t)atoi(e) : 0u; }
+    FQ_CUDA_CHECK(cudaEventRecord(ev_pre_, st_));
     FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));
     FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
     int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)lanes_blocks_);
@@ -1103,6 +1178,51 @@ class FqCudaDevice : public FqDevice {
     fq_shard_claim_kernel<<<grid, 256, 0, st2_>>>(P);
     toc(st2_); launched();
   }
+  void route_begin(unsigned long long* cursors, uint32_t world, bool beside) override {
+    /* beside: the main stream is busy with a clean-data pass launched after the names were complete; wait only for what was
+     * queued before that pass (ev_pre_).  Otherwise: everything queued on the main stream so far. */
+    if (beside) { FQ_CUDA_CHECK(cudaStreamWaitEvent(st2_, ev_pre_, 0)); } else after_main();
+    FQ_CUDA_CHECK(cudaMemsetAsync(cursors, 0, world * sizeof(unsigned long long), st2_));
+  }
+  void names_pack_slots(const FqName* names, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
+                        unsigned long long* cursors) override {
+    if (!nrec) return;
+    SlotPackParams P; P.names = names; P.nrec = nrec; P.g0 = g0; P.world = world; P.cap = cap; P.cursors = cursors; P.R = R;
+    int grid = (int)std::min<uint32_t>((nrec + 255) / 256, (uint32_t)sms_ * 8);
+    tic(FQG_K_OTHER, 0, nrec, st2_);
+    fq_names_pack_slots_kernel<<<grid, 256, 0, st2_>>>(P);
+    toc(st2_); launched();
+  }
+  void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R) override {
+    SlotHeaderParams P; P.cursors = cursors; P.world = world; P.R = R;
+    fq_slots_header_kernel<<<1, FQ_SHARD_MAX_SRC, 0, st2_>>>(P);
+    launched();
+    FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
+  }
+  void shard_insert_slots(const FqPackedName* regions, uint32_t n_src, uint64_t cap, FqSlot* slots, unsigned long long mask,
+                          unsigned long long* counters, bool beside) override {
+    if (!n_src || !cap) return;
+    SlotInsertParams P; P.regions = regions; P.n_src = n_src; P.cap = cap; P.slots = slots; P.mask = mask; P.counters = counters;
+    unsigned long long total = (unsigned long long)n_src * cap;
+    int grid = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)sms_ * (beside ? 1 : 8));
+    after_main();
+    tic(FQG_K_INDEX, 0, total, st2_);
+    fq_shard_insert_slots_kernel<<<grid, 256, 0, st2_>>>(P);
+    toc(st2_); launched();
+  }
+  void* ipc_alloc(size_t n, uint8_t handle[64]) override {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    void* p = nullptr; FQ_CUDA_CHECK(cudaSetDevice(dev_)); FQ_CUDA_CHECK(cudaMalloc(&p, n ? n : 1));
+    cudaIpcMemHandle_t h; FQ_CUDA_CHECK(cudaIpcGetMemHandle(&h, p)); memcpy(handle, &h, 64);
+    return p;
+  }
+  void* ipc_open(const uint8_t handle[64]) override {
+    cudaIpcMemHandle_t h; memcpy(&h, handle, 64);
+    void* p = nullptr; FQ_CUDA_CHECK(cudaSetDevice(dev_)); FQ_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return p;
+  }
+  void ipc_close(void* p) override { if (p) FQ_CUDA_CHECK(cudaIpcCloseMemHandle(p)); }
+  void ipc_free(void* p) override { if (p) { FQ_CUDA_CHECK(cudaDeviceSynchronize()); FQ_CUDA_CHECK(cudaFree(p)); } }
   void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {
     if (!n) return;
     int grid = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)sms_ * 8);
@@ -1154,6 +1274,7 @@ class FqCudaDevice : public FqDevice {
   int dev_ = 0, sms_ = kSMs, tile_blocks_ = 0, lanes_blocks_ = 0;
   cudaStream_t st_ = nullptr, st2_ = nullptr;
   cudaEvent_t evx_ = nullptr;
+  cudaEvent_t ev_pre_ = nullptr; /* main stream just before the latest clean-data pass: what the side stream waits for when it works beside that pass */
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;
   unsigned long long n_launch_ = 0;

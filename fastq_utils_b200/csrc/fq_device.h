@@ -9,6 +9,7 @@
 #define FQ_DEVICE_H
 #include <stddef.h>
 #include <stdint.h>
+#include <stdexcept>
 #include "fq_types.h"
 
 /* where to find the bytes of a name given the index of its record inside a file: one entry per segment */
@@ -62,6 +63,8 @@ typedef struct {
   unsigned long long* dup_key;   /* min event key of a duplicate */
   unsigned long long* counters;  /* [0] collisions, [2] table full */
 } FqShardArgs;
+/* pipelined routing: one fixed-capacity region per owner (header FqPackedName {count, 0, 0, 0}, then the tuples) */
+typedef struct { FqPackedName* region[FQ_SHARD_MAX_SRC]; } FqRegionPtrs;
 FQ_HD uint32_t fq_owner_of(uint64_t hash, uint32_t world) { return (uint32_t)((hash >> 40) % world); }
 
 /* fused scan + validate pass over one chunk (FqCudaDevice only): the records of the segment that starts at line j0 */
@@ -86,6 +89,9 @@ class FqDevice {
   virtual void download(void* dst, const void* src, size_t n) = 0; /* synchronises */
   virtual void copy(void* dst, const void* src, size_t n) = 0;
   virtual void fill(void* dst, int byte, size_t n) = 0;
+  /* fill ordered with the index kernels instead of the main stream's copies and passes (the stream of index_insert, mate_claim
+   * and the shard kernels): clearing the table then runs beside the first chunk's pass */
+  virtual void fill_index(void* dst, int byte, size_t n) { fill(dst, byte, n); }
   virtual void sync() = 0;
   /* wait for the copies and kernels queued on the main stream only (the index kernels on their own stream keep running) */
   virtual void sync_main() { sync(); }
@@ -125,6 +131,24 @@ class FqDevice {
   /* owner side of the mate loop: tuples of file 2 claim the slots filled from `inserted` (file 1's tuples); unpaired events
    * go to a.dup_key as FQ_KEY(step_base + record, FQ_R_NAME), first claims are counted in a.counters[1] */
   virtual void shard_claim(const FqShardArgs& a, const FqShardArgs& inserted, unsigned long long step_base) = 0;
+  /* pipelined routing (include/fastq_gpu.h: fqg_names_pack_slots / fqg_shard_insert_slots).  These run on the side stream so
+   * that they can be called while a clean-data pass occupies the main stream (beside = that pass has been launched and the names
+   * to pack were complete before it).  route_begin clears cursors[world]; names_pack_slots appends one segment's tuples to the
+   * owners' regions (tuples beyond cap are counted, not stored); route_end writes the counts into the region headers and
+   * returns when everything is in place. */
+  virtual void route_begin(unsigned long long* cursors, uint32_t world, bool beside) = 0;
+  virtual void names_pack_slots(const FqName* names, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
+                                unsigned long long* cursors) = 0;
+  virtual void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R) = 0;
+  /* tuples of n_src regions (stride cap + 1 tuples) into the table; counters[0] += equal hashes, counters[1] += inserted,
+   * counters[2] = 1 when a header count exceeds cap or the table is full.  Asynchronous. */
+  virtual void shard_insert_slots(const FqPackedName* regions, uint32_t n_src, uint64_t cap, FqSlot* slots, unsigned long long mask,
+                                  unsigned long long* counters, bool beside) = 0;
+  /* memory that other processes can map (CUDA IPC); devices without it throw */
+  virtual void* ipc_alloc(size_t n, uint8_t handle[64]) { (void)n; (void)handle; throw std::runtime_error("this device has no inter-process memory"); }
+  virtual void* ipc_open(const uint8_t handle[64]) { (void)handle; throw std::runtime_error("this device has no inter-process memory"); }
+  virtual void ipc_close(void* p) { (void)p; }
+  virtual void ipc_free(void* p) { (void)p; }
   virtual void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) = 0;
   /* details of one record for the error message */
   virtual void explain(const uint8_t* data, const FqLine* lines4_host, const FqRecCtx& cx, FqRecOut* out_dev) = 0;

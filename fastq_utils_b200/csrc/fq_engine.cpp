@@ -28,6 +28,7 @@ FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) 
   scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
   recout_ = (FqRecOut*)dev_->alloc(sizeof(FqRecOut));
   tile_out_ = (uint32_t*)dev_->alloc(32 * sizeof(uint32_t));
+  route_cursors_ = (unsigned long long*)dev_->alloc(FQ_SHARD_MAX_SRC * sizeof(unsigned long long));
   for (int f = 0; f < 2; f++) {
     f_[f].stats = (FqStats*)dev_->alloc(sizeof(FqStats));
     f_[f].hist = (unsigned long long*)dev_->alloc((size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
@@ -55,6 +56,7 @@ FqEngine::~FqEngine() {
   for (int f = 0; f < 2; f++) { free_file(f_[f]); dev_->release(f_[f].stats); dev_->release(f_[f].hist); }
   if (slots_) dev_->release(slots_);
   dev_->release(key_); dev_->release(counters_); dev_->release(scratch_); dev_->release(recout_); dev_->release(tile_out_);
+  dev_->release(route_cursors_);
 }
 
 /* forget input and results; the index keeps its allocation */
@@ -75,7 +77,7 @@ void FqEngine::reset() {
     dev_->fill(f_[f].hist, 0, (size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
   }
   dev_->sync(); /* `init` is a stack object */
-  if (slots_) dev_->fill(slots_, 0xFF, table_cap_ * sizeof(FqSlot));
+  if (slots_) dev_->fill_index(slots_, 0xFF, table_cap_ * sizeof(FqSlot)); /* on the index kernels' stream: beside the first chunk's pass */
   table_names_ = 0;
 }
 
@@ -131,7 +133,9 @@ void FqEngine::feed_device(int file, const void* dptr, size_t n, bool last) {
      * it, with the bytes in between marked as not its own (they are readable: same allocation) */
     const uint32_t lead = (uint32_t)((uintptr_t)p & 15u);
     const bool whole_records = F.pend_n == 0; /* nothing carried over: the chunk starts at a record start */
+    hook_fired_ = false;
     add_buffer(file, p - lead, (uint32_t)(k + lead), last && k == n, false, true, lead);
+    if (hook_ && !hook_fired_) hook_(hook_user_, file); /* the chunk did not take the clean-data pass: its hook call comes after it */
     p += k; n -= k;
     /* A record cut by the end of the chunk normally travels on as pending bytes and is finished in a bridge chunk.  The bytes are
      * still here, so the next chunk simply starts at that record instead: no bridge, no second pass over its lines. */
@@ -261,6 +265,11 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
     uint32_t linit[FQ_LANES_OUT_WORDS] = {0, 0, kNone32, 0, 0, kNone32, kNone32, 0, kNone32, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     dev_->upload(tile_out_, linit, sizeof linit);
     if (dev_->lanes_pass(a)) {
+      if (hook_) { /* the pass is running: the caller routes the names of the chunks before this one beside it */
+        in_beside_hook_ = true; hook_fired_ = true;
+        try { hook_(hook_user_, file); } catch (...) { in_beside_hook_ = false; throw; }
+        in_beside_hook_ = false;
+      }
       uint32_t o[FQ_LANES_OUT_WORDS];
       dev_->download(o, tile_out_, sizeof o);
       bool pass_ok = !o[1] && o[2] == kNone32 && !o[3] && !o[4];
@@ -1072,6 +1081,54 @@ void FqEngine::names_pack(int file, uint32_t world, void* meta, void* blob, cons
   }
   dev_->sync(); /* h is a local */
   dev_->release(base);
+}
+
+uint64_t FqEngine::names_new(int file) {
+  FqFile& F = f_[file];
+  uint64_t lim = eff_records(F), n = 0;
+  for (size_t si = F.routed_segs; si < F.segs.size(); si++) {
+    const FqSegment& s = F.segs[si];
+    if (s.g0 >= lim || !s.names) continue;
+    n += std::min<uint64_t>(s.nrec, lim - s.g0);
+  }
+  return n;
+}
+
+void FqEngine::names_pack_slots(int file, uint32_t world, void* const* region_ptrs, uint64_t cap) {
+  if (world == 0 || world > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_names_pack_slots: world out of range");
+  if (!(cfg_.flags & FQG_FLAG_EXTERNAL_INDEX)) throw std::runtime_error("fqg_names_pack_slots needs FQG_FLAG_EXTERNAL_INDEX");
+  FqFile& F = f_[file];
+  FqRegionPtrs R; memset(&R, 0, sizeof R);
+  for (uint32_t o = 0; o < world; o++) { if (!region_ptrs[o]) throw std::runtime_error("fqg_names_pack_slots: null region"); R.region[o] = (FqPackedName*)region_ptrs[o]; }
+  const bool beside = in_beside_hook_;
+  dev_->route_begin(route_cursors_, world, beside);
+  uint64_t lim = eff_records(F);
+  for (size_t si = F.routed_segs; si < F.segs.size(); si++) {
+    const FqSegment& s = F.segs[si];
+    if (s.g0 >= lim || !s.names) continue;
+    dev_->names_pack_slots(s.names, (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0), s.g0 + F.g_base, world, R, cap, route_cursors_);
+  }
+  dev_->route_end(route_cursors_, world, R);
+  F.routed_segs = F.segs.size();
+}
+
+void FqEngine::shard_reserve(uint64_t n_names) {
+  if (table_names_) throw std::runtime_error("fqg_shard_reserve after the first insert");
+  ensure_table(std::max<uint64_t>(n_names, 1));
+}
+
+void FqEngine::shard_insert_slots(const void* regions, uint32_t n_src, uint64_t cap, bool beside) {
+  if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_insert_slots: n_src out of range");
+  if (!slots_) ensure_table(1);
+  dev_->shard_insert_slots((const FqPackedName*)regions, n_src, cap, slots_, table_cap_ - 1, counters_, beside);
+  table_names_ = 1; /* the table holds names the engine cannot re-insert: it must not grow any more */
+}
+
+void FqEngine::shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow) {
+  dev_->sync();
+  unsigned long long ctr[4]; dev_->download(ctr, counters_, sizeof ctr);
+  *inserted = ctr[1]; *equal_hashes = ctr[0];
+  *overflow = (ctr[2] != 0 || ctr[1] * 2 > table_cap_) ? 1 : 0; /* above half full the probe sequences get long: let the exact path size the table */
 }
 
 void FqEngine::shard_insert(const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start) {

@@ -59,6 +59,7 @@ struct FqFile {
   uint64_t g_base = 0;      /* index (inside the whole file) of the first record of this stream */
   uint32_t start_skip = 0;  /* lines of the first buffer that belong to the previous range */
   bool started = false;
+  size_t routed_segs = 0;   /* pipelined routing: segments [0, routed_segs) have been packed by names_pack_slots */
   struct Prescan { const uint8_t* data; uint32_t n; bool last; uint32_t* line_end; uint32_t nlines; };
   std::vector<Prescan> prescans;
 };
@@ -84,6 +85,13 @@ class FqEngine {
   void sniff_device(int file, const void* dptr, size_t n, uint32_t skip, int32_t* fmt, int32_t* color);
   void shard_claim(const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start, uint64_t step_base);
   void shard_claim_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* claimed, uint64_t* collisions);
+  /* pipelined routing (include/fastq_gpu.h) */
+  void set_chunk_hook(fqg_chunk_hook hook, void* user) { hook_ = hook; hook_user_ = user; }
+  uint64_t names_new(int file);
+  void names_pack_slots(int file, uint32_t world, void* const* region_ptrs, uint64_t cap);
+  void shard_reserve(uint64_t n_names);
+  void shard_insert_slots(const void* regions, uint32_t n_src, uint64_t cap, bool beside);
+  void shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow);
   FqDevice* device() { return dev_; }
   std::string last_error;
   uint64_t path_counts[4] = {0, 0, 0, 0}; /* lanes accepted, lanes handed on, fused per-record accepted, two-pass fallbacks */
@@ -98,6 +106,10 @@ class FqEngine {
   FqRecOut* recout_ = nullptr;              /* device: explain result */
   FqSlot* slots_ = nullptr; uint64_t table_cap_ = 0; uint64_t table_names_ = 0;
   uint32_t seed_ = 0;
+  fqg_chunk_hook hook_ = nullptr; void* hook_user_ = nullptr;
+  bool hook_fired_ = false;                 /* the chunk being fed has called the hook already */
+  bool in_beside_hook_ = false;             /* the hook runs while a clean-data pass occupies the main stream */
+  unsigned long long* route_cursors_ = nullptr; /* device: FQ_SHARD_MAX_SRC per-owner tuple counts of the round being packed */
   const FqPackedName* shard_meta_ = nullptr; uint64_t shard_n_ = 0; const uint8_t* shard_blob_ = nullptr;
   uint32_t shard_nsrc_ = 0; uint64_t shard_meta_start_[FQ_SHARD_MAX_SRC + 1], shard_blob_start_[FQ_SHARD_MAX_SRC];
   void scan_buffer(FqBuffer& B, bool last);

@@ -18,6 +18,7 @@ Supported: MODE_SINGLE (-r), MODE_INDEX (default, one file), MODE_INDEX_PAIR (de
 file caused by a NUL-led header line (src/fastq.c:248) is reported as unsupported here (the single-GPU path handles it).
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -42,13 +43,23 @@ class ShardedFastqInfo:
         self.ctx = api.FastqInfo(mode, device=device, flags=api.FLAG_EXTERNAL_INDEX if indexed else 0)
         self.shard = api.FastqInfo(api.MODE_INDEX, device=device, index_capacity_hint=n_hint) if indexed else None
         self._keep = []
+        # small host objects travel over a gloo group of their own: no device round trip, and no NCCL kernel that would have to
+        # find room on SMs filled by a running clean-data pass (the per-round size exchange of the pipelined routing)
+        self._cpu_group = None
+        if self.world > 1 and dist.get_backend() != "gloo":
+            self._cpu_group = dist.new_group(backend="gloo")
+        self.pipeline = os.environ.get("FQG_NO_PIPELINE", "0") in ("", "0")
+        # pipelined rounds over peer memory (CUDA IPC) instead of all-to-all exchanges: GPUs only; FQG_P2P=0 turns it off
+        self.p2p = self.tdev.type == "cuda" and os.environ.get("FQG_P2P", "1") not in ("", "0")
+        self._arena, self._peer, self._arena_failed, self._p2p_ok = None, None, False, False
+        self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
 
     # ------------------------------------------------------------------ helpers
     def _gather(self, obj):
         if self.world == 1:
             return [obj]
         out = [None] * self.world
-        dist.all_gather_object(out, obj)
+        dist.all_gather_object(out, obj, group=self._cpu_group)
         return out
 
     def _sync(self):
@@ -146,9 +157,10 @@ class ShardedFastqInfo:
 
     def _guess_phase(self, ptr, nbytes):
         """Line class (0 header, 1 sequence, 2 plus, 3 quality) of the line this range starts in, from the range's own first lines:
-        a complete line that is exactly "+" is a plus line.  Returns (ok, class, ends of the first four lines, ends with LF)."""
+        a complete line that is exactly "+" is a plus line.  Returns (ok, class, ends of the first four lines, ends with LF, bytes
+        per record over the first complete records)."""
         if nbytes < 4096:
-            return (False, 0, [KEY_NONE] * 4, True)
+            return (False, 0, [KEY_NONE] * 4, True, 0.0)
         k = min(nbytes, 1 << 18)
         head = bytes(_as_tensor(ptr, k, self.tdev).cpu().numpy())
         last = bytes(_as_tensor(ptr + nbytes - 1, 1, self.tdev).cpu().numpy())
@@ -164,10 +176,11 @@ class ShardedFastqInfo:
                 cls = (2 - i) % 4
                 break
         if cls is None or len(ends) < 5:
-            return (False, 0, [KEY_NONE] * 4, last == b"\n")
-        return (True, cls, ends[:4], last == b"\n")
+            return (False, 0, [KEY_NONE] * 4, last == b"\n", 0.0)
+        k = (len(ends) - 1) // 4
+        return (True, cls, ends[:4], last == b"\n", (ends[4 * k] - ends[0]) / k)
 
-    def _feed_file_speculative(self, f, ptr, nbytes):
+    def _feed_file_speculative(self, f, ptr, nbytes, routed=False):
         """Steps 1-2 without counting the line feeds of the range first: every rank takes the line phase of its range from its own
         first plus line.  A wrong guess cannot go unnoticed on a valid file (a sequence line lands where a header or a plus line is
         expected), so any error afterwards simply sends the whole job through the exact path.  False: not applicable here."""
@@ -175,7 +188,7 @@ class ShardedFastqInfo:
         info = self._gather(self._guess_phase(ptr, nbytes) + (nbytes,))
         if not all(x[0] for x in info) or info[0][1] != 0:
             return False
-        skip, cut = [0] * W, [0] * W
+        skip, cut = [0] * W, [0] * (W + 1)
         for i in range(1, W):
             cls0, prev_lf = info[i][1], info[i - 1][3]
             skip[i] = 0 if (prev_lf and cls0 == 0) else ((4 - cls0) % 4 or 4)
@@ -195,6 +208,35 @@ class ShardedFastqInfo:
         for q in reqs:
             q.wait()
         ctx.set_stream_start(f, skip[r], 0)  # record numbers inside the range: they only matter when something is wrong
+        if routed:
+            # the names travel chunk by chunk beside the next chunk's pass: as many rounds as the longest range has chunks, so that
+            # no round carries more than one chunk (ranks with fewer chunks add empty rounds: the rounds are collective)
+            chunk = api.feed_chunk_bytes()
+            self._rounds_total = max(1, max(-(-x[-1] // chunk) for x in info))
+            est = sum(x[-1] / max(x[4], 16.0) for x in info) / W
+            self.shard.shard_reserve(int(est * 1.05) + 4096)
+            self._round, self._fires, self._inflight, self._hook_exc = 0, 0, [], None
+            # names of one chunk for one owner, with room to spare (the estimate comes from the first records of every range)
+            per = min(chunk, max(x[-1] for x in info)) / max(min(x[4] for x in info), 16.0) / W
+            self._p2p_cap = int(per * 1.25) + 4096
+            self._p2p_ok = self.p2p and self._ensure_arena(self._rounds_total * W * 24 * (self._p2p_cap + 1))
+            ctx.set_chunk_hook(self._on_chunk)
+        try:
+            self._feed_range(f, ptr, nbytes, head, cut[r + 1] if r < W - 1 else 0)
+        finally:
+            if routed:
+                ctx.set_chunk_hook(None)
+        if routed:
+            while self._round < self._rounds_total - 1:
+                self._route_round(False)
+            self._route_round(True)
+            self.rounds_done = self._round
+        return True
+
+    def _feed_range(self, f, ptr, nbytes, head, head_n):
+        """This rank's range, then the head of the next range (the rest of the record its end cut)."""
+        W, r, ctx = self.world, self.rank, self.ctx
+        cut = {r + 1: head_n}
         if r == W - 1:
             ctx.feed_device(f, ptr, nbytes, last=True)
         else:
@@ -204,7 +246,99 @@ class ShardedFastqInfo:
                 self._keep.append(head)
             else:
                 ctx.feed(f, b"", last=True)
+
+    # ------------------------------------------------------------------ pipelined routing (one file, tuples only)
+    def _on_chunk(self, file):
+        """Chunk hook of the feeding context (fqg_set_chunk_hook): called once per chunk, for a chunk of the clean-data pass while
+        that pass runs on the GPU.  Every rank performs exactly `_rounds_total` rounds (they are collective); the first call has
+        nothing to route yet."""
+        self._fires += 1
+        if self._hook_exc is None and self._fires >= 2 and self._round < self._rounds_total - 1:
+            try:
+                self._route_round(False)
+            except BaseException as ex:  # an exception cannot cross the C frames above us
+                self._hook_exc = ex
+
+    def _ensure_arena(self, need):
+        """Peer-writable receive memory (CUDA IPC over NVLink): `need` bytes on every rank, mapped by every other rank.  Collective;
+        False when some rank cannot map a peer (the rounds then use all-to-all exchanges)."""
+        W, r = self.world, self.rank
+        if self._arena is not None and self._arena[1] >= need:
+            return True
+        if self._arena_failed:
+            return False
+        self._sync()
+        ok = True
+        try:
+            if self._arena is not None:
+                for s, pp in enumerate(self._peer):
+                    if s != r:
+                        self.ctx.ipc_close(pp)
+                self._gather(0)  # nobody maps the old arena any more
+                self.shard.ipc_free(self._arena[0])
+                self._arena = None
+            size = int(need * 1.1) + (1 << 20)
+            ptr, handle = self.shard.ipc_alloc(size)
+        except RuntimeError:
+            ok, ptr, handle, size = False, 0, b"", 0
+        handles = self._gather(handle if ok else None)
+        peers = [ptr] * W
+        if all(h is not None for h in handles):
+            for s in range(W):
+                if s != r:
+                    try:
+                        peers[s] = self.ctx.ipc_open(handles[s])
+                    except RuntimeError:
+                        ok = False
+        else:
+            ok = False
+        if not all(self._gather(ok)):
+            self._arena_failed = True
+            return False
+        self._arena, self._peer = (ptr, size), peers
         return True
+
+    def _route_round_p2p(self, final):
+        """One routing round over peer memory: the pack kernel writes this rank's tuples straight into every owner's arena (NVLink
+        stores, no exchange kernel that would need SMs of its own); a host barrier says that every source has finished, then the
+        owner inserts its W regions of the round (beside the running pass unless this is the last round)."""
+        W, r = self.world, self.rank
+        cap = self._p2p_cap
+        stride = 24 * (cap + 1)
+        off = self._round * W * stride
+        self.ctx.names_pack_slots(0, [self._peer[o] + off + r * stride for o in range(W)], cap)
+        if W > 1:
+            dist.barrier(group=self._cpu_group)
+        self.shard.shard_insert_slots(self._arena[0] + off, W, cap, beside=not final)
+        self._round += 1
+
+    def _route_round(self, final):
+        """Pack the names that were not routed yet into one fixed-capacity region per owner, start their exchange and hand the
+        rounds whose exchange has finished to this rank's index shard (beside the running pass unless this is the last round)."""
+        if self._p2p_ok:
+            return self._route_round_p2p(final)
+        W = self.world
+        mx = max(self._gather(self.ctx.names_new(0)))
+        per = -(-mx // W)
+        cap = max(1, mx) if mx <= 8192 else int(per * 1.03) + 6 * int(per ** 0.5) + 1024
+        stride = 24 * (cap + 1)
+        send = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
+        recv = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
+        self.ctx.names_pack_slots(0, [send.data_ptr() + o * stride for o in range(W)], cap)
+        if W > 1:
+            work = dist.all_to_all_single(recv, send, async_op=True)
+        else:
+            recv, work = send, None
+        self._inflight.append((recv, send, cap, work))
+        self._round += 1
+        while len(self._inflight) > (0 if final else 1):
+            recv, send, cap, work = self._inflight.pop(0)
+            if work is not None:
+                work.wait()
+            if self.tdev.type == "cuda":
+                torch.cuda.current_stream().synchronize()  # not the device: the pass on the library's stream keeps running
+            self.shard.shard_insert_slots(recv.data_ptr(), W, cap, beside=not final)
+            self._keep += [recv, send]
 
     def _route_names(self, f, with_bytes=True):
         """Step 3, sender side: pack the names of file f by owner and exchange them.  Returns what the owner needs.
@@ -247,11 +381,23 @@ class ShardedFastqInfo:
         self._keep = []
         pair = self.mode == api.MODE_INDEX_PAIR
         again = dict(name=name, ptr2=ptr2, nbytes2=nbytes2, name2=name2, empty_ok=empty_ok, no_enc_ok=no_enc_ok, _exact=True)
-        speculative = (not _exact) and W > 1 and not pair and self._feed_file_speculative(0, ptr, nbytes)
+        routed = self.shard is not None and self.pipeline
+        self.rounds_done = 0
+        # (a world of one takes the same path when it has an index shard: the single-GPU tests of the pipelined routing)
+        speculative = (not _exact) and (W > 1 or routed) and not pair and self._feed_file_speculative(0, ptr, nbytes, routed=routed)
         if speculative:
             rep = ctx.finish()
-            bad = any(self._gather(rep.error.code != 0))  # every rank takes the same turn: the steps below are collective
-            if not bad and self.shard is not None:
+            if routed:
+                # the names went to their owners while the range was validated (tuples only): an equal hash, a region or table that
+                # overflowed, a chunk that was redone by the two-pass kernels after its names had left, or any error decides nothing here
+                inserted, equal, overflow = self.shard.shard_slots_result()
+                mine_bad = rep.error.code != 0 or equal > 0 or overflow or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
+                bad = any(self._gather(bool(mine_bad)))
+                if self._hook_exc is not None:
+                    raise self._hook_exc
+            else:
+                bad = any(self._gather(rep.error.code != 0))  # every rank takes the same turn: the steps below are collective
+            if not bad and self.shard is not None and not routed:
                 meta, blob, ms, bs = self._route_names(0, with_bytes=False)
                 self.shard.shard_insert(meta.data_ptr(), ms[-1], 0, ms, bs)
                 bad = any(self._gather(self.shard.shard_result()[3] > 0))

@@ -172,6 +172,36 @@ int fqg_set_file_total(fqg_ctx* ctx, int file, uint64_t total_records);
 /* bins [lo, hi] of a file's read-length histogram (terminator included, like the reference's rdlen_ctr) */
 int fqg_hist_range(fqg_ctx* ctx, int file, uint64_t lo, uint64_t hi, uint64_t* out);
 
+/* ---- pipelined routing (sharded index runs, one file, tuples only; dist.py `_route_round`) ----
+ * Instead of one exchange after the whole range has been validated, the names travel chunk by chunk while the next chunk's
+ * clean-data pass runs.  The hook is called from inside fqg_feed_device right after the pass of a chunk has been LAUNCHED
+ * (the GPU is busy with it): the callee packs the names of the chunks before it (fqg_names_pack_slots, on the context's side
+ * stream), starts their exchange and hands earlier rounds to the owner's index (fqg_shard_insert_slots).  Chunks that do not
+ * take the clean-data pass do not call the hook; whatever is left is routed by the caller after the last feed. */
+typedef void (*fqg_chunk_hook)(void* user, int file);
+int fqg_set_chunk_hook(fqg_ctx* ctx, fqg_chunk_hook hook, void* user);
+/* records whose names were not packed by fqg_names_pack_slots yet */
+int fqg_names_new(fqg_ctx* ctx, int file, uint64_t* n_new);
+/* Packs the 24-byte tuples of those records by owner into `world` regions of fixed capacity: region o starts at
+ * region_ptrs[o] (device memory, local or a peer's mapped with fqg_ipc_open), holds one 24-byte header {count, 0, 0} and
+ * then up to region_cap tuples.  A count above region_cap says the region overflowed (the surplus tuples are dropped): the owner
+ * reports it and the caller repeats the job through the exact path.  Returns when the regions are complete. */
+int fqg_names_pack_slots(fqg_ctx* ctx, int file, uint32_t world, void* const* region_ptrs, uint64_t region_cap);
+/* owner side: room for n_names in the index shard before the first fqg_shard_insert_slots (the table cannot grow between rounds) */
+int fqg_shard_reserve(fqg_ctx* ctx, uint64_t n_names);
+/* inserts the tuples of n_src regions (region s at regions + s * 24 * (region_cap + 1)); asynchronous: the regions must stay
+ * valid until fqg_shard_slots_result.  beside != 0: one block per SM, so that the kernel fits next to a running clean-data pass. */
+int fqg_shard_insert_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, uint64_t region_cap, int beside);
+/* waits for the inserts: tuples inserted, equal hashes met (a duplicate name or a 64-bit collision: tuples alone cannot tell),
+ * and whether a region or the table overflowed.  Any non-zero `equal_hashes` / `overflow` sends the job through the exact path. */
+int fqg_shard_slots_result(fqg_ctx* ctx, uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow);
+/* device memory other processes of this node can map (CUDA IPC): the owner's regions written by its peers' pack kernels
+ * over NVLink instead of an all-to-all.  fqg_ipc_alloc returns the pointer and a 64-byte handle; fqg_ipc_open maps a peer's. */
+int fqg_ipc_alloc(fqg_ctx* ctx, size_t bytes, void** device_ptr, uint8_t handle[64]);
+int fqg_ipc_open(fqg_ctx* ctx, const uint8_t handle[64], void** device_ptr);
+int fqg_ipc_close(fqg_ctx* ctx, void* device_ptr);
+int fqg_ipc_free(fqg_ctx* ctx, void* device_ptr);
+
 /* ---- per-kernel device timing (CUDA events around every launch on the context's stream) ---- */
 enum { FQG_K_SCAN = 0, FQG_K_RECORDS = 1, FQG_K_INDEX = 2, FQG_K_MATE = 3, FQG_K_PAIR = 4, FQG_K_OTHER = 5, FQG_K_TILE = 6 /* fused scan+records, one thread per record */,
        FQG_K_LANES = 7 /* clean-data pass, chunk-parallel */, FQG_K_COUNT = 8 };

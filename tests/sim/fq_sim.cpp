@@ -240,6 +240,42 @@ class FqSimDevice : public FqDevice {
       if (unpaired != FQ_IDX_NONE) { unsigned long long key = FQ_KEY(sb + unpaired, FQ_R_NAME); if (key < *a.dup_key) *a.dup_key = key; }
     }
   }
+  void route_begin(unsigned long long* cursors, uint32_t world, bool) override { memset(cursors, 0, world * sizeof(unsigned long long)); }
+  void names_pack_slots(const FqName* names, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
+                        unsigned long long* cursors) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < nrec; k++) {
+      const FqName& nm = names[k];
+      if (nm.hash == FQ_HASH_SKIP) continue;
+      uint32_t o = fq_owner_of(nm.hash, world);
+      unsigned long long pos = cursors[o]++;
+      if (pos < cap) { FqPackedName& pn = R.region[o][1 + pos]; pn.hash = nm.hash; pn.record = g0 + k; pn.off = 0; pn.len = nm.len; }
+    }
+  }
+  void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R) override {
+    for (uint32_t o = 0; o < world; o++) { FqPackedName& h = R.region[o][0]; h.hash = cursors[o]; h.record = 0; h.off = 0; h.len = 0; }
+  }
+  void shard_insert_slots(const FqPackedName* regions, uint32_t n_src, uint64_t cap, FqSlot* slots, unsigned long long mask,
+                          unsigned long long* counters, bool) override {
+    n_launch_++;
+    for (uint32_t src = 0; src < n_src; src++) {
+      const FqPackedName* reg = regions + (size_t)src * (cap + 1);
+      unsigned long long cnt = reg[0].hash;
+      if (cnt > cap) { counters[2] = 1; cnt = cap; }
+      for (unsigned long long m = 0; m < cnt; m++) {
+        const FqPackedName& pn = reg[1 + m];
+        unsigned long long i = pn.hash & mask, probes = 0;
+        for (;; i = (i + 1) & mask) {
+          if (++probes > mask) { counters[2] = 1; break; }
+          FqSlot& s = slots[i];
+          if (s.hash == FQ_HASH_EMPTY) { s.hash = pn.hash; s.idx1 = pn.record; counters[1]++; break; }
+          if (s.hash != pn.hash) continue;
+          counters[0]++;
+          break;
+        }
+      }
+    }
+  }
   void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {
     n_launch_++;
     for (unsigned long long m = 0; m < n; m++) if (meta[m].record == record && m < *out_pos) *out_pos = m;

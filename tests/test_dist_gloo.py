@@ -59,19 +59,33 @@ def _cases():
     return cases
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_transcripts_match_oracle(tmp_path, world):
+# variants of the name routing: pipelined (chunk by chunk through the chunk hook; the default), the same with tiny chunks so that
+# every range takes several routing rounds, and the one-exchange path (FQG_NO_PIPELINE=1)
+VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "one_exchange": {"FQG_NO_PIPELINE": "1"}}
+
+
+@pytest.mark.parametrize("world,variant", [(2, "pipelined"), (3, "pipelined"), (2, "small_chunks"), (3, "small_chunks"), (2, "one_exchange")])
+def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
     cases = _cases()
     cin, cout = tmp_path / "cases.json", tmp_path / "out.json"
     json.dump(cases, open(cin, "w"))
-    port = 29600 + world
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    port = 29600 + world + 10 * list(VARIANTS).index(variant)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", **VARIANTS[variant])
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"), str(cin), str(cout)], env=env, timeout=600)
-    got = json.load(open(cout))
+    res = json.load(open(cout))
+    got, rounds = res["transcripts"], res["rounds"]
     assert len(got) == len(cases)
     for c, g in zip(cases, got):
         argv = (["-r"] if c["mode"] == "single" else []) + ["a.fq"] + (["b.fq"] if c["mode"] == "pair" else [])
         want = oracle_run(argv, bytes.fromhex(c["hex"]), bytes.fromhex(c["hex2"]) if c["mode"] == "pair" else None)
         assert tuple(g) == want, (c["file"], c["mode"], c["cuts"], g)
+    # the routing under test was really taken: the clean big file goes through the chunk hook, in several rounds when chunks are small
+    by_name = {(c["file"], c["mode"]): r for c, r in zip(cases, rounds)}
+    if variant == "pipelined":
+        assert by_name[("big_clean", "index")] >= 1
+    elif variant == "small_chunks":
+        assert by_name[("big_clean", "index")] >= 3
+    else:
+        assert by_name[("big_clean", "index")] == 0

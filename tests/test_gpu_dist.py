@@ -23,3 +23,37 @@ def test_nccl_sharded_matches_oracle(tmp_path):
     assert len(res) == 9
     for x in res:
         assert x["ok"], x
+
+
+@pytest.mark.parametrize("variant", ["clean", "dup", "bad", "clean_exchange"])
+def test_pipelined_routing_one_gpu(variant, monkeypatch):
+    """The chunk-by-chunk routing of the sharded index (chunk hook beside the clean-data pass, fixed-capacity regions, owner-side
+    insert on the side stream) with a world of one: same kernels and stream choreography as N ranks, the exchange is a no-op."""
+    import torch
+    import fastq_utils_b200 as fq
+    from fastq_utils_b200 import dist as fqdist
+    from _util import oracle_run
+    monkeypatch.setenv("FQG_MAX_CHUNK_BYTES", str(24 << 20))  # ~9 chunks: the hook fires beside every pass after the first
+    if variant == "clean_exchange":  # the rounds as exchanges of packed send buffers instead of stores into the owner's arena
+        monkeypatch.setenv("FQG_P2P", "0")
+        variant = "clean"
+    rb = fq.illumina_record_bytes()
+    n = 600_000
+    t = torch.zeros(n * rb + 64, dtype=torch.uint8, device="cuda")
+    fq.synth_illumina(t, 0, n, seed=42, mate=1, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    if variant in ("dup", "bad"):
+        t[550_000 * rb:550_001 * rb] = t[3 * rb:4 * rb].clone()
+    if variant == "bad":
+        t[300_000 * rb + 80] = ord("*")
+    torch.cuda.synchronize()
+    run = fqdist.ShardedFastqInfo(fq.MODE_INDEX, device=0, n_hint=n)
+    res = run.run_device(t.data_ptr(), n * rb, name="a.fq")
+    want = oracle_run(["a.fq"], bytes(t[:n * rb].cpu().numpy()), None)
+    assert tuple(res["transcript"]) == want
+    if variant == "clean":
+        assert run.rounds_done >= 5 and run._p2p_ok == (os.environ.get("FQG_P2P", "1") != "0")
+        assert res["n_index_entries"] == n and run.ctx.path_counts()["lanes"] >= 8
+        # a second job on the same objects (bench loop): the table is cleared, the rounds start over
+        res2 = run.run_device(t.data_ptr(), n * rb, name="a.fq")
+        assert tuple(res2["transcript"]) == want
