@@ -189,7 +189,9 @@ def main():
     for _ in range(a.warmup):
         step()
     ctx.kernel_stats(reset=True)
-    l0 = ctx.launch_count()
+    if world > 1:
+        runner.shard.kernel_stats(reset=True)  # (the index shard's kernels were counted from the first warm-up step before)
+    l0 = ctx.launch_count() + (runner.shard.launch_count() if world > 1 else 0)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -205,6 +207,10 @@ def main():
     sampler.join(timeout=2)
     launches = ctx.launch_count() - l0
     ks = ctx.kernel_stats()
+    if world > 1 and os.environ.get("FQG_DEBUG_ROUTE"):
+        print(f"[rank {rank}] kernel ms per step:", {k: round(v["ms"] / a.steps, 2) for k, v in ks.items() if v["launches"]},
+              "index", round(runner.shard.kernel_stats()["index"]["ms"] / a.steps, 2), "wall", round(wall / a.steps * 1e3, 2), file=sys.stderr)
+        print(f"[rank {rank}] host ms per step inside the routing rounds:", {k: round(v / (a.steps + a.warmup), 2) for k, v in runner.host_ms.items()}, "rounds", runner.rounds_done, "p2p", runner._p2p_ok, file=sys.stderr)
     if world > 1:  # the index shard lives in its own context
         launches += runner.shard.launch_count()
         ks["index"] = runner.shard.kernel_stats()["index"]

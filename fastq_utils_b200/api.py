@@ -97,12 +97,15 @@ def lib():
         L.fqg_sniff_device.argtypes = [vp, ci, vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
         L.fqg_set_sniff.argtypes = [vp, ci, ctypes.c_int32, ctypes.c_int32]
         L.fqg_set_file_total.argtypes = [vp, ci, u64]
+        L.fqg_set_line_hint.argtypes = [vp, ci, ctypes.c_uint32]
         L.fqg_set_chunk_hook.argtypes = [vp, CHUNK_HOOK, vp]
         L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
         L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64]
         L.fqg_shard_reserve.argtypes = [vp, u64]
         L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ci]
         L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
+        L.fqg_side_copy.argtypes = [vp, vp, vp, sz]
+        L.fqg_side_sync.argtypes = [vp]
         L.fqg_ipc_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.c_char_p]
         L.fqg_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
         L.fqg_ipc_close.argtypes = [vp, vp]
@@ -279,6 +282,12 @@ class FastqInfo:
         _check(self._ctx, lib().fqg_shard_slots_result(self._ctx, ctypes.byref(ins), ctypes.byref(eq), ctypes.byref(ov)), "fqg_shard_slots_result")
         return int(ins.value), int(eq.value), bool(ov.value)
 
+    def side_copy(self, dst, src, n):
+        _check(self._ctx, lib().fqg_side_copy(self._ctx, ctypes.c_void_p(dst), ctypes.c_void_p(src), n), "fqg_side_copy")
+
+    def side_sync(self):
+        _check(self._ctx, lib().fqg_side_sync(self._ctx), "fqg_side_sync")
+
     def ipc_alloc(self, nbytes):
         p, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
         _check(self._ctx, lib().fqg_ipc_alloc(self._ctx, nbytes, ctypes.byref(p), h), "fqg_ipc_alloc")
@@ -302,6 +311,9 @@ class FastqInfo:
 
     def set_sniff(self, file, fmt, color):
         _check(self._ctx, lib().fqg_set_sniff(self._ctx, file, fmt, color), "fqg_set_sniff")
+
+    def set_line_hint(self, file, seq_line_len):
+        _check(self._ctx, lib().fqg_set_line_hint(self._ctx, file, seq_line_len), "fqg_set_line_hint")
 
     def set_file_total(self, file, total):
         _check(self._ctx, lib().fqg_set_file_total(self._ctx, file, total), "fqg_set_file_total")

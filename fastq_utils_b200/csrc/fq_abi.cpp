@@ -183,3 +183,15 @@ extern "C" int fqg_ipc_free(fqg_ctx* c, void* dptr) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->dev->ipc_free(dptr))
 }
+extern "C" int fqg_side_copy(fqg_ctx* c, void* dst, const void* src, size_t n) {
+  if (!c || ((!dst || !src) && n)) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->dev->side_copy(dst, src, n))
+}
+extern "C" int fqg_side_sync(fqg_ctx* c) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->dev->side_sync())
+}
+extern "C" int fqg_set_line_hint(fqg_ctx* c, int file, uint32_t len) {
+  if (!c || file < 0 || file > 1) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->set_line_hint(file, len))
+}

@@ -772,34 +772,46 @@ fq_names_pack_kernel(const FqName* __restrict__ names, const uint8_t* __restrict
 struct SlotPackParams {
   const FqName* names; uint32_t nrec; unsigned long long g0; uint32_t world; unsigned long long cap; unsigned long long* cursors; FqRegionPtrs R;
 };
+#define FQ_PACK_ILP 4
 __global__ void __launch_bounds__(256, 8)
 fq_names_pack_slots_kernel(const SlotPackParams P) {
-  __shared__ unsigned long long s_cnt[FQ_SHARD_MAX_SRC], s_base[FQ_SHARD_MAX_SRC];
+  /* One block per SM is all the room there is beside the pass: the kernel lives on memory-level parallelism instead of occupancy.
+   * Every thread has FQ_PACK_ILP names in flight; the rank of a name among the warp's names of the same owner comes from one
+   * match.any (no loop over the owners), the warp's share of an owner's region from one shared atomic by the group's first lane. */
+  __shared__ unsigned int s_cnt[FQ_SHARD_MAX_SRC];
+  __shared__ unsigned long long s_base[FQ_SHARD_MAX_SRC];
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
-  for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < P.nrec; b0 += gridDim.x * blockDim.x) {
+  for (uint32_t b0 = blockIdx.x * (256u * FQ_PACK_ILP); b0 < P.nrec; b0 += gridDim.x * (256u * FQ_PACK_ILP)) {
     if (threadIdx.x < P.world) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t k = b0 + threadIdx.x;
-    FqName nm; nm.hash = FQ_HASH_SKIP; nm.off = 0; nm.len = 0;
-    if (k < P.nrec) nm = P.names[k];
-    const bool valid = nm.hash != FQ_HASH_SKIP;
-    const uint32_t o = valid ? fq_owner_of(nm.hash, P.world) : 0xFFFFFFFFu;
-    unsigned long long my = 0;
-    for (uint32_t w = 0; w < P.world; w++) { /* rank among the lanes of the same owner by warp vote, one shared atomic per warp and owner */
-      const uint32_t m = __ballot_sync(FULL, o == w);
-      if (!m) continue;
-      unsigned long long wm = 0;
-      if (lane == 0) wm = atomicAdd(&s_cnt[w], (unsigned long long)__popc(m));
-      wm = __shfl_sync(FULL, wm, 0);
-      if (o == w) my = wm + __popc(m & lt);
+    unsigned long long h[FQ_PACK_ILP]; uint32_t len[FQ_PACK_ILP], my[FQ_PACK_ILP];
+#pragma unroll
+    for (int j = 0; j < FQ_PACK_ILP; j++) {
+      const uint32_t k = b0 + j * 256u + threadIdx.x;
+      h[j] = FQ_HASH_SKIP; len[j] = 0;
+      if (k < P.nrec) { const FqName nm = P.names[k]; h[j] = nm.hash; len[j] = nm.len; }
+    }
+#pragma unroll
+    for (int j = 0; j < FQ_PACK_ILP; j++) {
+      const bool valid = h[j] != FQ_HASH_SKIP;
+      const uint32_t o = valid ? fq_owner_of(h[j], P.world) : 0xFFFFFFFFu;
+      const uint32_t m = __match_any_sync(FULL, o);
+      const int leader = __ffs(m) - 1;
+      uint32_t wm = 0;
+      if (valid && lane == leader) wm = atomicAdd(&s_cnt[o], (unsigned int)__popc(m));
+      wm = __shfl_sync(FULL, wm, leader);
+      my[j] = wm + __popc(m & lt);
     }
     __syncthreads();
-    if (threadIdx.x < P.world) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(P.cursors + threadIdx.x, s_cnt[threadIdx.x]) : 0ull;
+    if (threadIdx.x < P.world) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(P.cursors + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
     __syncthreads();
-    if (valid) {
-      const unsigned long long pos = s_base[o] + my;
-      if (pos < P.cap) { FqPackedName pn; pn.hash = nm.hash; pn.record = P.g0 + k; pn.off = 0; pn.len = nm.len; P.R.region[o][1 + pos] = pn; }
+#pragma unroll
+    for (int j = 0; j < FQ_PACK_ILP; j++) {
+      if (h[j] == FQ_HASH_SKIP) continue;
+      const uint32_t o = fq_owner_of(h[j], P.world);
+      const unsigned long long pos = s_base[o] + my[j];
+      if (pos < P.cap) { FqPackedName pn; pn.hash = h[j]; pn.record = P.g0 + b0 + j * 256u + threadIdx.x; pn.off = 0; pn.len = len[j]; P.R.region[o][1 + pos] = pn; }
     }
     __syncthreads();
   }
@@ -811,6 +823,9 @@ __global__ void fq_slots_header_kernel(const SlotHeaderParams P) {
 struct SlotInsertParams { const FqPackedName* regions; uint32_t n_src; unsigned long long cap; FqSlot* slots; unsigned long long mask; unsigned long long* counters; };
 __global__ void __launch_bounds__(256, 8)
 fq_shard_insert_slots_kernel(const SlotInsertParams P) {
+  /* One probe in flight per thread.  Measured on B200 beside the pass: 2 or 4 independent first probes per thread are slower (the
+   * atomics, not their latency, are the limit), and so are short blocks on a low-priority stream (they crowd the start of the
+   * next pass, whose blocks must all be resident). */
   unsigned long long inserted = 0, equal = 0;
   const unsigned long long total = (unsigned long long)P.n_src * P.cap, step = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
@@ -821,13 +836,13 @@ fq_shard_insert_slots_kernel(const SlotInsertParams P) {
     const unsigned long long cnt = reg[0].hash;
     if (cnt > P.cap && idx == 0) atomicExch(P.counters + 2, 1ull); /* the sender had more names for this owner than the region holds */
     if (idx >= cnt) continue;
-    const FqPackedName pn = reg[1 + idx];
-    unsigned long long i = pn.hash & P.mask, probes = 0;
+    const unsigned long long hash = reg[1 + idx].hash, rec = reg[1 + idx].record;
+    unsigned long long i = hash & P.mask, probes = 0;
     for (;; i = (i + 1) & P.mask) {
       if (++probes > P.mask) { atomicExch(P.counters + 2, 1ull); break; }
       unsigned long long cur, cur_idx;
-      if (slot_claim128(P.slots + i, pn.hash, pn.record, &cur, &cur_idx)) { inserted++; break; }
-      if (cur != pn.hash) continue;
+      if (slot_claim128(P.slots + i, hash, rec, &cur, &cur_idx)) { inserted++; break; }
+      if (cur != hash) continue;
       equal++; /* a duplicate name or a 64-bit collision: tuples alone cannot tell, the exact path decides */
       break;
     }
@@ -1188,7 +1203,7 @@ class FqCudaDevice : public FqDevice {
                         unsigned long long* cursors) override {
     if (!nrec) return;
     SlotPackParams P; P.names = names; P.nrec = nrec; P.g0 = g0; P.world = world; P.cap = cap; P.cursors = cursors; P.R = R;
-    int grid = (int)std::min<uint32_t>((nrec + 255) / 256, (uint32_t)sms_ * 8);
+    int grid = (int)std::min<uint32_t>((nrec + 256u * FQ_PACK_ILP - 1) / (256u * FQ_PACK_ILP), (uint32_t)sms_ * 8);
     tic(FQG_K_OTHER, 0, nrec, st2_);
     fq_names_pack_slots_kernel<<<grid, 256, 0, st2_>>>(P);
     toc(st2_); launched();
@@ -1210,6 +1225,8 @@ class FqCudaDevice : public FqDevice {
     fq_shard_insert_slots_kernel<<<grid, 256, 0, st2_>>>(P);
     toc(st2_); launched();
   }
+  void side_copy(void* dst, const void* src, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, st2_)); }
+  void side_sync() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); }
   void* ipc_alloc(size_t n, uint8_t handle[64]) override {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     void* p = nullptr; FQ_CUDA_CHECK(cudaSetDevice(dev_)); FQ_CUDA_CHECK(cudaMalloc(&p, n ? n : 1));

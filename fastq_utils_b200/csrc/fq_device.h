@@ -144,6 +144,8 @@ class FqDevice {
    * counters[2] = 1 when a header count exceeds cap or the table is full.  Asynchronous. */
   virtual void shard_insert_slots(const FqPackedName* regions, uint32_t n_src, uint64_t cap, FqSlot* slots, unsigned long long mask,
                                   unsigned long long* counters, bool beside) = 0;
+  virtual void side_copy(void* dst, const void* src, size_t n) = 0;
+  virtual void side_sync() = 0;
   /* memory that other processes can map (CUDA IPC); devices without it throw */
   virtual void* ipc_alloc(size_t n, uint8_t handle[64]) { (void)n; (void)handle; throw std::runtime_error("this device has no inter-process memory"); }
   virtual void* ipc_open(const uint8_t handle[64]) { (void)handle; throw std::runtime_error("this device has no inter-process memory"); }

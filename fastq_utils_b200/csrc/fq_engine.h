@@ -82,6 +82,7 @@ class FqEngine {
   void hist_range(int file, uint64_t lo, uint64_t hi, uint64_t* out);
   void set_file_total(int file, uint64_t total);
   void set_sniff(int file, int fmt, int color);
+  void set_line_hint(int file, uint32_t len) { if (len && !f_[file].first_seq_len) f_[file].first_seq_len = len; }
   void sniff_device(int file, const void* dptr, size_t n, uint32_t skip, int32_t* fmt, int32_t* color);
   void shard_claim(const void* meta, uint64_t n, const void* blob, uint32_t n_src, const uint64_t* meta_start, const uint64_t* blob_start, uint64_t step_base);
   void shard_claim_result(uint64_t* key, uint64_t* record, char* name, uint32_t* name_len, uint64_t* claimed, uint64_t* collisions);

@@ -19,6 +19,7 @@ file caused by a NUL-led header line (src/fastq.c:248) is reported as unsupporte
 """
 import ctypes
 import os
+import time
 
 import torch
 import torch.distributed as dist
@@ -51,8 +52,12 @@ class ShardedFastqInfo:
         self.pipeline = os.environ.get("FQG_NO_PIPELINE", "0") in ("", "0")
         # pipelined rounds over peer memory (CUDA IPC) instead of all-to-all exchanges: GPUs only; FQG_P2P=0 turns it off
         self.p2p = self.tdev.type == "cuda" and os.environ.get("FQG_P2P", "1") not in ("", "0")
-        self._arena, self._peer, self._arena_failed, self._p2p_ok = None, None, False, False
+        self.p2p_stores = os.environ.get("FQG_P2P_STORES", "1") not in ("", "0")  # NVLink stores from the pack kernel (0: copy engines)
+        self.defer_insert = os.environ.get("FQG_DEFER_INSERT", "1") not in ("", "0")
+        self._pending_insert = None
+        self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage = None, None, False, False, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
+        self.host_ms = {"pack": 0.0, "copy": 0.0, "barrier": 0.0}  # host time inside the peer-memory rounds, accumulated
 
     # ------------------------------------------------------------------ helpers
     def _gather(self, obj):
@@ -158,9 +163,9 @@ class ShardedFastqInfo:
     def _guess_phase(self, ptr, nbytes):
         """Line class (0 header, 1 sequence, 2 plus, 3 quality) of the line this range starts in, from the range's own first lines:
         a complete line that is exactly "+" is a plus line.  Returns (ok, class, ends of the first four lines, ends with LF, bytes
-        per record over the first complete records)."""
+        per record over the first complete records, raw length of the first complete sequence line)."""
         if nbytes < 4096:
-            return (False, 0, [KEY_NONE] * 4, True, 0.0)
+            return (False, 0, [KEY_NONE] * 4, True, 0.0, 0)
         k = min(nbytes, 1 << 18)
         head = bytes(_as_tensor(ptr, k, self.tdev).cpu().numpy())
         last = bytes(_as_tensor(ptr + nbytes - 1, 1, self.tdev).cpu().numpy())
@@ -176,9 +181,10 @@ class ShardedFastqInfo:
                 cls = (2 - i) % 4
                 break
         if cls is None or len(ends) < 5:
-            return (False, 0, [KEY_NONE] * 4, last == b"\n", 0.0)
+            return (False, 0, [KEY_NONE] * 4, last == b"\n", 0.0, 0)
         k = (len(ends) - 1) // 4
-        return (True, cls, ends[:4], last == b"\n", (ends[4 * k] - ends[0]) / k)
+        seq = next(ends[i] - ends[i - 1] for i in range(1, 5) if (cls + i) % 4 == 1)
+        return (True, cls, ends[:4], last == b"\n", (ends[4 * k] - ends[0]) / k, seq)
 
     def _feed_file_speculative(self, f, ptr, nbytes, routed=False):
         """Steps 1-2 without counting the line feeds of the range first: every rank takes the line phase of its range from its own
@@ -208,6 +214,7 @@ class ShardedFastqInfo:
         for q in reqs:
             q.wait()
         ctx.set_stream_start(f, skip[r], 0)  # record numbers inside the range: they only matter when something is wrong
+        ctx.set_line_hint(f, info[r][5])  # a range that starts inside the file never sees the first record's sequence line
         if routed:
             # the names travel chunk by chunk beside the next chunk's pass: as many rounds as the longest range has chunks, so that
             # no round carries more than one chunk (ranks with fewer chunks add empty rounds: the rounds are collective)
@@ -215,15 +222,17 @@ class ShardedFastqInfo:
             self._rounds_total = max(1, max(-(-x[-1] // chunk) for x in info))
             est = sum(x[-1] / max(x[4], 16.0) for x in info) / W
             self.shard.shard_reserve(int(est * 1.05) + 4096)
-            self._round, self._fires, self._inflight, self._hook_exc = 0, 0, [], None
+            self._round, self._fires, self._inflight, self._hook_exc, self._pending_insert = 0, 0, [], None, None
             # names of one chunk for one owner, with room to spare (the estimate comes from the first records of every range)
             per = min(chunk, max(x[-1] for x in info)) / max(min(x[4] for x in info), 16.0) / W
             self._p2p_cap = int(per * 1.25) + 4096
             self._p2p_ok = self.p2p and self._ensure_arena(self._rounds_total * W * 24 * (self._p2p_cap + 1))
             ctx.set_chunk_hook(self._on_chunk)
+        t0 = time.perf_counter()
         try:
             self._feed_range(f, ptr, nbytes, head, cut[r + 1] if r < W - 1 else 0)
         finally:
+            self.host_ms["feed"] = self.host_ms.get("feed", 0.0) + (time.perf_counter() - t0) * 1e3
             if routed:
                 ctx.set_chunk_hook(None)
         if routed:
@@ -253,6 +262,11 @@ class ShardedFastqInfo:
         that pass runs on the GPU.  Every rank performs exactly `_rounds_total` rounds (they are collective); the first call has
         nothing to route yet."""
         self._fires += 1
+        t0 = time.perf_counter()
+        self._on_chunk_body()
+        self.host_ms["hook"] = self.host_ms.get("hook", 0.0) + (time.perf_counter() - t0) * 1e3
+
+    def _on_chunk_body(self):
         if self._hook_exc is None and self._fires >= 2 and self._round < self._rounds_total - 1:
             try:
                 self._route_round(False)
@@ -306,10 +320,36 @@ class ShardedFastqInfo:
         cap = self._p2p_cap
         stride = 24 * (cap + 1)
         off = self._round * W * stride
-        self.ctx.names_pack_slots(0, [self._peer[o] + off + r * stride for o in range(W)], cap)
+        t0 = time.perf_counter()
+        if self.p2p_stores:  # the pack kernel stores into the owners' arenas itself
+            self.ctx.names_pack_slots(0, [self._peer[o] + off + r * stride for o in range(W)], cap)
+            t1 = time.perf_counter()
+        else:  # packed next to the data, then moved by the copy engines: the SMs stay with the pass
+            if self._stage is None or self._stage.numel() < W * stride:
+                self._stage = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
+            st = self._stage.data_ptr()
+            self.ctx.names_pack_slots(0, [self._arena[0] + off + r * stride if o == r else st + o * stride for o in range(W)], cap)
+            t1 = time.perf_counter()
+            for d in range(1, W):
+                o = (r + d) % W
+                self.ctx.side_copy(self._peer[o] + off + r * stride, st + o * stride, stride)
+            self.ctx.side_sync()
+        t2 = time.perf_counter()
+        # the round before this one goes into the index now: its barrier was passed a whole pass ago, so the insert starts beside
+        # this pass right after the pack, not after this round's wait for the slowest rank (which would push it into the next pass)
+        if self._pending_insert is not None:
+            self.shard.shard_insert_slots(self._arena[0] + self._pending_insert, W, cap, beside=True)
+            self._pending_insert = None
         if W > 1:
             dist.barrier(group=self._cpu_group)
-        self.shard.shard_insert_slots(self._arena[0] + off, W, cap, beside=not final)
+        t3 = time.perf_counter()
+        self.host_ms["pack"] += (t1 - t0) * 1e3
+        self.host_ms["copy"] += (t2 - t1) * 1e3
+        self.host_ms["barrier"] += (t3 - t2) * 1e3
+        if final or not self.defer_insert:
+            self.shard.shard_insert_slots(self._arena[0] + off, W, cap, beside=not final)
+        else:
+            self._pending_insert = off
         self._round += 1
 
     def _route_round(self, final):

@@ -167,6 +167,9 @@ int fqg_shard_claim_result(fqg_ctx* ctx, uint64_t* event_key, uint64_t* record, 
  * one rank holds: that rank sniffs (fqg_sniff_device), everyone sets the result before feeding */
 int fqg_sniff_device(fqg_ctx* ctx, int file, const void* device_bytes, size_t n, uint32_t skip_lines, int32_t* sniff_format, int32_t* color_space);
 int fqg_set_sniff(fqg_ctx* ctx, int file, int32_t sniff_format, int32_t color_space);
+/* raw length of a typical sequence line of the file (a rank that does not hold the file's first record cannot see it): picks the
+ * mode of the clean-data pass, one thread per line for short lines; 0 = unknown.  A wrong hint costs time, never correctness. */
+int fqg_set_line_hint(fqg_ctx* ctx, int file, uint32_t seq_line_len);
 /* records of file 0 over all ranks: the mate loop's steps and line numbers continue after them */
 int fqg_set_file_total(fqg_ctx* ctx, int file, uint64_t total_records);
 /* bins [lo, hi] of a file's read-length histogram (terminator included, like the reference's rdlen_ctr) */
@@ -197,6 +200,10 @@ int fqg_shard_insert_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_
 int fqg_shard_slots_result(fqg_ctx* ctx, uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow);
 /* device memory other processes of this node can map (CUDA IPC): the owner's regions written by its peers' pack kernels
  * over NVLink instead of an all-to-all.  fqg_ipc_alloc returns the pointer and a 64-byte handle; fqg_ipc_open maps a peer's. */
+/* device-to-device copy on the context's side stream (the copy engines move a packed region into a peer's arena while the SMs
+ * stay with the clean-data pass), and the wait for it */
+int fqg_side_copy(fqg_ctx* ctx, void* device_dst, const void* device_src, size_t bytes);
+int fqg_side_sync(fqg_ctx* ctx);
 int fqg_ipc_alloc(fqg_ctx* ctx, size_t bytes, void** device_ptr, uint8_t handle[64]);
 int fqg_ipc_open(fqg_ctx* ctx, const uint8_t handle[64], void** device_ptr);
 int fqg_ipc_close(fqg_ctx* ctx, void* device_ptr);

@@ -276,6 +276,8 @@ class FqSimDevice : public FqDevice {
       }
     }
   }
+  void side_copy(void* dst, const void* src, size_t n) override { memmove(dst, src, n); }
+  void side_sync() override {}
   void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {
     n_launch_++;
     for (unsigned long long m = 0; m < n; m++) if (meta[m].record == record && m < *out_pos) *out_pos = m;

@@ -6,6 +6,11 @@ import torch
 import fastq_utils_b200 as fq
 from fastq_utils_b200 import dist as fqdist
 
+import torch.distributed as dist
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:  # experiment: NCCL initialised (two ranks, one all-reduce), every rank then works alone
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    x = torch.ones(1 << 20, device="cuda"); dist.all_reduce(x); torch.cuda.synchronize()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 40_000_000
 rb = fq.illumina_record_bytes()
 t = torch.zeros(n * rb + 64, dtype=torch.uint8, device="cuda")
@@ -14,7 +19,11 @@ for s in range(0, n, 8_000_000):
     k = min(8_000_000, n - s)
     fq.synth_illumina(t[s * rb:], s, k, seed=42, mate=1, perm_window=0, stream=st)
 torch.cuda.synchronize()
-run = fqdist.ShardedFastqInfo(fq.MODE_INDEX, device=0, n_hint=n)
+if os.environ.get("PEER") and torch.cuda.device_count() > 1:  # does an enabled peer mapping change the index kernels?
+    a = torch.zeros(1 << 20, device="cuda:1"); b = a.to("cuda:0"); torch.cuda.synchronize(); print("peer access enabled", torch.cuda.can_device_access_peer(0, 1))
+dev = torch.cuda.current_device()
+run = fqdist.ShardedFastqInfo(fq.MODE_INDEX, device=dev, n_hint=n)
+run.world, run.rank = 1, 0
 ts = []
 for i in range(5):
     if i == 2:
@@ -22,6 +31,8 @@ for i in range(5):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     res = run.run_device(t.data_ptr(), n * rb, name="a.fq")
     torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+if dist.is_initialized() and dist.get_rank() != 0:
+    sys.exit(0)
 print("pipeline", run.pipeline, "rounds", run.rounds_done, "step ms", [round(x, 2) for x in ts], "GB/s", round(n * rb / min(ts[2:]) / 1e6, 1), "rc", res["transcript"][0], res["n_index_entries"])
 for nm, c in (("ctx", run.ctx), ("shard", run.shard)):
     ks = c.kernel_stats()
