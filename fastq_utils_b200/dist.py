@@ -147,6 +147,8 @@ class ShardedFastqInfo:
                 reqs.append(dist.irecv(head[:cut[r + 1]], r + 1))
             for q in reqs:
                 q.wait()
+            if reqs:
+                self._sync()  # the library reads the head on its own stream
         ctx.set_stream_start(f, skip[r], firstrec[r])
         if last_rank:
             ctx.feed_device(f, ptr, nbytes, last=True)
@@ -213,6 +215,8 @@ class ShardedFastqInfo:
             reqs.append(dist.irecv(head[:cut[r + 1]], r + 1))
         for q in reqs:
             q.wait()
+        if reqs:
+            self._sync()  # the library reads the head on its own stream
         ctx.set_stream_start(f, skip[r], 0)  # record numbers inside the range: they only matter when something is wrong
         ctx.set_line_hint(f, info[r][5])  # a range that starts inside the file never sees the first record's sequence line
         if routed:
