@@ -52,12 +52,12 @@ class ShardedFastqInfo:
         self.pipeline = os.environ.get("FQG_NO_PIPELINE", "0") in ("", "0")
         # pipelined rounds over peer memory (CUDA IPC) instead of all-to-all exchanges: GPUs only; FQG_P2P=0 turns it off
         self.p2p = self.tdev.type == "cuda" and os.environ.get("FQG_P2P", "1") not in ("", "0")
-        self.p2p_stores = os.environ.get("FQG_P2P_STORES", "1") not in ("", "0")  # NVLink stores from the pack kernel (0: copy engines)
-        self.defer_insert = os.environ.get("FQG_DEFER_INSERT", "1") not in ("", "0")
+        # the copy engines move the packed regions; FQG_P2P_STORES=1: the pack kernel stores into the owners' arenas itself (A/B)
+        self.p2p_stores = os.environ.get("FQG_P2P_STORES", "0") not in ("", "0")
         self._pending_insert = None
         self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage = None, None, False, False, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
-        self.host_ms = {"pack": 0.0, "copy": 0.0, "barrier": 0.0}  # host time inside the peer-memory rounds, accumulated
+        self.host_ms = {"pack": 0.0, "barrier": 0.0}  # host time inside the peer-memory rounds, accumulated
 
     # ------------------------------------------------------------------ helpers
     def _gather(self, obj):
@@ -317,44 +317,51 @@ class ShardedFastqInfo:
         return True
 
     def _route_round_p2p(self, final):
-        """One routing round over peer memory: the pack kernel writes this rank's tuples straight into every owner's arena (NVLink
-        stores, no exchange kernel that would need SMs of its own); a host barrier says that every source has finished, then the
-        owner inserts its W regions of the round (beside the running pass unless this is the last round)."""
+        """One routing round over peer memory.  The tuples of this round are packed by owner next to the data and the copy engines
+        move each region into its owner's arena (CUDA IPC over NVLink): no exchange kernel needs SMs of its own, and the pass keeps
+        the memory system to itself (letting the pack kernel store into the peers' arenas directly, FQG_P2P_STORES=1, is as fast
+        with two ranks but slowed every pass threefold at eight: 5.9 M 24-byte remote stores per round and rank).  A host barrier
+        says that every source's round has landed; it is passed in the NEXT round, a whole pass later, so nobody waits long; then
+        the owner inserts the round beside the running pass.  Pack first, insert second: both want the one block slot per SM that
+        the pass leaves free."""
         W, r = self.world, self.rank
         cap = self._p2p_cap
         stride = 24 * (cap + 1)
         off = self._round * W * stride
         t0 = time.perf_counter()
-        if self.p2p_stores:  # the pack kernel stores into the owners' arenas itself
+        copies = []
+        if self.p2p_stores:
             self.ctx.names_pack_slots(0, [self._peer[o] + off + r * stride for o in range(W)], cap)
-            t1 = time.perf_counter()
-        else:  # packed next to the data, then moved by the copy engines: the SMs stay with the pass
+        else:
             if self._stage is None or self._stage.numel() < W * stride:
                 self._stage = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
             st = self._stage.data_ptr()
+            # (same stream as the copies of the round before: the pack overwrites the staging buffer after they have read it, and
+            # its completion says that they are done)
             self.ctx.names_pack_slots(0, [self._arena[0] + off + r * stride if o == r else st + o * stride for o in range(W)], cap)
-            t1 = time.perf_counter()
-            for d in range(1, W):
-                o = (r + d) % W
-                self.ctx.side_copy(self._peer[o] + off + r * stride, st + o * stride, stride)
-            self.ctx.side_sync()
+            copies = [(self._peer[(r + d) % W] + off + r * stride, st + ((r + d) % W) * stride) for d in range(1, W)]
+        t1 = time.perf_counter()
+        self._land_pending_round(beside=True)  # pack first, insert second: both want the one free block slot per SM
+        for dst, src in copies:
+            self.ctx.side_copy(dst, src, stride)
         t2 = time.perf_counter()
-        # the round before this one goes into the index now: its barrier was passed a whole pass ago, so the insert starts beside
-        # this pass right after the pack, not after this round's wait for the slowest rank (which would push it into the next pass)
-        if self._pending_insert is not None:
-            self.shard.shard_insert_slots(self._arena[0] + self._pending_insert, W, cap, beside=True)
-            self._pending_insert = None
-        if W > 1:
-            dist.barrier(group=self._cpu_group)
-        t3 = time.perf_counter()
         self.host_ms["pack"] += (t1 - t0) * 1e3
-        self.host_ms["copy"] += (t2 - t1) * 1e3
-        self.host_ms["barrier"] += (t3 - t2) * 1e3
-        if final or not self.defer_insert:
-            self.shard.shard_insert_slots(self._arena[0] + off, W, cap, beside=not final)
-        else:
-            self._pending_insert = off
+        self.host_ms["barrier"] += (t2 - t1) * 1e3
+        self._pending_insert = off
         self._round += 1
+        if final:
+            self.ctx.side_sync()
+            self._land_pending_round(beside=False)
+
+    def _land_pending_round(self, beside):
+        """The round packed before: this rank's copies of it are done (the caller has synchronised the side stream since); pass
+        the barrier (every source's are), insert."""
+        if self._pending_insert is None:
+            return
+        if self.world > 1:
+            dist.barrier(group=self._cpu_group)
+        self.shard.shard_insert_slots(self._arena[0] + self._pending_insert, self.world, self._p2p_cap, beside=beside)
+        self._pending_insert = None
 
     def _route_round(self, final):
         """Pack the names that were not routed yet into one fixed-capacity region per owner, start their exchange and hand the
