@@ -255,7 +255,10 @@ def main():
            "config": config, "reads_per_s": n * world / per_step, "device_ms_per_step": dev_ms / a.steps, "wall_ms_per_step": wall / a.steps * 1e3,
            "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary()}
     if world > 1:
-        out["config"]["parallelism"] = f"byte-range shards x{world}, names routed by hash (all-to-all over NCCL), stats all-reduced"
+        how = ("chunk by chunk into the owners' peer memory over NVLink (CUDA IPC), beside the next chunk's pass" if getattr(runner, "_p2p_ok", False)
+               else "chunk by chunk with all-to-all exchanges" if runner.pipeline else "one all-to-all over NCCL")
+        out["config"]["parallelism"] = f"byte-range shards x{world}, names routed by hash {how}, stats all-reduced"
+        out["config"]["routing_rounds"] = runner.rounds_done
         out["e2e"] = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "measured at N=1 only"}
 
     if rank == 0 and world == 1:

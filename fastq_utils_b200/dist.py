@@ -57,6 +57,7 @@ class ShardedFastqInfo:
         self._pending_insert = None
         self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage = None, None, False, False, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
+        self.exact_reruns = 0  # jobs the speculative / pipelined path handed to the exact path (tests)
         self.host_ms = {"pack": 0.0, "barrier": 0.0}  # host time inside the peer-memory rounds, accumulated
 
     # ------------------------------------------------------------------ helpers
@@ -230,6 +231,8 @@ class ShardedFastqInfo:
             # names of one chunk for one owner, with room to spare (the estimate comes from the first records of every range)
             per = min(chunk, max(x[-1] for x in info)) / max(min(x[4] for x in info), 16.0) / W
             self._p2p_cap = int(per * 1.25) + 4096
+            if os.environ.get("FQG_TEST_SLOT_CAP"):  # test hook: regions far too small, so that the overflow path is taken
+                self._p2p_cap = int(os.environ["FQG_TEST_SLOT_CAP"])
             self._p2p_ok = self.p2p and self._ensure_arena(self._rounds_total * W * 24 * (self._p2p_cap + 1))
             ctx.set_chunk_hook(self._on_chunk)
         t0 = time.perf_counter()
@@ -372,6 +375,8 @@ class ShardedFastqInfo:
         mx = max(self._gather(self.ctx.names_new(0)))
         per = -(-mx // W)
         cap = max(1, mx) if mx <= 8192 else int(per * 1.03) + 6 * int(per ** 0.5) + 1024
+        if os.environ.get("FQG_TEST_SLOT_CAP"):  # test hook: regions far too small, so that the overflow path is taken
+            cap = int(os.environ["FQG_TEST_SLOT_CAP"])
         stride = 24 * (cap + 1)
         send = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
         recv = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
@@ -453,6 +458,7 @@ class ShardedFastqInfo:
                 self.shard.shard_insert(meta.data_ptr(), ms[-1], 0, ms, bs)
                 bad = any(self._gather(self.shard.shard_result()[3] > 0))
             if bad:
+                self.exact_reruns += 1
                 return self.run_device(ptr, nbytes, **again)  # an error, a duplicate name or a wrong guess: the exact path decides
             local_key, T0, T1 = KEY_NONE, 0, 0
             dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0

@@ -177,10 +177,11 @@ int fqg_hist_range(fqg_ctx* ctx, int file, uint64_t lo, uint64_t hi, uint64_t* o
 
 /* ---- pipelined routing (sharded index runs, one file, tuples only; dist.py `_route_round`) ----
  * Instead of one exchange after the whole range has been validated, the names travel chunk by chunk while the next chunk's
- * clean-data pass runs.  The hook is called from inside fqg_feed_device right after the pass of a chunk has been LAUNCHED
- * (the GPU is busy with it): the callee packs the names of the chunks before it (fqg_names_pack_slots, on the context's side
- * stream), starts their exchange and hands earlier rounds to the owner's index (fqg_shard_insert_slots).  Chunks that do not
- * take the clean-data pass do not call the hook; whatever is left is routed by the caller after the last feed. */
+ * clean-data pass runs.  The hook is called once per chunk from inside fqg_feed_device: for a chunk that takes the clean-data
+ * pass right after that pass has been LAUNCHED (the GPU is busy with it; the names of the chunks before it are complete), for
+ * any other chunk after it has been validated.  The callee packs the names that were not packed yet
+ * (fqg_names_pack_slots, on the context's side stream), moves them to their owners and hands finished rounds to the owner's
+ * index (fqg_shard_insert_slots).  Whatever is left after the last feed is routed by the caller. */
 typedef void (*fqg_chunk_hook)(void* user, int file);
 int fqg_set_chunk_hook(fqg_ctx* ctx, fqg_chunk_hook hook, void* user);
 /* records whose names were not packed by fqg_names_pack_slots yet */

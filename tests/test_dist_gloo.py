@@ -61,10 +61,11 @@ def _cases():
 
 # variants of the name routing: pipelined (chunk by chunk through the chunk hook; the default), the same with tiny chunks so that
 # every range takes several routing rounds, and the one-exchange path (FQG_NO_PIPELINE=1)
-VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "one_exchange": {"FQG_NO_PIPELINE": "1"}}
+VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "one_exchange": {"FQG_NO_PIPELINE": "1"},
+            "overflow": {"FQG_TEST_SLOT_CAP": "7", "FQG_MAX_CHUNK_BYTES": "16384"}}  # regions of 7 tuples: every big job overflows and is redone exactly
 
 
-@pytest.mark.parametrize("world,variant", [(2, "pipelined"), (3, "pipelined"), (2, "small_chunks"), (3, "small_chunks"), (2, "one_exchange")])
+@pytest.mark.parametrize("world,variant", [(2, "pipelined"), (3, "pipelined"), (2, "small_chunks"), (3, "small_chunks"), (2, "one_exchange"), (2, "overflow")])
 def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
     cases = _cases()
@@ -87,5 +88,7 @@ def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
         assert by_name[("big_clean", "index")] >= 1
     elif variant == "small_chunks":
         assert by_name[("big_clean", "index")] >= 3
+    elif variant == "overflow":
+        assert by_name[("big_clean", "index")] == 1  # (the worker reports the exact reruns here)
     else:
         assert by_name[("big_clean", "index")] == 0

@@ -25,7 +25,7 @@ def test_nccl_sharded_matches_oracle(tmp_path):
         assert x["ok"], x
 
 
-@pytest.mark.parametrize("variant", ["clean", "dup", "bad", "clean_exchange"])
+@pytest.mark.parametrize("variant", ["clean", "dup", "bad", "clean_exchange", "overflow"])
 def test_pipelined_routing_one_gpu(variant, monkeypatch):
     """The chunk-by-chunk routing of the sharded index (chunk hook beside the clean-data pass, fixed-capacity regions, owner-side
     insert on the side stream) with a world of one: same kernels and stream choreography as N ranks, the exchange is a no-op."""
@@ -36,6 +36,10 @@ def test_pipelined_routing_one_gpu(variant, monkeypatch):
     monkeypatch.setenv("FQG_MAX_CHUNK_BYTES", str(24 << 20))  # ~9 chunks: the hook fires beside every pass after the first
     if variant == "clean_exchange":  # the rounds as exchanges of packed send buffers instead of stores into the owner's arena
         monkeypatch.setenv("FQG_P2P", "0")
+        variant = "clean"
+    overflow = variant == "overflow"
+    if overflow:  # regions of 1000 tuples for 65 000 names a round: the owner reports the overflow, the exact path redoes the job
+        monkeypatch.setenv("FQG_TEST_SLOT_CAP", "1000")
         variant = "clean"
     rb = fq.illumina_record_bytes()
     n = 600_000
@@ -51,7 +55,8 @@ def test_pipelined_routing_one_gpu(variant, monkeypatch):
     res = run.run_device(t.data_ptr(), n * rb, name="a.fq")
     want = oracle_run(["a.fq"], bytes(t[:n * rb].cpu().numpy()), None)
     assert tuple(res["transcript"]) == want
-    if variant == "clean":
+    assert run.exact_reruns == (0 if variant == "clean" and not overflow else 1)
+    if variant == "clean" and not overflow:
         assert run.rounds_done >= 5 and run._p2p_ok == (os.environ.get("FQG_P2P", "1") != "0")
         assert res["n_index_entries"] == n and run.ctx.path_counts()["lanes"] >= 8
         # a second job on the same objects (bench loop): the table is cleared, the rounds start over
