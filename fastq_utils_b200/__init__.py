@@ -4,7 +4,7 @@ The product is the C-ABI library `libfastq_gpu.so` (include/fastq_gpu.h); this p
 adds the multi-GPU orchestration (`dist`) that uses torch.distributed for the plumbing.  There is no CPU fallback:
 importing works anywhere, creating a context needs a CUDA device.
 """
-from .api import (FastqInfo, fastq_info, lib, MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED,  # noqa: F401
+from .api import (FastqInfo, fastq_info, reader_tool, lib, MODE_READER, MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED,  # noqa: F401
                   MODE_SORTED_PAIR, KERNEL_CLASSES, synth_illumina, synth_longreads, illumina_record_bytes)
 
-__all__ = ["FastqInfo", "fastq_info", "lib", "synth_illumina", "synth_longreads", "illumina_record_bytes"]
+__all__ = ["FastqInfo", "fastq_info", "reader_tool", "lib", "synth_illumina", "synth_longreads", "illumina_record_bytes"]

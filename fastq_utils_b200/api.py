@@ -9,7 +9,7 @@ _SO = os.path.join(_HERE, "libfastq_gpu.so")
 # so that the multi-rank orchestration can run under gloo on a machine without GPUs.  Never set outside the test-suite.
 _SO = os.environ.get("FQG_SIM_LIBRARY_FOR_TESTS", _SO)
 
-MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED, MODE_SORTED_PAIR = range(5)
+MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED, MODE_SORTED_PAIR, MODE_READER = range(6)
 KERNEL_CLASSES = ["scan", "records", "index", "mate", "pair", "other", "tile", "lanes"]
 FLAG_PAIRED_NAMES, FLAG_EXTERNAL_INDEX, FLAG_TWO_PASS = 1, 2, 4
 
@@ -83,6 +83,7 @@ def lib():
         L.fqg_transcript_free.argtypes = [ctypes.POINTER(Transcript)]
         L.fqg_transcript_free.restype = None
         L.fqg_fastq_info_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, vp, sz, ci, sz, ctypes.POINTER(Transcript)]
+        L.fqg_reader_tool_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, ci, sz, ctypes.POINTER(Transcript)]
         L.fqg_kernel_stats.argtypes = [vp, ci, ctypes.POINTER(KernelStat)]
         L.fqg_kernel_stats_reset.argtypes = [vp]
         L.fqg_prescan_device.argtypes = [vp, ci, vp, sz, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64)]
@@ -141,6 +142,19 @@ def fastq_info(argv, data1=None, data2=None, chunk=0, device=0):
                                   data2, len(data2) if data2 is not None else un, device, chunk, ctypes.byref(tr))
     if st != 0:
         raise RuntimeError(f"fqg_fastq_info_mem failed with status {st}")
+    return _take(tr)
+
+
+def reader_tool(tool, argv, data1=None, chunk=0, device=0):
+    """`fastq_num_reads argv...` / `fastq_not_empty argv...` (src/fastq_num_reads.c, src/fastq_not_empty.c) on an in-memory inflated
+    stream → (exit status, stdout, stderr).  data1=None = the file could not be opened."""
+    full = [tool.encode("latin-1")] + [a.encode("latin-1") if isinstance(a, str) else a for a in argv]
+    arr = (ctypes.c_char_p * (len(full) + 1))(*full, None)
+    tr = Transcript()
+    un = ctypes.c_size_t(-1).value
+    st = lib().fqg_reader_tool_mem(len(full), arr, data1, len(data1) if data1 is not None else un, device, chunk, ctypes.byref(tr))
+    if st != 0:
+        raise RuntimeError(f"fqg_reader_tool_mem failed with status {st}")
     return _take(tr)
 
 

@@ -31,7 +31,7 @@ static int classify(fqg_ctx* c, const std::exception& ex) {
 
 extern "C" int fqg_create(const fqg_config* cfg, fqg_ctx** out) {
   if (!cfg || !out) return FQG_ERR_USAGE;
-  if (cfg->mode < FQG_MODE_SINGLE || cfg->mode > FQG_MODE_SORTED_PAIR) return FQG_ERR_USAGE;
+  if (cfg->mode < FQG_MODE_SINGLE || cfg->mode > FQG_MODE_READER) return FQG_ERR_USAGE;
   *out = nullptr;
   fqg_ctx* c = new (std::nothrow) fqg_ctx();
   if (!c) return FQG_ERR_OOM;

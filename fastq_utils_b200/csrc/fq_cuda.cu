@@ -284,7 +284,7 @@ fq_records_kernel(const RecParams P) {
         P.names[k] = nm;
       }
       if (P.cx.loop == FQ_LOOP_INDEX && named) { my_names++; my_mem += o.mem_len; }
-      if (!o.flags && o.vrank == FQ_V_OK) { /* statistics are only reported when every record is clean */
+      if (!o.flags && (o.vrank == FQ_V_OK || P.cx.loop == FQ_LOOP_READER)) { /* statistics are only reported when every record is clean */
         my_rds += P.cx.weight;
         mn_rl = min(mn_rl, o.read_len); mx_rl = max(mx_rl, o.read_len);
         if (o.qmin <= o.qmax) { mn_q = min(mn_q, o.qmin); mx_q = max(mx_q, o.qmax); }
@@ -540,7 +540,7 @@ fq_tile_kernel(const TileParams P) {
                   P.names[g_local] = nm;
                 }
                 if (P.cx.loop == FQ_LOOP_INDEX && named) { my_names++; my_mem += o.mem_len; }
-                if (!o.flags && o.vrank == FQ_V_OK) {
+                if (!o.flags && (o.vrank == FQ_V_OK || P.cx.loop == FQ_LOOP_READER)) {
                   my_rds += P.cx.weight;
                   mn_rl = min(mn_rl, o.read_len); mx_rl = max(mx_rl, o.read_len);
                   if (o.qmin <= o.qmax) { mn_q = min(mn_q, o.qmin); mx_q = max(mx_q, o.qmax); }

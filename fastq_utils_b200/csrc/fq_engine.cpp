@@ -23,6 +23,7 @@ static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 
 static int fmt_of_sniff(int s) { return s == FQ_SNIFF_DEFAULT ? FQ_FMT_DEFAULT : s == FQ_SNIFF_CASAVA ? FQ_FMT_CASAVA : FQ_FMT_INT; }
 
 FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) {
+  if (cfg_.mode == FQG_MODE_READER) { reader_ = true; cfg_.mode = FQG_MODE_SINGLE; } /* same chunks, segments, tails and events; only the per-record verdict differs */
   key_ = (unsigned long long*)dev_->alloc(sizeof(unsigned long long));
   counters_ = (unsigned long long*)dev_->alloc(4 * sizeof(unsigned long long));
   scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
@@ -83,7 +84,7 @@ void FqEngine::reset() {
 
 int FqEngine::loop_of(int file) const {
   switch (cfg_.mode) {
-    case FQG_MODE_SINGLE: return FQ_LOOP_SINGLE;
+    case FQG_MODE_SINGLE: return reader_ ? FQ_LOOP_READER : FQ_LOOP_SINGLE;
     case FQG_MODE_INDEX: return FQ_LOOP_INDEX;
     case FQG_MODE_INDEX_PAIR: return file == 0 ? FQ_LOOP_INDEX : FQ_LOOP_MATE;
     case FQG_MODE_INTERLEAVED: return FQ_LOOP_INTERLEAVED;
@@ -251,7 +252,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   uint32_t cap = B.n / 32 + 4096;
   B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
   uint32_t ncap = cap / 4 + 1;
-  FqName* names = loop != FQ_LOOP_SINGLE ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
+  FqName* names = (loop != FQ_LOOP_SINGLE && loop != FQ_LOOP_READER) ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
   FqTileArgs a; memset(&a, 0, sizeof a);
   a.data = B.data; a.n = B.n; a.virtual_end = last ? 1 : 0; a.line_end = B.line_end; a.cap = cap; a.out5 = tile_out_;
   a.j0 = j0; a.max_rec = kNone32; a.g0 = g0_local + F.g_base; a.step_base = step_base(file); a.cx = make_ctx(file);
@@ -497,7 +498,7 @@ void FqEngine::sync_dir(int file) {
 void FqEngine::add_segment(int file, FqSegment s) {
   FqFile& F = f_[file];
   s.g0 = F.nrec; F.nrec += s.nrec;
-  if (loop_of(file) != FQ_LOOP_SINGLE) s.names = (FqName*)dev_->alloc((size_t)s.nrec * sizeof(FqName));
+  if (loop_of(file) != FQ_LOOP_SINGLE && loop_of(file) != FQ_LOOP_READER) s.names = (FqName*)dev_->alloc((size_t)s.nrec * sizeof(FqName));
   F.segs.push_back(s);
   FqDirEntry de; de.g0 = s.g0; de.names = s.names; de.data = F.bufs[s.buf].data;
   F.dir_host.push_back(de);
@@ -839,7 +840,7 @@ void FqEngine::finish(fqg_report* rep) {
       k = 0;
     }
     switch (cfg_.mode) {
-      case FQG_MODE_SINGLE: sniffed(0, FQ_KEY(0, FQ_R_V0 + FQ_V_PLUS)); break;
+      case FQG_MODE_SINGLE: if (!reader_) sniffed(0, FQ_KEY(0, FQ_R_V0 + FQ_V_PLUS)); break; /* the reader tools never sniff */
       case FQG_MODE_INDEX: sniffed(0, FQ_KEY(0, FQ_R_WRONGHDR)); break;
       case FQG_MODE_INDEX_PAIR: sniffed(0, FQ_KEY(0, FQ_R_WRONGHDR)); sniffed(1, FQ_KEY(total0() + 1, FQ_R_WRONGHDR)); break;
       case FQG_MODE_INTERLEAVED: sniffed(0, FQ_KEY(0, FQ_RI_WRONGHDR1)); break;

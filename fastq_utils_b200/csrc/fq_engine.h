@@ -99,6 +99,7 @@ class FqEngine {
 
  private:
   fqg_config cfg_;
+  bool reader_ = false;      /* FQG_MODE_READER: the single-file loop without validation (everything else as FQG_MODE_SINGLE) */
   FqDevice* dev_;
   FqFile f_[2];
   unsigned long long* key_ = nullptr;       /* device: global minimum event key */

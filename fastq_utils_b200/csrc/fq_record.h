@@ -317,7 +317,7 @@ FQ_HD void fq_check_record_careful(const uint8_t* d, const FqLine* L, const FqRe
 /* does a record of this loop reach the name step (index insert / mate claim / pair compare)? */
 FQ_HD bool fq_record_has_name(int loop, const FqRecOut& o) {
   if (o.flags & (FQ_RF_STOP | FQ_RF_TRUNC | FQ_RF_NOTAT)) return false;
-  return loop != FQ_LOOP_SINGLE;
+  return loop != FQ_LOOP_SINGLE && loop != FQ_LOOP_READER;
 }
 
 
@@ -630,6 +630,10 @@ FQ_HD uint64_t fq_record_key(int loop, uint64_t g, uint64_t step_base, const FqR
       if (o.flags & FQ_RF_STOP) return FQ_KEY(g, FQ_RS_STOP2);
       if (o.flags & FQ_RF_TRUNC) return FQ_KEY(g, FQ_RS_TRUNC2);
       if (o.vrank != FQ_V_OK) return FQ_KEY(g, FQ_RS_V2 + o.vrank);
+      return FQ_KEY_NONE;
+    case FQ_LOOP_READER: /* the reader alone: a NUL-led header ends the file, a partial record is 'file truncated'; nothing is validated */
+      if (o.flags & FQ_RF_STOP) return FQ_KEY(step_base + g, FQ_R_STOP);
+      if (o.flags & FQ_RF_TRUNC) return FQ_KEY(step_base + g, FQ_R_TRUNC);
       return FQ_KEY_NONE;
     case FQ_LOOP_SINGLE:
       if (o.flags & FQ_RF_STOP) return FQ_KEY(step_base + g, FQ_R_STOP);

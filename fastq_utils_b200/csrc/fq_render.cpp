@@ -334,3 +334,47 @@ extern "C" int fqg_fastq_info_mem(int argc, const char** argv_in, const void* f1
   to_transcript(t, tr);
   return 0;
 }
+
+/* main() of the reader-style tools on an inflated stream: src/fastq_num_reads.c:32-50, src/fastq_not_empty.c:32-47.  Both are
+ * the bare fastq_read_next_entry loop (src/fastq.c:237-261): records are delimited, a NUL-led header line ends the file quietly,
+ * a record with fewer than four lines is "file truncated" (exit 1); nothing is validated. */
+extern "C" int fqg_reader_tool_mem(int argc, const char** argv, const void* f1, size_t n1, int device, size_t chunk_bytes, fqg_transcript* tr) {
+  if (argc < 1 || !argv || !argv[0] || !tr) return FQG_ERR_USAGE;
+  const size_t UNOPENABLE = (size_t)-1;
+  Text t;
+  const char* tool = strrchr(argv[0], '/'); tool = tool ? tool + 1 : argv[0];
+  const bool num_reads = !strcmp(tool, "fastq_num_reads"), not_empty = !strcmp(tool, "fastq_not_empty");
+  if (!num_reads && !not_empty) return FQG_ERR_USAGE;
+  if (num_reads) t.e("fastq_utils %s\n", "0.25.3"); /* fastq_print_version, src/fastq_num_reads.c:34; fastq_not_empty prints none */
+  if (argc != 2) {
+    if (num_reads) { t.e("Usage: fastq_num_reads fastq_file\n"); t.rc = 1; }
+    else { t.e("Usage: fastq_not_empty fastq_file\nExit status of 0 if it is not empty, 0 otherwise. The fastq file may be compressed with gzip."); t.rc = 1; }
+    to_transcript(t, tr); return 0;
+  }
+  if (n1 == UNOPENABLE) { ERR_BEGIN(t); t.e("Unable to open %s", argv[1]); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; } /* src/fastq.c:651-655 */
+  if (!f1 && n1) return FQG_ERR_USAGE;
+  fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER;
+  fqg_report rep;
+  try {
+    FqDevice* dev = fq_default_device(device);
+    {
+      FqEngine eng(cfg, dev);
+      feed_all(eng, 0, f1, n1, chunk_bytes);
+      eng.finish(&rep);
+    }
+    delete dev;
+  } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
+  } catch (const std::exception& ex) {
+    fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
+    return strstr(ex.what(), "CUDA") ? (strstr(ex.what(), "no CUDA") ? FQG_ERR_NO_DEVICE : FQG_ERR_CUDA) : FQG_ERR_INTERNAL;
+  }
+  const uint64_t n = rep.file[0].n_records;
+  if (not_empty) { /* only the first entry is ever read: an error further down does not exist for this tool */
+    if (rep.reads_before_error[0] >= 1) t.rc = 0;
+    else if (rep.error.code == FQG_E_TRUNC) { error_text(t, rep.error, argv[1], argv[1]); t.rc = 1; }
+    else t.rc = 1;
+  } else if (rep.error.code == FQG_E_TRUNC) { error_text(t, rep.error, argv[1], argv[1]); t.rc = 1; }
+  else { t.o("%lu\n", (unsigned long)n); t.rc = 0; }
+  to_transcript(t, tr);
+  return 0;
+}

@@ -59,7 +59,8 @@ enum {
   FQ_LOOP_MATE = 2,        /* main()'s mate loop                    (default, file 2)       */
   FQ_LOOP_INTERLEAVED = 3, /* validate_interleaved                  (pe)                    */
   FQ_LOOP_SORTED1 = 4,     /* validate_paired_sorted_fastq_file, file 1 (-r -s)             */
-  FQ_LOOP_SORTED2 = 5      /* validate_paired_sorted_fastq_file, file 2                     */
+  FQ_LOOP_SORTED2 = 5,     /* validate_paired_sorted_fastq_file, file 2                     */
+  FQ_LOOP_READER = 6       /* fastq_read_next_entry loops without validation (src/fastq_num_reads.c:43-45, fastq_not_empty.c:41-43) */
 };
 
 /* One raw gz-line inside a chunk: bytes [off, off+len), '\n' included when the line has one. */

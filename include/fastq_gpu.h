@@ -14,7 +14,8 @@
  *        FQG_MODE_SORTED_PAIR  validate_paired_sorted_fastq_file    src/fastq_info.c:108-152   (-r -s file1 file2)
  *   fqg_render                  replaces   the fprintf/PRINT_ERROR/exit sequence of src/fastq_info.c:190-396
  *   fqg_fastq_info_mem          = main() on already-inflated streams (what the CLI and the parity tests call)
- *   fqg_index_records           exposes the record index for reader-style tools (src/fastq_num_reads.c, fastq_truncate.c)
+ *   fqg_index_records           exposes the record index for reader-style tools (src/fastq_truncate.c)
+ *   fqg_reader_tool_mem         = main() of fastq_num_reads / fastq_not_empty on an inflated stream (FQG_MODE_READER)
  *
  * Nothing here prints or exits.  All functions return 0 on success or a negative FQG_ERR_* (the caller maps
  * these to the reference's SYS_INT_ERROR_EXIT_STATUS = 2, src/fastq.h:79).  A context is used by one host
@@ -31,7 +32,8 @@ extern "C" {
 
 #define FQG_VERSION "0.25.3-b200.1"
 
-enum { FQG_MODE_SINGLE = 0, FQG_MODE_INDEX = 1, FQG_MODE_INDEX_PAIR = 2, FQG_MODE_INTERLEAVED = 3, FQG_MODE_SORTED_PAIR = 4 };
+enum { FQG_MODE_SINGLE = 0, FQG_MODE_INDEX = 1, FQG_MODE_INDEX_PAIR = 2, FQG_MODE_INTERLEAVED = 3, FQG_MODE_SORTED_PAIR = 4,
+       FQG_MODE_READER = 5 /* fastq_read_next_entry until the end of one file, nothing validated: src/fastq_num_reads.c:43-45 */ };
 enum { FQG_ERR_NO_DEVICE = -1, FQG_ERR_CUDA = -2, FQG_ERR_OOM = -3, FQG_ERR_USAGE = -4, FQG_ERR_INTERNAL = -5 };
 
 typedef struct fqg_ctx fqg_ctx;
@@ -132,6 +134,12 @@ void fqg_transcript_free(fqg_transcript* t);
  * be opened" (src/fastq.c:651-655).  chunk_bytes > 0 feeds the streams in pieces of that size. */
 int fqg_fastq_info_mem(int argc, const char** argv, const void* f1, size_t n1, const void* f2, size_t n2,
                        int device, size_t chunk_bytes, fqg_transcript* t);
+
+/* The reader-style tools on an already-inflated stream: argv[0] names the tool,
+ *   "fastq_num_reads"  src/fastq_num_reads.c:32-50   prints the number of entries fastq_read_next_entry delivers
+ *   "fastq_not_empty"  src/fastq_not_empty.c:32-47   exit status 0 when the file holds at least one entry, 1 otherwise
+ * with the reference's usage text, "file truncated" / "Unable to open" errors and exit statuses.  n = (size_t)-1: could not be opened. */
+int fqg_reader_tool_mem(int argc, const char** argv, const void* f1, size_t n1, int device, size_t chunk_bytes, fqg_transcript* t);
 
 /* ---- multi-GPU building blocks (fastq_utils_b200/dist.py drives them with torch.distributed) ----
  * A rank holds a contiguous byte range of a file.  fqg_prescan_device builds the line index of the range (kept for the

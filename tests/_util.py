@@ -134,6 +134,9 @@ def fqg_lib(kind="gpu"):
                                            ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_size_t,
                                            ctypes.POINTER(_Transcript)]
         lib.fqg_transcript_free.argtypes = [ctypes.POINTER(_Transcript)]
+        lib.fqg_reader_tool_mem.restype = ctypes.c_int
+        lib.fqg_reader_tool_mem.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.c_char_p, ctypes.c_size_t,
+                                            ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(_Transcript)]
         _fqg[kind] = lib
     return _fqg[kind]
 
@@ -165,3 +168,42 @@ def fqg_run_files(argv, cwd=GOLDEN, chunk=0, kind="gpu"):
     while len(datas) < 2:
         datas.append(None)
     return fqg_run(argv, datas[0], datas[1], chunk=chunk, kind=kind)
+
+
+def fqg_reader_tool(tool, argv, data1=None, chunk=0, kind="gpu"):
+    """fastq_num_reads / fastq_not_empty through the C ABI on an in-memory stream → (rc, stdout, stderr) as latin-1 text."""
+    lib = fqg_lib(kind)
+    full = [tool.encode("latin-1")] + [a.encode("latin-1") for a in argv]
+    arr = (ctypes.c_char_p * (len(full) + 1))(*full, None)
+    tr = _Transcript()
+    st = lib.fqg_reader_tool_mem(len(full), arr, data1, len(data1) if data1 is not None else ctypes.c_size_t(-1).value, 0, chunk, ctypes.byref(tr))
+    if st != 0:
+        raise RuntimeError(f"fqg_reader_tool_mem failed with status {st}")
+    out = ctypes.string_at(tr.out, tr.out_len).decode("latin-1")
+    err = ctypes.string_at(tr.err, tr.err_len).decode("latin-1")
+    rc = tr.rc
+    lib.fqg_transcript_free(ctypes.byref(tr))
+    return rc, out, err
+
+
+def fqg_reader_tool_files(tool, argv, cwd=GOLDEN, chunk=0, kind="gpu"):
+    data = None
+    if len(argv) >= 1:
+        path = os.path.join(cwd, argv[0])
+        data = read_stream(path) if os.path.isfile(path) else None
+    return fqg_reader_tool(tool, argv, data, chunk=chunk, kind=kind)
+
+
+def reader_golden():
+    with open(os.path.join(GOLDEN, "reader_transcripts.json")) as fh:
+        return json.load(fh)
+
+
+def ref_reader_tool(tool, data, name="a.fq"):
+    """The unmodified reference tool (oracle/_ref/<tool>) on a temporary plain-text file → (rc, stdout, stderr)."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, name), "wb") as fh:
+            fh.write(data)
+        p = subprocess.run([os.path.join(ROOT, "oracle", "_ref", tool), name], cwd=d, capture_output=True)
+    return p.returncode, p.stdout.decode("latin-1"), p.stderr.decode("latin-1")

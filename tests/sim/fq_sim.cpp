@@ -93,7 +93,7 @@ class FqSimDevice : public FqDevice {
       }
       if (a.cx.loop == FQ_LOOP_INDEX && named) { a.stats->n_names++; a.stats->mem_sum += o.mem_len; }
       /* statistics are only ever reported when every record was clean, so only clean records are counted */
-      if (o.flags || o.vrank != FQ_V_OK) continue;
+      if (o.flags || (o.vrank != FQ_V_OK && a.cx.loop != FQ_LOOP_READER)) continue; /* the reader loop counts what it read */
       uint32_t w = a.cx.weight;
       a.stats->num_rds += w;
       if (o.read_len < a.stats_range->min_rl) a.stats_range->min_rl = o.read_len;
