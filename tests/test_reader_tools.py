@@ -71,3 +71,43 @@ def test_gpu_reader_tools_count_large_streams():
     assert fqg_reader_tool("fastq_not_empty", ["a.fq"], bytes(data)) == (0, "", "")
     cut = bytes(data[:250_000 * rb + 100])   # the last record is cut inside its sequence line
     assert fqg_reader_tool("fastq_num_reads", ["a.fq"], cut) == (1, "", f"fastq_utils 0.25.3\n\nERROR: Error in file a.fq: line {4 * 250_000}: file truncated\n")
+
+
+def test_python_binding_of_the_reader_tools(tmp_path):
+    """fastq_utils_b200.reader_tool and FastqInfo(MODE_READER) (api.py) over the stand-in device, in a process of its own (the
+    library is chosen at import time)."""
+    import subprocess
+    import sys
+    code = (
+        "import fastq_utils_b200 as fq\n"
+        "d = b''.join(b'@r%d\\nACGT\\n+\\nIIII\\n' % i for i in range(7)) + b'@x\\nAC*T\\n+\\nII\\n'\n"  # the last record would not validate
+        "assert fq.reader_tool('fastq_num_reads', ['a.fq'], d) == (0, '8\\n', 'fastq_utils 0.25.3\\n')\n"
+        "assert fq.reader_tool('fastq_not_empty', ['a.fq'], d) == (0, '', '')\n"
+        "assert fq.reader_tool('fastq_not_empty', ['a.fq'], b'') == (1, '', '')\n"
+        "assert fq.reader_tool('fastq_num_reads', ['a.fq'], None)[0] == 1\n"
+        "h = fq.FastqInfo(fq.MODE_READER); h.feed(0, d[:40], last=False); h.feed(0, d[40:], last=True); r = h.finish()\n"
+        "assert r.error.code == 0 and r.file[0].n_records == 8, (r.error.code, r.file[0].n_records)\n"
+        "n, starts = h.index_records(d, cap=16)\n"  # fqg_index_records: where the four-line records start
+        "want = [i for i in range(len(d)) if (i == 0 or d[i - 1] == 10) and d[:i].count(b'\\n') % 4 == 0]\n"
+        "assert n == 8 and starts == want[:8], (n, starts, want)\n"
+        "assert h.index_records(d[:-1], cap=4) == (8, want[:4]) and h.index_records(d[:-3], cap=0) == (7, [])\n"  # a last line without LF counts
+        "print('ok')\n")
+    env = dict(os.environ, FQG_SIM_LIBRARY_FOR_TESTS=os.path.join(ROOT, "tests", "sim", "libfastq_sim.so"), PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_gpu_index_records():
+    """fqg_index_records on the real scan kernel: record starts of a 50 000-record stream (what fastq_truncate would cut at)."""
+    import fastq_utils_b200 as fq
+    recs = [b"@r%d\n%s\n+\n%s\n" % (i, b"ACGTN" * (1 + i % 37), b"I" * (5 * (1 + i % 37))) for i in range(50_000)]
+    data = b"".join(recs)
+    want, off = [], 0
+    for r in recs:
+        want.append(off)
+        off += len(r)
+    h = fq.FastqInfo(fq.MODE_SINGLE)
+    assert h.index_records(data, cap=len(recs)) == (len(recs), want)
+    assert h.index_records(data[:want[40_000] + 5], cap=3) == (40_000, want[:3])  # 160 001 lines: the cut record is not complete
+    h.close()
