@@ -48,10 +48,12 @@ class ShardedFastqInfo:
         # find room on SMs filled by a running clean-data pass (the per-round size exchange of the pipelined routing)
         self._cpu_group = None
         if self.world > 1 and dist.get_backend() != "gloo":
-            self._cpu_group = dist.new_group(backend="gloo")
+            import datetime
+            self._cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=300))  # a rank that died must not hang the others for half an hour
         self.pipeline = os.environ.get("FQG_NO_PIPELINE", "0") in ("", "0")
-        # pipelined rounds over peer memory (CUDA IPC) instead of all-to-all exchanges: GPUs only; FQG_P2P=0 turns it off
-        self.p2p = self.tdev.type == "cuda" and os.environ.get("FQG_P2P", "1") not in ("", "0")
+        # pipelined rounds over peer memory (CUDA IPC) instead of all-to-all exchanges: the default on GPUs, FQG_P2P=0 turns it off;
+        # FQG_P2P=1 asks for it on CPU tensors too (the gloo tests: the stand-in device maps shared memory between the ranks)
+        self.p2p = os.environ.get("FQG_P2P", "1" if self.tdev.type == "cuda" else "0") not in ("", "0")
         # the copy engines move the packed regions; FQG_P2P_STORES=1: the pack kernel stores into the owners' arenas itself (A/B)
         self.p2p_stores = os.environ.get("FQG_P2P_STORES", "0") not in ("", "0")
         self._pending_insert = None

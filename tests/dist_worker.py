@@ -20,7 +20,7 @@ def main():
     cases = json.load(open(sys.argv[1]))
     dist.init_process_group("gloo")
     r, W = dist.get_rank(), dist.get_world_size()
-    out, rounds = [], []
+    out, rounds, peer = [], [], []
     for c in cases:
         data = bytes.fromhex(c["hex"])
         cuts = [int(len(data) * x) for x in c["cuts"]][:W - 1]
@@ -45,14 +45,16 @@ def main():
             res = run.run_device(ctypes.addressof(buf), hi - lo, name="a.fq", **kw)
             tr = res.get("transcript")
             rounds.append(run.rounds_done if not os.environ.get("FQG_TEST_SLOT_CAP") else run.exact_reruns)
+            peer.append(bool(run._p2p_ok))
         except (NotImplementedError, RuntimeError) as ex:
             tr = ["EXC", type(ex).__name__, str(ex)]
             rounds.append(-1)
+            peer.append(False)
         if r == 0:
             out.append(list(tr))
         dist.barrier()
     if r == 0:
-        json.dump({"transcripts": out, "rounds": rounds}, open(sys.argv[2], "w"))
+        json.dump({"transcripts": out, "rounds": rounds, "peer": peer}, open(sys.argv[2], "w"))
     dist.destroy_process_group()
 
 

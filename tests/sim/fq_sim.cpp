@@ -8,6 +8,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <string>
+#include <map>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include "../../fastq_utils_b200/csrc/fq_device.h"
 #include "../../fastq_utils_b200/csrc/fq_record.h"
 
@@ -276,6 +281,35 @@ class FqSimDevice : public FqDevice {
       }
     }
   }
+  /* "peer memory" of the stand-in: a POSIX shared-memory segment that the other ranks of a gloo test map by name (the handle),
+   * so that the peer-memory routing rounds of dist.py run on CPU exactly as they do over CUDA IPC */
+  void* ipc_alloc(size_t n, uint8_t handle[64]) override {
+    static int counter = 0;
+    char name[64]; snprintf(name, sizeof name, "/fqgsim_%d_%d", (int)getpid(), counter++);
+    int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) throw std::runtime_error("stand-in ipc_alloc: shm_open failed");
+    if (ftruncate(fd, (off_t)(n ? n : 1)) != 0) { close(fd); shm_unlink(name); throw std::runtime_error("stand-in ipc_alloc: ftruncate failed"); }
+    void* p = mmap(nullptr, n ? n : 1, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { shm_unlink(name); throw std::runtime_error("stand-in ipc_alloc: mmap failed"); }
+    memset(handle, 0, 64); memcpy(handle, name, strlen(name));
+    shm_[p] = Seg{std::string(name), n ? n : 1, true};
+    return p;
+  }
+  void* ipc_open(const uint8_t handle[64]) override {
+    char name[65]; memcpy(name, handle, 64); name[64] = 0;
+    int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) throw std::runtime_error("stand-in ipc_open: shm_open failed");
+    off_t n = lseek(fd, 0, SEEK_END);
+    void* p = mmap(nullptr, (size_t)n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) throw std::runtime_error("stand-in ipc_open: mmap failed");
+    shm_[p] = Seg{std::string(name), (size_t)n, false};
+    return p;
+  }
+  void ipc_close(void* p) override { auto it = shm_.find(p); if (it != shm_.end()) { munmap(p, it->second.n); shm_.erase(it); } }
+  void ipc_free(void* p) override { auto it = shm_.find(p); if (it != shm_.end()) { munmap(p, it->second.n); if (it->second.owner) shm_unlink(it->second.name.c_str()); shm_.erase(it); } }
+  ~FqSimDevice() override { for (auto& kv : shm_) { munmap(kv.first, kv.second.n); if (kv.second.owner) shm_unlink(kv.second.name.c_str()); } }
   void side_copy(void* dst, const void* src, size_t n) override { memmove(dst, src, n); }
   void side_sync() override {}
   void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {
@@ -289,6 +323,8 @@ class FqSimDevice : public FqDevice {
 
  private:
   unsigned long long n_launch_ = 0;
+  struct Seg { std::string name; size_t n; bool owner; };
+  std::map<void*, Seg> shm_;
 };
 
 }  // namespace

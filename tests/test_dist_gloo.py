@@ -62,10 +62,16 @@ def _cases():
 # variants of the name routing: pipelined (chunk by chunk through the chunk hook; the default), the same with tiny chunks so that
 # every range takes several routing rounds, and the one-exchange path (FQG_NO_PIPELINE=1)
 VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "one_exchange": {"FQG_NO_PIPELINE": "1"},
-            "overflow": {"FQG_TEST_SLOT_CAP": "7", "FQG_MAX_CHUNK_BYTES": "16384"}}  # regions of 7 tuples: every big job overflows and is redone exactly
+            "overflow": {"FQG_TEST_SLOT_CAP": "7", "FQG_MAX_CHUNK_BYTES": "16384"},  # regions of 7 tuples: every big job overflows and is redone exactly
+            # the rounds over peer memory as on the GPUs (the stand-in device maps POSIX shared memory between the ranks): copies of
+            # packed regions, stores straight into the owners' arenas, and an overflowing arena
+            "peer_copies": {"FQG_P2P": "1", "FQG_MAX_CHUNK_BYTES": "8192"},
+            "peer_stores": {"FQG_P2P": "1", "FQG_P2P_STORES": "1", "FQG_MAX_CHUNK_BYTES": "8192"},
+            "peer_overflow": {"FQG_P2P": "1", "FQG_TEST_SLOT_CAP": "7", "FQG_MAX_CHUNK_BYTES": "16384"}}
 
 
-@pytest.mark.parametrize("world,variant", [(2, "pipelined"), (3, "pipelined"), (2, "small_chunks"), (3, "small_chunks"), (2, "one_exchange"), (2, "overflow")])
+@pytest.mark.parametrize("world,variant", [(2, "pipelined"), (2, "small_chunks"), (3, "small_chunks"), (2, "one_exchange"), (2, "overflow"),
+                                           (3, "peer_copies"), (2, "peer_stores"), (2, "peer_overflow")])
 def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
     cases = _cases()
@@ -84,11 +90,13 @@ def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
         assert tuple(g) == want, (c["file"], c["mode"], c["cuts"], g)
     # the routing under test was really taken: the clean big file goes through the chunk hook, in several rounds when chunks are small
     by_name = {(c["file"], c["mode"]): r for c, r in zip(cases, rounds)}
+    peer = {(c["file"], c["mode"]): p for c, p in zip(cases, res["peer"])}
+    assert peer[("big_clean", "index")] == variant.startswith("peer")  # the rounds went through mapped peer memory / through exchanges
     if variant == "pipelined":
         assert by_name[("big_clean", "index")] >= 1
-    elif variant == "small_chunks":
+    elif variant in ("small_chunks", "peer_copies", "peer_stores"):
         assert by_name[("big_clean", "index")] >= 3
-    elif variant == "overflow":
+    elif variant in ("overflow", "peer_overflow"):
         assert by_name[("big_clean", "index")] == 1  # (the worker reports the exact reruns here)
     else:
         assert by_name[("big_clean", "index")] == 0
