@@ -99,6 +99,7 @@ def lib():
         L.fqg_set_sniff.argtypes = [vp, ci, ctypes.c_int32, ctypes.c_int32]
         L.fqg_set_file_total.argtypes = [vp, ci, u64]
         L.fqg_set_line_hint.argtypes = [vp, ci, ctypes.c_uint32]
+        L.fqg_records_fed.argtypes = [vp, ci, ctypes.POINTER(u64)]
         L.fqg_set_chunk_hook.argtypes = [vp, CHUNK_HOOK, vp]
         L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
         L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64]
@@ -325,6 +326,11 @@ class FastqInfo:
 
     def set_sniff(self, file, fmt, color):
         _check(self._ctx, lib().fqg_set_sniff(self._ctx, file, fmt, color), "fqg_set_sniff")
+
+    def records_fed(self, file):
+        n = ctypes.c_uint64()
+        _check(self._ctx, lib().fqg_records_fed(self._ctx, file, ctypes.byref(n)), "fqg_records_fed")
+        return int(n.value)
 
     def set_line_hint(self, file, seq_line_len):
         _check(self._ctx, lib().fqg_set_line_hint(self._ctx, file, seq_line_len), "fqg_set_line_hint")

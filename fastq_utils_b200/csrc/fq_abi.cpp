@@ -195,3 +195,7 @@ extern "C" int fqg_set_line_hint(fqg_ctx* c, int file, uint32_t len) {
   if (!c || file < 0 || file > 1) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->eng->set_line_hint(file, len))
 }
+extern "C" int fqg_records_fed(fqg_ctx* c, int file, uint64_t* n) {
+  if (!c || file < 0 || file > 1 || !n) return FQG_ERR_USAGE;
+  FQG_GUARD(c, *n = c->eng->records_fed(file))
+}

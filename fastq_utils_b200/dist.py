@@ -15,7 +15,8 @@ Each rank holds a contiguous byte range of every input file.
      report is rendered with `fqg_render`, so the text and exit status equal the reference's.
 
 Supported: MODE_SINGLE (-r), MODE_INDEX (default, one file), MODE_INDEX_PAIR (default, two files).  A clean early end of
-file caused by a NUL-led header line (src/fastq.c:248) is reported as unsupported here (the single-GPU path handles it).
+file caused by a NUL-led header line (src/fastq.c:248) sends a one-file job to rank 0 as a whole (its engine knows the rule); with two
+files it is refused on every rank (the single-GPU path handles it).
 """
 import ctypes
 import os
@@ -82,7 +83,7 @@ class ShardedFastqInfo:
             dist.all_to_all_single(recv[:sum(out_splits)], send[:sum(in_splits)], output_split_sizes=out_splits, input_split_sizes=in_splits)
         return recv
 
-    def _feed_file(self, f, ptr, nbytes):
+    def _feed_file(self, f, ptr, nbytes, gather0=False):
         """Steps 1-2 for one file: line phase, head exchange, sniff, feed.  Returns (records expected on this rank or None
         when the file was gathered on rank 0, records of the file over all ranks)."""
         W, r, ctx = self.world, self.rank, self.ctx
@@ -109,7 +110,9 @@ class ShardedFastqInfo:
             cut[i] = info[i][2][skip[i] - 1] if skip[i] > 0 else 0
         total_lines = G[W] + info[W - 1][4]
         total_records = total_lines // 4
-        if degenerate or info[0][3] == 0:
+        if degenerate or info[0][3] == 0 or gather0:
+            if sum(info[i][3] for i in range(W)) > (64 << 30):  # (every rank sees the same sizes: the refusal is collective)
+                raise NotImplementedError("a sharded run that must be redone on one GPU, with more than 64 GiB of input")
             # tiny input: everything goes to rank 0, the other ranks hold an empty stream (the collectives below still run)
             sizes = [info[i][3] for i in range(W)]
             if r == 0:
@@ -429,7 +432,7 @@ class ShardedFastqInfo:
         return recv_meta, recv_blob, ms, bs
 
     # ------------------------------------------------------------------ one job
-    def run_device(self, ptr, nbytes, name="-", ptr2=None, nbytes2=0, name2=None, empty_ok=False, no_enc_ok=False, _exact=False):
+    def run_device(self, ptr, nbytes, name="-", ptr2=None, nbytes2=0, name2=None, empty_ok=False, no_enc_ok=False, _exact=False, _gather0=False):
         """ptr/nbytes (and ptr2/nbytes2 for MODE_INDEX_PAIR): this rank's byte range of each file in device memory (16-byte
         aligned, 64 readable bytes after it).  Returns the merged report and, on rank 0, the rendered (rc, stdout, stderr)."""
         W, r, ctx = self.world, self.rank, self.ctx
@@ -445,16 +448,19 @@ class ShardedFastqInfo:
         speculative = (not _exact) and (W > 1 or routed) and not pair and self._feed_file_speculative(0, ptr, nbytes, routed=routed)
         if speculative:
             rep = ctx.finish()
+            # a NUL-led header line ended this rank's range early and quietly (src/fastq.c:248): not an error here, but the ranges
+            # behind it do not exist for the reference — the exact path sorts that out
+            cut_short = int(rep.file[0].n_records) < ctx.records_fed(0)
             if routed:
                 # the names went to their owners while the range was validated (tuples only): an equal hash, a region or table that
                 # overflowed, a chunk that was redone by the two-pass kernels after its names had left, or any error decides nothing here
                 inserted, equal, overflow = self.shard.shard_slots_result()
-                mine_bad = rep.error.code != 0 or equal > 0 or overflow or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
+                mine_bad = rep.error.code != 0 or cut_short or equal > 0 or overflow or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
                 bad = any(self._gather(bool(mine_bad)))
                 if self._hook_exc is not None:
                     raise self._hook_exc
             else:
-                bad = any(self._gather(rep.error.code != 0))  # every rank takes the same turn: the steps below are collective
+                bad = any(self._gather(rep.error.code != 0 or cut_short))  # every rank takes the same turn: the steps below are collective
             if not bad and self.shard is not None and not routed:
                 meta, blob, ms, bs = self._route_names(0, with_bytes=False)
                 self.shard.shard_insert(meta.data_ptr(), ms[-1], 0, ms, bs)
@@ -465,7 +471,7 @@ class ShardedFastqInfo:
             local_key, T0, T1 = KEY_NONE, 0, 0
             dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0
         if not speculative:
-            exp0, T0 = self._feed_file(0, ptr, nbytes)
+            exp0, T0 = self._feed_file(0, ptr, nbytes, gather0=_gather0)
             exp1, T1 = None, 0
             if pair:
                 ctx.set_file_total(0, T0)
@@ -474,8 +480,14 @@ class ShardedFastqInfo:
             rep = ctx.finish()
             local_key = rep.error.event_key if rep.error.code != 0 else KEY_NONE
             stopped = (exp0 is not None and rep.file[0].n_records < exp0) or (exp1 is not None and rep.file[1].n_records < exp1)
-            if rep.error.code == 0 and stopped:
-                raise NotImplementedError("NUL-led header line (early clean EOF) in a sharded run")
+            # A NUL-led header line ends a file quietly (src/fastq.c:248): nothing behind it exists for the reference, on this rank
+            # (the engine restricts itself) or on the ranks behind it.  Rare enough for the simplest cure: the ranges are gathered on
+            # rank 0, whose engine knows the rule; the other ranks keep their part in the collectives with empty streams.
+            if any(self._gather(bool(rep.error.code == 0 and stopped))):
+                if pair or _gather0:
+                    raise NotImplementedError("NUL-led header line (early clean EOF) in a sharded run of two files")
+                self.exact_reruns += 1
+                return self.run_device(ptr, nbytes, **dict(again, _gather0=True))
             # -- 3. names to their owners
             dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0
             if self.shard is not None:

@@ -37,6 +37,19 @@ def _cases():
     for nm, rr in (("big_clean", big), ("big_dup", dupb), ("big_bad", badb), ("big_plusnames", plusb)):
         for mode in ("index", "single"):
             cases.append({"file": nm, "mode": mode, "hex": "".join(rr).encode().hex(), "cuts": [0.31, 0.64]})
+    # a NUL-led header line ends the file quietly (src/fastq.c:248): whatever follows — here a broken record, on a later rank — does
+    # not exist for the reference; small (exact path) and large enough for the speculative feed
+    for nm, rr, at in (("nul_stop_small", recs[:300], 120), ("nul_stop_big", big, 1500)):
+        rr = list(rr)
+        rr[at] = "\x00" + rr[at]
+        rr[at + (len(rr) - at) // 2] = rr[at + (len(rr) - at) // 2].replace("ACGTN", "AC*TN", 1)
+        for mode in ("index", "single"):
+            cases.append({"file": nm, "mode": mode, "hex": "".join(rr).encode("latin-1").hex(), "cuts": [0.2, 0.55]})
+    # ... and with nothing wrong behind it: no rank has an error to report, the count must still end at the NUL
+    quiet = list(big)
+    quiet[1500] = "\x00" + quiet[1500]
+    for mode in ("index", "single"):
+        cases.append({"file": "nul_stop_quiet", "mode": mode, "hex": "".join(quiet).encode("latin-1").hex(), "cuts": [0.2, 0.55]})
     # pairs: default two-file mode (index loop + mate loop)
     def pair_case(f1, f2, c1, c2):
         d1, d2 = read_stream(os.path.join(GOLDEN, "inputs", f1)), read_stream(os.path.join(GOLDEN, "inputs", f2))
