@@ -100,6 +100,7 @@ def lib():
         L.fqg_set_file_total.argtypes = [vp, ci, u64]
         L.fqg_set_line_hint.argtypes = [vp, ci, ctypes.c_uint32]
         L.fqg_records_fed.argtypes = [vp, ci, ctypes.POINTER(u64)]
+        L.fqg_set_hash_seed.argtypes = [vp, ctypes.c_uint32]
         L.fqg_set_chunk_hook.argtypes = [vp, CHUNK_HOOK, vp]
         L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
         L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64]
@@ -326,6 +327,9 @@ class FastqInfo:
 
     def set_sniff(self, file, fmt, color):
         _check(self._ctx, lib().fqg_set_sniff(self._ctx, file, fmt, color), "fqg_set_sniff")
+
+    def set_hash_seed(self, seed):
+        _check(self._ctx, lib().fqg_set_hash_seed(self._ctx, seed), "fqg_set_hash_seed")
 
     def records_fed(self, file):
         n = ctypes.c_uint64()

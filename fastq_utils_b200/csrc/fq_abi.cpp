@@ -199,3 +199,7 @@ extern "C" int fqg_records_fed(fqg_ctx* c, int file, uint64_t* n) {
   if (!c || file < 0 || file > 1 || !n) return FQG_ERR_USAGE;
   FQG_GUARD(c, *n = c->eng->records_fed(file))
 }
+extern "C" int fqg_set_hash_seed(fqg_ctx* c, uint32_t seed) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->set_hash_seed(seed))
+}

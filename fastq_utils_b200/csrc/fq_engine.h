@@ -82,6 +82,7 @@ class FqEngine {
   void hist_range(int file, uint64_t lo, uint64_t hi, uint64_t* out);
   void set_file_total(int file, uint64_t total);
   uint64_t records_fed(int file) const { return f_[file].nrec; }
+  void set_hash_seed(uint32_t seed) { if (f_[0].fed || f_[1].fed) throw std::runtime_error("fqg_set_hash_seed after the first feed"); seed_ = seed; }
   void set_sniff(int file, int fmt, int color);
   void set_line_hint(int file, uint32_t len) { if (len && !f_[file].first_seq_len) f_[file].first_seq_len = len; }
   void sniff_device(int file, const void* dptr, size_t n, uint32_t skip, int32_t* fmt, int32_t* color);

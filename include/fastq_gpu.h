@@ -178,6 +178,10 @@ int fqg_set_sniff(fqg_ctx* ctx, int file, int32_t sniff_format, int32_t color_sp
 /* raw length of a typical sequence line of the file (a rank that does not hold the file's first record cannot see it): picks the
  * mode of the clean-data pass, one thread per line for short lines; 0 = unknown.  A wrong hint costs time, never correctness. */
 int fqg_set_line_hint(fqg_ctx* ctx, int file, uint32_t seq_line_len);
+/* seed of the read-name hash for the job that starts now (after fqg_reset, before the first feed; fqg_reset goes back to 0).  The
+ * hash is unobservable behind the exact compare; a sharded run whose owners met two different names with one 64-bit hash repeats
+ * the job with the next seed, as the one-GPU engine does by itself */
+int fqg_set_hash_seed(fqg_ctx* ctx, uint32_t seed);
 /* records delimited in what was fed so far, whether or not the loop read them all: fqg_finish reports fewer (n_records) when a
  * NUL-led header line ended the file early (src/fastq.c:248) — a sharded run must then forget the ranges behind that rank's */
 int fqg_records_fed(fqg_ctx* ctx, int file, uint64_t* n_records);

@@ -80,11 +80,14 @@ VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "o
             # packed regions, stores straight into the owners' arenas, and an overflowing arena
             "peer_copies": {"FQG_P2P": "1", "FQG_MAX_CHUNK_BYTES": "8192"},
             "peer_stores": {"FQG_P2P": "1", "FQG_P2P_STORES": "1", "FQG_MAX_CHUNK_BYTES": "8192"},
-            "peer_overflow": {"FQG_P2P": "1", "FQG_TEST_SLOT_CAP": "7", "FQG_MAX_CHUNK_BYTES": "16384"}}
+            "peer_overflow": {"FQG_P2P": "1", "FQG_TEST_SLOT_CAP": "7", "FQG_MAX_CHUNK_BYTES": "16384"},
+            # two different names with one 64-bit hash cannot be made to order: the hook pretends that the owners met one under seed 0,
+            # every index job is repeated with seed 1 (names hashed, routed and compared anew) and must still equal the oracle's
+            "reseed": {"FQG_TEST_FAKE_COLLISION": "1"}}
 
 
 @pytest.mark.parametrize("world,variant", [(2, "pipelined"), (2, "small_chunks"), (3, "small_chunks"), (2, "one_exchange"), (2, "overflow"),
-                                           (3, "peer_copies"), (2, "peer_stores"), (2, "peer_overflow")])
+                                           (3, "peer_copies"), (2, "peer_stores"), (2, "peer_overflow"), (2, "reseed")])
 def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
     cases = _cases()
@@ -105,7 +108,7 @@ def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     by_name = {(c["file"], c["mode"]): r for c, r in zip(cases, rounds)}
     peer = {(c["file"], c["mode"]): p for c, p in zip(cases, res["peer"])}
     assert peer[("big_clean", "index")] == variant.startswith("peer")  # the rounds went through mapped peer memory / through exchanges
-    if variant == "pipelined":
+    if variant in ("pipelined", "reseed"):
         assert by_name[("big_clean", "index")] >= 1
     elif variant in ("small_chunks", "peer_copies", "peer_stores"):
         assert by_name[("big_clean", "index")] >= 3
