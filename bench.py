@@ -152,6 +152,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     n = a.reads
     nb = n * rb
+    config["l2"] = f"inputs ({nb / 1e9:.1f} GB per GPU) {'far larger than' if nb > (1 << 30) else 'NOT larger than'} L2; no flush between steps"
     data = torch.empty(nb + 64, dtype=torch.uint8, device="cuda")
     first = rank * n
     piece = 8_000_000
@@ -196,13 +197,17 @@ def main():
     sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()  # (torch's stream is idle here: the event marks the device's clock at the start of the timed region)
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(a.steps):
         rep = step()
         dev_ms += ctx.device_ms()
     barrier()
+    ev1.record()
+    torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    span_ms = ev0.elapsed_time(ev1)  # device clock over the whole timed region, every stream's work and every host gap included
     sampler.stop_flag = True
     sampler.join(timeout=2)
     launches = ctx.launch_count() - l0
@@ -214,7 +219,7 @@ def main():
     if world > 1:  # the index shard lives in its own context
         launches += runner.shard.launch_count()
         ks["index"] = runner.shard.kernel_stats()["index"]
-        dev_ms = 0.0
+        dev_ms = span_ms  # the sharded step runs on several streams of two contexts: the span between the two events is its device time
     # the step is host-driven (several synchronising read-backs); device-event time and wall time are both reported, the larger one counts
     per_step = max(dev_ms / 1e3, wall) / a.steps
     if world > 1:
