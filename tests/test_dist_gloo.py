@@ -116,3 +116,10 @@ def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
         assert by_name[("big_clean", "index")] == 1  # (the worker reports the exact reruns here)
     else:
         assert by_name[("big_clean", "index")] == 0
+
+
+def test_world_of_one():
+    """The same orchestration without a process group (what the one-GPU tests of the routing run on the device)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dist_world1_worker.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok 48"), (out.stdout[-500:], out.stderr[-2000:])
