@@ -229,7 +229,10 @@ class ShardedFastqInfo:
             # the names travel chunk by chunk beside the next chunk's pass: as many rounds as the longest range has chunks, so that
             # no round carries more than one chunk (ranks with fewer chunks add empty rounds: the rounds are collective)
             chunk = api.feed_chunk_bytes()
-            self._rounds_total = max(1, max(-(-x[-1] // chunk) for x in info))
+            # (a chunk restarts at the record the chunk before it cut, so a range may take one chunk more than its bytes suggest:
+            # count with slightly shorter chunks; a round too many is an empty round, a round too few would overflow the last one)
+            step = chunk - min(chunk // 4, 8 << 20)
+            self._rounds_total = max(1, max(-(-x[-1] // step) for x in info))
             est = sum(x[-1] / max(x[4], 16.0) for x in info) / W
             self.shard.shard_reserve(int(est * 1.05) + 4096)
             self._round, self._fires, self._inflight, self._hook_exc, self._pending_insert = 0, 0, [], None, None
