@@ -123,3 +123,33 @@ def test_world_of_one():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dist_world1_worker.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().startswith("ok 48"), (out.stdout[-500:], out.stderr[-2000:])
+
+
+@pytest.mark.parametrize("world,variant", [(3, "peer_copies"), (2, "small_chunks")])
+def test_random_cuts_through_the_routing_rounds(tmp_path, world, variant):
+    """Byte ranges cut at random positions (inside names, at line feeds, one byte apart) and chunks of 8 KiB: many different
+    phases of chunk and range boundaries through the chunk-by-chunk routing, clean files and files with one late duplicate."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
+    rng = random.Random(2024 + world)
+    cases = []
+    for k in range(24):
+        nrec = rng.choice([900, 1500, 2500, 4000])
+        recs = [f"@M{k}:1:FC:1:11:{i}:{i * 7} 1:N:0:AC\n{'ACGTN' * (3 + (i * 7 + k) % 9)}\n+\n{'F' * (5 * (3 + (i * 7 + k) % 9))}\n" for i in range(nrec)]
+        if k % 3 == 2:
+            recs[nrec - 1 - rng.randrange(50)] = recs[rng.randrange(50)]
+        data = "".join(recs).encode()
+        cuts = sorted(rng.random() for _ in range(world - 1))
+        if k % 5 == 0:  # two cuts right next to each other / at the very start of a line
+            p = data.find(b"\n@", int(len(data) * cuts[0])) + 1
+            cuts = sorted([p / len(data)] + [(p + 1) / len(data)] * (world - 2))
+        cases.append({"file": f"rand{k}", "mode": "index" if k % 4 else "single", "hex": data.hex(), "cuts": cuts})
+    cin, cout = tmp_path / "cases.json", tmp_path / "out.json"
+    json.dump(cases, open(cin, "w"))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", **VARIANTS[variant])
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                           "--master-port", str(29680 + world), os.path.join(ROOT, "tests", "dist_worker.py"), str(cin), str(cout)], env=env, timeout=600)
+    res = json.load(open(cout))
+    for c, g in zip(cases, res["transcripts"]):
+        argv = (["-r"] if c["mode"] == "single" else []) + ["a.fq"]
+        assert tuple(g) == oracle_run(argv, bytes.fromhex(c["hex"]), None), (c["file"], c["mode"], c["cuts"], g)
+    assert sum(1 for r in res["rounds"] if r >= 3) >= 8  # most index jobs really went round by round
