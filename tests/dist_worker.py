@@ -20,8 +20,13 @@ def main():
     cases = json.load(open(sys.argv[1]))
     dist.init_process_group("gloo")
     r, W = dist.get_rank(), dist.get_world_size()
-    out, rounds, peer = [], [], []
-    for c in cases:
+    out, rounds, peer, runners = [], [], [], {}
+    order = list(range(len(cases)))
+    if os.environ.get("FQG_TEST_REUSE_RUNNER"):  # small jobs first, so that the reused runner's arena has to grow
+        order.sort(key=lambda i: len(cases[i]["hex"]))
+    grown = 0
+    for ci in order:
+        c = cases[ci]
         data = bytes.fromhex(c["hex"])
         cuts = [int(len(data) * x) for x in c["cuts"]][:W - 1]
         cuts = [0] + sorted(cuts) + [len(data)]
@@ -41,9 +46,17 @@ def main():
             buf2 = (ctypes.c_uint8 * len(mine2)).from_buffer(mine2)
             kw = {"ptr2": ctypes.addressof(buf2), "nbytes2": cuts2[r + 1] - cuts2[r], "name2": "b.fq"}
         try:
-            run = fqdist.ShardedFastqInfo(mode, device=0, tensor_device=torch.device("cpu"))
+            if os.environ.get("FQG_TEST_REUSE_RUNNER"):  # one runner per mode for all cases: arenas are reused and regrown between jobs
+                if mode not in runners:
+                    runners[mode] = fqdist.ShardedFastqInfo(mode, device=0, tensor_device=torch.device("cpu"))
+                run = runners[mode]
+            else:
+                run = fqdist.ShardedFastqInfo(mode, device=0, tensor_device=torch.device("cpu"))
             res = run.run_device(ctypes.addressof(buf), hi - lo, name="a.fq", **kw)
             tr = res.get("transcript")
+            if run._arena is not None:
+                grown += int(run._arena[1] != getattr(run, "_seen_arena", run._arena[1]))
+                run._seen_arena = run._arena[1]
             rounds.append(run.rounds_done if not os.environ.get("FQG_TEST_SLOT_CAP") else run.exact_reruns)
             peer.append(bool(run._p2p_ok))
         except (NotImplementedError, RuntimeError) as ex:
@@ -54,7 +67,9 @@ def main():
             out.append(list(tr))
         dist.barrier()
     if r == 0:
-        json.dump({"transcripts": out, "rounds": rounds, "peer": peer}, open(sys.argv[2], "w"))
+        back = {ci: k for k, ci in enumerate(order)}  # results in the order of the case list
+        out, rounds, peer = [[x[back[i]] for i in range(len(cases))] for x in (out, rounds, peer)]
+        json.dump({"transcripts": out, "rounds": rounds, "peer": peer, "arena_regrown": grown}, open(sys.argv[2], "w"))
     dist.destroy_process_group()
 
 

@@ -83,11 +83,13 @@ VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "o
             "peer_overflow": {"FQG_P2P": "1", "FQG_TEST_SLOT_CAP": "7", "FQG_MAX_CHUNK_BYTES": "16384"},
             # two different names with one 64-bit hash cannot be made to order: the hook pretends that the owners met one under seed 0,
             # every index job is repeated with seed 1 (names hashed, routed and compared anew) and must still equal the oracle's
-            "reseed": {"FQG_TEST_FAKE_COLLISION": "1"}}
+            "reseed": {"FQG_TEST_FAKE_COLLISION": "1"},
+            # one runner for all jobs of a mode (a bench loop, a service): the arena of a small job is regrown for a larger one
+            "peer_reuse": {"FQG_P2P": "1", "FQG_MAX_CHUNK_BYTES": "8192", "FQG_TEST_REUSE_RUNNER": "1"}}
 
 
 @pytest.mark.parametrize("world,variant", [(2, "pipelined"), (2, "small_chunks"), (3, "small_chunks"), (2, "one_exchange"), (2, "overflow"),
-                                           (3, "peer_copies"), (2, "peer_stores"), (2, "peer_overflow"), (2, "reseed")])
+                                           (3, "peer_copies"), (2, "peer_stores"), (2, "peer_overflow"), (2, "reseed"), (2, "peer_reuse")])
 def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
     cases = _cases()
@@ -104,13 +106,15 @@ def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
         argv = (["-r"] if c["mode"] == "single" else []) + ["a.fq"] + (["b.fq"] if c["mode"] == "pair" else [])
         want = oracle_run(argv, bytes.fromhex(c["hex"]), bytes.fromhex(c["hex2"]) if c["mode"] == "pair" else None)
         assert tuple(g) == want, (c["file"], c["mode"], c["cuts"], g)
+    if variant == "peer_reuse":
+        assert res["arena_regrown"] >= 2  # the reused runner replaced its arena by a larger one (unmap, free, allocate, map again)
     # the routing under test was really taken: the clean big file goes through the chunk hook, in several rounds when chunks are small
     by_name = {(c["file"], c["mode"]): r for c, r in zip(cases, rounds)}
     peer = {(c["file"], c["mode"]): p for c, p in zip(cases, res["peer"])}
     assert peer[("big_clean", "index")] == variant.startswith("peer")  # the rounds went through mapped peer memory / through exchanges
     if variant in ("pipelined", "reseed"):
         assert by_name[("big_clean", "index")] >= 1
-    elif variant in ("small_chunks", "peer_copies", "peer_stores"):
+    elif variant in ("small_chunks", "peer_copies", "peer_stores", "peer_reuse"):
         assert by_name[("big_clean", "index")] >= 3
     elif variant in ("overflow", "peer_overflow"):
         assert by_name[("big_clean", "index")] == 1  # (the worker reports the exact reruns here)
