@@ -88,7 +88,7 @@ VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "o
             "peer_reuse": {"FQG_P2P": "1", "FQG_MAX_CHUNK_BYTES": "8192", "FQG_TEST_REUSE_RUNNER": "1"}}
 
 
-@pytest.mark.parametrize("world,variant", [(2, "pipelined"), (2, "small_chunks"), (3, "small_chunks"), (2, "one_exchange"), (2, "overflow"),
+@pytest.mark.parametrize("world,variant", [(2, "pipelined"), (3, "small_chunks"), (2, "one_exchange"), (3, "overflow"),
                                            (3, "peer_copies"), (2, "peer_stores"), (2, "peer_overflow"), (2, "reseed"), (2, "peer_reuse")])
 def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
