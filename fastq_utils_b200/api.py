@@ -5,13 +5,10 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libfastq_gpu.so")
-# Test hook (tests/test_dist_gloo.py only): the same host code linked against the sequential stand-in device of tests/sim,
-# so that the multi-rank orchestration can run under gloo on a machine without GPUs.  Never set outside the test-suite.
-_SO = os.environ.get("FQG_SIM_LIBRARY_FOR_TESTS", _SO)
 
 MODE_SINGLE, MODE_INDEX, MODE_INDEX_PAIR, MODE_INTERLEAVED, MODE_SORTED_PAIR, MODE_READER = range(6)
 KERNEL_CLASSES = ["scan", "records", "index", "mate", "pair", "other", "tile", "lanes"]
-FLAG_PAIRED_NAMES, FLAG_EXTERNAL_INDEX, FLAG_TWO_PASS = 1, 2, 4
+FLAG_PAIRED_NAMES, FLAG_EXTERNAL_INDEX, FLAG_TWO_PASS, FLAG_BORROW_FOR_CALL = 1, 2, 4, 8
 
 
 class Config(ctypes.Structure):
@@ -62,62 +59,67 @@ def lib():
     if _lib is None:
         if not os.path.exists(_SO):
             raise RuntimeError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
-        L = ctypes.CDLL(_SO)
-        vp, u64, sz, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int
-        L.fqg_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(vp)]
-        L.fqg_destroy.argtypes = [vp]
-        L.fqg_destroy.restype = None
-        L.fqg_feed.argtypes = [vp, ci, vp, sz, ci]
-        L.fqg_feed_device.argtypes = [vp, ci, vp, sz, ci]
-        L.fqg_finish.argtypes = [vp, ctypes.POINTER(Report)]
-        L.fqg_reset.argtypes = [vp]
-        L.fqg_last_error.argtypes = [vp]
-        L.fqg_last_error.restype = ctypes.c_char_p
-        L.fqg_launch_count.argtypes = [vp]
-        L.fqg_launch_count.restype = u64
-        L.fqg_path_counts.argtypes = [vp, ctypes.POINTER(u64 * 4)]
-        L.fqg_device_ms.argtypes = [vp]
-        L.fqg_device_ms.restype = ctypes.c_double
-        L.fqg_index_records.argtypes = [vp, vp, sz, ctypes.POINTER(u64), sz, ctypes.POINTER(u64)]
-        L.fqg_render.argtypes = [ctypes.POINTER(Report), ctypes.POINTER(RenderOpts), ctypes.POINTER(Transcript)]
-        L.fqg_transcript_free.argtypes = [ctypes.POINTER(Transcript)]
-        L.fqg_transcript_free.restype = None
-        L.fqg_fastq_info_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, vp, sz, ci, sz, ctypes.POINTER(Transcript)]
-        L.fqg_reader_tool_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, ci, sz, ctypes.POINTER(Transcript)]
-        L.fqg_kernel_stats.argtypes = [vp, ci, ctypes.POINTER(KernelStat)]
-        L.fqg_kernel_stats_reset.argtypes = [vp]
-        L.fqg_prescan_device.argtypes = [vp, ci, vp, sz, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64)]
-        L.fqg_set_stream_start.argtypes = [vp, ci, ctypes.c_uint32, u64]
-        L.fqg_names_count.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
-        L.fqg_names_pack.argtypes = [vp, ci, ctypes.c_uint32, vp, vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
-        L.fqg_shard_insert.argtypes = [vp, vp, u64, vp, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
-        L.fqg_shard_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(u64)]
-        L.fqg_hist_range.argtypes = [vp, ci, u64, u64, ctypes.POINTER(u64)]
-        L.fqg_shard_claim.argtypes = [vp, vp, u64, vp, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64), u64]
-        L.fqg_shard_claim_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(u64), ctypes.POINTER(u64)]
-        L.fqg_sniff_device.argtypes = [vp, ci, vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
-        L.fqg_set_sniff.argtypes = [vp, ci, ctypes.c_int32, ctypes.c_int32]
-        L.fqg_set_file_total.argtypes = [vp, ci, u64]
-        L.fqg_set_line_hint.argtypes = [vp, ci, ctypes.c_uint32]
-        L.fqg_records_fed.argtypes = [vp, ci, ctypes.POINTER(u64)]
-        L.fqg_set_hash_seed.argtypes = [vp, ctypes.c_uint32]
-        L.fqg_set_chunk_hook.argtypes = [vp, CHUNK_HOOK, vp]
-        L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
-        L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64]
-        L.fqg_shard_reserve.argtypes = [vp, u64]
-        L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ci]
-        L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
-        L.fqg_side_copy.argtypes = [vp, vp, vp, sz]
-        L.fqg_side_sync.argtypes = [vp]
-        L.fqg_ipc_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.c_char_p]
-        L.fqg_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
-        L.fqg_ipc_close.argtypes = [vp, vp]
-        L.fqg_ipc_free.argtypes = [vp, vp]
-        if hasattr(L, "fqg_synth_illumina"):  # absent from the test stand-in
-            L.fqg_synth_illumina.argtypes = [vp, u64, u64, u64, ci, u64, vp]
-            L.fqg_synth_longreads.argtypes = [vp, vp, u64, u64, u64, vp]
-        _lib = L
+        _lib = bind(ctypes.CDLL(_SO))
     return _lib
+
+
+def bind(L):
+    """Declare the argument types of include/fastq_gpu.h on a loaded library."""
+    vp, u64, sz, ci = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_int
+    L.fqg_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(vp)]
+    L.fqg_destroy.argtypes = [vp]
+    L.fqg_destroy.restype = None
+    L.fqg_feed.argtypes = [vp, ci, vp, sz, ci]
+    L.fqg_feed_device.argtypes = [vp, ci, vp, sz, ci]
+    L.fqg_finish.argtypes = [vp, ctypes.POINTER(Report)]
+    L.fqg_reset.argtypes = [vp]
+    L.fqg_last_error.argtypes = [vp]
+    L.fqg_last_error.restype = ctypes.c_char_p
+    L.fqg_launch_count.argtypes = [vp]
+    L.fqg_launch_count.restype = u64
+    L.fqg_path_counts.argtypes = [vp, ctypes.POINTER(u64 * 4)]
+    L.fqg_memory_stats.argtypes = [vp, ctypes.POINTER(u64 * 5)]
+    L.fqg_device_ms.argtypes = [vp]
+    L.fqg_device_ms.restype = ctypes.c_double
+    L.fqg_index_records.argtypes = [vp, vp, sz, ctypes.POINTER(u64), sz, ctypes.POINTER(u64)]
+    L.fqg_render.argtypes = [ctypes.POINTER(Report), ctypes.POINTER(RenderOpts), ctypes.POINTER(Transcript)]
+    L.fqg_transcript_free.argtypes = [ctypes.POINTER(Transcript)]
+    L.fqg_transcript_free.restype = None
+    L.fqg_fastq_info_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, vp, sz, ci, sz, ctypes.POINTER(Transcript)]
+    L.fqg_reader_tool_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, ci, sz, ctypes.POINTER(Transcript)]
+    L.fqg_kernel_stats.argtypes = [vp, ci, ctypes.POINTER(KernelStat)]
+    L.fqg_kernel_stats_reset.argtypes = [vp]
+    L.fqg_prescan_device.argtypes = [vp, ci, vp, sz, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64)]
+    L.fqg_set_stream_start.argtypes = [vp, ci, ctypes.c_uint32, u64]
+    L.fqg_names_count.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.fqg_names_pack.argtypes = [vp, ci, ctypes.c_uint32, vp, vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.fqg_shard_insert.argtypes = [vp, vp, u64, vp, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.fqg_shard_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(u64)]
+    L.fqg_hist_range.argtypes = [vp, ci, u64, u64, ctypes.POINTER(u64)]
+    L.fqg_shard_claim.argtypes = [vp, vp, u64, vp, ctypes.c_uint32, ctypes.POINTER(u64), ctypes.POINTER(u64), u64]
+    L.fqg_shard_claim_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.fqg_sniff_device.argtypes = [vp, ci, vp, sz, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+    L.fqg_set_sniff.argtypes = [vp, ci, ctypes.c_int32, ctypes.c_int32]
+    L.fqg_set_file_total.argtypes = [vp, ci, u64]
+    L.fqg_set_line_hint.argtypes = [vp, ci, ctypes.c_uint32]
+    L.fqg_records_fed.argtypes = [vp, ci, ctypes.POINTER(u64)]
+    L.fqg_set_hash_seed.argtypes = [vp, ctypes.c_uint32]
+    L.fqg_set_chunk_hook.argtypes = [vp, CHUNK_HOOK, vp]
+    L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
+    L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64]
+    L.fqg_shard_reserve.argtypes = [vp, u64]
+    L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ci]
+    L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
+    L.fqg_side_copy.argtypes = [vp, vp, vp, sz]
+    L.fqg_side_sync.argtypes = [vp]
+    L.fqg_ipc_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.fqg_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.fqg_ipc_close.argtypes = [vp, vp]
+    L.fqg_ipc_free.argtypes = [vp, vp]
+    if hasattr(L, "fqg_synth_illumina"):  # absent from the test stand-in
+        L.fqg_synth_illumina.argtypes = [vp, u64, u64, u64, ci, u64, vp]
+        L.fqg_synth_longreads.argtypes = [vp, vp, u64, u64, u64, vp]
+    return L
 
 
 def _check(ctx, st, what):
@@ -218,6 +220,12 @@ class FastqInfo:
         out = (ctypes.c_uint64 * 4)()
         _check(self._ctx, lib().fqg_path_counts(self._ctx, ctypes.byref(out)), "fqg_path_counts")
         return dict(zip(("lanes", "lanes_handed_on", "tile", "two_pass_fallbacks"), (int(x) for x in out)))
+
+    def memory_stats(self):
+        """{chunk_bytes_held, chunk_bytes_released, arena_bytes, records_final, collisions_walked} (include/fastq_gpu.h: fqg_memory_stats)"""
+        out = (ctypes.c_uint64 * 5)()
+        _check(self._ctx, lib().fqg_memory_stats(self._ctx, ctypes.byref(out)), "fqg_memory_stats")
+        return dict(zip(("chunk_bytes_held", "chunk_bytes_released", "arena_bytes", "records_final", "collisions_walked"), (int(x) for x in out)))
 
     def device_ms(self):
         return float(lib().fqg_device_ms(self._ctx))

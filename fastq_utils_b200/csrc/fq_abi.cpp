@@ -87,6 +87,10 @@ extern "C" int fqg_path_counts(fqg_ctx* c, uint64_t out[4]) {
   if (!c || !out) return FQG_ERR_USAGE;
   FQG_GUARD(c, { for (int i = 0; i < 4; i++) out[i] = c->eng->path_counts[i]; })
 }
+extern "C" int fqg_memory_stats(fqg_ctx* c, uint64_t out[5]) {
+  if (!c || !out) return FQG_ERR_USAGE;
+  FQG_GUARD(c, { for (int i = 0; i < 4; i++) out[i] = c->eng->mem_stats[i]; out[4] = c->eng->collisions_walked(); })
+}
 extern "C" int fqg_kernel_stats_reset(fqg_ctx* c) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->dev->kernel_stats_reset())

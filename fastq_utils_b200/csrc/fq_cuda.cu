@@ -630,15 +630,15 @@ fq_index_insert_kernel(const TableParams P) {
       unsigned long long cur, cur_idx;
       if (slot_claim128(s, nm.hash, g, &cur, &cur_idx)) break; /* first arrival of this name */
       if (cur != nm.hash) continue;
-      /* slot carries this hash: keep the smallest record index; whoever sees an earlier arrival compares the names */
+      /* the slot carries this hash: every record that ever held it has the SAME name (checked on the bytes on arrival), so any of
+       * them — the one the failed claim returned — tells whether this is our name.  Another name with the same 64-bit hash
+       * (the reference's hashit collision, src/hash.c:38-45 walks on to the next object): so do we, to the next slot. */
+      uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, cur_idx, &ol);
+      if (!(ol == nm.len && names_equal(on, P.data + nm.off, nm.len))) { atomicAdd(P.counters + 4, 1ull); continue; } /* [4]: diagnostics only */
+      /* keep the smallest record index; min over all arrivals of max(old, g) = 2nd smallest of the group = the reference's duplicate */
       unsigned long long old = atomicMin(&s->idx1, g);
-      if (old != FQ_IDX_NONE) {
-        uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, old, &ol);
-        if (ol == nm.len && names_equal(on, P.data + nm.off, nm.len)) {
-          unsigned long long later = old > g ? old : g; /* min over all arrivals of max(old, g) = 2nd smallest of the group */
-          atomicMin(P.key, FQ_KEY(P.step_base + later, FQ_R_NAME));
-        } else atomicAdd(P.counters + 0, 1ull);
-      }
+      unsigned long long later = old > g ? old : g;
+      atomicMin(P.key, FQ_KEY(P.step_base + later, FQ_R_NAME));
       break;
     }
   }
@@ -661,7 +661,7 @@ fq_mate_claim_kernel(const TableParams P) {
       if (cur == FQ_HASH_EMPTY) { unpaired = g; break; }
       if (cur != nm.hash) continue;
       uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, s->idx1, &ol);
-      if (!(ol == nm.len && names_equal(on, P.data + nm.off, nm.len))) { atomicAdd(P.counters + 0, 1ull); break; }
+      if (!(ol == nm.len && names_equal(on, P.data + nm.off, nm.len))) continue; /* another name with this hash: the lookup walks on */
       unsigned long long old = atomicMin(&P.slots[i].claim2, g);
       if (old == FQ_IDX_NONE) claimed++;           /* first claim = the reference's delete */
       else unpaired = old > g ? old : g;           /* the entry was already deleted when the later one arrives */
@@ -874,15 +874,12 @@ fq_shard_insert_kernel(const ShardParams P) {
       unsigned long long cur, cur_idx;
       if (slot_claim128(s, pn.hash, mine, &cur, &cur_idx)) break; /* first arrival of this name: one atomic on one sector */
       if (cur != pn.hash) continue;
+      if (!a.blob) { atomicAdd(a.counters + 0, 1ull); break; } /* tuples only: an equal hash cannot be judged here */
+      uint32_t ol, ml; const uint8_t* on = shard_name(a, cur_idx & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
+      if (!(ol == ml && names_equal(on, mn, ml))) { atomicAdd(a.counters + 4, 1ull); continue; } /* another name with this hash: next slot */
       unsigned long long old = atomicMin(&s->idx1, mine);
-      if (old != FQ_IDX_NONE && !a.blob) atomicAdd(a.counters + 0, 1ull); /* tuples only: an equal hash cannot be judged here */
-      else if (old != FQ_IDX_NONE) {
-        uint32_t ol, ml; const uint8_t* on = shard_name(a, old & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
-        if (ol == ml && names_equal(on, mn, ml)) {
-          unsigned long long og = old >> FQ_SHARD_POS_BITS, later = og > pn.record ? og : pn.record;
-          atomicMin(a.dup_key, FQ_KEY(later, FQ_R_NAME));
-        } else atomicAdd(a.counters + 0, 1ull);
-      }
+      unsigned long long og = old >> FQ_SHARD_POS_BITS, later = og > pn.record ? og : pn.record;
+      atomicMin(a.dup_key, FQ_KEY(later, FQ_R_NAME));
       break;
     }
   }
@@ -906,7 +903,7 @@ fq_shard_claim_kernel(const ClaimParams P) {
       if (cur == FQ_HASH_EMPTY) { unpaired = pn.record; break; }
       if (cur != pn.hash) continue;
       uint32_t ol, ml; const uint8_t* on = shard_name(P.ins, s->idx1 & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
-      if (!(ol == ml && names_equal(on, mn, ml))) { atomicAdd(a.counters + 0, 1ull); break; }
+      if (!(ol == ml && names_equal(on, mn, ml))) continue; /* another name with this hash: the lookup walks on */
       unsigned long long old = atomicMin(&a.slots[i].claim2, pn.record);
       if (old == FQ_IDX_NONE) claimed++;
       else unpaired = old > pn.record ? old : pn.record;
@@ -921,6 +918,78 @@ fq_shard_claim_kernel(const ClaimParams P) {
 __global__ void fq_shard_find_kernel(const FqPackedName* __restrict__ meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) {
   for (unsigned long long m = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; m < n; m += (unsigned long long)gridDim.x * blockDim.x)
     if (meta[m].record == record) atomicMin(out_pos, m);
+}
+
+/* ------------------------------------------------------------------------------------------------ the name arena
+ * What the reference keeps of a record is a copy of its name (new_indexentry, src/fastq.c:590-611).  Here the names of a segment
+ * are copied out of their chunk into one block of 16-byte units (zero padded: equal names are equal unit by unit), after which
+ * nothing refers to the chunk's bytes any more and the engine may release them.  This kernel serves the chunks of the per-record
+ * kernels; the clean-data pass writes its names into the arena itself, from shared memory. */
+__global__ void __launch_bounds__(256)
+fq_names_measure_kernel(const FqName* __restrict__ names, uint32_t nrec, unsigned long long* out_units) {
+  unsigned long long u = 0;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nrec; k += gridDim.x * blockDim.x) {
+    const FqName nm = names[k];
+    if (nm.hash != FQ_HASH_SKIP) u += (nm.len + 15u) >> 4;
+  }
+  u = warp_sum64(u);
+  if ((threadIdx.x & 31) == 0 && u) atomicAdd(out_units, u);
+}
+__global__ void __launch_bounds__(256)
+fq_names_gather_kernel(FqName* names, const uint8_t* __restrict__ data, uint32_t nrec, uint8_t* arena, unsigned long long* cursor_units) {
+  __shared__ uint32_t s_w[8];
+  __shared__ unsigned long long s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t b0 = blockIdx.x * 256u; b0 < nrec; b0 += gridDim.x * 256u) {
+    const uint32_t k = b0 + threadIdx.x;
+    FqName nm; nm.hash = FQ_HASH_SKIP; nm.off = 0; nm.len = 0;
+    if (k < nrec) nm = names[k];
+    const uint32_t units = nm.hash != FQ_HASH_SKIP ? (nm.len + 15u) >> 4 : 0u;
+    uint32_t incl = units;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t a = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += a; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t excl = incl - units, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t x = s_w[w]; total += x; if (w < warp) excl += x; }
+    if (threadIdx.x == 0) s_base = total ? atomicAdd(cursor_units, (unsigned long long)total) : 0ull; /* the block's names lie together, in any order among the blocks */
+    __syncthreads();
+    if (units) {
+      const unsigned long long at = (s_base + excl) * 16ull;
+      uint4* dst = (uint4*)(arena + at);
+      for (uint32_t u = 0; u < units; u++) {
+        const uint32_t o = nm.off + 16u * u, left = nm.len - 16u * u; /* left >= 1 */
+        uint4 v;
+        v.x = fq_low_bytes(fq_ldu32(data, o), left);
+        v.y = left > 4 ? fq_low_bytes(fq_ldu32(data, o + 4), left - 4) : 0u;
+        v.z = left > 8 ? fq_low_bytes(fq_ldu32(data, o + 8), left - 8) : 0u;
+        v.w = left > 12 ? fq_low_bytes(fq_ldu32(data, o + 12), left - 12) : 0u;
+        dst[u] = v;
+      }
+      names[k].off = (uint32_t)at;
+    }
+    __syncthreads(); /* s_w / s_base are rewritten by the next round */
+  }
+}
+/* open statistics -> main statistics (fq_device.h: stats_fold); two launches: the bins first (they read the open ranges), then the scalars */
+struct FoldParams { FqStats* main_[2]; FqStats* open_[2]; unsigned long long* hist[2]; unsigned long long* hopen[2]; };
+__global__ void fq_stats_fold_hist_kernel(const FoldParams P) {
+  uint32_t lo = min(P.open_[0]->min_rl, P.open_[1]->min_rl), hi = max(P.open_[0]->max_rl, P.open_[1]->max_rl);
+  if (hi >= FQ_MAX_READ_LENGTH) hi = FQ_MAX_READ_LENGTH - 1;
+  if (lo > hi) return;
+  for (uint32_t l = lo + blockIdx.x * blockDim.x + threadIdx.x; l <= hi; l += gridDim.x * blockDim.x)
+    for (int f = 0; f < 2; f++) { const unsigned long long v = P.hopen[f][l]; if (v) { P.hist[f][l] += v; P.hopen[f][l] = 0; } }
+}
+__global__ void fq_stats_fold_scalars_kernel(const FoldParams P) {
+  if (threadIdx.x || blockIdx.x) return;
+  for (int f = 0; f < 2; f++) {
+    FqStats* m = P.main_[f]; FqStats* o = P.open_[f];
+    m->num_rds += o->num_rds; m->mem_sum += o->mem_sum; m->n_names += o->n_names;
+    m->min_rl = min(m->min_rl, o->min_rl); m->max_rl = max(m->max_rl, o->max_rl);
+    m->min_q = min(m->min_q, o->min_q); m->max_q = max(m->max_q, o->max_q);
+    o->num_rds = 0; o->mem_sum = 0; o->n_names = 0; o->min_rl = 0xFFFFFFFFu; o->max_rl = 0; o->min_q = 255u; o->max_q = 0;
+  }
 }
 
 /* ------------------------------------------------------------------------------------------------ the device */
@@ -1245,6 +1314,25 @@ class FqCudaDevice : public FqDevice {
     int grid = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)sms_ * 8);
     fq_shard_find_kernel<<<grid, 256, 0, st_>>>(meta, n, record, out_pos);
     launched();
+  }
+  void names_measure(const FqName* names, uint32_t nrec, unsigned long long* out_units) override {
+    if (!nrec) return;
+    int grid = (int)std::min<uint32_t>((nrec + 255) / 256, (uint32_t)sms_ * 8);
+    fq_names_measure_kernel<<<grid, 256, 0, st_>>>(names, nrec, out_units);
+    launched();
+  }
+  void names_gather(FqName* names, const uint8_t* data, uint32_t nrec, uint8_t* arena, unsigned long long* cursor_units) override {
+    if (!nrec) return;
+    int grid = (int)std::min<uint32_t>((nrec + 255) / 256, (uint32_t)sms_ * 8);
+    tic(FQG_K_OTHER, 0, nrec);
+    fq_names_gather_kernel<<<grid, 256, 0, st_>>>(names, data, nrec, arena, cursor_units);
+    toc(); launched();
+  }
+  void stats_fold(FqStats* const main2[2], FqStats* const open2[2], unsigned long long* const hist2[2], unsigned long long* const hist_open2[2]) override {
+    FoldParams P;
+    for (int f = 0; f < 2; f++) { P.main_[f] = main2[f]; P.open_[f] = open2[f]; P.hist[f] = hist2[f]; P.hopen[f] = hist_open2[f]; }
+    fq_stats_fold_hist_kernel<<<sms_, 256, 0, st_>>>(P); launched();
+    fq_stats_fold_scalars_kernel<<<1, 32, 0, st_>>>(P); launched();
   }
   void explain(const uint8_t* data, const FqLine* L, const FqRecCtx& cx, FqRecOut* out_dev) override {
     fq_explain_kernel<<<1, 32, 0, st_>>>(data, L[0], L[1], L[2], L[3], cx, out_dev);

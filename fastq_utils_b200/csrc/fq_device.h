@@ -152,6 +152,17 @@ class FqDevice {
   virtual void ipc_close(void* p) { (void)p; }
   virtual void ipc_free(void* p) { (void)p; }
   virtual void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) = 0;
+  /* The name arena (what the reference's new_indexentry keeps of a record, src/fastq.c:590-611: a copy of its name).  Names leave
+   * their chunk so that the chunk's bytes can be released once its records are final: names_measure adds the 16-byte units the
+   * names of a segment take (*out_units += ...; records without a name step, hash == FQ_HASH_SKIP, take none), names_gather copies
+   * every such name into `arena` (one zero-padded run of 16-byte units per name, in any order; *cursor_units counts the units
+   * handed out and starts at 0) and rewrites names[k].off to the byte offset of the copy inside `arena`. */
+  virtual void names_measure(const FqName* names, uint32_t nrec, unsigned long long* out_units) = 0;
+  virtual void names_gather(FqName* names, const uint8_t* data, uint32_t nrec, uint8_t* arena, unsigned long long* cursor_units) = 0;
+  /* Statistics of records that are not final yet (a later event may still restrict the file) are kept in a second set, `open`;
+   * stats_fold adds the open set of both files into the main set (counters, minima / maxima, the histogram bins between the open
+   * minima and maxima of either file) and leaves the open set empty. */
+  virtual void stats_fold(FqStats* const main2[2], FqStats* const open2[2], unsigned long long* const hist2[2], unsigned long long* const hist_open2[2]) = 0;
   /* details of one record for the error message */
   virtual void explain(const uint8_t* data, const FqLine* lines4_host, const FqRecCtx& cx, FqRecOut* out_dev) = 0;
   /* device-side stopwatch on the stream (CUDA events) */

@@ -18,6 +18,9 @@ static const size_t kMaxChunk = 1ull << 31;      /* bytes per chunk: offsets are
  * bridges and every starting phase are reached with small inputs */
 static size_t feed_chunk() { const char* e = getenv("FQG_MAX_CHUNK_BYTES"); size_t v = e ? strtoull(e, nullptr, 10) & ~(size_t)15 : 0; return v >= 4096 && v < kMaxChunk ? v : kMaxChunk; }
 static const uint32_t kNone32 = 0xFFFFFFFFu;
+/* device words: [0] equal hashes that tuples alone could not judge, [1] claimed by the mate loop, [2] table full, [3] the owner's earliest
+ * name event, [4] names that met ANOTHER name with their hash (diagnostics), [5] units measured for an arena, [6] arena cursor */
+static const int kCounters = 8;
 
 static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 static int fmt_of_sniff(int s) { return s == FQ_SNIFF_DEFAULT ? FQ_FMT_DEFAULT : s == FQ_SNIFF_CASAVA ? FQ_FMT_CASAVA : FQ_FMT_INT; }
@@ -25,7 +28,8 @@ static int fmt_of_sniff(int s) { return s == FQ_SNIFF_DEFAULT ? FQ_FMT_DEFAULT :
 FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) {
   if (cfg_.mode == FQG_MODE_READER) { reader_ = true; cfg_.mode = FQG_MODE_SINGLE; } /* same chunks, segments, tails and events; only the per-record verdict differs */
   key_ = (unsigned long long*)dev_->alloc(sizeof(unsigned long long));
-  counters_ = (unsigned long long*)dev_->alloc(4 * sizeof(unsigned long long));
+  counters_ = (unsigned long long*)dev_->alloc(kCounters * sizeof(unsigned long long));
+  streaming_ = cfg_.mode == FQG_MODE_SINGLE || cfg_.mode == FQG_MODE_INDEX || cfg_.mode == FQG_MODE_INDEX_PAIR;
   scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
   recout_ = (FqRecOut*)dev_->alloc(sizeof(FqRecOut));
   tile_out_ = (uint32_t*)dev_->alloc(32 * sizeof(uint32_t));
@@ -33,6 +37,8 @@ FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) 
   for (int f = 0; f < 2; f++) {
     f_[f].stats = (FqStats*)dev_->alloc(sizeof(FqStats));
     f_[f].hist = (unsigned long long*)dev_->alloc((size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
+    f_[f].stats_open = (FqStats*)dev_->alloc(sizeof(FqStats));
+    f_[f].hist_open = (unsigned long long*)dev_->alloc((size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
   }
   if (cfg_.index_capacity_hint && (cfg_.mode == FQG_MODE_INDEX || cfg_.mode == FQG_MODE_INDEX_PAIR)) {
     table_cap_ = pow2_at_least(std::max<uint64_t>(1u << 16, cfg_.index_capacity_hint * 2));
@@ -42,19 +48,19 @@ FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) 
 }
 
 void FqEngine::free_file(FqFile& F) {
-  for (auto& s : F.segs) { if (s.names) dev_->release(s.names); if (s.lines_dev) dev_->release(s.lines_dev); }
+  for (auto& s : F.segs) { if (s.names) dev_->release(s.names); if (s.lines_dev) dev_->release(s.lines_dev); if (s.arena) dev_->release(s.arena); }
   for (auto& b : F.bufs) { if (b.owned && b.data) dev_->release(b.data); if (b.line_end) dev_->release(b.line_end); }
   if (F.pend) dev_->release(F.pend);
   if (F.dir_dev) dev_->release(F.dir_dev);
   for (auto& ps : F.prescans) dev_->release(ps.line_end);
-  FqStats* st = F.stats; unsigned long long* h = F.hist;
+  FqStats* st = F.stats; unsigned long long* h = F.hist; FqStats* so = F.stats_open; unsigned long long* ho = F.hist_open;
   F = FqFile();
-  F.stats = st; F.hist = h;
+  F.stats = st; F.hist = h; F.stats_open = so; F.hist_open = ho;
 }
 
 FqEngine::~FqEngine() {
   dev_->sync();
-  for (int f = 0; f < 2; f++) { free_file(f_[f]); dev_->release(f_[f].stats); dev_->release(f_[f].hist); }
+  for (int f = 0; f < 2; f++) { free_file(f_[f]); dev_->release(f_[f].stats); dev_->release(f_[f].hist); dev_->release(f_[f].stats_open); dev_->release(f_[f].hist_open); }
   if (slots_) dev_->release(slots_);
   dev_->release(key_); dev_->release(counters_); dev_->release(scratch_); dev_->release(recout_); dev_->release(tile_out_);
   dev_->release(route_cursors_);
@@ -68,16 +74,20 @@ void FqEngine::reset() {
   seed_ = 0; finished_ = false; total0_set_ = false; total0_ = 0; fused_ok_ = !(cfg_.flags & FQG_FLAG_TWO_PASS);
   { const char* e = getenv("FQG_FUSED_MIN_BYTES"); fused_min_ = e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 20); } /* test hook */
   { const char* e = getenv("FQG_NO_LANES"); lanes_ok_ = !(e && *e && *e != '0'); }                                  /* test hook */
+  { const char* e = getenv("FQG_TEST_WEAK_HASH"); if (e && *e && *e != '0') seed_ = FQ_SEED_WEAK; }                 /* test hook: 12-bit name hashes, so that equal hashes of different names are common */
+  for (auto& m : mem_stats) m = 0;
+  open_ = streaming_; add_depth_ = 0;
   /* results */
   dev_->fill(key_, 0xFF, sizeof(unsigned long long));
-  dev_->fill(counters_, 0, 4 * sizeof(unsigned long long));
+  dev_->fill(counters_, 0, kCounters * sizeof(unsigned long long));
   for (int f = 0; f < 2; f++) {
     FqStats init; memset(&init, 0, sizeof init);
     init.min_rl = 0xFFFFFFFFu; init.min_q = 255u;
     dev_->upload(f_[f].stats, &init, sizeof init);
     dev_->fill(f_[f].hist, 0, (size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
+    dev_->sync(); /* `init` is a stack object */
   }
-  dev_->sync(); /* `init` is a stack object */
+  clear_open();
   if (slots_) dev_->fill_index(slots_, 0xFF, table_cap_ * sizeof(FqSlot)); /* on the index kernels' stream: beside the first chunk's pass */
   table_names_ = 0;
 }
@@ -144,6 +154,17 @@ void FqEngine::feed_device(int file, const void* dptr, size_t n, bool last) {
       p -= F.pend_n; n += F.pend_n;
       F.pend_n = 0; F.pend_lfs = 0;
     }
+  }
+  if (cfg_.flags & FQG_FLAG_BORROW_FOR_CALL) {
+    /* the caller wants its buffer back now: chunks that could not be settled (an event fired; or a loop kind that keeps its chunks)
+     * move into memory of our own */
+    for (auto& B : F.bufs) {
+      if (B.released || B.owned || !B.data) continue;
+      uint8_t* d = (uint8_t*)dev_->alloc((size_t)B.n + kPad);
+      dev_->copy(d, B.data, B.n); dev_->fill(d + B.n, 0, kPad);
+      B.data = d; B.owned = true;
+    }
+    dev_->sync_main();
   }
 }
 
@@ -257,7 +278,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   a.data = B.data; a.n = B.n; a.virtual_end = last ? 1 : 0; a.line_end = B.line_end; a.cap = cap; a.out5 = tile_out_;
   a.j0 = j0; a.max_rec = kNone32; a.g0 = g0_local + F.g_base; a.step_base = step_base(file); a.cx = make_ctx(file);
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
-  a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; a.key = key_; a.names = names; a.names_cap = ncap;
+  a.stats = f_[target].stats_open; a.hist = f_[target].hist_open; a.stats_range = f_[file].stats_open; a.key = key_; a.names = names; a.names_cap = ncap;
   a.hint_line_len = F.first_seq_len;
   a.lead = B.lead;
   /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
@@ -278,7 +299,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
                                        B.n, j0, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10], o[11], o[12], o[13]);
       if (pass_ok && !o[10]) {
         dev_->lanes_commit(a, false);
-        path_counts[0]++;
+        path_counts[0]++; fused_lanes_ = true;
         B.nlines = o[0]; B.index_partial = false; B.index_virtual_end = last;
         B.tail_from = o[0] > 8 ? o[0] - 8 : 0; B.tail_n = o[0] - B.tail_from;
         for (uint32_t i = 0; i < B.tail_n; i++) B.tail_ends[i] = o[16 + i];
@@ -296,6 +317,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   }
   uint32_t init[6] = {0, 0, kNone32, 0, 0, 0};
   dev_->upload(tile_out_, init, sizeof init);
+  fused_lanes_ = false;
   bool launched = dev_->tile_pass(a);
   uint32_t out5[6] = {0, 0, kNone32, 0, 0, 0};
   if (launched) dev_->download(out5, tile_out_, sizeof out5); else dev_->sync();
@@ -319,7 +341,6 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
 void FqEngine::fused_fallback() {
   fused_ok_ = false;
   path_counts[3]++;
-  for (int f = 0; f < 2; f++) for (auto& s : f_[f].segs) s.fused = false;
   reprocess();
 }
 
@@ -334,8 +355,11 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
     if (last) flush_pending_as_last(file);
     return;
   }
+  struct Depth { FqEngine* e; int file; Depth(FqEngine* e_, int f_) : e(e_), file(f_) { e->add_depth_++; } ~Depth() { e->add_depth_--; } } depth_guard(this, file);
+  struct Settle { FqEngine* e; int file; ~Settle() { if (e->add_depth_ == 1 && !std::uncaught_exceptions()) e->try_settle(file); } } settle_guard{this, file};
   int b = (int)F.bufs.size();
   F.bufs.push_back(FqBuffer());
+  mem_stats[0] += n;
   bool fused = false; uint32_t fused_j0 = 0, fused_ncap = 0; uint64_t fused_g0 = 0; FqName* fused_names = nullptr;
   {
     FqBuffer& B = F.bufs[b];
@@ -401,10 +425,9 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
         j += 4 * nrec;
         uint32_t end = line_end_at(F.bufs[b], j - 1);
         s.span = end - pos; pos = end;
-        s.g0 = F.nrec; F.nrec += nrec; s.names = fused_names;
+        s.g0 = F.nrec; F.nrec += nrec; s.names = fused_names; s.lanes = fused_lanes_;
         F.segs.push_back(s);
-        FqDirEntry de; de.g0 = s.g0; de.names = s.names; de.data = B.data;
-        F.dir_host.push_back(de);
+        gather_segment(file, F.segs.size() - 1, nrec);
         launch_names(file, F.segs.size() - 1, nrec);
       } else if (fused_names) dev_->release(fused_names);
       segmentize(file, b, pos, j, last); /* what is left: fewer than four lines (over-long check, pending bytes / end of file) */
@@ -480,6 +503,98 @@ void FqEngine::end_file(int file, const uint8_t* dev_tail, size_t n) {
   F.ended = true;
 }
 
+/* ------------------------------------------------------------------------------------------------ name arena, settling */
+/* the names of segment si leave their chunk (names_gather); the directory entry of the segment points at the copy */
+void FqEngine::gather_segment(int file, size_t si, uint32_t nrec) {
+  FqFile& F = f_[file];
+  FqSegment& s = F.segs[si];
+  if (s.names) {
+    if (s.arena) { dev_->sync(); dev_->release(s.arena); s.arena = nullptr; } /* (a re-run: kernels of the side stream may still read the old copy) */
+    dev_->fill(counters_ + 5, 0, 2 * sizeof(unsigned long long));
+    dev_->names_measure(s.names, nrec, counters_ + 5);
+    unsigned long long units = 0; dev_->download(&units, counters_ + 5, sizeof units);
+    if (units * 16ull >= (1ull << 32)) throw std::runtime_error("internal: more than 4 GiB of read names in one chunk");
+    s.arena = (uint8_t*)dev_->alloc((size_t)units * 16 + kPad);
+    mem_stats[2] += units * 16;
+    dev_->names_gather(s.names, F.bufs[s.buf].data, nrec, s.arena, counters_ + 6);
+  }
+  set_dir(file, si);
+}
+void FqEngine::set_dir(int file, size_t si) {
+  FqFile& F = f_[file];
+  const FqSegment& s = F.segs[si];
+  if (F.dir_host.size() <= si) F.dir_host.resize(si + 1);
+  FqDirEntry de; de.g0 = s.g0; de.names = s.names; de.data = s.arena;
+  F.dir_host[si] = de;
+  if (F.dir_synced > si) F.dir_synced = si;
+}
+void FqEngine::fold_open() {
+  FqStats* m[2] = {f_[0].stats, f_[1].stats}; FqStats* o[2] = {f_[0].stats_open, f_[1].stats_open};
+  unsigned long long* h[2] = {f_[0].hist, f_[1].hist}; unsigned long long* ho[2] = {f_[0].hist_open, f_[1].hist_open};
+  dev_->stats_fold(m, o, h, ho);
+}
+void FqEngine::clear_open() {
+  for (int f = 0; f < 2; f++) {
+    FqStats init; memset(&init, 0, sizeof init);
+    init.min_rl = 0xFFFFFFFFu; init.min_q = 255u;
+    dev_->upload(f_[f].stats_open, &init, sizeof init);
+    dev_->fill(f_[f].hist_open, 0, (size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
+    dev_->sync(); /* `init` is a stack object */
+  }
+}
+/* main + open set of one file */
+FqStats FqEngine::read_stats(int file) {
+  FqStats m, o;
+  dev_->download(&m, f_[file].stats, sizeof m); dev_->download(&o, f_[file].stats_open, sizeof o);
+  m.num_rds += o.num_rds; m.mem_sum += o.mem_sum; m.n_names += o.n_names;
+  m.min_rl = std::min(m.min_rl, o.min_rl); m.max_rl = std::max(m.max_rl, o.max_rl);
+  m.min_q = std::min(m.min_q, o.min_q); m.max_q = std::max(m.max_q, o.max_q);
+  return m;
+}
+void FqEngine::release_buffer(FqBuffer& B) {
+  if (B.released) return;
+  /* stream-ordered: every kernel that reads the chunk runs on the main stream and has been queued (the index kernels of the side
+   * stream read names and arenas only) */
+  if (B.owned && B.data) dev_->release(B.data);
+  if (B.line_end) dev_->release(B.line_end);
+  mem_stats[0] -= B.n; mem_stats[1] += B.n;
+  B.data = nullptr; B.line_end = nullptr; B.owned = false; B.released = true;
+}
+/* The outermost add_buffer is done with its chunk.  While no event has fired, what was validated is final: the open statistics are
+ * folded into the main set and the chunk's bytes go (the reference keeps nothing of a record but its name either,
+ * src/fastq.c:396-439).  A chunk of the per-record kernels costs one look at the event key; a chunk of the clean-data pass, which
+ * can raise none, costs nothing.  The first chunk that cannot be settled ends this: it and everything after it stay resident. */
+void FqEngine::try_settle(int file) {
+  if (!open_) return;
+  FqFile& F = f_[file];
+  bool look = false;
+  for (size_t si = F.n_settled; si < F.segs.size(); si++) if (!F.segs[si].lanes) look = true;
+  if (look) {
+    unsigned long long k = 0; dev_->download(&k, key_, sizeof k);
+    if (k != FQ_KEY_NONE || f_[0].limit != ~0ull || f_[1].limit != ~0ull) { open_ = false; return; }
+  }
+  if (F.n_settled < F.segs.size()) fold_open();
+  for (size_t si = F.n_settled; si < F.segs.size(); si++) { F.segs[si].settled = true; mem_stats[3] += F.segs[si].nrec; }
+  F.n_settled = F.segs.size();
+  for (auto& B : F.bufs) release_buffer(B);
+}
+/* bytes of the normalised name of a record, from the arena (message details of the name events) */
+void FqEngine::fetch_name(int file, uint64_t g, char* dst, uint32_t* len_out) {
+  FqFile& F = f_[file];
+  dst[0] = 0; *len_out = 0;
+  if (F.segs.empty()) return;
+  size_t lo = 0, hi = F.segs.size();
+  while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (F.segs[mid].g0 <= g) lo = mid; else hi = mid; }
+  const FqSegment& s = F.segs[lo];
+  if (!s.names || !s.arena || g - s.g0 >= s.nrec) return;
+  FqName nm; dev_->download(&nm, s.names + (g - s.g0), sizeof nm);
+  uint32_t n = std::min<uint32_t>(nm.len, 1023);
+  std::vector<uint8_t> tmp(n);
+  if (n) dev_->download(tmp.data(), s.arena + nm.off, n);
+  uint32_t k = 0; while (k < n && tmp[k] != 0) k++; /* (printed with %s by the reference) */
+  memcpy(dst, tmp.data(), k); dst[k] = 0; *len_out = k;
+}
+
 void FqEngine::sync_dir(int file) {
   FqFile& F = f_[file];
   if (F.dir_synced == F.dir_host.size()) return;
@@ -500,8 +615,6 @@ void FqEngine::add_segment(int file, FqSegment s) {
   s.g0 = F.nrec; F.nrec += s.nrec;
   if (loop_of(file) != FQ_LOOP_SINGLE && loop_of(file) != FQ_LOOP_READER) s.names = (FqName*)dev_->alloc((size_t)s.nrec * sizeof(FqName));
   F.segs.push_back(s);
-  FqDirEntry de; de.g0 = s.g0; de.names = s.names; de.data = F.bufs[s.buf].data;
-  F.dir_host.push_back(de);
   launch_segment(file, F.segs.size() - 1);
 }
 
@@ -510,6 +623,7 @@ void FqEngine::record_lines(int file, uint64_t g, FqLine out[4], const uint8_t**
   size_t lo = 0, hi = F.segs.size();
   while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (F.segs[mid].g0 <= g) lo = mid; else hi = mid; }
   const FqSegment& s = F.segs[lo];
+  if (F.bufs[s.buf].released) throw std::runtime_error("internal: the lines of a record whose chunk has been released");
   ensure_full_index(F.bufs[s.buf]);
   const FqBuffer& B = F.bufs[s.buf];
   if (data) *data = B.data;
@@ -555,7 +669,7 @@ void FqEngine::launch_names(int file, size_t si, uint32_t nrec) {
   if (loop != FQ_LOOP_INDEX && loop != FQ_LOOP_MATE) return;
   if (cfg_.flags & FQG_FLAG_EXTERNAL_INDEX) return; /* the names go to the owners of their hashes instead (fqg_names_pack) */
   FqTableArgs t; memset(&t, 0, sizeof t);
-  t.names = s.names; t.data = F.bufs[s.buf].data; t.nrec = nrec; t.g0 = s.g0; t.step_base = step_base(file);
+  t.names = s.names; t.data = s.arena; t.nrec = nrec; t.g0 = s.g0; t.step_base = step_base(file);
   t.key = key_; t.counters = counters_;
   sync_dir(0);
   t.dir1 = f_[0].dir_dev; t.ndir1 = (uint32_t)f_[0].dir_host.size();
@@ -578,7 +692,7 @@ void FqEngine::launch_segment(int file, size_t si) {
   if (s.g0 >= lim) return;
   if (loop_of(file) == FQ_LOOP_MATE && total0() == 0) return; /* "No reads found": file 2 is never opened */
   uint32_t nrec = (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0);
-  if (s.fused) { launch_names(file, si, nrec); return; } /* only reached when a table rebuild replays the name step */
+  if (s.fused || s.settled) { launch_names(file, si, nrec); return; } /* only reached when a table rebuild replays the name step */
   ensure_full_index(F.bufs[s.buf]);
   sniff_if_needed(file, s);
   const FqBuffer& B = F.bufs[s.buf];
@@ -587,9 +701,10 @@ void FqEngine::launch_segment(int file, size_t si) {
   a.q = s.q; a.j0 = s.j0; a.nrec = nrec; a.span_bytes = s.span; a.g0 = s.g0 + F.g_base; a.step_base = step_base(file);
   a.cx = make_ctx(file);
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
-  a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats;
+  a.stats = f_[target].stats_open; a.hist = f_[target].hist_open; a.stats_range = f_[file].stats_open;
   a.key = key_; a.names = s.names;
   dev_->records(a);
+  gather_segment(file, si, nrec);
   launch_names(file, si, nrec);
 }
 
@@ -603,7 +718,7 @@ void FqEngine::launch_pairs() {
       if (s.g0 >= N) break;
       uint64_t end = std::min<uint64_t>(s.g0 + s.nrec, N);
       uint64_t e0 = s.g0 + (s.g0 & 1);
-      const uint8_t* d = F.bufs[s.buf].data;
+      const uint8_t* d = s.arena;
       if (e0 + 1 < end) {
         FqPairArgs p; memset(&p, 0, sizeof p);
         p.a = s.names + (e0 - s.g0); p.b = p.a + 1; p.da = p.db = d; p.stride_a = p.stride_b = 2;
@@ -614,7 +729,7 @@ void FqEngine::launch_pairs() {
       if (((s.g0 + s.nrec) & 1) && s.g0 + s.nrec < N && si + 1 < F.segs.size()) {
         const FqSegment& t = F.segs[si + 1];
         FqPairArgs p; memset(&p, 0, sizeof p);
-        p.a = s.names + (s.nrec - 1); p.da = d; p.b = t.names; p.db = F.bufs[t.buf].data; p.stride_a = p.stride_b = 1;
+        p.a = s.names + (s.nrec - 1); p.da = d; p.b = t.names; p.db = t.arena; p.stride_a = p.stride_b = 1;
         p.npairs = 1; p.p0 = (s.g0 + s.nrec - 1) / 2; p.rank = FQ_RI_UNPAIRED; p.key = key_;
         dev_->pair_compare(p);
       }
@@ -627,7 +742,7 @@ void FqEngine::launch_pairs() {
       uint64_t lo = std::max(s.g0, t.g0), hi = std::min<uint64_t>(std::min(s.g0 + s.nrec, t.g0 + t.nrec), N);
       if (lo < hi) {
         FqPairArgs p; memset(&p, 0, sizeof p);
-        p.a = s.names + (lo - s.g0); p.da = f_[0].bufs[s.buf].data; p.b = t.names + (lo - t.g0); p.db = f_[1].bufs[t.buf].data;
+        p.a = s.names + (lo - s.g0); p.da = s.arena; p.b = t.names + (lo - t.g0); p.db = t.arena;
         p.stride_a = p.stride_b = 1; p.npairs = (uint32_t)(hi - lo); p.p0 = lo; p.rank = FQ_RS_MISMATCH; p.key = key_;
         dev_->pair_compare(p);
       }
@@ -639,16 +754,12 @@ void FqEngine::launch_pairs() {
 /* run every kernel again over the resident chunks (after a limit or the hash seed changed) */
 void FqEngine::reprocess() {
   dev_->sync();
-  for (int f = 0; f < 2; f++) for (auto& s : f_[f].segs) s.fused = false; /* limits / seeds changed: the two-pass kernels redo every segment */
+  /* limits changed: the two-pass kernels redo every segment that is not final; the final ones (their statistics are in the main set,
+   * their chunks may be gone) only replay their name step into the cleared index */
+  for (int f = 0; f < 2; f++) for (auto& s : f_[f].segs) if (!s.settled) { s.fused = false; s.lanes = false; }
   dev_->fill(key_, 0xFF, sizeof(unsigned long long));
-  dev_->fill(counters_, 0, 4 * sizeof(unsigned long long));
-  for (int f = 0; f < 2; f++) {
-    FqStats init; memset(&init, 0, sizeof init);
-    init.min_rl = 0xFFFFFFFFu; init.min_q = 255u;
-    dev_->upload(f_[f].stats, &init, sizeof init);
-    dev_->sync();
-    dev_->fill(f_[f].hist, 0, (size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
-  }
+  dev_->fill(counters_, 0, kCounters * sizeof(unsigned long long));
+  clear_open();
   if (slots_) dev_->fill(slots_, 0xFF, table_cap_ * sizeof(FqSlot));
   table_names_ = 0;
   for (int f = 0; f < nfiles(); f++)
@@ -660,6 +771,11 @@ int FqEngine::first_byte_of_line(int file, uint64_t gl) {
   FqFile& F = f_[file];
   uint64_t r = gl / 4;
   if (r < F.nrec) {
+    {
+      size_t lo = 0, hi = F.segs.size();
+      while (hi - lo > 1) { size_t mid = (lo + hi) / 2; if (F.segs[mid].g0 <= r) lo = mid; else hi = mid; }
+      if (F.segs[lo].settled) return '@'; /* a final record raised no reader event: none of its lines starts with NUL; only that is asked */
+    }
     FqLine L[4]; const uint8_t* data;
     record_lines(file, r, L, &data);
     if (L[gl & 3].len == 0) return -1;
@@ -707,7 +823,7 @@ void FqEngine::finish(fqg_report* rep) {
     dev_->download(&dev_key, key_, sizeof dev_key);
     dev_->download(ctr, counters_, sizeof ctr);
     if (ctr[2]) throw std::runtime_error("index table overflow");
-    if (ctr[0]) { seed_++; reprocess(); continue; } /* two different names shared a 64-bit hash: new seed */
+    /* (two different names with one 64-bit hash are no event: the index kernels compare the bytes behind every equal hash and walk on) */
     /* events only the host can see: what is left at the end of each file */
     ev.key = FQ_KEY_NONE; ev.code = 0; ev.file = 0; ev.line = 0; ev.a = 0;
     auto offer = [&](uint64_t key, int code, int file, uint64_t line, uint64_t a) {
@@ -726,7 +842,7 @@ void FqEngine::finish(fqg_report* rep) {
           uint64_t S1 = total0() + 1;
           if (t1 > 0) offer(FQ_KEY(S1 + f_[1].g_base + N1, FQ_R_TRUNC), FQ_E_TRUNC, 1, 4 * (f_[1].g_base + N1), 0);
           if (!(cfg_.flags & FQG_FLAG_EXTERNAL_INDEX)) { /* sharded runs count the leftovers at the owners */
-            FqStats st; dev_->download(&st, f_[0].stats, sizeof st);
+            FqStats st = read_stats(0);
             uint64_t left = st.n_names - ctr[1];
             if (left > 0) offer(FQ_KEY(S1 + N1 + 1, 0), FQ_E_LEFTOVER, 0, 0, left);
           }
@@ -905,6 +1021,12 @@ void FqEngine::fill_error(fqg_report* rep, uint64_t key, int host_code, int host
     }
   }
   e.file = file; e.msg_file = msg_file; e.record = g;
+  if (vrank < 0 && (code == FQ_E_DUP || code == FQ_E_UNPAIRED || code == FQ_E_MISMATCH)) {
+    /* a name event: the message quotes the normalised name only, which lives in the arena (the record's chunk may be gone) */
+    e.code = code; e.line = L;
+    if (code != FQ_E_MISMATCH) fetch_name(file, g - f_[file].g_base, e.name, &e.name_len);
+    return;
+  }
   /* details from the record itself */
   FqLine Ls[4]; const uint8_t* data;
   record_lines(file, g - f_[file].g_base, Ls, &data);
@@ -934,7 +1056,7 @@ void FqEngine::fill_error(fqg_report* rep, uint64_t key, int host_code, int host
 void FqEngine::fill_stats(fqg_report* rep) {
   dev_->sync();
   FqStats st[2];
-  for (int f = 0; f < 2; f++) dev_->download(&st[f], f_[f].stats, sizeof(FqStats));
+  for (int f = 0; f < 2; f++) st[f] = read_stats(f);
   unsigned long long ctr[4]; dev_->download(ctr, counters_, sizeof ctr);
   for (int f = 0; f < 2; f++) {
     fqg_file_report& r = rep->file[f];
@@ -959,8 +1081,10 @@ void FqEngine::fill_stats(fqg_report* rep) {
   else {
     uint32_t lo = s.min_rl, hi = s.max_rl;
     if (cfg_.mode == FQG_MODE_INDEX_PAIR && st[1].max_rl > 0) { lo = std::min(lo, st[1].min_rl); hi = std::max(hi, st[1].max_rl); }
-    std::vector<unsigned long long> h(hi - lo + 1);
+    std::vector<unsigned long long> h(hi - lo + 1), ho(hi - lo + 1);
     dev_->download(h.data(), f_[0].hist + lo, h.size() * sizeof(unsigned long long));
+    dev_->download(ho.data(), f_[0].hist_open + lo, ho.size() * sizeof(unsigned long long));
+    for (size_t i = 0; i < h.size(); i++) h[i] += ho[i];
     unsigned long long c = 0; med = FQ_MAX_READ_LENGTH;
     for (uint32_t l = lo; l <= hi; l++) { c += h[l - lo]; if (c > s.num_rds / 2) { med = l; break; } }
   }
@@ -1077,7 +1201,7 @@ void FqEngine::names_pack(int file, uint32_t world, void* meta, void* blob, cons
   uint64_t lim = eff_records(F);
   for (auto& s : F.segs) {
     if (s.g0 >= lim || !s.names) continue;
-    dev_->names_pack(s.names, F.bufs[s.buf].data, (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0), s.g0 + F.g_base, world,
+    dev_->names_pack(s.names, s.arena, (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0), s.g0 + F.g_base, world,
                      (FqPackedName*)meta, (uint8_t*)blob, base, cursor);
   }
   dev_->sync(); /* h is a local */
@@ -1174,12 +1298,16 @@ void FqEngine::shard_result(uint64_t* key, uint64_t* record, char* name, uint32_
 void FqEngine::hist_range(int file, uint64_t lo, uint64_t hi, uint64_t* out) {
   if (hi < lo || hi >= FQ_MAX_READ_LENGTH) throw std::runtime_error("fqg_hist_range: bad range");
   dev_->download(out, f_[file].hist + lo, (hi - lo + 1) * sizeof(unsigned long long));
+  std::vector<unsigned long long> ho(hi - lo + 1);
+  dev_->download(ho.data(), f_[file].hist_open + lo, ho.size() * sizeof(unsigned long long));
+  for (size_t i = 0; i < ho.size(); i++) out[i] += ho[i];
 }
 
 void FqEngine::set_file_total(int file, uint64_t total) {
   if (file != 0) throw std::runtime_error("fqg_set_file_total: only file 0 has a total that other loops depend on");
   total0_set_ = true; total0_ = total;
 }
+uint64_t FqEngine::collisions_walked() { dev_->sync(); unsigned long long v = 0; dev_->download(&v, counters_ + 4, sizeof v); return v; }
 void FqEngine::set_sniff(int file, int fmt, int color) { f_[file].sniff_fmt = fmt; f_[file].sniff_color = color; }
 void FqEngine::sniff_device(int file, const void* dptr, size_t n, uint32_t skip, int32_t* fmt, int32_t* color) {
   FqFile& F = f_[file];

@@ -24,6 +24,7 @@ struct FqBuffer {
   /* the last line ends of the chunk, read back together with the pass's result words: the host needs only these (where the last
    * complete record ends, how long the lines after it are) and would otherwise fetch them one synchronising copy at a time */
   uint32_t tail_from = 0, tail_n = 0, tail_ends[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool released = false;     /* every record of the chunk is final and its names live in the arena: the bytes and the line index are gone */
 };
 
 struct FqSegment {
@@ -36,6 +37,9 @@ struct FqSegment {
   FqLine* lines_dev = nullptr;
   uint64_t g0 = 0;
   FqName* names = nullptr;   /* device, nrec entries (NULL for the single loop) */
+  uint8_t* arena = nullptr;  /* device: the bytes of the segment's names, copied out of the chunk (names[k].off points in here) */
+  bool settled = false;      /* final: validated without an event, statistics in the main set; the chunk's bytes are not needed again */
+  bool lanes = false;        /* validated by the clean-data pass (`fused` says: by one of the two fused passes) */
 };
 
 struct FqTailLine { uint32_t off, len; };
@@ -52,7 +56,9 @@ struct FqFile {
   std::vector<FqTailLine> tail_lines;
   int sniff_fmt = -1, sniff_color = -1;
   uint32_t first_seq_len = 0; /* raw length of the first record's sequence line (0: not seen by this context) */
-  FqStats* stats = nullptr; unsigned long long* hist = nullptr; /* device */
+  FqStats* stats = nullptr; unsigned long long* hist = nullptr; /* device: records that are final */
+  FqStats* stats_open = nullptr; unsigned long long* hist_open = nullptr; /* device: records a later event may still exclude */
+  size_t n_settled = 0;     /* segments [0, n_settled) are final */
   FqDirEntry* dir_dev = nullptr; size_t dir_cap = 0; std::vector<FqDirEntry> dir_host; size_t dir_synced = 0;
   uint64_t limit = ~0ull;   /* records at or beyond this index are never read (early clean end of file) */
   /* multi-GPU: this context holds a range of the file */
@@ -83,6 +89,7 @@ class FqEngine {
   void set_file_total(int file, uint64_t total);
   uint64_t records_fed(int file) const { return f_[file].nrec; }
   void set_hash_seed(uint32_t seed) { if (f_[0].fed || f_[1].fed) throw std::runtime_error("fqg_set_hash_seed after the first feed"); seed_ = seed; }
+  uint64_t collisions_walked();
   void set_sniff(int file, int fmt, int color);
   void set_line_hint(int file, uint32_t len) { if (len && !f_[file].first_seq_len) f_[file].first_seq_len = len; }
   void sniff_device(int file, const void* dptr, size_t n, uint32_t skip, int32_t* fmt, int32_t* color);
@@ -97,6 +104,7 @@ class FqEngine {
   void shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow);
   FqDevice* device() { return dev_; }
   std::string last_error;
+  uint64_t mem_stats[4] = {0, 0, 0, 0};   /* chunk bytes held, chunk bytes released, arena bytes, records that are final */
   uint64_t path_counts[4] = {0, 0, 0, 0}; /* lanes accepted, lanes handed on, fused per-record accepted, two-pass fallbacks */
 
  private:
@@ -118,6 +126,20 @@ class FqEngine {
   uint32_t shard_nsrc_ = 0; uint64_t shard_meta_start_[FQ_SHARD_MAX_SRC + 1], shard_blob_start_[FQ_SHARD_MAX_SRC];
   void scan_buffer(FqBuffer& B, bool last);
   bool finished_ = false;
+  /* Streaming (single / index loops): a chunk whose records raised no event is final — its statistics are folded into the main set,
+   * its names are in the arena, its bytes are released.  open_ turns false with the first chunk that cannot be settled; from there
+   * on everything is kept and counted in the open set, which reprocess() can clear and recount. */
+  bool streaming_ = false, open_ = false;
+  int add_depth_ = 0;
+  bool fused_lanes_ = false;                /* the fused pass that validated the chunk being added was the clean-data pass */
+  void try_settle(int file);
+  void release_buffer(FqBuffer& B);
+  void gather_segment(int file, size_t si, uint32_t nrec);
+  void set_dir(int file, size_t si);
+  void fold_open();
+  void clear_open();
+  void fetch_name(int file, uint64_t g_local, char* dst, uint32_t* len_out);
+  FqStats read_stats(int file);
   bool total0_set_ = false; uint64_t total0_ = 0; /* multi-GPU: records of file 1 over all ranks */
   uint64_t total0() const;
   const FqPackedName* claim_meta_ = nullptr; uint64_t claim_n_ = 0; const uint8_t* claim_blob_ = nullptr;

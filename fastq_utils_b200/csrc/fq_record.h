@@ -185,9 +185,9 @@ FQ_HD bool fq_compare_headers(const uint8_t* a, uint32_t alen, const uint8_t* b,
  * value itself is unobservable: equality is always confirmed on the bytes (reference: hashit + strcmp).
  * Two independent 32-bit multiplicative lanes per word (each step a bijection of its lane, so names that differ in
  * one word never collide in a lane) keep the per-word cost at five 32-bit instructions; a 64-bit finaliser mixes them. */
-typedef struct { uint32_t a, b; } FqHashState;
+typedef struct { uint32_t a, b, weak; } FqHashState;
 FQ_HD FqHashState fq_hash_init(uint32_t seed) {
-  FqHashState h; h.a = 0x85A308D3u ^ (seed * 0x9E3779B1u); h.b = 0x243F6A88u + seed * 0x85EBCA77u;
+  FqHashState h; h.a = 0x85A308D3u ^ (seed * 0x9E3779B1u); h.b = 0x243F6A88u + seed * 0x85EBCA77u; h.weak = seed & FQ_SEED_WEAK;
   return h;
 }
 FQ_HD void fq_hash_word(FqHashState* h, uint32_t w) {
@@ -200,6 +200,7 @@ FQ_HD uint64_t fq_hash_fin(FqHashState s, uint32_t len) {
   h ^= h >> 32;
   h *= 0xD6E8FEB86659FD93ull;
   h ^= h >> 32;
+  if (s.weak) h = (h & 0xFFFull) * 0x0000010000000001ull; /* the same 12 bits pick the slot and (bits 40..) the owning rank */
   return h >= FQ_HASH_SKIP ? h - 2 : h;
 }
 FQ_HD uint64_t fq_hash_name(const uint8_t* p, uint32_t len, uint32_t seed) {

@@ -107,6 +107,9 @@ typedef struct {
   uint32_t off;    /* name bytes: chunk data + off, len bytes */
   uint32_t len;
 } FqName;
+/* test mode (seed bit 31, fqg_set_hash_seed / FQG_TEST_WEAK_HASH): only 12 bits of the hash survive, so that different names with
+ * EQUAL hashes are common and the byte compare behind every equal hash (and the walk past a slot that holds another name) is exercised */
+#define FQ_SEED_WEAK 0x80000000u
 #define FQ_HASH_EMPTY 0xFFFFFFFFFFFFFFFFull
 #define FQ_HASH_SKIP 0xFFFFFFFFFFFFFFFEull
 #define FQ_KEY_NONE 0xFFFFFFFFFFFFFFFFull

@@ -52,6 +52,10 @@ typedef struct {
 #define FQG_FLAG_EXTERNAL_INDEX 2u
 /* never use the fused single-pass kernel (A/B measurements; results are identical) */
 #define FQG_FLAG_TWO_PASS 4u
+/* fqg_feed_device: the caller's buffer is borrowed for the duration of the call only (a streaming caller that refills it).
+ * Without the flag the buffer must stay valid until fqg_reset / fqg_destroy: chunks of a job in which an event fired, and all chunks
+ * of the interleaved / sorted-pair loops, are read again by fqg_finish. */
+#define FQG_FLAG_BORROW_FOR_CALL 8u
 
 /* statistics of one FASTQ_FILE as the reference holds them at the end of its loops (src/fastq.h:110-131) */
 typedef struct {
@@ -237,6 +241,12 @@ int fqg_kernel_stats_reset(fqg_ctx* ctx);
  * out[1] chunks it handed on (an anomaly: the per-record kernels decided), out[2] chunks validated by the fused per-record
  * kernel, out[3] times the job fell back to the two-pass kernels */
 int fqg_path_counts(fqg_ctx* ctx, uint64_t out[4]);
+
+/* what the job holds in device memory (since fqg_create / fqg_reset): out[0] bytes of input chunks still held (owned or borrowed),
+ * out[1] bytes of input chunks released because all their records are final, out[2] bytes of the read-name arena (the copy of each
+ * name the reference's new_indexentry keeps, src/fastq.c:590-611), out[3] records that are final, out[4] names that met a DIFFERENT
+ * name with the same 64-bit hash on their way into / through the index and walked on (src/hash.c:38-45 does the same along its chain) */
+int fqg_memory_stats(fqg_ctx* ctx, uint64_t out[5]);
 
 /* ---- synthetic inputs generated on the device (bench.py, large parity tests); see fq_synth.cu ---- */
 int fqg_synth_illumina_record_bytes(void);

@@ -7,16 +7,18 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["FQG_SIM_LIBRARY_FOR_TESTS"] = os.path.join(ROOT, "tests", "sim", "libfastq_sim.so")
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import fastq_utils_b200 as fq  # noqa: E402
+from sim_lib import use_sim_library  # noqa: E402
 from fastq_utils_b200 import dist as fqdist  # noqa: E402
 
 
 def main():
+    use_sim_library()
     cases = json.load(open(sys.argv[1]))
     dist.init_process_group("gloo")
     r, W = dist.get_rank(), dist.get_world_size()

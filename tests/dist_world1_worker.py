@@ -7,13 +7,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ["FQG_SIM_LIBRARY_FOR_TESTS"] = os.path.join(ROOT, "tests", "sim", "libfastq_sim.so")
 
 import torch  # noqa: E402
 
 import fastq_utils_b200 as fq  # noqa: E402
+from sim_lib import use_sim_library  # noqa: E402
 from fastq_utils_b200 import dist as fqdist  # noqa: E402
 from _util import oracle_run  # noqa: E402
+
+use_sim_library()
 
 big = [f"@M0:1:FC:1:11:{i}:{i * 7} 1:N:0:AC\n{'ACGTN' * (3 + i % 5)}\n+\n{'F' * (5 * (3 + i % 5))}\n" for i in range(4000)]
 dup = list(big); dup[3900] = dup[17]

@@ -129,13 +129,13 @@ class FqSimDevice : public FqDevice {
         FqSlot& s = a.slots[i];
         if (s.hash == FQ_HASH_EMPTY) { s.hash = nm.hash; s.idx1 = g; break; }
         if (s.hash != nm.hash) continue;
-        uint64_t old = s.idx1; if (g < old) s.idx1 = g;
+        uint64_t old = s.idx1;
         uint32_t ol; const uint8_t* on = name_of(a.dir1, a.ndir1, old, &ol);
-        if (ol == nm.len && fq_bytes_equal(on, a.data + nm.off, nm.len)) {
-          uint64_t later = old > g ? old : g;
-          uint64_t key = FQ_KEY(a.step_base + later, FQ_R_NAME);
-          if (key < *a.key) *a.key = key;
-        } else a.counters[0]++;
+        if (!(ol == nm.len && fq_bytes_equal(on, a.data + nm.off, nm.len))) { a.counters[4]++; continue; } /* another name with this hash: next slot */
+        if (g < old) s.idx1 = g;
+        uint64_t later = old > g ? old : g;
+        uint64_t key = FQ_KEY(a.step_base + later, FQ_R_NAME);
+        if (key < *a.key) *a.key = key;
         break;
       }
     }
@@ -155,7 +155,7 @@ class FqSimDevice : public FqDevice {
           else if (s.hash != nm.hash) continue;
           else {
             uint32_t ol; const uint8_t* on = name_of(a.dir1, a.ndir1, s.idx1, &ol);
-            if (!(ol == nm.len && fq_bytes_equal(on, a.data + nm.off, nm.len))) { a.counters[0]++; break; }
+            if (!(ol == nm.len && fq_bytes_equal(on, a.data + nm.off, nm.len))) continue; /* another name with this hash: the lookup walks on */
             uint64_t old = s.claim2; if (g < old) s.claim2 = g;
             if (old == FQ_IDX_NONE) a.counters[1]++;
             else unpaired = old > g ? old : g;
@@ -212,14 +212,14 @@ class FqSimDevice : public FqDevice {
         FqSlot& s = a.slots[i];
         if (s.hash == FQ_HASH_EMPTY) { s.hash = pn.hash; s.idx1 = mine; break; }
         if (s.hash != pn.hash) continue;
-        unsigned long long old = s.idx1; if (mine < old) s.idx1 = mine;
+        unsigned long long old = s.idx1;
         if (!a.blob) { a.counters[0]++; break; } /* tuples only: an equal hash cannot be judged here */
         uint32_t ol, ml; const uint8_t* on = shard_name(a, old & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
-        if (ol == ml && fq_bytes_equal(on, mn, ml)) {
-          unsigned long long later = std::max(old >> FQ_SHARD_POS_BITS, (unsigned long long)pn.record);
-          unsigned long long key = FQ_KEY(later, FQ_R_NAME);
-          if (key < *a.dup_key) *a.dup_key = key;
-        } else a.counters[0]++;
+        if (!(ol == ml && fq_bytes_equal(on, mn, ml))) { a.counters[4]++; continue; } /* another name with this hash: next slot */
+        if (mine < old) s.idx1 = mine;
+        unsigned long long later = std::max(old >> FQ_SHARD_POS_BITS, (unsigned long long)pn.record);
+        unsigned long long key = FQ_KEY(later, FQ_R_NAME);
+        if (key < *a.dup_key) *a.dup_key = key;
         break;
       }
     }
@@ -236,7 +236,7 @@ class FqSimDevice : public FqDevice {
         if (s.hash == FQ_HASH_EMPTY) { unpaired = pn.record; break; }
         if (s.hash != pn.hash) continue;
         uint32_t ol, ml; const uint8_t* on = shard_name(ins, s.idx1 & posmask, &ol); const uint8_t* mn = shard_name(a, m, &ml);
-        if (!(ol == ml && fq_bytes_equal(on, mn, ml))) { a.counters[0]++; break; }
+        if (!(ol == ml && fq_bytes_equal(on, mn, ml))) continue; /* another name with this hash: the lookup walks on */
         unsigned long long old = s.claim2; if (pn.record < old) s.claim2 = pn.record;
         if (old == FQ_IDX_NONE) a.counters[1]++;
         else unpaired = old > pn.record ? old : pn.record;
@@ -315,6 +315,33 @@ class FqSimDevice : public FqDevice {
   void shard_find(const FqPackedName* meta, unsigned long long n, unsigned long long record, unsigned long long* out_pos) override {
     n_launch_++;
     for (unsigned long long m = 0; m < n; m++) if (meta[m].record == record && m < *out_pos) *out_pos = m;
+  }
+  void names_measure(const FqName* names, uint32_t nrec, unsigned long long* out_units) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < nrec; k++) if (names[k].hash != FQ_HASH_SKIP) *out_units += (names[k].len + 15u) >> 4;
+  }
+  void names_gather(FqName* names, const uint8_t* data, uint32_t nrec, uint8_t* arena, unsigned long long* cursor_units) override {
+    n_launch_++;
+    for (uint32_t k = nrec; k-- > 0;) { /* (backwards: the order of the copies is free, and tests must not rely on it) */
+      FqName& nm = names[k];
+      if (nm.hash == FQ_HASH_SKIP || nm.len == 0) continue;
+      uint32_t units = (nm.len + 15u) >> 4;
+      unsigned long long at = *cursor_units * 16ull; *cursor_units += units;
+      memset(arena + at, 0, (size_t)units * 16); memcpy(arena + at, data + nm.off, nm.len);
+      nm.off = (uint32_t)at;
+    }
+  }
+  void stats_fold(FqStats* const m2[2], FqStats* const o2[2], unsigned long long* const h2[2], unsigned long long* const ho2[2]) override {
+    n_launch_++;
+    uint32_t lo = std::min(o2[0]->min_rl, o2[1]->min_rl), hi = std::min<uint32_t>(std::max(o2[0]->max_rl, o2[1]->max_rl), FQ_MAX_READ_LENGTH - 1);
+    for (int f = 0; f < 2; f++) {
+      if (lo <= hi) for (uint32_t l = lo; l <= hi; l++) { h2[f][l] += ho2[f][l]; ho2[f][l] = 0; }
+      FqStats* m = m2[f]; FqStats* o = o2[f];
+      m->num_rds += o->num_rds; m->mem_sum += o->mem_sum; m->n_names += o->n_names;
+      m->min_rl = std::min(m->min_rl, o->min_rl); m->max_rl = std::max(m->max_rl, o->max_rl);
+      m->min_q = std::min(m->min_q, o->min_q); m->max_q = std::max(m->max_q, o->max_q);
+      o->num_rds = 0; o->mem_sum = 0; o->n_names = 0; o->min_rl = 0xFFFFFFFFu; o->max_rl = 0; o->min_q = 255u; o->max_q = 0;
+    }
   }
   void explain(const uint8_t* data, const FqLine* lines4, const FqRecCtx& cx, FqRecOut* out) override {
     n_launch_++;

@@ -75,11 +75,12 @@ def test_gpu_reader_tools_count_large_streams():
 
 def test_python_binding_of_the_reader_tools(tmp_path):
     """fastq_utils_b200.reader_tool and FastqInfo(MODE_READER) (api.py) over the stand-in device, in a process of its own (the
-    library is chosen at import time)."""
+    stand-in is put behind the binding by tests/sim_lib.py)."""
     import subprocess
     import sys
     code = (
         "import fastq_utils_b200 as fq\n"
+        "from sim_lib import use_sim_library; use_sim_library()\n"
         "d = b''.join(b'@r%d\\nACGT\\n+\\nIIII\\n' % i for i in range(7)) + b'@x\\nAC*T\\n+\\nII\\n'\n"  # the last record would not validate
         "assert fq.reader_tool('fastq_num_reads', ['a.fq'], d) == (0, '8\\n', 'fastq_utils 0.25.3\\n')\n"
         "assert fq.reader_tool('fastq_not_empty', ['a.fq'], d) == (0, '', '')\n"
@@ -92,7 +93,7 @@ def test_python_binding_of_the_reader_tools(tmp_path):
         "assert n == 8 and starts == want[:8], (n, starts, want)\n"
         "assert h.index_records(d[:-1], cap=4) == (8, want[:4]) and h.index_records(d[:-3], cap=0) == (7, [])\n"  # a last line without LF counts
         "print('ok')\n")
-    env = dict(os.environ, FQG_SIM_LIBRARY_FOR_TESTS=os.path.join(ROOT, "tests", "sim", "libfastq_sim.so"), PYTHONPATH=ROOT)
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "tests"))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
 
