@@ -77,7 +77,7 @@ __device__ __forceinline__ void st_volatile64(unsigned long long* p, unsigned lo
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 fq_scan_kernel(const uint8_t* __restrict__ data, uint32_t n, int virtual_end, uint32_t* __restrict__ line_end, uint32_t cap,
-               unsigned long long* tile_state, uint32_t* ticket, uint32_t ntiles, uint32_t* out2) {
+               unsigned long long* tile_state, uint32_t* ticket, uint32_t ntiles, uint32_t* out2, uint32_t lead) {
   __shared__ uint32_t s_tile, s_warp_tot[SCAN_WARPS], s_warp_base[SCAN_WARPS], s_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u); /* tiles are claimed in order: look-back never waits on an unscheduled CTA */
@@ -92,6 +92,7 @@ fq_scan_kernel(const uint8_t* __restrict__ data, uint32_t n, int virtual_end, ui
     if (off < n) { /* the allocation is readable 64 bytes past n */
       m[i] = lf_mask16(ld_stream16(data + off));
       if (n - off < 16) m[i] &= (1u << (n - off)) - 1u;
+      if (off == 0) m[i] &= ~((1u << lead) - 1u); /* the first `lead` (< 16) bytes are not the chunk's own */
     }
   }
   /* inclusive prefix over the warp's four rows, two 16-bit counters per register */
@@ -1022,7 +1023,7 @@ class FqCudaDevice : public FqDevice {
     for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& d : deferred_) cudaEventDestroy(d.ready);
     for (auto e : free_ev_) cudaEventDestroy(e);
-    cudaFree(tile_state_);
+    cudaFree(tile_state_); if (stage_) cudaFree(stage_);
     cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_); cudaEventDestroy(ev_pre_);
     cudaStreamDestroy(st_); cudaStreamDestroy(st2_);
   }
@@ -1059,14 +1060,14 @@ class FqCudaDevice : public FqDevice {
   }
   void kernel_stats_reset() override { collect(); for (auto& k : kst_) k = KStat(); }
 
-  void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) override {
+  void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2, uint32_t lead = 0) override {
     uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (ntiles == 0) { FQ_CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(uint32_t), st_)); return; }
     if (ntiles > max_tiles_) throw std::runtime_error("scan_lines: chunk larger than 2 GiB (n=" + std::to_string(n) + ")");
     FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));
     FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
     tic(FQG_K_SCAN, n, ntiles);
-    fq_scan_kernel<<<ntiles, SCAN_THREADS, 0, st_>>>(data, n, virtual_end, line_end, cap, tile_state_, ticket_, ntiles, out2);
+    fq_scan_kernel<<<ntiles, SCAN_THREADS, 0, st_>>>(data, n, virtual_end, line_end, cap, tile_state_, ticket_, ntiles, out2, lead);
     toc();
     launched();
   }
@@ -1128,7 +1129,8 @@ class FqCudaDevice : public FqDevice {
     flush_deferred();
     return true;
   }
-  bool lanes_pass(const FqTileArgs& a) override {
+  bool lanes_pass(const FqTileArgs& a, bool* self_judged) override {
+    *self_judged = false;
     if (!a.n) return false;
     if ((uintptr_t)a.data & 15u) return false; /* bulk copies need a 16-byte aligned source (the engine aligns what it is fed) */
     /* short lines (they must end within the 1 KiB margin): one thread per line; anything longer: chunk-parallel */
@@ -1151,8 +1153,11 @@ class FqCudaDevice : public FqDevice {
     P.data = a.data; P.lead = a.lead; P.n = a.n; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
     P.tile_state = tile_state_; P.ticket = ticket_; P.ntiles = ntiles; P.out = a.out5;
     P.j0 = a.j0; P.cx = a.cx; P.names = a.names; P.names_cap = a.names_cap;
+    if (!stage_) FQ_CUDA_CHECK(cudaMalloc(&stage_, sizeof(LanesStage)));
+    P.stage = stage_; P.arena = lines_mode ? a.arena : nullptr; P.arena_units = a.arena_units;
     { const char* e = getenv("FQG_LANES_TUNE"); P.tune = e ? (uint32_t)atoi(e) : 0u; }
     FQ_CUDA_CHECK(cudaEventRecord(ev_pre_, st_));
+    if (lines_mode) FQ_CUDA_CHECK(cudaMemsetAsync(stage_, 0, sizeof(LanesStage), st_));
     FQ_CUDA_CHECK(cudaMemsetAsync(tile_state_, 0, (size_t)ntiles * sizeof(unsigned long long), st_));
     FQ_CUDA_CHECK(cudaMemsetAsync(ticket_, 0, sizeof(uint32_t), st_));
     int grid = (int)std::min<uint32_t>(ntiles, (uint32_t)lanes_blocks_);
@@ -1160,7 +1165,13 @@ class FqCudaDevice : public FqDevice {
     if (lines_mode) fq_lanes_kernel<true><<<grid, LN_THREADS, LN_SMEM, st_>>>(P);
     else fq_lanes_kernel<false><<<grid, LN_THREADS, LN_SMEM, st_>>>(P);
     toc(); launched();
-    lanes_records(a, false);
+    if (lines_mode) { /* the pass judged the records itself: one block turns what it staged into statistics if the chunk is clean */
+      LanesPostParams R;
+      R.out = a.out5; R.line_end = a.line_end; R.stage = stage_; R.j0 = a.j0; R.cx = a.cx; R.stats = a.stats; R.stats_range = a.stats_range; R.hist = a.hist;
+      fq_lanes_post_kernel<<<1, 1024, 0, st_>>>(R);
+      launched();
+      *self_judged = true;
+    } else lanes_records(a, false);
     flush_deferred(); /* the previous chunk's inserts run beside this pass */
     return true;
   }
@@ -1382,6 +1393,7 @@ class FqCudaDevice : public FqDevice {
   cudaEvent_t ev_pre_ = nullptr; /* main stream just before the latest clean-data pass: what the side stream waits for when it works beside that pass */
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;
+  LanesStage* stage_ = nullptr;
   unsigned long long n_launch_ = 0;
 };
 

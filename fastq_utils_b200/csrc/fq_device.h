@@ -75,9 +75,12 @@ typedef struct {
   FqStats* stats; FqStats* stats_range; unsigned long long* hist; unsigned long long* key; FqName* names; uint32_t names_cap;
   uint32_t hint_line_len;    /* length of the file's first sequence line (0 = unknown): picks the clean-data pass's mode */
   uint32_t lead;             /* clean-data pass only: the first `lead` (< 16) bytes of data[] are not the chunk's (offsets still count from data) */
+  uint8_t* arena;            /* clean-data pass, per-line mode: block for the names' bytes (names[k].off then points in here); NULL: names stay chunk-relative */
+  uint32_t arena_units;      /* its capacity in 16-byte units: a pass that needs more hands the chunk on (capacity anomaly) */
 } FqTileArgs;
 
-#define FQ_LANES_OUT_WORDS 24 /* [16..23]: the last 8 line ends of the chunk (fewer when it has fewer lines) */
+#define FQ_LANES_OUT_WORDS 32 /* [16..23]: the last 8 line ends of the chunk (fewer when it has fewer lines); [24] arena units used, [25] the per-line
+                               * pass accepted the chunk AND committed its statistics, [26] first line whose end the last tiles stored, [27] records staged */
 class FqDevice {
  public:
   virtual ~FqDevice() {}
@@ -97,7 +100,7 @@ class FqDevice {
   virtual void sync_main() { sync(); }
   /* K1: exclusive end offsets of all lines of data[0,n) in order; a last line without LF counts when virtual_end.
    * out[0] = number of lines, out[1] = 1 if more than cap were found (only the first cap are stored). */
-  virtual void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) = 0;
+  virtual void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2, uint32_t lead = 0) = 0; /* lead (< 16): bytes in front that are not the chunk's own */
   /* number of LF bytes in data[0,n): *out += count (64-bit) */
   virtual void count_lines(const uint8_t* data, uint32_t n, unsigned long long* out) = 0;
   /* first line i in [j0, j0+nlines) whose raw length reaches the gzgets limit of its phase ((i-j0)&3); *out = min(*out, i) */
@@ -117,7 +120,9 @@ class FqDevice {
    * line, [3] anomaly bits of the pass, [4] internal error, [5] index of a final line without LF, [6..9] staged min/max of
    * quality and read length, [10] a record broke a length rule.  The counters / histogram are committed by the pass itself
    * when [1..4] are clear; lanes_commit(undo=false) folds the staged min/max in, lanes_commit(undo=true) takes the counters back. */
-  virtual bool lanes_pass(const FqTileArgs& a) { (void)a; return false; }
+  /* *self_judged: the per-line mode ran — records, statistics and the commit are the pass's own business: out5[25] says whether the
+   * chunk was accepted (then everything is in place, names in a.arena), no lanes_commit in either case */
+  virtual bool lanes_pass(const FqTileArgs& a, bool* self_judged) { (void)a; (void)self_judged; return false; }
   virtual void lanes_commit(const FqTileArgs& a, bool undo) { (void)a; (void)undo; }
   /* K3: index insert (file 1) / K4: mate claim (file 2) / pair compare (interleaved, sorted) */
   virtual void index_insert(const FqTableArgs& a) = 0;

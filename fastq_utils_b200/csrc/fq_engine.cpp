@@ -18,6 +18,7 @@ static const size_t kMaxChunk = 1ull << 31;      /* bytes per chunk: offsets are
  * bridges and every starting phase are reached with small inputs */
 static size_t feed_chunk() { const char* e = getenv("FQG_MAX_CHUNK_BYTES"); size_t v = e ? strtoull(e, nullptr, 10) & ~(size_t)15 : 0; return v >= 4096 && v < kMaxChunk ? v : kMaxChunk; }
 static const uint32_t kNone32 = 0xFFFFFFFFu;
+static const double kLanesTile = 31744.0;        /* bytes of a tile of the per-line clean-data pass (fq_lanes.cuh: LS_TILE): sizes the arena */
 /* device words: [0] equal hashes that tuples alone could not judge, [1] claimed by the mate loop, [2] table full, [3] the owner's earliest
  * name event, [4] names that met ANOTHER name with their hash (diagnostics), [5] units measured for an arena, [6] arena cursor */
 static const int kCounters = 8;
@@ -184,7 +185,7 @@ void FqEngine::realign(FqBuffer& B) {
 void FqEngine::ensure_full_index(FqBuffer& b) {
   if (!b.index_partial) return;
   uint32_t cap = b.n / 32 + 4096; /* the capacity the fused pass allocated and did not overflow */
-  dev_->scan_lines(b.data, b.n, b.index_virtual_end ? 1 : 0, b.line_end, cap, scratch_);
+  dev_->scan_lines(b.data, b.n, b.index_virtual_end ? 1 : 0, b.line_end, cap, scratch_, b.lead);
   dev_->sync();
   b.index_partial = false;
 }
@@ -251,7 +252,7 @@ bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip
       dev_->sniff(data, h, q, (int32_t*)scratch_);
       int32_t o2[2]; dev_->download(o2, scratch_, sizeof o2);
       F.sniff_fmt = o2[0]; F.sniff_color = o2[1];
-      F.first_seq_len = q.len;
+      F.first_seq_len = q.len; F.first_hdr_len = h.len;
       ok = true;
     }
   }
@@ -284,9 +285,24 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
    * below decide (they own the reference's first-error semantics). */
   if (lanes_ok_ && !skip_lanes && a.cx.space != FQ_SPACE_COLOR) {
-    uint32_t linit[FQ_LANES_OUT_WORDS] = {0, 0, kNone32, 0, 0, kNone32, kNone32, 0, kNone32, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t linit[FQ_LANES_OUT_WORDS]; memset(linit, 0, sizeof linit);
+    linit[2] = kNone32; linit[5] = kNone32; linit[6] = kNone32; linit[8] = kNone32;
     dev_->upload(tile_out_, linit, sizeof linit);
-    if (dev_->lanes_pass(a)) {
+    /* room for the names of the chunk (the per-line mode of the pass copies them out of the window itself): what the chunks before
+     * it needed per byte and a quarter more; a pass that runs out of room hands the chunk on like any other anomaly */
+    uint8_t* arena = nullptr; uint64_t arena_units = 0;
+    if (names) {
+      double rate = F.arena_rate;
+      if (rate <= 0 && F.first_hdr_len >= 3 && F.first_seq_len) rate = 1.2 * (double)((F.first_hdr_len - 2 + 15) >> 4) / (double)(F.first_hdr_len + 2.0 * F.first_seq_len + 2);
+      if (rate <= 0) rate = 1.0 / 64;
+      /* (every tile of the pass gets the same stretch of the block: what the fullest tile needed so far, a quarter more, and a little) */
+      const uint64_t ntiles = ((uint64_t)B.n + (uint64_t)kLanesTile - 1) / (uint64_t)kLanesTile;
+      arena_units = std::min<uint64_t>(((uint64_t)(rate * 1.25 * kLanesTile) + 16) * ntiles, (1ull << 28) - 1);
+      arena = (uint8_t*)dev_->alloc((size_t)arena_units * 16 + kPad);
+    }
+    a.arena = arena; a.arena_units = (uint32_t)arena_units;
+    bool self_judged = false;
+    if (dev_->lanes_pass(a, &self_judged)) {
       if (hook_) { /* the pass is running: the caller routes the names of the chunks before this one beside it */
         in_beside_hook_ = true; hook_fired_ = true;
         try { hook_(hook_user_, file); } catch (...) { in_beside_hook_ = false; throw; }
@@ -295,20 +311,28 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
       uint32_t o[FQ_LANES_OUT_WORDS];
       dev_->download(o, tile_out_, sizeof o);
       bool pass_ok = !o[1] && o[2] == kNone32 && !o[3] && !o[4];
-      if (getenv("FQG_DEBUG")) fprintf(stderr, "[fqg] clean-data pass: n=%u j0=%u lines=%u capovf=%u overlong=%u anomaly=0x%x internal=%u virt=%u q=%u..%u rl=%u..%u recbad=%u | polls=%u lookback_rounds=%u waited=%u\n",
-                                       B.n, j0, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10], o[11], o[12], o[13]);
-      if (pass_ok && !o[10]) {
-        dev_->lanes_commit(a, false);
+      if (getenv("FQG_DEBUG")) fprintf(stderr, "[fqg] clean-data pass: n=%u j0=%u lines=%u capovf=%u overlong=%u anomaly=0x%x internal=%u virt=%u q=%u..%u rl=%u..%u recbad=%u | polls=%u lookback_rounds=%u waited=%u | arena %u of %llu units, accepted=%u, staged=%u\n",
+                                       B.n, j0, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10], o[11], o[12], o[13], o[24], (unsigned long long)arena_units, o[25], o[27]);
+      bool accepted = self_judged ? o[25] != 0 : (pass_ok && !o[10]);
+      if (accepted) {
+        if (!self_judged) dev_->lanes_commit(a, false);
         path_counts[0]++; fused_lanes_ = true;
-        B.nlines = o[0]; B.index_partial = false; B.index_virtual_end = last;
+        B.nlines = o[0]; B.index_partial = self_judged; B.index_from = self_judged ? o[26] : 0; B.index_virtual_end = last;
         B.tail_from = o[0] > 8 ? o[0] - 8 : 0; B.tail_n = o[0] - B.tail_from;
         for (uint32_t i = 0; i < B.tail_n; i++) B.tail_ends[i] = o[16 + i];
+        if (self_judged && arena) {
+          fused_arena_ = arena; mem_stats[2] += arena_units * 16;
+          F.arena_rate = std::max(F.arena_rate, (double)o[24] / kLanesTile); /* (the fullest tile's units: every tile gets the same stretch) */
+        } else if (arena) dev_->release(arena);
         *names_out = names; *names_cap = ncap;
         return true;
       }
       path_counts[1]++;
-      if (pass_ok) dev_->lanes_commit(a, true); /* counters went in before a record broke a length rule: take them back */
+      if (!self_judged && pass_ok) dev_->lanes_commit(a, true); /* counters went in before a record broke a length rule: take them back */
+      if (self_judged && (o[3] & 16u) && arena) F.arena_rate = std::max(F.arena_rate, 1.5 * (double)o[24] / kLanesTile); /* (perhaps) ran out of arena: what the fullest tile asked for, and half as much again */
     } else dev_->sync();
+    if (arena) dev_->release(arena);
+    a.arena = nullptr; a.arena_units = 0;
   }
   if (B.lead) { /* the per-record kernels want the chunk's data at offset 0: the caller copies it and comes back */
     if (names) dev_->release(names);
@@ -426,15 +450,17 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
         uint32_t end = line_end_at(F.bufs[b], j - 1);
         s.span = end - pos; pos = end;
         s.g0 = F.nrec; F.nrec += nrec; s.names = fused_names; s.lanes = fused_lanes_;
+        s.arena = fused_arena_; fused_arena_ = nullptr; /* the per-line mode of the clean-data pass put the names there itself */
         F.segs.push_back(s);
-        gather_segment(file, F.segs.size() - 1, nrec);
+        if (s.arena) set_dir(file, F.segs.size() - 1); else gather_segment(file, F.segs.size() - 1, nrec);
         launch_names(file, F.segs.size() - 1, nrec);
-      } else if (fused_names) dev_->release(fused_names);
+      } else { if (fused_names) dev_->release(fused_names); if (fused_arena_) { dev_->release(fused_arena_); fused_arena_ = nullptr; } }
       segmentize(file, b, pos, j, last); /* what is left: fewer than four lines (over-long check, pending bytes / end of file) */
       return;
     }
     /* the bridge did not behave as assumed (over-long lines around the chunk boundary): discard the fused results */
     if (fused_names) dev_->release(fused_names);
+    if (fused_arena_) { dev_->release(fused_arena_); fused_arena_ = nullptr; }
     fused_fallback();
   }
   segmentize(file, b, pos, j, last);

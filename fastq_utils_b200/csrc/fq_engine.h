@@ -56,6 +56,8 @@ struct FqFile {
   std::vector<FqTailLine> tail_lines;
   int sniff_fmt = -1, sniff_color = -1;
   uint32_t first_seq_len = 0; /* raw length of the first record's sequence line (0: not seen by this context) */
+  uint32_t first_hdr_len = 0; /* ... and of its header line */
+  double arena_rate = 0;      /* 16-byte arena units per input byte the chunks so far needed (sizes the next chunk's block) */
   FqStats* stats = nullptr; unsigned long long* hist = nullptr; /* device: records that are final */
   FqStats* stats_open = nullptr; unsigned long long* hist_open = nullptr; /* device: records a later event may still exclude */
   size_t n_settled = 0;     /* segments [0, n_settled) are final */
@@ -131,6 +133,7 @@ class FqEngine {
    * on everything is kept and counted in the open set, which reprocess() can clear and recount. */
   bool streaming_ = false, open_ = false;
   int add_depth_ = 0;
+  uint8_t* fused_arena_ = nullptr;          /* ... and it put the names of the chunk into this block */
   bool fused_lanes_ = false;                /* the fused pass that validated the chunk being added was the clean-data pass */
   void try_settle(int file);
   void release_buffer(FqBuffer& B);

@@ -37,7 +37,10 @@ constexpr int LN_LMAX = 2048;                 /* line ends kept per tile */
 constexpr int LN_SMAX = 256;                  /* header lines (name descriptors) staged per tile */
 constexpr int LN_OFF_MASK = LN_WIN;
 constexpr int LN_OFF_PURE = LN_OFF_MASK + LN_CHUNKS * 2;
-constexpr int LN_OFF_LEND = LN_OFF_PURE + LN_CHUNKS * 2;      /* two buffers: the line ends of a tile are written out one round later */
+constexpr int LN_OFF_LEND = LN_OFF_PURE + LN_CHUNKS * 2;      /* chunk-parallel mode: two buffers (the line ends of a tile are written out one round later);
+                                                                 per-line mode: one buffer, then the CTA's read-length histogram (lengths below LS_HBINS) */
+constexpr int LS_HBINS = LN_LMAX * 2 / 4;                     /* 1024 bins of 32 bits in the second buffer's place */
+constexpr int LS_STAGE_HIST = 36864;                          /* bins of the chunk's staged histogram: a line of the per-line mode lies inside one window */
 constexpr int LN_OFF_STAGE = LN_OFF_LEND + 2 * LN_LMAX * 2;
 constexpr int LN_OFF_LUT = LN_OFF_STAGE + LN_SMAX * 16;
 constexpr int LN_SMEM = LN_OFF_LUT + 32 * 16;
@@ -47,7 +50,18 @@ static_assert(LN_WIN % 16 == 0 && LN_OFF_LEND % 16 == 0 && LN_OFF_PURE % 16 == 0
 
 /* anomaly bits (out[3]) */
 enum { LN_A_BASE = 1, LN_A_QUAL = 2, LN_A_HEADER = 4, LN_A_PLUS = 8, LN_A_CAPACITY = 16, LN_A_PHASE = 32 };
+/* what a per-line pass found, staged per chunk (zeroed before the launch) and folded into the file statistics by fq_lanes_post_kernel
+ * only when the WHOLE chunk turned out clean: nothing of a chunk that is handed on to the per-record kernels is ever counted */
+struct LanesStage {
+  unsigned long long nrec;       /* complete records that keep the length rules */
+  unsigned long long mem;        /* sum of the `len` fastq_get_readname reports for them (index_mem, src/fastq.c:609) */
+  unsigned int rl_min_inv, rl_max; /* ~minimum and maximum of the read length (terminator included) */
+  unsigned int arena_used;       /* 16-byte units of the name arena the fullest tile asked for */
+  unsigned int pad;
+  unsigned int hist[LS_STAGE_HIST];
+};
 /* out words */
+enum { LN_O_ARENA_USED = 24, LN_O_ACCEPT = 25, LN_O_INDEX_FROM = 26, LN_O_STAGED = 27 };
 enum { LN_O_LINES = 0, LN_O_CAPOVF = 1, LN_O_OVERLONG = 2, LN_O_ANOMALY = 3, LN_O_INTERNAL = 4, LN_O_VIRTUAL = 5, LN_O_QMIN = 6, LN_O_QMAX = 7,
        LN_O_RLMIN = 8, LN_O_RLMAX = 9, LN_O_RECBAD = 10, LN_O_SPINS = 11 /* diagnostics: polls of unpublished tile states */,
        LN_O_ROUNDS = 12 /* look-back rounds */, LN_O_WAITED = 13 /* tiles that had to wait for the sum before their scans */, LN_O_WORDS = 16 };
@@ -59,6 +73,8 @@ struct LanesParams {
   unsigned long long* tile_state; uint32_t* ticket; uint32_t ntiles;
   uint32_t* out;
   uint32_t j0; FqRecCtx cx; FqName* names; uint32_t names_cap;
+  LanesStage* stage;   /* per-line mode */
+  uint8_t* arena; uint32_t arena_units; /* per-line mode: where the names go (16-byte units); NULL: the names stay in the chunk */
   uint32_t tune; /* experiment switch (FQG_LANES_TUNE): 1 = no L2 prefetch of the next tile */
 };
 
@@ -216,13 +232,22 @@ fq_lanes_kernel(const LanesParams P) {
   uint4* lut = (uint4*)(smem + LN_OFF_LUT);           /* [lo] bytes >= lo, [16 + h] bytes <= h */
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_next, s_fbase, s_fstate, s_w1[LN_WARPS], s_w3[LN_WARPS], s_w4[LN_WARPS];
+  __shared__ uint32_t s_cnt, s_mem, s_rlmin, s_rlmax;  /* per-line mode: this CTA's records, index_mem bytes, read lengths */
+  __shared__ uint32_t s_arena;                           /* per-line mode: arena units handed out to the names of the current tile */
+  uint32_t* s_hist = (uint32_t*)(smem + LN_OFF_LEND + LN_LMAX * 2); /* per-line mode: records by read length (below LS_HBINS) */
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = smem_u32(&s_bar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_next = atomicAdd(P.ticket, 1u);
+    s_cnt = 0; s_mem = 0; s_rlmin = 0xFFFFFFFFu; s_rlmax = 0; s_arena = 0;
   }
+  /* every tile has its own stretch of the arena (no global cursor: an atomic with a return value in a header group's path costs a
+   * round trip to L2, and several when the index kernel beside the pass keeps the atomic units busy) */
+  const uint32_t arena_stride = P.arena ? P.arena_units / P.ntiles : 0u;
+  uint32_t arena_max = 0;
+  if (LINES) for (int l = threadIdx.x; l < LS_HBINS; l += LN_THREADS) s_hist[l] = 0;
   if (tid < 32) {
     uint32_t w[4];
 #pragma unroll
@@ -251,6 +276,7 @@ fq_lanes_kernel(const LanesParams P) {
     const uint32_t tile = s_next;
     const bool active = tile < P.ntiles;
     const unsigned long long t0 = (unsigned long long)tile * TILE;
+    if (LINES && tid == 0) { arena_max = max(arena_max, s_arena); s_arena = 0; } /* (the barrier of phase B lies between this and the header groups) */
     if (active && tid == 0) {
       unsigned long long src = tile ? t0 - LN_LEFT : 0;
       uint32_t dst_off = tile ? 0 : LN_LEFT;
@@ -286,10 +312,12 @@ fq_lanes_kernel(const LanesParams P) {
         if (p_no_final_lf) { if (cnt < P.cap) P.line_end[cnt] = P.n; P.out[LN_O_VIRTUAL] = cnt; cnt++; }
         P.out[LN_O_LINES] = cnt; P.out[LN_O_CAPOVF] = cnt > P.cap ? 1u : 0u;
       }
-      const uint16_t* pl = lend2 + (buf ^ 1u) * LN_LMAX;
-      const uint32_t gofs = (uint32_t)((unsigned long long)p_tile * TILE - LN_LEFT); /* window offset → offset inside the chunk */
-      if (p_cnt <= (uint32_t)LN_LMAX)
-        for (uint32_t r = tid; r < p_cnt; r += LN_THREADS) { const uint32_t gi = base + r; if (gi < P.cap) P.line_end[gi] = gofs + pl[r]; }
+      if (!LINES) { /* (the per-line mode judges the records itself: nobody reads its line index but the host, who wants the chunk's first and last lines) */
+        const uint16_t* pl = lend2 + (buf ^ 1u) * LN_LMAX;
+        const uint32_t gofs = (uint32_t)((unsigned long long)p_tile * TILE - LN_LEFT); /* window offset → offset inside the chunk */
+        if (p_cnt <= (uint32_t)LN_LMAX)
+          for (uint32_t r = tid; r < p_cnt; r += LN_THREADS) { const uint32_t gi = base + r; if (gi < P.cap) P.line_end[gi] = gofs + pl[r]; }
+      }
       if (P.names) {
         /* record of a staged name: its number inside the tile plus the records in front of the tile; names of the record cut
          * by the start of the chunk (lines before j0) get a negative number and are dropped */
@@ -313,7 +341,7 @@ fq_lanes_kernel(const LanesParams P) {
     const uint32_t ns = min(left, (uint32_t)SCAN);      /* valid bytes of the scanned range */
     const uint32_t nloc = LN_LEFT + left;               /* window offsets below this hold data */
     const bool full = ns == (uint32_t)SCAN;
-    uint16_t* lend = lend2 + buf * LN_LMAX;
+    uint16_t* lend = LINES ? lend2 : lend2 + buf * LN_LMAX;
     {
       uint32_t spins = 0;
       while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 24)) { if (tid == 0) atomicExch(P.out + LN_O_INTERNAL, 1u); break; } }
@@ -440,7 +468,7 @@ fq_lanes_kernel(const LanesParams P) {
         if (tid == 0) st_volatile64(P.tile_state, ST_INCL | (unsigned long long)cntT);
         have_base = true;
         phi = (4u - P.j0) & 3u;
-      } else if (votes == 1u) phi = w0 ? 1u : w1 ? 0u : w2 ? 3u : 2u; /* k = 1, 5, .. → 1;  k = 2, 6, .. → 0;  k = 3, .. → 3;  k = 4, .. → 2 */
+      } else if (votes == 1u && !(LINES && tile + 2u >= P.ntiles)) phi = w0 ? 1u : w1 ? 0u : w2 ? 3u : 2u; /* k = 1, 5, .. → 1;  k = 2, 6, .. → 0;  k = 3, .. → 3;  k = 4, .. → 2 */
       else { /* no witness (long lines, or plus lines that repeat the name), or witnesses that disagree: wait for the sum now */
         __syncthreads(); /* the look-back scratch may still be read by the previous tile's look-back */
         if (tid == 0) atomicAdd(P.out + LN_O_WAITED, 1u);
@@ -449,6 +477,14 @@ fq_lanes_kernel(const LanesParams P) {
         have_base = true;
         phi = (base_line + 4u - P.j0) & 3u;
       }
+    }
+    if (LINES && (tile == 0 || tile + 2u >= P.ntiles) && !too_many) {
+      /* the host wants the first and the last line ends of the chunk (where its first record starts, where the last complete one
+       * ends): these tiles know the lines in front of them already and write their line ends out themselves */
+      const uint32_t gofs = (uint32_t)(t0 - LN_LEFT);
+      const bool all = tile + 2u >= P.ntiles;
+      for (uint32_t r = tid; r < cntT; r += LN_THREADS) { const uint32_t gi = base_line + r; if (gi < P.cap && (all || gi < 8u)) P.line_end[gi] = gofs + lend[r]; }
+      if (tid == 0 && (tile + 2u == P.ntiles || P.ntiles == 1u)) P.out[LN_O_INDEX_FROM] = base_line;
     }
     /* line numbers relative to the tile: class = number & 3, record of the tile = (number >> 2) - 1 */
     const uint32_t gbr = 4u + phi;
@@ -480,30 +516,92 @@ fq_lanes_kernel(const LanesParams P) {
           const uint32_t i = 32 * (cls == 3u ? g : cls == 1u ? g - GQ : g - GQ - GS) + lane;
           const uint32_t n = cls == 1u ? nS : cls == 3u ? nQ : nH;
           const uint32_t k = (cls == 1u ? kS : cls == 3u ? kQ : kH) + 4 * i;
-          if (cls == 0u && i < n) stage[i].len = 0xFFFFFFFFu; /* nothing to write out unless the header is judged below */
-          if (i >= n) continue;
-          const uint32_t s = k == 0 ? (uint32_t)LN_LEFT + lead0 : (uint32_t)lend[k - 1];
-          if (s >= tile_end) continue;
-          uint32_t e; /* one past the line's last byte; has_lf: that byte is its LF */
-          bool has_lf = true;
-          if (k < cntW) e = lend[k];
-          else if (nloc < (uint32_t)(LN_LEFT + TILE + LN_MARGIN)) { /* the data ends inside the window */
-            if (!P.virtual_end) continue;                             /* more follows: the rest of the line comes with the next chunk */
-            e = nloc; has_lf = false;                                 /* last line of the file, without LF */
-          } else { anomaly |= LN_A_CAPACITY; continue; }              /* longer than the margin: not for this mode */
-          const uint32_t ce = has_lf ? e - 1u : e;                    /* content: [s, ce) */
-          if (cls == 1u) { if (ce > s) seq_bad |= ls_seq_line(win, lut, s, ce); }
-          else if (cls == 3u) {
-            if (!(win[s - 1] == '\n' && win[s - 2] == '+' && win[s - 3] == '\n')) anomaly |= LN_A_PLUS; /* the line in front must be "+\n" */
-            if (ce > s) ls_qual_line(win, lut, s, ce, qmn, qmx);
-          } else {
-            const uint32_t hl = e - s;
-            if (!has_lf) { anomaly |= LN_A_HEADER; continue; }
-            if (hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, tile); continue; }
-            uint32_t nlen; uint64_t mem_len, hsh = FQ_HASH_SKIP;
-            if (!fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; continue; }
+          if (cls != 0u) {
+            if (i >= n) continue;
+            const uint32_t s = k == 0 ? (uint32_t)LN_LEFT + lead0 : (uint32_t)lend[k - 1];
+            if (s >= tile_end) continue;
+            uint32_t e; /* one past the line's last byte; has_lf: that byte is its LF */
+            bool has_lf = true;
+            if (k < cntW) e = lend[k];
+            else if (nloc < (uint32_t)(LN_LEFT + TILE + LN_MARGIN)) { /* the data ends inside the window */
+              if (!P.virtual_end) continue;                             /* more follows: the rest of the line comes with the next chunk */
+              e = nloc; has_lf = false;                                 /* last line of the file, without LF */
+            } else { anomaly |= LN_A_CAPACITY; continue; }              /* longer than the margin: not for this mode */
+            const uint32_t ce = has_lf ? e - 1u : e;                    /* content: [s, ce) */
+            if (cls == 1u) { if (ce > s) seq_bad |= ls_seq_line(win, lut, s, ce); }
+            else {
+              if (!(win[s - 1] == '\n' && win[s - 2] == '+' && win[s - 3] == '\n')) anomaly |= LN_A_PLUS; /* the line in front must be "+\n" */
+              if (ce > s) ls_qual_line(win, lut, s, ce, qmn, qmx);
+            }
+            continue;
+          }
+          /* ---- header lines: one RECORD per lane.  The '@' syntax, the name slice and its hash in one walk; the name's bytes go
+           * to the arena; the record's length rules (src/fastq.c:346, :380; src/fastq.h:30-37) and its statistics (src/fastq.c:97-110)
+           * from the ends of its four lines.  No lane leaves early: the warp reserves arena space and reduces the statistics together. */
+          const bool window_full = nloc == (uint32_t)(LN_LEFT + TILE + LN_MARGIN);
+          bool live = i < n;
+          uint32_t s = 0, e = 0;
+          if (live) { stage[i].len = 0xFFFFFFFFu; s = k == 0 ? (uint32_t)LN_LEFT + lead0 : (uint32_t)lend[k - 1]; live = s < tile_end; } /* (nothing to write out unless the header is judged below) */
+          if (live) {
+            if (k < cntW) e = lend[k];
+            else { live = false; if (window_full) anomaly |= LN_A_CAPACITY; else if (P.virtual_end) anomaly |= LN_A_HEADER; } /* no LF in the window: longer than the margin / the file's last line / the rest comes with the next chunk */
+          }
+          const uint32_t hl = e - s;
+          if (live && hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, tile); live = false; }
+          if (live && hl < 3u) { anomaly |= LN_A_HEADER; live = false; }
+          /* arena space for the group: the name is at most hl - 2 bytes */
+          const uint32_t units = (live && P.arena) ? (hl - 2u + 15u) >> 4 : 0u;
+          uint32_t incl_u = units;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const uint32_t a = __shfl_up_sync(FULL, incl_u, d); if (lane >= d) incl_u += a; }
+          uint32_t ubase = 0;
+          { const uint32_t tot = __shfl_sync(FULL, incl_u, 31); if (lane == 0 && tot) ubase = atomicAdd(&s_arena, tot); }
+          ubase = __shfl_sync(FULL, ubase, 0) + incl_u - units;
+          if (units && ubase + units > arena_stride) { anomaly |= LN_A_CAPACITY; live = false; }
+          const uint32_t my_unit = tile * arena_stride + ubase;
+          uint32_t nlen = 0; uint64_t mem_len = 0, hsh = FQ_HASH_SKIP;
+          if (live && !fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; live = false; }
+          if (live) {
             FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
+            if (units) { /* the name's bytes, 16 at a time from the window (any alignment), zero padded */
+              nm.off = my_unit * 16u;
+              uint4* dst = (uint4*)(P.arena + (size_t)my_unit * 16u);
+              const uint32_t a0 = (s + 1u) & ~3u, sh = ((s + 1u) & 3u) * 8u;
+              for (uint32_t u = 0; 16u * u < nlen; u++) {
+                const uint32_t* wp = (const uint32_t*)(win + a0 + 16u * u);
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+                const uint32_t left = nlen - 16u * u;
+                uint4 v;
+                v.x = fq_low_bytes(__funnelshift_r(w0, w1, sh), left);
+                v.y = left > 4u ? fq_low_bytes(__funnelshift_r(w1, w2, sh), left - 4u) : 0u;
+                v.z = left > 8u ? fq_low_bytes(__funnelshift_r(w2, w3, sh), left - 8u) : 0u;
+                v.w = left > 12u ? fq_low_bytes(__funnelshift_r(w3, w4, sh), left - 12u) : 0u;
+                dst[u] = v;
+              }
+            }
             stage[i] = nm;
+          }
+          /* the record's other three lines */
+          bool rec_ok = false; uint32_t sl = 0;
+          if (live) {
+            uint32_t e1 = 0, e2 = 0, e3 = 0; bool complete = false;
+            if (k + 3u < cntW) { e1 = lend[k + 1]; e2 = lend[k + 2]; e3 = lend[k + 3]; complete = true; }
+            else if (window_full) anomaly |= LN_A_CAPACITY; /* a record longer than the margin */
+            else if (P.virtual_end && k + 3u == cntW && win[nloc - 1] != '\n') { e1 = lend[k + 1]; e2 = lend[k + 2]; e3 = nloc + 1u; complete = true; } /* the file's last line has no LF: compare contents */
+            /* otherwise the end of the chunk cut the record: it is judged with the next chunk, or by the host at the end of the file */
+            if (complete) {
+              sl = e1 - e;
+              if (e2 - e1 != 2u || sl < 2u || e3 - e2 != sl) atomicOr(P.out + LN_O_RECBAD, 1u);
+              else rec_ok = true;
+            }
+          }
+          const uint32_t okm = __ballot_sync(FULL, rec_ok);
+          if (okm) {
+            const uint32_t memw = __reduce_add_sync(FULL, rec_ok ? (uint32_t)mem_len : 0u);
+            const uint32_t mn = __reduce_min_sync(FULL, rec_ok ? sl : 0xFFFFFFFFu), mx = __reduce_max_sync(FULL, rec_ok ? sl : 0u);
+            if (lane == 0) { atomicAdd(&s_cnt, (uint32_t)__popc(okm)); atomicAdd(&s_mem, memw); atomicMin(&s_rlmin, mn); atomicMax(&s_rlmax, mx); }
+            if (mn == mx && mx < (uint32_t)LS_HBINS) { if (lane == 0) atomicAdd(&s_hist[mx], (uint32_t)__popc(okm)); } /* one read length: the common case */
+            else if (rec_ok) { if (sl < (uint32_t)LS_HBINS) atomicAdd(&s_hist[sl], 1u); else atomicAdd(&P.stage->hist[sl < (uint32_t)LS_STAGE_HIST ? sl : (uint32_t)LS_STAGE_HIST - 1u], 1u); }
           }
         }
       }
@@ -645,6 +743,17 @@ fq_lanes_kernel(const LanesParams P) {
     buf ^= 1u;
   }
 
+  if (LINES) { /* this CTA's records → the chunk's stage */
+    __syncthreads();
+    for (int l = tid; l < LS_HBINS; l += LN_THREADS) { const uint32_t v = s_hist[l]; if (v) atomicAdd(&P.stage->hist[l], v); }
+    if (tid == 0) {
+      if (s_cnt) {
+        atomicAdd(&P.stage->nrec, (unsigned long long)s_cnt); atomicAdd(&P.stage->mem, (unsigned long long)s_mem);
+        atomicMax(&P.stage->rl_min_inv, ~s_rlmin); atomicMax(&P.stage->rl_max, s_rlmax);
+      }
+      atomicMax(&P.stage->arena_used, max(arena_max, s_arena)); /* the fullest tile's */
+    }
+  }
   /* ---- results of this thread → one set of atomics per warp */
   if ((seq_ok & 0x80808080u) != 0x80808080u || seq_bad) anomaly |= LN_A_BASE;
   uint32_t mn = min(qmn & 0xFFFFu, qmn >> 16), mx = max(qmx & 0xFFFFu, qmx >> 16);
@@ -654,6 +763,44 @@ fq_lanes_kernel(const LanesParams P) {
   if (lane == 0) {
     if (anomaly) atomicOr(P.out + LN_O_ANOMALY, anomaly);
     if (mn <= mx) { atomicMin(P.out + LN_O_QMIN, mn); atomicMax(P.out + LN_O_QMAX, mx); }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------ K5p: the verdict of a per-line pass
+ * One block after the pass: is the chunk clean?  Then (and only then) what the pass staged becomes part of the file statistics —
+ * fastq_new_entry_stats (src/fastq.c:97-110) `weight` times per record, the index bookkeeping (n_entries, index_mem), the quality
+ * range — and the chunk's last line ends travel to the host with the result words. */
+struct LanesPostParams {
+  uint32_t* out; const uint32_t* line_end; const LanesStage* stage; uint32_t j0; FqRecCtx cx;
+  FqStats* stats; FqStats* stats_range; unsigned long long* hist;
+};
+__global__ void __launch_bounds__(1024)
+fq_lanes_post_kernel(const LanesPostParams P) {
+  const uint32_t nlines = P.out[LN_O_LINES];
+  const uint32_t nrec = nlines > P.j0 ? (nlines - P.j0) / 4 : 0;
+  const bool consistent = P.stage->nrec == nrec || P.out[LN_O_RECBAD] != 0;
+  const bool accept = !P.out[LN_O_CAPOVF] && P.out[LN_O_OVERLONG] == 0xFFFFFFFFu && !P.out[LN_O_ANOMALY] && !P.out[LN_O_INTERNAL] && !P.out[LN_O_RECBAD] && consistent;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    P.out[LN_O_ACCEPT] = accept ? 1u : 0u; P.out[LN_O_ARENA_USED] = P.stage->arena_used; P.out[LN_O_STAGED] = (uint32_t)P.stage->nrec; /* (units per tile: the host scales) */
+    if (!consistent) P.out[LN_O_INTERNAL] = 3u; /* every complete record must have been judged exactly once */
+  }
+  if (!accept) return;
+  if (threadIdx.x < 8) { /* the last line ends travel to the host with the result words */
+    const uint32_t from = nlines > 8 ? nlines - 8 : 0;
+    if (from + threadIdx.x < nlines) P.out[16 + threadIdx.x] = P.line_end[from + threadIdx.x];
+  }
+  const unsigned long long w = P.cx.weight;
+  for (uint32_t l = threadIdx.x; l < (uint32_t)LS_STAGE_HIST; l += blockDim.x) { const uint32_t v = P.stage->hist[l]; if (v) atomicAdd(P.hist + l, w * v); }
+  if (threadIdx.x == 0) {
+    const unsigned long long n = P.stage->nrec;
+    if (n) {
+      atomicAdd(&P.stats->num_rds, n * w);
+      if (P.cx.loop == FQ_LOOP_INDEX) { atomicAdd(&P.stats->n_names, n); atomicAdd(&P.stats->mem_sum, P.stage->mem); }
+      atomicMin(&P.stats_range->min_rl, ~P.stage->rl_min_inv); atomicMax(&P.stats_range->max_rl, P.stage->rl_max);
+    }
+    if (P.out[LN_O_QMIN] <= P.out[LN_O_QMAX]) { atomicMin(&P.stats_range->min_q, P.out[LN_O_QMIN]); atomicMax(&P.stats_range->max_q, P.out[LN_O_QMAX]); }
+    P.out[LN_O_RLMIN] = ~P.stage->rl_min_inv; P.out[LN_O_RLMAX] = P.stage->rl_max;
   }
 }
 

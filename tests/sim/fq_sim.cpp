@@ -34,10 +34,10 @@ class FqSimDevice : public FqDevice {
   bool kernel_stat(int, double* ms, uint64_t* l, uint64_t* b, uint64_t* i) override { *ms = 0; *l = *b = *i = 0; return true; }
   void kernel_stats_reset() override {}
 
-  void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2) override {
+  void scan_lines(const uint8_t* data, uint32_t n, int virtual_end, uint32_t* line_end, uint32_t cap, uint32_t* out2, uint32_t lead = 0) override {
     n_launch_++;
     uint32_t k = 0;
-    for (uint32_t i = 0; i < n; i++)
+    for (uint32_t i = lead; i < n; i++)
       if (data[i] == '\n') { if (k < cap) line_end[k] = i + 1; k++; }
     if (virtual_end && n > 0 && data[n - 1] != '\n') { if (k < cap) line_end[k] = n; k++; }
     out2[0] = k; out2[1] = k > cap;
