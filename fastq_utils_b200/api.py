@@ -106,10 +106,11 @@ def bind(L):
     L.fqg_set_hash_seed.argtypes = [vp, ctypes.c_uint32]
     L.fqg_set_chunk_hook.argtypes = [vp, CHUNK_HOOK, vp]
     L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
-    L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64]
+    L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64, ctypes.c_uint32]
     L.fqg_shard_reserve.argtypes = [vp, u64]
-    L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ci]
-    L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
+    L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ctypes.c_uint32, ci]
+    L.fqg_shard_claim_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ctypes.c_uint32, ci]
+    L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.fqg_side_copy.argtypes = [vp, vp, vp, sz]
     L.fqg_side_sync.argtypes = [vp]
     L.fqg_ipc_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.c_char_p]
@@ -291,20 +292,24 @@ class FastqInfo:
         _check(self._ctx, lib().fqg_names_new(self._ctx, file, ctypes.byref(n)), "fqg_names_new")
         return int(n.value)
 
-    def names_pack_slots(self, file, region_ptrs, cap):
+    def names_pack_slots(self, file, region_ptrs, cap, units=0):
         arr = (ctypes.c_void_p * len(region_ptrs))(*region_ptrs)
-        _check(self._ctx, lib().fqg_names_pack_slots(self._ctx, file, len(region_ptrs), arr, cap), "fqg_names_pack_slots")
+        _check(self._ctx, lib().fqg_names_pack_slots(self._ctx, file, len(region_ptrs), arr, cap, units), "fqg_names_pack_slots")
 
     def shard_reserve(self, n_names):
         _check(self._ctx, lib().fqg_shard_reserve(self._ctx, n_names), "fqg_shard_reserve")
 
-    def shard_insert_slots(self, regions_ptr, n_src, cap, beside):
-        _check(self._ctx, lib().fqg_shard_insert_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, cap, 1 if beside else 0), "fqg_shard_insert_slots")
+    def shard_insert_slots(self, regions_ptr, n_src, cap, beside, units=0):
+        _check(self._ctx, lib().fqg_shard_insert_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, cap, units, 1 if beside else 0), "fqg_shard_insert_slots")
+
+    def shard_claim_slots(self, regions_ptr, n_src, cap, beside, units):
+        _check(self._ctx, lib().fqg_shard_claim_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, cap, units, 1 if beside else 0), "fqg_shard_claim_slots")
 
     def shard_slots_result(self):
-        ins, eq, ov = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int32()
-        _check(self._ctx, lib().fqg_shard_slots_result(self._ctx, ctypes.byref(ins), ctypes.byref(eq), ctypes.byref(ov)), "fqg_shard_slots_result")
-        return int(ins.value), int(eq.value), bool(ov.value)
+        """(inserted, names already there / equal hashes, overflow, claimed by mates, mates without a fresh partner)"""
+        ins, eq, ov, cl, un = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int32(), ctypes.c_uint64(), ctypes.c_uint64()
+        _check(self._ctx, lib().fqg_shard_slots_result(self._ctx, ctypes.byref(ins), ctypes.byref(eq), ctypes.byref(ov), ctypes.byref(cl), ctypes.byref(un)), "fqg_shard_slots_result")
+        return int(ins.value), int(eq.value), bool(ov.value), int(cl.value), int(un.value)
 
     def side_copy(self, dst, src, n):
         _check(self._ctx, lib().fqg_side_copy(self._ctx, ctypes.c_void_p(dst), ctypes.c_void_p(src), n), "fqg_side_copy")
@@ -360,6 +365,11 @@ class FastqInfo:
         starts = (ctypes.c_uint64 * max(cap, 1))()
         _check(self._ctx, lib().fqg_index_records(self._ctx, data, len(data), starts, cap, ctypes.byref(n)), "fqg_index_records")
         return int(n.value), list(starts[:min(cap, n.value)])
+
+
+def route_region_bytes(cap, units):
+    """bytes of one routing region (include/fastq_gpu.h: fqg_route_region_bytes)"""
+    return 16 + cap * (16 + 16 * units)
 
 
 def feed_chunk_bytes():

@@ -155,21 +155,25 @@ extern "C" int fqg_names_new(fqg_ctx* c, int file, uint64_t* n_new) {
   if (!c || file < 0 || file > 1 || !n_new) return FQG_ERR_USAGE;
   FQG_GUARD(c, *n_new = c->eng->names_new(file))
 }
-extern "C" int fqg_names_pack_slots(fqg_ctx* c, int file, uint32_t world, void* const* region_ptrs, uint64_t region_cap) {
+extern "C" int fqg_names_pack_slots(fqg_ctx* c, int file, uint32_t world, void* const* region_ptrs, uint64_t region_cap, uint32_t name_units) {
   if (!c || file < 0 || file > 1 || !region_ptrs || !region_cap) return FQG_ERR_USAGE;
-  FQG_GUARD(c, c->eng->names_pack_slots(file, world, region_ptrs, region_cap))
+  FQG_GUARD(c, c->eng->names_pack_slots(file, world, region_ptrs, region_cap, name_units))
 }
 extern "C" int fqg_shard_reserve(fqg_ctx* c, uint64_t n_names) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->eng->shard_reserve(n_names))
 }
-extern "C" int fqg_shard_insert_slots(fqg_ctx* c, const void* regions, uint32_t n_src, uint64_t region_cap, int beside) {
-  if (!c || !regions || !region_cap) return FQG_ERR_USAGE;
-  FQG_GUARD(c, c->eng->shard_insert_slots(regions, n_src, region_cap, beside != 0))
+extern "C" int fqg_shard_claim_slots(fqg_ctx* c, const void* regions, uint32_t n_src, uint64_t region_cap, uint32_t name_units, int beside) {
+  if (!c || !regions) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_claim_slots(regions, n_src, region_cap, name_units, beside != 0))
 }
-extern "C" int fqg_shard_slots_result(fqg_ctx* c, uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow) {
+extern "C" int fqg_shard_insert_slots(fqg_ctx* c, const void* regions, uint32_t n_src, uint64_t region_cap, uint32_t name_units, int beside) {
+  if (!c || !regions || !region_cap) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_insert_slots(regions, n_src, region_cap, name_units, beside != 0))
+}
+extern "C" int fqg_shard_slots_result(fqg_ctx* c, uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow, uint64_t* claimed, uint64_t* unpaired) {
   if (!c || !inserted || !equal_hashes || !overflow) return FQG_ERR_USAGE;
-  FQG_GUARD(c, c->eng->shard_slots_result(inserted, equal_hashes, overflow))
+  FQG_GUARD(c, c->eng->shard_slots_result(inserted, equal_hashes, overflow, claimed, unpaired))
 }
 extern "C" int fqg_ipc_alloc(fqg_ctx* c, size_t bytes, void** dptr, uint8_t handle[64]) {
   if (!c || !dptr || !handle) return FQG_ERR_USAGE;

@@ -771,32 +771,35 @@ fq_names_pack_kernel(const FqName* __restrict__ names, const uint8_t* __restrict
  * (local send buffer for an all-to-all, or the owner's own memory mapped over NVLink): no counting pass, no size exchange.  The
  * kernels are capped at 32 registers: one block fits on an SM beside the four resident blocks of the pass. */
 struct SlotPackParams {
-  const FqName* names; uint32_t nrec; unsigned long long g0; uint32_t world; unsigned long long cap; unsigned long long* cursors; FqRegionPtrs R;
+  const FqName* names; const uint8_t* arena; uint32_t nrec; unsigned long long g0; uint32_t world; unsigned long long cap; uint32_t units;
+  unsigned long long* cursors; FqRegionPtrs R;
 };
-#define FQ_PACK_ILP 4
+#define FQ_PACK_ILP 2
 __global__ void __launch_bounds__(256, 8)
 fq_names_pack_slots_kernel(const SlotPackParams P) {
   /* One block per SM is all the room there is beside the pass: the kernel lives on memory-level parallelism instead of occupancy.
    * Every thread has FQ_PACK_ILP names in flight; the rank of a name among the warp's names of the same owner comes from one
-   * match.any (no loop over the owners), the warp's share of an owner's region from one shared atomic by the group's first lane. */
+   * match.any (no loop over the owners), the warp's share of an owner's region from one shared atomic by the group's first lane.
+   * A slot is its 16-byte header and `units` 16-byte units of the name's bytes, copied from the arena (aligned, zero padded). */
   __shared__ unsigned int s_cnt[FQ_SHARD_MAX_SRC];
   __shared__ unsigned long long s_base[FQ_SHARD_MAX_SRC];
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
+  const size_t slot_bytes = fq_route_slot_bytes(P.units);
   for (uint32_t b0 = blockIdx.x * (256u * FQ_PACK_ILP); b0 < P.nrec; b0 += gridDim.x * (256u * FQ_PACK_ILP)) {
     if (threadIdx.x < P.world) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    unsigned long long h[FQ_PACK_ILP]; uint32_t len[FQ_PACK_ILP], my[FQ_PACK_ILP];
+    FqName nm[FQ_PACK_ILP]; uint32_t my[FQ_PACK_ILP];
 #pragma unroll
     for (int j = 0; j < FQ_PACK_ILP; j++) {
       const uint32_t k = b0 + j * 256u + threadIdx.x;
-      h[j] = FQ_HASH_SKIP; len[j] = 0;
-      if (k < P.nrec) { const FqName nm = P.names[k]; h[j] = nm.hash; len[j] = nm.len; }
+      nm[j].hash = FQ_HASH_SKIP; nm[j].len = 0; nm[j].off = 0;
+      if (k < P.nrec) nm[j] = P.names[k];
     }
 #pragma unroll
     for (int j = 0; j < FQ_PACK_ILP; j++) {
-      const bool valid = h[j] != FQ_HASH_SKIP;
-      const uint32_t o = valid ? fq_owner_of(h[j], P.world) : 0xFFFFFFFFu;
+      const bool valid = nm[j].hash != FQ_HASH_SKIP;
+      const uint32_t o = valid ? fq_owner_of(nm[j].hash, P.world) : 0xFFFFFFFFu;
       const uint32_t m = __match_any_sync(FULL, o);
       const int leader = __ffs(m) - 1;
       uint32_t wm = 0;
@@ -809,19 +812,34 @@ fq_names_pack_slots_kernel(const SlotPackParams P) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < FQ_PACK_ILP; j++) {
-      if (h[j] == FQ_HASH_SKIP) continue;
-      const uint32_t o = fq_owner_of(h[j], P.world);
+      if (nm[j].hash == FQ_HASH_SKIP) continue;
+      const uint32_t o = fq_owner_of(nm[j].hash, P.world);
       const unsigned long long pos = s_base[o] + my[j];
-      if (pos < P.cap) { FqPackedName pn; pn.hash = h[j]; pn.record = P.g0 + b0 + j * 256u + threadIdx.x; pn.off = 0; pn.len = len[j]; P.R.region[o][1 + pos] = pn; }
+      if (pos >= P.cap) continue; /* counted, not stored: the header's count tells the owner */
+      uint4* slot = (uint4*)(P.R.region[o] + 16 + pos * slot_bytes);
+      const unsigned long long rec = P.g0 + b0 + j * 256u + threadIdx.x, rl = (rec << 12) | nm[j].len;
+      slot[0] = make_uint4((uint32_t)nm[j].hash, (uint32_t)(nm[j].hash >> 32), (uint32_t)rl, (uint32_t)(rl >> 32));
+      for (uint32_t u = 0; u < P.units; u++)
+        slot[1 + u] = 16u * u < nm[j].len ? *(const uint4*)(P.arena + nm[j].off + 16u * u) : make_uint4(0u, 0u, 0u, 0u);
+      if (P.units && nm[j].len > 16u * P.units) atomicOr(P.cursors + FQ_SHARD_MAX_SRC + o, FQ_ROUTE_NAME_TOO_LONG);
     }
     __syncthreads();
   }
 }
 struct SlotHeaderParams { const unsigned long long* cursors; uint32_t world; FqRegionPtrs R; };
 __global__ void fq_slots_header_kernel(const SlotHeaderParams P) {
-  if (threadIdx.x < P.world) { FqPackedName h; h.hash = P.cursors[threadIdx.x]; h.record = 0; h.off = 0; h.len = 0; P.R.region[threadIdx.x][0] = h; }
+  if (threadIdx.x < P.world) { unsigned long long* h = (unsigned long long*)P.R.region[threadIdx.x]; h[0] = P.cursors[threadIdx.x]; h[1] = P.cursors[FQ_SHARD_MAX_SRC + threadIdx.x]; }
 }
-struct SlotInsertParams { const FqPackedName* regions; uint32_t n_src; unsigned long long cap; FqSlot* slots; unsigned long long mask; unsigned long long* counters; };
+/* the name a table slot points at (idx1 = address >> 4 of a route slot in this rank's own memory) against the name of route slot `sl` */
+__device__ __forceinline__ bool route_same_name(unsigned long long idx1, const FqRouteSlot* sl) {
+  const FqRouteSlot* other = (const FqRouteSlot*)(idx1 << 4);
+  const uint32_t len = (uint32_t)(sl->rec_len & 0xFFFull);
+  if ((uint32_t)(other->rec_len & 0xFFFull) != len) return false;
+  const uint4* a = (const uint4*)(other + 1); const uint4* b = (const uint4*)(sl + 1);
+  for (uint32_t u = 0; 16u * u < len; u++) { const uint4 x = a[u], y = b[u]; if ((x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w)) return false; }
+  return true;
+}
+struct SlotInsertParams { const uint8_t* regions; uint32_t n_src; unsigned long long cap; uint32_t units; FqSlot* slots; unsigned long long mask; unsigned long long* counters; };
 __global__ void __launch_bounds__(256, 8)
 fq_shard_insert_slots_kernel(const SlotInsertParams P) {
   /* One probe in flight per thread.  Measured on B200 beside the pass: 2 or 4 independent first probes per thread are slower (the
@@ -829,28 +847,62 @@ fq_shard_insert_slots_kernel(const SlotInsertParams P) {
    * next pass, whose blocks must all be resident). */
   unsigned long long inserted = 0, equal = 0;
   const unsigned long long total = (unsigned long long)P.n_src * P.cap, step = (unsigned long long)gridDim.x * blockDim.x;
+  const size_t slot_bytes = fq_route_slot_bytes(P.units), region_bytes = fq_route_region_bytes(P.cap, P.units);
   for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
     const unsigned long long m = m0 + threadIdx.x;
     if (m >= total) continue;
     const unsigned long long src = m / P.cap, idx = m - src * P.cap;
-    const FqPackedName* reg = P.regions + src * (P.cap + 1);
-    const unsigned long long cnt = reg[0].hash;
-    if (cnt > P.cap && idx == 0) atomicExch(P.counters + 2, 1ull); /* the sender had more names for this owner than the region holds */
+    const uint8_t* reg = P.regions + src * region_bytes;
+    const unsigned long long cnt = ((const unsigned long long*)reg)[0];
+    if (idx == 0 && (cnt > P.cap || ((const unsigned long long*)reg)[1])) atomicExch(P.counters + 2, 1ull); /* more names than the region holds, or a name longer than its slot */
     if (idx >= cnt) continue;
-    const unsigned long long hash = reg[1 + idx].hash, rec = reg[1 + idx].record;
+    const FqRouteSlot* sl = (const FqRouteSlot*)(reg + 16 + idx * slot_bytes);
+    const unsigned long long hash = sl->hash, me = (unsigned long long)(uintptr_t)sl >> 4;
     unsigned long long i = hash & P.mask, probes = 0;
     for (;; i = (i + 1) & P.mask) {
       if (++probes > P.mask) { atomicExch(P.counters + 2, 1ull); break; }
       unsigned long long cur, cur_idx;
-      if (slot_claim128(P.slots + i, hash, rec, &cur, &cur_idx)) { inserted++; break; }
+      if (slot_claim128(P.slots + i, hash, me, &cur, &cur_idx)) { inserted++; break; }
       if (cur != hash) continue;
-      equal++; /* a duplicate name or a 64-bit collision: tuples alone cannot tell, the exact path decides */
+      if (P.units && !route_same_name(cur_idx, sl)) continue; /* another name with this hash: walk on */
+      equal++; /* the name is there already (units = 0: or its hash is, which tuples alone cannot judge): the exact path reports it */
       break;
     }
   }
   __syncwarp();
   inserted = warp_sum64(inserted); equal = warp_sum64(equal);
   if ((threadIdx.x & 31) == 0) { if (inserted) atomicAdd(P.counters + 1, inserted); if (equal) atomicAdd(P.counters + 0, equal); }
+}
+__global__ void __launch_bounds__(256, 8)
+fq_shard_claim_slots_kernel(const SlotInsertParams P) {
+  unsigned long long claimed = 0, unpaired = 0;
+  const unsigned long long total = (unsigned long long)P.n_src * P.cap, step = (unsigned long long)gridDim.x * blockDim.x;
+  const size_t slot_bytes = fq_route_slot_bytes(P.units), region_bytes = fq_route_region_bytes(P.cap, P.units);
+  for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
+    const unsigned long long m = m0 + threadIdx.x;
+    if (m >= total) continue;
+    const unsigned long long src = m / P.cap, idx = m - src * P.cap;
+    const uint8_t* reg = P.regions + src * region_bytes;
+    const unsigned long long cnt = ((const unsigned long long*)reg)[0];
+    if (idx == 0 && (cnt > P.cap || ((const unsigned long long*)reg)[1])) atomicExch(P.counters + 2, 1ull);
+    if (idx >= cnt) continue;
+    const FqRouteSlot* sl = (const FqRouteSlot*)(reg + 16 + idx * slot_bytes);
+    const unsigned long long hash = sl->hash, rec = sl->rec_len >> 12;
+    unsigned long long i = hash & P.mask, probes = 0;
+    for (;; i = (i + 1) & P.mask) {
+      if (++probes > P.mask + 1) { unpaired++; break; }
+      const unsigned long long cur = P.slots[i].hash;
+      if (cur == FQ_HASH_EMPTY) { unpaired++; break; }
+      if (cur != hash) continue;
+      if (!route_same_name(P.slots[i].idx1, sl)) continue;
+      const unsigned long long old = atomicMin(&P.slots[i].claim2, rec);
+      if (old == FQ_IDX_NONE) claimed++; else unpaired++; /* the entry was deleted by an earlier mate: the reference reports the later one */
+      break;
+    }
+  }
+  __syncwarp();
+  claimed = warp_sum64(claimed); unpaired = warp_sum64(unpaired);
+  if ((threadIdx.x & 31) == 0) { if (claimed) atomicAdd(P.counters + 8, claimed); if (unpaired) atomicAdd(P.counters + 9, unpaired); }
 }
 
 struct ShardParams { FqShardArgs a; };
@@ -1167,7 +1219,7 @@ class FqCudaDevice : public FqDevice {
     toc(); launched();
     if (lines_mode) { /* the pass judged the records itself: one block turns what it staged into statistics if the chunk is clean */
       LanesPostParams R;
-      R.out = a.out5; R.line_end = a.line_end; R.stage = stage_; R.j0 = a.j0; R.cx = a.cx; R.stats = a.stats; R.stats_range = a.stats_range; R.hist = a.hist;
+      R.out = a.out5; R.line_end = a.line_end; R.stage = stage_; R.j0 = a.j0; R.cx = a.cx; R.stats = a.stats; R.stats_range = a.stats_range; R.hist = a.hist; R.names_cap = a.names ? a.names_cap : 0;
       fq_lanes_post_kernel<<<1, 1024, 0, st_>>>(R);
       launched();
       *self_judged = true;
@@ -1276,13 +1328,14 @@ class FqCudaDevice : public FqDevice {
   void route_begin(unsigned long long* cursors, uint32_t world, bool beside) override {
     /* beside: the main stream is busy with a clean-data pass launched after the names were complete; wait only for what was
      * queued before that pass (ev_pre_).  Otherwise: everything queued on the main stream so far. */
+    (void)world;
     if (beside) { FQ_CUDA_CHECK(cudaStreamWaitEvent(st2_, ev_pre_, 0)); } else after_main();
-    FQ_CUDA_CHECK(cudaMemsetAsync(cursors, 0, world * sizeof(unsigned long long), st2_));
+    FQ_CUDA_CHECK(cudaMemsetAsync(cursors, 0, 2 * FQ_SHARD_MAX_SRC * sizeof(unsigned long long), st2_));
   }
-  void names_pack_slots(const FqName* names, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
-                        unsigned long long* cursors) override {
+  void names_pack_slots(const FqName* names, const uint8_t* arena, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
+                        uint32_t units, unsigned long long* cursors) override {
     if (!nrec) return;
-    SlotPackParams P; P.names = names; P.nrec = nrec; P.g0 = g0; P.world = world; P.cap = cap; P.cursors = cursors; P.R = R;
+    SlotPackParams P; P.names = names; P.arena = arena; P.nrec = nrec; P.g0 = g0; P.world = world; P.cap = cap; P.units = units; P.cursors = cursors; P.R = R;
     int grid = (int)std::min<uint32_t>((nrec + 256u * FQ_PACK_ILP - 1) / (256u * FQ_PACK_ILP), (uint32_t)sms_ * 8);
     tic(FQG_K_OTHER, 0, nrec, st2_);
     fq_names_pack_slots_kernel<<<grid, 256, 0, st2_>>>(P);
@@ -1294,15 +1347,19 @@ class FqCudaDevice : public FqDevice {
     launched();
     FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
   }
-  void shard_insert_slots(const FqPackedName* regions, uint32_t n_src, uint64_t cap, FqSlot* slots, unsigned long long mask,
-                          unsigned long long* counters, bool beside) override {
+  void shard_insert_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
+                          unsigned long long* counters, bool beside) override { slots_kernel(regions, n_src, cap, units, slots, mask, counters, beside, false); }
+  void shard_claim_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
+                         unsigned long long* counters, bool beside) override { slots_kernel(regions, n_src, cap, units, slots, mask, counters, beside, true); }
+  void slots_kernel(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
+                    unsigned long long* counters, bool beside, bool claim) {
     if (!n_src || !cap) return;
-    SlotInsertParams P; P.regions = regions; P.n_src = n_src; P.cap = cap; P.slots = slots; P.mask = mask; P.counters = counters;
+    SlotInsertParams P; P.regions = regions; P.n_src = n_src; P.cap = cap; P.units = units; P.slots = slots; P.mask = mask; P.counters = counters;
     unsigned long long total = (unsigned long long)n_src * cap;
     int grid = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)sms_ * (beside ? 1 : 8));
     after_main();
-    tic(FQG_K_INDEX, 0, total, st2_);
-    fq_shard_insert_slots_kernel<<<grid, 256, 0, st2_>>>(P);
+    tic(claim ? FQG_K_MATE : FQG_K_INDEX, 0, total, st2_);
+    if (claim) fq_shard_claim_slots_kernel<<<grid, 256, 0, st2_>>>(P); else fq_shard_insert_slots_kernel<<<grid, 256, 0, st2_>>>(P);
     toc(st2_); launched();
   }
   void side_copy(void* dst, const void* src, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, st2_)); }

@@ -63,8 +63,14 @@ typedef struct {
   unsigned long long* dup_key;   /* min event key of a duplicate */
   unsigned long long* counters;  /* [0] collisions, [2] table full */
 } FqShardArgs;
-/* pipelined routing: one fixed-capacity region per owner (header FqPackedName {count, 0, 0, 0}, then the tuples) */
-typedef struct { FqPackedName* region[FQ_SHARD_MAX_SRC]; } FqRegionPtrs;
+/* pipelined routing: a name on its way to the owner of its hash is a slot of 16 + 16 * units bytes: this header, then `units`
+ * 16-byte units holding the name's bytes, zero padded (units = 0: the tuple travels alone and the owner cannot judge equal hashes).
+ * One fixed-capacity region per (round, source, owner): a header slot {count, flags}, then `cap` slots. */
+typedef struct { unsigned long long hash; unsigned long long rec_len; /* record << 12 | length of the name */ } FqRouteSlot;
+#define FQ_ROUTE_NAME_TOO_LONG 1ull  /* region flag: a name needed more units than the slots have (it travelled cut short) */
+typedef struct { uint8_t* region[FQ_SHARD_MAX_SRC]; } FqRegionPtrs;
+FQ_HD size_t fq_route_slot_bytes(uint32_t units) { return 16u + 16u * (size_t)units; }
+FQ_HD size_t fq_route_region_bytes(unsigned long long cap, uint32_t units) { return 16u + cap * fq_route_slot_bytes(units); }
 FQ_HD uint32_t fq_owner_of(uint64_t hash, uint32_t world) { return (uint32_t)((hash >> 40) % world); }
 
 /* fused scan + validate pass over one chunk (FqCudaDevice only): the records of the segment that starts at line j0 */
@@ -141,14 +147,20 @@ class FqDevice {
    * to pack were complete before it).  route_begin clears cursors[world]; names_pack_slots appends one segment's tuples to the
    * owners' regions (tuples beyond cap are counted, not stored); route_end writes the counts into the region headers and
    * returns when everything is in place. */
-  virtual void route_begin(unsigned long long* cursors, uint32_t world, bool beside) = 0;
-  virtual void names_pack_slots(const FqName* names, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
-                                unsigned long long* cursors) = 0;
+  virtual void route_begin(unsigned long long* cursors, uint32_t world, bool beside) = 0; /* cursors: 2 * FQ_SHARD_MAX_SRC words (counts, then flags) */
+  virtual void names_pack_slots(const FqName* names, const uint8_t* arena, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
+                                uint32_t units, unsigned long long* cursors) = 0;
   virtual void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R) = 0;
-  /* tuples of n_src regions (stride cap + 1 tuples) into the table; counters[0] += equal hashes, counters[1] += inserted,
-   * counters[2] = 1 when a header count exceeds cap or the table is full.  Asynchronous. */
-  virtual void shard_insert_slots(const FqPackedName* regions, uint32_t n_src, uint64_t cap, FqSlot* slots, unsigned long long mask,
+  /* slots of n_src regions (one after the other, fq_route_region_bytes each) into the table: counters[1] += inserted, counters[0] +=
+   * names that are in the table already (units > 0: hash AND bytes equal — a duplicated read name; units = 0: equal hashes, which
+   * tuples alone cannot judge), counters[2] = 1 when a header count exceeds cap, a name did not fit its slot, or the table is full.
+   * A slot whose hash is taken by ANOTHER name walks on (units > 0).  Asynchronous. */
+  virtual void shard_insert_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
                                   unsigned long long* counters, bool beside) = 0;
+  /* the mate loop at the owner (src/fastq_info.c:333-350: lookup, then delete): every slot (units > 0) looks its name up by hash and
+   * bytes; the first one to find it claims it (counters[8]++), a name that is not there or was claimed before counts in counters[9] */
+  virtual void shard_claim_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
+                                 unsigned long long* counters, bool beside) = 0;
   virtual void side_copy(void* dst, const void* src, size_t n) = 0;
   virtual void side_sync() = 0;
   /* memory that other processes can map (CUDA IPC); devices without it throw */

@@ -21,7 +21,7 @@ static const uint32_t kNone32 = 0xFFFFFFFFu;
 static const double kLanesTile = 31744.0;        /* bytes of a tile of the per-line clean-data pass (fq_lanes.cuh: LS_TILE): sizes the arena */
 /* device words: [0] equal hashes that tuples alone could not judge, [1] claimed by the mate loop, [2] table full, [3] the owner's earliest
  * name event, [4] names that met ANOTHER name with their hash (diagnostics), [5] units measured for an arena, [6] arena cursor */
-static const int kCounters = 8;
+static const int kCounters = 12; /* [8] names claimed / [9] mates without a (fresh) partner at the owner (pipelined routing of paired files) */
 
 static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 static int fmt_of_sniff(int s) { return s == FQ_SNIFF_DEFAULT ? FQ_FMT_DEFAULT : s == FQ_SNIFF_CASAVA ? FQ_FMT_CASAVA : FQ_FMT_INT; }
@@ -34,7 +34,7 @@ FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) 
   scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
   recout_ = (FqRecOut*)dev_->alloc(sizeof(FqRecOut));
   tile_out_ = (uint32_t*)dev_->alloc(32 * sizeof(uint32_t));
-  route_cursors_ = (unsigned long long*)dev_->alloc(FQ_SHARD_MAX_SRC * sizeof(unsigned long long));
+  route_cursors_ = (unsigned long long*)dev_->alloc(2 * FQ_SHARD_MAX_SRC * sizeof(unsigned long long));
   for (int f = 0; f < 2; f++) {
     f_[f].stats = (FqStats*)dev_->alloc(sizeof(FqStats));
     f_[f].hist = (unsigned long long*)dev_->alloc((size_t)FQ_MAX_READ_LENGTH * sizeof(unsigned long long));
@@ -274,6 +274,10 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   uint32_t cap = B.n / 32 + 4096;
   B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
   uint32_t ncap = cap / 4 + 1;
+  /* (16 bytes per record: with the lengths of the file's first record known, room for a third more records than such records would
+   * fill the chunk with — a chunk with more hands itself on, see fq_lanes_post_kernel, and the next one asks for the full bound) */
+  if (lanes_ok_ && !names_cap_full_ && F.first_hdr_len && F.first_seq_len)
+    ncap = std::min<uint32_t>(ncap, (uint32_t)((double)B.n / (0.75 * (F.first_hdr_len + 2.0 * F.first_seq_len + 2))) + 4096);
   FqName* names = (loop != FQ_LOOP_SINGLE && loop != FQ_LOOP_READER) ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
   FqTileArgs a; memset(&a, 0, sizeof a);
   a.data = B.data; a.n = B.n; a.virtual_end = last ? 1 : 0; a.line_end = B.line_end; a.cap = cap; a.out5 = tile_out_;
@@ -328,6 +332,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
         return true;
       }
       path_counts[1]++;
+      if (self_judged && o[4] == 3) names_cap_full_ = true; /* (perhaps) more records than name descriptors */
       if (!self_judged && pass_ok) dev_->lanes_commit(a, true); /* counters went in before a record broke a length rule: take them back */
       if (self_judged && (o[3] & 16u) && arena) F.arena_rate = std::max(F.arena_rate, 1.5 * (double)o[24] / kLanesTile); /* (perhaps) ran out of arena: what the fullest tile asked for, and half as much again */
     } else dev_->sync();
@@ -1245,19 +1250,20 @@ uint64_t FqEngine::names_new(int file) {
   return n;
 }
 
-void FqEngine::names_pack_slots(int file, uint32_t world, void* const* region_ptrs, uint64_t cap) {
+void FqEngine::names_pack_slots(int file, uint32_t world, void* const* region_ptrs, uint64_t cap, uint32_t units) {
   if (world == 0 || world > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_names_pack_slots: world out of range");
   if (!(cfg_.flags & FQG_FLAG_EXTERNAL_INDEX)) throw std::runtime_error("fqg_names_pack_slots needs FQG_FLAG_EXTERNAL_INDEX");
+  if (units > 62) throw std::runtime_error("fqg_names_pack_slots: at most 62 name units (a read name is shorter than 1000 bytes)");
   FqFile& F = f_[file];
   FqRegionPtrs R; memset(&R, 0, sizeof R);
-  for (uint32_t o = 0; o < world; o++) { if (!region_ptrs[o]) throw std::runtime_error("fqg_names_pack_slots: null region"); R.region[o] = (FqPackedName*)region_ptrs[o]; }
+  for (uint32_t o = 0; o < world; o++) { if (!region_ptrs[o]) throw std::runtime_error("fqg_names_pack_slots: null region"); R.region[o] = (uint8_t*)region_ptrs[o]; }
   const bool beside = in_beside_hook_;
   dev_->route_begin(route_cursors_, world, beside);
   uint64_t lim = eff_records(F);
   for (size_t si = F.routed_segs; si < F.segs.size(); si++) {
     const FqSegment& s = F.segs[si];
     if (s.g0 >= lim || !s.names) continue;
-    dev_->names_pack_slots(s.names, (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0), s.g0 + F.g_base, world, R, cap, route_cursors_);
+    dev_->names_pack_slots(s.names, s.arena, (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0), s.g0 + F.g_base, world, R, cap, units, route_cursors_);
   }
   dev_->route_end(route_cursors_, world, R);
   F.routed_segs = F.segs.size();
@@ -1268,17 +1274,23 @@ void FqEngine::shard_reserve(uint64_t n_names) {
   ensure_table(std::max<uint64_t>(n_names, 1));
 }
 
-void FqEngine::shard_insert_slots(const void* regions, uint32_t n_src, uint64_t cap, bool beside) {
+void FqEngine::shard_insert_slots(const void* regions, uint32_t n_src, uint64_t cap, uint32_t units, bool beside) {
   if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_insert_slots: n_src out of range");
   if (!slots_) ensure_table(1);
-  dev_->shard_insert_slots((const FqPackedName*)regions, n_src, cap, slots_, table_cap_ - 1, counters_, beside);
+  dev_->shard_insert_slots((const uint8_t*)regions, n_src, cap, units, slots_, table_cap_ - 1, counters_, beside);
   table_names_ = 1; /* the table holds names the engine cannot re-insert: it must not grow any more */
 }
+void FqEngine::shard_claim_slots(const void* regions, uint32_t n_src, uint64_t cap, uint32_t units, bool beside) {
+  if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_claim_slots: n_src out of range");
+  if (!units) throw std::runtime_error("fqg_shard_claim_slots: the mate loop compares names, the slots must carry their bytes");
+  if (!slots_) ensure_table(1);
+  dev_->shard_claim_slots((const uint8_t*)regions, n_src, cap, units, slots_, table_cap_ - 1, counters_, beside);
+}
 
-void FqEngine::shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow) {
+void FqEngine::shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow, uint64_t* claimed, uint64_t* unpaired) {
   dev_->sync();
-  unsigned long long ctr[4]; dev_->download(ctr, counters_, sizeof ctr);
-  *inserted = ctr[1]; *equal_hashes = ctr[0];
+  unsigned long long ctr[kCounters]; dev_->download(ctr, counters_, sizeof ctr);
+  *inserted = ctr[1]; *equal_hashes = ctr[0]; *claimed = ctr[8]; *unpaired = ctr[9];
   *overflow = (ctr[2] != 0 || ctr[1] * 2 > table_cap_) ? 1 : 0; /* above half full the probe sequences get long: let the exact path size the table */
 }
 

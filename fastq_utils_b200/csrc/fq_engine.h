@@ -100,10 +100,11 @@ class FqEngine {
   /* pipelined routing (include/fastq_gpu.h) */
   void set_chunk_hook(fqg_chunk_hook hook, void* user) { hook_ = hook; hook_user_ = user; }
   uint64_t names_new(int file);
-  void names_pack_slots(int file, uint32_t world, void* const* region_ptrs, uint64_t cap);
+  void names_pack_slots(int file, uint32_t world, void* const* region_ptrs, uint64_t cap, uint32_t units);
   void shard_reserve(uint64_t n_names);
-  void shard_insert_slots(const void* regions, uint32_t n_src, uint64_t cap, bool beside);
-  void shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow);
+  void shard_insert_slots(const void* regions, uint32_t n_src, uint64_t cap, uint32_t units, bool beside);
+  void shard_claim_slots(const void* regions, uint32_t n_src, uint64_t cap, uint32_t units, bool beside);
+  void shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow, uint64_t* claimed, uint64_t* unpaired);
   FqDevice* device() { return dev_; }
   std::string last_error;
   uint64_t mem_stats[4] = {0, 0, 0, 0};   /* chunk bytes held, chunk bytes released, arena bytes, records that are final */
@@ -134,6 +135,7 @@ class FqEngine {
   bool streaming_ = false, open_ = false;
   int add_depth_ = 0;
   uint8_t* fused_arena_ = nullptr;          /* ... and it put the names of the chunk into this block */
+  bool names_cap_full_ = false;             /* size the name descriptors of a chunk by the line bound, not by the first record's lengths */
   bool fused_lanes_ = false;                /* the fused pass that validated the chunk being added was the clean-data pass */
   void try_settle(int file);
   void release_buffer(FqBuffer& B);

@@ -549,8 +549,10 @@ fq_lanes_kernel(const LanesParams P) {
           const uint32_t hl = e - s;
           if (live && hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, tile); live = false; }
           if (live && hl < 3u) { anomaly |= LN_A_HEADER; live = false; }
-          /* arena space for the group: the name is at most hl - 2 bytes */
-          const uint32_t units = (live && P.arena) ? (hl - 2u + 15u) >> 4 : 0u;
+          uint32_t nlen = 0; uint64_t mem_len = 0, hsh = FQ_HASH_SKIP;
+          if (live && !fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; live = false; }
+          /* arena space for the names of the group, inside the tile's own stretch */
+          const uint32_t units = (live && P.arena) ? (nlen + 15u) >> 4 : 0u;
           uint32_t incl_u = units;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) { const uint32_t a = __shfl_up_sync(FULL, incl_u, d); if (lane >= d) incl_u += a; }
@@ -559,8 +561,6 @@ fq_lanes_kernel(const LanesParams P) {
           ubase = __shfl_sync(FULL, ubase, 0) + incl_u - units;
           if (units && ubase + units > arena_stride) { anomaly |= LN_A_CAPACITY; live = false; }
           const uint32_t my_unit = tile * arena_stride + ubase;
-          uint32_t nlen = 0; uint64_t mem_len = 0, hsh = FQ_HASH_SKIP;
-          if (live && !fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; live = false; }
           if (live) {
             FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
             if (units) { /* the name's bytes, 16 at a time from the window (any alignment), zero padded */
@@ -772,13 +772,13 @@ fq_lanes_kernel(const LanesParams P) {
  * range — and the chunk's last line ends travel to the host with the result words. */
 struct LanesPostParams {
   uint32_t* out; const uint32_t* line_end; const LanesStage* stage; uint32_t j0; FqRecCtx cx;
-  FqStats* stats; FqStats* stats_range; unsigned long long* hist;
+  FqStats* stats; FqStats* stats_range; unsigned long long* hist; uint32_t names_cap; /* 0: the loop has no names */
 };
 __global__ void __launch_bounds__(1024)
 fq_lanes_post_kernel(const LanesPostParams P) {
   const uint32_t nlines = P.out[LN_O_LINES];
   const uint32_t nrec = nlines > P.j0 ? (nlines - P.j0) / 4 : 0;
-  const bool consistent = P.stage->nrec == nrec || P.out[LN_O_RECBAD] != 0;
+  const bool consistent = (P.stage->nrec == nrec && (!P.names_cap || nrec <= P.names_cap)) || P.out[LN_O_RECBAD] != 0; /* (a name descriptor beyond the array's capacity was dropped) */
   const bool accept = !P.out[LN_O_CAPOVF] && P.out[LN_O_OVERLONG] == 0xFFFFFFFFu && !P.out[LN_O_ANOMALY] && !P.out[LN_O_INTERNAL] && !P.out[LN_O_RECBAD] && consistent;
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -63,6 +63,16 @@ class ShardedFastqInfo:
         self.exact_reruns = 0  # jobs the speculative / pipelined path handed to the exact path (tests)
         self.host_ms = {"pack": 0.0, "barrier": 0.0}  # host time inside the peer-memory rounds, accumulated
 
+    def route_description(self):
+        """how the names of the last job reached their owners (bench.py's config line)"""
+        if self.shard is None:
+            return "no name index in this mode"
+        if self.rounds_done and self._p2p_ok:
+            return "chunk by chunk into the owners' peer memory over NVLink (CUDA IPC), beside the next chunk's pass"
+        if self.rounds_done:
+            return "chunk by chunk with all-to-all exchanges"
+        return "one all-to-all over NCCL after the pass"
+
     # ------------------------------------------------------------------ helpers
     def _gather(self, obj):
         if self.world == 1:
@@ -173,7 +183,7 @@ class ShardedFastqInfo:
         a complete line that is exactly "+" is a plus line.  Returns (ok, class, ends of the first four lines, ends with LF, bytes
         per record over the first complete records, raw length of the first complete sequence line)."""
         if nbytes < 4096:
-            return (False, 0, [KEY_NONE] * 4, True, 0.0, 0)
+            return (False, 0, [KEY_NONE] * 4, True, 0.0, 0, b"")
         k = min(nbytes, 1 << 18)
         head = bytes(_as_tensor(ptr, k, self.tdev).cpu().numpy())
         last = bytes(_as_tensor(ptr + nbytes - 1, 1, self.tdev).cpu().numpy())
@@ -189,26 +199,54 @@ class ShardedFastqInfo:
                 cls = (2 - i) % 4
                 break
         if cls is None or len(ends) < 5:
-            return (False, 0, [KEY_NONE] * 4, last == b"\n", 0.0, 0)
+            return (False, 0, [KEY_NONE] * 4, last == b"\n", 0.0, 0, b"")
         k = (len(ends) - 1) // 4
         seq = next(ends[i] - ends[i - 1] for i in range(1, 5) if (cls + i) % 4 == 1)
-        return (True, cls, ends[:4], last == b"\n", (ends[4 * k] - ends[0]) / k, seq)
+        return (True, cls, ends[:4], last == b"\n", (ends[4 * k] - ends[0]) / k, seq, head[:min(ends[0], 1024)])
 
-    def _feed_file_speculative(self, f, ptr, nbytes, routed=False):
+    def _plan_routes(self, infos, pair):
+        """The routing rounds of a job, from the ranks' guesses about their ranges (infos[f][rank]): per file the number of rounds
+        (as many as the longest range has chunks, so that no round carries more than one chunk; ranks with fewer chunks add empty
+        rounds: the rounds are collective), the capacity of a region, and where the file's regions start in every rank's arena."""
+        W = self.world
+        chunk = api.feed_chunk_bytes()
+        # (a chunk restarts at the record the chunk before it cut, so a range may take one chunk more than its bytes suggest:
+        # count with slightly shorter chunks; a round too many is an empty round, a round too few would overflow the last one)
+        step = chunk - min(chunk // 4, 8 << 20)
+        # name bytes travel with the tuples when the mate loop has to compare them: 16-byte units for the length of the first
+        # record's name and a few bytes more (a longer name later in the file overflows its slot: the exact path takes over)
+        units = 0
+        if pair:
+            first = infos[0][0][6]
+            line = first[1:first.index(b"\n")] if b"\n" in first else first[1:]
+            name = line.split(b" ")[0] if self._sniff[0][0] == 1 else line
+            units = max(1, -(-(len(name) + 3) // 16))
+        plan, base = [], 0
+        for info in infos:
+            rounds = max(1, max(-(-x[7] // step) for x in info))
+            per = min(chunk, max(x[7] for x in info)) / max(min(x[4] for x in info), 16.0) / W
+            cap = int(per * 1.25) + 4096  # names of one chunk for one owner, with room to spare (the estimate comes from the first records of every range)
+            if os.environ.get("FQG_TEST_SLOT_CAP"):  # test hook: regions far too small, so that the overflow path is taken
+                cap = int(os.environ["FQG_TEST_SLOT_CAP"])
+            stride = api.route_region_bytes(cap, units)
+            plan.append({"rounds": rounds, "cap": cap, "units": units, "stride": stride, "base": base, "round": 0, "fires": 0})
+            base += rounds * W * stride
+        est = sum(x[7] / max(x[4], 16.0) for x in infos[0]) / W
+        self.shard.shard_reserve(int(est * 1.05) + 4096)
+        self._plan, self._inflight, self._hook_exc, self._pending_insert = plan, [], None, None
+        self._p2p_ok = self.p2p and self._ensure_arena(base)
+
+    def _feed_file_speculative(self, f, ptr, nbytes, info, routed=False):
         """Steps 1-2 without counting the line feeds of the range first: every rank takes the line phase of its range from its own
-        first plus line.  A wrong guess cannot go unnoticed on a valid file (a sequence line lands where a header or a plus line is
-        expected), so any error afterwards simply sends the whole job through the exact path.  False: not applicable here."""
+        first plus line (`info`: the ranks' guesses, gathered).  A wrong guess cannot go unnoticed on a valid file (a sequence line
+        lands where a header or a plus line is expected), so any error afterwards simply sends the whole job through the exact path."""
         W, r, ctx = self.world, self.rank, self.ctx
-        info = self._gather(self._guess_phase(ptr, nbytes) + (nbytes,))
-        if not all(x[0] for x in info) or info[0][1] != 0:
-            return False
         skip, cut = [0] * W, [0] * (W + 1)
         for i in range(1, W):
             cls0, prev_lf = info[i][1], info[i - 1][3]
             skip[i] = 0 if (prev_lf and cls0 == 0) else ((4 - cls0) % 4 or 4)
             cut[i] = info[i][2][skip[i] - 1] if skip[i] > 0 else 0
-        sn = ctx.sniff_device(f, ptr, nbytes, 0) if r == 0 else None
-        sn = self._gather(sn)[0]
+        sn = self._sniff[f]
         if sn[0] >= 0:
             ctx.set_sniff(f, sn[0], sn[1])
         head, reqs = None, []
@@ -226,22 +264,7 @@ class ShardedFastqInfo:
         ctx.set_stream_start(f, skip[r], 0)  # record numbers inside the range: they only matter when something is wrong
         ctx.set_line_hint(f, info[r][5])  # a range that starts inside the file never sees the first record's sequence line
         if routed:
-            # the names travel chunk by chunk beside the next chunk's pass: as many rounds as the longest range has chunks, so that
-            # no round carries more than one chunk (ranks with fewer chunks add empty rounds: the rounds are collective)
-            chunk = api.feed_chunk_bytes()
-            # (a chunk restarts at the record the chunk before it cut, so a range may take one chunk more than its bytes suggest:
-            # count with slightly shorter chunks; a round too many is an empty round, a round too few would overflow the last one)
-            step = chunk - min(chunk // 4, 8 << 20)
-            self._rounds_total = max(1, max(-(-x[-1] // step) for x in info))
-            est = sum(x[-1] / max(x[4], 16.0) for x in info) / W
-            self.shard.shard_reserve(int(est * 1.05) + 4096)
-            self._round, self._fires, self._inflight, self._hook_exc, self._pending_insert = 0, 0, [], None, None
-            # names of one chunk for one owner, with room to spare (the estimate comes from the first records of every range)
-            per = min(chunk, max(x[-1] for x in info)) / max(min(x[4] for x in info), 16.0) / W
-            self._p2p_cap = int(per * 1.25) + 4096
-            if os.environ.get("FQG_TEST_SLOT_CAP"):  # test hook: regions far too small, so that the overflow path is taken
-                self._p2p_cap = int(os.environ["FQG_TEST_SLOT_CAP"])
-            self._p2p_ok = self.p2p and self._ensure_arena(self._rounds_total * W * 24 * (self._p2p_cap + 1))
+            self._cur = f
             ctx.set_chunk_hook(self._on_chunk)
         t0 = time.perf_counter()
         try:
@@ -251,11 +274,11 @@ class ShardedFastqInfo:
             if routed:
                 ctx.set_chunk_hook(None)
         if routed:
-            while self._round < self._rounds_total - 1:
+            pl = self._plan[f]
+            while pl["round"] < pl["rounds"] - 1:
                 self._route_round(False)
             self._route_round(True)
-            self.rounds_done = self._round
-        return True
+            self.rounds_done += pl["round"]
 
     def _feed_range(self, f, ptr, nbytes, head, head_n):
         """This rank's range, then the head of the next range (the rest of the record its end cut)."""
@@ -274,19 +297,17 @@ class ShardedFastqInfo:
     # ------------------------------------------------------------------ pipelined routing (one file, tuples only)
     def _on_chunk(self, file):
         """Chunk hook of the feeding context (fqg_set_chunk_hook): called once per chunk, for a chunk of the clean-data pass while
-        that pass runs on the GPU.  Every rank performs exactly `_rounds_total` rounds (they are collective); the first call has
-        nothing to route yet."""
-        self._fires += 1
+        that pass runs on the GPU.  Every rank performs exactly the planned number of rounds per file (they are collective); the
+        first call of a file has nothing to route yet."""
+        pl = self._plan[self._cur]
+        pl["fires"] += 1
         t0 = time.perf_counter()
-        self._on_chunk_body()
-        self.host_ms["hook"] = self.host_ms.get("hook", 0.0) + (time.perf_counter() - t0) * 1e3
-
-    def _on_chunk_body(self):
-        if self._hook_exc is None and self._fires >= 2 and self._round < self._rounds_total - 1:
+        if self._hook_exc is None and pl["fires"] >= 2 and pl["round"] < pl["rounds"] - 1:
             try:
                 self._route_round(False)
             except BaseException as ex:  # an exception cannot cross the C frames above us
                 self._hook_exc = ex
+        self.host_ms["hook"] = self.host_ms.get("hook", 0.0) + (time.perf_counter() - t0) * 1e3
 
     def _ensure_arena(self, need):
         """Peer-writable receive memory (CUDA IPC over NVLink): `need` bytes on every rank, mapped by every other rank.  Collective;
@@ -328,28 +349,28 @@ class ShardedFastqInfo:
         return True
 
     def _route_round_p2p(self, final):
-        """One routing round over peer memory.  The tuples of this round are packed by owner next to the data and the copy engines
+        """One routing round over peer memory.  The names of this round are packed by owner next to the data and the copy engines
         move each region into its owner's arena (CUDA IPC over NVLink): no exchange kernel needs SMs of its own, and the pass keeps
         the memory system to itself (letting the pack kernel store into the peers' arenas directly, FQG_P2P_STORES=1, is as fast
-        with two ranks but slowed every pass threefold at eight: 5.9 M 24-byte remote stores per round and rank).  A host barrier
+        with two ranks but slowed every pass threefold at eight: 5.9 M remote stores per round and rank).  A host barrier
         says that every source's round has landed; it is passed in the NEXT round, a whole pass later, so nobody waits long; then
-        the owner inserts the round beside the running pass.  Pack first, insert second: both want the one block slot per SM that
-        the pass leaves free."""
-        W, r = self.world, self.rank
-        cap = self._p2p_cap
-        stride = 24 * (cap + 1)
-        off = self._round * W * stride
+        the owner inserts (file 1: claims) the round beside the running pass.  Pack first, insert second: both want the one block
+        slot per SM that the pass leaves free."""
+        W, r, f = self.world, self.rank, self._cur
+        pl = self._plan[f]
+        cap, units, stride = pl["cap"], pl["units"], pl["stride"]
+        off = pl["base"] + pl["round"] * W * stride
         t0 = time.perf_counter()
         copies = []
         if self.p2p_stores:
-            self.ctx.names_pack_slots(0, [self._peer[o] + off + r * stride for o in range(W)], cap)
+            self.ctx.names_pack_slots(f, [self._peer[o] + off + r * stride for o in range(W)], cap, units)
         else:
             if self._stage is None or self._stage.numel() < W * stride:
                 self._stage = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
             st = self._stage.data_ptr()
             # (same stream as the copies of the round before: the pack overwrites the staging buffer after they have read it, and
             # its completion says that they are done)
-            self.ctx.names_pack_slots(0, [self._arena[0] + off + r * stride if o == r else st + o * stride for o in range(W)], cap)
+            self.ctx.names_pack_slots(f, [self._arena[0] + off + r * stride if o == r else st + o * stride for o in range(W)], cap, units)
             copies = [(self._peer[(r + d) % W] + off + r * stride, st + ((r + d) % W) * stride) for d in range(1, W)]
         t1 = time.perf_counter()
         self._land_pending_round(beside=True)  # pack first, insert second: both want the one free block slot per SM
@@ -358,50 +379,60 @@ class ShardedFastqInfo:
         t2 = time.perf_counter()
         self.host_ms["pack"] += (t1 - t0) * 1e3
         self.host_ms["barrier"] += (t2 - t1) * 1e3
-        self._pending_insert = off
-        self._round += 1
+        self._pending_insert = (off, f)
+        pl["round"] += 1
         if final:
             self.ctx.side_sync()
             self._land_pending_round(beside=False)
 
     def _land_pending_round(self, beside):
         """The round packed before: this rank's copies of it are done (the caller has synchronised the side stream since); pass
-        the barrier (every source's are), insert."""
+        the barrier (every source's are), insert — or, for the names of file 2, claim."""
         if self._pending_insert is None:
             return
         if self.world > 1:
             dist.barrier(group=self._cpu_group)
-        self.shard.shard_insert_slots(self._arena[0] + self._pending_insert, self.world, self._p2p_cap, beside=beside)
+        off, f = self._pending_insert
+        pl = self._plan[f]
+        self._owner_round(self._arena[0] + off, pl["cap"], pl["units"], f, beside)
         self._pending_insert = None
+
+    def _owner_round(self, regions_ptr, cap, units, f, beside):
+        if f == 0:
+            self.shard.shard_insert_slots(regions_ptr, self.world, cap, beside=beside, units=units)
+        else:
+            self.shard.shard_claim_slots(regions_ptr, self.world, cap, beside=beside, units=units)
 
     def _route_round(self, final):
         """Pack the names that were not routed yet into one fixed-capacity region per owner, start their exchange and hand the
         rounds whose exchange has finished to this rank's index shard (beside the running pass unless this is the last round)."""
         if self._p2p_ok:
             return self._route_round_p2p(final)
-        W = self.world
-        mx = max(self._gather(self.ctx.names_new(0)))
+        W, f = self.world, self._cur
+        pl = self._plan[f]
+        units = pl["units"]
+        mx = max(self._gather(self.ctx.names_new(f)))
         per = -(-mx // W)
         cap = max(1, mx) if mx <= 8192 else int(per * 1.03) + 6 * int(per ** 0.5) + 1024
         if os.environ.get("FQG_TEST_SLOT_CAP"):  # test hook: regions far too small, so that the overflow path is taken
             cap = int(os.environ["FQG_TEST_SLOT_CAP"])
-        stride = 24 * (cap + 1)
+        stride = api.route_region_bytes(cap, units)
         send = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
         recv = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
-        self.ctx.names_pack_slots(0, [send.data_ptr() + o * stride for o in range(W)], cap)
+        self.ctx.names_pack_slots(f, [send.data_ptr() + o * stride for o in range(W)], cap, units)
         if W > 1:
             work = dist.all_to_all_single(recv, send, async_op=True)
         else:
             recv, work = send, None
-        self._inflight.append((recv, send, cap, work))
-        self._round += 1
+        self._inflight.append((recv, send, cap, work, f))
+        pl["round"] += 1
         while len(self._inflight) > (0 if final else 1):
-            recv, send, cap, work = self._inflight.pop(0)
+            recv, send, cap, work, ff = self._inflight.pop(0)
             if work is not None:
                 work.wait()
             if self.tdev.type == "cuda":
                 torch.cuda.current_stream().synchronize()  # not the device: the pass on the library's stream keeps running
-            self.shard.shard_insert_slots(recv.data_ptr(), W, cap, beside=not final)
+            self._owner_round(recv.data_ptr(), cap, self._plan[ff]["units"], ff, beside=not final)
             self._keep += [recv, send]
 
     def _route_names(self, f, with_bytes=True):
@@ -435,33 +466,54 @@ class ShardedFastqInfo:
         return recv_meta, recv_blob, ms, bs
 
     # ------------------------------------------------------------------ one job
-    def run_device(self, ptr, nbytes, name="-", ptr2=None, nbytes2=0, name2=None, empty_ok=False, no_enc_ok=False, _exact=False, _gather0=False, _seed=0):
+    def run_device(self, ptr, nbytes, name="-", ptr2=None, nbytes2=0, name2=None, empty_ok=False, no_enc_ok=False, _exact=False, _gather0=False):
         """ptr/nbytes (and ptr2/nbytes2 for MODE_INDEX_PAIR): this rank's byte range of each file in device memory (16-byte
         aligned, 64 readable bytes after it).  Returns the merged report and, on rank 0, the rendered (rc, stdout, stderr)."""
         W, r, ctx = self.world, self.rank, self.ctx
         ctx.reset()
         if self.shard:
             self.shard.reset()
-        if _seed:
-            ctx.set_hash_seed(_seed)
         self._keep = []
         pair = self.mode == api.MODE_INDEX_PAIR
-        again = dict(name=name, ptr2=ptr2, nbytes2=nbytes2, name2=name2, empty_ok=empty_ok, no_enc_ok=no_enc_ok, _exact=True, _seed=_seed)
+        again = dict(name=name, ptr2=ptr2, nbytes2=nbytes2, name2=name2, empty_ok=empty_ok, no_enc_ok=no_enc_ok, _exact=True)
         routed = self.shard is not None and self.pipeline
         self.rounds_done = 0
         # (a world of one takes the same path when it has an index shard: the single-GPU tests of the pipelined routing)
-        speculative = (not _exact) and (W > 1 or routed) and not pair and self._feed_file_speculative(0, ptr, nbytes, routed=routed)
+        speculative = (not _exact) and (W > 1 or routed) and (routed or not pair)
+        files = [(0, ptr, nbytes)] + ([(1, ptr2, nbytes2)] if pair else [])
         if speculative:
+            # every rank guesses the line phase of its ranges from their own first lines; rank 0, which holds the first record of each
+            # file, sniffs the read-name format and colour space (src/fastq.c:459-485); all of it travels in one gather
+            mine = [self._guess_phase(p, n) + (n,) for _, p, n in files]
+            sn = [ctx.sniff_device(f, p, n, 0) if (r == 0 and n >= 4096) else None for f, p, n in files]
+            got = self._gather((mine, sn))
+            infos = [[g[0][k] for g in got] for k in range(len(files))]
+            self._sniff = got[0][1]
+            speculative = all(all(x[0] for x in info) and info[0][1] == 0 for info in infos) and all(x is not None for x in self._sniff)
+        if speculative:
+            if routed:
+                self._plan_routes(infos, pair)
+            if pair:
+                ctx.set_file_total(0, 1 << 40)  # (the mate loop's event keys continue after file 1's: only their order matters here)
+            for (f, p, n), info in zip(files, infos):
+                self._feed_file_speculative(f, p, n, info, routed=routed)
             rep = ctx.finish()
             # a NUL-led header line ended this rank's range early and quietly (src/fastq.c:248): not an error here, but the ranges
             # behind it do not exist for the reference — the exact path sorts that out
-            cut_short = int(rep.file[0].n_records) < ctx.records_fed(0)
+            cut_short = any(int(rep.file[f].n_records) < ctx.records_fed(f) for f, _, _ in files)
+            claimed = 0
             if routed:
-                # the names went to their owners while the range was validated (tuples only): an equal hash, a region or table that
-                # overflowed, a chunk that was redone by the two-pass kernels after its names had left, or any error decides nothing here
-                inserted, equal, overflow = self.shard.shard_slots_result()
-                mine_bad = rep.error.code != 0 or cut_short or equal > 0 or overflow or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
-                bad = any(self._gather(bool(mine_bad)))
+                # The names went to their owners while the ranges were validated.  One file: tuples only — an equal hash decides
+                # nothing.  Two files: with their bytes — the owner knows a duplicate, an unpaired mate or a name left over when it
+                # sees one, but the reference's message (which record, which line) is the exact path's business.  So is a region,
+                # slot or table that overflowed, a chunk redone by the two-pass kernels after its names had left, and any error.
+                inserted, equal, overflow, claimed, unpaired = self.shard.shard_slots_result()
+                mine_bad = rep.error.code != 0 or cut_short or equal > 0 or unpaired > 0 or overflow or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
+                sums = self._gather((bool(mine_bad), inserted, claimed, int(rep.n_index_entries), int(rep.file[1].n_records)))
+                bad = any(x[0] for x in sums)
+                tot_ins, tot_cl, tot_names, tot_mates = (sum(x[k] for x in sums) for k in (1, 2, 3, 4))
+                if tot_ins != tot_names or (pair and (tot_cl != tot_names or tot_cl != tot_mates)):
+                    bad = True  # a name was dropped on its way, a mate found nothing to claim, or names of file 1 are left over
                 if self._hook_exc is not None:
                     raise self._hook_exc
             else:
@@ -474,7 +526,7 @@ class ShardedFastqInfo:
                 self.exact_reruns += 1
                 return self.run_device(ptr, nbytes, **again)  # an error, a duplicate name or a wrong guess: the exact path decides
             local_key, T0, T1 = KEY_NONE, 0, 0
-            dup, unp, claimed = (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), 0
+            dup, unp = (KEY_NONE, 0, b""), (KEY_NONE, 0, b"")
         if not speculative:
             exp0, T0 = self._feed_file(0, ptr, nbytes, gather0=_gather0)
             exp1, T1 = None, 0
@@ -517,15 +569,10 @@ class ShardedFastqInfo:
                     ukey, urec, uname, claimed, coll2 = self.shard.shard_claim_result()
                     unp = (ukey, urec, uname)
                     coll += coll2
-                if os.environ.get("FQG_TEST_FAKE_COLLISION") and _seed == 0:  # test hook: pretend that seed 0 made two names collide
-                    coll += 1
+                # (two different names with one 64-bit hash are no event any more: the owners compare the bytes behind every equal
+                # hash and walk on to the next slot, like the reference walks its chain, src/hash.c:38-45)
                 if sum(self._gather(coll)):
-                    # two different names with one 64-bit hash (the owners compared the bytes): the hash is unobservable, so the job is
-                    # simply repeated with the next seed, like the one-GPU engine does by itself (fq_engine.cpp: finish)
-                    if _seed >= 4:
-                        raise RuntimeError("64-bit name hash collisions with five seeds in a row")
-                    self.exact_reruns += 1
-                    return self.run_device(ptr, nbytes, **dict(again, _gather0=_gather0, _seed=_seed + 1))
+                    raise RuntimeError("internal: an owner could not judge an equal hash although the name bytes travelled")
         # -- 4. merge
         f0, f1 = rep.file[0], rep.file[1]
         mine = {"key": local_key, "dup": dup, "unp": unp, "claimed": claimed,

@@ -205,19 +205,29 @@ typedef void (*fqg_chunk_hook)(void* user, int file);
 int fqg_set_chunk_hook(fqg_ctx* ctx, fqg_chunk_hook hook, void* user);
 /* records whose names were not packed by fqg_names_pack_slots yet */
 int fqg_names_new(fqg_ctx* ctx, int file, uint64_t* n_new);
-/* Packs the 24-byte tuples of those records by owner into `world` regions of fixed capacity: region o starts at
- * region_ptrs[o] (device memory, local or a peer's mapped with fqg_ipc_open), holds one 24-byte header {count, 0, 0} and
- * then up to region_cap tuples.  A count above region_cap says the region overflowed (the surplus tuples are dropped): the owner
- * reports it and the caller repeats the job through the exact path.  Returns when the regions are complete. */
-int fqg_names_pack_slots(fqg_ctx* ctx, int file, uint32_t world, void* const* region_ptrs, uint64_t region_cap);
+/* Packs those records' names by owner into `world` regions of fixed capacity.  A name travels as a slot of 16 + 16 * name_units
+ * bytes: {hash, record << 12 | length} and name_units 16-byte units of its bytes, zero padded (name_units = 0: the tuple alone —
+ * enough for a one-file job, whose owner only has to notice equal hashes; a two-file job needs the bytes, the mate loop compares
+ * every name).  Region o starts at region_ptrs[o] (device memory, local or a peer's mapped with fqg_ipc_open): one 16-byte header
+ * {count, flags} and room for region_cap slots; fqg_route_region_bytes() bytes in all.  A count above region_cap says the region
+ * overflowed (the surplus is dropped), flag 1 that a name was longer than its slot: the owner reports either and the caller repeats
+ * the job through the exact path.  Returns when the regions are complete. */
+int fqg_names_pack_slots(fqg_ctx* ctx, int file, uint32_t world, void* const* region_ptrs, uint64_t region_cap, uint32_t name_units);
+static inline size_t fqg_route_region_bytes(uint64_t region_cap, uint32_t name_units) { return 16u + (size_t)region_cap * (16u + 16u * (size_t)name_units); }
 /* owner side: room for n_names in the index shard before the first fqg_shard_insert_slots (the table cannot grow between rounds) */
 int fqg_shard_reserve(fqg_ctx* ctx, uint64_t n_names);
-/* inserts the tuples of n_src regions (region s at regions + s * 24 * (region_cap + 1)); asynchronous: the regions must stay
- * valid until fqg_shard_slots_result.  beside != 0: one block per SM, so that the kernel fits next to a running clean-data pass. */
-int fqg_shard_insert_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, uint64_t region_cap, int beside);
-/* waits for the inserts: tuples inserted, equal hashes met (a duplicate name or a 64-bit collision: tuples alone cannot tell),
- * and whether a region or the table overflowed.  Any non-zero `equal_hashes` / `overflow` sends the job through the exact path. */
-int fqg_shard_slots_result(fqg_ctx* ctx, uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow);
+/* inserts the slots of n_src regions (one after the other, fqg_route_region_bytes each); asynchronous: the regions must stay valid
+ * until fqg_shard_slots_result — the index points at the names inside them.  beside != 0: one block per SM, so that the kernel fits
+ * next to a running clean-data pass. */
+int fqg_shard_insert_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, uint64_t region_cap, uint32_t name_units, int beside);
+/* the mate loop at the owner (src/fastq_info.c:333-350): the slots of file 2's names (name_units > 0) look their name up by hash and
+ * bytes and claim it (the reference's lookup-then-delete) */
+int fqg_shard_claim_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, uint64_t region_cap, uint32_t name_units, int beside);
+/* waits for the inserts and claims: names inserted; names that were in the index already (name_units = 0: equal hashes, which
+ * tuples alone cannot tell from a duplicate); whether a region, a slot or the table overflowed; names claimed by mates; mates that
+ * found no name, or one that had been claimed before.  Anything but inserted == names of file 1, claimed == inserted == mates
+ * sends the job through the exact path, which reports what the reference reports. */
+int fqg_shard_slots_result(fqg_ctx* ctx, uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow, uint64_t* claimed, uint64_t* unpaired);
 /* device memory other processes of this node can map (CUDA IPC): the owner's regions written by its peers' pack kernels
  * over NVLink instead of an all-to-all.  fqg_ipc_alloc returns the pointer and a 64-byte handle; fqg_ipc_open maps a peer's. */
 /* device-to-device copy on the context's side stream (the copy engines move a packed region into a peer's arena while the SMs

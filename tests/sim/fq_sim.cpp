@@ -245,37 +245,72 @@ class FqSimDevice : public FqDevice {
       if (unpaired != FQ_IDX_NONE) { unsigned long long key = FQ_KEY(sb + unpaired, FQ_R_NAME); if (key < *a.dup_key) *a.dup_key = key; }
     }
   }
-  void route_begin(unsigned long long* cursors, uint32_t world, bool) override { memset(cursors, 0, world * sizeof(unsigned long long)); }
-  void names_pack_slots(const FqName* names, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
-                        unsigned long long* cursors) override {
+  void route_begin(unsigned long long* cursors, uint32_t, bool) override { memset(cursors, 0, 2 * FQ_SHARD_MAX_SRC * sizeof(unsigned long long)); }
+  void names_pack_slots(const FqName* names, const uint8_t* arena, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
+                        uint32_t units, unsigned long long* cursors) override {
     n_launch_++;
+    const size_t sb = fq_route_slot_bytes(units);
     for (uint32_t k = 0; k < nrec; k++) {
       const FqName& nm = names[k];
       if (nm.hash == FQ_HASH_SKIP) continue;
       uint32_t o = fq_owner_of(nm.hash, world);
       unsigned long long pos = cursors[o]++;
-      if (pos < cap) { FqPackedName& pn = R.region[o][1 + pos]; pn.hash = nm.hash; pn.record = g0 + k; pn.off = 0; pn.len = nm.len; }
+      if (pos >= cap) continue;
+      uint8_t* slot = R.region[o] + 16 + pos * sb;
+      FqRouteSlot h; h.hash = nm.hash; h.rec_len = ((unsigned long long)(g0 + k) << 12) | nm.len;
+      memcpy(slot, &h, 16);
+      if (units) { memset(slot + 16, 0, (size_t)units * 16); memcpy(slot + 16, arena + nm.off, std::min<size_t>(nm.len, (size_t)units * 16)); }
+      if (units && nm.len > 16u * units) cursors[FQ_SHARD_MAX_SRC + o] |= FQ_ROUTE_NAME_TOO_LONG;
     }
   }
   void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R) override {
-    for (uint32_t o = 0; o < world; o++) { FqPackedName& h = R.region[o][0]; h.hash = cursors[o]; h.record = 0; h.off = 0; h.len = 0; }
+    for (uint32_t o = 0; o < world; o++) { unsigned long long* h = (unsigned long long*)R.region[o]; h[0] = cursors[o]; h[1] = cursors[FQ_SHARD_MAX_SRC + o]; }
   }
-  void shard_insert_slots(const FqPackedName* regions, uint32_t n_src, uint64_t cap, FqSlot* slots, unsigned long long mask,
+  static bool same_name(unsigned long long idx1, const FqRouteSlot* sl) {
+    const FqRouteSlot* other = (const FqRouteSlot*)(uintptr_t)(idx1 << 4);
+    uint32_t len = (uint32_t)(sl->rec_len & 0xFFF);
+    return (uint32_t)(other->rec_len & 0xFFF) == len && memcmp(other + 1, sl + 1, len) == 0;
+  }
+  void shard_insert_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
                           unsigned long long* counters, bool) override {
     n_launch_++;
+    const size_t sb = fq_route_slot_bytes(units), rb = fq_route_region_bytes(cap, units);
     for (uint32_t src = 0; src < n_src; src++) {
-      const FqPackedName* reg = regions + (size_t)src * (cap + 1);
-      unsigned long long cnt = reg[0].hash;
-      if (cnt > cap) { counters[2] = 1; cnt = cap; }
+      const uint8_t* reg = regions + (size_t)src * rb;
+      unsigned long long cnt = ((const unsigned long long*)reg)[0];
+      if (cnt > cap || ((const unsigned long long*)reg)[1]) { counters[2] = 1; cnt = std::min<unsigned long long>(cnt, cap); }
       for (unsigned long long m = 0; m < cnt; m++) {
-        const FqPackedName& pn = reg[1 + m];
-        unsigned long long i = pn.hash & mask, probes = 0;
+        const FqRouteSlot* sl = (const FqRouteSlot*)(reg + 16 + m * sb);
+        unsigned long long i = sl->hash & mask, probes = 0;
         for (;; i = (i + 1) & mask) {
           if (++probes > mask) { counters[2] = 1; break; }
           FqSlot& s = slots[i];
-          if (s.hash == FQ_HASH_EMPTY) { s.hash = pn.hash; s.idx1 = pn.record; counters[1]++; break; }
-          if (s.hash != pn.hash) continue;
+          if (s.hash == FQ_HASH_EMPTY) { s.hash = sl->hash; s.idx1 = (unsigned long long)(uintptr_t)sl >> 4; counters[1]++; break; }
+          if (s.hash != sl->hash) continue;
+          if (units && !same_name(s.idx1, sl)) continue;
           counters[0]++;
+          break;
+        }
+      }
+    }
+  }
+  void shard_claim_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
+                         unsigned long long* counters, bool) override {
+    n_launch_++;
+    const size_t sb = fq_route_slot_bytes(units), rb = fq_route_region_bytes(cap, units);
+    for (uint32_t src = 0; src < n_src; src++) {
+      const uint8_t* reg = regions + (size_t)src * rb;
+      unsigned long long cnt = ((const unsigned long long*)reg)[0];
+      if (cnt > cap || ((const unsigned long long*)reg)[1]) { counters[2] = 1; cnt = std::min<unsigned long long>(cnt, cap); }
+      for (unsigned long long m = 0; m < cnt; m++) {
+        const FqRouteSlot* sl = (const FqRouteSlot*)(reg + 16 + m * sb);
+        unsigned long long i = sl->hash & mask, probes = 0;
+        for (;; i = (i + 1) & mask) {
+          if (++probes > mask + 1) { counters[9]++; break; }
+          FqSlot& s = slots[i];
+          if (s.hash == FQ_HASH_EMPTY) { counters[9]++; break; }
+          if (s.hash != sl->hash || !same_name(s.idx1, sl)) continue;
+          if (s.claim2 == FQ_IDX_NONE) { s.claim2 = sl->rec_len >> 12; counters[8]++; } else counters[9]++;
           break;
         }
       }

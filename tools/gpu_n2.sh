@@ -1,11 +1,6 @@
 #!/bin/bash
-# N-GPU check (default 2): sharded parity over NCCL + CUDA IPC, then the sharded bench under the routing variants of dist.py
-#   bash tools/gpu_n2.sh [N]        (QUICK=1: the default routing only)
+# 2 GPUs: the sharded tests, then the paired bench (arguments: extra bench.py flags)
 cd "$(dirname "$0")/.."
-N=${1:-2}
-timeout 300 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -8
-if [ -n "$QUICK" ]; then
-  bash tools/gpu_n2_sweep.sh "$N" "FQG_P2P=1"
-else
-  bash tools/gpu_n2_sweep.sh "$N" "FQG_P2P=1" "FQG_P2P_STORES=1" "FQG_P2P=0" "FQG_NO_PIPELINE=1"
-fi
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_dist.py -m gpu -x -q 2>&1 | tail -5
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 "$@" > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; tail -5 gpurun_out/bench_n2.err; cat gpurun_out/bench_n2.json
