@@ -108,8 +108,12 @@ def bind(L):
     L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
     L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64, ctypes.c_uint32]
     L.fqg_shard_reserve.argtypes = [vp, u64]
-    L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ctypes.c_uint32, ci]
-    L.fqg_shard_claim_slots.argtypes = [vp, vp, ctypes.c_uint32, u64, ctypes.c_uint32, ci]
+    L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, sz, ctypes.c_uint32, u64, ctypes.c_uint32, ci]
+    L.fqg_shard_claim_slots.argtypes = [vp, vp, ctypes.c_uint32, sz, ctypes.c_uint32, u64, ctypes.c_uint32, ci]
+    L.fqg_set_route.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), sz, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+    L.fqg_route_chunks.argtypes = [vp, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
+    L.fqg_route_blocks.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
+    L.fqg_side_mark.argtypes = [vp]
     L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.fqg_side_copy.argtypes = [vp, vp, vp, sz]
     L.fqg_side_sync.argtypes = [vp]
@@ -299,11 +303,29 @@ class FastqInfo:
     def shard_reserve(self, n_names):
         _check(self._ctx, lib().fqg_shard_reserve(self._ctx, n_names), "fqg_shard_reserve")
 
-    def shard_insert_slots(self, regions_ptr, n_src, cap, beside, units=0):
-        _check(self._ctx, lib().fqg_shard_insert_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, cap, units, 1 if beside else 0), "fqg_shard_insert_slots")
+    def shard_insert_slots(self, regions_ptr, n_src, region_bytes, nblocks, stride, beside, units=0):
+        _check(self._ctx, lib().fqg_shard_insert_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, region_bytes, nblocks, stride, units, 1 if beside else 0), "fqg_shard_insert_slots")
 
-    def shard_claim_slots(self, regions_ptr, n_src, cap, beside, units):
-        _check(self._ctx, lib().fqg_shard_claim_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, cap, units, 1 if beside else 0), "fqg_shard_claim_slots")
+    def shard_claim_slots(self, regions_ptr, n_src, region_bytes, nblocks, stride, beside, units):
+        _check(self._ctx, lib().fqg_shard_claim_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, region_bytes, nblocks, stride, units, 1 if beside else 0), "fqg_shard_claim_slots")
+
+    def set_route(self, file, region_ptrs, region_bytes, depth, stride, units):
+        """the clean-data pass of every chunk of `file` writes the names into per-owner regions itself (include/fastq_gpu.h); [] switches it off"""
+        arr = (ctypes.c_void_p * max(1, len(region_ptrs)))(*region_ptrs)
+        _check(self._ctx, lib().fqg_set_route(self._ctx, file, len(region_ptrs), arr, region_bytes, depth, stride, units), "fqg_set_route")
+
+    def route_chunks(self, file):
+        n, b = ctypes.c_uint64(), ctypes.c_int32()
+        _check(self._ctx, lib().fqg_route_chunks(self._ctx, file, ctypes.byref(n), ctypes.byref(b)), "fqg_route_chunks")
+        return int(n.value), bool(b.value)
+
+    def route_blocks(self):
+        n = ctypes.c_uint32()
+        _check(self._ctx, lib().fqg_route_blocks(self._ctx, ctypes.byref(n)), "fqg_route_blocks")
+        return int(n.value)
+
+    def side_mark(self):
+        _check(self._ctx, lib().fqg_side_mark(self._ctx), "fqg_side_mark")
 
     def shard_slots_result(self):
         """(inserted, names already there / equal hashes, overflow, claimed by mates, mates without a fresh partner)"""
@@ -367,9 +389,9 @@ class FastqInfo:
         return int(n.value), list(starts[:min(cap, n.value)])
 
 
-def route_region_bytes(cap, units):
+def route_region_bytes(nblocks, stride, units):
     """bytes of one routing region (include/fastq_gpu.h: fqg_route_region_bytes)"""
-    return 16 + cap * (16 + 16 * units)
+    return 16 + ((nblocks * 4 + 15) & ~15) + nblocks * stride * (16 + 16 * units)
 
 
 def feed_chunk_bytes():

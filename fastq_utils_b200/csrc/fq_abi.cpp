@@ -163,13 +163,29 @@ extern "C" int fqg_shard_reserve(fqg_ctx* c, uint64_t n_names) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->eng->shard_reserve(n_names))
 }
-extern "C" int fqg_shard_claim_slots(fqg_ctx* c, const void* regions, uint32_t n_src, uint64_t region_cap, uint32_t name_units, int beside) {
+extern "C" int fqg_shard_claim_slots(fqg_ctx* c, const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside) {
   if (!c || !regions) return FQG_ERR_USAGE;
-  FQG_GUARD(c, c->eng->shard_claim_slots(regions, n_src, region_cap, name_units, beside != 0))
+  FQG_GUARD(c, c->eng->shard_claim_slots(regions, n_src, region_bytes, nblocks, stride, name_units, beside != 0))
 }
-extern "C" int fqg_shard_insert_slots(fqg_ctx* c, const void* regions, uint32_t n_src, uint64_t region_cap, uint32_t name_units, int beside) {
-  if (!c || !regions || !region_cap) return FQG_ERR_USAGE;
-  FQG_GUARD(c, c->eng->shard_insert_slots(regions, n_src, region_cap, name_units, beside != 0))
+extern "C" int fqg_shard_insert_slots(fqg_ctx* c, const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside) {
+  if (!c || !regions) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->shard_insert_slots(regions, n_src, region_bytes, nblocks, stride, name_units, beside != 0))
+}
+extern "C" int fqg_set_route(fqg_ctx* c, int file, uint32_t world, void* const* region_ptrs, size_t region_bytes, uint32_t depth, uint32_t stride, uint32_t name_units) {
+  if (!c || file < 0 || file > 1 || (world && !region_ptrs)) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->eng->set_route(file, world, region_ptrs, region_bytes, depth, stride, name_units))
+}
+extern "C" int fqg_route_chunks(fqg_ctx* c, int file, uint64_t* n_chunks, int32_t* broken) {
+  if (!c || file < 0 || file > 1 || !n_chunks || !broken) return FQG_ERR_USAGE;
+  FQG_GUARD(c, { int b = 0; *n_chunks = c->eng->route_chunks(file, &b); *broken = b; })
+}
+extern "C" int fqg_route_blocks(fqg_ctx* c, uint32_t* nblocks) {
+  if (!c || !nblocks) return FQG_ERR_USAGE;
+  FQG_GUARD(c, *nblocks = c->dev->lanes_max_blocks())
+}
+extern "C" int fqg_side_mark(fqg_ctx* c) {
+  if (!c) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->dev->side_mark())
 }
 extern "C" int fqg_shard_slots_result(fqg_ctx* c, uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow, uint64_t* claimed, uint64_t* unpaired) {
   if (!c || !inserted || !equal_hashes || !overflow) return FQG_ERR_USAGE;

@@ -816,19 +816,24 @@ fq_names_pack_slots_kernel(const SlotPackParams P) {
       const uint32_t o = fq_owner_of(nm[j].hash, P.world);
       const unsigned long long pos = s_base[o] + my[j];
       if (pos >= P.cap) continue; /* counted, not stored: the header's count tells the owner */
-      uint4* slot = (uint4*)(P.R.region[o] + 16 + pos * slot_bytes);
+      uint4* slot = (uint4*)(P.R.region[o] + 16 + fq_route_counts_bytes(1) + pos * slot_bytes); /* one writer: one stretch of `cap` slots */
       const unsigned long long rec = P.g0 + b0 + j * 256u + threadIdx.x, rl = (rec << 12) | nm[j].len;
       slot[0] = make_uint4((uint32_t)nm[j].hash, (uint32_t)(nm[j].hash >> 32), (uint32_t)rl, (uint32_t)(rl >> 32));
       for (uint32_t u = 0; u < P.units; u++)
         slot[1 + u] = 16u * u < nm[j].len ? *(const uint4*)(P.arena + nm[j].off + 16u * u) : make_uint4(0u, 0u, 0u, 0u);
-      if (P.units && nm[j].len > 16u * P.units) atomicOr(P.cursors + FQ_SHARD_MAX_SRC + o, FQ_ROUTE_NAME_TOO_LONG);
+      if (P.units && nm[j].len > 16u * P.units) atomicOr(P.cursors + FQ_SHARD_MAX_SRC + o, (unsigned long long)FQ_ROUTE_NAME_TOO_LONG);
     }
     __syncthreads();
   }
 }
-struct SlotHeaderParams { const unsigned long long* cursors; uint32_t world; FqRegionPtrs R; };
+struct SlotHeaderParams { const unsigned long long* cursors; uint32_t world; unsigned long long cap; FqRegionPtrs R; };
 __global__ void fq_slots_header_kernel(const SlotHeaderParams P) {
-  if (threadIdx.x < P.world) { unsigned long long* h = (unsigned long long*)P.R.region[threadIdx.x]; h[0] = P.cursors[threadIdx.x]; h[1] = P.cursors[FQ_SHARD_MAX_SRC + threadIdx.x]; }
+  if (threadIdx.x < P.world) {
+    FqRegionHdr h; h.nblocks = 1; h.stride = (uint32_t)P.cap; h.flags = (uint32_t)P.cursors[FQ_SHARD_MAX_SRC + threadIdx.x]; h.pad = 0;
+    *(FqRegionHdr*)P.R.region[threadIdx.x] = h;
+    const unsigned long long c = P.cursors[threadIdx.x];
+    *(uint32_t*)(P.R.region[threadIdx.x] + 16) = c > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c; /* a count above the stride: the surplus was dropped */
+  }
 }
 /* the name a table slot points at (idx1 = address >> 4 of a route slot in this rank's own memory) against the name of route slot `sl` */
 __device__ __forceinline__ bool route_same_name(unsigned long long idx1, const FqRouteSlot* sl) {
@@ -839,24 +844,37 @@ __device__ __forceinline__ bool route_same_name(unsigned long long idx1, const F
   for (uint32_t u = 0; 16u * u < len; u++) { const uint4 x = a[u], y = b[u]; if ((x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w)) return false; }
   return true;
 }
-struct SlotInsertParams { const uint8_t* regions; uint32_t n_src; unsigned long long cap; uint32_t units; FqSlot* slots; unsigned long long mask; unsigned long long* counters; };
+struct SlotInsertParams {
+  const uint8_t* regions; uint32_t n_src; size_t region_bytes; uint32_t nblocks; unsigned long long stride; uint32_t units;
+  FqSlot* slots; unsigned long long mask; unsigned long long* counters;
+};
+/* item m of the planned n_src x nblocks x stride slots → the route slot, or NULL when the stretch holds fewer */
+__device__ __forceinline__ const FqRouteSlot* route_item(const SlotInsertParams& P, unsigned long long m, size_t slot_bytes) {
+  const unsigned long long per = (unsigned long long)P.nblocks * P.stride;
+  const unsigned long long src = m / per, in = m - src * per, b = in / P.stride, k = in - b * P.stride;
+  const uint8_t* reg = P.regions + src * P.region_bytes;
+  const FqRegionHdr h = *(const FqRegionHdr*)reg;
+  if (h.nblocks == 0) return nullptr; /* this source had nothing for us in this round */
+  if (in == 0 && (h.nblocks > P.nblocks || h.stride != P.stride || h.flags)) atomicExch(P.counters + 2, 1ull); /* not what was planned, or a name longer than its slot */
+  if (b >= h.nblocks) return nullptr;
+  const uint32_t cnt = ((const uint32_t*)(reg + 16))[b];
+  if (k == 0 && cnt > P.stride) atomicExch(P.counters + 2, 1ull); /* the writer had more names for this owner than its stretch holds */
+  if (k >= cnt) return nullptr;
+  return (const FqRouteSlot*)(reg + 16 + fq_route_counts_bytes(h.nblocks) + (b * P.stride + k) * slot_bytes);
+}
 __global__ void __launch_bounds__(256, 8)
 fq_shard_insert_slots_kernel(const SlotInsertParams P) {
   /* One probe in flight per thread.  Measured on B200 beside the pass: 2 or 4 independent first probes per thread are slower (the
    * atomics, not their latency, are the limit), and so are short blocks on a low-priority stream (they crowd the start of the
    * next pass, whose blocks must all be resident). */
   unsigned long long inserted = 0, equal = 0;
-  const unsigned long long total = (unsigned long long)P.n_src * P.cap, step = (unsigned long long)gridDim.x * blockDim.x;
-  const size_t slot_bytes = fq_route_slot_bytes(P.units), region_bytes = fq_route_region_bytes(P.cap, P.units);
+  const unsigned long long total = (unsigned long long)P.n_src * P.nblocks * P.stride, step = (unsigned long long)gridDim.x * blockDim.x;
+  const size_t slot_bytes = fq_route_slot_bytes(P.units);
   for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
     const unsigned long long m = m0 + threadIdx.x;
     if (m >= total) continue;
-    const unsigned long long src = m / P.cap, idx = m - src * P.cap;
-    const uint8_t* reg = P.regions + src * region_bytes;
-    const unsigned long long cnt = ((const unsigned long long*)reg)[0];
-    if (idx == 0 && (cnt > P.cap || ((const unsigned long long*)reg)[1])) atomicExch(P.counters + 2, 1ull); /* more names than the region holds, or a name longer than its slot */
-    if (idx >= cnt) continue;
-    const FqRouteSlot* sl = (const FqRouteSlot*)(reg + 16 + idx * slot_bytes);
+    const FqRouteSlot* sl = route_item(P, m, slot_bytes);
+    if (!sl) continue;
     const unsigned long long hash = sl->hash, me = (unsigned long long)(uintptr_t)sl >> 4;
     unsigned long long i = hash & P.mask, probes = 0;
     for (;; i = (i + 1) & P.mask) {
@@ -876,17 +894,13 @@ fq_shard_insert_slots_kernel(const SlotInsertParams P) {
 __global__ void __launch_bounds__(256, 8)
 fq_shard_claim_slots_kernel(const SlotInsertParams P) {
   unsigned long long claimed = 0, unpaired = 0;
-  const unsigned long long total = (unsigned long long)P.n_src * P.cap, step = (unsigned long long)gridDim.x * blockDim.x;
-  const size_t slot_bytes = fq_route_slot_bytes(P.units), region_bytes = fq_route_region_bytes(P.cap, P.units);
+  const unsigned long long total = (unsigned long long)P.n_src * P.nblocks * P.stride, step = (unsigned long long)gridDim.x * blockDim.x;
+  const size_t slot_bytes = fq_route_slot_bytes(P.units);
   for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
     const unsigned long long m = m0 + threadIdx.x;
     if (m >= total) continue;
-    const unsigned long long src = m / P.cap, idx = m - src * P.cap;
-    const uint8_t* reg = P.regions + src * region_bytes;
-    const unsigned long long cnt = ((const unsigned long long*)reg)[0];
-    if (idx == 0 && (cnt > P.cap || ((const unsigned long long*)reg)[1])) atomicExch(P.counters + 2, 1ull);
-    if (idx >= cnt) continue;
-    const FqRouteSlot* sl = (const FqRouteSlot*)(reg + 16 + idx * slot_bytes);
+    const FqRouteSlot* sl = route_item(P, m, slot_bytes);
+    if (!sl) continue;
     const unsigned long long hash = sl->hash, rec = sl->rec_len >> 12;
     unsigned long long i = hash & P.mask, probes = 0;
     for (;; i = (i + 1) & P.mask) {
@@ -1061,6 +1075,7 @@ class FqCudaDevice : public FqDevice {
     FQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st2_, cudaStreamNonBlocking));
     FQ_CUDA_CHECK(cudaEventCreateWithFlags(&evx_, cudaEventDisableTiming));
     FQ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_pre_, cudaEventDisableTiming));
+    FQ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side_, cudaEventDisableTiming));
     FQ_CUDA_CHECK(cudaEventCreate(&ev0_)); FQ_CUDA_CHECK(cudaEventCreate(&ev1_));
     cudaMemPool_t pool; FQ_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev_));
     unsigned long long thr = ~0ull; /* keep freed blocks in the pool: allocations repeat every chunk */
@@ -1076,7 +1091,7 @@ class FqCudaDevice : public FqDevice {
     for (auto& d : deferred_) cudaEventDestroy(d.ready);
     for (auto e : free_ev_) cudaEventDestroy(e);
     cudaFree(tile_state_); if (stage_) cudaFree(stage_);
-    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_); cudaEventDestroy(ev_pre_);
+    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_); cudaEventDestroy(ev_pre_); cudaEventDestroy(ev_side_);
     cudaStreamDestroy(st_); cudaStreamDestroy(st2_);
   }
   const char* name() const override { return "cuda"; }
@@ -1190,23 +1205,19 @@ class FqCudaDevice : public FqDevice {
     const uint32_t tile_bytes = lines_mode ? LS_TILE : LN_TILE;
     uint32_t ntiles = (a.n + tile_bytes - 1) / tile_bytes;
     if (ntiles > max_tiles_) return false;
-    if (lanes_blocks_ == 0) {
-      FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
-      FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
-      int per_sm = 0, per_sm2 = 0;
-      FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fq_lanes_kernel<false>, LN_THREADS, LN_SMEM));
-      FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, fq_lanes_kernel<true>, LN_THREADS, LN_SMEM));
-      per_sm = std::min(per_sm, per_sm2);
-      if (per_sm < 1) return false;
-      if (const char* e = getenv("FQG_LANES_CTAS")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; } /* tuning hook: leave room for the index kernel */
-      lanes_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
-    }
+    ensure_lanes_blocks();
+    if (lanes_blocks_ < 1) return false;
     LanesParams P;
     P.data = a.data; P.lead = a.lead; P.n = a.n; P.virtual_end = a.virtual_end; P.line_end = a.line_end; P.cap = a.cap;
     P.tile_state = tile_state_; P.ticket = ticket_; P.ntiles = ntiles; P.out = a.out5;
     P.j0 = a.j0; P.cx = a.cx; P.names = a.names; P.names_cap = a.names_cap;
     if (!stage_) FQ_CUDA_CHECK(cudaMalloc(&stage_, sizeof(LanesStage)));
     P.stage = stage_; P.arena = lines_mode ? a.arena : nullptr; P.arena_units = a.arena_units;
+    P.route_world = lines_mode ? a.route_world : 0; P.route_stride = a.route_stride; P.route_units = a.route_units;
+    for (int o = 0; o < FQ_ROUTE_MAX_WORLD; o++) P.route_region[o] = a.route_region[o];
+    if (a.route_world && !lines_mode) return false; /* only the per-line mode routes names itself */
+    if (side_marked_) { FQ_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_side_, 0)); side_marked_ = false; } /* copies out of the regions this pass overwrites */
+    for (uint32_t o = 0; o < P.route_world; o++) FQ_CUDA_CHECK(cudaMemsetAsync(P.route_region[o], 0, sizeof(FqRegionHdr), st_)); /* (flags are or-ed in; nblocks = 0 until the pass is through) */
     { const char* e = getenv("FQG_LANES_TUNE"); P.tune = e ? (uint32_t)atoi(e) : 0u; }
     FQ_CUDA_CHECK(cudaEventRecord(ev_pre_, st_));
     if (lines_mode) FQ_CUDA_CHECK(cudaMemsetAsync(stage_, 0, sizeof(LanesStage), st_));
@@ -1240,6 +1251,18 @@ class FqCudaDevice : public FqDevice {
     if (undo) { lanes_records(a, true); return; }
     fq_lanes_commit_kernel<<<1, 32, 0, st_>>>(a.out5, a.stats_range);
     launched();
+  }
+  void ensure_lanes_blocks() {
+    if (lanes_blocks_ != 0) return;
+    FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    FQ_CUDA_CHECK(cudaFuncSetAttribute(fq_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM));
+    int per_sm = 0, per_sm2 = 0;
+    FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fq_lanes_kernel<false>, LN_THREADS, LN_SMEM));
+    FQ_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, fq_lanes_kernel<true>, LN_THREADS, LN_SMEM));
+    per_sm = std::min(per_sm, per_sm2);
+    if (per_sm < 1) { lanes_blocks_ = -1; return; }
+    if (const char* e = getenv("FQG_LANES_CTAS")) { int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; } /* tuning hook: leave room for the index kernel */
+    lanes_blocks_ = per_sm * sms_; /* every CTA resident: the look-back may wait on any earlier tile */
   }
   static TableParams table_params(const FqTableArgs& a) {
     TableParams P;
@@ -1341,27 +1364,30 @@ class FqCudaDevice : public FqDevice {
     fq_names_pack_slots_kernel<<<grid, 256, 0, st2_>>>(P);
     toc(st2_); launched();
   }
-  void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R) override {
-    SlotHeaderParams P; P.cursors = cursors; P.world = world; P.R = R;
+  void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R, uint64_t cap) override {
+    SlotHeaderParams P; P.cursors = cursors; P.world = world; P.cap = cap; P.R = R;
     fq_slots_header_kernel<<<1, FQ_SHARD_MAX_SRC, 0, st2_>>>(P);
     launched();
     FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
   }
-  void shard_insert_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
-                          unsigned long long* counters, bool beside) override { slots_kernel(regions, n_src, cap, units, slots, mask, counters, beside, false); }
-  void shard_claim_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
-                         unsigned long long* counters, bool beside) override { slots_kernel(regions, n_src, cap, units, slots, mask, counters, beside, true); }
-  void slots_kernel(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
-                    unsigned long long* counters, bool beside, bool claim) {
-    if (!n_src || !cap) return;
-    SlotInsertParams P; P.regions = regions; P.n_src = n_src; P.cap = cap; P.units = units; P.slots = slots; P.mask = mask; P.counters = counters;
-    unsigned long long total = (unsigned long long)n_src * cap;
+  void shard_insert_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
+                          unsigned long long mask, unsigned long long* counters, bool beside) override { slots_kernel(regions, n_src, region_bytes, nblocks, stride, units, slots, mask, counters, beside, false); }
+  void shard_claim_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
+                         unsigned long long mask, unsigned long long* counters, bool beside) override { slots_kernel(regions, n_src, region_bytes, nblocks, stride, units, slots, mask, counters, beside, true); }
+  void slots_kernel(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
+                    unsigned long long mask, unsigned long long* counters, bool beside, bool claim) {
+    if (!n_src || !nblocks || !stride) return;
+    SlotInsertParams P; P.regions = regions; P.n_src = n_src; P.region_bytes = region_bytes; P.nblocks = nblocks; P.stride = stride; P.units = units;
+    P.slots = slots; P.mask = mask; P.counters = counters;
+    unsigned long long total = (unsigned long long)n_src * nblocks * stride;
     int grid = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)sms_ * (beside ? 1 : 8));
     after_main();
     tic(claim ? FQG_K_MATE : FQG_K_INDEX, 0, total, st2_);
     if (claim) fq_shard_claim_slots_kernel<<<grid, 256, 0, st2_>>>(P); else fq_shard_insert_slots_kernel<<<grid, 256, 0, st2_>>>(P);
     toc(st2_); launched();
   }
+  uint32_t lanes_max_blocks() override { ensure_lanes_blocks(); return (uint32_t)lanes_blocks_; }
+  void side_mark() override { FQ_CUDA_CHECK(cudaEventRecord(ev_side_, st2_)); side_marked_ = true; }
   void side_copy(void* dst, const void* src, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, st2_)); }
   void side_sync() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); }
   void* ipc_alloc(size_t n, uint8_t handle[64]) override {
@@ -1447,6 +1473,7 @@ class FqCudaDevice : public FqDevice {
   int dev_ = 0, sms_ = kSMs, tile_blocks_ = 0, lanes_blocks_ = 0;
   cudaStream_t st_ = nullptr, st2_ = nullptr;
   cudaEvent_t evx_ = nullptr;
+  cudaEvent_t ev_side_ = nullptr; bool side_marked_ = false;
   cudaEvent_t ev_pre_ = nullptr; /* main stream just before the latest clean-data pass: what the side stream waits for when it works beside that pass */
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;

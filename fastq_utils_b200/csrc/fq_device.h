@@ -65,13 +65,20 @@ typedef struct {
 } FqShardArgs;
 /* pipelined routing: a name on its way to the owner of its hash is a slot of 16 + 16 * units bytes: this header, then `units`
  * 16-byte units holding the name's bytes, zero padded (units = 0: the tuple travels alone and the owner cannot judge equal hashes).
- * One fixed-capacity region per (round, source, owner): a header slot {count, flags}, then `cap` slots. */
+ * A region holds the names one source has for one owner in one round, written by `nblocks` writers that do not talk to each other
+ * (the CTAs of a clean-data pass; or one writer, the pack kernel): header {nblocks, stride, flags}, one count per writer, then
+ * nblocks stretches of `stride` slots. */
 typedef struct { unsigned long long hash; unsigned long long rec_len; /* record << 12 | length of the name */ } FqRouteSlot;
-#define FQ_ROUTE_NAME_TOO_LONG 1ull  /* region flag: a name needed more units than the slots have (it travelled cut short) */
+typedef struct { uint32_t nblocks, stride, flags, pad; } FqRegionHdr;
+#define FQ_ROUTE_NAME_TOO_LONG 1u  /* region flag: a name needed more units than the slots have (it travelled cut short) */
+#define FQ_ROUTE_MAX_WORLD 16      /* owners a clean-data pass can write to directly */
 typedef struct { uint8_t* region[FQ_SHARD_MAX_SRC]; } FqRegionPtrs;
 FQ_HD size_t fq_route_slot_bytes(uint32_t units) { return 16u + 16u * (size_t)units; }
-FQ_HD size_t fq_route_region_bytes(unsigned long long cap, uint32_t units) { return 16u + cap * fq_route_slot_bytes(units); }
-FQ_HD uint32_t fq_owner_of(uint64_t hash, uint32_t world) { return (uint32_t)((hash >> 40) % world); }
+FQ_HD size_t fq_route_counts_bytes(uint32_t nblocks) { return ((size_t)nblocks * 4u + 15u) & ~(size_t)15u; }
+FQ_HD size_t fq_route_region_bytes(uint32_t nblocks, unsigned long long stride, uint32_t units) {
+  return 16u + fq_route_counts_bytes(nblocks) + (size_t)nblocks * stride * fq_route_slot_bytes(units);
+}
+FQ_HD uint32_t fq_owner_of(uint64_t hash, uint32_t world) { return (uint32_t)((((hash >> 40) & 0xFFFFFFull) * world) >> 24); }
 
 /* fused scan + validate pass over one chunk (FqCudaDevice only): the records of the segment that starts at line j0 */
 typedef struct {
@@ -83,6 +90,11 @@ typedef struct {
   uint32_t lead;             /* clean-data pass only: the first `lead` (< 16) bytes of data[] are not the chunk's (offsets still count from data) */
   uint8_t* arena;            /* clean-data pass, per-line mode: block for the names' bytes (names[k].off then points in here); NULL: names stay chunk-relative */
   uint32_t arena_units;      /* its capacity in 16-byte units: a pass that needs more hands the chunk on (capacity anomaly) */
+  /* clean-data pass, per-line mode, sharded runs: the pass writes every name straight into the region of the rank that owns its
+   * hash (no name descriptors, no arena, no pack kernel): route_world owners, regions of lanes_max_blocks() stretches of
+   * route_stride slots with route_units name units */
+  uint32_t route_world, route_stride, route_units;
+  uint8_t* route_region[FQ_ROUTE_MAX_WORLD];
 } FqTileArgs;
 
 #define FQ_LANES_OUT_WORDS 32 /* [16..23]: the last 8 line ends of the chunk (fewer when it has fewer lines); [24] arena units used, [25] the per-line
@@ -150,17 +162,23 @@ class FqDevice {
   virtual void route_begin(unsigned long long* cursors, uint32_t world, bool beside) = 0; /* cursors: 2 * FQ_SHARD_MAX_SRC words (counts, then flags) */
   virtual void names_pack_slots(const FqName* names, const uint8_t* arena, uint32_t nrec, uint64_t g0, uint32_t world, const FqRegionPtrs& R, uint64_t cap,
                                 uint32_t units, unsigned long long* cursors) = 0;
-  virtual void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R) = 0;
-  /* slots of n_src regions (one after the other, fq_route_region_bytes each) into the table: counters[1] += inserted, counters[0] +=
-   * names that are in the table already (units > 0: hash AND bytes equal — a duplicated read name; units = 0: equal hashes, which
-   * tuples alone cannot judge), counters[2] = 1 when a header count exceeds cap, a name did not fit its slot, or the table is full.
-   * A slot whose hash is taken by ANOTHER name walks on (units > 0).  Asynchronous. */
-  virtual void shard_insert_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
-                                  unsigned long long* counters, bool beside) = 0;
+  virtual void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R, uint64_t cap) = 0;
+  /* slots of n_src regions (region_bytes apart, each planned for nblocks stretches of `stride` slots; a header with nblocks = 0 is an
+   * empty region) into the table: counters[1] += inserted, counters[0] += names that are in the table already (units > 0: hash AND
+   * bytes equal — a duplicated read name; units = 0: equal hashes, which tuples alone cannot judge), counters[2] = 1 when a count
+   * exceeds its stretch, a name did not fit its slot, a header contradicts the plan, or the table is full.  A slot whose hash is
+   * taken by ANOTHER name walks on (units > 0).  Asynchronous. */
+  virtual void shard_insert_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units,
+                                  FqSlot* slots, unsigned long long mask, unsigned long long* counters, bool beside) = 0;
   /* the mate loop at the owner (src/fastq_info.c:333-350: lookup, then delete): every slot (units > 0) looks its name up by hash and
    * bytes; the first one to find it claims it (counters[8]++), a name that is not there or was claimed before counts in counters[9] */
-  virtual void shard_claim_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
-                                 unsigned long long* counters, bool beside) = 0;
+  virtual void shard_claim_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units,
+                                 FqSlot* slots, unsigned long long mask, unsigned long long* counters, bool beside) = 0;
+  /* the number of writers (CTAs) a clean-data pass in per-line mode uses at most: the nblocks of the regions it routes into */
+  virtual uint32_t lanes_max_blocks() { return 0; }
+  /* the main stream's next clean-data pass waits for what was queued on the side stream so far (copies out of the regions that
+   * pass will overwrite) */
+  virtual void side_mark() {}
   virtual void side_copy(void* dst, const void* src, size_t n) = 0;
   virtual void side_sync() = 0;
   /* memory that other processes can map (CUDA IPC); devices without it throw */

@@ -75,6 +75,7 @@ void FqEngine::reset() {
   seed_ = 0; finished_ = false; total0_set_ = false; total0_ = 0; fused_ok_ = !(cfg_.flags & FQG_FLAG_TWO_PASS);
   { const char* e = getenv("FQG_FUSED_MIN_BYTES"); fused_min_ = e ? (uint32_t)strtoul(e, nullptr, 10) : (1u << 20); } /* test hook */
   { const char* e = getenv("FQG_NO_LANES"); lanes_ok_ = !(e && *e && *e != '0'); }                                  /* test hook */
+  { const char* e = getenv("FQG_ROUTE_AFTER"); hook_after_ = e && *e && *e != '0'; } /* A/B: the chunk hook fires when the chunk is done (the routing kernels then have the GPU to themselves) instead of beside the next pass */
   { const char* e = getenv("FQG_TEST_WEAK_HASH"); if (e && *e && *e != '0') seed_ = FQ_SEED_WEAK; }                 /* test hook: 12-bit name hashes, so that equal hashes of different names are common */
   for (auto& m : mem_stats) m = 0;
   open_ = streaming_; add_depth_ = 0;
@@ -278,7 +279,8 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
    * fill the chunk with — a chunk with more hands itself on, see fq_lanes_post_kernel, and the next one asks for the full bound) */
   if (lanes_ok_ && !names_cap_full_ && F.first_hdr_len && F.first_seq_len)
     ncap = std::min<uint32_t>(ncap, (uint32_t)((double)B.n / (0.75 * (F.first_hdr_len + 2.0 * F.first_seq_len + 2))) + 4096);
-  FqName* names = (loop != FQ_LOOP_SINGLE && loop != FQ_LOOP_READER) ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
+  const bool routed = F.route_world > 0 && lanes_ok_ && !skip_lanes && f_[loop == FQ_LOOP_MATE ? 0 : file].sniff_color != FQ_SPACE_COLOR; /* the pass routes the names itself: no descriptors, no arena */
+  FqName* names = (loop != FQ_LOOP_SINGLE && loop != FQ_LOOP_READER && !routed) ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
   FqTileArgs a; memset(&a, 0, sizeof a);
   a.data = B.data; a.n = B.n; a.virtual_end = last ? 1 : 0; a.line_end = B.line_end; a.cap = cap; a.out5 = tile_out_;
   a.j0 = j0; a.max_rec = kNone32; a.g0 = g0_local + F.g_base; a.step_base = step_base(file); a.cx = make_ctx(file);
@@ -305,9 +307,13 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
       arena = (uint8_t*)dev_->alloc((size_t)arena_units * 16 + kPad);
     }
     a.arena = arena; a.arena_units = (uint32_t)arena_units;
+    if (routed) {
+      a.route_world = F.route_world; a.route_stride = F.route_stride; a.route_units = F.route_units;
+      for (uint32_t o = 0; o < F.route_world; o++) a.route_region[o] = F.route_region[o] + (size_t)(F.route_chunks % F.route_depth) * F.route_bytes;
+    }
     bool self_judged = false;
     if (dev_->lanes_pass(a, &self_judged)) {
-      if (hook_) { /* the pass is running: the caller routes the names of the chunks before this one beside it */
+      if (hook_ && !hook_after_) { /* the pass is running: the caller routes the names of the chunks before this one beside it */
         in_beside_hook_ = true; hook_fired_ = true;
         try { hook_(hook_user_, file); } catch (...) { in_beside_hook_ = false; throw; }
         in_beside_hook_ = false;
@@ -318,6 +324,8 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
       if (getenv("FQG_DEBUG")) fprintf(stderr, "[fqg] clean-data pass: n=%u j0=%u lines=%u capovf=%u overlong=%u anomaly=0x%x internal=%u virt=%u q=%u..%u rl=%u..%u recbad=%u | polls=%u lookback_rounds=%u waited=%u | arena %u of %llu units, accepted=%u, staged=%u\n",
                                        B.n, j0, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10], o[11], o[12], o[13], o[24], (unsigned long long)arena_units, o[25], o[27]);
       bool accepted = self_judged ? o[25] != 0 : (pass_ok && !o[10]);
+      if (routed && !(accepted && self_judged)) F.route_broken = true; /* names of this chunk did not reach the regions: the caller repeats the job */
+      if (accepted && routed) F.route_chunks++;
       if (accepted) {
         if (!self_judged) dev_->lanes_commit(a, false);
         path_counts[0]++; fused_lanes_ = true;
@@ -335,9 +343,13 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
       if (self_judged && o[4] == 3) names_cap_full_ = true; /* (perhaps) more records than name descriptors */
       if (!self_judged && pass_ok) dev_->lanes_commit(a, true); /* counters went in before a record broke a length rule: take them back */
       if (self_judged && (o[3] & 16u) && arena) F.arena_rate = std::max(F.arena_rate, 1.5 * (double)o[24] / kLanesTile); /* (perhaps) ran out of arena: what the fullest tile asked for, and half as much again */
-    } else dev_->sync();
+    } else { dev_->sync(); if (routed) F.route_broken = true; }
     if (arena) dev_->release(arena);
-    a.arena = nullptr; a.arena_units = 0;
+    a.arena = nullptr; a.arena_units = 0; a.route_world = 0;
+    if (routed) { /* the per-record kernels deliver name descriptors: the caller packs them (fqg_names_pack_slots) */
+      names = (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName));
+      a.names = names;
+    }
   }
   if (B.lead) { /* the per-record kernels want the chunk's data at offset 0: the caller copies it and comes back */
     if (names) dev_->release(names);
@@ -1265,7 +1277,7 @@ void FqEngine::names_pack_slots(int file, uint32_t world, void* const* region_pt
     if (s.g0 >= lim || !s.names) continue;
     dev_->names_pack_slots(s.names, s.arena, (uint32_t)std::min<uint64_t>(s.nrec, lim - s.g0), s.g0 + F.g_base, world, R, cap, units, route_cursors_);
   }
-  dev_->route_end(route_cursors_, world, R);
+  dev_->route_end(route_cursors_, world, R, cap);
   F.routed_segs = F.segs.size();
 }
 
@@ -1274,17 +1286,26 @@ void FqEngine::shard_reserve(uint64_t n_names) {
   ensure_table(std::max<uint64_t>(n_names, 1));
 }
 
-void FqEngine::shard_insert_slots(const void* regions, uint32_t n_src, uint64_t cap, uint32_t units, bool beside) {
+void FqEngine::shard_insert_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside) {
   if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_insert_slots: n_src out of range");
   if (!slots_) ensure_table(1);
-  dev_->shard_insert_slots((const uint8_t*)regions, n_src, cap, units, slots_, table_cap_ - 1, counters_, beside);
+  dev_->shard_insert_slots((const uint8_t*)regions, n_src, region_bytes, nblocks, stride, units, slots_, table_cap_ - 1, counters_, beside);
   table_names_ = 1; /* the table holds names the engine cannot re-insert: it must not grow any more */
 }
-void FqEngine::shard_claim_slots(const void* regions, uint32_t n_src, uint64_t cap, uint32_t units, bool beside) {
+void FqEngine::shard_claim_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside) {
   if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_claim_slots: n_src out of range");
   if (!units) throw std::runtime_error("fqg_shard_claim_slots: the mate loop compares names, the slots must carry their bytes");
   if (!slots_) ensure_table(1);
-  dev_->shard_claim_slots((const uint8_t*)regions, n_src, cap, units, slots_, table_cap_ - 1, counters_, beside);
+  dev_->shard_claim_slots((const uint8_t*)regions, n_src, region_bytes, nblocks, stride, units, slots_, table_cap_ - 1, counters_, beside);
+}
+/* sharded runs: the clean-data pass of every chunk of `file` writes the names straight into per-owner regions (include/fastq_gpu.h) */
+void FqEngine::set_route(int file, uint32_t world, void* const* region_ptrs, size_t region_bytes, uint32_t depth, uint32_t stride, uint32_t units) {
+  if (!(cfg_.flags & FQG_FLAG_EXTERNAL_INDEX)) throw std::runtime_error("fqg_set_route needs FQG_FLAG_EXTERNAL_INDEX");
+  if (world > FQ_ROUTE_MAX_WORLD) throw std::runtime_error("fqg_set_route: too many owners for the pass to write to directly");
+  if (units > 62) throw std::runtime_error("fqg_set_route: at most 62 name units");
+  FqFile& F = f_[file];
+  F.route_world = world; F.route_bytes = region_bytes; F.route_depth = depth ? depth : 1; F.route_stride = stride; F.route_units = units;
+  for (uint32_t o = 0; o < world; o++) { if (!region_ptrs[o]) throw std::runtime_error("fqg_set_route: null region"); F.route_region[o] = (uint8_t*)region_ptrs[o]; }
 }
 
 void FqEngine::shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow, uint64_t* claimed, uint64_t* unpaired) {

@@ -68,6 +68,10 @@ struct FqFile {
   uint32_t start_skip = 0;  /* lines of the first buffer that belong to the previous range */
   bool started = false;
   size_t routed_segs = 0;   /* pipelined routing: segments [0, routed_segs) have been packed by names_pack_slots */
+  /* pipelined routing by the clean-data pass itself: chunk n of the file writes into region_o + (n % depth) * bytes */
+  uint32_t route_world = 0, route_depth = 1, route_stride = 0, route_units = 0; size_t route_bytes = 0;
+  uint8_t* route_region[FQ_ROUTE_MAX_WORLD] = {nullptr};
+  uint64_t route_chunks = 0; bool route_broken = false;
   struct Prescan { const uint8_t* data; uint32_t n; bool last; uint32_t* line_end; uint32_t nlines; };
   std::vector<Prescan> prescans;
 };
@@ -102,8 +106,10 @@ class FqEngine {
   uint64_t names_new(int file);
   void names_pack_slots(int file, uint32_t world, void* const* region_ptrs, uint64_t cap, uint32_t units);
   void shard_reserve(uint64_t n_names);
-  void shard_insert_slots(const void* regions, uint32_t n_src, uint64_t cap, uint32_t units, bool beside);
-  void shard_claim_slots(const void* regions, uint32_t n_src, uint64_t cap, uint32_t units, bool beside);
+  void shard_insert_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside);
+  void shard_claim_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside);
+  void set_route(int file, uint32_t world, void* const* region_ptrs, size_t region_bytes, uint32_t depth, uint32_t stride, uint32_t units);
+  uint64_t route_chunks(int file, int* broken) const { *broken = f_[file].route_broken ? 1 : 0; return f_[file].route_chunks; }
   void shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow, uint64_t* claimed, uint64_t* unpaired);
   FqDevice* device() { return dev_; }
   std::string last_error;
@@ -122,6 +128,7 @@ class FqEngine {
   FqSlot* slots_ = nullptr; uint64_t table_cap_ = 0; uint64_t table_names_ = 0;
   uint32_t seed_ = 0;
   fqg_chunk_hook hook_ = nullptr; void* hook_user_ = nullptr;
+  bool hook_after_ = false;                 /* never call the hook beside a running pass */
   bool hook_fired_ = false;                 /* the chunk being fed has called the hook already */
   bool in_beside_hook_ = false;             /* the hook runs while a clean-data pass occupies the main stream */
   unsigned long long* route_cursors_ = nullptr; /* device: FQ_SHARD_MAX_SRC per-owner tuple counts of the round being packed */

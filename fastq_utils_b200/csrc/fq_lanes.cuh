@@ -75,6 +75,9 @@ struct LanesParams {
   uint32_t j0; FqRecCtx cx; FqName* names; uint32_t names_cap;
   LanesStage* stage;   /* per-line mode */
   uint8_t* arena; uint32_t arena_units; /* per-line mode: where the names go (16-byte units); NULL: the names stay in the chunk */
+  /* per-line mode, sharded runs: every name goes straight into the region of the rank that owns its hash (fq_device.h: FqRegionHdr);
+   * this CTA writes stretch blockIdx.x of every region */
+  uint32_t route_world, route_stride, route_units; uint8_t* route_region[FQ_ROUTE_MAX_WORLD];
   uint32_t tune; /* experiment switch (FQG_LANES_TUNE): 1 = no L2 prefetch of the next tile */
 };
 
@@ -234,6 +237,8 @@ fq_lanes_kernel(const LanesParams P) {
   __shared__ uint32_t s_next, s_fbase, s_fstate, s_w1[LN_WARPS], s_w3[LN_WARPS], s_w4[LN_WARPS];
   __shared__ uint32_t s_cnt, s_mem, s_rlmin, s_rlmax;  /* per-line mode: this CTA's records, index_mem bytes, read lengths */
   __shared__ uint32_t s_arena;                           /* per-line mode: arena units handed out to the names of the current tile */
+  __shared__ uint32_t s_own[FQ_ROUTE_MAX_WORLD];         /* routing: names this CTA has written for each owner so far */
+  __shared__ uint8_t* s_reg[FQ_ROUTE_MAX_WORLD];         /* ... and where this CTA's stretch of the owner's region starts */
   uint32_t* s_hist = (uint32_t*)(smem + LN_OFF_LEND + LN_LMAX * 2); /* per-line mode: records by read length (below LS_HBINS) */
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = smem_u32(&s_bar);
@@ -247,7 +252,13 @@ fq_lanes_kernel(const LanesParams P) {
    * round trip to L2, and several when the index kernel beside the pass keeps the atomic units busy) */
   const uint32_t arena_stride = P.arena ? P.arena_units / P.ntiles : 0u;
   uint32_t arena_max = 0;
+  uint32_t route_tile_max = 0; /* (thread 0) the most header lines a tile of this CTA has held so far */
   if (LINES) for (int l = threadIdx.x; l < LS_HBINS; l += LN_THREADS) s_hist[l] = 0;
+  const uint32_t route_slot_bytes = 16u + 16u * P.route_units;
+  if (LINES && P.route_world && tid < (int)P.route_world) {
+    s_own[tid] = 0;
+    s_reg[tid] = P.route_region[tid] + 16 + fq_route_counts_bytes(gridDim.x) + (size_t)blockIdx.x * P.route_stride * route_slot_bytes;
+  }
   if (tid < 32) {
     uint32_t w[4];
 #pragma unroll
@@ -414,7 +425,15 @@ fq_lanes_kernel(const LanesParams P) {
       /* Per-line mode claims the next tile now (and pulls it into L2).  The chunk-parallel mode claims at the end of the round: many
        * of its tiles (long lines: no plus line inside) wait for the counts of the tiles in front, and a tile claimed a round before
        * it is scanned would keep every tile behind it waiting that long. */
-      const uint32_t nxt = LINES ? ((lost_a != 0 || lost_o != 0xFFFFFFFFu) ? 0xFFFFFFFFu : atomicAdd(P.ticket, 1u)) : 0xFFFFFFFFu;
+      /* routing: this CTA's stretch of an owner's region must hold the names of the tile in hand and of the next one — otherwise the
+       * CTA stops claiming tiles (the others take them: the stretches hold a third more than the chunk's names) */
+      bool route_full = false;
+      if (LINES && P.route_world) {
+        uint32_t most = 0;
+        for (uint32_t o = 0; o < P.route_world; o++) most = max(most, s_own[o]);
+        route_full = most + 2u * min((uint32_t)LN_SMAX, max(route_tile_max, 64u)) > P.route_stride;
+      }
+      const uint32_t nxt = LINES ? ((lost_a != 0 || lost_o != 0xFFFFFFFFu || route_full) ? 0xFFFFFFFFu : atomicAdd(P.ticket, 1u)) : 0xFFFFFFFFu;
       if (LINES) s_next = nxt; /* read after the barrier at the top of the next round */
       if (LINES && nxt < P.ntiles && !(P.tune & 1u)) { /* pull the next tile into L2 now: its bulk copy, issued when this round is over, then finds it there */
         const unsigned long long src = (unsigned long long)nxt * TILE - LN_LEFT;
@@ -507,6 +526,7 @@ fq_lanes_kernel(const LanesParams P) {
         uint32_t nH = kH <= cntT ? (cntT - kH) / 4 + 1 : 0;
         if (nH > (uint32_t)LN_SMAX) { anomaly |= LN_A_CAPACITY; nH = 0; }
         p_nstage = nH; p_rl0 = (gbr + kH) >> 2;
+        route_tile_max = max(route_tile_max, nH);
         /* groups of 32 lines of one class, handed to the warps round-robin in the order quality, sequence, header: the warp that
          * gets a second group gets the light ones (measured: 0.89 ms against 0.94 for sequence-first, 0.96 for a shared work counter
          * with sequence lines split in halves — extra instructions cost more than balance gains) */
@@ -550,38 +570,8 @@ fq_lanes_kernel(const LanesParams P) {
           if (live && hl >= FQ_MAX_LABEL_LENGTH) { atomicMin(P.out + LN_O_OVERLONG, tile); live = false; }
           if (live && hl < 3u) { anomaly |= LN_A_HEADER; live = false; }
           uint32_t nlen = 0; uint64_t mem_len = 0, hsh = FQ_HASH_SKIP;
-          if (live && !fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; live = false; }
-          /* arena space for the names of the group, inside the tile's own stretch */
-          const uint32_t units = (live && P.arena) ? (nlen + 15u) >> 4 : 0u;
-          uint32_t incl_u = units;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) { const uint32_t a = __shfl_up_sync(FULL, incl_u, d); if (lane >= d) incl_u += a; }
-          uint32_t ubase = 0;
-          { const uint32_t tot = __shfl_sync(FULL, incl_u, 31); if (lane == 0 && tot) ubase = atomicAdd(&s_arena, tot); }
-          ubase = __shfl_sync(FULL, ubase, 0) + incl_u - units;
-          if (units && ubase + units > arena_stride) { anomaly |= LN_A_CAPACITY; live = false; }
-          const uint32_t my_unit = tile * arena_stride + ubase;
-          if (live) {
-            FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
-            if (units) { /* the name's bytes, 16 at a time from the window (any alignment), zero padded */
-              nm.off = my_unit * 16u;
-              uint4* dst = (uint4*)(P.arena + (size_t)my_unit * 16u);
-              const uint32_t a0 = (s + 1u) & ~3u, sh = ((s + 1u) & 3u) * 8u;
-              for (uint32_t u = 0; 16u * u < nlen; u++) {
-                const uint32_t* wp = (const uint32_t*)(win + a0 + 16u * u);
-                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-                const uint32_t left = nlen - 16u * u;
-                uint4 v;
-                v.x = fq_low_bytes(__funnelshift_r(w0, w1, sh), left);
-                v.y = left > 4u ? fq_low_bytes(__funnelshift_r(w1, w2, sh), left - 4u) : 0u;
-                v.z = left > 8u ? fq_low_bytes(__funnelshift_r(w2, w3, sh), left - 8u) : 0u;
-                v.w = left > 12u ? fq_low_bytes(__funnelshift_r(w3, w4, sh), left - 12u) : 0u;
-                dst[u] = v;
-              }
-            }
-            stage[i] = nm;
-          }
-          /* the record's other three lines */
+          if (live && !fq_header_hash_fast(win, s, hl, P.cx.fmt_key, P.cx.pe_key, P.cx.seed, P.names != nullptr || P.route_world != 0, &nlen, &mem_len, &hsh)) { anomaly |= LN_A_HEADER; live = false; }
+          /* the record's other three lines: is it complete in this chunk, does it keep the length rules? */
           bool rec_ok = false; uint32_t sl = 0;
           if (live) {
             uint32_t e1 = 0, e2 = 0, e3 = 0; bool complete = false;
@@ -594,6 +584,56 @@ fq_lanes_kernel(const LanesParams P) {
               if (e2 - e1 != 2u || sl < 2u || e3 - e2 != sl) atomicOr(P.out + LN_O_RECBAD, 1u);
               else rec_ok = true;
             }
+          }
+          /* arena space for the names of the group, inside the tile's own stretch */
+          const uint32_t units = (live && P.arena) ? (nlen + 15u) >> 4 : 0u;
+          uint32_t incl_u = units;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const uint32_t a = __shfl_up_sync(FULL, incl_u, d); if (lane >= d) incl_u += a; }
+          uint32_t ubase = 0;
+          { const uint32_t tot = __shfl_sync(FULL, incl_u, 31); if (lane == 0 && tot) ubase = atomicAdd(&s_arena, tot); }
+          ubase = __shfl_sync(FULL, ubase, 0) + incl_u - units;
+          if (units && ubase + units > arena_stride) { anomaly |= LN_A_CAPACITY; live = false; }
+          const uint32_t my_unit = tile * arena_stride + ubase;
+          uint4* dst = (uint4*)(P.arena + (size_t)my_unit * 16u);
+          uint32_t copy_units = units;
+          if (P.route_world) { /* the owner of the name's hash gets it at once: the next free slot of this CTA's stretch of its region */
+            const bool go = live && rec_ok; /* (a record the end of the chunk cut travels with the chunk that holds all of it) */
+            const uint32_t o = go ? fq_owner_of(hsh, P.route_world) : 0xFFFFFFFFu;
+            const uint32_t m = __match_any_sync(FULL, o);
+            const int leader = __ffs(m) - 1;
+            uint32_t pos = 0;
+            if (go && lane == leader) pos = atomicAdd(&s_own[o], (uint32_t)__popc(m));
+            pos = __shfl_sync(FULL, pos, leader) + __popc(m & ((1u << lane) - 1u));
+            if (go && pos >= P.route_stride) { anomaly |= LN_A_CAPACITY; live = false; }
+            copy_units = 0;
+            if (go && live) {
+              uint4* slot = (uint4*)(s_reg[o] + (size_t)pos * route_slot_bytes);
+              const unsigned long long rl = ((unsigned long long)tile << 24 | (unsigned long long)(i & 0xFFFu) << 12) | nlen; /* (a record number of its own kind: unique, nothing more is asked of it) */
+              slot[0] = make_uint4((uint32_t)hsh, (uint32_t)(hsh >> 32), (uint32_t)rl, (uint32_t)(rl >> 32));
+              dst = slot + 1; copy_units = (nlen + 15u) >> 4;
+              if (copy_units > P.route_units) { copy_units = P.route_units; if (P.route_units) atomicOr(&((FqRegionHdr*)P.route_region[o])->flags, FQ_ROUTE_NAME_TOO_LONG); } /* (no units: the tuple travels alone by design) */
+              for (uint32_t u = copy_units; u < P.route_units; u++) dst[u] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          if (live) {
+            FqName nm; nm.off = gofs + s + 1; nm.len = nlen; nm.hash = hsh;
+            if (copy_units) { /* the name's bytes, 16 at a time from the window (any alignment), zero padded */
+              if (units) nm.off = my_unit * 16u;
+              const uint32_t a0 = (s + 1u) & ~3u, sh = ((s + 1u) & 3u) * 8u;
+              for (uint32_t u = 0; u < copy_units; u++) {
+                const uint32_t* wp = (const uint32_t*)(win + a0 + 16u * u);
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+                const uint32_t left = nlen - 16u * u;
+                uint4 v;
+                v.x = fq_low_bytes(__funnelshift_r(w0, w1, sh), left);
+                v.y = left > 4u ? fq_low_bytes(__funnelshift_r(w1, w2, sh), left - 4u) : 0u;
+                v.z = left > 8u ? fq_low_bytes(__funnelshift_r(w2, w3, sh), left - 8u) : 0u;
+                v.w = left > 12u ? fq_low_bytes(__funnelshift_r(w3, w4, sh), left - 12u) : 0u;
+                dst[u] = v;
+              }
+            }
+            stage[i] = nm;
           }
           const uint32_t okm = __ballot_sync(FULL, rec_ok);
           if (okm) {
@@ -752,6 +792,10 @@ fq_lanes_kernel(const LanesParams P) {
         atomicMax(&P.stage->rl_min_inv, ~s_rlmin); atomicMax(&P.stage->rl_max, s_rlmax);
       }
       atomicMax(&P.stage->arena_used, max(arena_max, s_arena)); /* the fullest tile's */
+    }
+    if (P.route_world && tid < (int)P.route_world) { /* this CTA's stretch of every region: how many slots it filled */
+      ((uint32_t*)(P.route_region[tid] + 16))[blockIdx.x] = s_own[tid];
+      if (blockIdx.x == 0) { FqRegionHdr* h = (FqRegionHdr*)P.route_region[tid]; h->nblocks = gridDim.x; h->stride = P.route_stride; }
     }
   }
   /* ---- results of this thread → one set of atomics per warp */

@@ -50,7 +50,7 @@ class ShardedFastqInfo:
         self._cpu_group = None
         if self.world > 1 and dist.get_backend() != "gloo":
             import datetime
-            self._cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=300))  # a rank that died must not hang the others for half an hour
+            self._cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=int(os.environ.get("FQG_GLOO_TIMEOUT_S", "120"))))  # a rank that died must not hang the others for half an hour
         self.pipeline = os.environ.get("FQG_NO_PIPELINE", "0") in ("", "0")
         # pipelined rounds over peer memory (CUDA IPC) instead of all-to-all exchanges: the default on GPUs, FQG_P2P=0 turns it off;
         # FQG_P2P=1 asks for it on CPU tensors too (the gloo tests: the stand-in device maps shared memory between the ranks)
@@ -58,8 +58,9 @@ class ShardedFastqInfo:
         # the copy engines move the packed regions; FQG_P2P_STORES=1: the pack kernel stores into the owners' arenas itself (A/B)
         self.p2p_stores = os.environ.get("FQG_P2P_STORES", "0") not in ("", "0")
         self._pending_insert = None
-        self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage = None, None, False, False, None
+        self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage, self._zero = None, None, False, False, None, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
+        self._plan = None
         self.exact_reruns = 0  # jobs the speculative / pipelined path handed to the exact path (tests)
         self.host_ms = {"pack": 0.0, "barrier": 0.0}  # host time inside the peer-memory rounds, accumulated
 
@@ -67,6 +68,8 @@ class ShardedFastqInfo:
         """how the names of the last job reached their owners (bench.py's config line)"""
         if self.shard is None:
             return "no name index in this mode"
+        if self.rounds_done and self._p2p_ok and self._plan and self._plan[0]["mode"] == "pass":
+            return "written by the clean-data pass into per-owner regions, moved chunk by chunk into the owners' peer memory over NVLink (CUDA IPC) by the copy engines"
         if self.rounds_done and self._p2p_ok:
             return "chunk by chunk into the owners' peer memory over NVLink (CUDA IPC), beside the next chunk's pass"
         if self.rounds_done:
@@ -207,7 +210,12 @@ class ShardedFastqInfo:
     def _plan_routes(self, infos, pair):
         """The routing rounds of a job, from the ranks' guesses about their ranges (infos[f][rank]): per file the number of rounds
         (as many as the longest range has chunks, so that no round carries more than one chunk; ranks with fewer chunks add empty
-        rounds: the rounds are collective), the capacity of a region, and where the file's regions start in every rank's arena."""
+        rounds: the rounds are collective), the shape of a region, and where the file's regions start in every rank's arena.
+        Three ways for the names of a chunk to reach their owners (`mode`):
+          pass  the clean-data pass writes them into per-owner regions while it validates (GPU, peer memory); the copy engines move
+                the regions; what the per-record kernels validated (the seams of the byte ranges) follows in one packed round
+          pack  a pack kernel fills dense regions beside the next pass, the copy engines move them (peer memory)
+          a2a   the same pack kernel, regions exchanged with all-to-all (no peer memory; the gloo tests)"""
         W = self.world
         chunk = api.feed_chunk_bytes()
         # (a chunk restarts at the record the chunk before it cut, so a range may take one chunk more than its bytes suggest:
@@ -221,20 +229,40 @@ class ShardedFastqInfo:
             line = first[1:first.index(b"\n")] if b"\n" in first else first[1:]
             name = line.split(b" ")[0] if self._sniff[0][0] == 1 else line
             units = max(1, -(-(len(name) + 3) // 16))
+        nb = self.ctx.route_blocks() if (self.p2p and not self.p2p_stores and os.environ.get("FQG_ROUTE_IN_PASS", "1") not in ("", "0")) else 0
+        tiny = os.environ.get("FQG_TEST_SLOT_CAP")  # test hook: regions far too small, so that the overflow path is taken
         plan, base = [], 0
         for info in infos:
             rounds = max(1, max(-(-x[7] // step) for x in info))
-            per = min(chunk, max(x[7] for x in info)) / max(min(x[4] for x in info), 16.0) / W
-            cap = int(per * 1.25) + 4096  # names of one chunk for one owner, with room to spare (the estimate comes from the first records of every range)
-            if os.environ.get("FQG_TEST_SLOT_CAP"):  # test hook: regions far too small, so that the overflow path is taken
-                cap = int(os.environ["FQG_TEST_SLOT_CAP"])
-            stride = api.route_region_bytes(cap, units)
-            plan.append({"rounds": rounds, "cap": cap, "units": units, "stride": stride, "base": base, "round": 0, "fires": 0})
-            base += rounds * W * stride
+            names_chunk = min(chunk, max(x[7] for x in info)) / max(min(x[4] for x in info), 16.0)  # (the estimate comes from the first records of every range)
+            pl = {"rounds": rounds, "units": units, "round": 0, "fires": 0, "base": base}
+            if nb:  # one stretch per CTA of the pass and owner, with room to spare
+                # (the CTAs claim tiles as they go: a CTA may get a few tiles more than its share)
+                per_tile = 31744.0 / max(min(x[4] for x in info), 16.0)
+                stride = int(tiny) if tiny else int(names_chunk / nb / W * 1.3 + 4 * per_tile) + 32
+                left = int(tiny) if tiny else 16384
+                pl.update(mode="pass", nblocks=nb, stride=stride, region=api.route_region_bytes(nb, stride, units),
+                          left_stride=left, left_region=api.route_region_bytes(1, left, units))
+                base += rounds * W * pl["region"]
+                pl["left_base"] = base
+                base += W * pl["left_region"]
+            else:  # names of one chunk for one owner, with room to spare
+                cap = int(tiny) if tiny else int(names_chunk / W * 1.25) + 4096
+                pl.update(mode="pack", nblocks=1, stride=cap, region=api.route_region_bytes(1, cap, units))
+                base += rounds * W * pl["region"]
+            plan.append(pl)
         est = sum(x[7] / max(x[4], 16.0) for x in infos[0]) / W
         self.shard.shard_reserve(int(est * 1.05) + 4096)
         self._plan, self._inflight, self._hook_exc, self._pending_insert = plan, [], None, None
         self._p2p_ok = self.p2p and self._ensure_arena(base)
+        if not self._p2p_ok:
+            for pl in plan:
+                pl["mode"] = "a2a"
+        need = max([2 * W * pl["region"] for pl in plan if pl["mode"] == "pass"] + [W * pl["region"] for pl in plan if pl["mode"] == "pack"] + [0])
+        if need and (self._stage is None or self._stage.numel() < need + 64):
+            self._stage = torch.zeros(need + 64, dtype=torch.uint8, device=self.tdev)
+        if self._zero is None:
+            self._zero = torch.zeros(64, dtype=torch.uint8, device=self.tdev)
 
     def _feed_file_speculative(self, f, ptr, nbytes, info, routed=False):
         """Steps 1-2 without counting the line feeds of the range first: every rank takes the line phase of its range from its own
@@ -265,6 +293,10 @@ class ShardedFastqInfo:
         ctx.set_line_hint(f, info[r][5])  # a range that starts inside the file never sees the first record's sequence line
         if routed:
             self._cur = f
+            pl = self._plan[f]
+            if pl["mode"] == "pass":  # the clean-data pass of every chunk writes into two alternating sets of W regions
+                st = self._stage.data_ptr()
+                ctx.set_route(f, [st + o * 2 * pl["region"] for o in range(W)], pl["region"], 2, pl["stride"], pl["units"])
             ctx.set_chunk_hook(self._on_chunk)
         t0 = time.perf_counter()
         try:
@@ -275,9 +307,14 @@ class ShardedFastqInfo:
                 ctx.set_chunk_hook(None)
         if routed:
             pl = self._plan[f]
-            while pl["round"] < pl["rounds"] - 1:
-                self._route_round(False)
-            self._route_round(True)
+            if pl["mode"] == "pass":
+                while pl["round"] < pl["rounds"]:
+                    self._pass_round()
+                self._left_round()
+            else:
+                while pl["round"] < pl["rounds"] - 1:
+                    self._route_round(False)
+                self._route_round(True)
             self.rounds_done += pl["round"]
 
     def _feed_range(self, f, ptr, nbytes, head, head_n):
@@ -302,12 +339,59 @@ class ShardedFastqInfo:
         pl = self._plan[self._cur]
         pl["fires"] += 1
         t0 = time.perf_counter()
-        if self._hook_exc is None and pl["fires"] >= 2 and pl["round"] < pl["rounds"] - 1:
+        if self._hook_exc is None:
             try:
-                self._route_round(False)
+                if pl["mode"] == "pass":
+                    done = self.ctx.route_chunks(self._cur)[0]  # chunks whose regions the pass has completed
+                    while pl["round"] < min(done, pl["rounds"]):
+                        self._pass_round()
+                elif pl["fires"] >= 2 and pl["round"] < pl["rounds"] - 1:
+                    self._route_round(False)
             except BaseException as ex:  # an exception cannot cross the C frames above us
                 self._hook_exc = ex
         self.host_ms["hook"] = self.host_ms.get("hook", 0.0) + (time.perf_counter() - t0) * 1e3
+
+    def _pass_round(self):
+        """Round j of the current file, mode `pass`: the regions the clean-data pass of this rank's chunk j filled (none: an empty
+        header) go to their owners' arenas through the copy engines; the pass that will reuse the regions waits for the copies."""
+        W, r, f = self.world, self.rank, self._cur
+        pl = self._plan[f]
+        j, region = pl["round"], pl["region"]
+        have = j < self.ctx.route_chunks(f)[0]
+        _dbg(f"rank {r} file {f} pass round {j} of {pl['rounds']} have={have} chunks={self.ctx.route_chunks(f)}")
+        off = pl["base"] + (j * W + r) * region
+        st = self._stage.data_ptr()
+        for d in range(W):
+            o = (r + d) % W
+            dst = (self._arena[0] if o == r else self._peer[o]) + off
+            if have:
+                self.ctx.side_copy(dst, st + (o * 2 + j % 2) * region, region)
+            else:
+                self.ctx.side_copy(dst, self._zero.data_ptr(), 16)
+        self.ctx.side_mark()
+        self._land_pending_round(beside=True)
+        self._pending_insert = (pl["base"] + j * W * region, f, region, pl["nblocks"], pl["stride"])
+        self._sync_side_later = True
+        pl["round"] += 1
+
+    def _left_round(self):
+        """After the last chunk of a file, mode `pass`: what the per-record kernels validated (the seams between byte ranges, a short
+        last chunk) has name descriptors; one packed round takes them to their owners.  Then every round of the file lands."""
+        W, r, f = self.world, self.rank, self._cur
+        pl = self._plan[f]
+        region, cap = pl["left_region"], pl["left_stride"]
+        _dbg(f"rank {r} file {f} left round, names left {self.ctx.names_new(f)}")
+        self.ctx.side_sync()  # the staging regions are free: every copy out of them is done
+        st = self._stage.data_ptr()
+        off = pl["left_base"] + r * region
+        self.ctx.names_pack_slots(f, [self._arena[0] + off if o == r else st + o * region for o in range(W)], cap, pl["units"])
+        for d in range(1, W):
+            o = (r + d) % W
+            self.ctx.side_copy(self._peer[o] + off, st + o * region, region)
+        self.ctx.side_sync()
+        self._land_pending_round(beside=False)
+        self._pending_insert = (pl["left_base"], f, region, 1, cap)
+        self._land_pending_round(beside=False)
 
     def _ensure_arena(self, need):
         """Peer-writable receive memory (CUDA IPC over NVLink): `need` bytes on every rank, mapped by every other rank.  Collective;
@@ -349,24 +433,22 @@ class ShardedFastqInfo:
         return True
 
     def _route_round_p2p(self, final):
-        """One routing round over peer memory.  The names of this round are packed by owner next to the data and the copy engines
-        move each region into its owner's arena (CUDA IPC over NVLink): no exchange kernel needs SMs of its own, and the pass keeps
-        the memory system to itself (letting the pack kernel store into the peers' arenas directly, FQG_P2P_STORES=1, is as fast
-        with two ranks but slowed every pass threefold at eight: 5.9 M remote stores per round and rank).  A host barrier
+        """One routing round over peer memory, mode `pack`.  The names of this round are packed by owner next to the data and the
+        copy engines move each region into its owner's arena (CUDA IPC over NVLink): no exchange kernel needs SMs of its own, and
+        the pass keeps the memory system to itself (letting the pack kernel store into the peers' arenas directly, FQG_P2P_STORES=1,
+        is as fast with two ranks but slowed every pass threefold at eight: 5.9 M remote stores per round and rank).  A host barrier
         says that every source's round has landed; it is passed in the NEXT round, a whole pass later, so nobody waits long; then
         the owner inserts (file 1: claims) the round beside the running pass.  Pack first, insert second: both want the one block
         slot per SM that the pass leaves free."""
         W, r, f = self.world, self.rank, self._cur
         pl = self._plan[f]
-        cap, units, stride = pl["cap"], pl["units"], pl["stride"]
+        cap, units, stride = pl["stride"], pl["units"], pl["region"]
         off = pl["base"] + pl["round"] * W * stride
         t0 = time.perf_counter()
         copies = []
         if self.p2p_stores:
             self.ctx.names_pack_slots(f, [self._peer[o] + off + r * stride for o in range(W)], cap, units)
         else:
-            if self._stage is None or self._stage.numel() < W * stride:
-                self._stage = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
             st = self._stage.data_ptr()
             # (same stream as the copies of the round before: the pack overwrites the staging buffer after they have read it, and
             # its completion says that they are done)
@@ -379,29 +461,32 @@ class ShardedFastqInfo:
         t2 = time.perf_counter()
         self.host_ms["pack"] += (t1 - t0) * 1e3
         self.host_ms["barrier"] += (t2 - t1) * 1e3
-        self._pending_insert = (off, f)
+        self._pending_insert = (off, f, stride, 1, cap)
         pl["round"] += 1
         if final:
             self.ctx.side_sync()
             self._land_pending_round(beside=False)
 
     def _land_pending_round(self, beside):
-        """The round packed before: this rank's copies of it are done (the caller has synchronised the side stream since); pass
-        the barrier (every source's are), insert — or, for the names of file 2, claim."""
+        """The round sent before: this rank's copies of it are queued or done (the caller has synchronised the side stream when it
+        matters); pass the barrier (every source's are), insert — or, for the names of file 2, claim."""
         if self._pending_insert is None:
             return
         if self.world > 1:
+            if getattr(self, "_sync_side_later", False):
+                self.ctx.side_sync()  # (the copies of the round being landed: queued a whole pass ago)
+                self._sync_side_later = False
             dist.barrier(group=self._cpu_group)
-        off, f = self._pending_insert
-        pl = self._plan[f]
-        self._owner_round(self._arena[0] + off, pl["cap"], pl["units"], f, beside)
+        off, f, region, nblocks, stride = self._pending_insert
+        _dbg(f"rank {self.rank} landed a round of file {f} at {off} (nblocks {nblocks}, stride {stride})")
+        self._owner_round(self._arena[0] + off, region, nblocks, stride, self._plan[f]["units"], f, beside)
         self._pending_insert = None
 
-    def _owner_round(self, regions_ptr, cap, units, f, beside):
+    def _owner_round(self, regions_ptr, region_bytes, nblocks, stride, units, f, beside):
         if f == 0:
-            self.shard.shard_insert_slots(regions_ptr, self.world, cap, beside=beside, units=units)
+            self.shard.shard_insert_slots(regions_ptr, self.world, region_bytes, nblocks, stride, beside=beside, units=units)
         else:
-            self.shard.shard_claim_slots(regions_ptr, self.world, cap, beside=beside, units=units)
+            self.shard.shard_claim_slots(regions_ptr, self.world, region_bytes, nblocks, stride, beside=beside, units=units)
 
     def _route_round(self, final):
         """Pack the names that were not routed yet into one fixed-capacity region per owner, start their exchange and hand the
@@ -416,7 +501,7 @@ class ShardedFastqInfo:
         cap = max(1, mx) if mx <= 8192 else int(per * 1.03) + 6 * int(per ** 0.5) + 1024
         if os.environ.get("FQG_TEST_SLOT_CAP"):  # test hook: regions far too small, so that the overflow path is taken
             cap = int(os.environ["FQG_TEST_SLOT_CAP"])
-        stride = api.route_region_bytes(cap, units)
+        stride = api.route_region_bytes(1, cap, units)
         send = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
         recv = torch.empty(W * stride, dtype=torch.uint8, device=self.tdev)
         self.ctx.names_pack_slots(f, [send.data_ptr() + o * stride for o in range(W)], cap, units)
@@ -432,7 +517,7 @@ class ShardedFastqInfo:
                 work.wait()
             if self.tdev.type == "cuda":
                 torch.cuda.current_stream().synchronize()  # not the device: the pass on the library's stream keeps running
-            self._owner_round(recv.data_ptr(), cap, self._plan[ff]["units"], ff, beside=not final)
+            self._owner_round(recv.data_ptr(), api.route_region_bytes(1, cap, self._plan[ff]["units"]), 1, cap, self._plan[ff]["units"], ff, beside=not final)
             self._keep += [recv, send]
 
     def _route_names(self, f, with_bytes=True):
@@ -508,10 +593,13 @@ class ShardedFastqInfo:
                 # sees one, but the reference's message (which record, which line) is the exact path's business.  So is a region,
                 # slot or table that overflowed, a chunk redone by the two-pass kernels after its names had left, and any error.
                 inserted, equal, overflow, claimed, unpaired = self.shard.shard_slots_result()
-                mine_bad = rep.error.code != 0 or cut_short or equal > 0 or unpaired > 0 or overflow or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
+                broken = any(ctx.route_chunks(f)[1] for f, _, _ in files)  # a chunk whose names the pass should have routed went to the per-record kernels
+                mine_bad = rep.error.code != 0 or cut_short or equal > 0 or unpaired > 0 or overflow or broken or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
                 sums = self._gather((bool(mine_bad), inserted, claimed, int(rep.n_index_entries), int(rep.file[1].n_records)))
                 bad = any(x[0] for x in sums)
                 tot_ins, tot_cl, tot_names, tot_mates = (sum(x[k] for x in sums) for k in (1, 2, 3, 4))
+                _dbg(f"rank {r} verdict: error {rep.error.code} cut_short {cut_short} inserted {inserted} equal {equal} overflow {overflow} claimed {claimed} unpaired {unpaired} broken {broken} "
+                     f"two_pass {ctx.path_counts()['two_pass_fallbacks']} | totals inserted {tot_ins} names {tot_names} claimed {tot_cl} mates {tot_mates}")
                 if tot_ins != tot_names or (pair and (tot_cl != tot_names or tot_cl != tot_mates)):
                     bad = True  # a name was dropped on its way, a mate found nothing to claim, or names of file 1 are left over
                 if self._hook_exc is not None:
@@ -646,6 +734,12 @@ class ShardedFastqInfo:
         if r == 0:
             out["transcript"] = self.ctx.render(merged, name, name2 if pair else None, empty_ok=empty_ok, no_enc_ok=no_enc_ok)
         return out
+
+
+def _dbg(msg):
+    if os.environ.get("FQG_DEBUG_ROUTE"):
+        import sys
+        print("[route] " + msg, file=sys.stderr, flush=True)
 
 
 def _as_tensor(ptr, n, device):

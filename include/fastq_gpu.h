@@ -205,24 +205,39 @@ typedef void (*fqg_chunk_hook)(void* user, int file);
 int fqg_set_chunk_hook(fqg_ctx* ctx, fqg_chunk_hook hook, void* user);
 /* records whose names were not packed by fqg_names_pack_slots yet */
 int fqg_names_new(fqg_ctx* ctx, int file, uint64_t* n_new);
-/* Packs those records' names by owner into `world` regions of fixed capacity.  A name travels as a slot of 16 + 16 * name_units
- * bytes: {hash, record << 12 | length} and name_units 16-byte units of its bytes, zero padded (name_units = 0: the tuple alone —
- * enough for a one-file job, whose owner only has to notice equal hashes; a two-file job needs the bytes, the mate loop compares
- * every name).  Region o starts at region_ptrs[o] (device memory, local or a peer's mapped with fqg_ipc_open): one 16-byte header
- * {count, flags} and room for region_cap slots; fqg_route_region_bytes() bytes in all.  A count above region_cap says the region
- * overflowed (the surplus is dropped), flag 1 that a name was longer than its slot: the owner reports either and the caller repeats
- * the job through the exact path.  Returns when the regions are complete. */
+/* A name travels as a slot of 16 + 16 * name_units bytes: {hash, record << 12 | length} and name_units 16-byte units of its bytes,
+ * zero padded (name_units = 0: the tuple alone — enough for a one-file job, whose owner only has to notice equal hashes; a two-file
+ * job needs the bytes, the mate loop compares every name).  A region holds what one source has for one owner in one round, written
+ * by nblocks writers that do not talk to each other: a 16-byte header {uint32 nblocks, stride, flags, 0}, nblocks uint32 counts
+ * (padded to 16 bytes), then nblocks stretches of `stride` slots.  A count above `stride` says a stretch overflowed (the surplus is
+ * dropped), flag 1 that a name was longer than its slot: the owner reports either and the caller repeats the job through the
+ * exact path.  nblocks = 0: the source had nothing in this round. */
+static inline size_t fqg_route_region_bytes(uint32_t nblocks, uint64_t stride, uint32_t name_units) {
+  return 16u + (((size_t)nblocks * 4u + 15u) & ~(size_t)15u) + (size_t)nblocks * stride * (16u + 16u * (size_t)name_units);
+}
+/* (1) The clean-data pass writes the names itself, from shared memory, while it validates: chunk n of `file` (counting the chunks the
+ * pass accepted) goes to region_ptrs[o] + (n % depth) * region_bytes for owner o, laid out for fqg_route_blocks() writers of `stride`
+ * slots.  No name descriptors, no arena, no pack kernel on this path.  fqg_route_chunks says how many chunks are complete in their
+ * regions, and whether a chunk went another way (*broken: an anomaly handed it to the per-record kernels — the caller repeats the
+ * job).  The caller moves the regions to their owners (fqg_side_copy) and calls fqg_side_mark so that the pass that reuses a region
+ * waits for the copies out of it.  world = 0 switches the routing off. */
+int fqg_set_route(fqg_ctx* ctx, int file, uint32_t world, void* const* region_ptrs, size_t region_bytes, uint32_t depth, uint32_t stride, uint32_t name_units);
+int fqg_route_chunks(fqg_ctx* ctx, int file, uint64_t* n_chunks, int32_t* broken);
+int fqg_route_blocks(fqg_ctx* ctx, uint32_t* nblocks);
+int fqg_side_mark(fqg_ctx* ctx);
+/* (2) Records validated by the per-record kernels (the few at the seams of byte ranges; everything on the stand-in device) have name
+ * descriptors: this packs those not packed yet by owner into `world` dense regions (one writer: nblocks = 1, stride = region_cap).
+ * Region o starts at region_ptrs[o] (device memory, local or a peer's mapped with fqg_ipc_open).  Returns when they are complete. */
 int fqg_names_pack_slots(fqg_ctx* ctx, int file, uint32_t world, void* const* region_ptrs, uint64_t region_cap, uint32_t name_units);
-static inline size_t fqg_route_region_bytes(uint64_t region_cap, uint32_t name_units) { return 16u + (size_t)region_cap * (16u + 16u * (size_t)name_units); }
 /* owner side: room for n_names in the index shard before the first fqg_shard_insert_slots (the table cannot grow between rounds) */
 int fqg_shard_reserve(fqg_ctx* ctx, uint64_t n_names);
-/* inserts the slots of n_src regions (one after the other, fqg_route_region_bytes each); asynchronous: the regions must stay valid
- * until fqg_shard_slots_result — the index points at the names inside them.  beside != 0: one block per SM, so that the kernel fits
- * next to a running clean-data pass. */
-int fqg_shard_insert_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, uint64_t region_cap, uint32_t name_units, int beside);
+/* inserts the slots of n_src regions (region_bytes apart, planned for nblocks writers of `stride` slots); asynchronous: the regions
+ * must stay valid until fqg_shard_slots_result — the index points at the names inside them.  beside != 0: one block per SM, so that
+ * the kernel fits next to a running clean-data pass. */
+int fqg_shard_insert_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside);
 /* the mate loop at the owner (src/fastq_info.c:333-350): the slots of file 2's names (name_units > 0) look their name up by hash and
  * bytes and claim it (the reference's lookup-then-delete) */
-int fqg_shard_claim_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, uint64_t region_cap, uint32_t name_units, int beside);
+int fqg_shard_claim_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside);
 /* waits for the inserts and claims: names inserted; names that were in the index already (name_units = 0: equal hashes, which
  * tuples alone cannot tell from a duplicate); whether a region, a slot or the table overflowed; names claimed by mates; mates that
  * found no name, or one that had been claimed before.  Anything but inserted == names of file 1, claimed == inserted == mates

@@ -256,65 +256,72 @@ class FqSimDevice : public FqDevice {
       uint32_t o = fq_owner_of(nm.hash, world);
       unsigned long long pos = cursors[o]++;
       if (pos >= cap) continue;
-      uint8_t* slot = R.region[o] + 16 + pos * sb;
+      uint8_t* slot = R.region[o] + 16 + fq_route_counts_bytes(1) + pos * sb;
       FqRouteSlot h; h.hash = nm.hash; h.rec_len = ((unsigned long long)(g0 + k) << 12) | nm.len;
       memcpy(slot, &h, 16);
       if (units) { memset(slot + 16, 0, (size_t)units * 16); memcpy(slot + 16, arena + nm.off, std::min<size_t>(nm.len, (size_t)units * 16)); }
       if (units && nm.len > 16u * units) cursors[FQ_SHARD_MAX_SRC + o] |= FQ_ROUTE_NAME_TOO_LONG;
     }
   }
-  void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R) override {
-    for (uint32_t o = 0; o < world; o++) { unsigned long long* h = (unsigned long long*)R.region[o]; h[0] = cursors[o]; h[1] = cursors[FQ_SHARD_MAX_SRC + o]; }
+  void route_end(const unsigned long long* cursors, uint32_t world, const FqRegionPtrs& R, uint64_t cap) override {
+    for (uint32_t o = 0; o < world; o++) {
+      FqRegionHdr h; h.nblocks = 1; h.stride = (uint32_t)cap; h.flags = (uint32_t)cursors[FQ_SHARD_MAX_SRC + o]; h.pad = 0;
+      memcpy(R.region[o], &h, sizeof h);
+      uint32_t c = cursors[o] > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cursors[o];
+      memcpy(R.region[o] + 16, &c, 4);
+    }
   }
   static bool same_name(unsigned long long idx1, const FqRouteSlot* sl) {
     const FqRouteSlot* other = (const FqRouteSlot*)(uintptr_t)(idx1 << 4);
     uint32_t len = (uint32_t)(sl->rec_len & 0xFFF);
     return (uint32_t)(other->rec_len & 0xFFF) == len && memcmp(other + 1, sl + 1, len) == 0;
   }
-  void shard_insert_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
-                          unsigned long long* counters, bool) override {
-    n_launch_++;
-    const size_t sb = fq_route_slot_bytes(units), rb = fq_route_region_bytes(cap, units);
+  /* calls f(slot) for every slot the n_src regions hold; flags what contradicts the plan in counters[2] */
+  template <class F> static void each_slot(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units,
+                                           unsigned long long* counters, F f) {
+    const size_t sb = fq_route_slot_bytes(units);
     for (uint32_t src = 0; src < n_src; src++) {
-      const uint8_t* reg = regions + (size_t)src * rb;
-      unsigned long long cnt = ((const unsigned long long*)reg)[0];
-      if (cnt > cap || ((const unsigned long long*)reg)[1]) { counters[2] = 1; cnt = std::min<unsigned long long>(cnt, cap); }
-      for (unsigned long long m = 0; m < cnt; m++) {
-        const FqRouteSlot* sl = (const FqRouteSlot*)(reg + 16 + m * sb);
-        unsigned long long i = sl->hash & mask, probes = 0;
-        for (;; i = (i + 1) & mask) {
-          if (++probes > mask) { counters[2] = 1; break; }
-          FqSlot& s = slots[i];
-          if (s.hash == FQ_HASH_EMPTY) { s.hash = sl->hash; s.idx1 = (unsigned long long)(uintptr_t)sl >> 4; counters[1]++; break; }
-          if (s.hash != sl->hash) continue;
-          if (units && !same_name(s.idx1, sl)) continue;
-          counters[0]++;
-          break;
-        }
+      const uint8_t* reg = regions + (size_t)src * region_bytes;
+      FqRegionHdr h; memcpy(&h, reg, sizeof h);
+      if (h.nblocks == 0) continue;
+      if (h.nblocks > nblocks || h.stride != stride || h.flags) counters[2] = 1;
+      for (uint32_t b = 0; b < std::min(h.nblocks, nblocks); b++) {
+        uint32_t cnt; memcpy(&cnt, reg + 16 + 4 * (size_t)b, 4);
+        if (cnt > stride) { counters[2] = 1; cnt = (uint32_t)stride; }
+        for (uint32_t k = 0; k < cnt; k++) f((const FqRouteSlot*)(reg + 16 + fq_route_counts_bytes(h.nblocks) + ((size_t)b * stride + k) * sb));
       }
     }
   }
-  void shard_claim_slots(const uint8_t* regions, uint32_t n_src, uint64_t cap, uint32_t units, FqSlot* slots, unsigned long long mask,
-                         unsigned long long* counters, bool) override {
+  void shard_insert_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
+                          unsigned long long mask, unsigned long long* counters, bool) override {
     n_launch_++;
-    const size_t sb = fq_route_slot_bytes(units), rb = fq_route_region_bytes(cap, units);
-    for (uint32_t src = 0; src < n_src; src++) {
-      const uint8_t* reg = regions + (size_t)src * rb;
-      unsigned long long cnt = ((const unsigned long long*)reg)[0];
-      if (cnt > cap || ((const unsigned long long*)reg)[1]) { counters[2] = 1; cnt = std::min<unsigned long long>(cnt, cap); }
-      for (unsigned long long m = 0; m < cnt; m++) {
-        const FqRouteSlot* sl = (const FqRouteSlot*)(reg + 16 + m * sb);
-        unsigned long long i = sl->hash & mask, probes = 0;
-        for (;; i = (i + 1) & mask) {
-          if (++probes > mask + 1) { counters[9]++; break; }
-          FqSlot& s = slots[i];
-          if (s.hash == FQ_HASH_EMPTY) { counters[9]++; break; }
-          if (s.hash != sl->hash || !same_name(s.idx1, sl)) continue;
-          if (s.claim2 == FQ_IDX_NONE) { s.claim2 = sl->rec_len >> 12; counters[8]++; } else counters[9]++;
-          break;
-        }
+    each_slot(regions, n_src, region_bytes, nblocks, stride, units, counters, [&](const FqRouteSlot* sl) {
+      unsigned long long i = sl->hash & mask, probes = 0;
+      for (;; i = (i + 1) & mask) {
+        if (++probes > mask) { counters[2] = 1; break; }
+        FqSlot& s = slots[i];
+        if (s.hash == FQ_HASH_EMPTY) { s.hash = sl->hash; s.idx1 = (unsigned long long)(uintptr_t)sl >> 4; counters[1]++; break; }
+        if (s.hash != sl->hash) continue;
+        if (units && !same_name(s.idx1, sl)) continue;
+        counters[0]++;
+        break;
       }
-    }
+    });
+  }
+  void shard_claim_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
+                         unsigned long long mask, unsigned long long* counters, bool) override {
+    n_launch_++;
+    each_slot(regions, n_src, region_bytes, nblocks, stride, units, counters, [&](const FqRouteSlot* sl) {
+      unsigned long long i = sl->hash & mask, probes = 0;
+      for (;; i = (i + 1) & mask) {
+        if (++probes > mask + 1) { counters[9]++; break; }
+        FqSlot& s = slots[i];
+        if (s.hash == FQ_HASH_EMPTY) { counters[9]++; break; }
+        if (s.hash != sl->hash || !same_name(s.idx1, sl)) continue;
+        if (s.claim2 == FQ_IDX_NONE) { s.claim2 = sl->rec_len >> 12; counters[8]++; } else counters[9]++;
+        break;
+      }
+    });
   }
   /* "peer memory" of the stand-in: a POSIX shared-memory segment that the other ranks of a gloo test map by name (the handle),
    * so that the peer-memory routing rounds of dist.py run on CPU exactly as they do over CUDA IPC */
