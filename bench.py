@@ -49,20 +49,21 @@ class ClockSampler(threading.Thread):
     """nvidia-smi clocks and throttle reasons during the timed region."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, indices, period=0.05):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.indices, self.rows, self.stop_flag, self.period = indices, [], False, period
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                out = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                for line in out.splitlines():
+                    if line.strip():
+                        self.rows.append([x.strip() for x in line.split(",")])
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(self.period)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
@@ -385,12 +386,18 @@ def main():
 
     for _ in range(a.warmup):
         step()
+    if world > 1:
+        runner.phase_ms.clear()
+        for k in runner.host_ms:
+            runner.host_ms[k] = 0.0
     ctx.kernel_stats(reset=True)
     if world > 1 and runner.shard is not None:
         runner.shard.kernel_stats(reset=True)
     l0 = ctx.launch_count() + (runner.shard.launch_count() if world > 1 and runner.shard is not None else 0)
-    sampler = ClockSampler(local)
-    sampler.start()
+    # (one sampler for all GPUs of the job, on rank 0: every nvidia-smi call takes the driver's attention for a moment)
+    sampler = ClockSampler(list(range(world)) if world > 1 else [local], period=0.05 if world == 1 else 0.25)
+    if rank == 0:
+        sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()  # (torch's stream is idle here: the event marks the device's clock at the start of the timed region)
@@ -405,7 +412,8 @@ def main():
     wall = time.perf_counter() - t0
     span_ms = ev0.elapsed_time(ev1)  # device clock over the whole timed region, every stream's work and every host gap included
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     launches = ctx.launch_count() - l0
     ks = ctx.kernel_stats()
     paths = ctx.path_counts()
@@ -479,6 +487,8 @@ def main():
         out["config"]["parallelism"] = f"byte-range shards x{world}, names routed by hash to the owner of their index shard ({runner.route_description()}), stats all-reduced"
         out["config"]["routing_rounds"] = runner.rounds_done
         out["rank_ms_per_step"] = allms
+        out["host_phase_ms_per_step_rank0"] = {k: round(v / a.steps, 2) for k, v in runner.phase_ms.items()}  # wall time of the phases of ShardedFastqInfo.run_device
+        out["host_round_ms_per_step_rank0"] = {k: round(v / a.steps, 2) for k, v in runner.host_ms.items()}  # ... inside the routing rounds: waiting for the barrier, queueing copies
         out["e2e"] = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "measured at N=1 only"}
 
     if rank == 0 and world == 1:

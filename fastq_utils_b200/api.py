@@ -108,8 +108,8 @@ def bind(L):
     L.fqg_names_new.argtypes = [vp, ci, ctypes.POINTER(u64)]
     L.fqg_names_pack_slots.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), u64, ctypes.c_uint32]
     L.fqg_shard_reserve.argtypes = [vp, u64]
-    L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, sz, ctypes.c_uint32, u64, ctypes.c_uint32, ci]
-    L.fqg_shard_claim_slots.argtypes = [vp, vp, ctypes.c_uint32, sz, ctypes.c_uint32, u64, ctypes.c_uint32, ci]
+    L.fqg_shard_insert_slots.argtypes = [vp, vp, ctypes.c_uint32, sz, ctypes.c_uint32, u64, ctypes.c_uint32, ci, vp, u64]
+    L.fqg_shard_claim_slots.argtypes = [vp, vp, ctypes.c_uint32, sz, ctypes.c_uint32, u64, ctypes.c_uint32, ci, vp, u64]
     L.fqg_set_route.argtypes = [vp, ci, ctypes.c_uint32, ctypes.POINTER(vp), sz, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
     L.fqg_route_chunks.argtypes = [vp, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
     L.fqg_route_blocks.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
@@ -303,11 +303,13 @@ class FastqInfo:
     def shard_reserve(self, n_names):
         _check(self._ctx, lib().fqg_shard_reserve(self._ctx, n_names), "fqg_shard_reserve")
 
-    def shard_insert_slots(self, regions_ptr, n_src, region_bytes, nblocks, stride, beside, units=0):
-        _check(self._ctx, lib().fqg_shard_insert_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, region_bytes, nblocks, stride, units, 1 if beside else 0), "fqg_shard_insert_slots")
+    def shard_insert_slots(self, regions_ptr, n_src, region_bytes, nblocks, stride, beside, units=0, flags_ptr=0, expect=0):
+        _check(self._ctx, lib().fqg_shard_insert_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, region_bytes, nblocks, stride, units, 1 if beside else 0,
+                                                       ctypes.c_void_p(flags_ptr), expect), "fqg_shard_insert_slots")
 
-    def shard_claim_slots(self, regions_ptr, n_src, region_bytes, nblocks, stride, beside, units):
-        _check(self._ctx, lib().fqg_shard_claim_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, region_bytes, nblocks, stride, units, 1 if beside else 0), "fqg_shard_claim_slots")
+    def shard_claim_slots(self, regions_ptr, n_src, region_bytes, nblocks, stride, beside, units, flags_ptr=0, expect=0):
+        _check(self._ctx, lib().fqg_shard_claim_slots(self._ctx, ctypes.c_void_p(regions_ptr), n_src, region_bytes, nblocks, stride, units, 1 if beside else 0,
+                                                      ctypes.c_void_p(flags_ptr), expect), "fqg_shard_claim_slots")
 
     def set_route(self, file, region_ptrs, region_bytes, depth, stride, units):
         """the clean-data pass of every chunk of `file` writes the names into per-owner regions itself (include/fastq_gpu.h); [] switches it off"""

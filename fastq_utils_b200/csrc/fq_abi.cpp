@@ -163,13 +163,15 @@ extern "C" int fqg_shard_reserve(fqg_ctx* c, uint64_t n_names) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->eng->shard_reserve(n_names))
 }
-extern "C" int fqg_shard_claim_slots(fqg_ctx* c, const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside) {
+extern "C" int fqg_shard_claim_slots(fqg_ctx* c, const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside,
+                                     const void* device_flags, uint64_t expect) {
   if (!c || !regions) return FQG_ERR_USAGE;
-  FQG_GUARD(c, c->eng->shard_claim_slots(regions, n_src, region_bytes, nblocks, stride, name_units, beside != 0))
+  FQG_GUARD(c, c->eng->shard_claim_slots(regions, n_src, region_bytes, nblocks, stride, name_units, beside != 0, device_flags, expect))
 }
-extern "C" int fqg_shard_insert_slots(fqg_ctx* c, const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside) {
+extern "C" int fqg_shard_insert_slots(fqg_ctx* c, const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside,
+                                      const void* device_flags, uint64_t expect) {
   if (!c || !regions) return FQG_ERR_USAGE;
-  FQG_GUARD(c, c->eng->shard_insert_slots(regions, n_src, region_bytes, nblocks, stride, name_units, beside != 0))
+  FQG_GUARD(c, c->eng->shard_insert_slots(regions, n_src, region_bytes, nblocks, stride, name_units, beside != 0, device_flags, expect))
 }
 extern "C" int fqg_set_route(fqg_ctx* c, int file, uint32_t world, void* const* region_ptrs, size_t region_bytes, uint32_t depth, uint32_t stride, uint32_t name_units) {
   if (!c || file < 0 || file > 1 || (world && !region_ptrs)) return FQG_ERR_USAGE;

@@ -847,7 +847,30 @@ __device__ __forceinline__ bool route_same_name(unsigned long long idx1, const F
 struct SlotInsertParams {
   const uint8_t* regions; uint32_t n_src; size_t region_bytes; uint32_t nblocks; unsigned long long stride; uint32_t units;
   FqSlot* slots; unsigned long long mask; unsigned long long* counters;
+  const unsigned long long* flags; unsigned long long expect; /* flags[s] >= expect: source s has delivered its region (NULL: the host knows) */
 };
+/* The sources announce their regions with a flag word written behind the region's bytes (same stream of copies, so the bytes are
+ * there when the flag is): the owner's kernel waits for the flags on the device — no host takes part in a routing round.  One
+ * thread per source polls (system-scope acquire: the writers are the copy engines of other GPUs); a source that stays silent for
+ * seconds is given up (counters[2]: the caller repeats the job).  False: do not touch the regions. */
+__device__ __forceinline__ bool route_wait_sources(const SlotInsertParams& P) {
+  __shared__ int s_late;
+  if (!P.flags) return true;
+  if (threadIdx.x == 0) s_late = 0;
+  __syncthreads();
+  if (threadIdx.x < P.n_src) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(P.flags + threadIdx.x) : "memory");
+      if (v >= P.expect) break;
+      if (clock64() - t0 > 20000000000ll) { s_late = 1; atomicExch(P.counters + 2, 1ull); break; } /* about ten seconds */
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  return s_late == 0;
+}
 /* item m of the planned n_src x nblocks x stride slots → the route slot, or NULL when the stretch holds fewer */
 __device__ __forceinline__ const FqRouteSlot* route_item(const SlotInsertParams& P, unsigned long long m, size_t slot_bytes) {
   const unsigned long long per = (unsigned long long)P.nblocks * P.stride;
@@ -868,6 +891,7 @@ fq_shard_insert_slots_kernel(const SlotInsertParams P) {
    * atomics, not their latency, are the limit), and so are short blocks on a low-priority stream (they crowd the start of the
    * next pass, whose blocks must all be resident). */
   unsigned long long inserted = 0, equal = 0;
+  if (!route_wait_sources(P)) return;
   const unsigned long long total = (unsigned long long)P.n_src * P.nblocks * P.stride, step = (unsigned long long)gridDim.x * blockDim.x;
   const size_t slot_bytes = fq_route_slot_bytes(P.units);
   for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
@@ -894,6 +918,7 @@ fq_shard_insert_slots_kernel(const SlotInsertParams P) {
 __global__ void __launch_bounds__(256, 8)
 fq_shard_claim_slots_kernel(const SlotInsertParams P) {
   unsigned long long claimed = 0, unpaired = 0;
+  if (!route_wait_sources(P)) return;
   const unsigned long long total = (unsigned long long)P.n_src * P.nblocks * P.stride, step = (unsigned long long)gridDim.x * blockDim.x;
   const size_t slot_bytes = fq_route_slot_bytes(P.units);
   for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
@@ -1371,14 +1396,18 @@ class FqCudaDevice : public FqDevice {
     FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
   }
   void shard_insert_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
-                          unsigned long long mask, unsigned long long* counters, bool beside) override { slots_kernel(regions, n_src, region_bytes, nblocks, stride, units, slots, mask, counters, beside, false); }
+                          unsigned long long mask, unsigned long long* counters, bool beside, const unsigned long long* flags, unsigned long long expect) override {
+    slots_kernel(regions, n_src, region_bytes, nblocks, stride, units, slots, mask, counters, beside, false, flags, expect);
+  }
   void shard_claim_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
-                         unsigned long long mask, unsigned long long* counters, bool beside) override { slots_kernel(regions, n_src, region_bytes, nblocks, stride, units, slots, mask, counters, beside, true); }
+                         unsigned long long mask, unsigned long long* counters, bool beside, const unsigned long long* flags, unsigned long long expect) override {
+    slots_kernel(regions, n_src, region_bytes, nblocks, stride, units, slots, mask, counters, beside, true, flags, expect);
+  }
   void slots_kernel(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
-                    unsigned long long mask, unsigned long long* counters, bool beside, bool claim) {
+                    unsigned long long mask, unsigned long long* counters, bool beside, bool claim, const unsigned long long* flags, unsigned long long expect) {
     if (!n_src || !nblocks || !stride) return;
     SlotInsertParams P; P.regions = regions; P.n_src = n_src; P.region_bytes = region_bytes; P.nblocks = nblocks; P.stride = stride; P.units = units;
-    P.slots = slots; P.mask = mask; P.counters = counters;
+    P.slots = slots; P.mask = mask; P.counters = counters; P.flags = flags; P.expect = expect;
     unsigned long long total = (unsigned long long)n_src * nblocks * stride;
     int grid = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)sms_ * (beside ? 1 : 8));
     after_main();

@@ -169,11 +169,13 @@ class FqDevice {
    * exceeds its stretch, a name did not fit its slot, a header contradicts the plan, or the table is full.  A slot whose hash is
    * taken by ANOTHER name walks on (units > 0).  Asynchronous. */
   virtual void shard_insert_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units,
-                                  FqSlot* slots, unsigned long long mask, unsigned long long* counters, bool beside) = 0;
+                                  FqSlot* slots, unsigned long long mask, unsigned long long* counters, bool beside,
+                                  const unsigned long long* flags, unsigned long long expect) = 0; /* flags != NULL: wait on the device until flags[s] >= expect for every source s */
   /* the mate loop at the owner (src/fastq_info.c:333-350: lookup, then delete): every slot (units > 0) looks its name up by hash and
    * bytes; the first one to find it claims it (counters[8]++), a name that is not there or was claimed before counts in counters[9] */
   virtual void shard_claim_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units,
-                                 FqSlot* slots, unsigned long long mask, unsigned long long* counters, bool beside) = 0;
+                                 FqSlot* slots, unsigned long long mask, unsigned long long* counters, bool beside,
+                                 const unsigned long long* flags, unsigned long long expect) = 0;
   /* the number of writers (CTAs) a clean-data pass in per-line mode uses at most: the nblocks of the regions it routes into */
   virtual uint32_t lanes_max_blocks() { return 0; }
   /* the main stream's next clean-data pass waits for what was queued on the side stream so far (copies out of the regions that

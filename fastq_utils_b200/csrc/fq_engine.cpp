@@ -1286,17 +1286,17 @@ void FqEngine::shard_reserve(uint64_t n_names) {
   ensure_table(std::max<uint64_t>(n_names, 1));
 }
 
-void FqEngine::shard_insert_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside) {
+void FqEngine::shard_insert_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside, const void* flags, uint64_t expect) {
   if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_insert_slots: n_src out of range");
   if (!slots_) ensure_table(1);
-  dev_->shard_insert_slots((const uint8_t*)regions, n_src, region_bytes, nblocks, stride, units, slots_, table_cap_ - 1, counters_, beside);
+  dev_->shard_insert_slots((const uint8_t*)regions, n_src, region_bytes, nblocks, stride, units, slots_, table_cap_ - 1, counters_, beside, (const unsigned long long*)flags, expect);
   table_names_ = 1; /* the table holds names the engine cannot re-insert: it must not grow any more */
 }
-void FqEngine::shard_claim_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside) {
+void FqEngine::shard_claim_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside, const void* flags, uint64_t expect) {
   if (n_src == 0 || n_src > FQ_SHARD_MAX_SRC) throw std::runtime_error("fqg_shard_claim_slots: n_src out of range");
   if (!units) throw std::runtime_error("fqg_shard_claim_slots: the mate loop compares names, the slots must carry their bytes");
   if (!slots_) ensure_table(1);
-  dev_->shard_claim_slots((const uint8_t*)regions, n_src, region_bytes, nblocks, stride, units, slots_, table_cap_ - 1, counters_, beside);
+  dev_->shard_claim_slots((const uint8_t*)regions, n_src, region_bytes, nblocks, stride, units, slots_, table_cap_ - 1, counters_, beside, (const unsigned long long*)flags, expect);
 }
 /* sharded runs: the clean-data pass of every chunk of `file` writes the names straight into per-owner regions (include/fastq_gpu.h) */
 void FqEngine::set_route(int file, uint32_t world, void* const* region_ptrs, size_t region_bytes, uint32_t depth, uint32_t stride, uint32_t units) {

@@ -106,8 +106,8 @@ class FqEngine {
   uint64_t names_new(int file);
   void names_pack_slots(int file, uint32_t world, void* const* region_ptrs, uint64_t cap, uint32_t units);
   void shard_reserve(uint64_t n_names);
-  void shard_insert_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside);
-  void shard_claim_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside);
+  void shard_insert_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside, const void* flags, uint64_t expect);
+  void shard_claim_slots(const void* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, bool beside, const void* flags, uint64_t expect);
   void set_route(int file, uint32_t world, void* const* region_ptrs, size_t region_bytes, uint32_t depth, uint32_t stride, uint32_t units);
   uint64_t route_chunks(int file, int* broken) const { *broken = f_[file].route_broken ? 1 : 0; return f_[file].route_chunks; }
   void shard_slots_result(uint64_t* inserted, uint64_t* equal_hashes, int32_t* overflow, uint64_t* claimed, uint64_t* unpaired);

@@ -431,7 +431,7 @@ fq_lanes_kernel(const LanesParams P) {
       if (LINES && P.route_world) {
         uint32_t most = 0;
         for (uint32_t o = 0; o < P.route_world; o++) most = max(most, s_own[o]);
-        route_full = most + 2u * min((uint32_t)LN_SMAX, max(route_tile_max, 64u)) > P.route_stride;
+        route_full = most + 2u * (min((uint32_t)LN_SMAX, max(route_tile_max, 64u)) / P.route_world + 16u) > P.route_stride; /* (an owner's share of a tile's names, generously) */
       }
       const uint32_t nxt = LINES ? ((lost_a != 0 || lost_o != 0xFFFFFFFFu || route_full) ? 0xFFFFFFFFu : atomicAdd(P.ticket, 1u)) : 0xFFFFFFFFu;
       if (LINES) s_next = nxt; /* read after the barrier at the top of the next round */

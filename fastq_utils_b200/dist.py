@@ -28,6 +28,8 @@ import torch.distributed as dist
 from . import api
 
 KEY_NONE = (1 << 64) - 1
+FLAG_AREA = 4 << 20     # head of every rank's arena: the flag words its sources write behind their regions (8 bytes per file, round and source)
+FLAG_ROUNDS = 2048      # rounds per file the flag area has words for
 R_STOP, R_NAME = 0, 3
 E_DUP, E_UNPAIRED, E_LEFTOVER = 13, 14, 15
 MAX_READ_LENGTH = 2_500_000
@@ -60,9 +62,10 @@ class ShardedFastqInfo:
         self._pending_insert = None
         self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage, self._zero = None, None, False, False, None, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
-        self._plan = None
+        self._plan, self._job, self._flagvals = None, 0, None
         self.exact_reruns = 0  # jobs the speculative / pipelined path handed to the exact path (tests)
         self.host_ms = {"pack": 0.0, "barrier": 0.0}  # host time inside the peer-memory rounds, accumulated
+        self.phase_ms = {}  # host wall time of the phases of run_device, accumulated over jobs (bench.py reports them)
 
     def route_description(self):
         """how the names of the last job reached their owners (bench.py's config line)"""
@@ -231,15 +234,16 @@ class ShardedFastqInfo:
             units = max(1, -(-(len(name) + 3) // 16))
         nb = self.ctx.route_blocks() if (self.p2p and not self.p2p_stores and os.environ.get("FQG_ROUTE_IN_PASS", "1") not in ("", "0")) else 0
         tiny = os.environ.get("FQG_TEST_SLOT_CAP")  # test hook: regions far too small, so that the overflow path is taken
-        plan, base = [], 0
+        plan, base = [], FLAG_AREA
+        self._job += 1
         for info in infos:
-            rounds = max(1, max(-(-x[7] // step) for x in info))
+            rounds = min(FLAG_ROUNDS - 2, max(1, max(-(-x[7] // step) for x in info)))
             names_chunk = min(chunk, max(x[7] for x in info)) / max(min(x[4] for x in info), 16.0)  # (the estimate comes from the first records of every range)
             pl = {"rounds": rounds, "units": units, "round": 0, "fires": 0, "base": base}
             if nb:  # one stretch per CTA of the pass and owner, with room to spare
                 # (the CTAs claim tiles as they go: a CTA may get a few tiles more than its share)
                 per_tile = 31744.0 / max(min(x[4] for x in info), 16.0)
-                stride = int(tiny) if tiny else int(names_chunk / nb / W * 1.3 + 4 * per_tile) + 32
+                stride = int(tiny) if tiny else int(names_chunk / nb / W * 1.2 + 4 * (per_tile / W + 16)) + 32
                 left = int(tiny) if tiny else 16384
                 pl.update(mode="pass", nblocks=nb, stride=stride, region=api.route_region_bytes(nb, stride, units),
                           left_stride=left, left_region=api.route_region_bytes(1, left, units))
@@ -253,7 +257,7 @@ class ShardedFastqInfo:
             plan.append(pl)
         est = sum(x[7] / max(x[4], 16.0) for x in infos[0]) / W
         self.shard.shard_reserve(int(est * 1.05) + 4096)
-        self._plan, self._inflight, self._hook_exc, self._pending_insert = plan, [], None, None
+        self._plan, self._inflight, self._hook_exc = plan, [], None
         self._p2p_ok = self.p2p and self._ensure_arena(base)
         if not self._p2p_ok:
             for pl in plan:
@@ -263,6 +267,9 @@ class ShardedFastqInfo:
             self._stage = torch.zeros(need + 64, dtype=torch.uint8, device=self.tdev)
         if self._zero is None:
             self._zero = torch.zeros(64, dtype=torch.uint8, device=self.tdev)
+        # the flag words this rank will write behind its regions: job and round, never the same value twice
+        self._flagvals = torch.arange(1, FLAG_ROUNDS + 1, dtype=torch.int64, device=self.tdev) + (self._job << 20)
+        self._sync()
 
     def _feed_file_speculative(self, f, ptr, nbytes, info, routed=False):
         """Steps 1-2 without counting the line feeds of the range first: every rank takes the line phase of its range from its own
@@ -361,6 +368,7 @@ class ShardedFastqInfo:
         _dbg(f"rank {r} file {f} pass round {j} of {pl['rounds']} have={have} chunks={self.ctx.route_chunks(f)}")
         off = pl["base"] + (j * W + r) * region
         st = self._stage.data_ptr()
+        t1 = time.perf_counter()
         for d in range(W):
             o = (r + d) % W
             dst = (self._arena[0] if o == r else self._peer[o]) + off
@@ -368,10 +376,11 @@ class ShardedFastqInfo:
                 self.ctx.side_copy(dst, st + (o * 2 + j % 2) * region, region)
             else:
                 self.ctx.side_copy(dst, self._zero.data_ptr(), 16)
+            self._send_flag(o, f, j)
         self.ctx.side_mark()
-        self._land_pending_round(beside=True)
-        self._pending_insert = (pl["base"] + j * W * region, f, region, pl["nblocks"], pl["stride"])
-        self._sync_side_later = True
+        self.host_ms["pack"] += (time.perf_counter() - t1) * 1e3
+        # the owner's kernel waits for its sources on the device (their flag words): launched now, beside the running pass
+        self._owner_round(self._arena[0] + pl["base"] + j * W * region, region, pl["nblocks"], pl["stride"], pl["units"], f, True, flag_round=j)
         pl["round"] += 1
 
     def _left_round(self):
@@ -385,13 +394,20 @@ class ShardedFastqInfo:
         st = self._stage.data_ptr()
         off = pl["left_base"] + r * region
         self.ctx.names_pack_slots(f, [self._arena[0] + off if o == r else st + o * region for o in range(W)], cap, pl["units"])
-        for d in range(1, W):
+        for d in range(W):
             o = (r + d) % W
-            self.ctx.side_copy(self._peer[o] + off, st + o * region, region)
-        self.ctx.side_sync()
-        self._land_pending_round(beside=False)
-        self._pending_insert = (pl["left_base"], f, region, 1, cap)
-        self._land_pending_round(beside=False)
+            if o != r:
+                self.ctx.side_copy(self._peer[o] + off, st + o * region, region)
+            self._send_flag(o, f, pl["rounds"])
+        self._owner_round(self._arena[0] + pl["left_base"], region, 1, cap, pl["units"], f, False, flag_round=pl["rounds"])
+
+    def _flag_off(self, f, j):
+        return 8 * ((f * FLAG_ROUNDS + j) * self.world)
+
+    def _send_flag(self, o, f, j):
+        """behind the bytes of round j for owner o (same stream of copies): the word that tells o's kernel they are there"""
+        dst = (self._arena[0] if o == self.rank else self._peer[o]) + self._flag_off(f, j) + 8 * self.rank
+        self.ctx.side_copy(dst, self._flagvals.data_ptr() + 8 * j, 8)
 
     def _ensure_arena(self, need):
         """Peer-writable receive memory (CUDA IPC over NVLink): `need` bytes on every rank, mapped by every other rank.  Collective;
@@ -413,6 +429,8 @@ class ShardedFastqInfo:
                 self._arena = None
             size = int(need * 1.1) + (1 << 20)
             ptr, handle = self.shard.ipc_alloc(size)
+            _as_tensor(ptr, FLAG_AREA, self.tdev).zero_()  # no flag word has been written yet (the gathers below: before anybody writes one)
+            self._sync()
         except RuntimeError:
             ok, ptr, handle, size = False, 0, b"", 0
         handles = self._gather(handle if ok else None)
@@ -455,38 +473,25 @@ class ShardedFastqInfo:
             self.ctx.names_pack_slots(f, [self._arena[0] + off + r * stride if o == r else st + o * stride for o in range(W)], cap, units)
             copies = [(self._peer[(r + d) % W] + off + r * stride, st + ((r + d) % W) * stride) for d in range(1, W)]
         t1 = time.perf_counter()
-        self._land_pending_round(beside=True)  # pack first, insert second: both want the one free block slot per SM
         for dst, src in copies:
             self.ctx.side_copy(dst, src, stride)
-        t2 = time.perf_counter()
+        for o in range(W):
+            self._send_flag(o, f, pl["round"])
         self.host_ms["pack"] += (t1 - t0) * 1e3
-        self.host_ms["barrier"] += (t2 - t1) * 1e3
-        self._pending_insert = (off, f, stride, 1, cap)
+        # pack first, insert second (both want the one block slot per SM that the pass leaves free); the owner's kernel waits on the
+        # device for its sources' flag words: no host barrier
+        self._owner_round(self._arena[0] + off, stride, 1, cap, units, f, not final, flag_round=pl["round"])
         pl["round"] += 1
-        if final:
-            self.ctx.side_sync()
-            self._land_pending_round(beside=False)
 
-    def _land_pending_round(self, beside):
-        """The round sent before: this rank's copies of it are queued or done (the caller has synchronised the side stream when it
-        matters); pass the barrier (every source's are), insert — or, for the names of file 2, claim."""
-        if self._pending_insert is None:
-            return
-        if self.world > 1:
-            if getattr(self, "_sync_side_later", False):
-                self.ctx.side_sync()  # (the copies of the round being landed: queued a whole pass ago)
-                self._sync_side_later = False
-            dist.barrier(group=self._cpu_group)
-        off, f, region, nblocks, stride = self._pending_insert
-        _dbg(f"rank {self.rank} landed a round of file {f} at {off} (nblocks {nblocks}, stride {stride})")
-        self._owner_round(self._arena[0] + off, region, nblocks, stride, self._plan[f]["units"], f, beside)
-        self._pending_insert = None
-
-    def _owner_round(self, regions_ptr, region_bytes, nblocks, stride, units, f, beside):
+    def _owner_round(self, regions_ptr, region_bytes, nblocks, stride, units, f, beside, flag_round=None):
+        """this rank's index shard takes a round: file 1's names are inserted, file 2's claim them"""
+        kw = {}
+        if flag_round is not None:
+            kw = {"flags_ptr": self._arena[0] + self._flag_off(f, flag_round), "expect": (self._job << 20) + flag_round + 1}
         if f == 0:
-            self.shard.shard_insert_slots(regions_ptr, self.world, region_bytes, nblocks, stride, beside=beside, units=units)
+            self.shard.shard_insert_slots(regions_ptr, self.world, region_bytes, nblocks, stride, beside=beside, units=units, **kw)
         else:
-            self.shard.shard_claim_slots(regions_ptr, self.world, region_bytes, nblocks, stride, beside=beside, units=units)
+            self.shard.shard_claim_slots(regions_ptr, self.world, region_bytes, nblocks, stride, beside=beside, units=units, **kw)
 
     def _route_round(self, final):
         """Pack the names that were not routed yet into one fixed-capacity region per owner, start their exchange and hand the
@@ -517,7 +522,7 @@ class ShardedFastqInfo:
                 work.wait()
             if self.tdev.type == "cuda":
                 torch.cuda.current_stream().synchronize()  # not the device: the pass on the library's stream keeps running
-            self._owner_round(recv.data_ptr(), api.route_region_bytes(1, cap, self._plan[ff]["units"]), 1, cap, self._plan[ff]["units"], ff, beside=not final)
+            self._owner_round(recv.data_ptr(), api.route_region_bytes(1, cap, self._plan[ff]["units"]), 1, cap, self._plan[ff]["units"], ff, not final)
             self._keep += [recv, send]
 
     def _route_names(self, f, with_bytes=True):
@@ -555,10 +560,17 @@ class ShardedFastqInfo:
         """ptr/nbytes (and ptr2/nbytes2 for MODE_INDEX_PAIR): this rank's byte range of each file in device memory (16-byte
         aligned, 64 readable bytes after it).  Returns the merged report and, on rank 0, the rendered (rc, stdout, stderr)."""
         W, r, ctx = self.world, self.rank, self.ctx
+        tm = {"t": time.perf_counter()}
+
+        def lap(name):
+            now = time.perf_counter()
+            self.phase_ms[name] = self.phase_ms.get(name, 0.0) + (now - tm["t"]) * 1e3
+            tm["t"] = now
         ctx.reset()
         if self.shard:
             self.shard.reset()
         self._keep = []
+        lap("reset")
         pair = self.mode == api.MODE_INDEX_PAIR
         again = dict(name=name, ptr2=ptr2, nbytes2=nbytes2, name2=name2, empty_ok=empty_ok, no_enc_ok=no_enc_ok, _exact=True)
         routed = self.shard is not None and self.pipeline
@@ -576,13 +588,17 @@ class ShardedFastqInfo:
             self._sniff = got[0][1]
             speculative = all(all(x[0] for x in info) and info[0][1] == 0 for info in infos) and all(x is not None for x in self._sniff)
         if speculative:
+            lap("guess")
             if routed:
                 self._plan_routes(infos, pair)
+            lap("plan")
             if pair:
                 ctx.set_file_total(0, 1 << 40)  # (the mate loop's event keys continue after file 1's: only their order matters here)
             for (f, p, n), info in zip(files, infos):
                 self._feed_file_speculative(f, p, n, info, routed=routed)
+                lap(f"file{f}")
             rep = ctx.finish()
+            lap("finish")
             # a NUL-led header line ended this rank's range early and quietly (src/fastq.c:248): not an error here, but the ranges
             # behind it do not exist for the reference — the exact path sorts that out
             cut_short = any(int(rep.file[f].n_records) < ctx.records_fed(f) for f, _, _ in files)
@@ -615,6 +631,7 @@ class ShardedFastqInfo:
                 return self.run_device(ptr, nbytes, **again)  # an error, a duplicate name or a wrong guess: the exact path decides
             local_key, T0, T1 = KEY_NONE, 0, 0
             dup, unp = (KEY_NONE, 0, b""), (KEY_NONE, 0, b"")
+            lap("verdict")
         if not speculative:
             exp0, T0 = self._feed_file(0, ptr, nbytes, gather0=_gather0)
             exp1, T1 = None, 0
@@ -730,6 +747,7 @@ class ShardedFastqInfo:
             over = c > m0.num_rds // 2
             med = lo + int(torch.nonzero(over)[0]) if bool(over.any()) else MAX_READ_LENGTH
         merged.median_rl = med
+        lap("merge")
         out = {"report": merged, "event_key": best, "n_records": N0, "n_records2": N1, "n_index_entries": names_total, "n_index_left": left}
         if r == 0:
             out["transcript"] = self.ctx.render(merged, name, name2 if pair else None, empty_ok=empty_ok, no_enc_ok=no_enc_ok)

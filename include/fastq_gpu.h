@@ -234,10 +234,15 @@ int fqg_shard_reserve(fqg_ctx* ctx, uint64_t n_names);
 /* inserts the slots of n_src regions (region_bytes apart, planned for nblocks writers of `stride` slots); asynchronous: the regions
  * must stay valid until fqg_shard_slots_result — the index points at the names inside them.  beside != 0: one block per SM, so that
  * the kernel fits next to a running clean-data pass. */
-int fqg_shard_insert_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside);
+int fqg_shard_insert_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside,
+                           const void* device_flags, uint64_t expect);
+/* device_flags != NULL: n_src 64-bit words; the kernel itself waits until word s is >= expect before it reads source s's region.  The
+ * sources write their word behind the region's bytes (fqg_side_copy, same stream): no host takes part in a routing round.  A source
+ * that stays silent for about ten seconds is given up (overflow is reported: the caller repeats the job). */
 /* the mate loop at the owner (src/fastq_info.c:333-350): the slots of file 2's names (name_units > 0) look their name up by hash and
  * bytes and claim it (the reference's lookup-then-delete) */
-int fqg_shard_claim_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside);
+int fqg_shard_claim_slots(fqg_ctx* ctx, const void* device_regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t name_units, int beside,
+                          const void* device_flags, uint64_t expect);
 /* waits for the inserts and claims: names inserted; names that were in the index already (name_units = 0: equal hashes, which
  * tuples alone cannot tell from a duplicate); whether a region, a slot or the table overflowed; names claimed by mates; mates that
  * found no name, or one that had been claimed before.  Anything but inserted == names of file 1, claimed == inserted == mates

@@ -292,9 +292,22 @@ class FqSimDevice : public FqDevice {
       }
     }
   }
+  /* the sources' flag words (fq_device.h): written by other processes through the shared-memory "peer" mapping */
+  static bool wait_sources(const unsigned long long* flags, unsigned long long expect, uint32_t n_src, unsigned long long* counters) {
+    if (!flags) return true;
+    for (uint32_t s2 = 0; s2 < n_src; s2++) {
+      const volatile unsigned long long* f = flags + s2;
+      for (long spins = 0; __atomic_load_n(f, __ATOMIC_ACQUIRE) < expect; spins++) {
+        if (spins > 200000000L) { counters[2] = 1; return false; }
+        if ((spins & 1023) == 1023) usleep(50);
+      }
+    }
+    return true;
+  }
   void shard_insert_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
-                          unsigned long long mask, unsigned long long* counters, bool) override {
+                          unsigned long long mask, unsigned long long* counters, bool, const unsigned long long* flags, unsigned long long expect) override {
     n_launch_++;
+    if (!wait_sources(flags, expect, n_src, counters)) return;
     each_slot(regions, n_src, region_bytes, nblocks, stride, units, counters, [&](const FqRouteSlot* sl) {
       unsigned long long i = sl->hash & mask, probes = 0;
       for (;; i = (i + 1) & mask) {
@@ -309,8 +322,9 @@ class FqSimDevice : public FqDevice {
     });
   }
   void shard_claim_slots(const uint8_t* regions, uint32_t n_src, size_t region_bytes, uint32_t nblocks, uint64_t stride, uint32_t units, FqSlot* slots,
-                         unsigned long long mask, unsigned long long* counters, bool) override {
+                         unsigned long long mask, unsigned long long* counters, bool, const unsigned long long* flags, unsigned long long expect) override {
     n_launch_++;
+    if (!wait_sources(flags, expect, n_src, counters)) return;
     each_slot(regions, n_src, region_bytes, nblocks, stride, units, counters, [&](const FqRouteSlot* sl) {
       unsigned long long i = sl->hash & mask, probes = 0;
       for (;; i = (i + 1) & mask) {
