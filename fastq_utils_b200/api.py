@@ -114,6 +114,8 @@ def bind(L):
     L.fqg_route_chunks.argtypes = [vp, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
     L.fqg_route_blocks.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     L.fqg_side_mark.argtypes = [vp]
+    L.fqg_route_region_bytes.argtypes = [ctypes.c_uint32, u64, ctypes.c_uint32]
+    L.fqg_route_region_bytes.restype = sz
     L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.fqg_side_copy.argtypes = [vp, vp, vp, sz]
     L.fqg_side_sync.argtypes = [vp]
@@ -393,7 +395,7 @@ class FastqInfo:
 
 def route_region_bytes(nblocks, stride, units):
     """bytes of one routing region (include/fastq_gpu.h: fqg_route_region_bytes)"""
-    return 16 + ((nblocks * 4 + 15) & ~15) + nblocks * stride * (16 + 16 * units)
+    return int(lib().fqg_route_region_bytes(nblocks, stride, units))
 
 
 def feed_chunk_bytes():

@@ -185,6 +185,7 @@ extern "C" int fqg_route_blocks(fqg_ctx* c, uint32_t* nblocks) {
   if (!c || !nblocks) return FQG_ERR_USAGE;
   FQG_GUARD(c, *nblocks = c->dev->lanes_max_blocks())
 }
+extern "C" size_t fqg_route_region_bytes(uint32_t nblocks, uint64_t stride, uint32_t name_units) { return fq_route_region_bytes(nblocks, stride, name_units); }
 extern "C" int fqg_side_mark(fqg_ctx* c) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->dev->side_mark())

@@ -212,9 +212,7 @@ int fqg_names_new(fqg_ctx* ctx, int file, uint64_t* n_new);
  * (padded to 16 bytes), then nblocks stretches of `stride` slots.  A count above `stride` says a stretch overflowed (the surplus is
  * dropped), flag 1 that a name was longer than its slot: the owner reports either and the caller repeats the job through the
  * exact path.  nblocks = 0: the source had nothing in this round. */
-static inline size_t fqg_route_region_bytes(uint32_t nblocks, uint64_t stride, uint32_t name_units) {
-  return 16u + (((size_t)nblocks * 4u + 15u) & ~(size_t)15u) + (size_t)nblocks * stride * (16u + 16u * (size_t)name_units);
-}
+size_t fqg_route_region_bytes(uint32_t nblocks, uint64_t stride, uint32_t name_units);
 /* (1) The clean-data pass writes the names itself, from shared memory, while it validates: chunk n of `file` (counting the chunks the
  * pass accepted) goes to region_ptrs[o] + (n % depth) * region_bytes for owner o, laid out for fqg_route_blocks() writers of `stride`
  * slots.  No name descriptors, no arena, no pack kernel on this path.  fqg_route_chunks says how many chunks are complete in their
