@@ -75,7 +75,7 @@ extern "C" uint64_t fqg_launch_count(const fqg_ctx* c) { return c ? c->dev->laun
 extern "C" double fqg_device_ms(const fqg_ctx* c) { return c ? c->ms : 0.0; }
 
 extern "C" int fqg_index_records(fqg_ctx* c, const void* host_bytes, size_t n, uint64_t* starts, size_t cap, uint64_t* n_records) {
-  if (!c || (!host_bytes && n) || !n_records) return FQG_ERR_USAGE;
+  if (!c || (!host_bytes && n) || !n_records || (cap && !starts)) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->eng->index_records(host_bytes, n, starts, cap, n_records))
 }
 

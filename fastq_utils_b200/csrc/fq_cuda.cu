@@ -590,6 +590,12 @@ __device__ __forceinline__ bool names_equal(const uint8_t* a, const uint8_t* b, 
   }
   return true;
 }
+/* two names of equal length n in arenas: runs of 16-byte units, zero padded, 16-byte aligned — equal names are equal unit by unit */
+__device__ __forceinline__ bool names_equal16(const uint8_t* a, const uint8_t* b, uint32_t n) {
+  const uint4* ua = (const uint4*)a; const uint4* ub = (const uint4*)b;
+  for (uint32_t u = 0; 16u * u < n; u++) { const uint4 x = ua[u], y = ub[u]; if ((x.x ^ y.x) | (x.y ^ y.y) | (x.z ^ y.z) | (x.w ^ y.w)) return false; }
+  return true;
+}
 __device__ __forceinline__ const uint8_t* dir_name(const FqDirEntry* dir, uint32_t nd, unsigned long long g, uint32_t* len) {
   uint32_t lo = 0, hi = nd;
   while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (dir[mid].g0 <= g) lo = mid; else hi = mid; }
@@ -635,7 +641,7 @@ fq_index_insert_kernel(const TableParams P) {
        * them — the one the failed claim returned — tells whether this is our name.  Another name with the same 64-bit hash
        * (the reference's hashit collision, src/hash.c:38-45 walks on to the next object): so do we, to the next slot. */
       uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, cur_idx, &ol);
-      if (!(ol == nm.len && names_equal(on, P.data + nm.off, nm.len))) { atomicAdd(P.counters + 4, 1ull); continue; } /* [4]: diagnostics only */
+      if (!(ol == nm.len && names_equal16(on, P.data + nm.off, nm.len))) { atomicAdd(P.counters + 4, 1ull); continue; } /* [4]: diagnostics only */
       /* keep the smallest record index; min over all arrivals of max(old, g) = 2nd smallest of the group = the reference's duplicate */
       unsigned long long old = atomicMin(&s->idx1, g);
       unsigned long long later = old > g ? old : g;
@@ -662,7 +668,7 @@ fq_mate_claim_kernel(const TableParams P) {
       if (cur == FQ_HASH_EMPTY) { unpaired = g; break; }
       if (cur != nm.hash) continue;
       uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, s->idx1, &ol);
-      if (!(ol == nm.len && names_equal(on, P.data + nm.off, nm.len))) continue; /* another name with this hash: the lookup walks on */
+      if (!(ol == nm.len && names_equal16(on, P.data + nm.off, nm.len))) continue; /* another name with this hash: the lookup walks on */
       unsigned long long old = atomicMin(&P.slots[i].claim2, g);
       if (old == FQ_IDX_NONE) claimed++;           /* first claim = the reference's delete */
       else unpaired = old > g ? old : g;           /* the entry was already deleted when the later one arrives */
@@ -1127,6 +1133,8 @@ class FqCudaDevice : public FqDevice {
     return p;
   }
   void release(void* p) override { if (p) cudaFreeAsync(p, st_); }
+  void* host_alloc(size_t n) override { void* p = nullptr; FQ_CUDA_CHECK(cudaSetDevice(dev_)); FQ_CUDA_CHECK(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault)); return p; }
+  void host_release(void* p) override { if (p) cudaFreeHost(p); }
   void upload(void* d, const void* s, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st_)); }
   void download(void* d, const void* s, size_t n) override {
     if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st_));

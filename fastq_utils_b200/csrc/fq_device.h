@@ -9,6 +9,8 @@
 #define FQ_DEVICE_H
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <new>
 #include <stdexcept>
 #include "fq_types.h"
 
@@ -114,6 +116,9 @@ class FqDevice {
    * and the shard kernels): clearing the table then runs beside the first chunk's pass */
   virtual void fill_index(void* dst, int byte, size_t n) { fill(dst, byte, n); }
   virtual void sync() = 0;
+  /* page-locked host memory for pieces on their way to the device (a streaming caller's double buffer) */
+  virtual void* host_alloc(size_t n) { void* p = malloc(n ? n : 1); if (!p) throw std::bad_alloc(); return p; }
+  virtual void host_release(void* p) { free(p); }
   /* wait for the copies and kernels queued on the main stream only (the index kernels on their own stream keep running) */
   virtual void sync_main() { sync(); }
   /* K1: exclusive end offsets of all lines of data[0,n) in order; a last line without LF counts when virtual_end.

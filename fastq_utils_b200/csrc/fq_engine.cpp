@@ -1229,6 +1229,8 @@ void FqEngine::names_count(int file, uint32_t world, uint64_t* counts, uint64_t*
   std::vector<unsigned long long> h(2 * world);
   dev_->download(h.data(), d, h.size() * sizeof(unsigned long long));
   for (uint32_t o = 0; o < world; o++) { counts[o] = h[2 * o]; bytes[o] = h[2 * o + 1]; }
+  for (uint32_t o = 0; o < world; o++)
+    if (bytes[o] >= (1ull << 32)) { dev_->release(d); throw std::runtime_error("fqg_names_count: more than 4 GiB of read-name bytes for one owner (the packed offsets are 32-bit): use more ranks or the pipelined routing"); }
   dev_->release(d);
 }
 

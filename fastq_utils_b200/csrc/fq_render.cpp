@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "fq_engine.h"
 
@@ -204,6 +207,64 @@ void feed_all(FqEngine& eng, int file, const void* p, size_t n, size_t chunk) {
   }
 }
 
+/* where the inflated bytes of the file operands come from */
+struct Source {
+  virtual ~Source() {}
+  virtual bool open(int file, const char* name) = 0; /* false: the reference's "Unable to open" (src/fastq.c:651-655) */
+  virtual void feed(FqEngine& eng, int file) = 0;    /* everything of an opened file; the last piece is marked */
+};
+struct MemSource : Source {
+  const void* p[2]; size_t n[2]; size_t chunk;
+  bool open(int file, const char*) override { return n[file] != (size_t)-1; }
+  void feed(FqEngine& eng, int file) override { feed_all(eng, file, p[file], n[file], chunk); }
+};
+/* The caller's reader (zlib in the CLI) fills one pinned buffer on a helper thread while the engine takes the other: inflating,
+ * the copy to the device and the kernels overlap, and the host never holds more than two pieces of the file (the reference's own
+ * loop is gzbuffer + gzgets, src/fastq.c:631-661: it holds one line). */
+struct StreamSource : Source {
+  const fqg_stream_io* io; void* h[2] = {nullptr, nullptr}; size_t piece;
+  bool open(int file, const char* name) override { h[file] = io->open ? io->open(io->user, name) : nullptr; return h[file] != nullptr; }
+  ~StreamSource() override { for (int f = 0; f < 2; f++) if (h[f] && io->close) io->close(io->user, h[f]); }
+  void feed(FqEngine& eng, int file) override {
+    FqDevice* dev = eng.device();
+    uint8_t* buf[2] = {(uint8_t*)dev->host_alloc(piece), (uint8_t*)dev->host_alloc(piece)};
+    struct Slot { long n = 0; bool full = false; } slot[2];
+    std::mutex mu; std::condition_variable cv; bool failed = false, quit = false;
+    std::thread reader([&] {
+      for (int k = 0;; k ^= 1) {
+        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !slot[k].full || quit; }); if (quit) return; }
+        size_t got = 0; long r = 1;
+        while (got < piece && (r = io->read(io->user, h[file], buf[k] + got, piece - got)) > 0) got += (size_t)r; /* whole pieces: fewer, larger chunks */
+        { std::lock_guard<std::mutex> lk(mu); slot[k].n = r < 0 ? -1 : (long)got; slot[k].full = true; }
+        cv.notify_all();
+        if (r <= 0) return; /* the end of the stream (or an error): this piece is the last one */
+      }
+    });
+    try {
+      for (int k = 0;; k ^= 1) {
+        long n;
+        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return slot[k].full; }); n = slot[k].n; }
+        if (n < 0) { failed = true; break; }
+        const bool last = (size_t)n < piece;
+        eng.feed_host(file, buf[k], (size_t)n, last);
+        { std::lock_guard<std::mutex> lk(mu); slot[k].full = false; }
+        cv.notify_all();
+        if (last) break;
+      }
+    } catch (...) {
+      { std::lock_guard<std::mutex> lk(mu); quit = true; slot[0].full = slot[1].full = false; }
+      cv.notify_all(); reader.join(); dev->host_release(buf[0]); dev->host_release(buf[1]);
+      throw;
+    }
+    { std::lock_guard<std::mutex> lk(mu); quit = true; }
+    cv.notify_all(); reader.join();
+    dev->host_release(buf[0]); dev->host_release(buf[1]);
+    if (failed) throw std::runtime_error("fqg_fastq_info_stream: the read callback reported an error");
+  }
+};
+
+int fastq_info_run(int argc, const char** argv_in, Source& src, int device, fqg_transcript* tr);
+
 }  // namespace
 
 extern "C" int fqg_render(const fqg_report* rep, const fqg_render_opts* opts, fqg_transcript* tr) {
@@ -231,8 +292,19 @@ FqDevice* fq_default_device(int ordinal); /* fq_abi.cpp (CUDA) or the test stand
 
 extern "C" int fqg_fastq_info_mem(int argc, const char** argv_in, const void* f1, size_t n1, const void* f2, size_t n2,
                                   int device, size_t chunk_bytes, fqg_transcript* tr) {
+  if (!tr || argc < 1 || !argv_in) return FQG_ERR_USAGE;
+  MemSource src; src.p[0] = f1; src.n[0] = n1; src.p[1] = f2; src.n[1] = n2; src.chunk = chunk_bytes;
+  return fastq_info_run(argc, argv_in, src, device, tr);
+}
+extern "C" int fqg_fastq_info_stream(int argc, const char** argv_in, const fqg_stream_io* io, int device, size_t piece_bytes, fqg_transcript* tr) {
+  if (!tr || argc < 1 || !argv_in || !io || !io->read) return FQG_ERR_USAGE;
+  StreamSource src; src.io = io; src.piece = piece_bytes ? piece_bytes : ((size_t)64 << 20);
+  return fastq_info_run(argc, argv_in, src, device, tr);
+}
+
+namespace {
+int fastq_info_run(int argc, const char** argv_in, Source& src, int device, fqg_transcript* tr) {
   Text t;
-  const size_t UNOPENABLE = (size_t)-1;
   bool is_paired = false, is_interleaved = false, is_sorted = false, empty_ok = false, no_enc_ok = false, skip_names = false;
   int nopt = 0;
   t.e("fastq_utils %s\n", "0.25.3");
@@ -288,27 +360,27 @@ extern "C" int fqg_fastq_info_mem(int argc, const char** argv_in, const void* f1
   bool second_file = false, f2_unopenable = false;
   if (is_interleaved) {
     cfg.mode = FQG_MODE_INTERLEAVED; t.e("Paired-end interleaved\n");
-    if (n1 == UNOPENABLE) return unopenable(a1);
+    if (!src.open(0, a1)) return unopenable(a1);
   } else if (is_paired && is_sorted && skip_names) {
     cfg.mode = FQG_MODE_SORTED_PAIR; second_file = true;
     t.e("-s option used: assuming that reads have the same ordering in both files\n");
-    if (n1 == UNOPENABLE) return unopenable(a1);
-    if (n2 == UNOPENABLE) return unopenable(a2);
+    if (!src.open(0, a1)) return unopenable(a1);
+    if (!src.open(1, a2)) return unopenable(a2);
   } else if (!is_paired && skip_names) {
     cfg.mode = FQG_MODE_SINGLE; t.e("Skipping check for duplicated read names\n");
-    if (n1 == UNOPENABLE) return unopenable(a1);
+    if (!src.open(0, a1)) return unopenable(a1);
   } else {
     second_file = is_paired && !is_sorted;
     cfg.mode = second_file ? FQG_MODE_INDEX_PAIR : FQG_MODE_INDEX;
     if (is_paired) cfg.flags |= FQG_FLAG_PAIRED_NAMES;
-    if (n1 == UNOPENABLE) return unopenable(a1);
+    if (!src.open(0, a1)) return unopenable(a1);
   }
   fqg_report rep;
   try {
     FqDevice* dev = fq_default_device(device);
     {
       FqEngine eng(cfg, dev);
-      feed_all(eng, 0, f1, n1, chunk_bytes);
+      src.feed(eng, 0);
       if (second_file) {
         bool open2 = true;
         if (cfg.mode == FQG_MODE_INDEX_PAIR) {
@@ -316,9 +388,9 @@ extern "C" int fqg_fastq_info_mem(int argc, const char** argv_in, const void* f1
           fqg_report r1; eng.finish(&r1);
           bool stop_after_1 = (r1.error.code != FQG_OK && r1.error.file == 0) || r1.n_index_entries == 0;
           if (stop_after_1) open2 = false;
-          else if (n2 == UNOPENABLE) { open2 = false; f2_unopenable = true; }
+          else if (!src.open(1, a2)) { open2 = false; f2_unopenable = true; }
         }
-        if (open2) feed_all(eng, 1, f2, n2, chunk_bytes);
+        if (open2) src.feed(eng, 1);
       }
       eng.finish(&rep);
     }
@@ -334,6 +406,7 @@ extern "C" int fqg_fastq_info_mem(int argc, const char** argv_in, const void* f1
   to_transcript(t, tr);
   return 0;
 }
+}  // namespace
 
 /* main() of the reader-style tools on an inflated stream: src/fastq_num_reads.c:32-50, src/fastq_not_empty.c:32-47.  Both are
  * the bare fastq_read_next_entry loop (src/fastq.c:237-261): records are delimited, a NUL-led header line ends the file quietly,

@@ -445,6 +445,16 @@ class ShardedFastqInfo:
         else:
             ok = False
         if not all(self._gather(ok)):
+            # some rank could not allocate or map: nobody keeps half an arena (the rounds use all-to-all exchanges from now on)
+            for sidx in range(W):
+                if sidx != r and peers[sidx] != ptr:
+                    try:
+                        self.ctx.ipc_close(peers[sidx])
+                    except RuntimeError:
+                        pass
+            self._gather(0)  # nobody maps this rank's memory any more
+            if ptr:
+                self.shard.ipc_free(ptr)
             self._arena_failed = True
             return False
         self._arena, self._peer = (ptr, size), peers

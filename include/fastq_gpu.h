@@ -106,9 +106,12 @@ void fqg_destroy(fqg_ctx* ctx);
 /* Hand `n` decompressed bytes of file `file` (0 or 1) to the device.  `last` marks the end of that file.
  * INDEX_PAIR: file 1 may only be fed after file 0 was fed with last=1 (the reference's order). */
 int fqg_feed(fqg_ctx* ctx, int file, const void* host_bytes, size_t n, int last);
-/* Same, for bytes already in device memory; the buffer is borrowed until fqg_reset / fqg_destroy and must be
- * followed by at least 64 readable bytes.  A pointer that is not 16-byte aligned is accepted but costs one device copy
- * of the piece (the kernels read 16 bytes at a time). */
+/* Same, for bytes already in device memory.  The buffer must be followed by at least 64 readable bytes, and — the kernels read 16 bytes
+ * at a time — the bytes between the 16-byte boundary below `device_bytes` and the pointer must be readable too (true inside any
+ * allocation; a caller that hands over the very first byte of a mapped range aligns it).  It is borrowed until fqg_reset /
+ * fqg_destroy, or only for the duration of the call with FQG_FLAG_BORROW_FOR_CALL.  Device memory the job keeps: the read names (a
+ * copy of each, like the reference's new_indexentry) and the index; chunks whose records raised no event are dropped as the job goes,
+ * so files far larger than the device's memory stream through (single-file and default two-file modes). */
 int fqg_feed_device(fqg_ctx* ctx, int file, const void* device_bytes, size_t n, int last);
 int fqg_finish(fqg_ctx* ctx, fqg_report* out);
 /* forget all input and results, keep the device workspace (bench loops) */
@@ -138,6 +141,20 @@ void fqg_transcript_free(fqg_transcript* t);
  * be opened" (src/fastq.c:651-655).  chunk_bytes > 0 feeds the streams in pieces of that size. */
 int fqg_fastq_info_mem(int argc, const char** argv, const void* f1, size_t n1, const void* f2, size_t n2,
                        int device, size_t chunk_bytes, fqg_transcript* t);
+
+/* The same for streams the caller reads piece by piece (the CLI: zlib inflation of files of any size, `-` for standard input).  The
+ * library decides which words of argv are file operands exactly as the reference's main() does (its getopt quirks included) and calls
+ * `open` for those, in the reference's order — file 2 of the default two-file mode only after file 1 was indexed without error.  `read`
+ * delivers the next inflated bytes (0: end of the stream, < 0: error) and is called from a helper thread of the library, one call at a
+ * time per handle: while it fills one page-locked piece, the other is copied to the device and validated.  Host memory: two pieces of
+ * piece_bytes (0 = 64 MiB); device memory: the read names and the index, whatever the size of the files. */
+typedef struct {
+  void* user;
+  void* (*open)(void* user, const char* name);   /* NULL result: "Unable to open <name>" */
+  long (*read)(void* user, void* handle, void* buf, size_t cap);
+  void (*close)(void* user, void* handle);
+} fqg_stream_io;
+int fqg_fastq_info_stream(int argc, const char** argv, const fqg_stream_io* io, int device, size_t piece_bytes, fqg_transcript* t);
 
 /* The reader-style tools on an already-inflated stream: argv[0] names the tool,
  *   "fastq_num_reads"  src/fastq_num_reads.c:32-50   prints the number of entries fastq_read_next_entry delivers

@@ -207,3 +207,51 @@ def ref_reader_tool(tool, data, name="a.fq"):
             fh.write(data)
         p = subprocess.run([os.path.join(ROOT, "oracle", "_ref", tool), name], cwd=d, capture_output=True)
     return p.returncode, p.stdout.decode("latin-1"), p.stderr.decode("latin-1")
+
+
+# ---------------------------------------------------------------------------------------------- streamed entry point
+class _StreamIO(ctypes.Structure):
+    _fields_ = [("user", ctypes.c_void_p),
+                ("open", ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p)),
+                ("read", ctypes.CFUNCTYPE(ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)),
+                ("close", ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p))]
+
+
+def fqg_run_stream(argv, files, piece=0, kind="gpu", max_read=None):
+    """fastq_info through fqg_fastq_info_stream: `files` maps operand names to inflated bytes (a missing name cannot be opened); the
+    library asks for the operands it wants → (rc, stdout, stderr, names opened in order)."""
+    lib = fqg_lib(kind)
+    lib.fqg_fastq_info_stream.restype = ctypes.c_int
+    lib.fqg_fastq_info_stream.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_StreamIO), ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(_Transcript)]
+    opened, state = [], {}
+
+    def _open(user, name):
+        nm = name.decode("latin-1")
+        opened.append(nm)
+        if nm not in files:
+            return None
+        h = len(state) + 1
+        state[h] = [files[nm], 0]
+        return h
+
+    def _read(user, h, buf, cap):
+        data, pos = state[h]
+        k = min(cap, len(data) - pos, max_read or cap)
+        ctypes.memmove(buf, data[pos:pos + k], k)
+        state[h][1] = pos + k
+        return k
+
+    def _close(user, h):
+        state.pop(h, None)
+    io = _StreamIO(None, _StreamIO._fields_[1][1](_open), _StreamIO._fields_[2][1](_read), _StreamIO._fields_[3][1](_close))
+    full = [b"fastq_info"] + [a.encode("latin-1") for a in argv]
+    arr = (ctypes.c_char_p * (len(full) + 1))(*full, None)
+    tr = _Transcript()
+    st = lib.fqg_fastq_info_stream(len(full), arr, ctypes.byref(io), 0, piece, ctypes.byref(tr))
+    if st != 0:
+        raise RuntimeError(f"fqg_fastq_info_stream failed with status {st}")
+    out = ctypes.string_at(tr.out, tr.out_len).decode("latin-1")
+    err = ctypes.string_at(tr.err, tr.err_len).decode("latin-1")
+    rc = tr.rc
+    lib.fqg_transcript_free(ctypes.byref(tr))
+    return rc, out, err, opened
