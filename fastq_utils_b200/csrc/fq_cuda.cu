@@ -1090,6 +1090,9 @@ __global__ void fq_stats_fold_scalars_kernel(const FoldParams P) {
   }
 }
 
+struct WordsParams { uint32_t* dst; uint32_t n; uint32_t w[32]; };
+__global__ void fq_set_words_kernel(const WordsParams P) { if (threadIdx.x < P.n) P.dst[threadIdx.x] = P.w[threadIdx.x]; }
+
 /* ------------------------------------------------------------------------------------------------ the device */
 class FqCudaDevice : public FqDevice {
  public:
@@ -1121,7 +1124,7 @@ class FqCudaDevice : public FqDevice {
     for (auto& p : pending_) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto& d : deferred_) cudaEventDestroy(d.ready);
     for (auto e : free_ev_) cudaEventDestroy(e);
-    cudaFree(tile_state_); if (stage_) cudaFree(stage_);
+    cudaFree(tile_state_); if (stage_) cudaFree(stage_); if (small_pinned_) cudaFreeHost(small_pinned_);
     cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_); cudaEventDestroy(ev_pre_); cudaEventDestroy(ev_side_);
     cudaStreamDestroy(st_); cudaStreamDestroy(st2_);
   }
@@ -1137,8 +1140,21 @@ class FqCudaDevice : public FqDevice {
   void host_release(void* p) override { if (p) cudaFreeHost(p); }
   void upload(void* d, const void* s, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st_)); }
   void download(void* d, const void* s, size_t n) override {
+    if (n && n <= sizeof small_) { /* result words: through page-locked memory (no staging inside the driver) */
+      if (!small_pinned_) FQ_CUDA_CHECK(cudaHostAlloc(&small_pinned_, sizeof small_, cudaHostAllocDefault));
+      FQ_CUDA_CHECK(cudaMemcpyAsync(small_pinned_, s, n, cudaMemcpyDeviceToHost, st_));
+      FQ_CUDA_CHECK(cudaStreamSynchronize(st_));
+      memcpy(d, small_pinned_, n);
+      return;
+    }
     if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st_));
     FQ_CUDA_CHECK(cudaStreamSynchronize(st_));
+  }
+  void set_words(uint32_t* d, const uint32_t* words, uint32_t nwords) override { /* (a launch instead of a copy out of pageable memory) */
+    WordsParams P; P.dst = d; P.n = nwords > 32 ? 32 : nwords;
+    for (uint32_t i = 0; i < P.n; i++) P.w[i] = words[i];
+    fq_set_words_kernel<<<1, 32, 0, st_>>>(P);
+    launched();
   }
   void copy(void* d, const void* s, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st_)); }
   void fill(void* d, int b, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemsetAsync(d, b, n, st_)); }
@@ -1515,6 +1531,7 @@ class FqCudaDevice : public FqDevice {
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;
   LanesStage* stage_ = nullptr;
+  uint8_t small_[4096]; void* small_pinned_ = nullptr;
   unsigned long long n_launch_ = 0;
 };
 

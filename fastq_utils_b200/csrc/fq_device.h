@@ -112,6 +112,8 @@ class FqDevice {
   virtual void download(void* dst, const void* src, size_t n) = 0; /* synchronises */
   virtual void copy(void* dst, const void* src, size_t n) = 0;
   virtual void fill(void* dst, int byte, size_t n) = 0;
+  /* up to 32 words of device memory set from host values, ordered on the main stream */
+  virtual void set_words(uint32_t* dst, const uint32_t* words, uint32_t nwords) { upload(dst, words, nwords * sizeof(uint32_t)); sync_main(); }
   /* fill ordered with the index kernels instead of the main stream's copies and passes (the stream of index_insert, mate_claim
    * and the shard kernels): clearing the table then runs beside the first chunk's pass */
   virtual void fill_index(void* dst, int byte, size_t n) { fill(dst, byte, n); }

@@ -78,7 +78,7 @@ void FqEngine::reset() {
   { const char* e = getenv("FQG_ROUTE_AFTER"); hook_after_ = e && *e && *e != '0'; } /* A/B: the chunk hook fires when the chunk is done (the routing kernels then have the GPU to themselves) instead of beside the next pass */
   { const char* e = getenv("FQG_TEST_WEAK_HASH"); if (e && *e && *e != '0') seed_ = FQ_SEED_WEAK; }                 /* test hook: 12-bit name hashes, so that equal hashes of different names are common */
   for (auto& m : mem_stats) m = 0;
-  open_ = streaming_; add_depth_ = 0;
+  open_ = streaming_; add_depth_ = 0; open_dirty_ = false;
   /* results */
   dev_->fill(key_, 0xFF, sizeof(unsigned long long));
   dev_->fill(counters_, 0, kCounters * sizeof(unsigned long long));
@@ -293,7 +293,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   if (lanes_ok_ && !skip_lanes && a.cx.space != FQ_SPACE_COLOR) {
     uint32_t linit[FQ_LANES_OUT_WORDS]; memset(linit, 0, sizeof linit);
     linit[2] = kNone32; linit[5] = kNone32; linit[6] = kNone32; linit[8] = kNone32;
-    dev_->upload(tile_out_, linit, sizeof linit);
+    dev_->set_words(tile_out_, linit, FQ_LANES_OUT_WORDS);
     /* room for the names of the chunk (the per-line mode of the pass copies them out of the window itself): what the chunks before
      * it needed per byte and a quarter more; a pass that runs out of room hands the chunk on like any other anomaly */
     uint8_t* arena = nullptr; uint64_t arena_units = 0;
@@ -311,6 +311,10 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
       a.route_world = F.route_world; a.route_stride = F.route_stride; a.route_units = F.route_units;
       for (uint32_t o = 0; o < F.route_world; o++) a.route_region[o] = F.route_region[o] + (size_t)(F.route_chunks % F.route_depth) * F.route_bytes;
     }
+    /* While every chunk so far is final and no bytes wait for the rest of their record, an accepted clean-data pass is final too: its
+     * statistics go straight into the main set (a chunk the pass hands on leaves no trace in either set). */
+    const bool direct = open_ && add_depth_ == 1 && F.pend_n == 0 && !open_dirty_ && !getenv("FQG_NO_DIRECT");
+    if (direct) { a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; }
     bool self_judged = false;
     if (dev_->lanes_pass(a, &self_judged)) {
       if (hook_ && !hook_after_) { /* the pass is running: the caller routes the names of the chunks before this one beside it */
@@ -329,6 +333,8 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
       if (accepted) {
         if (!self_judged) dev_->lanes_commit(a, false);
         path_counts[0]++; fused_lanes_ = true;
+        if (!direct) open_dirty_ = true;
+        fused_direct_ = direct;
         B.nlines = o[0]; B.index_partial = self_judged; B.index_from = self_judged ? o[26] : 0; B.index_virtual_end = last;
         B.tail_from = o[0] > 8 ? o[0] - 8 : 0; B.tail_n = o[0] - B.tail_from;
         for (uint32_t i = 0; i < B.tail_n; i++) B.tail_ends[i] = o[16 + i];
@@ -346,6 +352,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
     } else { dev_->sync(); if (routed) F.route_broken = true; }
     if (arena) dev_->release(arena);
     a.arena = nullptr; a.arena_units = 0; a.route_world = 0;
+    a.stats = f_[target].stats_open; a.hist = f_[target].hist_open; a.stats_range = f_[file].stats_open; /* the per-record kernels count into the open set */
     if (routed) { /* the per-record kernels deliver name descriptors: the caller packs them (fqg_names_pack_slots) */
       names = (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName));
       a.names = names;
@@ -358,7 +365,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   }
   uint32_t init[6] = {0, 0, kNone32, 0, 0, 0};
   dev_->upload(tile_out_, init, sizeof init);
-  fused_lanes_ = false;
+  fused_lanes_ = false; fused_direct_ = false; open_dirty_ = true;
   bool launched = dev_->tile_pass(a);
   uint32_t out5[6] = {0, 0, kNone32, 0, 0, 0};
   if (launched) dev_->download(out5, tile_out_, sizeof out5); else dev_->sync();
@@ -467,6 +474,7 @@ void FqEngine::add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool o
         uint32_t end = line_end_at(F.bufs[b], j - 1);
         s.span = end - pos; pos = end;
         s.g0 = F.nrec; F.nrec += nrec; s.names = fused_names; s.lanes = fused_lanes_;
+        if (fused_lanes_ && fused_direct_) { s.settled = true; mem_stats[3] += nrec; } /* (its statistics are in the main set already) */
         s.arena = fused_arena_; fused_arena_ = nullptr; /* the per-line mode of the clean-data pass put the names there itself */
         F.segs.push_back(s);
         if (s.arena) set_dir(file, F.segs.size() - 1); else gather_segment(file, F.segs.size() - 1, nrec);
@@ -616,8 +624,8 @@ void FqEngine::try_settle(int file) {
     unsigned long long k = 0; dev_->download(&k, key_, sizeof k);
     if (k != FQ_KEY_NONE || f_[0].limit != ~0ull || f_[1].limit != ~0ull) { open_ = false; return; }
   }
-  if (F.n_settled < F.segs.size()) fold_open();
-  for (size_t si = F.n_settled; si < F.segs.size(); si++) { F.segs[si].settled = true; mem_stats[3] += F.segs[si].nrec; }
+  if (open_dirty_) { fold_open(); open_dirty_ = false; }
+  for (size_t si = F.n_settled; si < F.segs.size(); si++) if (!F.segs[si].settled) { F.segs[si].settled = true; mem_stats[3] += F.segs[si].nrec; }
   F.n_settled = F.segs.size();
   for (auto& B : F.bufs) release_buffer(B);
 }
@@ -746,6 +754,7 @@ void FqEngine::launch_segment(int file, size_t si) {
   int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
   a.stats = f_[target].stats_open; a.hist = f_[target].hist_open; a.stats_range = f_[file].stats_open;
   a.key = key_; a.names = s.names;
+  open_dirty_ = true;
   dev_->records(a);
   gather_segment(file, si, nrec);
   launch_names(file, si, nrec);

@@ -140,9 +140,11 @@ class FqEngine {
    * its names are in the arena, its bytes are released.  open_ turns false with the first chunk that cannot be settled; from there
    * on everything is kept and counted in the open set, which reprocess() can clear and recount. */
   bool streaming_ = false, open_ = false;
+  bool open_dirty_ = false;                 /* a kernel has counted into the open set since the last fold */
   int add_depth_ = 0;
   uint8_t* fused_arena_ = nullptr;          /* ... and it put the names of the chunk into this block */
   bool names_cap_full_ = false;             /* size the name descriptors of a chunk by the line bound, not by the first record's lengths */
+  bool fused_direct_ = false;               /* ... and counted into the main set directly */
   bool fused_lanes_ = false;                /* the fused pass that validated the chunk being added was the clean-data pass */
   void try_settle(int file);
   void release_buffer(FqBuffer& B);

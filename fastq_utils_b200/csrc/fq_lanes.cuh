@@ -531,9 +531,19 @@ fq_lanes_kernel(const LanesParams P) {
          * gets a second group gets the light ones (measured: 0.89 ms against 0.94 for sequence-first, 0.96 for a shared work counter
          * with sequence lines split in halves — extra instructions cost more than balance gains) */
         const uint32_t GQ = (nQ + 31) >> 5, GS = (nS + 31) >> 5, GH = (nH + 31) >> 5;
-        for (uint32_t g = warp; g < GQ + GS + GH; g += LN_WARPS) {
-          const uint32_t cls = g < GQ ? 3u : g < GQ + GS ? 1u : 0u; /* uniform over the warp */
-          const uint32_t i = 32 * (cls == 3u ? g : cls == 1u ? g - GQ : g - GQ - GS) + lane;
+        const bool snake = (P.tune & 2u) == 0u;
+        for (uint32_t rr = 0;; rr++) {
+          /* groups in the order of their cost — sequence lines (the alphabet), header lines (walk, hash, name copy, record rules), quality
+           * lines — dealt to the warps back and forth, so that the warp with a heavy first group gets a light second one */
+          uint32_t g;
+          if (snake) g = (rr & 1u) ? LN_WARPS * rr + (LN_WARPS - 1u - warp) : LN_WARPS * rr + warp;
+          else g = LN_WARPS * rr + warp;
+          if (LN_WARPS * rr >= GQ + GS + GH) break;
+          if (g >= GQ + GS + GH) continue;
+          uint32_t cls, gi;
+          if (snake) { cls = g < GS ? 1u : g < GS + GH ? 0u : 3u; gi = cls == 1u ? g : cls == 0u ? g - GS : g - GS - GH; }
+          else { cls = g < GQ ? 3u : g < GQ + GS ? 1u : 0u; gi = cls == 3u ? g : cls == 1u ? g - GQ : g - GQ - GS; } /* uniform over the warp */
+          const uint32_t i = 32 * gi + lane;
           const uint32_t n = cls == 1u ? nS : cls == 3u ? nQ : nH;
           const uint32_t k = (cls == 1u ? kS : cls == 3u ? kQ : kH) + 4 * i;
           if (cls != 0u) {
@@ -835,7 +845,8 @@ fq_lanes_post_kernel(const LanesPostParams P) {
     if (from + threadIdx.x < nlines) P.out[16 + threadIdx.x] = P.line_end[from + threadIdx.x];
   }
   const unsigned long long w = P.cx.weight;
-  for (uint32_t l = threadIdx.x; l < (uint32_t)LS_STAGE_HIST; l += blockDim.x) { const uint32_t v = P.stage->hist[l]; if (v) atomicAdd(P.hist + l, w * v); }
+  const uint32_t lmax = min(P.stage->rl_max, (uint32_t)LS_STAGE_HIST - 1u); /* (no bin above the longest read is set) */
+  for (uint32_t l = threadIdx.x; l <= lmax; l += blockDim.x) { const uint32_t v = P.stage->hist[l]; if (v) atomicAdd(P.hist + l, w * v); }
   if (threadIdx.x == 0) {
     const unsigned long long n = P.stage->nrec;
     if (n) {
