@@ -61,6 +61,7 @@ void FqEngine::free_file(FqFile& F) {
 
 FqEngine::~FqEngine() {
   dev_->sync();
+  if (pre_.valid) { try { lanes_discard(&pre_); } catch (...) {} }
   for (int f = 0; f < 2; f++) { free_file(f_[f]); dev_->release(f_[f].stats); dev_->release(f_[f].hist); dev_->release(f_[f].stats_open); dev_->release(f_[f].hist_open); }
   if (slots_) dev_->release(slots_);
   dev_->release(key_); dev_->release(counters_); dev_->release(scratch_); dev_->release(recout_); dev_->release(tile_out_);
@@ -70,6 +71,7 @@ FqEngine::~FqEngine() {
 /* forget input and results; the index keeps its allocation */
 void FqEngine::reset() {
   dev_->sync();
+  if (pre_.valid) { try { lanes_discard(&pre_); } catch (...) {} }
   for (int f = 0; f < 2; f++) free_file(f_[f]);
   for (auto& c : path_counts) c = 0;
   seed_ = 0; finished_ = false; total0_set_ = false; total0_ = 0; fused_ok_ = !(cfg_.flags & FQG_FLAG_TWO_PASS);
@@ -147,7 +149,9 @@ void FqEngine::feed_device(int file, const void* dptr, size_t n, bool last) {
     const uint32_t lead = (uint32_t)((uintptr_t)p & 15u);
     const bool whole_records = F.pend_n == 0; /* nothing carried over: the chunk starts at a record start */
     hook_fired_ = false;
+    next_.valid = whole_records && n > k; next_.file = file; next_.ptr = p + k; next_.remaining = n - k; next_.last = last;
     add_buffer(file, p - lead, (uint32_t)(k + lead), last && k == n, false, true, lead);
+    next_.valid = false;
     if (hook_ && !hook_fired_) hook_(hook_user_, file); /* the chunk did not take the clean-data pass: its hook call comes after it */
     p += k; n -= k;
     /* A record cut by the end of the chunk normally travels on as pending bytes and is finished in a bridge chunk.  The bytes are
@@ -262,66 +266,113 @@ bool FqEngine::presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip
 }
 
 /* K1+K2 fused over buffer b.  Returns false (nothing launched, or results discarded) when the two-pass path must be used. */
+/* Everything a fused pass over one chunk needs, and the launch of the clean-data pass when the chunk may take it.  Split from the
+ * collection of its results so that the pass of chunk k+1 can be launched as soon as the pass of chunk k has said where chunk k+1
+ * starts — before the host has done its bookkeeping for chunk k (segments, name kernels, settling), which then runs beside it. */
+void FqEngine::lanes_prepare(int file, uint8_t* data, uint32_t n, uint32_t lead, bool last, uint32_t j0, uint64_t g0_local, bool skip_lanes, LanesLaunch* L) {
+  FqFile& F = f_[file];
+  const int loop = loop_of(file);
+  *L = LanesLaunch();
+  L->valid = true; L->file = file; L->data = data; L->n = n; L->lead = lead; L->last = last; L->j0 = j0;
+  L->cap = n / 32 + 4096;
+  L->line_end = (uint32_t*)dev_->alloc((size_t)L->cap * sizeof(uint32_t) + kPad);
+  L->ncap = L->cap / 4 + 1;
+  /* (16 bytes per record: with the lengths of the file's first record known, room for a third more records than such records would
+   * fill the chunk with — a chunk with more hands itself on, see fq_lanes_post_kernel, and the next one asks for the full bound) */
+  if (lanes_ok_ && !names_cap_full_ && F.first_hdr_len && F.first_seq_len)
+    L->ncap = std::min<uint32_t>(L->ncap, (uint32_t)((double)n / (0.75 * (F.first_hdr_len + 2.0 * F.first_seq_len + 2))) + 4096);
+  L->routed = F.route_world > 0 && lanes_ok_ && !skip_lanes && f_[loop == FQ_LOOP_MATE ? 0 : file].sniff_color != FQ_SPACE_COLOR; /* the pass routes the names itself: no descriptors, no arena */
+  L->names = (loop != FQ_LOOP_SINGLE && loop != FQ_LOOP_READER && !L->routed) ? (FqName*)dev_->alloc((size_t)L->ncap * sizeof(FqName)) : nullptr;
+  FqTileArgs& a = L->a; memset(&a, 0, sizeof a);
+  a.data = data; a.n = n; a.virtual_end = last ? 1 : 0; a.line_end = L->line_end; a.cap = L->cap; a.out5 = tile_out_;
+  a.j0 = j0; a.max_rec = kNone32; a.g0 = g0_local + F.g_base; a.step_base = step_base(file); a.cx = make_ctx(file);
+  const int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
+  a.stats = f_[target].stats_open; a.hist = f_[target].hist_open; a.stats_range = f_[file].stats_open; a.key = key_; a.names = L->names; a.names_cap = L->ncap;
+  a.hint_line_len = F.first_seq_len;
+  a.lead = lead;
+  /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
+   * decide (they own the reference's first-error semantics). */
+  if (!(lanes_ok_ && !skip_lanes && a.cx.space != FQ_SPACE_COLOR)) return;
+  L->tried = true;
+  uint32_t linit[FQ_LANES_OUT_WORDS]; memset(linit, 0, sizeof linit);
+  linit[2] = kNone32; linit[5] = kNone32; linit[6] = kNone32; linit[8] = kNone32;
+  dev_->set_words(tile_out_, linit, FQ_LANES_OUT_WORDS);
+  /* room for the names of the chunk (the per-line mode of the pass copies them out of the window itself): what the chunks before
+   * it needed per byte and a quarter more; a pass that runs out of room hands the chunk on like any other anomaly */
+  if (L->names) {
+    double rate = F.arena_rate;
+    if (rate <= 0 && F.first_hdr_len >= 3 && F.first_seq_len) rate = 1.2 * (double)((F.first_hdr_len - 2 + 15) >> 4) / (double)(F.first_hdr_len + 2.0 * F.first_seq_len + 2);
+    if (rate <= 0) rate = 1.0 / 64;
+    /* (every tile of the pass gets the same stretch of the block: what the fullest tile needed so far, a quarter more, and a little) */
+    const uint64_t ntiles = ((uint64_t)n + (uint64_t)kLanesTile - 1) / (uint64_t)kLanesTile;
+    L->arena_units = std::min<uint64_t>(((uint64_t)(rate * 1.25 * kLanesTile) + 16) * ntiles, (1ull << 28) - 1);
+    L->arena = (uint8_t*)dev_->alloc((size_t)L->arena_units * 16 + kPad);
+  }
+  a.arena = L->arena; a.arena_units = (uint32_t)L->arena_units;
+  if (L->routed) {
+    a.route_world = F.route_world; a.route_stride = F.route_stride; a.route_units = F.route_units;
+    for (uint32_t o = 0; o < F.route_world; o++) a.route_region[o] = F.route_region[o] + (size_t)(F.route_chunks % F.route_depth) * F.route_bytes;
+  }
+  /* While every chunk so far is final and no bytes wait for the rest of their record, an accepted clean-data pass is final too: its
+   * statistics go straight into the main set (a chunk the pass hands on leaves no trace in either set). */
+  L->direct = open_ && add_depth_ == 1 && F.pend_n == 0 && !open_dirty_ && !getenv("FQG_NO_DIRECT");
+  if (L->direct) { a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; }
+  L->launched = dev_->lanes_pass(a, &L->self_judged);
+  if (L->launched && hook_ && !hook_after_) { /* the pass is running: the caller routes the names of the chunks before this one beside it */
+    in_beside_hook_ = true; L->hooked = true;
+    try { hook_(hook_user_, file); } catch (...) { in_beside_hook_ = false; throw; }
+    in_beside_hook_ = false;
+  }
+}
+
+/* a pass launched ahead whose chunk never came (it cannot happen for the chunks of one fqg_feed_device call: the start of the next
+ * chunk was taken from the pass's own line ends; a caller may stop feeding, though) */
+void FqEngine::lanes_discard(LanesLaunch* L) {
+  if (!L->valid) return;
+  dev_->sync();
+  if (L->launched) {
+    uint32_t o[FQ_LANES_OUT_WORDS]; dev_->download(o, tile_out_, sizeof o);
+    const bool pass_ok = !o[1] && o[2] == kNone32 && !o[3] && !o[4];
+    const bool accepted = L->self_judged ? o[25] != 0 : false;
+    if (!L->self_judged && pass_ok) dev_->lanes_commit(L->a, true);
+    if (accepted) { L->valid = false; throw std::runtime_error("internal: a clean-data pass launched ahead of its chunk was never collected"); }
+  }
+  if (L->line_end) dev_->release(L->line_end);
+  if (L->names) dev_->release(L->names);
+  if (L->arena) dev_->release(L->arena);
+  L->valid = false;
+}
+
+/* K1+K2 fused over buffer b.  Returns false (nothing launched, or results discarded) when the two-pass path must be used. */
 bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap, bool skip_lanes) {
   FqFile& F = f_[file];
   FqBuffer& B = F.bufs[b];
   int loop = loop_of(file);
-  if (loop == FQ_LOOP_MATE && total0() == 0) return false;
-  if (F.limit != ~0ull) return false;
-  if (F.sniff_fmt < 0) {
-    if (F.nrec != 0 || F.pend_n != 0) return false;
-    if (!presniff(file, B.data, B.n, j0, !lanes_ok_)) return false; /* the clean-data pass has no record-length limit */
+  LanesLaunch L;
+  if (pre_.valid) { /* this chunk's pass may be running already */
+    if (pre_.file == file && pre_.data == B.data && pre_.n == B.n && pre_.lead == B.lead && pre_.j0 == j0 && pre_.last == last && !skip_lanes) { L = pre_; pre_.valid = false; }
+    else lanes_discard(&pre_);
   }
-  uint32_t cap = B.n / 32 + 4096;
-  B.line_end = (uint32_t*)dev_->alloc((size_t)cap * sizeof(uint32_t) + kPad);
-  uint32_t ncap = cap / 4 + 1;
-  /* (16 bytes per record: with the lengths of the file's first record known, room for a third more records than such records would
-   * fill the chunk with — a chunk with more hands itself on, see fq_lanes_post_kernel, and the next one asks for the full bound) */
-  if (lanes_ok_ && !names_cap_full_ && F.first_hdr_len && F.first_seq_len)
-    ncap = std::min<uint32_t>(ncap, (uint32_t)((double)B.n / (0.75 * (F.first_hdr_len + 2.0 * F.first_seq_len + 2))) + 4096);
-  const bool routed = F.route_world > 0 && lanes_ok_ && !skip_lanes && f_[loop == FQ_LOOP_MATE ? 0 : file].sniff_color != FQ_SPACE_COLOR; /* the pass routes the names itself: no descriptors, no arena */
-  FqName* names = (loop != FQ_LOOP_SINGLE && loop != FQ_LOOP_READER && !routed) ? (FqName*)dev_->alloc((size_t)ncap * sizeof(FqName)) : nullptr;
-  FqTileArgs a; memset(&a, 0, sizeof a);
-  a.data = B.data; a.n = B.n; a.virtual_end = last ? 1 : 0; a.line_end = B.line_end; a.cap = cap; a.out5 = tile_out_;
-  a.j0 = j0; a.max_rec = kNone32; a.g0 = g0_local + F.g_base; a.step_base = step_base(file); a.cx = make_ctx(file);
-  int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
-  a.stats = f_[target].stats_open; a.hist = f_[target].hist_open; a.stats_range = f_[file].stats_open; a.key = key_; a.names = names; a.names_cap = ncap;
-  a.hint_line_len = F.first_seq_len;
-  a.lead = B.lead;
-  /* first choice: the clean-data pass.  It commits nothing unless the whole chunk is clean; otherwise the per-record kernels
-   * below decide (they own the reference's first-error semantics). */
-  if (lanes_ok_ && !skip_lanes && a.cx.space != FQ_SPACE_COLOR) {
-    uint32_t linit[FQ_LANES_OUT_WORDS]; memset(linit, 0, sizeof linit);
-    linit[2] = kNone32; linit[5] = kNone32; linit[6] = kNone32; linit[8] = kNone32;
-    dev_->set_words(tile_out_, linit, FQ_LANES_OUT_WORDS);
-    /* room for the names of the chunk (the per-line mode of the pass copies them out of the window itself): what the chunks before
-     * it needed per byte and a quarter more; a pass that runs out of room hands the chunk on like any other anomaly */
-    uint8_t* arena = nullptr; uint64_t arena_units = 0;
-    if (names) {
-      double rate = F.arena_rate;
-      if (rate <= 0 && F.first_hdr_len >= 3 && F.first_seq_len) rate = 1.2 * (double)((F.first_hdr_len - 2 + 15) >> 4) / (double)(F.first_hdr_len + 2.0 * F.first_seq_len + 2);
-      if (rate <= 0) rate = 1.0 / 64;
-      /* (every tile of the pass gets the same stretch of the block: what the fullest tile needed so far, a quarter more, and a little) */
-      const uint64_t ntiles = ((uint64_t)B.n + (uint64_t)kLanesTile - 1) / (uint64_t)kLanesTile;
-      arena_units = std::min<uint64_t>(((uint64_t)(rate * 1.25 * kLanesTile) + 16) * ntiles, (1ull << 28) - 1);
-      arena = (uint8_t*)dev_->alloc((size_t)arena_units * 16 + kPad);
+  if (!L.valid) {
+    if (loop == FQ_LOOP_MATE && total0() == 0) return false;
+    if (F.limit != ~0ull) return false;
+    if (F.sniff_fmt < 0) {
+      if (F.nrec != 0 || F.pend_n != 0) return false;
+      if (!presniff(file, B.data, B.n, j0, !lanes_ok_)) return false; /* the clean-data pass has no record-length limit */
     }
-    a.arena = arena; a.arena_units = (uint32_t)arena_units;
-    if (routed) {
-      a.route_world = F.route_world; a.route_stride = F.route_stride; a.route_units = F.route_units;
-      for (uint32_t o = 0; o < F.route_world; o++) a.route_region[o] = F.route_region[o] + (size_t)(F.route_chunks % F.route_depth) * F.route_bytes;
-    }
-    /* While every chunk so far is final and no bytes wait for the rest of their record, an accepted clean-data pass is final too: its
-     * statistics go straight into the main set (a chunk the pass hands on leaves no trace in either set). */
-    const bool direct = open_ && add_depth_ == 1 && F.pend_n == 0 && !open_dirty_ && !getenv("FQG_NO_DIRECT");
-    if (direct) { a.stats = f_[target].stats; a.hist = f_[target].hist; a.stats_range = f_[file].stats; }
-    bool self_judged = false;
-    if (dev_->lanes_pass(a, &self_judged)) {
-      if (hook_ && !hook_after_) { /* the pass is running: the caller routes the names of the chunks before this one beside it */
-        in_beside_hook_ = true; hook_fired_ = true;
-        try { hook_(hook_user_, file); } catch (...) { in_beside_hook_ = false; throw; }
-        in_beside_hook_ = false;
-      }
+    lanes_prepare(file, B.data, B.n, B.lead, last, j0, g0_local, skip_lanes, &L);
+  }
+  if (L.hooked) hook_fired_ = true;
+  B.line_end = L.line_end;
+  uint32_t cap = L.cap, ncap = L.ncap;
+  FqName* names = L.names;
+  FqTileArgs a = L.a;
+  const bool routed = L.routed, direct = L.direct, self_judged = L.self_judged;
+  uint8_t* arena = L.arena; const uint64_t arena_units = L.arena_units;
+  const int target = a.cx.loop == FQ_LOOP_MATE ? 0 : file;
+  (void)cap;
+  if (L.tried) {
+    if (L.launched) {
       uint32_t o[FQ_LANES_OUT_WORDS];
       dev_->download(o, tile_out_, sizeof o);
       bool pass_ok = !o[1] && o[2] == kNone32 && !o[3] && !o[4];
@@ -343,6 +394,7 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
           F.arena_rate = std::max(F.arena_rate, (double)o[24] / kLanesTile); /* (the fullest tile's units: every tile gets the same stretch) */
         } else if (arena) dev_->release(arena);
         *names_out = names; *names_cap = ncap;
+        launch_ahead(file, B, j0, g0_local); /* the next chunk's pass, before this chunk's bookkeeping */
         return true;
       }
       path_counts[1]++;
@@ -383,6 +435,36 @@ bool FqEngine::try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t 
   if (launched) fused_fallback();
   else fused_ok_ = false;
   return false;
+}
+
+/* The pass of chunk k has told where its last complete record ends: chunk k+1 of the same fqg_feed_device call starts there (see
+ * feed_device) and its pass is launched now, while the host still has chunk k's segment, name kernels and settling to do.  Only when
+ * nothing can move that start: what is left behind the last record must be a plain partial record (no line gzgets would split). */
+void FqEngine::launch_ahead(int file, const FqBuffer& B, uint32_t j0, uint64_t g0_local) {
+  if (!next_.valid || next_.file != file || getenv("FQG_NO_AHEAD")) return;
+  next_.valid = false;
+  FqFile& F = f_[file];
+  if (hook_ && F.route_world == 0) return; /* a caller that packs the name descriptors of finished chunks from its hook wants this chunk's segment first */
+  if (B.nlines < j0 + 4u || !fused_ok_ || F.limit != ~0ull) return;
+  const uint32_t nrec = (B.nlines - j0) / 4, idx = j0 + 4 * nrec - 1;
+  if (idx < B.tail_from || idx >= B.tail_from + B.tail_n) return;
+  const uint32_t end_off = B.tail_ends[idx - B.tail_from];
+  uint32_t start = end_off;
+  for (uint32_t i = idx + 1, c = 0; i <= B.nlines; i++, c++) { /* the lines behind the last record, and the bytes behind the last line */
+    const uint32_t end = i < B.nlines ? B.tail_ends[i - B.tail_from] : B.n;
+    if (end - start >= ((c & 1u) == 0 ? FQ_MAX_LABEL_LENGTH : FQ_MAX_READ_LENGTH)) return;
+    start = end;
+  }
+  const size_t pend = B.n - end_off, own = B.n - B.lead;
+  if (pend >= own / 2) return;
+  uint8_t* p = next_.ptr - pend;
+  const size_t rem = next_.remaining + pend;
+  if (rem == 0) return;
+  const size_t maxc = std::min(feed_chunk(), kMaxChunk - 16), k = std::min(rem, maxc);
+  if (k < fused_min_) return;
+  const uint32_t lead = (uint32_t)((uintptr_t)p & 15u);
+  lanes_prepare(file, p - lead, (uint32_t)(k + lead), lead, next_.last && k == rem, 0, g0_local + nrec, false, &pre_);
+  if (!pre_.tried) lanes_discard(&pre_);
 }
 
 /* the fused pass touched the global statistics / event key with results we cannot use: redo everything seen so far two-pass */

@@ -76,6 +76,13 @@ struct FqFile {
   std::vector<Prescan> prescans;
 };
 
+/* a clean-data pass that has been prepared (buffers) and perhaps launched, not collected yet */
+struct LanesLaunch {
+  bool valid = false; int file = 0; uint8_t* data = nullptr; uint32_t n = 0, lead = 0, j0 = 0; bool last = false;
+  uint32_t cap = 0, ncap = 0; uint32_t* line_end = nullptr; FqName* names = nullptr; uint8_t* arena = nullptr; uint64_t arena_units = 0;
+  FqTileArgs a; bool tried = false, launched = false, self_judged = false, routed = false, direct = false, hooked = false;
+};
+
 class FqEngine {
  public:
   FqEngine(const fqg_config& cfg, FqDevice* dev);
@@ -170,6 +177,11 @@ class FqEngine {
   void add_buffer(int file, uint8_t* data, uint32_t n, bool last, bool owned, bool allow_fused = true, uint32_t lead = 0);
   void realign(FqBuffer& B);
   bool try_fused_pass(int file, int b, bool last, uint32_t j0, uint64_t g0_local, FqName** names_out, uint32_t* names_cap, bool skip_lanes = false);
+  void lanes_prepare(int file, uint8_t* data, uint32_t n, uint32_t lead, bool last, uint32_t j0, uint64_t g0_local, bool skip_lanes, LanesLaunch* L);
+  void lanes_discard(LanesLaunch* L);
+  void launch_ahead(int file, const FqBuffer& B, uint32_t j0, uint64_t g0_local);
+  LanesLaunch pre_;                         /* the pass of the next chunk, launched ahead */
+  struct { bool valid = false; int file = 0; uint8_t* ptr = nullptr; size_t remaining = 0; bool last = false; } next_; /* what follows the chunk being added (fqg_feed_device) */
   bool presniff(int file, const uint8_t* data, uint32_t n, uint32_t skip, bool short_only = true);
   void fused_fallback();
   void segmentize(int file, int b, uint32_t pos, uint32_t j, bool last);
