@@ -1090,6 +1090,32 @@ __global__ void fq_stats_fold_scalars_kernel(const FoldParams P) {
   }
 }
 
+/* fastq_filter_n (src/fastq_filter_n.c:77-86): one warp per sequence line, the lanes stride over its bytes */
+__global__ void __launch_bounds__(256)
+fq_count_n_kernel(const uint8_t* __restrict__ data, const FqLine* __restrict__ lines, uint32_t n, uint32_t* out2) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n; k += (gridDim.x * blockDim.x) >> 5) {
+    const FqLine L = lines[k];
+    uint32_t cnt = 0, stop = L.len, nul = L.len; /* first LF or NUL / first NUL */
+    for (uint32_t base = 0; base < L.len; base += 32) {
+      const uint32_t i = base + lane;
+      const uint32_t c = i < L.len ? data[L.off + i] : 1u;
+      const uint32_t mstop = __ballot_sync(FULL, c == '\n' || c == 0), mnul = __ballot_sync(FULL, c == 0);
+      if (mnul && nul == L.len) nul = base + (uint32_t)__ffs(mnul) - 1;
+      const uint32_t upto = mstop ? (uint32_t)__ffs(mstop) - 1 : 32u;
+      cnt += __popc(__ballot_sync(FULL, (c == 'N' || c == 'n') && (uint32_t)lane < upto));
+      if (mstop) { stop = base + upto; break; }
+    }
+    if (nul == L.len && stop < L.len) { /* the line goes on behind its LF only when gzgets cut it: look for a NUL there too (strlen) */
+      for (uint32_t base = stop & ~31u; base < L.len && nul == L.len; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t mnul = __ballot_sync(FULL, i < L.len && i >= stop && data[L.off + i] == 0);
+        if (mnul) nul = base + (uint32_t)__ffs(mnul) - 1;
+      }
+    }
+    if (lane == 0) { out2[2 * k] = cnt; out2[2 * k + 1] = nul; }
+  }
+}
 struct WordsParams { uint32_t* dst; uint32_t n; uint32_t w[32]; };
 __global__ void fq_set_words_kernel(const WordsParams P) { if (threadIdx.x < P.n) P.dst[threadIdx.x] = P.w[threadIdx.x]; }
 
@@ -1480,6 +1506,12 @@ class FqCudaDevice : public FqDevice {
     for (int f = 0; f < 2; f++) { P.main_[f] = main2[f]; P.open_[f] = open2[f]; P.hist[f] = hist2[f]; P.hopen[f] = hist_open2[f]; }
     fq_stats_fold_hist_kernel<<<sms_, 256, 0, st_>>>(P); launched();
     fq_stats_fold_scalars_kernel<<<1, 32, 0, st_>>>(P); launched();
+  }
+  void count_n(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out2) override {
+    if (!n) return;
+    int grid = (int)std::min<uint32_t>((n + 7) / 8, (uint32_t)sms_ * 8);
+    fq_count_n_kernel<<<grid, 256, 0, st_>>>(data, seq_lines, n, out2);
+    launched();
   }
   void explain(const uint8_t* data, const FqLine* L, const FqRecCtx& cx, FqRecOut* out_dev) override {
     fq_explain_kernel<<<1, 32, 0, st_>>>(data, L[0], L[1], L[2], L[3], cx, out_dev);

@@ -207,6 +207,9 @@ class FqDevice {
    * stats_fold adds the open set of both files into the main set (counters, minima / maxima, the histogram bins between the open
    * minima and maxima of either file) and leaves the open set empty. */
   virtual void stats_fold(FqStats* const main2[2], FqStats* const open2[2], unsigned long long* const hist2[2], unsigned long long* const hist_open2[2]) = 0;
+  /* fastq_filter_n's predicate (src/fastq_filter_n.c:77-86) for n sequence lines of a chunk: out2[2k] = 'N' / 'n' bytes before the first LF or
+   * NUL of line k, out2[2k+1] = strlen of the line (bytes before the first NUL, terminator included) */
+  virtual void count_n(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out2) = 0;
   /* details of one record for the error message */
   virtual void explain(const uint8_t* data, const FqLine* lines4_host, const FqRecCtx& cx, FqRecOut* out_dev) = 0;
   /* device-side stopwatch on the stream (CUDA events) */

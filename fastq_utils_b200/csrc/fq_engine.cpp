@@ -30,7 +30,7 @@ FqEngine::FqEngine(const fqg_config& cfg, FqDevice* dev) : cfg_(cfg), dev_(dev) 
   if (cfg_.mode == FQG_MODE_READER) { reader_ = true; cfg_.mode = FQG_MODE_SINGLE; } /* same chunks, segments, tails and events; only the per-record verdict differs */
   key_ = (unsigned long long*)dev_->alloc(sizeof(unsigned long long));
   counters_ = (unsigned long long*)dev_->alloc(kCounters * sizeof(unsigned long long));
-  streaming_ = cfg_.mode == FQG_MODE_SINGLE || cfg_.mode == FQG_MODE_INDEX || cfg_.mode == FQG_MODE_INDEX_PAIR;
+  streaming_ = (cfg_.mode == FQG_MODE_SINGLE || cfg_.mode == FQG_MODE_INDEX || cfg_.mode == FQG_MODE_INDEX_PAIR) && !(cfg_.flags & FQG_FLAG_KEEP_CHUNKS);
   scratch_ = (uint32_t*)dev_->alloc(64 * sizeof(uint32_t));
   recout_ = (FqRecOut*)dev_->alloc(sizeof(FqRecOut));
   tile_out_ = (uint32_t*)dev_->alloc(32 * sizeof(uint32_t));
@@ -1223,6 +1223,40 @@ void FqEngine::fill_stats(fqg_report* rep) {
     for (uint32_t l = lo; l <= hi; l++) { c += h[l - lo]; if (c > s.num_rds / 2) { med = l; break; } }
   }
   rep->median_rl = med;
+}
+
+/* The four gz-lines of the first `want` records the reader loop delivered (after fqg_finish, single-file loops fed as ONE chunk with
+ * FQG_FLAG_KEEP_CHUNKS): offsets into that chunk.  For the tools that write records (src/fastq_truncate.c, src/fastq_filter_n.c). */
+void FqEngine::record_table(uint64_t want, std::vector<FqLine>* lines4, const uint8_t** data) {
+  FqFile& F = f_[0];
+  lines4->clear(); *data = nullptr;
+  uint64_t lim = std::min<uint64_t>(eff_records(F), want);
+  if (lim == 0) return;
+  if (F.bufs.empty()) return;
+  for (auto& sg : F.segs) if (sg.buf != F.segs[0].buf) throw std::runtime_error("fqg_reader_tool_mem: the record-writing tools take the stream as one chunk");
+  *data = F.bufs[F.segs[0].buf].data;
+  lines4->reserve((size_t)lim * 4);
+  for (auto& sg : F.segs) {
+    if (sg.g0 >= lim) break;
+    uint64_t nrec = std::min<uint64_t>(sg.nrec, lim - sg.g0);
+    FqBuffer& B = F.bufs[sg.buf];
+    if (sg.explicit_lines) { for (int i = 0; i < 4; i++) lines4->push_back(sg.lines_host[i]); continue; }
+    ensure_full_index(B);
+    std::vector<uint32_t> e((size_t)nrec * 4);
+    dev_->download(e.data(), B.line_end + sg.j0, e.size() * sizeof(uint32_t));
+    uint32_t start = sg.q;
+    for (size_t i = 0; i < e.size(); i++) { FqLine L; L.off = start; L.len = e[i] - start; lines4->push_back(L); start = e[i]; }
+  }
+}
+void FqEngine::count_n(const uint8_t* data, const std::vector<FqLine>& seq_lines, std::vector<uint32_t>* out2) {
+  out2->assign(seq_lines.size() * 2, 0);
+  if (seq_lines.empty()) return;
+  FqLine* d = (FqLine*)dev_->alloc(seq_lines.size() * sizeof(FqLine));
+  uint32_t* o = (uint32_t*)dev_->alloc(seq_lines.size() * 2 * sizeof(uint32_t));
+  dev_->upload(d, seq_lines.data(), seq_lines.size() * sizeof(FqLine));
+  dev_->count_n(data, d, (uint32_t)seq_lines.size(), o);
+  dev_->download(out2->data(), o, out2->size() * sizeof(uint32_t));
+  dev_->release(d); dev_->release(o);
 }
 
 void FqEngine::index_records(const void* host_bytes, size_t n, uint64_t* starts, size_t cap, uint64_t* n_records) {

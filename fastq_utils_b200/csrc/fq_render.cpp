@@ -408,6 +408,94 @@ int fastq_info_run(int argc, const char** argv_in, Source& src, int device, fqg_
 }
 }  // namespace
 
+namespace {
+/* main() of the reader tools that WRITE records: src/fastq_truncate.c:32-57 (the first num_reads entries) and src/fastq_filter_n.c:33-93
+ * (entries whose share of N bases is within -n percent).  Both are the fastq_read_entry loop (src/fastq.c:245-261) followed by
+ * fastq_write_entry2stdout (:81-86: four `%s` of the line buffers, so a line ends at its first NUL).  The records are delimited on the
+ * device (FQG_MODE_READER, the stream as one chunk), fastq_filter_n's predicate is evaluated there (count_n); the host writes the
+ * chosen byte ranges of the stream it was given. */
+int writer_tool(bool filter_n, int argc, const char** argv_in, const void* f1, size_t n1, int device, fqg_transcript* tr) {
+  const size_t UNOPENABLE = (size_t)-1;
+  Text t;
+  t.e("fastq_utils %s\n", "0.25.3");
+  const char* fname = nullptr; long num_reads = 0; unsigned max_n = 0;
+  if (!filter_n) {
+    if (argc != 3) { t.e("Usage: fastq_truncate fastq1 num_reads\n"); t.rc = 1; to_transcript(t, tr); return 0; }
+    fname = argv_in[1]; num_reads = atol(argv_in[2]);
+  } else {
+    /* getopt(argc, argv, "n:") with opterr = 0, as GNU libc runs it: option words (and the arguments they take) are permuted to the front */
+    std::vector<const char*> opts, rest; int nopt = 0;
+    bool stop = false;
+    for (int i = 1; i < argc; i++) {
+      const char* w = argv_in[i];
+      if (!stop && !strcmp(w, "--")) { opts.push_back(w); stop = true; continue; }
+      if (stop || !(w[0] == '-' && w[1] != '\0')) { rest.push_back(w); continue; }
+      opts.push_back(w);
+      for (const char* c = w + 1; *c; c++) {
+        if (*c == 'n') {
+          const char* arg = c[1] ? c + 1 : (i + 1 < argc ? argv_in[++i] : nullptr);
+          if (!arg) { ++nopt; ERR_BEGIN(t); t.e("Option -%c invalid", 'n'); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; } /* a missing argument is getopt's '?' */
+          if (!c[1]) opts.push_back(arg);
+          max_n = (unsigned)atoi(arg); if (max_n > 100) max_n = 100;
+          nopt += 2;
+          break; /* the rest of the word was the argument */
+        }
+        ++nopt; ERR_BEGIN(t); t.e("Option -%c invalid", *c); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0;
+      }
+    }
+    if (argc - nopt < 2 || argc - nopt > 3) { ERR_BEGIN(t); t.e("Usage: fastq_filter_n [ -n 0 ] fastq1"); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; }
+    std::vector<const char*> argv; argv.push_back(argv_in[0]);
+    argv.insert(argv.end(), opts.begin(), opts.end()); argv.insert(argv.end(), rest.begin(), rest.end());
+    if (max_n > 0) t.e("Discard reads with more than %d%% of Ns\n", (int)max_n); else t.e("Discard reads with at least one N\n");
+    fname = (size_t)(nopt + 1) < argv.size() ? argv[nopt + 1] : "";
+  }
+  if (n1 == UNOPENABLE) { ERR_BEGIN(t); t.e("Unable to open %s", fname); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; }
+  if (!f1 && n1) return FQG_ERR_USAGE;
+  if (n1 > (((size_t)1 << 31) - 64)) return FQG_ERR_USAGE; /* one chunk: the record-writing tools take streams below 2 GiB */
+  fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER; cfg.flags = FQG_FLAG_KEEP_CHUNKS;
+  try {
+    FqDevice* dev = fq_default_device(device);
+    {
+      FqEngine eng(cfg, dev);
+      eng.feed_host(0, f1, n1, true);
+      fqg_report rep; eng.finish(&rep);
+      const bool truncated = rep.error.code == FQG_E_TRUNC;      /* the loop met a record without all four lines ... */
+      const uint64_t nread = truncated ? rep.reads_before_error[0] : rep.file[0].n_records; /* ... after this many entries (else: all that fastq_read_entry delivered) */
+      const uint64_t want = filter_n ? nread : (num_reads < 0 ? nread : std::min<uint64_t>(nread, (uint64_t)num_reads));
+      std::vector<FqLine> L; const uint8_t* ddata = nullptr;
+      eng.record_table(want, &L, &ddata);
+      std::vector<uint32_t> nn;
+      if (filter_n && !L.empty()) {
+        std::vector<FqLine> seq(L.size() / 4);
+        for (size_t r = 0; r < seq.size(); r++) seq[r] = L[4 * r + 1];
+        eng.count_n(ddata, seq, &nn);
+      }
+      const char* bytes = (const char*)f1;
+      for (size_t r = 0; r < L.size() / 4; r++) {
+        if (filter_n) {
+          const unsigned long read_len = nn[2 * r + 1];
+          const unsigned max_num_n = (unsigned)(read_len * max_n / 100);
+          const bool keep = nn[2 * r] <= max_num_n;
+          if (keep) for (int i = 0; i < 4; i++) { const FqLine& l = L[4 * r + i]; t.out.append(bytes + l.off, strnlen(bytes + l.off, l.len)); }
+          const unsigned long cline = 4ul * (unsigned long)(r + 1);
+          if (cline % 100000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", cline);
+        } else for (int i = 0; i < 4; i++) { const FqLine& l = L[4 * r + i]; t.out.append(bytes + l.off, strnlen(bytes + l.off, l.len)); }
+      }
+      /* the loop met the broken record only if it went on reading that far (src/fastq_truncate.c:47-49) */
+      if (truncated && (filter_n || num_reads < 0 || (uint64_t)num_reads > nread)) { error_text(t, rep.error, fname, fname); t.rc = 1; }
+      else t.rc = 0;
+    }
+    delete dev;
+  } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
+  } catch (const std::exception& ex) {
+    fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
+    return strstr(ex.what(), "CUDA") ? (strstr(ex.what(), "no CUDA") ? FQG_ERR_NO_DEVICE : FQG_ERR_CUDA) : FQG_ERR_INTERNAL;
+  }
+  to_transcript(t, tr);
+  return 0;
+}
+}  // namespace
+
 /* main() of the reader-style tools on an inflated stream: src/fastq_num_reads.c:32-50, src/fastq_not_empty.c:32-47.  Both are
  * the bare fastq_read_next_entry loop (src/fastq.c:237-261): records are delimited, a NUL-led header line ends the file quietly,
  * a record with fewer than four lines is "file truncated" (exit 1); nothing is validated. */
@@ -417,6 +505,7 @@ extern "C" int fqg_reader_tool_mem(int argc, const char** argv, const void* f1, 
   Text t;
   const char* tool = strrchr(argv[0], '/'); tool = tool ? tool + 1 : argv[0];
   const bool num_reads = !strcmp(tool, "fastq_num_reads"), not_empty = !strcmp(tool, "fastq_not_empty");
+  if (!strcmp(tool, "fastq_truncate") || !strcmp(tool, "fastq_filter_n")) return writer_tool(!strcmp(tool, "fastq_filter_n"), argc, argv, f1, n1, device, tr);
   if (!num_reads && !not_empty) return FQG_ERR_USAGE;
   if (num_reads) t.e("fastq_utils %s\n", "0.25.3"); /* fastq_print_version, src/fastq_num_reads.c:34; fastq_not_empty prints none */
   if (argc != 2) {

@@ -56,6 +56,8 @@ typedef struct {
  * Without the flag the buffer must stay valid until fqg_reset / fqg_destroy: chunks of a job in which an event fired, and all chunks
  * of the interleaved / sorted-pair loops, are read again by fqg_finish. */
 #define FQG_FLAG_BORROW_FOR_CALL 8u
+/* keep every chunk until fqg_reset (the record-writing reader tools read the line index of the whole stream afterwards) */
+#define FQG_FLAG_KEEP_CHUNKS 16u
 
 /* statistics of one FASTQ_FILE as the reference holds them at the end of its loops (src/fastq.h:110-131) */
 typedef struct {

@@ -399,6 +399,16 @@ class FqSimDevice : public FqDevice {
       o->num_rds = 0; o->mem_sum = 0; o->n_names = 0; o->min_rl = 0xFFFFFFFFu; o->max_rl = 0; o->min_q = 255u; o->max_q = 0;
     }
   }
+  void count_n(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out2) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < n; k++) {
+      const FqLine& L = seq_lines[k];
+      uint32_t cnt = 0, i = 0;
+      for (; i < L.len; i++) { uint8_t c = data[L.off + i]; if (c == '\n' || c == 0) break; if (c == 'N' || c == 'n') cnt++; }
+      uint32_t nul = 0; while (nul < L.len && data[L.off + nul] != 0) nul++;
+      out2[2 * k] = cnt; out2[2 * k + 1] = nul;
+    }
+  }
   void explain(const uint8_t* data, const FqLine* lines4, const FqRecCtx& cx, FqRecOut* out) override {
     n_launch_++;
     fq_check_record_careful(data, lines4, cx, out);
