@@ -114,6 +114,7 @@ def bind(L):
     L.fqg_route_chunks.argtypes = [vp, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32)]
     L.fqg_route_blocks.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     L.fqg_side_mark.argtypes = [vp]
+    L.fqg_order_after.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
     L.fqg_route_region_bytes.argtypes = [ctypes.c_uint32, u64, ctypes.c_uint32]
     L.fqg_route_region_bytes.restype = sz
     L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64), ctypes.POINTER(u64)]
@@ -327,6 +328,10 @@ class FastqInfo:
         n = ctypes.c_uint32()
         _check(self._ctx, lib().fqg_route_blocks(self._ctx, ctypes.byref(n)), "fqg_route_blocks")
         return int(n.value)
+
+    def order_after(self, my_side, earlier, their_side):
+        """what this context queues from now on (side / main stream) starts after what `earlier` has queued so far"""
+        _check(self._ctx, lib().fqg_order_after(self._ctx, int(bool(my_side)), earlier._ctx, int(bool(their_side))), "fqg_order_after")
 
     def side_mark(self):
         _check(self._ctx, lib().fqg_side_mark(self._ctx), "fqg_side_mark")

@@ -186,6 +186,10 @@ extern "C" int fqg_route_blocks(fqg_ctx* c, uint32_t* nblocks) {
   FQG_GUARD(c, *nblocks = c->dev->lanes_max_blocks())
 }
 extern "C" size_t fqg_route_region_bytes(uint32_t nblocks, uint64_t stride, uint32_t name_units) { return fq_route_region_bytes(nblocks, stride, name_units); }
+extern "C" int fqg_order_after(fqg_ctx* later, int later_side, fqg_ctx* earlier, int earlier_side) {
+  if (!later || !earlier) return FQG_ERR_USAGE;
+  FQG_GUARD(later, later->dev->order_after(later_side != 0, *earlier->dev, earlier_side != 0))
+}
 extern "C" int fqg_side_mark(fqg_ctx* c) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->dev->side_mark())

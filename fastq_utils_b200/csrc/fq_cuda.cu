@@ -854,6 +854,7 @@ struct SlotInsertParams {
   const uint8_t* regions; uint32_t n_src; size_t region_bytes; uint32_t nblocks; unsigned long long stride; uint32_t units;
   FqSlot* slots; unsigned long long mask; unsigned long long* counters;
   const unsigned long long* flags; unsigned long long expect; /* flags[s] >= expect: source s has delivered its region (NULL: the host knows) */
+  long long patience; /* clock cycles a source may stay silent */
 };
 /* The sources announce their regions with a flag word written behind the region's bytes (same stream of copies, so the bytes are
  * there when the flag is): the owner's kernel waits for the flags on the device — no host takes part in a routing round.  One
@@ -870,26 +871,55 @@ __device__ __forceinline__ bool route_wait_sources(const SlotInsertParams& P) {
       unsigned long long v;
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(P.flags + threadIdx.x) : "memory");
       if (v >= P.expect) break;
-      if (clock64() - t0 > 20000000000ll) { s_late = 1; atomicExch(P.counters + 2, 1ull); break; } /* about ten seconds */
+      if (clock64() - t0 > P.patience) { s_late = 1; atomicExch(P.counters + 2, 1ull); break; } /* about ten seconds */
       __nanosleep(200);
     }
   }
   __syncthreads();
   return s_late == 0;
 }
-/* item m of the planned n_src x nblocks x stride slots → the route slot, or NULL when the stretch holds fewer */
-__device__ __forceinline__ const FqRouteSlot* route_item(const SlotInsertParams& P, unsigned long long m, size_t slot_bytes) {
-  const unsigned long long per = (unsigned long long)P.nblocks * P.stride;
-  const unsigned long long src = m / per, in = m - src * per, b = in / P.stride, k = in - b * P.stride;
-  const uint8_t* reg = P.regions + src * P.region_bytes;
-  const FqRegionHdr h = *(const FqRegionHdr*)reg;
-  if (h.nblocks == 0) return nullptr; /* this source had nothing for us in this round */
-  if (in == 0 && (h.nblocks > P.nblocks || h.stride != P.stride || h.flags)) atomicExch(P.counters + 2, 1ull); /* not what was planned, or a name longer than its slot */
-  if (b >= h.nblocks) return nullptr;
-  const uint32_t cnt = ((const uint32_t*)(reg + 16))[b];
-  if (k == 0 && cnt > P.stride) atomicExch(P.counters + 2, 1ull); /* the writer had more names for this owner than its stretch holds */
-  if (k >= cnt) return nullptr;
-  return (const FqRouteSlot*)(reg + 16 + fq_route_counts_bytes(h.nblocks) + (b * P.stride + k) * slot_bytes);
+/* The wait is a kernel of its own, one warp in front of the owner's kernel on the same stream: a grid that filled the device while
+ * it polled would keep out whatever the flags still depend on (a copy the driver performs with a kernel, a collective's kernel, the
+ * pass of a slower peer's host) — measured with four ranks as a deadlock that only the patience above resolved. */
+__global__ void __launch_bounds__(32, 1)
+fq_route_wait_kernel(const SlotInsertParams P) { route_wait_sources(P); }
+/* the owner's kernel itself only looks: the flags are there unless the wait gave up */
+__device__ __forceinline__ bool route_sources_there(const SlotInsertParams& P) {
+  __shared__ int s_missing;
+  if (!P.flags) return true;
+  if (threadIdx.x == 0) s_missing = 0;
+  __syncthreads();
+  if (threadIdx.x < P.n_src) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(P.flags + threadIdx.x) : "memory");
+    if (v < P.expect) s_missing = 1;
+  }
+  __syncthreads();
+  return s_missing == 0;
+}
+/* The slots of the regions, one warp per stretch (source s, writer b): the stretch's count is read once, the lanes take its slots
+ * 32 at a time.  f(slot) for every slot; stretches that are not what was planned raise counters[2]. */
+template <class F>
+__device__ __forceinline__ void route_each_slot(const SlotInsertParams& P, F f) {
+  const size_t slot_bytes = fq_route_slot_bytes(P.units);
+  const int lane = threadIdx.x & 31;
+  const unsigned long long segs = (P.stride + 1023ull) >> 10; /* a stretch is taken in pieces of 1024 slots (a dense region is one long stretch) */
+  const unsigned long long nunits = (unsigned long long)P.n_src * P.nblocks * segs;
+  const unsigned long long warp0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long un = warp0; un < nunits; un += nwarps) {
+    const unsigned long long st = un / segs, sg = un - st * segs;
+    const unsigned long long src = st / P.nblocks, b = st - src * P.nblocks;
+    const uint8_t* reg = P.regions + src * P.region_bytes;
+    const FqRegionHdr h = *(const FqRegionHdr*)reg;
+    if (h.nblocks == 0) continue; /* this source had nothing for us in this round */
+    if (b == 0 && sg == 0 && lane == 0 && (h.nblocks > P.nblocks || h.stride != P.stride || h.flags)) atomicExch(P.counters + 2, 1ull); /* not what was planned, or a name longer than its slot */
+    if (b >= h.nblocks) continue;
+    uint32_t cnt = ((const uint32_t*)(reg + 16))[b];
+    if (cnt > P.stride) { if (lane == 0 && sg == 0) atomicExch(P.counters + 2, 1ull); cnt = (uint32_t)P.stride; } /* the writer had more names for this owner than its stretch holds */
+    const uint8_t* base = reg + 16 + fq_route_counts_bytes(h.nblocks) + b * P.stride * slot_bytes;
+    const uint32_t k1 = (uint32_t)min((unsigned long long)cnt, (sg + 1) << 10);
+    for (uint32_t k = (uint32_t)(sg << 10) + lane; k < k1; k += 32) f((const FqRouteSlot*)(base + (size_t)k * slot_bytes));
+  }
 }
 __global__ void __launch_bounds__(256, 8)
 fq_shard_insert_slots_kernel(const SlotInsertParams P) {
@@ -897,14 +927,8 @@ fq_shard_insert_slots_kernel(const SlotInsertParams P) {
    * atomics, not their latency, are the limit), and so are short blocks on a low-priority stream (they crowd the start of the
    * next pass, whose blocks must all be resident). */
   unsigned long long inserted = 0, equal = 0;
-  if (!route_wait_sources(P)) return;
-  const unsigned long long total = (unsigned long long)P.n_src * P.nblocks * P.stride, step = (unsigned long long)gridDim.x * blockDim.x;
-  const size_t slot_bytes = fq_route_slot_bytes(P.units);
-  for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
-    const unsigned long long m = m0 + threadIdx.x;
-    if (m >= total) continue;
-    const FqRouteSlot* sl = route_item(P, m, slot_bytes);
-    if (!sl) continue;
+  if (!route_sources_there(P)) return;
+  route_each_slot(P, [&](const FqRouteSlot* sl) {
     const unsigned long long hash = sl->hash, me = (unsigned long long)(uintptr_t)sl >> 4;
     unsigned long long i = hash & P.mask, probes = 0;
     for (;; i = (i + 1) & P.mask) {
@@ -916,7 +940,7 @@ fq_shard_insert_slots_kernel(const SlotInsertParams P) {
       equal++; /* the name is there already (units = 0: or its hash is, which tuples alone cannot judge): the exact path reports it */
       break;
     }
-  }
+  });
   __syncwarp();
   inserted = warp_sum64(inserted); equal = warp_sum64(equal);
   if ((threadIdx.x & 31) == 0) { if (inserted) atomicAdd(P.counters + 1, inserted); if (equal) atomicAdd(P.counters + 0, equal); }
@@ -924,14 +948,8 @@ fq_shard_insert_slots_kernel(const SlotInsertParams P) {
 __global__ void __launch_bounds__(256, 8)
 fq_shard_claim_slots_kernel(const SlotInsertParams P) {
   unsigned long long claimed = 0, unpaired = 0;
-  if (!route_wait_sources(P)) return;
-  const unsigned long long total = (unsigned long long)P.n_src * P.nblocks * P.stride, step = (unsigned long long)gridDim.x * blockDim.x;
-  const size_t slot_bytes = fq_route_slot_bytes(P.units);
-  for (unsigned long long m0 = (unsigned long long)blockIdx.x * blockDim.x; m0 < total; m0 += step) {
-    const unsigned long long m = m0 + threadIdx.x;
-    if (m >= total) continue;
-    const FqRouteSlot* sl = route_item(P, m, slot_bytes);
-    if (!sl) continue;
+  if (!route_sources_there(P)) return;
+  route_each_slot(P, [&](const FqRouteSlot* sl) {
     const unsigned long long hash = sl->hash, rec = sl->rec_len >> 12;
     unsigned long long i = hash & P.mask, probes = 0;
     for (;; i = (i + 1) & P.mask) {
@@ -944,7 +962,7 @@ fq_shard_claim_slots_kernel(const SlotInsertParams P) {
       if (old == FQ_IDX_NONE) claimed++; else unpaired++; /* the entry was deleted by an earlier mate: the reference reports the later one */
       break;
     }
-  }
+  });
   __syncwarp();
   claimed = warp_sum64(claimed); unpaired = warp_sum64(unpaired);
   if ((threadIdx.x & 31) == 0) { if (claimed) atomicAdd(P.counters + 8, claimed); if (unpaired) atomicAdd(P.counters + 9, unpaired); }
@@ -1136,6 +1154,7 @@ class FqCudaDevice : public FqDevice {
     FQ_CUDA_CHECK(cudaEventCreateWithFlags(&evx_, cudaEventDisableTiming));
     FQ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_pre_, cudaEventDisableTiming));
     FQ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side_, cudaEventDisableTiming));
+    FQ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_order_, cudaEventDisableTiming));
     FQ_CUDA_CHECK(cudaEventCreate(&ev0_)); FQ_CUDA_CHECK(cudaEventCreate(&ev1_));
     cudaMemPool_t pool; FQ_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev_));
     unsigned long long thr = ~0ull; /* keep freed blocks in the pool: allocations repeat every chunk */
@@ -1151,7 +1170,7 @@ class FqCudaDevice : public FqDevice {
     for (auto& d : deferred_) cudaEventDestroy(d.ready);
     for (auto e : free_ev_) cudaEventDestroy(e);
     cudaFree(tile_state_); if (stage_) cudaFree(stage_); if (small_pinned_) cudaFreeHost(small_pinned_);
-    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_); cudaEventDestroy(ev_pre_); cudaEventDestroy(ev_side_);
+    cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_); cudaEventDestroy(ev_pre_); cudaEventDestroy(ev_side_); cudaEventDestroy(ev_order_);
     cudaStreamDestroy(st_); cudaStreamDestroy(st2_);
   }
   const char* name() const override { return "cuda"; }
@@ -1458,14 +1477,25 @@ class FqCudaDevice : public FqDevice {
     if (!n_src || !nblocks || !stride) return;
     SlotInsertParams P; P.regions = regions; P.n_src = n_src; P.region_bytes = region_bytes; P.nblocks = nblocks; P.stride = stride; P.units = units;
     P.slots = slots; P.mask = mask; P.counters = counters; P.flags = flags; P.expect = expect;
+    static const long long patience_ms = getenv("FQG_FLAG_PATIENCE_MS") ? atoll(getenv("FQG_FLAG_PATIENCE_MS")) : 10000; /* (tests, debugging) */
+    P.patience = patience_ms * 2000000ll;
     unsigned long long total = (unsigned long long)n_src * nblocks * stride;
-    int grid = (int)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)sms_ * (beside ? 1 : 8));
+    /* one warp per stretch when there are many stretches; a dense region (one writer) is one stretch: its warp would work alone */
+    const unsigned long long pieces = (unsigned long long)n_src * nblocks * ((stride + 1023) >> 10);
+    int grid = (int)std::min<unsigned long long>(std::max<unsigned long long>((pieces + 7) / 8, 1), (unsigned long long)sms_ * (beside ? 1 : 8));
     after_main();
+    if (flags) { fq_route_wait_kernel<<<1, 32, 0, st2_>>>(P); launched(); }
     tic(claim ? FQG_K_MATE : FQG_K_INDEX, 0, total, st2_);
     if (claim) fq_shard_claim_slots_kernel<<<grid, 256, 0, st2_>>>(P); else fq_shard_insert_slots_kernel<<<grid, 256, 0, st2_>>>(P);
     toc(st2_); launched();
   }
   uint32_t lanes_max_blocks() override { ensure_lanes_blocks(); return (uint32_t)lanes_blocks_; }
+  void order_after(bool my_side, FqDevice& earlier, bool their_side) override {
+    auto* e = dynamic_cast<FqCudaDevice*>(&earlier);
+    if (!e || e->dev_ != dev_) throw std::runtime_error("fqg_order_after: two contexts of one CUDA device");
+    FQ_CUDA_CHECK(cudaEventRecord(ev_order_, their_side ? e->st2_ : e->st_));
+    FQ_CUDA_CHECK(cudaStreamWaitEvent(my_side ? st2_ : st_, ev_order_, 0));
+  }
   void side_mark() override { FQ_CUDA_CHECK(cudaEventRecord(ev_side_, st2_)); side_marked_ = true; }
   void side_copy(void* dst, const void* src, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, st2_)); }
   void side_sync() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); }
@@ -1522,7 +1552,7 @@ class FqCudaDevice : public FqDevice {
   void launched() { n_launch_++; FQ_CUDA_CHECK(cudaGetLastError()); }
   /* CUDA-event stopwatch around one launch; elapsed times are read back lazily (collect) */
   struct KStat { double ms = 0; uint64_t launches = 0, bytes = 0, items = 0; };
-  struct Pending { int cls; cudaEvent_t a, b; };
+  struct Pending { int cls; cudaEvent_t a, b; bool side; };
   /* The index kernels (random-access, latency-bound) run on a second stream so that they overlap the next chunk's
    * streaming pass; they start after everything queued on the main stream so far (names, table fills, directories). */
   void after_main() {
@@ -1531,10 +1561,11 @@ class FqCudaDevice : public FqDevice {
   }
   void tic(int cls, uint64_t bytes, uint64_t items, cudaStream_t st = nullptr) {
     if (!st) st = st_;
-    Pending p; p.cls = cls;
+    Pending p; p.cls = cls; p.side = st == st2_;
     if (free_ev_.size() >= 2) { p.a = free_ev_.back(); free_ev_.pop_back(); p.b = free_ev_.back(); free_ev_.pop_back(); }
     else { FQ_CUDA_CHECK(cudaEventCreate(&p.a)); FQ_CUDA_CHECK(cudaEventCreate(&p.b)); }
     kst_[cls].launches++; kst_[cls].bytes += bytes; kst_[cls].items += items;
+    if (!g_origin && getenv("FQG_TIMELINE")) { FQ_CUDA_CHECK(cudaEventCreate(&g_origin)); FQ_CUDA_CHECK(cudaEventRecord(g_origin, st)); }
     FQ_CUDA_CHECK(cudaEventRecord(p.a, st));
     pending_.push_back(p);
   }
@@ -1543,13 +1574,23 @@ class FqCudaDevice : public FqDevice {
     flush_deferred();
     if (pending_.empty()) return;
     FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
+    /* FQG_TIMELINE=<file>: where every timed launch of this batch sat, in ms after the batch's first one (a development aid) */
+    const char* tl = getenv("FQG_TIMELINE");
+    FILE* tf = tl && *tl && g_origin ? fopen(tl, "a") : nullptr;
+    if (tf) fprintf(tf, "# device %d object %p, %zu launches\n", dev_, (void*)this, pending_.size());
     for (auto& p : pending_) {
       float ms = 0; FQ_CUDA_CHECK(cudaEventElapsedTime(&ms, p.a, p.b));
       kst_[p.cls].ms += ms;
+      if (tf) {
+        float t0 = 0; FQ_CUDA_CHECK(cudaEventElapsedTime(&t0, g_origin, p.a));
+        fprintf(tf, "%d %s %.3f %.3f\n", p.cls, p.side ? "side" : "main", t0, t0 + ms);
+      }
       free_ev_.push_back(p.a); free_ev_.push_back(p.b);
     }
     pending_.clear();
+    if (tf) fclose(tf);
   }
+  static cudaEvent_t g_origin; /* FQG_TIMELINE: the first timed launch of the process */
   struct Deferred { TableParams tp; cudaEvent_t ready; bool claim; };
   std::vector<Deferred> deferred_;
   KStat kst_[FQG_K_COUNT];
@@ -1559,6 +1600,7 @@ class FqCudaDevice : public FqDevice {
   cudaStream_t st_ = nullptr, st2_ = nullptr;
   cudaEvent_t evx_ = nullptr;
   cudaEvent_t ev_side_ = nullptr; bool side_marked_ = false;
+  cudaEvent_t ev_order_ = nullptr;
   cudaEvent_t ev_pre_ = nullptr; /* main stream just before the latest clean-data pass: what the side stream waits for when it works beside that pass */
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;
@@ -1566,6 +1608,8 @@ class FqCudaDevice : public FqDevice {
   uint8_t small_[4096]; void* small_pinned_ = nullptr;
   unsigned long long n_launch_ = 0;
 };
+
+cudaEvent_t FqCudaDevice::g_origin = nullptr;
 
 }  // namespace
 

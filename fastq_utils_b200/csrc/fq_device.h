@@ -188,6 +188,8 @@ class FqDevice {
   /* the main stream's next clean-data pass waits for what was queued on the side stream so far (copies out of the regions that
    * pass will overwrite) */
   virtual void side_mark() {}
+  /* what this device queues from now on (side or main stream) starts after what `earlier` has queued so far */
+  virtual void order_after(bool /*my_side*/, FqDevice& /*earlier*/, bool /*their_side*/) {}
   virtual void side_copy(void* dst, const void* src, size_t n) = 0;
   virtual void side_sync() = 0;
   /* memory that other processes can map (CUDA IPC); devices without it throw */

@@ -59,6 +59,7 @@ class ShardedFastqInfo:
         self.p2p = os.environ.get("FQG_P2P", "1" if self.tdev.type == "cuda" else "0") not in ("", "0")
         # the copy engines move the packed regions; FQG_P2P_STORES=1: the pack kernel stores into the owners' arenas itself (A/B)
         self.p2p_stores = os.environ.get("FQG_P2P_STORES", "0") not in ("", "0")
+        self._owner_beside = int(os.environ.get("FQG_OWNER_BESIDE", "0") or 0)  # (A/B) 1: the owner's kernels beside the running pass, 2: the inserts only
         self._pending_insert = None
         self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage, self._zero = None, None, False, False, None, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
@@ -292,10 +293,12 @@ class ShardedFastqInfo:
         if r < W - 1 and cut[r + 1] > 0:
             head = torch.zeros(cut[r + 1] + 64, dtype=torch.uint8, device=self.tdev)
             reqs.append(dist.irecv(head[:cut[r + 1]], r + 1))
+        _dbg(f"rank {r} file {f} seam exchange, {len(reqs)} requests")
         for q in reqs:
             q.wait()
         if reqs:
             self._sync()  # the library reads the head on its own stream
+        _dbg(f"rank {r} file {f} seam exchange done")
         ctx.set_stream_start(f, skip[r], 0)  # record numbers inside the range: they only matter when something is wrong
         ctx.set_line_hint(f, info[r][5])  # a range that starts inside the file never sees the first record's sequence line
         if routed:
@@ -316,7 +319,7 @@ class ShardedFastqInfo:
             pl = self._plan[f]
             if pl["mode"] == "pass":
                 while pl["round"] < pl["rounds"]:
-                    self._pass_round()
+                    self._pass_round(beside=False)  # (no pass is running any more: the owner's kernel may take the whole GPU)
                 self._left_round()
             else:
                 while pl["round"] < pl["rounds"] - 1:
@@ -358,10 +361,10 @@ class ShardedFastqInfo:
                 self._hook_exc = ex
         self.host_ms["hook"] = self.host_ms.get("hook", 0.0) + (time.perf_counter() - t0) * 1e3
 
-    def _pass_round(self):
+    def _pass_round(self, beside=True):
         """Round j of the current file, mode `pass`: the regions the clean-data pass of this rank's chunk j filled (none: an empty
         header) go to their owners' arenas through the copy engines; the pass that will reuse the regions waits for the copies."""
-        W, r, f = self.world, self.rank, self._cur
+        W, r, f, ctx = self.world, self.rank, self._cur, self.ctx
         pl = self._plan[f]
         j, region = pl["round"], pl["region"]
         have = j < self.ctx.route_chunks(f)[0]
@@ -379,8 +382,15 @@ class ShardedFastqInfo:
             self._send_flag(o, f, j)
         self.ctx.side_mark()
         self.host_ms["pack"] += (time.perf_counter() - t1) * 1e3
-        # the owner's kernel waits for its sources on the device (their flag words): launched now, beside the running pass
-        self._owner_round(self._arena[0] + pl["base"] + j * W * region, region, pl["nblocks"], pl["stride"], pl["units"], f, True, flag_round=j)
+        # The owner's kernel waits for its sources on the device (their flag words).  It takes the whole device between two passes:
+        # behind the pass that is running now (launched ahead), in front of the next one.  Squeezed in beside a pass (one block
+        # per SM, FQG_OWNER_BESIDE=1) it was measured at a quarter of its speed, and the pass lost a third of its own.
+        between = beside and not (self._owner_beside == 1 or (self._owner_beside == 2 and f == 0))
+        if between:
+            self.shard.order_after(True, ctx, False)
+        self._owner_round(self._arena[0] + pl["base"] + j * W * region, region, pl["nblocks"], pl["stride"], pl["units"], f, beside and not between, flag_round=j)
+        if between:
+            ctx.order_after(False, self.shard, True)
         pl["round"] += 1
 
     def _left_round(self):
@@ -391,6 +401,7 @@ class ShardedFastqInfo:
         region, cap = pl["left_region"], pl["left_stride"]
         _dbg(f"rank {r} file {f} left round, names left {self.ctx.names_new(f)}")
         self.ctx.side_sync()  # the staging regions are free: every copy out of them is done
+        _dbg(f"rank {r} file {f} left round: copies done")
         st = self._stage.data_ptr()
         off = pl["left_base"] + r * region
         self.ctx.names_pack_slots(f, [self._arena[0] + off if o == r else st + o * region for o in range(W)], cap, pl["units"])
@@ -618,6 +629,7 @@ class ShardedFastqInfo:
                 # nothing.  Two files: with their bytes — the owner knows a duplicate, an unpaired mate or a name left over when it
                 # sees one, but the reference's message (which record, which line) is the exact path's business.  So is a region,
                 # slot or table that overflowed, a chunk redone by the two-pass kernels after its names had left, and any error.
+                _dbg(f"rank {r} waits for its owner kernels")
                 inserted, equal, overflow, claimed, unpaired = self.shard.shard_slots_result()
                 broken = any(ctx.route_chunks(f)[1] for f, _, _ in files)  # a chunk whose names the pass should have routed went to the per-record kernels
                 mine_bad = rep.error.code != 0 or cut_short or equal > 0 or unpaired > 0 or overflow or broken or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
@@ -767,7 +779,7 @@ class ShardedFastqInfo:
 def _dbg(msg):
     if os.environ.get("FQG_DEBUG_ROUTE"):
         import sys
-        print("[route] " + msg, file=sys.stderr, flush=True)
+        print(f"[route] {time.perf_counter() % 1000:9.4f} " + msg, file=sys.stderr, flush=True)
 
 
 def _as_tensor(ptr, n, device):

@@ -242,6 +242,11 @@ int fqg_set_route(fqg_ctx* ctx, int file, uint32_t world, void* const* region_pt
 int fqg_route_chunks(fqg_ctx* ctx, int file, uint64_t* n_chunks, int32_t* broken);
 int fqg_route_blocks(fqg_ctx* ctx, uint32_t* nblocks);
 int fqg_side_mark(fqg_ctx* ctx);
+/* Stream order between two contexts of one process and device (the feeding context and the context that holds the index shard):
+ * what `later` queues from now on, on its side stream (later_side != 0) or its main stream, starts after everything `earlier` has
+ * queued so far on its side / main stream.  The owner's kernel of a round takes the whole device between two passes with this (a
+ * table kernel squeezed in beside a running pass was measured 4x slower, and slowed the pass as well). */
+int fqg_order_after(fqg_ctx* later, int later_side, fqg_ctx* earlier, int earlier_side);
 /* (2) Records validated by the per-record kernels (the few at the seams of byte ranges; everything on the stand-in device) have name
  * descriptors: this packs those not packed yet by owner into `world` dense regions (one writer: nblocks = 1, stride = region_cap).
  * Region o starts at region_ptrs[o] (device memory, local or a peer's mapped with fqg_ipc_open).  Returns when they are complete. */
