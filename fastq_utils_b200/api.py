@@ -120,6 +120,7 @@ def bind(L):
     L.fqg_shard_slots_result.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.fqg_side_copy.argtypes = [vp, vp, vp, sz]
     L.fqg_side_sync.argtypes = [vp]
+    L.fqg_side_copy_lane.argtypes = [vp, ctypes.c_int, vp, vp, sz]
     L.fqg_ipc_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.c_char_p]
     L.fqg_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
     L.fqg_ipc_close.argtypes = [vp, vp]
@@ -344,6 +345,9 @@ class FastqInfo:
 
     def side_copy(self, dst, src, n):
         _check(self._ctx, lib().fqg_side_copy(self._ctx, ctypes.c_void_p(dst), ctypes.c_void_p(src), n), "fqg_side_copy")
+
+    def side_copy_lane(self, lane, dst, src, n):
+        _check(self._ctx, lib().fqg_side_copy_lane(self._ctx, int(lane), ctypes.c_void_p(dst), ctypes.c_void_p(src), n), "fqg_side_copy_lane")
 
     def side_sync(self):
         _check(self._ctx, lib().fqg_side_sync(self._ctx), "fqg_side_sync")

@@ -218,6 +218,10 @@ extern "C" int fqg_side_copy(fqg_ctx* c, void* dst, const void* src, size_t n) {
   if (!c || ((!dst || !src) && n)) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->dev->side_copy(dst, src, n))
 }
+extern "C" int fqg_side_copy_lane(fqg_ctx* c, int lane, void* dst, const void* src, size_t n) {
+  if (!c || lane < 0 || lane > 7) return FQG_ERR_USAGE;
+  FQG_GUARD(c, c->dev->side_copy_lane(lane, dst, src, n))
+}
 extern "C" int fqg_side_sync(fqg_ctx* c) {
   if (!c) return FQG_ERR_USAGE;
   FQG_GUARD(c, c->dev->side_sync())

@@ -1171,6 +1171,7 @@ class FqCudaDevice : public FqDevice {
     for (auto e : free_ev_) cudaEventDestroy(e);
     cudaFree(tile_state_); if (stage_) cudaFree(stage_); if (small_pinned_) cudaFreeHost(small_pinned_);
     cudaEventDestroy(ev0_); cudaEventDestroy(ev1_); cudaEventDestroy(evx_); cudaEventDestroy(ev_pre_); cudaEventDestroy(ev_side_); cudaEventDestroy(ev_order_);
+    for (int k = 0; k < 7; k++) if (st_lane_[k]) { cudaStreamDestroy(st_lane_[k]); cudaEventDestroy(ev_lane_[k]); }
     cudaStreamDestroy(st_); cudaStreamDestroy(st2_);
   }
   const char* name() const override { return "cuda"; }
@@ -1311,6 +1312,8 @@ class FqCudaDevice : public FqDevice {
     for (int o = 0; o < FQ_ROUTE_MAX_WORLD; o++) P.route_region[o] = a.route_region[o];
     if (a.route_world && !lines_mode) return false; /* only the per-line mode routes names itself */
     if (side_marked_) { FQ_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_side_, 0)); side_marked_ = false; } /* copies out of the regions this pass overwrites */
+    for (int k = 0; k < 7; k++) if (lane_marked_ & (1u << k)) FQ_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_lane_[k], 0));
+    lane_marked_ = 0;
     for (uint32_t o = 0; o < P.route_world; o++) FQ_CUDA_CHECK(cudaMemsetAsync(P.route_region[o], 0, sizeof(FqRegionHdr), st_)); /* (flags are or-ed in; nblocks = 0 until the pass is through) */
     { const char* e = getenv("FQG_LANES_TUNE"); P.tune = e ? (uint32_t)atoi(e) : 0u; }
     FQ_CUDA_CHECK(cudaEventRecord(ev_pre_, st_));
@@ -1496,9 +1499,27 @@ class FqCudaDevice : public FqDevice {
     FQ_CUDA_CHECK(cudaEventRecord(ev_order_, their_side ? e->st2_ : e->st_));
     FQ_CUDA_CHECK(cudaStreamWaitEvent(my_side ? st2_ : st_, ev_order_, 0));
   }
-  void side_mark() override { FQ_CUDA_CHECK(cudaEventRecord(ev_side_, st2_)); side_marked_ = true; }
+  void side_mark() override {
+    FQ_CUDA_CHECK(cudaEventRecord(ev_side_, st2_)); side_marked_ = true;
+    for (int k = 0; k < 7; k++) if (lane_dirty_ & (1u << k)) { FQ_CUDA_CHECK(cudaEventRecord(ev_lane_[k], st_lane_[k])); lane_marked_ |= 1u << k; }
+    lane_dirty_ = 0;
+  }
+  void side_copy_lane(int lane, void* dst, const void* src, size_t n) override {
+    if (lane <= 0) return side_copy(dst, src, n);
+    const int k = lane - 1;
+    if (!st_lane_[k]) {
+      FQ_CUDA_CHECK(cudaStreamCreateWithFlags(&st_lane_[k], cudaStreamNonBlocking));
+      FQ_CUDA_CHECK(cudaEventCreateWithFlags(&ev_lane_[k], cudaEventDisableTiming));
+    }
+    if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, st_lane_[k]));
+    lane_dirty_ |= 1u << k; lane_unsynced_ |= 1u << k;
+  }
   void side_copy(void* dst, const void* src, size_t n) override { if (n) FQ_CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, st2_)); }
-  void side_sync() override { FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); }
+  void side_sync() override {
+    FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
+    for (int k = 0; k < 7; k++) if (lane_unsynced_ & (1u << k)) FQ_CUDA_CHECK(cudaStreamSynchronize(st_lane_[k]));
+    lane_unsynced_ = 0;
+  }
   void* ipc_alloc(size_t n, uint8_t handle[64]) override {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     void* p = nullptr; FQ_CUDA_CHECK(cudaSetDevice(dev_)); FQ_CUDA_CHECK(cudaMalloc(&p, n ? n : 1));
@@ -1576,7 +1597,7 @@ class FqCudaDevice : public FqDevice {
     FQ_CUDA_CHECK(cudaStreamSynchronize(st_)); FQ_CUDA_CHECK(cudaStreamSynchronize(st2_));
     /* FQG_TIMELINE=<file>: where every timed launch of this batch sat, in ms after the batch's first one (a development aid) */
     const char* tl = getenv("FQG_TIMELINE");
-    FILE* tf = tl && *tl && g_origin ? fopen(tl, "a") : nullptr;
+    FILE* tf = tl && *tl && g_origin ? fopen((std::string(tl) + "." + std::to_string(dev_)).c_str(), "a") : nullptr; /* one file per device */
     if (tf) fprintf(tf, "# device %d object %p, %zu launches\n", dev_, (void*)this, pending_.size());
     for (auto& p : pending_) {
       float ms = 0; FQ_CUDA_CHECK(cudaEventElapsedTime(&ms, p.a, p.b));
@@ -1601,6 +1622,8 @@ class FqCudaDevice : public FqDevice {
   cudaEvent_t evx_ = nullptr;
   cudaEvent_t ev_side_ = nullptr; bool side_marked_ = false;
   cudaEvent_t ev_order_ = nullptr;
+  cudaStream_t st_lane_[7] = {}; cudaEvent_t ev_lane_[7] = {}; /* more copy streams (side_copy_lane) */
+  uint32_t lane_dirty_ = 0, lane_marked_ = 0, lane_unsynced_ = 0;
   cudaEvent_t ev_pre_ = nullptr; /* main stream just before the latest clean-data pass: what the side stream waits for when it works beside that pass */
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   unsigned long long* tile_state_ = nullptr; uint32_t* ticket_ = nullptr; uint32_t max_tiles_ = 0;

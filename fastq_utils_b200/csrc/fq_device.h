@@ -192,6 +192,7 @@ class FqDevice {
   virtual void order_after(bool /*my_side*/, FqDevice& /*earlier*/, bool /*their_side*/) {}
   virtual void side_copy(void* dst, const void* src, size_t n) = 0;
   virtual void side_sync() = 0;
+  virtual void side_copy_lane(int /*lane*/, void* dst, const void* src, size_t n) { side_copy(dst, src, n); }
   /* memory that other processes can map (CUDA IPC); devices without it throw */
   virtual void* ipc_alloc(size_t n, uint8_t handle[64]) { (void)n; (void)handle; throw std::runtime_error("this device has no inter-process memory"); }
   virtual void* ipc_open(const uint8_t handle[64]) { (void)handle; throw std::runtime_error("this device has no inter-process memory"); }

@@ -60,6 +60,8 @@ class ShardedFastqInfo:
         # the copy engines move the packed regions; FQG_P2P_STORES=1: the pack kernel stores into the owners' arenas itself (A/B)
         self.p2p_stores = os.environ.get("FQG_P2P_STORES", "0") not in ("", "0")
         self._owner_beside = int(os.environ.get("FQG_OWNER_BESIDE", "0") or 0)  # (A/B) 1: the owner's kernels beside the running pass, 2: the inserts only
+        # more copy streams for the peers' regions of a round (A/B; measured with four ranks: no faster than one stream, the links are the limit)
+        self._copy_lanes = max(0, min(7, int(os.environ.get("FQG_COPY_LANES", "0") or 0)))
         self._pending_insert = None
         self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage, self._zero = None, None, False, False, None, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
@@ -81,6 +83,18 @@ class ShardedFastqInfo:
         return "one all-to-all over NCCL after the pass"
 
     # ------------------------------------------------------------------ helpers
+    def _mine(self, rep, local_key, dup, unp, claimed, pair, with_hist=False):
+        """this rank's part of the merged report"""
+        f0, f1 = rep.file[0], rep.file[1]
+        mine = {"key": local_key, "dup": dup, "unp": unp, "claimed": claimed,
+                "err": bytes(ctypes.string_at(ctypes.addressof(rep.error), ctypes.sizeof(api.Error))) if local_key != KEY_NONE else None,
+                "nrec": (int(f0.n_records), int(f1.n_records)), "num_rds": int(f0.num_rds), "min_rl": int(f0.min_rl), "max_rl": int(f0.max_rl),
+                "rl1": (int(f1.min_rl), int(f1.max_rl)), "min_q": int(f0.min_qual), "max_q": int(f0.max_qual), "names": int(rep.n_index_entries),
+                "mem": int(rep.index_mem) - 8, "sniff": ((int(f0.sniff_format), int(f0.color_space)), (int(f1.sniff_format), int(f1.color_space)))}
+        if with_hist:
+            mine["hist"] = _local_hist(self.ctx, f0, f1)
+        return mine
+
     def _gather(self, obj):
         if self.world == 1:
             return [obj]
@@ -185,13 +199,13 @@ class ShardedFastqInfo:
         expected = (lfs + virt - skip[r] + (skip[r + 1] if r < W - 1 else 0)) // 4
         return expected, total_records
 
-    def _guess_phase(self, ptr, nbytes):
+    def _guess_phase(self, ptr, nbytes, want=1 << 14):
         """Line class (0 header, 1 sequence, 2 plus, 3 quality) of the line this range starts in, from the range's own first lines:
         a complete line that is exactly "+" is a plus line.  Returns (ok, class, ends of the first four lines, ends with LF, bytes
         per record over the first complete records, raw length of the first complete sequence line)."""
         if nbytes < 4096:
             return (False, 0, [KEY_NONE] * 4, True, 0.0, 0, b"")
-        k = min(nbytes, 1 << 18)
+        k = min(nbytes, want)
         head = bytes(_as_tensor(ptr, k, self.tdev).cpu().numpy())
         last = bytes(_as_tensor(ptr + nbytes - 1, 1, self.tdev).cpu().numpy())
         ends, pos = [], -1
@@ -206,6 +220,8 @@ class ShardedFastqInfo:
                 cls = (2 - i) % 4
                 break
         if cls is None or len(ends) < 5:
+            if want < (1 << 18) and nbytes > want:  # long lines: look further (short reads are answered by the first 16 KiB)
+                return self._guess_phase(ptr, nbytes, 1 << 18)
             return (False, 0, [KEY_NONE] * 4, last == b"\n", 0.0, 0, b"")
         k = (len(ends) - 1) // 4
         seq = next(ends[i] - ends[i - 1] for i in range(1, 5) if (cls + i) % 4 == 1)
@@ -368,18 +384,20 @@ class ShardedFastqInfo:
         pl = self._plan[f]
         j, region = pl["round"], pl["region"]
         have = j < self.ctx.route_chunks(f)[0]
-        _dbg(f"rank {r} file {f} pass round {j} of {pl['rounds']} have={have} chunks={self.ctx.route_chunks(f)}")
+        if os.environ.get("FQG_DEBUG_ROUTE"):
+            _dbg(f"rank {r} file {f} pass round {j} of {pl['rounds']} have={have} chunks={self.ctx.route_chunks(f)}")
         off = pl["base"] + (j * W + r) * region
         st = self._stage.data_ptr()
         t1 = time.perf_counter()
         for d in range(W):
             o = (r + d) % W
             dst = (self._arena[0] if o == r else self._peer[o]) + off
+            lane = 0 if (d == 0 or not self._copy_lanes) else 1 + (d - 1) % self._copy_lanes  # (FQG_COPY_LANES: the peers' regions on copy streams side by side)
             if have:
-                self.ctx.side_copy(dst, st + (o * 2 + j % 2) * region, region)
+                self.ctx.side_copy_lane(lane, dst, st + (o * 2 + j % 2) * region, region)
             else:
-                self.ctx.side_copy(dst, self._zero.data_ptr(), 16)
-            self._send_flag(o, f, j)
+                self.ctx.side_copy_lane(lane, dst, self._zero.data_ptr(), 16)
+            self._send_flag(o, f, j, lane)
         self.ctx.side_mark()
         self.host_ms["pack"] += (time.perf_counter() - t1) * 1e3
         # The owner's kernel waits for its sources on the device (their flag words).  It takes the whole device between two passes:
@@ -389,7 +407,7 @@ class ShardedFastqInfo:
         if between:
             self.shard.order_after(True, ctx, False)
         self._owner_round(self._arena[0] + pl["base"] + j * W * region, region, pl["nblocks"], pl["stride"], pl["units"], f, beside and not between, flag_round=j)
-        if between:
+        if between and j + 2 < pl["rounds"]:  # (the last rounds have no pass behind them that would have to wait: the next file starts at once)
             ctx.order_after(False, self.shard, True)
         pl["round"] += 1
 
@@ -399,9 +417,11 @@ class ShardedFastqInfo:
         W, r, f = self.world, self.rank, self._cur
         pl = self._plan[f]
         region, cap = pl["left_region"], pl["left_stride"]
-        _dbg(f"rank {r} file {f} left round, names left {self.ctx.names_new(f)}")
-        self.ctx.side_sync()  # the staging regions are free: every copy out of them is done
-        _dbg(f"rank {r} file {f} left round: copies done")
+        if os.environ.get("FQG_DEBUG_ROUTE"):
+            _dbg(f"rank {r} file {f} left round, names left {self.ctx.names_new(f)}")
+        if self._copy_lanes:
+            self.ctx.side_sync()  # the staging regions are free: every copy out of them is done
+        # (one copy stream: the pack kernel below runs on it, behind the copies out of the staging regions it overwrites)
         st = self._stage.data_ptr()
         off = pl["left_base"] + r * region
         self.ctx.names_pack_slots(f, [self._arena[0] + off if o == r else st + o * region for o in range(W)], cap, pl["units"])
@@ -410,15 +430,16 @@ class ShardedFastqInfo:
             if o != r:
                 self.ctx.side_copy(self._peer[o] + off, st + o * region, region)
             self._send_flag(o, f, pl["rounds"])
+        self.ctx.side_mark()  # the next file's first pass writes into the staging regions: behind these copies
         self._owner_round(self._arena[0] + pl["left_base"], region, 1, cap, pl["units"], f, False, flag_round=pl["rounds"])
 
     def _flag_off(self, f, j):
         return 8 * ((f * FLAG_ROUNDS + j) * self.world)
 
-    def _send_flag(self, o, f, j):
+    def _send_flag(self, o, f, j, lane=0):
         """behind the bytes of round j for owner o (same stream of copies): the word that tells o's kernel they are there"""
         dst = (self._arena[0] if o == self.rank else self._peer[o]) + self._flag_off(f, j) + 8 * self.rank
-        self.ctx.side_copy(dst, self._flagvals.data_ptr() + 8 * j, 8)
+        self.ctx.side_copy_lane(lane, dst, self._flagvals.data_ptr() + 8 * j, 8)
 
     def _ensure_arena(self, need):
         """Peer-writable receive memory (CUDA IPC over NVLink): `need` bytes on every rank, mapped by every other rank.  Collective;
@@ -593,6 +614,7 @@ class ShardedFastqInfo:
         self._keep = []
         lap("reset")
         pair = self.mode == api.MODE_INDEX_PAIR
+        allr = None  # every rank's report, once gathered
         again = dict(name=name, ptr2=ptr2, nbytes2=nbytes2, name2=name2, empty_ok=empty_ok, no_enc_ok=no_enc_ok, _exact=True)
         routed = self.shard is not None and self.pipeline
         self.rounds_done = 0
@@ -633,7 +655,9 @@ class ShardedFastqInfo:
                 inserted, equal, overflow, claimed, unpaired = self.shard.shard_slots_result()
                 broken = any(ctx.route_chunks(f)[1] for f, _, _ in files)  # a chunk whose names the pass should have routed went to the per-record kernels
                 mine_bad = rep.error.code != 0 or cut_short or equal > 0 or unpaired > 0 or overflow or broken or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
-                sums = self._gather((bool(mine_bad), inserted, claimed, int(rep.n_index_entries), int(rep.file[1].n_records)))
+                # (the merge below needs every rank's report: it travels in the same gather)
+                sums = self._gather((bool(mine_bad), inserted, claimed, int(rep.n_index_entries), int(rep.file[1].n_records),
+                                     None if mine_bad else self._mine(rep, KEY_NONE, (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), claimed, pair, with_hist=True)))
                 bad = any(x[0] for x in sums)
                 tot_ins, tot_cl, tot_names, tot_mates = (sum(x[k] for x in sums) for k in (1, 2, 3, 4))
                 _dbg(f"rank {r} verdict: error {rep.error.code} cut_short {cut_short} inserted {inserted} equal {equal} overflow {overflow} claimed {claimed} unpaired {unpaired} broken {broken} "
@@ -651,6 +675,8 @@ class ShardedFastqInfo:
             if bad:
                 self.exact_reruns += 1
                 return self.run_device(ptr, nbytes, **again)  # an error, a duplicate name or a wrong guess: the exact path decides
+            if routed:
+                allr = [x[5] for x in sums]
             local_key, T0, T1 = KEY_NONE, 0, 0
             dup, unp = (KEY_NONE, 0, b""), (KEY_NONE, 0, b"")
             lap("verdict")
@@ -701,13 +727,8 @@ class ShardedFastqInfo:
                 if sum(self._gather(coll)):
                     raise RuntimeError("internal: an owner could not judge an equal hash although the name bytes travelled")
         # -- 4. merge
-        f0, f1 = rep.file[0], rep.file[1]
-        mine = {"key": local_key, "dup": dup, "unp": unp, "claimed": claimed,
-                "err": bytes(ctypes.string_at(ctypes.addressof(rep.error), ctypes.sizeof(api.Error))) if local_key != KEY_NONE else None,
-                "nrec": (int(f0.n_records), int(f1.n_records)), "num_rds": int(f0.num_rds), "min_rl": int(f0.min_rl), "max_rl": int(f0.max_rl),
-                "rl1": (int(f1.min_rl), int(f1.max_rl)), "min_q": int(f0.min_qual), "max_q": int(f0.max_qual), "names": int(rep.n_index_entries),
-                "mem": int(rep.index_mem) - 8, "sniff": ((int(f0.sniff_format), int(f0.color_space)), (int(f1.sniff_format), int(f1.color_space)))}
-        allr = self._gather(mine)
+        if allr is None:
+            allr = self._gather(self._mine(rep, local_key, dup, unp, claimed, pair))
         N0, N1 = sum(a["nrec"][0] for a in allr), sum(a["nrec"][1] for a in allr)
         names_total = sum(a["names"] for a in allr)
         left = names_total - sum(a["claimed"] for a in allr)
@@ -761,6 +782,18 @@ class ShardedFastqInfo:
         med = MAX_READ_LENGTH
         if m0.num_rds == 1 and not (pair and T0 > 0):
             med = int(m0.min_rl)
+        elif m0.num_rds > 1 and lo <= hi < MAX_READ_LENGTH and all("hist" in a for a in allr):
+            # every rank's histogram came with its report: summed here
+            total, acc, med = [0] * (hi - lo + 1), 0, MAX_READ_LENGTH
+            for a in allr:
+                if a["hist"] is not None:
+                    for i, c in enumerate(a["hist"][1]):
+                        total[a["hist"][0] - lo + i] += c
+            for i, c in enumerate(total):
+                acc += c
+                if acc > m0.num_rds // 2:
+                    med = lo + i
+                    break
         elif m0.num_rds > 1 and lo <= hi < MAX_READ_LENGTH:
             h = torch.tensor(self.ctx.hist_range(0, lo, hi), dtype=torch.int64, device=self.tdev)
             if W > 1:
@@ -774,6 +807,16 @@ class ShardedFastqInfo:
         if r == 0:
             out["transcript"] = self.ctx.render(merged, name, name2 if pair else None, empty_ok=empty_ok, no_enc_ok=no_enc_ok)
         return out
+
+
+def _local_hist(ctx, f0, f1):
+    """this rank's read lengths (src/fastq_info.c:39-55 counts the mates into the same histogram): (lowest length, counts)"""
+    lo, hi = int(f0.min_rl), int(f0.max_rl)
+    if int(f1.max_rl) > 0:
+        lo, hi = min(lo, int(f1.min_rl)), max(hi, int(f1.max_rl))
+    if not (lo <= hi < MAX_READ_LENGTH):
+        return None
+    return (lo, [int(x) for x in ctx.hist_range(0, lo, hi)])
 
 
 def _dbg(msg):

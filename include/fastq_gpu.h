@@ -276,6 +276,10 @@ int fqg_shard_slots_result(fqg_ctx* ctx, uint64_t* inserted, uint64_t* equal_has
  * stay with the clean-data pass), and the wait for it */
 int fqg_side_copy(fqg_ctx* ctx, void* device_dst, const void* device_src, size_t bytes);
 int fqg_side_sync(fqg_ctx* ctx);
+/* the same on one of a few more copy streams (lane 1..7; lane 0 is the side stream itself): the regions for different owners travel
+ * side by side on several copy engines instead of one after the other.  A lane keeps the order of its own copies (a region, then its
+ * flag word); fqg_side_mark and fqg_side_sync cover every lane. */
+int fqg_side_copy_lane(fqg_ctx* ctx, int lane, void* device_dst, const void* device_src, size_t bytes);
 int fqg_ipc_alloc(fqg_ctx* ctx, size_t bytes, void** device_ptr, uint8_t handle[64]);
 int fqg_ipc_open(fqg_ctx* ctx, const uint8_t handle[64], void** device_ptr);
 int fqg_ipc_close(fqg_ctx* ctx, void* device_ptr);

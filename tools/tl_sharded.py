@@ -26,8 +26,8 @@ for k in range(steps):
     if k == steps - 1:
         run.ctx.kernel_stats(); run.shard.kernel_stats()  # collect what is pending
         os.environ["FQG_TIMELINE"] = tl
-        if os.path.exists(tl):
-            os.remove(tl)
+        if os.path.exists(tl + ".0"):
+            os.remove(tl + ".0")
     run.phase_ms = {}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -39,7 +39,7 @@ run.ctx.kernel_stats(); run.shard.kernel_stats()
 os.environ.pop("FQG_TIMELINE")
 names = list(fq.KERNEL_CLASSES)
 rows = []
-for line in open(tl):
+for line in open(tl + ".0"):
     if line.startswith("#"):
         continue
     c, s, a, b = line.split()
