@@ -461,7 +461,8 @@ def main():
         import glob
         import re
         if dom == "lanes":
-            f = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_lanes_*ncu_summary.txt")), key=os.path.getmtime)[-1]
+            f = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_lanes_*ncu_summary.txt")),
+                       key=lambda x: (int(re.match(r"r(\d+)", os.path.basename(x)).group(1)), os.path.basename(x)))[-1]  # the latest round's
             txt = open(f, errors="ignore").read()
             rd = float(re.search(r"dram__bytes_read\.sum\s+([\d.]+)\s+Gbyte", txt).group(1))
             wr = re.search(r"dram__bytes_write\.sum\s+([\d.]+)\s+(M|G)byte", txt)
