@@ -1501,7 +1501,12 @@ class FqCudaDevice : public FqDevice {
   }
   void side_mark() override {
     FQ_CUDA_CHECK(cudaEventRecord(ev_side_, st2_)); side_marked_ = true;
-    for (int k = 0; k < 7; k++) if (lane_dirty_ & (1u << k)) { FQ_CUDA_CHECK(cudaEventRecord(ev_lane_[k], st_lane_[k])); lane_marked_ |= 1u << k; }
+    /* (the side stream joins the lanes as well: what it does next — the pack kernel of a file's last round writes into the staging
+     * regions — comes behind every copy out of them, without the host waiting for anything) */
+    for (int k = 0; k < 7; k++) if (lane_dirty_ & (1u << k)) {
+      FQ_CUDA_CHECK(cudaEventRecord(ev_lane_[k], st_lane_[k])); lane_marked_ |= 1u << k;
+      FQ_CUDA_CHECK(cudaStreamWaitEvent(st2_, ev_lane_[k], 0));
+    }
     lane_dirty_ = 0;
   }
   void side_copy_lane(int lane, void* dst, const void* src, size_t n) override {

@@ -20,6 +20,7 @@ files it is refused on every rank (the single-GPU path handles it).
 """
 import ctypes
 import os
+import pickle
 import time
 
 import torch
@@ -59,9 +60,14 @@ class ShardedFastqInfo:
         self.p2p = os.environ.get("FQG_P2P", "1" if self.tdev.type == "cuda" else "0") not in ("", "0")
         # the copy engines move the packed regions; FQG_P2P_STORES=1: the pack kernel stores into the owners' arenas itself (A/B)
         self.p2p_stores = os.environ.get("FQG_P2P_STORES", "0") not in ("", "0")
+        # FQG_NCCL_GATHER=0: the small gathers over gloo (A/B)
+        self._nccl_gather = (self.world > 1 and self.tdev.type == "cuda" and dist.get_backend() == "nccl" and os.environ.get("FQG_NCCL_GATHER", "1") not in ("", "0"))
+        self._gbuf = None
         self._owner_beside = int(os.environ.get("FQG_OWNER_BESIDE", "0") or 0)  # (A/B) 1: the owner's kernels beside the running pass, 2: the inserts only
-        # more copy streams for the peers' regions of a round (A/B; measured with four ranks: no faster than one stream, the links are the limit)
-        self._copy_lanes = max(0, min(7, int(os.environ.get("FQG_COPY_LANES", "0") or 0)))
+        # One copy stream per peer for the regions of a round (FQG_COPY_LANES=0: all on the side stream).  Measured on 8 B200s: 43.3 ms
+        # per job with one stream — seven copies of 60 MB one after the other take longer than the pass they should hide behind —
+        # 38.8 ms with seven; with four ranks no difference (34.2 / 34.5 ms).
+        self._copy_lanes = max(0, min(7, int(os.environ.get("FQG_COPY_LANES", str(self.world - 1)) or 0)))
         self._pending_insert = None
         self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage, self._zero = None, None, False, False, None, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
@@ -96,8 +102,30 @@ class ShardedFastqInfo:
         return mine
 
     def _gather(self, obj):
+        """Small host objects, one per rank, to every rank.  On GPUs: pickled into a fixed 16 KiB slot and gathered by one NCCL
+        all-gather (the device is idle at the two places a job gathers — before its first pass and after its last owner kernel; a
+        gloo gather of Python objects costs 0.7 ms with four ranks and 1 ms with eight, this 0.15 ms).  An object that does not
+        fit says so in its slot and every rank repeats the gather over gloo."""
         if self.world == 1:
             return [obj]
+        if self._nccl_gather:
+            blob = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+            n = len(blob) if len(blob) <= GATHER_SLOT - 8 else GATHER_SLOT  # (GATHER_SLOT: does not fit)
+            if self._gbuf is None:
+                self._gbuf = (torch.zeros(GATHER_SLOT, dtype=torch.uint8).pin_memory(), torch.zeros(GATHER_SLOT, dtype=torch.uint8, device=self.tdev),
+                              torch.zeros(GATHER_SLOT * self.world, dtype=torch.uint8, device=self.tdev), torch.zeros(GATHER_SLOT * self.world, dtype=torch.uint8).pin_memory())
+            mine_h, mine_d, all_d, all_h = self._gbuf
+            mine_h[:8] = torch.frombuffer(bytearray(int(n).to_bytes(8, "little")), dtype=torch.uint8)
+            if n < GATHER_SLOT:
+                mine_h[8:8 + n] = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+            mine_d.copy_(mine_h, non_blocking=True)
+            dist.all_gather_into_tensor(all_d, mine_d)
+            all_h.copy_(all_d, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            raw = all_h.numpy()
+            sizes = [int.from_bytes(raw[k * GATHER_SLOT:k * GATHER_SLOT + 8].tobytes(), "little") for k in range(self.world)]
+            if all(x < GATHER_SLOT for x in sizes):
+                return [pickle.loads(raw[k * GATHER_SLOT + 8:k * GATHER_SLOT + 8 + sizes[k]].tobytes()) for k in range(self.world)]
         out = [None] * self.world
         dist.all_gather_object(out, obj, group=self._cpu_group)
         return out
@@ -419,9 +447,8 @@ class ShardedFastqInfo:
         region, cap = pl["left_region"], pl["left_stride"]
         if os.environ.get("FQG_DEBUG_ROUTE"):
             _dbg(f"rank {r} file {f} left round, names left {self.ctx.names_new(f)}")
-        if self._copy_lanes:
-            self.ctx.side_sync()  # the staging regions are free: every copy out of them is done
-        # (one copy stream: the pack kernel below runs on it, behind the copies out of the staging regions it overwrites)
+        # (the pack kernel below runs on the side stream, behind the copies out of the staging regions it overwrites: fqg_side_mark
+        # of the last round joined the copy lanes into that stream)
         st = self._stage.data_ptr()
         off = pl["left_base"] + r * region
         self.ctx.names_pack_slots(f, [self._arena[0] + off if o == r else st + o * region for o in range(W)], cap, pl["units"])
@@ -807,6 +834,9 @@ class ShardedFastqInfo:
         if r == 0:
             out["transcript"] = self.ctx.render(merged, name, name2 if pair else None, empty_ok=empty_ok, no_enc_ok=no_enc_ok)
         return out
+
+
+GATHER_SLOT = 16384  # bytes per rank in the NCCL gather of small host objects
 
 
 def _local_hist(ctx, f0, f1):

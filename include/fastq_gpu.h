@@ -278,7 +278,7 @@ int fqg_side_copy(fqg_ctx* ctx, void* device_dst, const void* device_src, size_t
 int fqg_side_sync(fqg_ctx* ctx);
 /* the same on one of a few more copy streams (lane 1..7; lane 0 is the side stream itself): the regions for different owners travel
  * side by side on several copy engines instead of one after the other.  A lane keeps the order of its own copies (a region, then its
- * flag word); fqg_side_mark and fqg_side_sync cover every lane. */
+ * flag word); fqg_side_mark and fqg_side_sync cover every lane, and fqg_side_mark makes the side stream itself wait for the lanes. */
 int fqg_side_copy_lane(fqg_ctx* ctx, int lane, void* device_dst, const void* device_src, size_t bytes);
 int fqg_ipc_alloc(fqg_ctx* ctx, size_t bytes, void** device_ptr, uint8_t handle[64]);
 int fqg_ipc_open(fqg_ctx* ctx, const uint8_t handle[64], void** device_ptr);
