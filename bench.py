@@ -106,6 +106,41 @@ def time_reference(files, argv_head):
             os.unlink(p)
 
 
+def time_gz_cli(files, argv_head):
+    """The whole command line on gzip files, host inflate included (north_star: reported separately): `fastq_info_gpu` (zlib on a helper
+    thread into pinned pieces, copied and validated while the next piece inflates) against the reference binary on the same files.
+    Wall clock of each process — for ours that includes loading CUDA and creating the context.  The two transcripts must be equal."""
+    import zlib
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    cli = os.path.join(ROOT, "fastq_utils_b200", "fastq_info_gpu")
+    ref = reference_binary()
+    paths, gz_bytes = [], 0
+    try:
+        for i, data in enumerate(files):
+            path = os.path.join(shm, f"fqg_bench_{os.getpid()}_{i + 1}.fastq.gz")
+            co = zlib.compressobj(1, zlib.DEFLATED, 31)
+            with open(path, "wb") as fh:
+                fh.write(co.compress(bytes(data)))
+                fh.write(co.flush())
+            gz_bytes += os.path.getsize(path)
+            paths.append(path)
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "fastq_utils_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        t0 = time.perf_counter()
+        ours = subprocess.run([cli] + argv_head + paths, capture_output=True, env=env)
+        t_ours = time.perf_counter() - t0
+        res = {"ours_wall_s": t_ours, "ours_exit_status": ours.returncode, "gz_bytes": gz_bytes}
+        if ref:
+            t0 = time.perf_counter()
+            r = subprocess.run([ref] + argv_head + paths, capture_output=True)
+            res.update({"reference_wall_s": time.perf_counter() - t0, "reference_exit_status": r.returncode,
+                        "transcripts_equal": (r.returncode, r.stdout, r.stderr) == (ours.returncode, ours.stdout, ours.stderr)})
+        return res
+    finally:
+        for p in paths:
+            if os.path.exists(p):
+                os.unlink(p)
+
+
 def host_sample(workload, n):
     """The first n records (pairs) of the workload as host bytes, from the numpy twin of the device generator: libfastq_gpu.so is not
     loaded by the reference arm."""
@@ -576,6 +611,22 @@ def main():
                                    "sample": f"first {ns} {'pairs' if wl == 'illumina_pe' else 'records'} ({sb / 1e6:.0f} MB plain text) of the workload; reference is single-threaded; host nproc={os.cpu_count()}"}
         except Exception as ex:
             out["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
+        # ---------------- the command line on gzip files, host inflate included (a quarter of the CPU baseline's sample)
+        if not a.no_extras and wl in ("illumina_pe", "illumina_se") and out["cpu_baseline"].get("value"):
+            try:
+                from fastq_utils_b200 import synth as _synth
+                k = min(ns, 256 * 1024) * _synth.ILL_REC
+                part = [f[:k] for f in files]
+                g = time_gz_cli(part, head)
+                pb = sum(len(f) for f in part)
+                g.update({"plain_bytes": pb, "ours_GBps_inflated": pb / g["ours_wall_s"] / 1e9,
+                          "note": "wall clock of the whole process on .gz operands: zlib inflate on the host (one thread, as in the reference), pinned pieces, H2D, kernels; "
+                                  "ours includes CUDA start-up; GB/s counts inflated bytes"})
+                if g.get("reference_wall_s"):
+                    g["reference_GBps_inflated"] = pb / g["reference_wall_s"] / 1e9
+                out.setdefault("also", {})["gz_cli"] = g
+            except Exception as ex:
+                out.setdefault("also", {})["gz_cli"] = {"error": str(ex)[:300]}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

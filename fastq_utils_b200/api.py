@@ -44,6 +44,14 @@ class Transcript(ctypes.Structure):
                 ("err", ctypes.c_void_p), ("err_len", ctypes.c_size_t)]
 
 
+class StreamIO(ctypes.Structure):
+    """fqg_stream_io: the caller's open / read / close (include/fastq_gpu.h)"""
+    _fields_ = [("user", ctypes.c_void_p),
+                ("open", ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p)),
+                ("read", ctypes.CFUNCTYPE(ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)),
+                ("close", ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p))]
+
+
 class KernelStat(ctypes.Structure):
     _fields_ = [("ms", ctypes.c_double), ("launches", ctypes.c_uint64), ("bytes", ctypes.c_uint64), ("items", ctypes.c_uint64)]
 
@@ -87,6 +95,10 @@ def bind(L):
     L.fqg_transcript_free.restype = None
     L.fqg_fastq_info_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, vp, sz, ci, sz, ctypes.POINTER(Transcript)]
     L.fqg_reader_tool_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, ci, sz, ctypes.POINTER(Transcript)]
+    L.fqg_trim_poly_at_stream.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(StreamIO), ci, ctypes.POINTER(Transcript),
+                                          ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_char_p)]
+    L.fqg_buffer_free.argtypes = [vp]
+    L.fqg_buffer_free.restype = None
     L.fqg_kernel_stats.argtypes = [vp, ci, ctypes.POINTER(KernelStat)]
     L.fqg_kernel_stats_reset.argtypes = [vp]
     L.fqg_prescan_device.argtypes = [vp, ci, vp, sz, ci, ctypes.POINTER(u64), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(u64)]
@@ -169,6 +181,64 @@ def reader_tool(tool, argv, data1=None, chunk=0, device=0):
     if st != 0:
         raise RuntimeError(f"fqg_reader_tool_mem failed with status {st}")
     return _take(tr)
+
+
+def _read_inflated(path):
+    """a file as the reference's gzopen/gzread deliver it: gzip members inflated, anything else as it is"""
+    import zlib
+    raw = open(path, "rb").read()
+    if raw[:2] != b"\x1f\x8b":
+        return raw
+    out = []
+    while raw[:2] == b"\x1f\x8b":
+        d = zlib.decompressobj(31)
+        out.append(d.decompress(raw))
+        raw = d.unused_data
+    return b"".join(out)
+
+
+def trim_poly_at(argv, files=None, device=0, write=False, _lib=None):
+    """`fastq_trim_poly_at argv...` (src/fastq_trim_poly_at.c) → (exit status, stdout, stderr, name of the output file or None, its
+    inflated contents).  files: operand name → inflated bytes (a missing name cannot be opened); None reads the named file from disk.
+    write=True gzips the result into the output file like the reference does (level 4, src/fastq_trim_poly_at.c:201)."""
+    full = [b"fastq_trim_poly_at"] + [a.encode("latin-1") if isinstance(a, str) else a for a in argv]
+    arr = (ctypes.c_char_p * (len(full) + 1))(*full, None)
+    state = {}
+
+    def _open(user, name):
+        try:
+            data = files[name.decode("latin-1")] if files is not None else _read_inflated(name.decode("latin-1"))
+        except (KeyError, OSError):
+            return None
+        h = len(state) + 1
+        state[h] = [data, 0]
+        return h
+
+    def _read(user, h, buf, cap):
+        data, pos = state[h]
+        k = min(cap, len(data) - pos)
+        ctypes.memmove(buf, data[pos:pos + k], k)
+        state[h][1] = pos + k
+        return k
+
+    def _close(user, h):
+        state.pop(h, None)
+    io = StreamIO(None, StreamIO._fields_[1][1](_open), StreamIO._fields_[2][1](_read), StreamIO._fields_[3][1](_close))
+    tr, buf, n, name = Transcript(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_char_p()
+    L = _lib if _lib is not None else lib()  # (_lib: the tests' stand-in library)
+    st = L.fqg_trim_poly_at_stream(len(full), arr, ctypes.byref(io), device, ctypes.byref(tr), ctypes.byref(buf), ctypes.byref(n), ctypes.byref(name))
+    if st != 0:
+        raise RuntimeError(f"fqg_trim_poly_at_stream failed with status {st}")
+    data = ctypes.string_at(buf, n.value) if buf else b""
+    L.fqg_buffer_free(buf)
+    oname = name.value.decode("latin-1") if name.value is not None else None
+    rc, out, err = tr.rc, ctypes.string_at(tr.out, tr.out_len).decode("latin-1"), ctypes.string_at(tr.err, tr.err_len).decode("latin-1")
+    L.fqg_transcript_free(ctypes.byref(tr))
+    if write and oname is not None:
+        import gzip
+        with gzip.open(oname, "wb", compresslevel=4) as fh:
+            fh.write(data)
+    return rc, out, err, oname, data
 
 
 class FastqInfo:

@@ -1134,6 +1134,16 @@ fq_count_n_kernel(const uint8_t* __restrict__ data, const FqLine* __restrict__ l
     if (lane == 0) { out2[2 * k] = cnt; out2[2 * k + 1] = nul; }
   }
 }
+/* fastq_trim_poly_at (src/fastq_trim_poly_at.c:77-115): one thread per sequence line (the scans stop at the first other base) */
+__global__ void __launch_bounds__(256)
+fq_poly_at_kernel(const uint8_t* __restrict__ data, const FqLine* __restrict__ lines, uint32_t n, uint32_t* out3) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const FqLine L = lines[k];
+    uint32_t rl, a, b;
+    fq_poly_at(data + L.off, L.len, &rl, &a, &b);
+    out3[3 * k] = rl; out3[3 * k + 1] = a; out3[3 * k + 2] = b;
+  }
+}
 struct WordsParams { uint32_t* dst; uint32_t n; uint32_t w[32]; };
 __global__ void fq_set_words_kernel(const WordsParams P) { if (threadIdx.x < P.n) P.dst[threadIdx.x] = P.w[threadIdx.x]; }
 
@@ -1567,6 +1577,12 @@ class FqCudaDevice : public FqDevice {
     if (!n) return;
     int grid = (int)std::min<uint32_t>((n + 7) / 8, (uint32_t)sms_ * 8);
     fq_count_n_kernel<<<grid, 256, 0, st_>>>(data, seq_lines, n, out2);
+    launched();
+  }
+  void poly_at(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out3) override {
+    if (!n) return;
+    int grid = (int)std::min<uint32_t>((n + 255) / 256, (uint32_t)sms_ * 8);
+    fq_poly_at_kernel<<<grid, 256, 0, st_>>>(data, seq_lines, n, out3);
     launched();
   }
   void explain(const uint8_t* data, const FqLine* L, const FqRecCtx& cx, FqRecOut* out_dev) override {

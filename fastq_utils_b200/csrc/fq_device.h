@@ -213,6 +213,8 @@ class FqDevice {
   /* fastq_filter_n's predicate (src/fastq_filter_n.c:77-86) for n sequence lines of a chunk: out2[2k] = 'N' / 'n' bytes before the first LF or
    * NUL of line k, out2[2k+1] = strlen of the line (bytes before the first NUL, terminator included) */
   virtual void count_n(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out2) = 0;
+  /* fastq_trim_poly_at: out3[3k..] = read_len, poly-A/N bytes at the line's end, poly-T/N bytes at its start (fq_poly_at) */
+  virtual void poly_at(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out3) = 0;
   /* details of one record for the error message */
   virtual void explain(const uint8_t* data, const FqLine* lines4_host, const FqRecCtx& cx, FqRecOut* out_dev) = 0;
   /* device-side stopwatch on the stream (CUDA events) */

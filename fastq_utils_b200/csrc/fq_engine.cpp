@@ -1259,6 +1259,17 @@ void FqEngine::count_n(const uint8_t* data, const std::vector<FqLine>& seq_lines
   dev_->release(d); dev_->release(o);
 }
 
+void FqEngine::poly_at(const uint8_t* data, const std::vector<FqLine>& seq_lines, std::vector<uint32_t>* out3) {
+  out3->assign(seq_lines.size() * 3, 0);
+  if (seq_lines.empty()) return;
+  FqLine* d = (FqLine*)dev_->alloc(seq_lines.size() * sizeof(FqLine));
+  uint32_t* o = (uint32_t*)dev_->alloc(seq_lines.size() * 3 * sizeof(uint32_t));
+  dev_->upload(d, seq_lines.data(), seq_lines.size() * sizeof(FqLine));
+  dev_->poly_at(data, d, (uint32_t)seq_lines.size(), o);
+  dev_->download(out3->data(), o, out3->size() * sizeof(uint32_t));
+  dev_->release(d); dev_->release(o);
+}
+
 void FqEngine::index_records(const void* host_bytes, size_t n, uint64_t* starts, size_t cap, uint64_t* n_records) {
   if (n > kMaxChunk) throw std::runtime_error("fqg_index_records: at most 2 GiB per call");
   uint8_t* d = (uint8_t*)dev_->alloc(n + kPad);

@@ -94,6 +94,7 @@ class FqEngine {
   void index_records(const void* host_bytes, size_t n, uint64_t* starts, size_t cap, uint64_t* n_records);
   void record_table(uint64_t want, std::vector<FqLine>* lines4, const uint8_t** data);
   void count_n(const uint8_t* data, const std::vector<FqLine>& seq_lines, std::vector<uint32_t>* out2);
+  void poly_at(const uint8_t* data, const std::vector<FqLine>& seq_lines, std::vector<uint32_t>* out3);
   void prescan_device(int file, const void* dptr, size_t n, bool at_eof, uint64_t* n_lines, int32_t* ends_lf, uint64_t first_ends[4]);
   void set_stream_start(int file, uint32_t skip_lines, uint64_t first_record);
   void names_count(int file, uint32_t world, uint64_t* counts, uint64_t* bytes);

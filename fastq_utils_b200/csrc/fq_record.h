@@ -42,6 +42,19 @@ FQ_HD uint32_t fq_cstrlen(const uint8_t* d, uint32_t off, uint32_t len) {
 }
 
 /* ---------------------------------------------------------------- sequence line (src/fastq.c:317-341) */
+/* fastq_trim_poly_at's two scans over a sequence line as gzgets left it (src/fastq_trim_poly_at.c:77-115).  read_len = strlen of the
+ * line buffer: the bytes up to the first NUL, terminators included (src/fastq.c:259).  tail: bytes from index read_len - 2 downwards
+ * that are one of N A n a (the loop starts in front of the line's last byte, which is its LF in a complete line); head: bytes from
+ * index 0 upwards that are one of N T n t. */
+FQ_HD void fq_poly_at(const uint8_t* s, uint32_t len, uint32_t* read_len, uint32_t* tail, uint32_t* head) {
+  uint32_t rl = 0;
+  while (rl < len && s[rl] != 0) rl++;
+  uint32_t a = 0;
+  for (long x = (long)rl - 2; x >= 0; --x) { const uint8_t c = s[x]; if (c != 'N' && c != 'A' && c != 'n' && c != 'a') break; ++a; }
+  uint32_t b = 0;
+  for (uint32_t x = 0; x < rl; ++x) { const uint8_t c = s[x]; if (c != 'N' && c != 'T' && c != 'n' && c != 't') break; ++b; }
+  *read_len = rl; *tail = a; *head = b;
+}
 FQ_HD bool fq_is_base(uint8_t c) {
   switch (c) {
     case 'A': case 'C': case 'G': case 'T': case 'U': case 'a': case 'c': case 'g': case 't': case 'u':

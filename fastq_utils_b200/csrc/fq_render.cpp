@@ -3,6 +3,7 @@
  * (stdout / stderr split, message wording, blank lines: src/fastq_info.c:190-396, src/fastq.h:69-82), and
  * fqg_fastq_info_mem(): main() on inflated streams — option parsing, mode dispatch, feeding, rendering.
  */
+#include <getopt.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -495,6 +496,136 @@ int writer_tool(bool filter_n, int argc, const char** argv_in, const void* f1, s
   return 0;
 }
 }  // namespace
+
+/* main() of fastq_trim_poly_at (src/fastq_trim_poly_at.c:121-233).  The options go through the C library's getopt_long, as the reference
+ * calls it (long options and their unambiguous prefixes, `--opt=value`, the short forms a: b: c: d:, unknown words ignored); the input
+ * is read through the caller's callbacks into one chunk, the records are delimited on the device (the bare fastq_read_next_entry loop,
+ * FQG_MODE_READER) and the two scans of trim_poly_at run there too (fq_poly_at, one result triple per record).  The host then does what
+ * the reference does to its line buffers: the buffers of a FASTQ_ENTRY live across records, and the trimming writes and reads at indices
+ * taken from the SEQUENCE line into the QUALITY buffer too (:92-95, :108-111) — with a quality line shorter than its sequence line what
+ * is printed depends on what an earlier record left there, so the two buffers are kept exactly as the reference keeps them.  What the
+ * reference gzips into --outfile comes back inflated. */
+extern "C" int fqg_trim_poly_at_stream(int argc, const char** argv_in, const fqg_stream_io* io, int device, fqg_transcript* tr,
+                                       char** outfile, size_t* outfile_len, const char** outfile_name) {
+  if (argc < 1 || !argv_in || !io || !tr || !outfile || !outfile_len || !outfile_name) return FQG_ERR_USAGE;
+  *outfile = nullptr; *outfile_len = 0; *outfile_name = nullptr;
+  Text t;
+  const char* file = nullptr; const char* ofile = nullptr; int min_poly = 10; long min_len = 10;
+  static std::mutex getopt_mu; /* getopt's state is the C library's: one parse at a time */
+  int help = 0;
+  {
+    std::lock_guard<std::mutex> lk(getopt_mu);
+    static int help_flag; help_flag = 0;
+    static struct option long_options[] = {{"help", no_argument, &help_flag, 1}, {"min_poly_at_len", required_argument, 0, 'a'}, {"file", required_argument, 0, 'b'},
+                                           {"outfile", required_argument, 0, 'c'}, {"min_len", required_argument, 0, 'd'}, {0, 0, 0, 0}};
+    std::vector<char*> argv; /* getopt permutes the words: a copy of the pointers */
+    for (int i = 0; i < argc; i++) argv.push_back(const_cast<char*>(argv_in[i]));
+    argv.push_back(nullptr);
+    optind = 0; opterr = 0; /* (optind = 0: the GNU way to start over) */
+    for (;;) {
+      int option_index = 0;
+      const int c = getopt_long(argc, argv.data(), "a:b:c:d:", long_options, &option_index);
+      if (c == -1) break;
+      switch (c) {
+        case 'a': min_poly = (int)atol(optarg); break;
+        case 'b': file = optarg; break;
+        case 'c': ofile = optarg; break;
+        case 'd': min_len = atol(optarg); break;
+        default: break;
+      }
+    }
+    help = help_flag;
+  }
+  t.e("fastq_utils %s\n", "0.25.3");
+  if (help) {
+    t.o("usage: fastq_trim_poly_at --file fastq_file --outfile out_file [optional parameters]");
+    t.o("%s", "\n  --help       :print the usage\n  --file <filename> :fastq (optional gzipped) file name \n  --ofile <filename> : fastq file name where the processed reads will be written \n"
+              "  --min_poly_at_len integer     : minimum length of poly-A|T sequence to remove.\n  --min_len integer     : minimum read length.\n");
+    t.rc = 0; to_transcript(t, tr); return 0;
+  }
+  t.e("INFO:Validating options...\n");
+  if (!file) { ERR_BEGIN(t); t.e("missing input file (--file)"); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; }
+  if (!ofile) { ERR_BEGIN(t); t.e("missing output file name (--outfile)"); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; }
+  t.e("INFO:Options OK.\n");
+  void* h = io->open ? io->open(io->user, file) : nullptr;
+  if (!h) { ERR_BEGIN(t); t.e("Unable to open %s", file); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; } /* src/fastq.c:651-655 */
+  std::vector<char> in;
+  {
+    std::vector<char> piece(8u << 20);
+    long r;
+    while ((r = io->read(io->user, h, piece.data(), piece.size())) > 0) in.insert(in.end(), piece.data(), piece.data() + r);
+    if (io->close) io->close(io->user, h);
+    if (r < 0) return FQG_ERR_USAGE;
+  }
+  if (in.size() > (((size_t)1 << 31) - 64)) return FQG_ERR_USAGE; /* one chunk: the record-writing tools take streams below 2 GiB */
+  *outfile_name = ofile; /* from here on the reference has created the file */
+  std::string out;
+  fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER; cfg.flags = FQG_FLAG_KEEP_CHUNKS;
+  try {
+    FqDevice* dev = fq_default_device(device);
+    {
+      FqEngine eng(cfg, dev);
+      eng.feed_host(0, in.data(), in.size(), true);
+      fqg_report rep; eng.finish(&rep);
+      const bool truncated = rep.error.code == FQG_E_TRUNC;
+      const uint64_t nread = truncated ? rep.reads_before_error[0] : rep.file[0].n_records;
+      std::vector<FqLine> L; const uint8_t* ddata = nullptr;
+      eng.record_table(nread, &L, &ddata);
+      std::vector<FqLine> seq(L.size() / 4);
+      uint32_t longest = 0;
+      for (size_t r = 0; r < seq.size(); r++) { seq[r] = L[4 * r + 1]; longest = std::max(longest, std::max(L[4 * r + 1].len, L[4 * r + 3].len)); }
+      std::vector<uint32_t> pa;
+      eng.poly_at(ddata, seq, &pa);
+      std::vector<char> sbuf((size_t)longest + 4, 0), qbuf((size_t)longest + 4, 0); /* the entry's seq and qual buffers: they outlive a record */
+      const char* bytes = in.data();
+      unsigned long trimmed = 0, discarded = 0, processed = 0;
+      for (size_t r = 0; r < seq.size(); r++) {
+        const FqLine &lh = L[4 * r], &ls = L[4 * r + 1], &lp = L[4 * r + 2], &lq = L[4 * r + 3];
+        memcpy(sbuf.data(), bytes + ls.off, ls.len); sbuf[ls.len] = 0; /* gzgets: the line's bytes and a NUL behind them */
+        memcpy(qbuf.data(), bytes + lq.off, lq.len); qbuf[lq.len] = 0;
+        ++processed;
+        unsigned long read_len = pa[3 * r];
+        const long tail = pa[3 * r + 1], head = pa[3 * r + 2];
+        if (min_poly > 0) {
+          if (tail >= min_poly) { /* the 3' end (:79-96) */
+            const long x = (long)read_len - 2 - tail;
+            read_len -= (unsigned long)tail;
+            sbuf[x + 1] = '\n'; sbuf[x + 2] = 0; qbuf[x + 1] = '\n'; qbuf[x + 2] = 0;
+            ++trimmed;
+          } else if (head >= min_poly) { /* the 5' end (:99-113) */
+            for (long x = 0; x <= (long)read_len - head; ++x) { sbuf[x] = sbuf[x + head]; qbuf[x] = qbuf[x + head]; }
+            read_len -= (unsigned long)head;
+            ++trimmed;
+          }
+        }
+        if (read_len >= (unsigned long)min_len) {
+          out.append(bytes + lh.off, strnlen(bytes + lh.off, lh.len));
+          out.append(sbuf.data(), strlen(sbuf.data()));
+          out.append(bytes + lp.off, strnlen(bytes + lp.off, lp.len));
+          out.append(qbuf.data(), strlen(qbuf.data()));
+        } else ++discarded;
+        const unsigned long c = (unsigned long)(r + 1);
+        if (c % 100000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", c);
+      }
+      if (truncated) { error_text(t, rep.error, file, file); t.rc = 1; }
+      else {
+        t.e("INFO:Reads processed: %ld\n", (long)processed); t.e("INFO:Reads trimmed: %ld\n", (long)trimmed); t.e("INFO:Reads discarded: %ld\n", (long)discarded);
+        t.rc = 0;
+      }
+    }
+    delete dev;
+  } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
+  } catch (const std::exception& ex) {
+    fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
+    return strstr(ex.what(), "CUDA") ? (strstr(ex.what(), "no CUDA") ? FQG_ERR_NO_DEVICE : FQG_ERR_CUDA) : FQG_ERR_INTERNAL;
+  }
+  *outfile = (char*)malloc(out.size() + 1);
+  if (!*outfile) return FQG_ERR_OOM;
+  memcpy(*outfile, out.data(), out.size()); (*outfile)[out.size()] = 0; *outfile_len = out.size();
+  to_transcript(t, tr);
+  return 0;
+}
+extern "C" void fqg_buffer_free(void* p) { free(p); }
 
 /* main() of the reader-style tools on an inflated stream: src/fastq_num_reads.c:32-50, src/fastq_not_empty.c:32-47.  Both are
  * the bare fastq_read_next_entry loop (src/fastq.c:237-261): records are delimited, a NUL-led header line ends the file quietly,

@@ -164,6 +164,16 @@ int fqg_fastq_info_stream(int argc, const char** argv, const fqg_stream_io* io, 
  * with the reference's usage text, "file truncated" / "Unable to open" errors and exit statuses.  n = (size_t)-1: could not be opened. */
 int fqg_reader_tool_mem(int argc, const char** argv, const void* f1, size_t n1, int device, size_t chunk_bytes, fqg_transcript* t);
 
+/* fastq_trim_poly_at (src/fastq_trim_poly_at.c:121-233): argv as the reference receives it (--file, --outfile,
+ * --min_poly_at_len, --min_len, --help, parsed by the C library's getopt_long like the reference does).  The library opens --file
+ * through `io` (streams below 2 GiB), delimits the records and scans their poly-A / poly-T ends on the device, and returns what the
+ * reference would gzip into --outfile, inflated, in *outfile (release with fqg_buffer_free); *outfile_name is the argv word naming that
+ * file, NULL when the run ended before the reference creates it (usage errors, --help, an input that cannot be opened).  After a
+ * "file truncated" error (exit status 1) the reference leaves an unfinished gzip file behind: *outfile then holds the records written so far. */
+int fqg_trim_poly_at_stream(int argc, const char** argv, const fqg_stream_io* io, int device, fqg_transcript* t,
+                            char** outfile, size_t* outfile_len, const char** outfile_name);
+void fqg_buffer_free(void* p);
+
 /* ---- multi-GPU building blocks (fastq_utils_b200/dist.py drives them with torch.distributed) ----
  * A rank holds a contiguous byte range of a file.  fqg_prescan_device builds the line index of the range (kept for the
  * following fqg_feed_device of the same pointer) and reports what the ranks exchange to fix each range's line phase. */

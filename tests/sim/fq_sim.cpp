@@ -409,6 +409,10 @@ class FqSimDevice : public FqDevice {
       out2[2 * k] = cnt; out2[2 * k + 1] = nul;
     }
   }
+  void poly_at(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out3) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < n; k++) fq_poly_at(data + seq_lines[k].off, seq_lines[k].len, out3 + 3 * k, out3 + 3 * k + 1, out3 + 3 * k + 2);
+  }
   void explain(const uint8_t* data, const FqLine* lines4, const FqRecCtx& cx, FqRecOut* out) override {
     n_launch_++;
     fq_check_record_careful(data, lines4, cx, out);
