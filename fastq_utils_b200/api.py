@@ -98,6 +98,8 @@ def bind(L):
     L.fqg_trim_poly_at_stream.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(StreamIO), ci, ctypes.POINTER(Transcript),
                                           ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(ctypes.c_char_p)]
     L.fqg_buffer_free.argtypes = [vp]
+    L.fqg_filterpair_mem.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), vp, sz, vp, sz, ci, ctypes.POINTER(Transcript), ctypes.POINTER(vp), ctypes.POINTER(sz),
+                                     ctypes.POINTER(ctypes.c_int32)]
     L.fqg_buffer_free.restype = None
     L.fqg_kernel_stats.argtypes = [vp, ci, ctypes.POINTER(KernelStat)]
     L.fqg_kernel_stats_reset.argtypes = [vp]
@@ -195,6 +197,33 @@ def _read_inflated(path):
         out.append(d.decompress(raw))
         raw = d.unused_data
     return b"".join(out)
+
+
+def filterpair(argv, data1=None, data2=None, device=0, write=False, _lib=None):
+    """`fastq_filterpair argv...` (src/fastq_filterpair.c; argv = fastq1 fastq2 paired1 paired2 unpaired [sorted]) on two in-memory inflated
+    streams → (exit status, stdout, stderr, created, [paired1, paired2, unpaired] inflated).  data=None: the file could not be opened.
+    write=True gzips the three results into the named files (level 3, like the reference)."""
+    full = [b"fastq_filterpair"] + [a.encode("latin-1") if isinstance(a, str) else a for a in argv]
+    arr = (ctypes.c_char_p * (len(full) + 1))(*full, None)
+    un = ctypes.c_size_t(-1).value
+    tr, outs, lens, created = Transcript(), (ctypes.c_void_p * 3)(), (ctypes.c_size_t * 3)(), ctypes.c_int32(0)
+    L = _lib if _lib is not None else lib()  # (_lib: the tests' stand-in library)
+    st = L.fqg_filterpair_mem(len(full), arr, data1, len(data1) if data1 is not None else un, data2, len(data2) if data2 is not None else un, device,
+                              ctypes.byref(tr), outs, lens, ctypes.byref(created))
+    if st != 0:
+        raise RuntimeError(f"fqg_filterpair_mem failed with status {st}")
+    bufs = []
+    for i in range(3):
+        bufs.append(ctypes.string_at(outs[i], lens[i]) if outs[i] else b"")
+        L.fqg_buffer_free(outs[i])
+    rc, out, err = tr.rc, ctypes.string_at(tr.out, tr.out_len).decode("latin-1"), ctypes.string_at(tr.err, tr.err_len).decode("latin-1")
+    L.fqg_transcript_free(ctypes.byref(tr))
+    if write and created.value and len(argv) >= 5:
+        import gzip
+        for name, b in zip(argv[2:5], bufs):
+            with gzip.open(name, "wb", compresslevel=3) as fh:
+                fh.write(b)
+    return rc, out, err, bool(created.value), bufs
 
 
 def trim_poly_at(argv, files=None, device=0, write=False, _lib=None):

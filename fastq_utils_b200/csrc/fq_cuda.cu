@@ -1134,6 +1134,33 @@ fq_count_n_kernel(const uint8_t* __restrict__ data, const FqLine* __restrict__ l
     if (lane == 0) { out2[2 * k] = cnt; out2[2 * k + 1] = nul; }
   }
 }
+/* fastq_filterpair (src/fastq_filterpair.c): names of header lines, and where the index holds them */
+__global__ void __launch_bounds__(256)
+fq_header_names_kernel(const uint8_t* __restrict__ data, const FqLine* __restrict__ lines, uint32_t n, int fmt, int is_pe, uint32_t seed, FqName* out) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) out[k] = fq_header_name(data, lines[k].off, lines[k].len, fmt, is_pe, seed);
+}
+__global__ void __launch_bounds__(256)
+fq_names_lookup_kernel(const TableParams P, unsigned long long* out_idx) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < P.nrec; k += gridDim.x * blockDim.x) {
+    const FqName nm = P.names[k];
+    unsigned long long found = FQ_IDX_NONE;
+    if (nm.hash != FQ_HASH_SKIP) {
+      unsigned long long i = nm.hash & P.mask, probes = 0;
+      for (;; i = (i + 1) & P.mask) {
+        if (++probes > P.mask + 1) break;
+        const FqSlot* s = P.slots + i;
+        const unsigned long long cur = s->hash;
+        if (cur == FQ_HASH_EMPTY) break;
+        if (cur != nm.hash) continue;
+        uint32_t ol; const uint8_t* on = dir_name(P.dir1, P.ndir1, s->idx1, &ol);
+        if (!(ol == nm.len && fq_bytes_equal(on, P.data + nm.off, nm.len))) continue; /* another name with this hash: the lookup walks on (src/hash.c:38-45) */
+        found = s->idx1;
+        break;
+      }
+    }
+    out_idx[k] = found;
+  }
+}
 /* fastq_trim_poly_at (src/fastq_trim_poly_at.c:77-115): one thread per sequence line (the scans stop at the first other base) */
 __global__ void __launch_bounds__(256)
 fq_poly_at_kernel(const uint8_t* __restrict__ data, const FqLine* __restrict__ lines, uint32_t n, uint32_t* out3) {
@@ -1577,6 +1604,21 @@ class FqCudaDevice : public FqDevice {
     if (!n) return;
     int grid = (int)std::min<uint32_t>((n + 7) / 8, (uint32_t)sms_ * 8);
     fq_count_n_kernel<<<grid, 256, 0, st_>>>(data, seq_lines, n, out2);
+    launched();
+  }
+  void header_names(const uint8_t* data, const FqLine* hdr_lines, uint32_t n, int fmt, int is_pe, uint32_t seed, FqName* out) override {
+    if (!n) return;
+    int grid = (int)std::min<uint32_t>((n + 255) / 256, (uint32_t)sms_ * 8);
+    fq_header_names_kernel<<<grid, 256, 0, st_>>>(data, hdr_lines, n, fmt, is_pe, seed, out);
+    launched();
+  }
+  void names_lookup(const FqTableArgs& a, unsigned long long* out_idx) override {
+    if (!a.nrec) return;
+    TableParams P; P.names = a.names; P.data = a.data; P.nrec = a.nrec; P.g0 = a.g0; P.step_base = a.step_base;
+    P.slots = a.slots; P.mask = a.mask; P.dir1 = a.dir1; P.ndir1 = a.ndir1; P.key = a.key; P.counters = a.counters;
+    FQ_CUDA_CHECK(cudaStreamSynchronize(st2_)); /* the inserts run on the index stream */
+    int grid = (int)std::min<uint32_t>((a.nrec + 255) / 256, (uint32_t)sms_ * 8);
+    fq_names_lookup_kernel<<<grid, 256, 0, st_>>>(P, out_idx);
     launched();
   }
   void poly_at(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out3) override {

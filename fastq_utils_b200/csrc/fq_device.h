@@ -213,6 +213,10 @@ class FqDevice {
   /* fastq_filter_n's predicate (src/fastq_filter_n.c:77-86) for n sequence lines of a chunk: out2[2k] = 'N' / 'n' bytes before the first LF or
    * NUL of line k, out2[2k+1] = strlen of the line (bytes before the first NUL, terminator included) */
   virtual void count_n(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out2) = 0;
+  /* fastq_filterpair: the names of `n` header lines as descriptors (fq_header_name); and for every descriptor the record index the
+   * table holds for an equal name (FQ_IDX_NONE: none), names compared byte by byte against the indexed names (a.dir1) */
+  virtual void header_names(const uint8_t* data, const FqLine* hdr_lines, uint32_t n, int fmt, int is_pe, uint32_t seed, FqName* out) = 0;
+  virtual void names_lookup(const FqTableArgs& a, unsigned long long* out_idx) = 0;
   /* fastq_trim_poly_at: out3[3k..] = read_len, poly-A/N bytes at the line's end, poly-T/N bytes at its start (fq_poly_at) */
   virtual void poly_at(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out3) = 0;
   /* details of one record for the error message */

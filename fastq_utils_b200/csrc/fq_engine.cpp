@@ -1259,6 +1259,34 @@ void FqEngine::count_n(const uint8_t* data, const std::vector<FqLine>& seq_lines
   dev_->release(d); dev_->release(o);
 }
 
+FqName* FqEngine::header_names(const uint8_t* data, const std::vector<FqLine>& hdr_lines, int fmt, int is_pe) {
+  if (hdr_lines.empty()) return nullptr;
+  FqLine* d = (FqLine*)dev_->alloc(hdr_lines.size() * sizeof(FqLine));
+  FqName* o = (FqName*)dev_->alloc(hdr_lines.size() * sizeof(FqName));
+  dev_->upload(d, hdr_lines.data(), hdr_lines.size() * sizeof(FqLine));
+  dev_->header_names(data, d, (uint32_t)hdr_lines.size(), fmt, is_pe, seed_, o);
+  dev_->sync();
+  dev_->release(d);
+  return o;
+}
+void FqEngine::sniff_first(const uint8_t* data, FqLine hdr1, FqLine seq, int32_t* sniff_fmt, int32_t* color) {
+  dev_->sniff(data, hdr1, seq, (int32_t*)scratch_);
+  int32_t o2[2]; dev_->download(o2, scratch_, sizeof o2);
+  *sniff_fmt = o2[0]; *color = o2[1];
+}
+void FqEngine::lookup_names(const FqName* dev_names, const uint8_t* data, uint32_t n, std::vector<unsigned long long>* idx) {
+  idx->assign(n, FQ_IDX_NONE);
+  if (!n || !slots_) return; /* (an empty index holds nothing) */
+  FqTableArgs t; memset(&t, 0, sizeof t);
+  t.names = dev_names; t.data = data; t.nrec = n; t.key = key_; t.counters = counters_;
+  sync_dir(0);
+  t.dir1 = f_[0].dir_dev; t.ndir1 = (uint32_t)f_[0].dir_host.size();
+  t.slots = slots_; t.mask = table_cap_ - 1;
+  unsigned long long* o = (unsigned long long*)dev_->alloc((size_t)n * sizeof(unsigned long long));
+  dev_->names_lookup(t, o);
+  dev_->download(idx->data(), o, (size_t)n * sizeof(unsigned long long));
+  dev_->release(o);
+}
 void FqEngine::poly_at(const uint8_t* data, const std::vector<FqLine>& seq_lines, std::vector<uint32_t>* out3) {
   out3->assign(seq_lines.size() * 3, 0);
   if (seq_lines.empty()) return;

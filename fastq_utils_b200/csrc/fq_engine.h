@@ -95,6 +95,11 @@ class FqEngine {
   void record_table(uint64_t want, std::vector<FqLine>* lines4, const uint8_t** data);
   void count_n(const uint8_t* data, const std::vector<FqLine>& seq_lines, std::vector<uint32_t>* out2);
   void poly_at(const uint8_t* data, const std::vector<FqLine>& seq_lines, std::vector<uint32_t>* out3);
+  /* fastq_filterpair: the names of header lines of a resident chunk (device descriptors, released by the caller through device()),
+   * the sniff of a file's first record, and the record this engine's index holds for each name (FQ_IDX_NONE: none) */
+  FqName* header_names(const uint8_t* data, const std::vector<FqLine>& hdr_lines, int fmt, int is_pe);
+  void sniff_first(const uint8_t* data, FqLine hdr1, FqLine seq, int32_t* sniff_fmt, int32_t* color);
+  void lookup_names(const FqName* dev_names, const uint8_t* data, uint32_t n, std::vector<unsigned long long>* idx);
   void prescan_device(int file, const void* dptr, size_t n, bool at_eof, uint64_t* n_lines, int32_t* ends_lf, uint64_t first_ends[4]);
   void set_stream_start(int file, uint32_t skip_lines, uint64_t first_record);
   void names_count(int file, uint32_t world, uint64_t* counts, uint64_t* bytes);

@@ -183,6 +183,10 @@ FQ_HD void fq_readname(const uint8_t* d, uint32_t hoff, uint32_t hcl, int fmt, i
   }
 }
 
+/* The name fastq_get_readname (src/fastq.c:442-516) makes of a header line, as a descriptor: hash, offset and length of the name's
+ * bytes.  A line that does not start with '@' is the reference's "wrong header" (:448): hash = FQ_HASH_SKIP, len = 0xFFFFFFFF. */
+FQ_HD FqName fq_header_name(const uint8_t* d, uint32_t off, uint32_t len, int fmt, int is_pe, uint32_t seed);
+
 /* compare_headers, src/fastq.c:543-566, on two normalised names */
 FQ_HD bool fq_compare_headers(const uint8_t* a, uint32_t alen, const uint8_t* b, uint32_t blen) {
   if (blen == 0 || b[0] == '\n' || b[0] == '\r') return true;
@@ -233,6 +237,15 @@ FQ_HD uint64_t fq_hash_name(const uint8_t* p, uint32_t len, uint32_t seed) {
 FQ_HD bool fq_bytes_equal(const uint8_t* a, const uint8_t* b, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) if (a[i] != b[i]) return false;
   return true;
+}
+FQ_HD FqName fq_header_name(const uint8_t* d, uint32_t off, uint32_t len, int fmt, int is_pe, uint32_t seed) {
+  FqName nm;
+  const uint32_t hcl = fq_cstrlen(d, off, len);
+  if (hcl == 0 || d[off] != '@') { nm.hash = FQ_HASH_SKIP; nm.off = off; nm.len = 0xFFFFFFFFu; return nm; }
+  uint32_t noff, nlen; uint64_t mem;
+  fq_readname(d, off, hcl, fmt, is_pe, &noff, &nlen, &mem);
+  nm.hash = fq_hash_name(d + noff, nlen, seed); nm.off = noff; nm.len = nlen;
+  return nm;
 }
 
 /* ---------------------------------------------------------------- sniffers (src/fastq.c:666-754), first record of a file */

@@ -497,6 +497,179 @@ int writer_tool(bool filter_n, int argc, const char** argv_in, const void* f1, s
 }
 }  // namespace
 
+/* main() of fastq_filterpair (src/fastq_filterpair.c:38-240) on two inflated streams.  File 1 goes through the index loop
+ * (fastq_index_readnames, src/fastq.c:396-439: validation, duplicate check — FQG_MODE_INDEX with paired names); the records of both files
+ * are delimited by the reader loop (FQG_MODE_READER), their names hashed on the device (fq_header_name) and looked up in the index there
+ * (names_lookup: exact byte compare behind an equal hash).  What is left for the host is what the reference does one record at a time:
+ * lookup-then-delete decides that the FIRST record of file 2 with a name gets the mate; the copies out of file 1 count seeks against the
+ * reader's position; the last loop over file 1 starts where the last copy left the reader, not at the start of the file.  The three
+ * gzip files the reference writes come back inflated. */
+namespace {
+struct PairFile { /* one input: its records (reader loop) on the device and on the host */
+  FqEngine* rd = nullptr; std::vector<FqLine> L; const uint8_t* ddata = nullptr; const char* bytes = nullptr; uint64_t nrec = 0; fqg_report rep;
+  void load(const fqg_config& base, FqDevice* dev, const void* p, size_t n) {
+    fqg_config cfg = base; cfg.mode = FQG_MODE_READER; cfg.flags = FQG_FLAG_KEEP_CHUNKS;
+    rd = new FqEngine(cfg, dev);
+    rd->feed_host(0, p, n, true);
+    rd->finish(&rep);
+    nrec = rep.error.code == FQG_E_TRUNC ? rep.reads_before_error[0] : rep.file[0].n_records;
+    rd->record_table(nrec, &L, &ddata);
+    bytes = (const char*)p;
+  }
+  ~PairFile() { delete rd; }
+  std::vector<FqLine> headers() const { std::vector<FqLine> h(L.size() / 4); for (size_t r = 0; r < h.size(); r++) h[r] = L[4 * r]; return h; }
+  void write(std::string& out, size_t r) const { for (int i = 0; i < 4; i++) { const FqLine& l = L[4 * r + i]; out.append(bytes + l.off, strnlen(bytes + l.off, l.len)); } }
+  uint32_t raw_len(size_t r) const { return L[4 * r].len + L[4 * r + 1].len + L[4 * r + 2].len + L[4 * r + 3].len; }
+};
+/* the index loop over one file (fastq_index_readnames and the lines fastq_filterpair prints around it); false: it ended the run */
+bool index_file(Text& t, FqEngine& ix, const void* p, size_t n, const char* name, unsigned long* index_mem, fqg_report* rep) {
+  t.e("Scanning and indexing all reads from %s\n", name);
+  ix.feed_host(0, p, n, true);
+  ix.finish(rep);
+  sniff_lines(t, rep->file[0]);
+  progress(t, rep->reads_before_error[0], 1);
+  if (rep->error.code != FQG_OK) { error_text(t, rep->error, name, name); return false; }
+  t.e("Scanning complete.\n");
+  *index_mem += (unsigned long)rep->index_mem; /* (sizeof(hashtable) and the entries, src/fastq_filterpair.c:70, src/fastq.c:609) */
+  t.e("Reads indexed: %llu\n", (unsigned long long)rep->n_index_entries);
+  t.e("Memory used in indexing: %ld MB\n", (long)(*index_mem / 1024 / 1024));
+  return true;
+}
+}  // namespace
+extern "C" int fqg_filterpair_mem(int argc, const char** argv, const void* f1, size_t n1, const void* f2, size_t n2, int device,
+                                  fqg_transcript* tr, char* outs[3], size_t lens[3], int32_t* created) {
+  if (argc < 1 || !argv || !tr || !outs || !lens || !created) return FQG_ERR_USAGE;
+  const size_t UNOPENABLE = (size_t)-1;
+  for (int i = 0; i < 3; i++) { outs[i] = nullptr; lens[i] = 0; }
+  *created = 0;
+  Text t;
+  t.e("fastq_utils %s\n", "0.25.3");
+  if (argc != 6 && argc != 7) { t.e("Usage: filterpair fastq1 fastq2 paired1 paired2 unpaired [sorted]\n"); t.rc = 1; to_transcript(t, tr); return 0; }
+  t.e("%d", argc);
+  if (n1 == UNOPENABLE) { ERR_BEGIN(t); t.e("Unable to open %s", argv[1]); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; } /* src/fastq.c:651-655 */
+  if (n2 == UNOPENABLE) { ERR_BEGIN(t); t.e("Unable to open %s", argv[2]); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; }
+  if ((!f1 && n1) || (!f2 && n2)) return FQG_ERR_USAGE;
+  const size_t LIMIT = ((size_t)1 << 31) - 64; /* one chunk per file: the record-writing tools take streams below 2 GiB */
+  if (n1 > LIMIT || n2 > LIMIT) return FQG_ERR_USAGE;
+  const bool sorted = argc == 7 && !strcmp(argv[6], "sorted");
+  t.e("HASHSIZE=%u\n", 100000001u);
+  if (sorted) t.e("Assuming sorted fastq files\n");
+  std::string out[3]; /* paired1, paired2, unpaired */
+  fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_INDEX; cfg.flags = FQG_FLAG_PAIRED_NAMES;
+  try {
+    FqDevice* dev = fq_default_device(device);
+    {
+      unsigned long index_mem = 0;
+      fqg_report rep1, rep2;
+      FqEngine ix1(cfg, dev);
+      bool go = index_file(t, ix1, f1, n1, argv[1], &index_mem, &rep1);
+      if (go) {
+        *created = 1; /* the three output files exist from here on (src/fastq_filterpair.c:83-92) */
+        PairFile A, B;
+        A.load(cfg, dev, f1, n1);
+        const int fmt1 = rep1.file[0].sniff_format == FQ_SNIFF_DEFAULT ? FQ_FMT_DEFAULT : rep1.file[0].sniff_format == FQ_SNIFF_CASAVA ? FQ_FMT_CASAVA : FQ_FMT_INT;
+        unsigned long paired = 0, up2 = 0;
+        if (sorted) {
+          FqEngine ix2(cfg, dev);
+          go = index_file(t, ix2, f2, n2, argv[2], &index_mem, &rep2);
+          if (go) {
+            B.load(cfg, dev, f2, n2);
+            const int fmt2 = rep2.file[0].sniff_format == FQ_SNIFF_DEFAULT ? FQ_FMT_DEFAULT : rep2.file[0].sniff_format == FQ_SNIFF_CASAVA ? FQ_FMT_CASAVA : FQ_FMT_INT;
+            /* both files hold every name once (the index loop saw to that): a record has its mate iff the other index holds its name */
+            std::vector<unsigned long long> in2, in1;
+            FqName* na = ix2.header_names(A.ddata, A.headers(), fmt1, 1);
+            ix2.lookup_names(na, A.ddata, (uint32_t)A.nrec, &in2);
+            if (na) dev->release(na);
+            FqName* nb = ix1.header_names(B.ddata, B.headers(), fmt2, 1);
+            ix1.lookup_names(nb, B.ddata, (uint32_t)B.nrec, &in1);
+            if (nb) dev->release(nb);
+            t.e("Filtering %s...\n", argv[1]);
+            for (size_t r = 0; r < A.nrec; r++) {
+              if (in2[r] == FQ_IDX_NONE) { ++up2; A.write(out[2], r); } else { ++paired; A.write(out[0], r); }
+              if ((r + 1) % 10000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", (unsigned long)(r + 1)); /* cline = 1 + 4(r+1) after the rewind */
+            }
+            t.e("Filtering %s...\n", argv[2]);
+            for (size_t r = 0; r < B.nrec; r++) {
+              if (in1[r] == FQ_IDX_NONE) { ++up2; B.write(out[2], r); } else B.write(out[1], r);
+              if ((r + 1) % 10000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", (unsigned long)(r + 1));
+            }
+          }
+        } else {
+          t.e("Processing %s\n", argv[2]);
+          B.load(cfg, dev, f2, n2);
+          int32_t sf2 = FQ_SNIFF_DEFAULT, col2 = 0;
+          std::vector<unsigned long long> hit; std::vector<FqName> names2;
+          if (B.nrec) {
+            B.rd->sniff_first(B.ddata, B.L[0], B.L[1], &sf2, &col2);
+            const int fmt2 = sf2 == FQ_SNIFF_DEFAULT ? FQ_FMT_DEFAULT : sf2 == FQ_SNIFF_CASAVA ? FQ_FMT_CASAVA : FQ_FMT_INT;
+            FqName* nb = ix1.header_names(B.ddata, B.headers(), fmt2, 1);
+            ix1.lookup_names(nb, B.ddata, (uint32_t)B.nrec, &hit);
+            names2.resize(B.nrec);
+            dev->download(names2.data(), nb, B.nrec * sizeof(FqName));
+            dev->release(nb);
+          }
+          std::vector<uint8_t> gone(A.nrec, 0); /* fastq_index_delete: a name is found once */
+          unsigned long ctr_seek = 0, ctr_noseek = 0;
+          uint64_t pos1 = 0; /* where the reader of file 1 stands (inflated offset; 0 after the rewind) */
+          for (size_t r = 0; r < B.nrec && go; r++) {
+            if (names2[r].len == 0xFFFFFFFFu) { /* fastq_get_readname: src/fastq.c:448 */
+              const FqLine& l = B.L[4 * r];
+              ERR_BEGIN(t); t.e("Error in file %s: line %lu: wrong header ", argv[2], 4ul * (unsigned long)(r + 1)); t.err.append(B.bytes + l.off, strnlen(B.bytes + l.off, l.len)); ERR_END(t);
+              t.rc = 3; go = false; break;
+            }
+            if (r == 0) { fqg_file_report fr; memset(&fr, 0, sizeof fr); fr.sniff_format = sf2; fr.color_space = col2; sniff_lines(t, fr); }
+            const unsigned long long a = hit[r];
+            if (a == FQ_IDX_NONE || a >= A.nrec || gone[a]) { ++up2; B.write(out[2], r); }
+            else {
+              ++paired;
+              B.write(out[1], r);
+              const uint64_t offset = A.L[4 * a].off; /* fastq_quick_copy_entry, src/fastq.c:122-159 */
+              if (pos1 != offset) ++ctr_seek; else ++ctr_noseek;
+              t.e("%lu / %lu\n", ctr_seek, ctr_noseek);
+              A.write(out[0], (size_t)a);
+              pos1 = offset + A.raw_len((size_t)a);
+              gone[a] = 1;
+            }
+            if ((r + 1) % 10000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", (unsigned long)(r + 1));
+          }
+          if (go && B.rep.error.code == FQG_E_TRUNC) { error_text(t, B.rep.error, argv[2], argv[2]); go = false; } /* the reader met the broken record after those */
+          if (go) {
+            t.e("\n");
+            const unsigned long long left = rep1.n_index_entries - paired;
+            t.e("Recording %llu unpaired reads from %s\n", left, argv[1]);
+            unsigned long long remaining = left;
+            size_t j = 0;
+            while (j < A.nrec && A.L[4 * j].off < pos1) j++; /* the reader stands behind the last record it copied */
+            for (unsigned long m = 1; j < A.nrec && remaining; j++, m++) {
+              if (!gone[j]) { A.write(out[2], j); remaining--; }
+              if (m % 100000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", m); /* cline = 1 + 4m */
+            }
+            t.e("Unpaired from %s: %llu\n", argv[1], left);
+            t.e("Unpaired from %s: %ld\n", argv[2], (long)up2);
+          }
+        }
+        if (go) {
+          t.e("\n");
+          t.e("Paired: %ld\n", (long)paired);
+          if (paired == 0) { t.e("!!!WARNING!!! 0 paired reads! are the headers ok?\n"); t.rc = 3; } else t.rc = 0;
+        }
+      }
+    }
+    delete dev;
+  } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
+  } catch (const std::exception& ex) {
+    fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
+    return strstr(ex.what(), "CUDA") ? (strstr(ex.what(), "no CUDA") ? FQG_ERR_NO_DEVICE : FQG_ERR_CUDA) : FQG_ERR_INTERNAL;
+  }
+  for (int i = 0; i < 3; i++) {
+    outs[i] = (char*)malloc(out[i].size() + 1);
+    if (!outs[i]) return FQG_ERR_OOM;
+    memcpy(outs[i], out[i].data(), out[i].size()); outs[i][out[i].size()] = 0; lens[i] = out[i].size();
+  }
+  to_transcript(t, tr);
+  return 0;
+}
+
 /* main() of fastq_trim_poly_at (src/fastq_trim_poly_at.c:121-233).  The options go through the C library's getopt_long, as the reference
  * calls it (long options and their unambiguous prefixes, `--opt=value`, the short forms a: b: c: d:, unknown words ignored); the input
  * is read through the caller's callbacks into one chunk, the records are delimited on the device (the bare fastq_read_next_entry loop,

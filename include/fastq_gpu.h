@@ -164,6 +164,15 @@ int fqg_fastq_info_stream(int argc, const char** argv, const fqg_stream_io* io, 
  * with the reference's usage text, "file truncated" / "Unable to open" errors and exit statuses.  n = (size_t)-1: could not be opened. */
 int fqg_reader_tool_mem(int argc, const char** argv, const void* f1, size_t n1, int device, size_t chunk_bytes, fqg_transcript* t);
 
+/* fastq_filterpair (src/fastq_filterpair.c:38-240) on two inflated streams below 2 GiB each: argv as the reference
+ * receives it (fastq1 fastq2 paired1 paired2 unpaired [sorted]); n = (size_t)-1: the file could not be opened.  File 1 (with "sorted":
+ * both files) goes through the index loop of fastq_info — validation and duplicate check included — the mates are found through the
+ * index on the device.  outs[0..2] / lens[0..2]: what the reference gzips into paired1, paired2 and unpaired, inflated (release each
+ * with fqg_buffer_free); *created != 0 when the run got as far as creating the three files.  After an error (exit status 1 or 3) the
+ * reference leaves unfinished gzip files behind: the buffers then hold the records written so far. */
+int fqg_filterpair_mem(int argc, const char** argv, const void* f1, size_t n1, const void* f2, size_t n2, int device,
+                       fqg_transcript* t, char* outs[3], size_t lens[3], int32_t* created);
+
 /* fastq_trim_poly_at (src/fastq_trim_poly_at.c:121-233): argv as the reference receives it (--file, --outfile,
  * --min_poly_at_len, --min_len, --help, parsed by the C library's getopt_long like the reference does).  The library opens --file
  * through `io` (streams below 2 GiB), delimits the records and scans their poly-A / poly-T ends on the device, and returns what the

@@ -409,6 +409,31 @@ class FqSimDevice : public FqDevice {
       out2[2 * k] = cnt; out2[2 * k + 1] = nul;
     }
   }
+  void header_names(const uint8_t* data, const FqLine* hdr_lines, uint32_t n, int fmt, int is_pe, uint32_t seed, FqName* out) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < n; k++) out[k] = fq_header_name(data, hdr_lines[k].off, hdr_lines[k].len, fmt, is_pe, seed);
+  }
+  void names_lookup(const FqTableArgs& a, unsigned long long* out_idx) override {
+    n_launch_++;
+    for (uint32_t k = 0; k < a.nrec; k++) {
+      const FqName& nm = a.names[k];
+      uint64_t found = FQ_IDX_NONE;
+      if (nm.hash != FQ_HASH_SKIP) {
+        uint64_t i = nm.hash & a.mask, probes = 0;
+        for (;; i = (i + 1) & a.mask) {
+          if (++probes > a.mask + 1) break;
+          const FqSlot& s = a.slots[i];
+          if (s.hash == FQ_HASH_EMPTY) break;
+          if (s.hash != nm.hash) continue;
+          uint32_t ol; const uint8_t* on = name_of(a.dir1, a.ndir1, s.idx1, &ol);
+          if (!(ol == nm.len && fq_bytes_equal(on, a.data + nm.off, nm.len))) continue;
+          found = s.idx1;
+          break;
+        }
+      }
+      out_idx[k] = found;
+    }
+  }
   void poly_at(const uint8_t* data, const FqLine* seq_lines, uint32_t n, uint32_t* out3) override {
     n_launch_++;
     for (uint32_t k = 0; k < n; k++) fq_poly_at(data + seq_lines[k].off, seq_lines[k].len, out3 + 3 * k, out3 + 3 * k + 1, out3 + 3 * k + 2);
