@@ -38,8 +38,12 @@ MAX_READ_LENGTH = 2_500_000
 
 class ShardedFastqInfo:
     def __init__(self, mode, device=0, n_hint=0, tensor_device=None):
-        if mode not in (api.MODE_SINGLE, api.MODE_INDEX, api.MODE_INDEX_PAIR):
-            raise NotImplementedError("sharded runs support MODE_SINGLE, MODE_INDEX and MODE_INDEX_PAIR")
+        if mode not in (api.MODE_SINGLE, api.MODE_INDEX, api.MODE_INDEX_PAIR, api.MODE_INTERLEAVED, api.MODE_SORTED_PAIR):
+            raise NotImplementedError("sharded runs support the five fastq_info modes")
+        # MODE_INTERLEAVED and MODE_SORTED_PAIR are NOT sharded: a pair must sit on one rank (interleaved: cut at even records; sorted
+        # pairs: file 2 cut by record index, not by byte offset — SURVEY.md §8e), which the byte ranges do not give.  The ranks' ranges
+        # are gathered on rank 0, whose engine runs the loop (at most 64 GiB in all); every rank gets the result.
+        self.gathered = mode in (api.MODE_INTERLEAVED, api.MODE_SORTED_PAIR)
         self.mode = mode
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
@@ -192,7 +196,7 @@ class ShardedFastqInfo:
             else:
                 if nbytes:
                     dist.send(_as_tensor(ptr, nbytes, self.tdev), 0)
-                ctx.set_stream_start(f, 0, total_records)
+                ctx.set_stream_start(f, 0, 0 if self.gathered else total_records)  # (gathered modes: this rank's empty report is not used)
                 ctx.feed(f, b"", last=True)
             return None, total_records
         # the read-name format and colour space come from the file's first record, which rank 0 holds
@@ -625,10 +629,31 @@ class ShardedFastqInfo:
         return recv_meta, recv_blob, ms, bs
 
     # ------------------------------------------------------------------ one job
+    def _run_gathered(self, ptr, nbytes, name, ptr2, nbytes2, name2, empty_ok, no_enc_ok):
+        """MODE_INTERLEAVED / MODE_SORTED_PAIR: the ranges travel to rank 0 (the path a tiny input takes in the other modes), whose
+        engine sees the whole stream; the other ranks feed nothing."""
+        ctx, r = self.ctx, self.rank
+        ctx.reset()
+        self._keep = []
+        two = self.mode == api.MODE_SORTED_PAIR
+        self._feed_file(0, ptr, nbytes, gather0=True)
+        if two:
+            self._feed_file(1, ptr2, nbytes2, gather0=True)
+        rep = ctx.finish()
+        tr = ctx.render(rep, name, name2 if two else None, empty_ok=empty_ok, no_enc_ok=no_enc_ok) if r == 0 else None
+        mine = (int(rep.error.event_key) if rep.error.code != 0 else KEY_NONE, int(rep.file[0].n_records), int(rep.file[1].n_records), tr)
+        got = self._gather(mine)[0]
+        out = {"report": rep if r == 0 else None, "event_key": got[0], "n_records": got[1], "n_records2": got[2], "n_index_entries": 0, "n_index_left": 0}
+        if r == 0:
+            out["transcript"] = tr
+        return out
+
     def run_device(self, ptr, nbytes, name="-", ptr2=None, nbytes2=0, name2=None, empty_ok=False, no_enc_ok=False, _exact=False, _gather0=False):
         """ptr/nbytes (and ptr2/nbytes2 for MODE_INDEX_PAIR): this rank's byte range of each file in device memory (16-byte
         aligned, 64 readable bytes after it).  Returns the merged report and, on rank 0, the rendered (rc, stdout, stderr)."""
         W, r, ctx = self.world, self.rank, self.ctx
+        if self.gathered:
+            return self._run_gathered(ptr, nbytes, name, ptr2, nbytes2, name2, empty_ok, no_enc_ok)
         tm = {"t": time.perf_counter()}
 
         def lap(name):

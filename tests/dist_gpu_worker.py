@@ -76,6 +76,33 @@ def main():
             want = oracle_run(["a.fq", "b.fq"], bytes(a.cpu().numpy()), bytes(b.cpu().numpy()))
             results.append({"variant": "pair_" + variant, "argv": ["a.fq", "b.fq"], "ok": tuple(res["transcript"]) == want, "got": res["transcript"][2][-200:], "want": want[2][-200:]})
         dist.barrier()
+    # interleaved and sorted-pair files are not sharded: the ranges are gathered on rank 0 (dist.py, _run_gathered)
+    n3 = 20_480
+    g1 = torch.zeros(n3 * rb + 64, dtype=torch.uint8, device="cuda")
+    g2 = torch.zeros(n3 * rb + 64, dtype=torch.uint8, device="cuda")
+    fq.synth_illumina(g1, 0, n3, seed=44, mate=1, stream=st)
+    fq.synth_illumina(g2, 0, n3, seed=44, mate=2, perm_window=0, stream=st)
+    torch.cuda.synchronize()
+    inter = torch.stack([g1[:n3 * rb].view(n3, rb), g2[:n3 * rb].view(n3, rb)], 1).reshape(-1).contiguous()
+    jobs = [("interleaved", fq.MODE_INTERLEAVED, ["a.fq", "pe"], [inter]), ("sorted_pair", fq.MODE_SORTED_PAIR, ["-r", "-s", "a.fq", "b.fq"], [g1[:n3 * rb], g2[:n3 * rb]]),
+            ("sorted_pair_permuted", fq.MODE_SORTED_PAIR, ["-r", "-s", "a.fq", "b.fq"], [f1[:n3 * rb], f2[:n3 * rb]])]
+    for variant, mode, argv, files in jobs:
+        parts = []
+        for t in files:
+            nb = t.numel()
+            cuts = [0] + [int(nb * (i + 1) / W) + 41 * (i + 1) for i in range(W - 1)] + [nb]
+            mine = torch.zeros(cuts[r + 1] - cuts[r] + 64, dtype=torch.uint8, device="cuda")
+            mine[:cuts[r + 1] - cuts[r]] = t[cuts[r]:cuts[r + 1]]
+            parts.append((mine, cuts[r + 1] - cuts[r]))
+        torch.cuda.synchronize()
+        run = fqdist.ShardedFastqInfo(mode, device=local)
+        kw = {"ptr2": parts[1][0].data_ptr(), "nbytes2": parts[1][1], "name2": "b.fq"} if len(parts) > 1 else {}
+        res = run.run_device(parts[0][0].data_ptr(), parts[0][1], name="a.fq", **kw)
+        if r == 0:
+            from _util import oracle_run
+            want = oracle_run(argv, bytes(files[0].cpu().numpy()), bytes(files[1].cpu().numpy()) if len(files) > 1 else None)
+            results.append({"variant": variant, "argv": argv, "ok": tuple(res["transcript"]) == want, "got": res["transcript"][2][-200:], "want": want[2][-200:]})
+        dist.barrier()
     if r == 0:
         json.dump(results, open(sys.argv[1], "w"))
     dist.destroy_process_group()

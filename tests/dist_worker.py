@@ -37,9 +37,9 @@ def main():
         lo, hi = cuts[r], cuts[r + 1]
         mine = bytearray(data[lo:hi]) + bytearray(64)
         buf = (ctypes.c_uint8 * len(mine)).from_buffer(mine)
-        mode = {"single": fq.MODE_SINGLE, "index": fq.MODE_INDEX, "pair": fq.MODE_INDEX_PAIR}[c["mode"]]
+        mode = {"single": fq.MODE_SINGLE, "index": fq.MODE_INDEX, "pair": fq.MODE_INDEX_PAIR, "interleaved": fq.MODE_INTERLEAVED, "sorted": fq.MODE_SORTED_PAIR}[c["mode"]]
         kw = {}
-        if mode == fq.MODE_INDEX_PAIR:
+        if mode in (fq.MODE_INDEX_PAIR, fq.MODE_SORTED_PAIR):
             data2 = bytes.fromhex(c["hex2"])
             cuts2 = [0] + sorted(int(len(data2) * x) for x in c["cuts2"])[:W - 1] + [len(data2)]
             while len(cuts2) < W + 1:

@@ -59,6 +59,13 @@ def _cases():
                    ("edge_pair_1.fastq", "edge_pair_2_bad.fastq"), ("edge_pair_1.fastq", "edge_pair_2_trunc.fastq"), ("casava.1.8_1.fastq.gz", "casava.1.8_2.fastq.gz"),
                    ("test_solid_1.fastq.gz", "test_solid_2.fastq.gz"), ("test_e19_1.fastq.gz", "test_empty.fastq.gz"), ("test_empty.fastq.gz", "test_1.fastq.gz")]:
         cases.append(pair_case(f1, f2, sorted([rng.random(), rng.random()]), sorted([rng.random(), rng.random()])))
+    # interleaved and sorted-pair files: not sharded, the ranges are gathered on rank 0 (dist.py, _run_gathered)
+    for f in ("inter.fastq.gz", "edge_il_ok.fastq", "edge_il_odd.fastq", "edge_il_mismatch.fastq", "edge_il_bad_m2.fastq", "edge_il_trunc_m2.fastq"):
+        data = read_stream(os.path.join(GOLDEN, "inputs", f))
+        cases.append({"file": f, "mode": "interleaved", "hex": data.hex(), "cuts": sorted([rng.random(), rng.random()])})
+    for f1, f2 in [("a_1.fastq.gz", "a_2.fastq.gz"), ("edge_pair_1.fastq", "edge_pair_2_perm.fastq"), ("edge_pair_1.fastq", "edge_pair_2_short.fastq"),
+                   ("c18_10000_1.fastq.gz", "c18_10000_2.fastq.gz"), ("edge_pair_1.fastq", "edge_pair_2_bad.fastq")]:
+        cases.append(dict(pair_case(f1, f2, sorted([rng.random(), rng.random()]), sorted([rng.random(), rng.random()])), mode="sorted"))
     mates = [r.replace(" 1:N", " 2:N") for r in recs]
     mates[17] = recs[17].replace(" 1:N", " 2:N")
     rng.shuffle(mates)
@@ -89,7 +96,7 @@ VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "o
 
 
 @pytest.mark.parametrize("world,variant", [(2, "pipelined"), (3, "small_chunks"), (2, "one_exchange"), (3, "overflow"),
-                                           (3, "peer_copies"), (2, "peer_stores"), (2, "peer_overflow"), (2, "weak_hash"), (2, "peer_reuse")])
+                                           (3, "peer_copies"), (2, "peer_overflow"), (2, "weak_hash"), (2, "peer_reuse")])
 def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
     cases = _cases()
@@ -103,8 +110,8 @@ def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     got, rounds = res["transcripts"], res["rounds"]
     assert len(got) == len(cases)
     for c, g in zip(cases, got):
-        argv = (["-r"] if c["mode"] == "single" else []) + ["a.fq"] + (["b.fq"] if c["mode"] == "pair" else [])
-        want = oracle_run(argv, bytes.fromhex(c["hex"]), bytes.fromhex(c["hex2"]) if c["mode"] == "pair" else None)
+        argv = {"single": ["-r", "a.fq"], "index": ["a.fq"], "pair": ["a.fq", "b.fq"], "interleaved": ["a.fq", "pe"], "sorted": ["-r", "-s", "a.fq", "b.fq"]}[c["mode"]]
+        want = oracle_run(argv, bytes.fromhex(c["hex"]), bytes.fromhex(c["hex2"]) if c["mode"] in ("pair", "sorted") else None)
         assert tuple(g) == want, (c["file"], c["mode"], c["cuts"], g)
     if variant == "peer_reuse":
         assert res["arena_regrown"] >= 2  # the reused runner replaced its arena by a larger one (unmap, free, allocate, map again)

