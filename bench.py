@@ -126,12 +126,21 @@ def time_gz_cli(files, argv_head):
             paths.append(path)
         env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "fastq_utils_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
         t0 = time.perf_counter()
-        ours = subprocess.run([cli] + argv_head + paths, capture_output=True, env=env)
+        ours = subprocess.run([cli] + argv_head + paths, capture_output=True, env=env, timeout=300)
         t_ours = time.perf_counter() - t0
         res = {"ours_wall_s": t_ours, "ours_exit_status": ours.returncode, "gz_bytes": gz_bytes}
+        # what of that is start-up (loading CUDA, creating the context, page-locked buffers): the same command on an empty file
+        empty = os.path.join(shm, f"fqg_bench_{os.getpid()}_empty.fastq")
+        open(empty, "wb").close()
+        try:
+            t0 = time.perf_counter()
+            subprocess.run([cli, "-e", empty], capture_output=True, env=env, timeout=300)
+            res["ours_startup_wall_s"] = time.perf_counter() - t0
+        finally:
+            os.unlink(empty)
         if ref:
             t0 = time.perf_counter()
-            r = subprocess.run([ref] + argv_head + paths, capture_output=True)
+            r = subprocess.run([ref] + argv_head + paths, capture_output=True, timeout=300)
             res.update({"reference_wall_s": time.perf_counter() - t0, "reference_exit_status": r.returncode,
                         "transcripts_equal": (r.returncode, r.stdout, r.stderr) == (ours.returncode, ours.stdout, ours.stderr)})
         return res
@@ -611,11 +620,11 @@ def main():
                                    "sample": f"first {ns} {'pairs' if wl == 'illumina_pe' else 'records'} ({sb / 1e6:.0f} MB plain text) of the workload; reference is single-threaded; host nproc={os.cpu_count()}"}
         except Exception as ex:
             out["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
-        # ---------------- the command line on gzip files, host inflate included (a quarter of the CPU baseline's sample)
+        # ---------------- the command line on gzip files, host inflate included (the CPU baseline's sample, gzipped)
         if not a.no_extras and wl in ("illumina_pe", "illumina_se") and out["cpu_baseline"].get("value"):
             try:
                 from fastq_utils_b200 import synth as _synth
-                k = min(ns, 256 * 1024) * _synth.ILL_REC
+                k = ns * _synth.ILL_REC  # (the CPU baseline's sample)
                 part = [f[:k] for f in files]
                 g = time_gz_cli(part, head)
                 pb = sum(len(f) for f in part)
