@@ -490,9 +490,11 @@ class FastqInfo:
         _check(self._ctx, lib().fqg_set_file_total(self._ctx, file, total), "fqg_set_file_total")
 
     def hist_range(self, file, lo, hi):
-        out = (ctypes.c_uint64 * (hi - lo + 1))()
-        _check(self._ctx, lib().fqg_hist_range(self._ctx, file, lo, hi, out), "fqg_hist_range")
-        return list(out)
+        """records by read length lo..hi → numpy uint64 (a long-read file spans 100 000 bins: no Python list)"""
+        import numpy as np
+        out = np.zeros(hi - lo + 1, dtype=np.uint64)
+        _check(self._ctx, lib().fqg_hist_range(self._ctx, file, lo, hi, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))), "fqg_hist_range")
+        return out
 
     def index_records(self, data, cap=0):
         n = ctypes.c_uint64()

@@ -847,7 +847,7 @@ class ShardedFastqInfo:
                     med = lo + i
                     break
         elif m0.num_rds > 1 and lo <= hi < MAX_READ_LENGTH:
-            h = torch.tensor(self.ctx.hist_range(0, lo, hi), dtype=torch.int64, device=self.tdev)
+            h = torch.from_numpy(self.ctx.hist_range(0, lo, hi).astype("int64")).to(self.tdev)
             if W > 1:
                 dist.all_reduce(h)
             c = torch.cumsum(h, 0)
@@ -871,7 +871,7 @@ def _local_hist(ctx, f0, f1):
         lo, hi = min(lo, int(f1.min_rl)), max(hi, int(f1.max_rl))
     if not (lo <= hi < MAX_READ_LENGTH):
         return None
-    return (lo, [int(x) for x in ctx.hist_range(0, lo, hi)])
+    return (lo, ctx.hist_range(0, lo, hi).tolist())
 
 
 def _dbg(msg):
