@@ -847,6 +847,7 @@ void FqEngine::launch_pairs() {
   if (cfg_.mode == FQG_MODE_INTERLEAVED) {
     FqFile& F = f_[0];
     uint64_t N = eff_records(F);
+    const uint64_t gb = F.g_base; /* even: the pairs of this stream are records (2k, 2k + 1) of it, pair numbers continue at gb / 2 */
     for (size_t si = 0; si < F.segs.size(); si++) {
       const FqSegment& s = F.segs[si];
       if (s.g0 >= N) break;
@@ -856,7 +857,7 @@ void FqEngine::launch_pairs() {
       if (e0 + 1 < end) {
         FqPairArgs p; memset(&p, 0, sizeof p);
         p.a = s.names + (e0 - s.g0); p.b = p.a + 1; p.da = p.db = d; p.stride_a = p.stride_b = 2;
-        p.npairs = (uint32_t)((end - e0) / 2); p.p0 = e0 / 2; p.rank = FQ_RI_UNPAIRED; p.key = key_;
+        p.npairs = (uint32_t)((end - e0) / 2); p.p0 = (gb + e0) / 2; p.rank = FQ_RI_UNPAIRED; p.key = key_;
         dev_->pair_compare(p);
       }
       /* a pair split across two segments */
@@ -864,7 +865,7 @@ void FqEngine::launch_pairs() {
         const FqSegment& t = F.segs[si + 1];
         FqPairArgs p; memset(&p, 0, sizeof p);
         p.a = s.names + (s.nrec - 1); p.da = d; p.b = t.names; p.db = t.arena; p.stride_a = p.stride_b = 1;
-        p.npairs = 1; p.p0 = (s.g0 + s.nrec - 1) / 2; p.rank = FQ_RI_UNPAIRED; p.key = key_;
+        p.npairs = 1; p.p0 = (gb + s.g0 + s.nrec - 1) / 2; p.rank = FQ_RI_UNPAIRED; p.key = key_;
         dev_->pair_compare(p);
       }
     }
@@ -984,9 +985,10 @@ void FqEngine::finish(fqg_report* rep) {
         break;
       case FQG_MODE_INTERLEAVED:
         if (f_[0].limit >= f_[0].nrec) {
-          if ((N0 & 1) == 0) { if (t0 > 0) offer(FQ_KEY(N0 / 2, FQ_RI_TRUNC1), FQ_E_TRUNC, 0, 4 * N0, 0); }
-          else if (t0 > 0) offer(FQ_KEY(N0 / 2, FQ_RI_TRUNC2), FQ_E_TRUNC, 0, 4 * N0, 0);
-          else offer(FQ_KEY(N0 / 2, FQ_RI_NOM2), FQ_E_TRUNC_PE, 0, 4 * N0, 0);
+          const uint64_t G0 = f_[0].g_base + N0; /* records of the file in front of what is left */
+          if ((N0 & 1) == 0) { if (t0 > 0) offer(FQ_KEY(G0 / 2, FQ_RI_TRUNC1), FQ_E_TRUNC, 0, 4 * G0, 0); }
+          else if (t0 > 0) offer(FQ_KEY(G0 / 2, FQ_RI_TRUNC2), FQ_E_TRUNC, 0, 4 * G0, 0);
+          else offer(FQ_KEY(G0 / 2, FQ_RI_NOM2), FQ_E_TRUNC_PE, 0, 4 * G0, 0);
         }
         break;
       default: { /* sorted pair: the loop ends at the first file that runs out (fastq_info.c:121-141) */
@@ -1015,7 +1017,7 @@ void FqEngine::finish(fqg_report* rep) {
           }
           break;
         case FQG_MODE_INTERLEAVED:
-          if (rank == FQ_RI_STOP1) { f_[0].limit = 2 * step; restricted = true; }
+          if (rank == FQ_RI_STOP1) { f_[0].limit = 2 * step - f_[0].g_base; restricted = true; }
           break;
         default:
           if (rank == FQ_RS_STOP1) { f_[0].limit = step; f_[1].limit = std::min<uint64_t>(f_[1].limit, step); restricted = true; }
@@ -1375,8 +1377,10 @@ full_scan:
 void FqEngine::set_stream_start(int file, uint32_t skip_lines, uint64_t first_record) {
   FqFile& F = f_[file];
   if (F.started) throw std::runtime_error("fqg_set_stream_start after the first feed");
-  if (first_record && !(cfg_.mode == FQG_MODE_SINGLE || ((cfg_.mode == FQG_MODE_INDEX || cfg_.mode == FQG_MODE_INDEX_PAIR) && (cfg_.flags & FQG_FLAG_EXTERNAL_INDEX))))
-    throw std::runtime_error("fqg_set_stream_start: a record offset needs FQG_MODE_SINGLE, or an index mode with FQG_FLAG_EXTERNAL_INDEX");
+  /* (interleaved: a range starts with the first mate of a pair, so the offset is even; a pair never straddles two ranks) */
+  if (first_record && !(cfg_.mode == FQG_MODE_SINGLE || (cfg_.mode == FQG_MODE_INTERLEAVED && (first_record & 1) == 0) ||
+                        ((cfg_.mode == FQG_MODE_INDEX || cfg_.mode == FQG_MODE_INDEX_PAIR) && (cfg_.flags & FQG_FLAG_EXTERNAL_INDEX))))
+    throw std::runtime_error("fqg_set_stream_start: a record offset needs FQG_MODE_SINGLE, FQG_MODE_INTERLEAVED with an even offset, or an index mode with FQG_FLAG_EXTERNAL_INDEX");
   F.start_skip = skip_lines; F.g_base = first_record;
 }
 

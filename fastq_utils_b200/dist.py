@@ -40,15 +40,18 @@ class ShardedFastqInfo:
     def __init__(self, mode, device=0, n_hint=0, tensor_device=None):
         if mode not in (api.MODE_SINGLE, api.MODE_INDEX, api.MODE_INDEX_PAIR, api.MODE_INTERLEAVED, api.MODE_SORTED_PAIR):
             raise NotImplementedError("sharded runs support the five fastq_info modes")
-        # MODE_INTERLEAVED and MODE_SORTED_PAIR are NOT sharded: a pair must sit on one rank (interleaved: cut at even records; sorted
-        # pairs: file 2 cut by record index, not by byte offset — SURVEY.md §8e), which the byte ranges do not give.  The ranks' ranges
-        # are gathered on rank 0, whose engine runs the loop (at most 64 GiB in all); every rank gets the result.
-        self.gathered = mode in (api.MODE_INTERLEAVED, api.MODE_SORTED_PAIR)
+        # MODE_INTERLEAVED is sharded like a one-file job, with the ranges cut at PAIR boundaries (eight lines instead of four: the exact
+        # path only — the lines of a range do not say whether its first record is a first or a second mate).  MODE_SORTED_PAIR is NOT
+        # sharded: file 2 would have to be cut by record index, not by byte offset, which byte ranges do not give.  The
+        # ranks' ranges are gathered on rank 0, whose engine runs the loop (at most 64 GiB in all); every rank gets the result.
+        # FQG_GATHER_INTERLEAVED=1 takes that way for interleaved files too (A/B).
+        self.gathered = mode == api.MODE_SORTED_PAIR or (mode == api.MODE_INTERLEAVED and os.environ.get("FQG_GATHER_INTERLEAVED", "0") not in ("", "0"))
+        self.lines_per_step = 8 if mode == api.MODE_INTERLEAVED else 4  # a range starts where a loop iteration starts
         self.mode = mode
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.tdev = tensor_device if tensor_device is not None else torch.device("cuda", device)
-        indexed = mode != api.MODE_SINGLE
+        indexed = mode in (api.MODE_INDEX, api.MODE_INDEX_PAIR)
         self.ctx = api.FastqInfo(mode, device=device, flags=api.FLAG_EXTERNAL_INDEX if indexed else 0)
         self.shard = api.FastqInfo(api.MODE_INDEX, device=device, index_capacity_hint=n_hint) if indexed else None
         self._keep = []
@@ -76,6 +79,7 @@ class ShardedFastqInfo:
         self._arena, self._peer, self._arena_failed, self._p2p_ok, self._stage, self._zero = None, None, False, False, None, None
         self.rounds_done = 0  # routing rounds of the last pipelined run (tests, bench)
         self._plan, self._job, self._flagvals = None, 0, None
+        self.gathered_jobs = 0  # feeds that sent every range to rank 0 (tiny inputs, a NUL-led header line, the sorted-pair mode)
         self.exact_reruns = 0  # jobs the speculative / pipelined path handed to the exact path (tests)
         self.host_ms = {"pack": 0.0, "barrier": 0.0}  # host time inside the peer-memory rounds, accumulated
         self.phase_ms = {}  # host wall time of the phases of run_device, accumulated over jobs (bench.py reports them)
@@ -151,10 +155,13 @@ class ShardedFastqInfo:
         when the file was gathered on rank 0, records of the file over all ranks)."""
         W, r, ctx = self.world, self.rank, self.ctx
         last_rank = r == W - 1
+        M = self.lines_per_step
         if nbytes > 0:
             nlines, ends_lf, first = ctx.prescan_device(f, ptr, nbytes, at_eof=last_rank)
+            if M > 4:
+                first = self._first_line_ends(ptr, nbytes, M)
         else:
-            nlines, ends_lf, first = 0, True, [KEY_NONE] * 4
+            nlines, ends_lf, first = 0, True, [KEY_NONE] * M
         virt = 1 if (last_rank and nbytes > 0 and not ends_lf) else 0
         lfs = nlines - virt
         info = self._gather((lfs, ends_lf, first, nbytes, virt))
@@ -165,7 +172,7 @@ class ShardedFastqInfo:
         degenerate = False
         for i in range(W):
             prev_lf = True if i == 0 else info[i - 1][1]
-            skip[i] = 0 if (i == 0 or (prev_lf and G[i] % 4 == 0)) else ((4 - G[i] % 4) % 4 or 4)
+            skip[i] = 0 if (i == 0 or (prev_lf and G[i] % M == 0)) else ((M - G[i] % M) % M or M)
             if i > 0 and (info[i][0] < skip[i] or info[i][3] == 0):
                 degenerate = True  # a range without a record start of its own (tiny inputs)
                 break
@@ -174,6 +181,7 @@ class ShardedFastqInfo:
         total_lines = G[W] + info[W - 1][4]
         total_records = total_lines // 4
         if degenerate or info[0][3] == 0 or gather0:
+            self.gathered_jobs += 1  # (tests: which jobs were NOT sharded)
             if sum(info[i][3] for i in range(W)) > (64 << 30):  # (every rank sees the same sizes: the refusal is collective)
                 raise NotImplementedError("a sharded run that must be redone on one GPU, with more than 64 GiB of input")
             # tiny input: everything goes to rank 0, the other ranks hold an empty stream (the collectives below still run)
@@ -196,7 +204,7 @@ class ShardedFastqInfo:
             else:
                 if nbytes:
                     dist.send(_as_tensor(ptr, nbytes, self.tdev), 0)
-                ctx.set_stream_start(f, 0, 0 if self.gathered else total_records)  # (gathered modes: this rank's empty report is not used)
+                ctx.set_stream_start(f, 0, 0 if (self.gathered or M > 4) else total_records)  # (gathered / interleaved: this rank's empty report is not used)
                 ctx.feed(f, b"", last=True)
             return None, total_records
         # the read-name format and colour space come from the file's first record, which rank 0 holds
@@ -230,6 +238,22 @@ class ShardedFastqInfo:
                 ctx.feed(f, b"", last=True)
         expected = (lfs + virt - skip[r] + (skip[r + 1] if r < W - 1 else 0)) // 4
         return expected, total_records
+
+    def _first_line_ends(self, ptr, nbytes, k):
+        """ends (offsets behind the line feed) of the first k lines of this rank's range, KEY_NONE where the range has fewer"""
+        want, ends = 1 << 14, []
+        while True:
+            n = min(nbytes, want)
+            head = bytes(_as_tensor(ptr, n, self.tdev).cpu().numpy())
+            ends, pos = [], -1
+            while len(ends) < k:
+                pos = head.find(b"\n", pos + 1)
+                if pos < 0:
+                    break
+                ends.append(pos + 1)
+            if len(ends) == k or n == nbytes:
+                return ends + [KEY_NONE] * (k - len(ends))
+            want *= 16
 
     def _guess_phase(self, ptr, nbytes, want=1 << 14):
         """Line class (0 header, 1 sequence, 2 plus, 3 quality) of the line this range starts in, from the range's own first lines:
@@ -671,7 +695,7 @@ class ShardedFastqInfo:
         routed = self.shard is not None and self.pipeline
         self.rounds_done = 0
         # (a world of one takes the same path when it has an index shard: the single-GPU tests of the pipelined routing)
-        speculative = (not _exact) and (W > 1 or routed) and (routed or not pair)
+        speculative = (not _exact) and (W > 1 or routed) and (routed or not pair) and self.mode != api.MODE_INTERLEAVED
         files = [(0, ptr, nbytes)] + ([(1, ptr2, nbytes2)] if pair else [])
         if speculative:
             # every rank guesses the line phase of its ranges from their own first lines; rank 0, which holds the first record of each
@@ -803,7 +827,7 @@ class ShardedFastqInfo:
         merged.n_index_entries = names_total
         merged.n_index_left = left
         merged.index_mem = 8 + sum(a["mem"] for a in allr)
-        merged.reads_before_error[0], merged.reads_before_error[1] = N0, N1
+        merged.reads_before_error[0], merged.reads_before_error[1] = (N0 // 2 if self.mode == api.MODE_INTERLEAVED else N0), N1  # (loop iterations: pairs)
         if best != KEY_NONE:
             step = best >> 6
             e = merged.error

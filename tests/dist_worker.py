@@ -22,7 +22,7 @@ def main():
     cases = json.load(open(sys.argv[1]))
     dist.init_process_group("gloo")
     r, W = dist.get_rank(), dist.get_world_size()
-    out, rounds, peer, runners = [], [], [], {}
+    out, rounds, peer, gathered, runners = [], [], [], [], {}
     order = list(range(len(cases)))
     if os.environ.get("FQG_TEST_REUSE_RUNNER"):  # small jobs first, so that the reused runner's arena has to grow
         order.sort(key=lambda i: len(cases[i]["hex"]))
@@ -61,17 +61,19 @@ def main():
                 run._seen_arena = run._arena[1]
             rounds.append(run.rounds_done if not os.environ.get("FQG_TEST_SLOT_CAP") else run.exact_reruns)
             peer.append(bool(run._p2p_ok))
+            gathered.append(run.gathered_jobs)
         except (NotImplementedError, RuntimeError) as ex:
             tr = ["EXC", type(ex).__name__, str(ex)]
             rounds.append(-1)
             peer.append(False)
+            gathered.append(-1)
         if r == 0:
             out.append(list(tr))
         dist.barrier()
     if r == 0:
         back = {ci: k for k, ci in enumerate(order)}  # results in the order of the case list
-        out, rounds, peer = [[x[back[i]] for i in range(len(cases))] for x in (out, rounds, peer)]
-        json.dump({"transcripts": out, "rounds": rounds, "peer": peer, "arena_regrown": grown}, open(sys.argv[2], "w"))
+        out, rounds, peer, gathered = [[x[back[i]] for i in range(len(cases))] for x in (out, rounds, peer, gathered)]
+        json.dump({"transcripts": out, "rounds": rounds, "peer": peer, "gathered": gathered, "arena_regrown": grown}, open(sys.argv[2], "w"))
     dist.destroy_process_group()
 
 

@@ -59,10 +59,24 @@ def _cases():
                    ("edge_pair_1.fastq", "edge_pair_2_bad.fastq"), ("edge_pair_1.fastq", "edge_pair_2_trunc.fastq"), ("casava.1.8_1.fastq.gz", "casava.1.8_2.fastq.gz"),
                    ("test_solid_1.fastq.gz", "test_solid_2.fastq.gz"), ("test_e19_1.fastq.gz", "test_empty.fastq.gz"), ("test_empty.fastq.gz", "test_1.fastq.gz")]:
         cases.append(pair_case(f1, f2, sorted([rng.random(), rng.random()]), sorted([rng.random(), rng.random()])))
-    # interleaved and sorted-pair files: not sharded, the ranges are gathered on rank 0 (dist.py, _run_gathered)
-    for f in ("inter.fastq.gz", "edge_il_ok.fastq", "edge_il_odd.fastq", "edge_il_mismatch.fastq", "edge_il_bad_m2.fastq", "edge_il_trunc_m2.fastq"):
+    # interleaved files: ranges cut at pair boundaries (eight lines); sorted-pair files: not sharded, gathered on rank 0 (dist.py)
+    for f in ("inter.fastq.gz", "edge_il_ok.fastq", "edge_il_odd.fastq", "edge_il_mismatch.fastq", "edge_il_bad_m2.fastq", "edge_il_trunc_m2.fastq",
+              "edge_il_bad_m1_mm.fastq", "edge_il_m2_noat.fastq", "c18_10000_1.fastq.gz"):
         data = read_stream(os.path.join(GOLDEN, "inputs", f))
         cases.append({"file": f, "mode": "interleaved", "hex": data.hex(), "cuts": sorted([rng.random(), rng.random()])})
+    il = []
+    for i in range(3000):
+        for m in (1, 2):
+            il.append(f"@M0:1:FC:1:11:{i}:{i * 7} {m}:N:0:AC\n{'ACGTN' * (3 + i % 5)}\n+\n{'F' * (5 * (3 + i % 5))}\n")
+    mism = list(il); mism[4001] = mism[4001].replace(":2000:", ":2001:", 1)
+    badm2 = list(il); badm2[5001] = badm2[5001].replace("ACGTN", "AC*TN", 1)
+    badm1 = list(il); badm1[1000] = badm1[1000].replace("ACGTN", "AC*TN", 1); badm1[301] = badm1[301].replace(":150:", ":151:", 1)
+    nulm1 = list(il); nulm1[3000] = "\x00" + nulm1[3000]; nulm1[5000] = nulm1[5000].replace("ACGTN", "AC*TN", 1)
+    nulm2 = list(il); nulm2[3001] = "\x00" + nulm2[3001]
+    for nm, rr in (("il_clean", il), ("il_odd", il[:-1]), ("il_mismatch", mism), ("il_bad_m2", badm2), ("il_bad_m1_after_mismatch", badm1), ("il_nul_m1", nulm1),
+                   ("il_nul_m2", nulm2), ("il_cut_tail", ["".join(il)[:-30]])):
+        for cuts in ([0.31, 0.64], [0.5003, 0.5004]):
+            cases.append({"file": nm, "mode": "interleaved", "hex": "".join(rr).encode("latin-1").hex(), "cuts": cuts})
     for f1, f2 in [("a_1.fastq.gz", "a_2.fastq.gz"), ("edge_pair_1.fastq", "edge_pair_2_perm.fastq"), ("edge_pair_1.fastq", "edge_pair_2_short.fastq"),
                    ("c18_10000_1.fastq.gz", "c18_10000_2.fastq.gz"), ("edge_pair_1.fastq", "edge_pair_2_bad.fastq")]:
         cases.append(dict(pair_case(f1, f2, sorted([rng.random(), rng.random()]), sorted([rng.random(), rng.random()])), mode="sorted"))
@@ -113,6 +127,12 @@ def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
         argv = {"single": ["-r", "a.fq"], "index": ["a.fq"], "pair": ["a.fq", "b.fq"], "interleaved": ["a.fq", "pe"], "sorted": ["-r", "-s", "a.fq", "b.fq"]}[c["mode"]]
         want = oracle_run(argv, bytes.fromhex(c["hex"]), bytes.fromhex(c["hex2"]) if c["mode"] in ("pair", "sorted") else None)
         assert tuple(g) == want, (c["file"], c["mode"], c["cuts"], g)
+    # interleaved files were sharded (ranges cut at pair boundaries), sorted pairs gathered on rank 0
+    if not os.environ.get("FQG_TEST_REUSE_RUNNER") and variant != "peer_reuse":
+        gath = {(c["file"], c["mode"], tuple(c["cuts"])): g for c, g in zip(cases, res["gathered"])}
+        assert gath[("il_clean", "interleaved", (0.31, 0.64))] == 0 and gath[("il_mismatch", "interleaved", (0.31, 0.64))] == 0
+        assert gath[("il_nul_m1", "interleaved", (0.31, 0.64))] == 1  # (a NUL-led header line: redone on rank 0)
+        assert all(g >= 1 for c, g in zip(cases, res["gathered"]) if c["mode"] == "sorted")
     if variant == "peer_reuse":
         assert res["arena_regrown"] >= 2  # the reused runner replaced its arena by a larger one (unmap, free, allocate, map again)
     # the routing under test was really taken: the clean big file goes through the chunk hook, in several rounds when chunks are small
