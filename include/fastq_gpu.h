@@ -189,7 +189,9 @@ void fqg_buffer_free(void* p);
 int fqg_prescan_device(fqg_ctx* ctx, int file, const void* device_bytes, size_t n, int at_eof,
                        uint64_t* n_lines, int32_t* ends_with_lf, uint64_t first_line_ends[4]);
 /* the first record of this context's stream starts after `skip_lines` lines of the first fed buffer and is record
- * number `first_record` of the whole file (event keys, line numbers and name indices become global) */
+ * number `first_record` of the whole file (event keys, line numbers and name indices become global).  A record offset is taken in
+ * FQG_MODE_SINGLE, in the index modes with FQG_FLAG_EXTERNAL_INDEX, and — even offsets only: a range starts with the first mate of a
+ * pair — in FQG_MODE_INTERLEAVED. */
 int fqg_set_stream_start(fqg_ctx* ctx, int file, uint32_t skip_lines, uint64_t first_record);
 /* names of all records fed so far, routed by hash to `world` owners: sizes, then the packed tuples
  * (24-byte fqg_packed_name grouped by owner + the name bytes grouped by owner) into caller-provided device memory.
