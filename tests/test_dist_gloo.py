@@ -114,6 +114,8 @@ VARIANTS = {"pipelined": {}, "small_chunks": {"FQG_MAX_CHUNK_BYTES": "8192"}, "o
 def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "sim")], stdout=subprocess.DEVNULL)
     cases = _cases()
+    if variant not in ("pipelined", "small_chunks"):  # the variants of the name routing: only the jobs that route names
+        cases = [c for c in cases if c["mode"] in ("index", "pair")]
     cin, cout = tmp_path / "cases.json", tmp_path / "out.json"
     json.dump(cases, open(cin, "w"))
     port = 29600 + world + 10 * list(VARIANTS).index(variant)
@@ -128,7 +130,7 @@ def test_sharded_transcripts_match_oracle(tmp_path, world, variant):
         want = oracle_run(argv, bytes.fromhex(c["hex"]), bytes.fromhex(c["hex2"]) if c["mode"] in ("pair", "sorted") else None)
         assert tuple(g) == want, (c["file"], c["mode"], c["cuts"], g)
     # interleaved files were sharded (ranges cut at pair boundaries), sorted pairs gathered on rank 0
-    if not os.environ.get("FQG_TEST_REUSE_RUNNER") and variant != "peer_reuse":
+    if variant in ("pipelined", "small_chunks"):
         gath = {(c["file"], c["mode"], tuple(c["cuts"])): g for c, g in zip(cases, res["gathered"])}
         assert gath[("il_clean", "interleaved", (0.31, 0.64))] == 0 and gath[("il_mismatch", "interleaved", (0.31, 0.64))] == 0
         assert gath[("il_nul_m1", "interleaved", (0.31, 0.64))] == 1  # (a NUL-led header line: redone on rank 0)
