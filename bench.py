@@ -13,7 +13,8 @@ One step = one complete fastq_info job over synthetic input already resident in 
 `value` is GB/s of decompressed FASTQ over the whole job; `e2e` is the same job fed from pinned HOST memory through fqg_feed (H2D
 copy inside the timed region) with the report read back.  Before the timed region the workload's negative twins run once and every
 transcript (clean run included, at full size) is compared with the text the reference prints, known by construction: `parity`.
-At N=1 the line also carries `also`: the other single-GPU configurations, among them the 400 M-pair job streamed through one GPU.
+At N=1 the line also carries `also`: the 400 M-pair job streamed through one GPU (`illumina_pe_streamed`) and the command line on gzip
+operands against the reference binary, host inflate included (`gz_cli`).
 The reference arm times the unmodified reference binary (oracle/_ref/fastq_info, 1 thread — it has none) on a bounded sample.
 """
 import argparse

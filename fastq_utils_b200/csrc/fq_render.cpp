@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -378,7 +379,8 @@ int fastq_info_run(int argc, const char** argv_in, Source& src, int device, fqg_
   }
   fqg_report rep;
   try {
-    FqDevice* dev = fq_default_device(device);
+    std::unique_ptr<FqDevice> dev_owner(fq_default_device(device)); /* released after the engines, also when one of them throws */
+    FqDevice* dev = dev_owner.get();
     {
       FqEngine eng(cfg, dev);
       src.feed(eng, 0);
@@ -395,7 +397,6 @@ int fastq_info_run(int argc, const char** argv_in, Source& src, int device, fqg_
       }
       eng.finish(&rep);
     }
-    delete dev;
   } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
   } catch (const std::exception& ex) {
     fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
@@ -455,7 +456,8 @@ int writer_tool(bool filter_n, int argc, const char** argv_in, const void* f1, s
   if (n1 > (((size_t)1 << 31) - 64)) return FQG_ERR_USAGE; /* one chunk: the record-writing tools take streams below 2 GiB */
   fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER; cfg.flags = FQG_FLAG_KEEP_CHUNKS;
   try {
-    FqDevice* dev = fq_default_device(device);
+    std::unique_ptr<FqDevice> dev_owner(fq_default_device(device)); /* released after the engines, also when one of them throws */
+    FqDevice* dev = dev_owner.get();
     {
       FqEngine eng(cfg, dev);
       eng.feed_host(0, f1, n1, true);
@@ -486,7 +488,6 @@ int writer_tool(bool filter_n, int argc, const char** argv_in, const void* f1, s
       if (truncated && (filter_n || num_reads < 0 || (uint64_t)num_reads > nread)) { error_text(t, rep.error, fname, fname); t.rc = 1; }
       else t.rc = 0;
     }
-    delete dev;
   } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
   } catch (const std::exception& ex) {
     fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
@@ -557,7 +558,8 @@ extern "C" int fqg_filterpair_mem(int argc, const char** argv, const void* f1, s
   std::string out[3]; /* paired1, paired2, unpaired */
   fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_INDEX; cfg.flags = FQG_FLAG_PAIRED_NAMES;
   try {
-    FqDevice* dev = fq_default_device(device);
+    std::unique_ptr<FqDevice> dev_owner(fq_default_device(device)); /* released after the engines, also when one of them throws */
+    FqDevice* dev = dev_owner.get();
     {
       unsigned long index_mem = 0;
       fqg_report rep1, rep2;
@@ -655,7 +657,6 @@ extern "C" int fqg_filterpair_mem(int argc, const char** argv, const void* f1, s
         }
       }
     }
-    delete dev;
   } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
   } catch (const std::exception& ex) {
     fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
@@ -735,7 +736,8 @@ extern "C" int fqg_trim_poly_at_stream(int argc, const char** argv_in, const fqg
   std::string out;
   fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER; cfg.flags = FQG_FLAG_KEEP_CHUNKS;
   try {
-    FqDevice* dev = fq_default_device(device);
+    std::unique_ptr<FqDevice> dev_owner(fq_default_device(device)); /* released after the engines, also when one of them throws */
+    FqDevice* dev = dev_owner.get();
     {
       FqEngine eng(cfg, dev);
       eng.feed_host(0, in.data(), in.size(), true);
@@ -786,7 +788,6 @@ extern "C" int fqg_trim_poly_at_stream(int argc, const char** argv_in, const fqg
         t.rc = 0;
       }
     }
-    delete dev;
   } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
   } catch (const std::exception& ex) {
     fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
@@ -822,13 +823,13 @@ extern "C" int fqg_reader_tool_mem(int argc, const char** argv, const void* f1, 
   fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER;
   fqg_report rep;
   try {
-    FqDevice* dev = fq_default_device(device);
+    std::unique_ptr<FqDevice> dev_owner(fq_default_device(device)); /* released after the engines, also when one of them throws */
+    FqDevice* dev = dev_owner.get();
     {
       FqEngine eng(cfg, dev);
       feed_all(eng, 0, f1, n1, chunk_bytes);
       eng.finish(&rep);
     }
-    delete dev;
   } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
   } catch (const std::exception& ex) {
     fprintf(stderr, "libfastq_gpu: %s\n", ex.what());
