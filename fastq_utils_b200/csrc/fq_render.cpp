@@ -416,6 +416,55 @@ namespace {
  * fastq_write_entry2stdout (:81-86: four `%s` of the line buffers, so a line ends at its first NUL).  The records are delimited on the
  * device (FQG_MODE_READER, the stream as one chunk), fastq_filter_n's predicate is evaluated there (count_n); the host writes the
  * chosen byte ranges of the stream it was given. */
+/* The reader loop (FQG_MODE_READER) over a stream of any size, for the tools that write records.  The stream is taken in windows, each
+ * one chunk of its own that starts at a record start; a window that is not the last one ends where the data was cut, so its last record
+ * is trusted only when the engine saw all four of its lines AND the window ends behind a line feed — otherwise the next window starts at
+ * that record.  A window that does not even hold its first record grows (a record is at most two lines of 2 499 999 bytes and two of
+ * 999: a window of 6 MiB that still shows a broken first record shows a broken FILE).  visit(engine, lines of the window's records,
+ * device bytes, host bytes, number of the first record) → false: the tool has what it wants. */
+struct WindowsResult { bool truncated = false; fqg_error error; uint64_t records = 0; };
+template <class Visit>
+WindowsResult reader_windows(FqDevice* dev, int device, const char* p, size_t n, uint64_t want, Visit visit) {
+  WindowsResult R; memset(&R.error, 0, sizeof R.error);
+  if (want == 0) return R;
+  const size_t CAP = ((size_t)1 << 31) - 64, MAXREC = 6u << 20;
+  size_t window = (size_t)1 << 30;
+  if (const char* e = getenv("FQG_TOOL_WINDOW_BYTES")) { const unsigned long long v = strtoull(e, nullptr, 10); if (v >= 64) window = (size_t)std::min<unsigned long long>(v, CAP); } /* tests */
+  fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER; cfg.flags = FQG_FLAG_KEEP_CHUNKS;
+  size_t pos = 0;
+  for (;;) {
+    const size_t len = std::min(window, n - pos);
+    const bool final = pos + len == n;
+    FqEngine eng(cfg, dev);
+    eng.feed_host(0, p + pos, len, true);
+    fqg_report rep; eng.finish(&rep);
+    const bool trunc = rep.error.code == FQG_E_TRUNC; /* the loop met a record without all four lines ... */
+    uint64_t nrec = trunc ? rep.reads_before_error[0] : rep.file[0].n_records; /* ... after this many entries (else: all that fastq_read_entry delivered) */
+    const bool cut_line = !final && len > 0 && p[pos + len - 1] != '\n';
+    if (!final && !trunc && cut_line && nrec > 0) nrec--; /* its fourth line is where the window was cut */
+    if (!final && nrec == 0 && (trunc || cut_line)) {
+      if (len < MAXREC && window < CAP) { window = std::min(CAP, window * 2); continue; } /* the first record does not fit: a larger window */
+      R.truncated = true; R.error = rep.error; R.error.line = 4 * R.records; /* (a broken record in the middle of the file) */
+      return R;
+    }
+    const uint64_t take = std::min<uint64_t>(nrec, want - R.records);
+    std::vector<FqLine> L; const uint8_t* ddata = nullptr;
+    eng.record_table(take, &L, &ddata);
+    const bool more = visit(eng, L, ddata, p + pos, R.records);
+    R.records += take;
+    if (!more || R.records >= want) return R; /* (the broken record, if there is one, was not reached) */
+    if (final) {
+      if (trunc) { R.truncated = true; R.error = rep.error; R.error.line = 4 * R.records; } /* fd->cline before the increment, src/fastq.c:254 */
+      return R;
+    }
+    const size_t consumed = nrec ? (size_t)L[4 * nrec - 1].off + L[4 * nrec - 1].len : 0; /* (take == nrec here) */
+    if (!trunc && !cut_line) {
+      if (consumed < len) return R; /* a NUL-led header line ended the file quietly (src/fastq.c:248) */
+      pos += len;
+    } else pos += consumed;
+  }
+}
+
 int writer_tool(bool filter_n, int argc, const char** argv_in, const void* f1, size_t n1, int device, fqg_transcript* tr) {
   const size_t UNOPENABLE = (size_t)-1;
   Text t;
@@ -453,39 +502,32 @@ int writer_tool(bool filter_n, int argc, const char** argv_in, const void* f1, s
   }
   if (n1 == UNOPENABLE) { ERR_BEGIN(t); t.e("Unable to open %s", fname); ERR_END(t); t.rc = 1; to_transcript(t, tr); return 0; }
   if (!f1 && n1) return FQG_ERR_USAGE;
-  if (n1 > (((size_t)1 << 31) - 64)) return FQG_ERR_USAGE; /* one chunk: the record-writing tools take streams below 2 GiB */
-  fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER; cfg.flags = FQG_FLAG_KEEP_CHUNKS;
   try {
     std::unique_ptr<FqDevice> dev_owner(fq_default_device(device)); /* released after the engines, also when one of them throws */
     FqDevice* dev = dev_owner.get();
     {
-      FqEngine eng(cfg, dev);
-      eng.feed_host(0, f1, n1, true);
-      fqg_report rep; eng.finish(&rep);
-      const bool truncated = rep.error.code == FQG_E_TRUNC;      /* the loop met a record without all four lines ... */
-      const uint64_t nread = truncated ? rep.reads_before_error[0] : rep.file[0].n_records; /* ... after this many entries (else: all that fastq_read_entry delivered) */
-      const uint64_t want = filter_n ? nread : (num_reads < 0 ? nread : std::min<uint64_t>(nread, (uint64_t)num_reads));
-      std::vector<FqLine> L; const uint8_t* ddata = nullptr;
-      eng.record_table(want, &L, &ddata);
-      std::vector<uint32_t> nn;
-      if (filter_n && !L.empty()) {
-        std::vector<FqLine> seq(L.size() / 4);
-        for (size_t r = 0; r < seq.size(); r++) seq[r] = L[4 * r + 1];
-        eng.count_n(ddata, seq, &nn);
-      }
-      const char* bytes = (const char*)f1;
-      for (size_t r = 0; r < L.size() / 4; r++) {
-        if (filter_n) {
-          const unsigned long read_len = nn[2 * r + 1];
-          const unsigned max_num_n = (unsigned)(read_len * max_n / 100);
-          const bool keep = nn[2 * r] <= max_num_n;
-          if (keep) for (int i = 0; i < 4; i++) { const FqLine& l = L[4 * r + i]; t.out.append(bytes + l.off, strnlen(bytes + l.off, l.len)); }
-          const unsigned long cline = 4ul * (unsigned long)(r + 1);
-          if (cline % 100000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", cline);
-        } else for (int i = 0; i < 4; i++) { const FqLine& l = L[4 * r + i]; t.out.append(bytes + l.off, strnlen(bytes + l.off, l.len)); }
-      }
+      const uint64_t want = (filter_n || num_reads < 0) ? ~0ull : (uint64_t)num_reads;
+      WindowsResult W = reader_windows(dev, device, (const char*)f1, n1, want, [&](FqEngine& eng, const std::vector<FqLine>& L, const uint8_t* ddata, const char* bytes, uint64_t g0) {
+        std::vector<uint32_t> nn;
+        if (filter_n && !L.empty()) {
+          std::vector<FqLine> seq(L.size() / 4);
+          for (size_t r = 0; r < seq.size(); r++) seq[r] = L[4 * r + 1];
+          eng.count_n(ddata, seq, &nn);
+        }
+        for (size_t r = 0; r < L.size() / 4; r++) {
+          if (filter_n) {
+            const unsigned long read_len = nn[2 * r + 1];
+            const unsigned max_num_n = (unsigned)(read_len * max_n / 100);
+            const bool keep = nn[2 * r] <= max_num_n;
+            if (keep) for (int i = 0; i < 4; i++) { const FqLine& l = L[4 * r + i]; t.out.append(bytes + l.off, strnlen(bytes + l.off, l.len)); }
+            const unsigned long cline = 4ul * (unsigned long)(g0 + r + 1);
+            if (cline % 100000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", cline);
+          } else for (int i = 0; i < 4; i++) { const FqLine& l = L[4 * r + i]; t.out.append(bytes + l.off, strnlen(bytes + l.off, l.len)); }
+        }
+        return true;
+      });
       /* the loop met the broken record only if it went on reading that far (src/fastq_truncate.c:47-49) */
-      if (truncated && (filter_n || num_reads < 0 || (uint64_t)num_reads > nread)) { error_text(t, rep.error, fname, fname); t.rc = 1; }
+      if (W.truncated) { error_text(t, W.error, fname, fname); t.rc = 1; }
       else t.rc = 0;
     }
   } catch (const std::bad_alloc&) { return FQG_ERR_OOM;
@@ -731,58 +773,52 @@ extern "C" int fqg_trim_poly_at_stream(int argc, const char** argv_in, const fqg
     if (io->close) io->close(io->user, h);
     if (r < 0) return FQG_ERR_USAGE;
   }
-  if (in.size() > (((size_t)1 << 31) - 64)) return FQG_ERR_USAGE; /* one chunk: the record-writing tools take streams below 2 GiB */
   *outfile_name = ofile; /* from here on the reference has created the file */
   std::string out;
-  fqg_config cfg; memset(&cfg, 0, sizeof cfg); cfg.device = device; cfg.mode = FQG_MODE_READER; cfg.flags = FQG_FLAG_KEEP_CHUNKS;
   try {
     std::unique_ptr<FqDevice> dev_owner(fq_default_device(device)); /* released after the engines, also when one of them throws */
     FqDevice* dev = dev_owner.get();
     {
-      FqEngine eng(cfg, dev);
-      eng.feed_host(0, in.data(), in.size(), true);
-      fqg_report rep; eng.finish(&rep);
-      const bool truncated = rep.error.code == FQG_E_TRUNC;
-      const uint64_t nread = truncated ? rep.reads_before_error[0] : rep.file[0].n_records;
-      std::vector<FqLine> L; const uint8_t* ddata = nullptr;
-      eng.record_table(nread, &L, &ddata);
-      std::vector<FqLine> seq(L.size() / 4);
-      uint32_t longest = 0;
-      for (size_t r = 0; r < seq.size(); r++) { seq[r] = L[4 * r + 1]; longest = std::max(longest, std::max(L[4 * r + 1].len, L[4 * r + 3].len)); }
-      std::vector<uint32_t> pa;
-      eng.poly_at(ddata, seq, &pa);
-      std::vector<char> sbuf((size_t)longest + 4, 0), qbuf((size_t)longest + 4, 0); /* the entry's seq and qual buffers: they outlive a record */
-      const char* bytes = in.data();
+      std::vector<char> sbuf(4, 0), qbuf(4, 0); /* the entry's seq and qual buffers: they outlive a record (and a window) */
       unsigned long trimmed = 0, discarded = 0, processed = 0;
-      for (size_t r = 0; r < seq.size(); r++) {
-        const FqLine &lh = L[4 * r], &ls = L[4 * r + 1], &lp = L[4 * r + 2], &lq = L[4 * r + 3];
-        memcpy(sbuf.data(), bytes + ls.off, ls.len); sbuf[ls.len] = 0; /* gzgets: the line's bytes and a NUL behind them */
-        memcpy(qbuf.data(), bytes + lq.off, lq.len); qbuf[lq.len] = 0;
-        ++processed;
-        unsigned long read_len = pa[3 * r];
-        const long tail = pa[3 * r + 1], head = pa[3 * r + 2];
-        if (min_poly > 0) {
-          if (tail >= min_poly) { /* the 3' end (:79-96) */
-            const long x = (long)read_len - 2 - tail;
-            read_len -= (unsigned long)tail;
-            sbuf[x + 1] = '\n'; sbuf[x + 2] = 0; qbuf[x + 1] = '\n'; qbuf[x + 2] = 0;
-            ++trimmed;
-          } else if (head >= min_poly) { /* the 5' end (:99-113) */
-            for (long x = 0; x <= (long)read_len - head; ++x) { sbuf[x] = sbuf[x + head]; qbuf[x] = qbuf[x + head]; }
-            read_len -= (unsigned long)head;
-            ++trimmed;
+      WindowsResult W = reader_windows(dev, device, in.data(), in.size(), ~0ull, [&](FqEngine& eng, const std::vector<FqLine>& L, const uint8_t* ddata, const char* bytes, uint64_t g0) {
+        std::vector<FqLine> seq(L.size() / 4);
+        uint32_t longest = 0;
+        for (size_t r = 0; r < seq.size(); r++) { seq[r] = L[4 * r + 1]; longest = std::max(longest, std::max(L[4 * r + 1].len, L[4 * r + 3].len)); }
+        std::vector<uint32_t> pa;
+        eng.poly_at(ddata, seq, &pa);
+        if (sbuf.size() < (size_t)longest + 4) { sbuf.resize((size_t)longest + 4, 0); qbuf.resize((size_t)longest + 4, 0); }
+        for (size_t r = 0; r < seq.size(); r++) {
+          const FqLine &lh = L[4 * r], &ls = L[4 * r + 1], &lp = L[4 * r + 2], &lq = L[4 * r + 3];
+          memcpy(sbuf.data(), bytes + ls.off, ls.len); sbuf[ls.len] = 0; /* gzgets: the line's bytes and a NUL behind them */
+          memcpy(qbuf.data(), bytes + lq.off, lq.len); qbuf[lq.len] = 0;
+          ++processed;
+          unsigned long read_len = pa[3 * r];
+          const long tail = pa[3 * r + 1], head = pa[3 * r + 2];
+          if (min_poly > 0) {
+            if (tail >= min_poly) { /* the 3' end (:79-96) */
+              const long x = (long)read_len - 2 - tail;
+              read_len -= (unsigned long)tail;
+              sbuf[x + 1] = '\n'; sbuf[x + 2] = 0; qbuf[x + 1] = '\n'; qbuf[x + 2] = 0;
+              ++trimmed;
+            } else if (head >= min_poly) { /* the 5' end (:99-113) */
+              for (long x = 0; x <= (long)read_len - head; ++x) { sbuf[x] = sbuf[x + head]; qbuf[x] = qbuf[x + head]; }
+              read_len -= (unsigned long)head;
+              ++trimmed;
+            }
           }
+          if (read_len >= (unsigned long)min_len) {
+            out.append(bytes + lh.off, strnlen(bytes + lh.off, lh.len));
+            out.append(sbuf.data(), strlen(sbuf.data()));
+            out.append(bytes + lp.off, strnlen(bytes + lp.off, lp.len));
+            out.append(qbuf.data(), strlen(qbuf.data()));
+          } else ++discarded;
+          const unsigned long c = (unsigned long)(g0 + r + 1);
+          if (c % 100000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", c);
         }
-        if (read_len >= (unsigned long)min_len) {
-          out.append(bytes + lh.off, strnlen(bytes + lh.off, lh.len));
-          out.append(sbuf.data(), strlen(sbuf.data()));
-          out.append(bytes + lp.off, strnlen(bytes + lp.off, lp.len));
-          out.append(qbuf.data(), strlen(qbuf.data()));
-        } else ++discarded;
-        const unsigned long c = (unsigned long)(r + 1);
-        if (c % 100000 == 0) t.e("\b\b\b\b\b\b\b\b\b\b\b\b\b\b\b%lu", c);
-      }
-      if (truncated) { error_text(t, rep.error, file, file); t.rc = 1; }
+        return true;
+      });
+      if (W.truncated) { error_text(t, W.error, file, file); t.rc = 1; }
       else {
         t.e("INFO:Reads processed: %ld\n", (long)processed); t.e("INFO:Reads trimmed: %ld\n", (long)trimmed); t.e("INFO:Reads discarded: %ld\n", (long)discarded);
         t.rc = 0;

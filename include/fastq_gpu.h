@@ -175,7 +175,7 @@ int fqg_filterpair_mem(int argc, const char** argv, const void* f1, size_t n1, c
 
 /* fastq_trim_poly_at (src/fastq_trim_poly_at.c:121-233): argv as the reference receives it (--file, --outfile,
  * --min_poly_at_len, --min_len, --help, parsed by the C library's getopt_long like the reference does).  The library opens --file
- * through `io` (streams below 2 GiB), delimits the records and scans their poly-A / poly-T ends on the device, and returns what the
+ * through `io` (any size: the stream is taken in windows that start at record starts), delimits the records and scans their poly-A / poly-T ends on the device, and returns what the
  * reference would gzip into --outfile, inflated, in *outfile (release with fqg_buffer_free); *outfile_name is the argv word naming that
  * file, NULL when the run ended before the reference creates it (usage errors, --help, an input that cannot be opened).  After a
  * "file truncated" error (exit status 1) the reference leaves an unfinished gzip file behind: *outfile then holds the records written so far. */

@@ -72,6 +72,13 @@ def test_sim_trim_matches_reference(idx):
     _check(CASES[idx], _run(CASES[idx], "sim"))
 
 
+@pytest.mark.parametrize("idx", [i for i, c in enumerate(CASES) if "trim_inputs/" in " ".join(c["argv"]) and "poly_100k" not in " ".join(c["argv"])][::2])
+def test_sim_trim_in_small_windows(idx, monkeypatch):
+    """the stream in windows of 256 bytes: the line buffers' history (poly_shortqual.fq) must survive the window boundaries"""
+    monkeypatch.setenv("FQG_TOOL_WINDOW_BYTES", "256")
+    _check(CASES[idx], _run(CASES[idx], "sim"))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("idx", range(0, len(CASES), 3))
 def test_gpu_trim_matches_reference(idx):

@@ -41,6 +41,15 @@ def test_sim_writer_tool_matches_reference(idx):
     _check(CASES[idx], _run(CASES[idx], "sim"))
 
 
+@pytest.mark.parametrize("window", [300, 4096])
+@pytest.mark.parametrize("idx", range(0, len(CASES), 37))
+def test_sim_writer_tool_in_small_windows(idx, window, monkeypatch):
+    """streams above the size of a chunk are taken in windows that start at record starts (FQG_TOOL_WINDOW_BYTES shrinks them): a
+    record cut by a window, a window without a whole record, a broken record in the middle of the stream"""
+    monkeypatch.setenv("FQG_TOOL_WINDOW_BYTES", str(window))
+    _check(CASES[idx], _run(CASES[idx], "sim"))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("idx", range(0, len(CASES), 2))
 def test_gpu_writer_tool_matches_reference(idx):
