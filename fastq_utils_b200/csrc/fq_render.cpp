@@ -414,7 +414,7 @@ namespace {
 /* main() of the reader tools that WRITE records: src/fastq_truncate.c:32-57 (the first num_reads entries) and src/fastq_filter_n.c:33-93
  * (entries whose share of N bases is within -n percent).  Both are the fastq_read_entry loop (src/fastq.c:245-261) followed by
  * fastq_write_entry2stdout (:81-86: four `%s` of the line buffers, so a line ends at its first NUL).  The records are delimited on the
- * device (FQG_MODE_READER, the stream as one chunk), fastq_filter_n's predicate is evaluated there (count_n); the host writes the
+ * device (FQG_MODE_READER, the stream in windows of one chunk each: reader_windows), fastq_filter_n's predicate is evaluated there (count_n); the host writes the
  * chosen byte ranges of the stream it was given. */
 /* The reader loop (FQG_MODE_READER) over a stream of any size, for the tools that write records.  The stream is taken in windows, each
  * one chunk of its own that starts at a record start; a window that is not the last one ends where the data was cut, so its last record
