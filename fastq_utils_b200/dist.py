@@ -733,7 +733,8 @@ class ShardedFastqInfo:
                 mine_bad = rep.error.code != 0 or cut_short or equal > 0 or unpaired > 0 or overflow or broken or ctx.path_counts()["two_pass_fallbacks"] > 0 or self._hook_exc is not None
                 # (the merge below needs every rank's report: it travels in the same gather)
                 sums = self._gather((bool(mine_bad), inserted, claimed, int(rep.n_index_entries), int(rep.file[1].n_records),
-                                     None if mine_bad else self._mine(rep, KEY_NONE, (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), claimed, pair, with_hist=True)))
+                                     None if mine_bad else self._mine(rep, KEY_NONE, (KEY_NONE, 0, b""), (KEY_NONE, 0, b""), claimed, pair, with_hist=True),
+                                     self._hook_exc is not None))
                 bad = any(x[0] for x in sums)
                 tot_ins, tot_cl, tot_names, tot_mates = (sum(x[k] for x in sums) for k in (1, 2, 3, 4))
                 _dbg(f"rank {r} verdict: error {rep.error.code} cut_short {cut_short} inserted {inserted} equal {equal} overflow {overflow} claimed {claimed} unpaired {unpaired} broken {broken} "
@@ -742,6 +743,8 @@ class ShardedFastqInfo:
                     bad = True  # a name was dropped on its way, a mate found nothing to claim, or names of file 1 are left over
                 if self._hook_exc is not None:
                     raise self._hook_exc
+                if any(x[6] for x in sums):  # every rank leaves together: nobody waits in a collective for the rank that failed
+                    raise RuntimeError("the chunk hook of another rank failed (its exception is raised there)")
             else:
                 bad = any(self._gather(rep.error.code != 0 or cut_short))  # every rank takes the same turn: the steps below are collective
             if not bad and self.shard is not None and not routed:
